@@ -1,0 +1,214 @@
+/*
+ * r3dgpu.h -- C ABI of libr3dgpu.so: the B200 (sm_100a) replacement of Regard3D's compute-matches
+ * hot path and the downstream bundle-adjustment solve.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the Regard3D
+ * tree, rhiestan/Regard3D @ 2822275).  The reference has no FFI of its own: the binding a
+ * maintainer adds is the C++ shim in regard3d_b200/csrc/R3DComputeMatches_b200.{h,cpp} (same
+ * class name / method set as src/R3DComputeMatches.h:30-74); see INTEGRATION.md.
+ *
+ * Conventions: plain pointers + sizes, host memory in and out, no C++/CUDA/torch types.
+ * Return value: 0 = R3D_OK, negative = error (r3d_last_error() gives the text).  There is NO CPU
+ * fallback: without a usable sm_100 device r3d_create() fails with R3D_ERR_NO_DEVICE.
+ * Threading: a context may be used from any one thread at a time (the reference calls
+ * computeMatches() on one dedicated wxThread: src/threads/R3DComputeMatchesThread.cpp:91-103).
+ */
+#ifndef R3DGPU_H
+#define R3DGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_ABI_VERSION 1
+
+typedef enum {
+  R3D_OK = 0,
+  R3D_ERR_INVALID = -1,      /* bad argument */
+  R3D_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+  R3D_ERR_NOMEM = -3,
+  R3D_ERR_IO = -4,           /* file could not be read / written */
+  R3D_ERR_UNSUPPORTED = -5,  /* e.g. descriptor range outside what the fp16 operand can hold */
+  R3D_ERR_NO_DEVICE = -6     /* no sm_100 GPU: the library never falls back to the CPU */
+} r3d_status;
+
+typedef enum { R3D_F32 = 0, R3D_U8 = 1 } r3d_dtype;
+
+/* openMVG::matching::IndMatch{i_,j_}: i_ indexes the FIRST image of the pair, j_ the second
+ * (consumer: src/threads/PreviewGeneratorThread.cpp:373-390). */
+typedef struct { uint32_t i, j; } r3d_indmatch;
+
+typedef struct r3d_ctx r3d_ctx;
+/* openMVG::matching::PairWiseMatches = std::map<Pair, IndMatches> (opaque, host memory). */
+typedef struct r3d_matches r3d_matches;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* One context drives the listed CUDA devices (one worker + stream set per device; pairs shard
+ * across them without any collective).  bench.py uses one process per GPU, i.e. n_devices = 1.
+ * Replaces: construction of R3DComputeMatches (src/threads/R3DComputeMatchesThread.cpp:91). */
+int r3d_create(const int* device_ids, int n_devices, r3d_ctx** out);
+void r3d_destroy(r3d_ctx* ctx);
+const char* r3d_last_error(const r3d_ctx* ctx); /* ctx may be NULL: last global error */
+int r3d_abi_version(void);
+
+/* ---- regions ------------------------------------------------------------------------------- */
+/* Replaces Regions_Provider::load (src/R3DComputeMatches.cpp:2040) for one view:
+ * desc = Regions::DescriptorRawData() (n x dim row-major, float32 or uint8; Regard3D's native
+ * type is Scalar_Regions<SIOPointFeature,float,144>, src/Regard3DFeatures.h:42-48),
+ * xy = feature positions (n x 2 float32, from the .feat file; may be NULL if no coordinate
+ * de-duplication / geometric filtering will be requested).  Data is copied. */
+int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_t n, uint32_t dim,
+                       int dtype, const float* xy);
+int r3d_clear_regions(r3d_ctx* ctx);
+
+/* ---- putative matching --------------------------------------------------------------------- */
+#define R3D_MATCH_DEFAULT 0u
+#define R3D_MATCH_EXACT_SCAN 1u   /* skip the tensor-core candidate pass: CUDA-core exact scan only */
+#define R3D_MATCH_NO_COORD_DEDUP 2u /* skip IndMatchDecorator (for callers without positions) */
+
+/* Replaces Matcher_Regions(fDistRatio, BRUTE_FORCE_L2)::Match(regions_provider, pairs, out)
+ * (src/R3DComputeMatches.cpp:2039, :2048; loop shape :437-488): for every pair (I,J): 2-NN of each
+ * J descriptor in I under squared L2, keep iff d1 < ratio^2 * d2, IndMatch(i in I, j in J),
+ * (i,j) de-duplication, coordinate de-duplication.  pairs = P x 2 view ids.  Pairs without
+ * matches are absent from the result, like in the reference's map. */
+int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio,
+                    uint32_t flags, r3d_matches** out);
+
+/* Replaces openMVG::matching::ArrayMatcher<float,L2>::SearchNeighbours(query, nbQuery, &idx, &dist,
+ * NN=2) -- the plug-in API Regard3D implements in src/utils/matcher_hnsw.h:133-191 -- with the
+ * database = regions of view_db (ArrayMatcher::Build, :53-68) and queries = regions of view_query.
+ * idx / dist: n_query x 2, ascending exact squared distance (float accumulate, upstream order). */
+int r3d_search_neighbours(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, int32_t* idx,
+                          float* dist);
+
+/* ---- PairWiseMatches accessors ------------------------------------------------------------- */
+uint64_t r3d_matches_num_pairs(const r3d_matches* m);
+uint64_t r3d_matches_total(const r3d_matches* m);
+/* k-th pair in std::map order (sorted by I, then J). */
+int r3d_matches_get_pair(const r3d_matches* m, uint64_t k, uint32_t* I, uint32_t* J,
+                         const r3d_indmatch** matches, uint64_t* count);
+/* Build a PairWiseMatches from CSR arrays (pair_ofs has n_pairs+1 entries). */
+int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t* pair_ofs,
+                         const r3d_indmatch* matches, r3d_matches** out);
+void r3d_free_matches(r3d_matches* m);
+/* matching::Save / matching::Load, text format (src/R3DComputeMatches.cpp:2064, :2120;
+ * SURVEY.md Appendix B.3). */
+int r3d_save_matches_txt(const r3d_matches* m, const char* path);
+int r3d_load_matches_txt(const char* path, r3d_matches** out);
+
+/* ---- geometric filtering ------------------------------------------------------------------- */
+typedef enum { R3D_MODEL_F = 0, R3D_MODEL_E = 1, R3D_MODEL_H = 2 } r3d_model;
+typedef struct { uint32_t width, height; } r3d_view_info;
+
+/* Replaces ImageCollectionGeometricFilter::Robust_model_estimation(
+ *   GeometricFilter_FMatrix_AC(precision_px = 4.0, max_iter = 2048), putative, false)
+ * + Get_geometric_matches() (src/R3DComputeMatches.cpp:2099-2115).  Uses the positions uploaded
+ * with r3d_upload_regions.  views[v] = image size of view v (sfm_data views).  Only
+ * R3D_MODEL_F is implemented in this round (E/H: R3D_ERR_UNSUPPORTED). */
+int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_iter,
+                     const r3d_matches* putative, const r3d_view_info* views, uint32_t n_views,
+                     r3d_matches** out);
+
+/* ---- bundle adjustment --------------------------------------------------------------------- */
+/* Replaces openMVG::sfm::Bundle_Adjustment_Ceres::Adjust as driven by the SfM engines' Process()
+ * (src/threads/R3DTriangulationThread.cpp:441, :512, :250).  Pinhole radial-K3 cameras
+ * (model chosen at :398, built at src/R3DProject.cpp:1177-1180). */
+typedef struct {
+  uint32_t n_cams, n_pts, n_intr;
+  uint64_t n_obs;
+  double* poses;       /* n_cams x 6: angle-axis, t ; X_cam = R X + t          (in/out) */
+  double* intrinsics;  /* n_intr x 6: f, ppx, ppy, k1, k2, k3                  (in/out) */
+  double* points;      /* n_pts x 3                                            (in/out) */
+  const uint32_t* obs_cam;   /* n_obs */
+  const uint32_t* obs_pt;    /* n_obs */
+  const uint32_t* cam_intr;  /* n_cams: intrinsic group of each camera */
+  const double* obs_xy;      /* n_obs x 2 */
+} r3d_ba_problem;
+
+typedef struct {
+  uint32_t max_iterations;   /* 500 */
+  double huber_a;            /* HuberLoss(Square(4.0)) -> 16 ; <= 0: trivial loss */
+  int refine_intrinsics;     /* Intrinsic_Parameter_Type ADJUST_ALL (1) / NONE (0), R3DTriangulationThread.cpp:429-432 */
+  double function_tolerance; /* 1e-6 */
+  double gradient_tolerance; /* 1e-10 */
+  double parameter_tolerance;/* 1e-8 */
+  double initial_radius;     /* 1e4 */
+} r3d_ba_options;
+
+typedef struct {
+  uint32_t iterations, successful_steps;
+  double initial_cost, final_cost;
+  int termination;           /* 0 max iters, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
+  double seconds_total, seconds_linear;
+} r3d_ba_summary;
+
+void r3d_ba_default_options(r3d_ba_options* o);
+int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* io, const r3d_ba_options* opt,
+                      r3d_ba_summary* summary, double* cost_trace /* max_iterations+1 or NULL */);
+/* OpenMVGHelper::calculateResiduals (src/utils/OpenMVGHelper.cpp:2572-2590): |residual| per
+ * coordinate, 2 per observation -- the BA quality metric the GUI reports. */
+int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res /* n_obs x 2 */);
+
+/* ---- file-level twin of R3DComputeMatches::computeMatches() --------------------------------- */
+typedef void (*r3d_progress_cb)(float fraction, const char* message, void* user);
+
+typedef struct {
+  float dist_ratio;               /* R3DFParams::distRatio_ (src/Regard3DFeatures.h:52-69) */
+  int compute_fundamental;        /* R3DFParams::computeFundalmentalMatrix_ */
+  int compute_essential;          /* accepted, not implemented this round */
+  int compute_homography;         /* accepted, not implemented this round */
+  int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher */
+  uint32_t descriptor_dim;        /* 144 for R3D_AKAZE_LIOP_Regions */
+} r3d_cm_params;
+
+typedef struct {
+  const char* matches_dir;        /* R3DProjectPaths::relativeMatchesPath_ : holds <img>.feat/.desc, outputs */
+  const char* const* image_basenames; /* n_views names without extension (image%06d, src/R3DProject.cpp:1042) */
+  const r3d_view_info* views;     /* image sizes (sfm_data views) */
+  uint32_t n_views;
+  const char* matches_f_filename; /* R3DProjectPaths::matchesFFilename_ ; NULL -> <matches_dir>/matches.f.txt */
+} r3d_cm_paths;
+
+typedef struct {
+  uint32_t n_views;
+  uint32_t* number_of_keypoints;  /* caller array of n_views (R3DComputeMatchesStatistics::numberOfKeypoints_) */
+  uint64_t putative_pairs, putative_matches, f_pairs, f_matches;
+  double seconds_load, seconds_match, seconds_filter;
+} r3d_cm_stats;
+
+/* Steps of R3DComputeMatches::computeMatches() after feature extraction
+ * (src/R3DComputeMatches.cpp:2035-2126): load regions, exhaustive pairs, putative matching,
+ * Save(matches.putative.txt), F filter, Save(matches.f.txt); progress fractions as the reference
+ * emits them (0.7 putative, 0.8 F). */
+int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, const r3d_cm_paths* paths,
+                        r3d_progress_cb cb, void* user, r3d_cm_stats* stats);
+
+/* ---- instrumentation ----------------------------------------------------------------------- */
+typedef struct {
+  double ms_prep;        /* upload-time operand preparation kernels */
+  double ms_candidates;  /* tcgen05 candidate kernel(s), CUDA-event time on their stream */
+  double ms_rerank;      /* exact re-rank + ratio kernel(s) */
+  double ms_fallback;    /* exact-scan kernel for uncertified queries */
+  double ms_device_total;/* first launch -> last kernel of the last r3d_match_pairs */
+  double ms_host_post;   /* host de-duplication */
+  uint64_t kernel_launches;
+  uint64_t queries, fallback_queries, third_chunk_queries;
+  uint64_t h2d_bytes, d2h_bytes;
+} r3d_match_timing;
+int r3d_get_match_timing(const r3d_ctx* ctx, r3d_match_timing* out);
+
+typedef struct {
+  double ms_solve, ms_score, ms_device_total, ms_host;
+  uint64_t kernel_launches, hypotheses, rounds;
+} r3d_filter_timing;
+int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out);
+
+/* Diagnostics: the 4 packed candidate keys per query row (n_query padded to 256 rows x 4 uint32)
+ * the tensor-core pass produced for (view_db, view_query), and the pair's error bound. */
+int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, uint32_t* keys,
+                             float* eps_abs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R3DGPU_H */

@@ -1,0 +1,288 @@
+"""ctypes wrapper of the CPU ORACLE (oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY -- importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (regard3d_b200) never imports this.
+PARITY UNPINNED: see oracle/oracle.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++ -O3 -fopenmp -ffp-contract=off)."""
+    if force or not os.path.exists(_LIB_PATH):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+_lib = None
+
+
+class IndMatch(C.Structure):
+    _fields_ = [("i", C.c_uint32), ("j", C.c_uint32)]
+
+
+indmatch_dtype = np.dtype([("i", np.uint32), ("j", np.uint32)])
+
+
+class BAProblem(C.Structure):
+    _fields_ = [
+        ("n_cams", C.c_uint32), ("n_pts", C.c_uint32), ("n_intr", C.c_uint32),
+        ("n_obs", C.c_uint64),
+        ("poses", C.c_void_p), ("intrinsics", C.c_void_p), ("points", C.c_void_p),
+        ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_intr", C.c_void_p),
+        ("obs_xy", C.c_void_p),
+    ]
+
+
+class BAOptions(C.Structure):
+    _fields_ = [
+        ("max_iterations", C.c_uint32), ("huber_a", C.c_double), ("refine_intrinsics", C.c_int),
+        ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("n_threads", C.c_int),
+    ]
+
+
+class BASummary(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_uint32), ("successful_steps", C.c_uint32),
+        ("initial_cost", C.c_double), ("final_cost", C.c_double), ("termination", C.c_int),
+        ("seconds_total", C.c_double), ("seconds_linear", C.c_double),
+    ]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_l2_f32.restype = C.c_float
+        _lib.orc_l2_u8.restype = C.c_float
+        _lib.orc_match_distance_ratio.restype = C.c_int64
+        _lib.orc_match_pairs.restype = C.c_int64
+        _lib.orc_coord_dedup.restype = C.c_int64
+        _lib.orc_acransac_F.restype = C.c_int64
+        _lib.orc_filter_pairs_F.restype = C.c_int64
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dt(desc):
+    if desc.dtype == np.float32:
+        return 0
+    if desc.dtype == np.uint8:
+        return 1
+    raise TypeError("descriptors must be float32 or uint8")
+
+
+def l2(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    if a.dtype == np.uint8:
+        return float(lib().orc_l2_u8(_p(a), _p(b), C.c_uint64(a.size)))
+    a = a.astype(np.float32, copy=False)
+    b = b.astype(np.float32, copy=False)
+    return float(lib().orc_l2_f32(_p(a), _p(b), C.c_uint64(a.size)))
+
+
+def search_neighbours(db, q, n_threads=0):
+    """ArrayMatcherBruteForce::SearchNeighbours(NN=2): returns (idx[nq,2] int32, dist[nq,2] f32) or None."""
+    db = np.ascontiguousarray(db)
+    q = np.ascontiguousarray(q)
+    nq = q.shape[0]
+    idx = np.zeros((nq, 2), np.int32)
+    dist = np.zeros((nq, 2), np.float32)
+    rc = lib().orc_search_neighbours(_p(db), C.c_uint32(db.shape[0]), _p(q), C.c_uint32(nq),
+                                     C.c_uint32(db.shape[1]), _dt(db), _p(idx), _p(dist),
+                                     C.c_int(n_threads))
+    return None if rc else (idx, dist)
+
+
+def match_distance_ratio(descI, xyI, descJ, xyJ, ratio, n_threads=0):
+    descI = np.ascontiguousarray(descI)
+    descJ = np.ascontiguousarray(descJ)
+    xyI = np.ascontiguousarray(xyI, np.float32)
+    xyJ = np.ascontiguousarray(xyJ, np.float32)
+    out = np.zeros(max(1, descJ.shape[0]), indmatch_dtype)
+    n = lib().orc_match_distance_ratio(_p(descI), _p(xyI), C.c_uint32(descI.shape[0]), _p(descJ),
+                                       _p(xyJ), C.c_uint32(descJ.shape[0]),
+                                       C.c_uint32(descI.shape[1] if descI.ndim == 2 else 0),
+                                       _dt(descI), C.c_float(ratio), _p(out), C.c_int(n_threads))
+    return out[:n].copy()
+
+
+def _ptr_array(arrs):
+    T = C.c_void_p * len(arrs)
+    return T(*[a.ctypes.data for a in arrs])
+
+
+def match_pairs(descs, xys, pairs, ratio, n_threads=0):
+    """Matcher_Regions::Match twin.  Returns (pair_ofs[P+1] uint64, matches structured array)."""
+    descs = [np.ascontiguousarray(d) for d in descs]
+    xys = [np.ascontiguousarray(x, np.float32) for x in xys]
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    P = pairs.shape[0]
+    ns = np.array([d.shape[0] for d in descs], np.uint32)
+    dim = max([d.shape[1] for d in descs if d.ndim == 2 and d.shape[0] > 0] + [0])
+    cap = int(sum(int(ns[j]) for _, j in pairs)) + 1
+    out = np.zeros(cap, indmatch_dtype)
+    ofs = np.zeros(P + 1, np.uint64)
+    dt = _dt(descs[0])
+    n = lib().orc_match_pairs(_ptr_array(descs), _ptr_array(xys), _p(ns), C.c_uint32(len(descs)),
+                              C.c_uint32(dim), dt, _p(pairs), C.c_uint64(P), C.c_float(ratio),
+                              _p(ofs), _p(out), C.c_uint64(cap), C.c_int(n_threads))
+    if n < 0:
+        raise RuntimeError("orc_match_pairs overflow")
+    return ofs, out[:n].copy()
+
+
+def coord_dedup(m, xyI, xyJ):
+    m = np.ascontiguousarray(m, indmatch_dtype).copy()
+    xyI = np.ascontiguousarray(xyI, np.float32)
+    xyJ = np.ascontiguousarray(xyJ, np.float32)
+    n = lib().orc_coord_dedup(_p(m), C.c_int64(m.shape[0]), _p(xyI), _p(xyJ))
+    return m[:n].copy()
+
+
+def seven_point(x1, x2):
+    x1 = np.ascontiguousarray(x1, np.float64)
+    x2 = np.ascontiguousarray(x2, np.float64)
+    F = np.zeros((3, 3, 3), np.float64)
+    n = lib().orc_seven_point(_p(x1), _p(x2), _p(F))
+    return F[:n].copy()
+
+
+def acransac_F(xI, xJ, wI, hI, wJ, hJ, precision_px=4.0, max_iter=2048):
+    xI = np.ascontiguousarray(xI, np.float64)
+    xJ = np.ascontiguousarray(xJ, np.float64)
+    M = xI.shape[0]
+    inl = np.zeros(max(M, 1), np.uint32)
+    F = np.zeros((3, 3), np.float64)
+    info = np.zeros(3, np.float64)
+    n = lib().orc_acransac_F(_p(xI), _p(xJ), C.c_uint32(M), C.c_uint32(wI), C.c_uint32(hI),
+                             C.c_uint32(wJ), C.c_uint32(hJ), C.c_double(precision_px),
+                             C.c_uint32(max_iter), _p(inl), _p(F), _p(info))
+    return inl[:n].copy(), F, info
+
+
+def filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, max_iter=2048,
+                   n_threads=0):
+    xys = [np.ascontiguousarray(x, np.float32) for x in xys]
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    P = pairs.shape[0]
+    widths = np.ascontiguousarray(widths, np.uint32)
+    heights = np.ascontiguousarray(heights, np.uint32)
+    put_ofs = np.ascontiguousarray(put_ofs, np.uint64)
+    put = np.ascontiguousarray(put, indmatch_dtype)
+    out = np.zeros(max(1, put.shape[0]), indmatch_dtype)
+    out_ofs = np.zeros(P + 1, np.uint64)
+    n = lib().orc_filter_pairs_F(_ptr_array(xys), _p(widths), _p(heights), C.c_uint32(len(xys)),
+                                 _p(pairs), C.c_uint64(P), _p(put_ofs), _p(put),
+                                 C.c_double(precision_px), C.c_uint32(max_iter), _p(out_ofs), _p(out),
+                                 C.c_int(n_threads))
+    return out_ofs, out[:n].copy()
+
+
+def save_feat(path, xyso):
+    xyso = np.ascontiguousarray(xyso, np.float32)
+    return lib().orc_save_feat(path.encode(), _p(xyso), C.c_uint32(xyso.shape[0]))
+
+
+def load_feat(path, cap=1 << 22):
+    buf = np.zeros((cap, 4), np.float32)
+    n = C.c_uint32(0)
+    rc = lib().orc_load_feat(path.encode(), _p(buf), C.c_uint32(cap), C.byref(n))
+    if rc:
+        raise IOError(path)
+    return buf[: n.value].copy()
+
+
+def save_desc(path, d):
+    d = np.ascontiguousarray(d, np.float32)
+    return lib().orc_save_desc_f32(path.encode(), _p(d), C.c_uint64(d.shape[0]), C.c_uint32(d.shape[1]))
+
+
+def load_desc(path, dim, cap=1 << 22):
+    buf = np.zeros((cap, dim), np.float32)
+    n = C.c_uint64(0)
+    rc = lib().orc_load_desc_f32(path.encode(), _p(buf), C.c_uint64(cap), C.c_uint32(dim), C.byref(n))
+    if rc:
+        raise IOError(path)
+    return buf[: n.value].copy()
+
+
+def save_matches_txt(path, pairs, pair_ofs, m):
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    pair_ofs = np.ascontiguousarray(pair_ofs, np.uint64)
+    m = np.ascontiguousarray(m, indmatch_dtype)
+    return lib().orc_save_matches_txt(path.encode(), _p(pairs), C.c_uint64(pairs.shape[0]),
+                                      _p(pair_ofs), _p(m))
+
+
+def _ba_struct(p):
+    s = BAProblem()
+    s.n_cams = p["poses"].shape[0]
+    s.n_pts = p["points"].shape[0]
+    s.n_intr = p["intrinsics"].shape[0]
+    s.n_obs = p["obs_xy"].shape[0]
+    for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy"):
+        setattr(s, k, p[k].ctypes.data)
+    return s
+
+
+def ba_prepare(poses, intrinsics, points, obs_cam, obs_pt, cam_intr, obs_xy):
+    return {
+        "poses": np.ascontiguousarray(poses, np.float64).copy(),
+        "intrinsics": np.ascontiguousarray(intrinsics, np.float64).copy(),
+        "points": np.ascontiguousarray(points, np.float64).copy(),
+        "obs_cam": np.ascontiguousarray(obs_cam, np.uint32),
+        "obs_pt": np.ascontiguousarray(obs_pt, np.uint32),
+        "cam_intr": np.ascontiguousarray(cam_intr, np.uint32),
+        "obs_xy": np.ascontiguousarray(obs_xy, np.float64),
+    }
+
+
+def default_ba_options(max_iterations=500, huber_a=16.0, refine_intrinsics=1, n_threads=0):
+    o = BAOptions()
+    o.max_iterations = max_iterations
+    o.huber_a = huber_a
+    o.refine_intrinsics = refine_intrinsics
+    o.function_tolerance = 1e-6
+    o.gradient_tolerance = 1e-10
+    o.parameter_tolerance = 1e-8
+    o.initial_radius = 1e4
+    o.n_threads = n_threads
+    return o
+
+
+def bundle_adjust(p, opts=None):
+    """In-place on the dict from ba_prepare().  Returns (summary dict, cost_trace)."""
+    opts = opts or default_ba_options()
+    s = _ba_struct(p)
+    summ = BASummary()
+    trace = np.full(opts.max_iterations + 1, np.nan, np.float64)
+    rc = lib().orc_bundle_adjust(C.byref(s), C.byref(opts), C.byref(summ), _p(trace))
+    if rc:
+        raise RuntimeError("orc_bundle_adjust rc=%d" % rc)
+    d = {k: getattr(summ, k) for k, _ in BASummary._fields_}
+    return d, trace[: summ.iterations + 1].copy()
+
+
+def ba_residuals(p):
+    s = _ba_struct(p)
+    res = np.zeros((p["obs_xy"].shape[0], 2), np.float64)
+    lib().orc_ba_residuals(C.byref(s), _p(res))
+    return res
+
+
+def num_threads():
+    return lib().orc_num_threads()

@@ -1,0 +1,337 @@
+"""ctypes binding of libr3dgpu.so (include/r3dgpu.h).
+
+Fails loudly: importing works anywhere (the CPU-only tests check the exported symbols), but
+`Context()` raises R3DError when no sm_100 device is present -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libr3dgpu.so")
+
+R3D_F32, R3D_U8 = 0, 1
+MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP = 0, 1, 2
+MODEL_F, MODEL_E, MODEL_H = 0, 1, 2
+
+indmatch_dtype = np.dtype([("i", np.uint32), ("j", np.uint32)])
+
+EXPORTS = [
+    "r3d_create", "r3d_destroy", "r3d_last_error", "r3d_abi_version", "r3d_upload_regions",
+    "r3d_clear_regions", "r3d_match_pairs", "r3d_search_neighbours", "r3d_matches_num_pairs",
+    "r3d_matches_total", "r3d_matches_get_pair", "r3d_matches_from_csr", "r3d_free_matches",
+    "r3d_save_matches_txt", "r3d_load_matches_txt", "r3d_filter_pairs", "r3d_ba_default_options",
+    "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
+    "r3d_get_filter_timing", "r3d_debug_candidate_keys",
+]
+
+
+class R3DError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libr3dgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class MatchTiming(C.Structure):
+    _fields_ = [("ms_prep", C.c_double), ("ms_candidates", C.c_double), ("ms_rerank", C.c_double),
+                ("ms_fallback", C.c_double), ("ms_device_total", C.c_double), ("ms_host_post", C.c_double),
+                ("kernel_launches", C.c_uint64), ("queries", C.c_uint64), ("fallback_queries", C.c_uint64),
+                ("third_chunk_queries", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class FilterTiming(C.Structure):
+    _fields_ = [("ms_solve", C.c_double), ("ms_score", C.c_double), ("ms_device_total", C.c_double),
+                ("ms_host", C.c_double), ("kernel_launches", C.c_uint64), ("hypotheses", C.c_uint64),
+                ("rounds", C.c_uint64)]
+
+
+class ViewInfo(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class BAProblem(C.Structure):
+    _fields_ = [("n_cams", C.c_uint32), ("n_pts", C.c_uint32), ("n_intr", C.c_uint32), ("n_obs", C.c_uint64),
+                ("poses", C.c_void_p), ("intrinsics", C.c_void_p), ("points", C.c_void_p),
+                ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_intr", C.c_void_p),
+                ("obs_xy", C.c_void_p)]
+
+
+class BAOptions(C.Structure):
+    _fields_ = [("max_iterations", C.c_uint32), ("huber_a", C.c_double), ("refine_intrinsics", C.c_int),
+                ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
+                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double)]
+
+
+class BASummary(C.Structure):
+    _fields_ = [("iterations", C.c_uint32), ("successful_steps", C.c_uint32), ("initial_cost", C.c_double),
+                ("final_cost", C.c_double), ("termination", C.c_int), ("seconds_total", C.c_double),
+                ("seconds_linear", C.c_double)]
+
+
+class CMParams(C.Structure):
+    _fields_ = [("dist_ratio", C.c_float), ("compute_fundamental", C.c_int), ("compute_essential", C.c_int),
+                ("compute_homography", C.c_int), ("matching_algorithm", C.c_int), ("descriptor_dim", C.c_uint32)]
+
+
+class CMPaths(C.Structure):
+    _fields_ = [("matches_dir", C.c_char_p), ("image_basenames", C.POINTER(C.c_char_p)),
+                ("views", C.POINTER(ViewInfo)), ("n_views", C.c_uint32), ("matches_f_filename", C.c_char_p)]
+
+
+class CMStats(C.Structure):
+    _fields_ = [("n_views", C.c_uint32), ("number_of_keypoints", C.POINTER(C.c_uint32)),
+                ("putative_pairs", C.c_uint64), ("putative_matches", C.c_uint64), ("f_pairs", C.c_uint64),
+                ("f_matches", C.c_uint64), ("seconds_load", C.c_double), ("seconds_match", C.c_double),
+                ("seconds_filter", C.c_double)]
+
+
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_float, C.c_char_p, C.c_void_p)
+
+_lib = None
+
+
+def lib():
+    """Load libr3dgpu.so (raises if it has not been built: `python -m regard3d_b200.build`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libr3dgpu.so is not built; run `python -m regard3d_b200.build` "
+                              "(there is no fallback implementation)")
+        L = C.CDLL(LIB_PATH)
+        L.r3d_last_error.restype = C.c_char_p
+        L.r3d_last_error.argtypes = [C.c_void_p]
+        L.r3d_matches_num_pairs.restype = C.c_uint64
+        L.r3d_matches_num_pairs.argtypes = [C.c_void_p]
+        L.r3d_matches_total.restype = C.c_uint64
+        L.r3d_matches_total.argtypes = [C.c_void_p]
+        L.r3d_free_matches.argtypes = [C.c_void_p]
+        L.r3d_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Matches:
+    """PairWiseMatches handle (openMVG::matching::PairWiseMatches)."""
+
+    def __init__(self, handle):
+        self.handle = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().r3d_free_matches(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    @property
+    def num_pairs(self):
+        return int(lib().r3d_matches_num_pairs(self.handle))
+
+    @property
+    def total(self):
+        return int(lib().r3d_matches_total(self.handle))
+
+    def pair(self, k):
+        I, J = C.c_uint32(), C.c_uint32()
+        ptr = C.c_void_p()
+        cnt = C.c_uint64()
+        rc = lib().r3d_matches_get_pair(self.handle, C.c_uint64(k), C.byref(I), C.byref(J), C.byref(ptr), C.byref(cnt))
+        if rc:
+            raise R3DError(rc, "r3d_matches_get_pair")
+        n = cnt.value
+        if n == 0:
+            return I.value, J.value, np.zeros(0, indmatch_dtype)
+        buf = (C.c_uint8 * (8 * n)).from_address(ptr.value)
+        return I.value, J.value, np.frombuffer(buf, dtype=indmatch_dtype).copy()
+
+    def to_dict(self):
+        out = {}
+        for k in range(self.num_pairs):
+            I, J, m = self.pair(k)
+            out[(I, J)] = m
+        return out
+
+    def to_csr(self, pairs):
+        """CSR over the caller's pair list (empty range for pairs absent from the map)."""
+        d = self.to_dict()
+        pairs = np.asarray(pairs, np.uint32).reshape(-1, 2)
+        ofs = np.zeros(len(pairs) + 1, np.uint64)
+        chunks = []
+        for k, (I, J) in enumerate(pairs):
+            m = d.get((int(I), int(J)))
+            n = 0 if m is None else len(m)
+            ofs[k + 1] = ofs[k] + n
+            if n:
+                chunks.append(m)
+        allm = np.concatenate(chunks) if chunks else np.zeros(0, indmatch_dtype)
+        return ofs, allm
+
+    def save_txt(self, path):
+        rc = lib().r3d_save_matches_txt(self.handle, path.encode())
+        if rc:
+            raise R3DError(rc, "r3d_save_matches_txt(%s)" % path)
+
+    @staticmethod
+    def load_txt(path):
+        h = C.c_void_p()
+        rc = lib().r3d_load_matches_txt(path.encode(), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_load_matches_txt(%s)" % path)
+        return Matches(h)
+
+    @staticmethod
+    def from_csr(pairs, ofs, m):
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        ofs = np.ascontiguousarray(ofs, np.uint64)
+        m = np.ascontiguousarray(m, indmatch_dtype)
+        h = C.c_void_p()
+        rc = lib().r3d_matches_from_csr(_p(pairs), C.c_uint64(len(pairs)), _p(ofs), _p(m), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_matches_from_csr")
+        return Matches(h)
+
+
+class Context:
+    """r3d_ctx: one per process / GPU in bench.py; device_ids selects the CUDA devices."""
+
+    def __init__(self, device_ids=(0,)):
+        self._h = C.c_void_p()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        rc = lib().r3d_create(ids, len(device_ids), C.byref(self._h))
+        if rc:
+            raise R3DError(rc, lib().r3d_last_error(None).decode())
+
+    def close(self):
+        if self._h:
+            lib().r3d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise R3DError(rc, lib().r3d_last_error(self._h).decode())
+
+    def upload_regions(self, view_id, desc, xy=None):
+        desc = np.ascontiguousarray(desc)
+        if desc.dtype == np.float32:
+            dt = R3D_F32
+        elif desc.dtype == np.uint8:
+            dt = R3D_U8
+        else:
+            raise TypeError("descriptors must be float32 or uint8")
+        n, dim = (desc.shape[0], desc.shape[1]) if desc.ndim == 2 else (0, 0)
+        xyp = None
+        if xy is not None:
+            xy = np.ascontiguousarray(xy, np.float32)
+            xyp = _p(xy)
+        self._check(lib().r3d_upload_regions(self._h, C.c_uint32(view_id), _p(desc), C.c_uint32(n), C.c_uint32(dim),
+                                             C.c_int(dt), xyp))
+
+    def clear_regions(self):
+        self._check(lib().r3d_clear_regions(self._h))
+
+    def match_pairs(self, pairs, dist_ratio, flags=MATCH_DEFAULT):
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        h = C.c_void_p()
+        self._check(lib().r3d_match_pairs(self._h, _p(pairs), C.c_uint64(len(pairs)), C.c_float(dist_ratio),
+                                          C.c_uint32(flags), C.byref(h)))
+        return Matches(h)
+
+    def search_neighbours(self, view_db, view_query, n_query):
+        idx = np.zeros((n_query, 2), np.int32)
+        dist = np.zeros((n_query, 2), np.float32)
+        self._check(lib().r3d_search_neighbours(self._h, C.c_uint32(view_db), C.c_uint32(view_query), _p(idx), _p(dist)))
+        return idx, dist
+
+    def debug_candidate_keys(self, view_db, view_query, n_query):
+        npad = (max(n_query, 1) + 255) // 256 * 256
+        keys = np.zeros((npad, 4), np.uint32)
+        eps = C.c_float()
+        self._check(lib().r3d_debug_candidate_keys(self._h, C.c_uint32(view_db), C.c_uint32(view_query), _p(keys), C.byref(eps)))
+        return keys, eps.value
+
+    def filter_pairs(self, putative, widths, heights, model=MODEL_F, precision_px=4.0, max_iter=2048):
+        n = len(widths)
+        views = (ViewInfo * n)()
+        for k in range(n):
+            views[k].width = int(widths[k])
+            views[k].height = int(heights[k])
+        h = C.c_void_p()
+        self._check(lib().r3d_filter_pairs(self._h, C.c_int(model), C.c_double(precision_px), C.c_uint32(max_iter),
+                                           putative.handle, views, C.c_uint32(n), C.byref(h)))
+        return Matches(h)
+
+    def match_timing(self):
+        t = MatchTiming()
+        self._check(lib().r3d_get_match_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in MatchTiming._fields_}
+
+    def filter_timing(self):
+        t = FilterTiming()
+        self._check(lib().r3d_get_filter_timing(self._h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in FilterTiming._fields_}
+
+    # ---- bundle adjustment ------------------------------------------------------------------
+    @staticmethod
+    def _ba_struct(p):
+        s = BAProblem()
+        s.n_cams = p["poses"].shape[0]
+        s.n_pts = p["points"].shape[0]
+        s.n_intr = p["intrinsics"].shape[0]
+        s.n_obs = p["obs_xy"].shape[0]
+        for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy"):
+            setattr(s, k, p[k].ctypes.data)
+        return s
+
+    def bundle_adjust(self, p, max_iterations=500, huber_a=16.0, refine_intrinsics=1, **tol):
+        """In place on a dict of contiguous arrays (see synth.make_ba_problem / ba_prepare)."""
+        o = BAOptions()
+        lib().r3d_ba_default_options(C.byref(o))
+        o.max_iterations = max_iterations
+        o.huber_a = huber_a
+        o.refine_intrinsics = refine_intrinsics
+        for k, v in tol.items():
+            setattr(o, k, v)
+        s = self._ba_struct(p)
+        summ = BASummary()
+        trace = np.full(max_iterations + 1, np.nan, np.float64)
+        self._check(lib().r3d_bundle_adjust(self._h, C.byref(s), C.byref(o), C.byref(summ), _p(trace)))
+        d = {k: getattr(summ, k) for k, _ in BASummary._fields_}
+        return d, trace[: summ.iterations + 1].copy()
+
+    def ba_residuals(self, p):
+        s = self._ba_struct(p)
+        res = np.zeros((p["obs_xy"].shape[0], 2), np.float64)
+        self._check(lib().r3d_ba_residuals(self._h, C.byref(s), _p(res)))
+        return res
+
+    def compute_matches(self, matches_dir, basenames, widths, heights, dist_ratio=0.6, dim=144,
+                        compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None):
+        n = len(basenames)
+        names = (C.c_char_p * n)(*[b.encode() for b in basenames])
+        views = (ViewInfo * n)()
+        for k in range(n):
+            views[k].width = int(widths[k])
+            views[k].height = int(heights[k])
+        params = CMParams(dist_ratio, int(compute_fundamental), 0, 0, matching_algorithm, dim)
+        paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None)
+        kp = (C.c_uint32 * n)()
+        stats = CMStats()
+        stats.n_views = n
+        stats.number_of_keypoints = kp
+        cb = PROGRESS_CB(progress) if progress else C.cast(None, PROGRESS_CB)
+        self._check(lib().r3d_compute_matches(self._h, C.byref(params), C.byref(paths), cb, None, C.byref(stats)))
+        d = {k: getattr(stats, k) for k, _ in CMStats._fields_ if k != "number_of_keypoints"}
+        d["number_of_keypoints"] = [int(kp[k]) for k in range(n)]
+        return d

@@ -1,0 +1,297 @@
+// context.cu -- context life-cycle, region upload and tensor-core operand preparation.
+#include "r3d_internal.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace r3d {
+
+static std::mutex g_err_mutex;
+static std::string g_last_error;
+
+void set_global_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_err_mutex);
+  g_last_error = s;
+}
+
+int fail(r3d_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->last_error = msg;
+  set_global_error(msg);
+  return code;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)p;
+  return fn;
+}
+
+static void free_view(ViewDev& v) {
+  if (v.d_desc) cudaFree(v.d_desc);
+  if (v.d_opQ) cudaFree(v.d_opQ);
+  if (v.d_opD) cudaFree(v.d_opD);
+  if (v.d_xy) cudaFree(v.d_xy);
+  if (v.d_stats) cudaFree(v.d_stats);
+  v = ViewDev();
+}
+
+static void free_worker(DeviceWorker& w) {
+  if (w.device < 0) return;
+  cudaSetDevice(w.device);
+  for (auto& kv : w.views) free_view(kv.second);
+  w.views.clear();
+  void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_matches, w.d_fb, w.d_nn, w.d_counters, w.d_tmapQ, w.d_tmapD};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (w.h_counters) cudaFreeHost(w.h_counters);
+  if (w.h_matches) cudaFreeHost(w.h_matches);
+  if (w.stream) cudaStreamDestroy(w.stream);
+  if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
+  w = DeviceWorker();
+}
+
+// Encode the two TMA descriptors of a view: 2-D fp16 [n_pad][kp], box = 64 columns x 128 rows,
+// 128-byte swizzle (the canonical K-major SWIZZLE_128B UMMA operand layout).
+static int encode_view_maps(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, uint32_t slot) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return fail(ctx, R3D_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  CUtensorMap maps[2];
+  void* bases[2] = {(void*)v.d_opQ, (void*)v.d_opD};
+  for (int m = 0; m < 2; ++m) {
+    cuuint64_t gdim[2] = {(cuuint64_t)v.kp, (cuuint64_t)v.n_pad};
+    cuuint64_t gstride[1] = {(cuuint64_t)v.kp * sizeof(__half)};
+    cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)kTileRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&maps[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, bases[m], gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, R3D_ERR_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  }
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_tmapQ + slot, &maps[0], sizeof(CUtensorMap), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_tmapD + slot, &maps[1], sizeof(CUtensorMap), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // maps[] is a stack temporary
+  return R3D_OK;
+}
+
+static int ensure_tmap_capacity(r3d_ctx* ctx, DeviceWorker& w, uint32_t need) {
+  if (need <= w.tmap_cap) return R3D_OK;
+  uint32_t cap = w.tmap_cap ? w.tmap_cap : 64;
+  while (cap < need) cap *= 2;
+  CUtensorMap *nq = nullptr, *nd = nullptr;
+  R3D_CUDA_TRY(ctx, cudaMalloc(&nq, cap * sizeof(CUtensorMap)));
+  R3D_CUDA_TRY(ctx, cudaMalloc(&nd, cap * sizeof(CUtensorMap)));
+  if (w.tmap_cap) {
+    R3D_CUDA_TRY(ctx, cudaMemcpy(nq, w.d_tmapQ, w.tmap_cap * sizeof(CUtensorMap), cudaMemcpyDeviceToDevice));
+    R3D_CUDA_TRY(ctx, cudaMemcpy(nd, w.d_tmapD, w.tmap_cap * sizeof(CUtensorMap), cudaMemcpyDeviceToDevice));
+    cudaFree(w.d_tmapQ);
+    cudaFree(w.d_tmapD);
+  }
+  w.d_tmapQ = nq;
+  w.d_tmapD = nd;
+  w.tmap_cap = cap;
+  return R3D_OK;
+}
+
+// Bring every view of a worker to the "prepared" state (fp16 operands + error constants).
+// Lazy: called by the first matching call after uploads.  One synchronisation for all views.
+int prepare_views(r3d_ctx* ctx, DeviceWorker& w) {
+  R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+  std::vector<ViewDev*> fresh;
+  for (auto& kv : w.views)
+    if (!kv.second.prepared) fresh.push_back(&kv.second);
+  if (fresh.empty()) return R3D_OK;
+  for (ViewDev* v : fresh) {
+    int rc = launch_view_stats(ctx, w, *v);
+    if (rc) return rc;
+  }
+  std::vector<float> stats(4 * fresh.size());
+  for (size_t i = 0; i < fresh.size(); ++i)
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(&stats[4 * i], fresh[i]->d_stats, 4 * sizeof(float), cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+  float max_n2 = 0.f;
+  for (size_t i = 0; i < fresh.size(); ++i) {
+    ViewDev* v = fresh[i];
+    v->max_norm = std::sqrt(stats[4 * i + 0]) * (1.f + 1e-6f);
+    v->max_hnorm = std::sqrt(stats[4 * i + 1]) * (1.f + 1e-6f);
+    v->max_dnorm = std::sqrt(stats[4 * i + 2]) * (1.f + 1e-6f);
+    v->max_abs = stats[4 * i + 3];
+    if (v->max_abs > 32000.f)
+      return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor magnitude exceeds the fp16 operand range");
+    max_n2 = std::fmax(max_n2, stats[4 * i + 0]);
+  }
+  for (auto& kv : w.views)
+    if (kv.second.prepared) max_n2 = std::fmax(max_n2, kv.second.max_norm * kv.second.max_norm);
+  // Norm split scale: ||a||^2 ~= p0*2^e0 + p1*2^(e0-11) with p0 <= 2^13 and 2^(e0-11) a normal fp16.
+  int e0 = -3;
+  if (max_n2 > 0.f) {
+    int ex;
+    std::frexp(max_n2 * 1.0001f, &ex);  // max_n2 < 2^ex
+    e0 = std::max(-3, ex - 13);
+  }
+  if (e0 > 15) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor norms exceed the fp16 operand range");
+  if (w.e0_fixed && e0 < w.e0) e0 = w.e0;  // never shrink: keeps already prepared views valid
+  const bool redo_all = w.e0_fixed && e0 != w.e0;
+  w.e0 = e0;
+  w.e0_fixed = true;
+  for (auto& kv : w.views) {
+    ViewDev& v = kv.second;
+    if (v.prepared && !redo_all) continue;
+    int rc = launch_view_prepare(ctx, w, v, e0);
+    if (rc) return rc;
+    v.prepared = true;
+    v.prepared_e0 = e0;
+  }
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+  return R3D_OK;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" {
+
+int r3d_abi_version(void) { return R3D_ABI_VERSION; }
+
+const char* r3d_last_error(const r3d_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_err_mutex);
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+int r3d_create(const int* device_ids, int n_devices, r3d_ctx** out) {
+  if (!out) return fail(nullptr, R3D_ERR_INVALID, "r3d_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, R3D_ERR_NO_DEVICE,
+                std::string("r3d_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count=0") +
+                    "); libr3dgpu has no CPU fallback");
+  std::vector<int> ids;
+  if (device_ids && n_devices > 0) ids.assign(device_ids, device_ids + n_devices);
+  else ids.push_back(0);
+  r3d_ctx* ctx = new r3d_ctx();
+  for (int id : ids) {
+    if (id < 0 || id >= count) {
+      delete ctx;
+      return fail(nullptr, R3D_ERR_INVALID, "r3d_create: bad device id " + std::to_string(id));
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, id);
+    if (prop.major != 10) {
+      delete ctx;
+      return fail(nullptr, R3D_ERR_NO_DEVICE,
+                  "r3d_create: device " + std::to_string(id) + " is sm_" + std::to_string(prop.major) +
+                      std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    }
+    DeviceWorker w;
+    w.device = id;
+    w.sm_count = prop.multiProcessorCount;
+    cudaSetDevice(id);
+    if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&w.d_counters, 16 * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMallocHost(&w.h_counters, 16 * sizeof(uint32_t)) != cudaSuccess) {
+      delete ctx;
+      return fail(nullptr, R3D_ERR_CUDA, "r3d_create: stream / counter allocation failed");
+    }
+    ctx->workers.push_back(w);
+  }
+  ctx->host_threads = (int)std::thread::hardware_concurrency();
+  if (ctx->host_threads < 1) ctx->host_threads = 1;
+  if (ctx->host_threads > 64) ctx->host_threads = 64;
+  *out = ctx;
+  return R3D_OK;
+}
+
+void r3d_destroy(r3d_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& w : ctx->workers) free_worker(w);
+  delete ctx;
+}
+
+int r3d_clear_regions(r3d_ctx* ctx) {
+  if (!ctx) return R3D_ERR_INVALID;
+  for (auto& w : ctx->workers) {
+    cudaSetDevice(w.device);
+    cudaStreamSynchronize(w.stream);
+    for (auto& kv : w.views) free_view(kv.second);
+    w.views.clear();
+    w.view_slot.clear();
+    w.e0_fixed = false;
+    w.e0 = -3;
+  }
+  return R3D_OK;
+}
+
+int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_t n, uint32_t dim, int dtype,
+                       const float* xy) {
+  if (!ctx) return R3D_ERR_INVALID;
+  if (dtype != R3D_F32 && dtype != R3D_U8) return fail(ctx, R3D_ERR_INVALID, "r3d_upload_regions: bad dtype");
+  if (n > 0 && (!desc || dim == 0)) return fail(ctx, R3D_ERR_INVALID, "r3d_upload_regions: NULL descriptors");
+  if (dim > 240) return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_upload_regions: descriptor dimension > 240");
+  for (auto& w : ctx->workers) {
+    R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+    auto it = w.views.find(view_id);
+    if (it != w.views.end()) {
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+      free_view(it->second);
+      w.views.erase(it);
+    }
+    ViewDev v;
+    v.n = n; v.dim = dim; v.dtype = (uint32_t)dtype;
+    v.n_pad = (uint32_t)pad_up((int)(n ? n : 1), kRowPad);
+    v.kp = (uint32_t)operand_cols((int)(dim ? dim : 16));
+    const size_t rb = dtype == R3D_F32 ? (size_t)dim * 4 : (size_t)dim;
+    R3D_CUDA_TRY(ctx, cudaMalloc(&v.d_desc, std::max<size_t>(rb * n, 16)));
+    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_opQ, (size_t)v.n_pad * v.kp * sizeof(__half)));
+    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_opD, (size_t)v.n_pad * v.kp * sizeof(__half)));
+    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_stats, 4 * sizeof(float)));
+    if (n) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_desc, desc, rb * n, cudaMemcpyHostToDevice, w.stream));
+    if (xy && n) {
+      R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_xy, (size_t)n * sizeof(float2)));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_xy, xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, w.stream));
+      v.h_xy.assign(xy, xy + 2 * (size_t)n);
+      v.has_xy = true;
+    }
+    ctx->match_timing.h2d_bytes += rb * n + (xy ? (size_t)n * 8 : 0);
+    uint32_t slot;
+    auto sit = w.view_slot.find(view_id);
+    if (sit == w.view_slot.end()) {
+      slot = (uint32_t)w.view_slot.size();
+      w.view_slot[view_id] = slot;
+    } else {
+      slot = sit->second;
+    }
+    int rc = ensure_tmap_capacity(ctx, w, slot + 1);
+    if (rc) return rc;
+    rc = encode_view_maps(ctx, w, v, slot);  // synchronises the stream: host buffers are consumed
+    if (rc) return rc;
+    w.views[view_id] = std::move(v);
+  }
+  return R3D_OK;
+}
+
+int r3d_get_match_timing(const r3d_ctx* ctx, r3d_match_timing* out) {
+  if (!ctx || !out) return R3D_ERR_INVALID;
+  *out = ctx->match_timing;
+  return R3D_OK;
+}
+
+int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out) {
+  if (!ctx || !out) return R3D_ERR_INVALID;
+  *out = ctx->filter_timing;
+  return R3D_OK;
+}
+
+}  // extern "C"

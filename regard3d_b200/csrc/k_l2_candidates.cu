@@ -1,0 +1,356 @@
+// k_l2_candidates.cu -- all-pairs squared-L2 candidate generation on the 5th-gen tensor cores.
+//
+// Replaces the inner loop of ArrayMatcherBruteForce<float,L2<float>>::SearchNeighbours (the a6 row
+// of SURVEY.md 8a; contract visible at src/utils/matcher_hnsw.h:133-191): for every query
+// descriptor of image J, the distances to all descriptors of image I.
+//
+// Formulation.  With the operands built by k_view_prepare,
+//     D[q, i] = opQ_J[q, :] . opD_I[i, :] = ||a_i||^2 + ||b_q||^2 - 2 a_i.b_q
+// is a plain K-major x K-major GEMM with K = pad16(dim) + 16 (the norm terms ride in one extra
+// UMMA K-step).  fp16 operands, fp32 accumulation in TMEM.
+//
+// The GEMM is only the CANDIDATE generator: the epilogue reduces every 16-column chunk of a
+// query row to its minimum (FMNMX3 tree), packs the chunk id into the 12 low mantissa bits and
+// keeps the 4 smallest packed keys per query in registers.  k_rerank then recomputes the
+// candidate chunks exactly (upstream float order) and certifies the result against the 4th key
+// (DESIGN.md "certification"); what cannot be certified goes to k_exact_scan.  Bit-exact output
+// therefore never depends on tensor-core rounding.
+//
+// CTA organisation (one persistent CTA per SM, 384 threads):
+//   warp 0   : TMA producer (one elected lane)
+//   warp 1   : tcgen05.mma issuer (one elected lane)
+//   warp 2   : TMEM allocator
+//   warp 3   : idle
+//   warps 4-11: epilogue; warp w owns TMEM lanes 32*(w%4).., query block (w-4)/4
+// A work item is (pair, 256-query super-block).  The 2x128 query rows stay resident in shared
+// memory (A operand, M = 128 each); the database image streams through a ring of 128-row x 64-col
+// TMA boxes (B operand, N = 128).  Two accumulator stages of 2 x (128 lanes x 128 fp32 columns)
+// fill the 512 TMEM columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
+#include "r3d_internal.cuh"
+
+namespace r3d {
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (4 + kEpiWarps);
+constexpr uint32_t kBoxBytes = kTileRows * kKBlock * 2;  // 16384
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCols = 128;                        // fp32 columns per (stage, query block)
+constexpr uint32_t kKeySentinel = 0x7f7fffffu;            // FLT_MAX
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+// tcgen05.wait::ld that also names the destination registers, so no use of them can be scheduled
+// above the wait by the compiler.
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (SM100 "version 1"):
+//   start address >> 4 | LBO (ignored for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) |
+//   version = 1 | layout type = SWIZZLE_128B (2)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128.
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+
+// minimum of 16 accumulator columns, packed with the chunk id, inserted into the sorted 4-key set
+__device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_id, float (&key)[4]) {
+  float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
+  m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
+  m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
+  m = fmin3(m, __uint_as_float(v[7]), __uint_as_float(v[8]));
+  m = fmin3(m, __uint_as_float(v[9]), __uint_as_float(v[10]));
+  m = fmin3(m, __uint_as_float(v[11]), __uint_as_float(v[12]));
+  m = fmin3(m, __uint_as_float(v[13]), __uint_as_float(v[14]));
+  m = fminf(m, __uint_as_float(v[15]));
+  const float x = __uint_as_float((__float_as_uint(m) & ~((1u << kChunkBits) - 1u)) | chunk_id);
+  const float t0 = fmaxf(key[0], x);
+  key[0] = fminf(key[0], x);
+  const float t1 = fmaxf(key[1], t0);
+  key[1] = fminf(key[1], t0);
+  const float t2 = fmaxf(key[2], t1);
+  key[2] = fminf(key[2], t1);
+  key[3] = fminf(key[3], t2);
+}
+
+struct SmemLayout {
+  uint32_t q_base, d_base, bars;  // byte offsets from the 1024-aligned base
+};
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
+                const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
+                uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_base = base;                                   // kQB * nkb boxes
+  const uint32_t d_base = q_base + kQB * nkb * kBoxBytes;          // n_stages boxes
+  const uint32_t bar_base = d_base + n_stages * kBoxBytes;         // 8-byte barriers
+  const uint32_t bar_full = bar_base;                              // [kMaxStages]
+  const uint32_t bar_empty = bar_base + 8 * kMaxStages;            // [kMaxStages]
+  const uint32_t bar_qfull = bar_base + 16 * kMaxStages;
+  const uint32_t bar_qempty = bar_qfull + 8;
+  const uint32_t bar_tfull = bar_qempty + 8;                       // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                      // [2]
+  const uint32_t tmem_slot = bar_tempty + 16;                      // uint32
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < kMaxStages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_qfull, 1);
+    mbar_init(bar_qempty, 1);
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, qphase = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem wi = items[it];
+        const PairDesc pd = pairs[wi.pair];
+        const CUtensorMap* mq = tmapQ + pd.slotJ;
+        const CUtensorMap* md = tmapD + pd.slotI;
+        const uint32_t nboxes = (pd.nI_pad / kTileRows) * nkb;
+        // Database boxes do not depend on the query tiles: run the ring ahead (it fills as the
+        // previous item's MMAs retire) before blocking on the query buffer.
+        const uint32_t ahead = nboxes < n_stages ? nboxes : n_stages;
+        uint32_t b = 0, t = 0, kb = 0;
+        for (;;) {
+          if (b == ahead) {
+            mbar_wait(bar_qempty, qphase ^ 1u);  // previous item's MMAs no longer read the query tiles
+            qphase ^= 1u;
+            mbar_arrive_expect_tx(bar_qfull, kQB * nkb * kBoxBytes);
+            for (uint32_t qb = 0; qb < (uint32_t)kQB; ++qb)
+              for (uint32_t k2 = 0; k2 < nkb; ++k2)
+                tma_load_2d(q_base + (qb * nkb + k2) * kBoxBytes, mq, (int)(k2 * kKBlock),
+                            (int)(wi.sb * kSuperRows + qb * kTileRows), bar_qfull);
+          }
+          if (b == nboxes) break;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, kBoxBytes);
+          tma_load_2d(d_base + stage * kBoxBytes, md, (int)(kb * kKBlock), (int)(t * kTileRows),
+                      bar_full + 8 * stage);
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+          ++b;
+          if (++kb == nkb) { kb = 0; ++t; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
+      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const WorkItem wi = items[it];
+        const PairDesc pd = pairs[wi.pair];
+        const uint32_t ntiles = pd.nI_pad / kTileRows;
+        mbar_wait(bar_qfull, qf);
+        qf ^= 1u;
+        tc_fence_after();
+        for (uint32_t t = 0; t < ntiles; ++t) {
+          mbar_wait(bar_tempty + 8 * acc, accphase ^ 1u);  // epilogue drained this accumulator stage
+          tc_fence_after();
+          for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t ks_here = (ksteps - kb * 4u) < 4u ? (ksteps - kb * 4u) : 4u;
+            for (uint32_t k = 0; k < ks_here; ++k) {
+              const uint64_t bdesc = make_smem_desc(d_base + stage * kBoxBytes + k * 32u);
+#pragma unroll
+              for (uint32_t qb = 0; qb < (uint32_t)kQB; ++qb) {
+                const uint64_t adesc = make_smem_desc(q_base + (qb * nkb + kb) * kBoxBytes + k * 32u);
+                tc_mma_f16(tmem_base + (acc * kQB + qb) * kAccCols, adesc, bdesc, kInstrDesc,
+                           (kb | k) != 0u ? 1u : 0u);
+              }
+            }
+            tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+          }
+          tc_commit(bar_tfull + 8 * acc);      // accumulator stage complete -> epilogue
+          acc ^= 1u;
+          if (acc == 0) accphase ^= 1u;
+        }
+        tc_commit(bar_qempty);                 // query tiles may be overwritten
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue =======================================
+    const uint32_t ew = warp - 4u;
+    const uint32_t qb = ew >> 2;
+    const uint32_t lane_quarter = warp & 3u;  // TMEM lanes this warp may touch
+    uint32_t acc = 0, accphase = 0;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem wi = items[it];
+      const PairDesc pd = pairs[wi.pair];
+      const uint32_t ntiles = pd.nI_pad / kTileRows;
+      float key[4];
+      key[0] = key[1] = key[2] = key[3] = __uint_as_float(kKeySentinel);
+      for (uint32_t t = 0; t < ntiles; ++t) {
+        mbar_wait(bar_tfull + 8 * acc, accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((lane_quarter * 32u) << 16) + (acc * kQB + qb) * kAccCols;
+        const uint32_t chunk0 = t * (kTileRows / kChunk);
+        uint32_t va[32], vb[32];
+        tc_ld32(taddr, va);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 32, vb);
+        chunk_update(va, chunk0 + 0, key);
+        chunk_update(va + 16, chunk0 + 1, key);
+        tc_wait_ld(vb);
+        tc_ld32(taddr + 64, va);
+        chunk_update(vb, chunk0 + 2, key);
+        chunk_update(vb + 16, chunk0 + 3, key);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 96, vb);
+        chunk_update(va, chunk0 + 4, key);
+        chunk_update(va + 16, chunk0 + 5, key);
+        tc_wait_ld(vb);
+        // all TMEM reads of this stage are done: hand it back before the last two chunks
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        chunk_update(vb, chunk0 + 6, key);
+        chunk_update(vb + 16, chunk0 + 7, key);
+        acc ^= 1u;
+        if (acc == 0) accphase ^= 1u;
+      }
+      const uint32_t row = wi.sb * kSuperRows + qb * kTileRows + lane_quarter * 32u + lane;
+      uint4 o;
+      o.x = __float_as_uint(key[0]); o.y = __float_as_uint(key[1]);
+      o.z = __float_as_uint(key[2]); o.w = __float_as_uint(key[3]);
+      ((uint4*)keys_out)[pd.q_ofs + row] = o;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+size_t l2_candidates_smem_bytes(int kp_cols) {
+  const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
+  int stages = kMaxStages;
+  if (nkb >= 4) stages = 6;
+  return 1024 + (size_t)(kQB * nkb + stages) * kBoxBytes + 8 * (2 * kMaxStages + 2 + 4) + 16;
+}
+
+int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int grid_limit) {
+  if (n_items == 0) return R3D_OK;
+  const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
+  if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
+  const int stages = nkb >= 4 ? 6 : kMaxStages;
+  const size_t smem = l2_candidates_smem_bytes(kp_cols);
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_l2_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  uint32_t grid = (uint32_t)w.sm_count;
+  if (grid_limit > 0 && (uint32_t)grid_limit < grid) grid = (uint32_t)grid_limit;
+  if (n_items < grid) grid = n_items;
+  k_l2_candidates<<<grid, kThreads, smem, w.stream>>>(w.d_tmapQ, w.d_tmapD, d_pairs, d_items, n_items, d_keys,
+                                                      (uint32_t)nkb, (uint32_t)(kp_cols / 16), (uint32_t)stages);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+}  // namespace r3d

@@ -1,0 +1,389 @@
+// match_host.cu -- host orchestration of putative matching.
+//
+// r3d_match_pairs replaces Matcher_Regions(fDistRatio, BRUTE_FORCE_L2)::Match
+// (src/R3DComputeMatches.cpp:2039, :2048; loop shape :437-488).  The reference's "serial I,
+// omp-dynamic J, critical insert" becomes: all pairs of a batch in ONE persistent tensor-core
+// launch (work item = pair x 256-query super-block), one re-rank launch, one exact-scan launch for
+// the uncertified remainder, one compacted device->host copy, host de-duplication on a thread pool.
+#include "r3d_internal.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace r3d {
+
+namespace {
+
+struct BatchPair {
+  uint64_t src_index;  // index in the caller's pair list
+  PairDesc pd;
+};
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename F>
+void parallel_for(int n_threads, size_t n, F&& f) {
+  if (n == 0) return;
+  if (n_threads <= 1 || n == 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  const int nt = (int)std::min<size_t>((size_t)n_threads, n);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+float pair_eps(const ViewDev& vi, const ViewDev& vj) {
+  const double nI = vi.max_norm, nJ = vj.max_norm;
+  double e = 2.0 * ((double)vi.max_dnorm * nJ + (double)vi.max_hnorm * (double)vj.max_dnorm);
+  e += std::ldexp(nI * nI + nJ * nJ, -21);         // two-piece fp16 split of the squared norms
+  e += std::ldexp((nI + nJ) * (nI + nJ), -18);     // fp32 accumulation inside the tensor core
+  e *= 1.001;
+  return (float)e + 1e-30f;
+}
+
+struct EventTimer {
+  cudaEvent_t ev[5];
+  bool ok = false;
+  EventTimer() {
+    ok = true;
+    for (auto& e : ev)
+      if (cudaEventCreate(&e) != cudaSuccess) ok = false;
+  }
+  ~EventTimer() {
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+};
+
+}  // namespace
+
+// Runs the device pipeline for a list of pairs on one worker.
+//  results[k]   : matches of pairs[k] (empty if none)
+//  nn_out       : optional, for r3d_search_neighbours (single pair): float4 per query
+static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs, uint64_t n_pairs, float ratio,
+                           uint32_t flags, std::vector<std::vector<r3d_indmatch>>& results,
+                           std::vector<float4>* nn_out, std::vector<uint4>* keys_dbg = nullptr) {
+  R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+  int rc = prepare_views(ctx, w);
+  if (rc) return rc;
+  results.assign(n_pairs, {});
+  const float ratio2 = ratio * ratio;  // Square(fDistRatio): b_squared_metric = true for BRUTE_FORCE_L2
+  const bool want_matches = (nn_out == nullptr);
+
+  // ---- build pair descriptors --------------------------------------------------------------
+  std::vector<BatchPair> all;
+  all.reserve(n_pairs);
+  uint32_t dim = 0;
+  int dtype = -1;
+  for (uint64_t p = 0; p < n_pairs; ++p) {
+    const uint32_t I = pairs[2 * p], J = pairs[2 * p + 1];
+    auto iI = w.views.find(I), iJ = w.views.find(J);
+    if (iI == w.views.end() || iJ == w.views.end())
+      return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: view " + std::to_string(iI == w.views.end() ? I : J) + " was not uploaded");
+    const ViewDev& vi = iI->second;
+    const ViewDev& vj = iJ->second;
+    // reference: skip when either side has no regions (R3DComputeMatches.cpp:444-447, :471-475);
+    // SearchNeighbours returns false when NN(2) > #database rows.
+    if (vi.n < 2 || vj.n == 0) continue;
+    if (vi.dim != vj.dim || vi.dtype != vj.dtype) continue;  // Type_id() mismatch -> skipped
+    if (dtype < 0) { dim = vi.dim; dtype = (int)vi.dtype; }
+    if (vi.dim != dim || (int)vi.dtype != dtype)
+      return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_match_pairs: mixed descriptor types in one call");
+    BatchPair bp;
+    bp.src_index = p;
+    PairDesc& pd = bp.pd;
+    std::memset(&pd, 0, sizeof(pd));
+    pd.I = I; pd.J = J; pd.nI = vi.n; pd.nJ = vj.n; pd.nI_pad = vi.n_pad; pd.nJ_pad = vj.n_pad;
+    pd.slotI = w.view_slot[I]; pd.slotJ = w.view_slot[J];
+    pd.descI = vi.d_desc; pd.descJ = vj.d_desc;
+    pd.use_tc = ((flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
+    pd.eps_abs = pair_eps(vi, vj);
+    all.push_back(bp);
+  }
+  if (all.empty()) return R3D_OK;
+  const int kp = operand_cols((int)dim);
+
+  EventTimer evt;
+  if (!evt.ok) return fail(ctx, R3D_ERR_CUDA, "cudaEventCreate failed");
+  r3d_match_timing& T = w.timing;
+
+  // ---- batches ---------------------------------------------------------------------------------
+  const uint64_t kMaxRowsPerBatch = 48ull << 20;  // 48 Mi query rows -> 768 MiB of keys
+  size_t b0 = 0;
+  while (b0 < all.size()) {
+    size_t b1 = b0;
+    uint64_t rows = 0, qtotal = 0, n_items = 0;
+    uint32_t max_nJ = 0;
+    while (b1 < all.size() && (b1 - b0) < 32768 && (rows + all[b1].pd.nJ_pad <= kMaxRowsPerBatch || b1 == b0)) {
+      all[b1].pd.q_ofs = (uint32_t)rows;
+      rows += all[b1].pd.nJ_pad;
+      qtotal += all[b1].pd.nJ;
+      if (all[b1].pd.use_tc) n_items += all[b1].pd.nJ_pad / kSuperRows;
+      max_nJ = std::max(max_nJ, all[b1].pd.nJ);
+      ++b1;
+    }
+    const uint32_t nb = (uint32_t)(b1 - b0);
+    std::vector<PairDesc> hp(nb);
+    for (uint32_t k = 0; k < nb; ++k) hp[k] = all[b0 + k].pd;
+    std::vector<WorkItem> hitems;
+    hitems.reserve(n_items);
+    for (uint32_t k = 0; k < nb; ++k)
+      if (hp[k].use_tc)
+        for (uint32_t sb = 0; sb < hp[k].nJ_pad / kSuperRows; ++sb) hitems.push_back(WorkItem{k, sb});
+
+    if ((rc = ensure_capacity<PairDesc>(ctx, &w.d_pairs, &w.pairs_cap, nb))) return rc;
+    if ((rc = ensure_capacity<WorkItem>(ctx, &w.d_items, &w.items_cap, std::max<size_t>(hitems.size(), 1)))) return rc;
+    if ((rc = ensure_capacity<uint4>(ctx, &w.d_keys, &w.keys_cap, rows))) return rc;
+    if ((rc = ensure_capacity<uint2>(ctx, &w.d_fb, &w.fb_cap, qtotal))) return rc;
+    if (want_matches) {
+      if ((rc = ensure_capacity<uint3>(ctx, &w.d_matches, &w.matches_cap, qtotal))) return rc;
+    } else {
+      if ((rc = ensure_capacity<float4>(ctx, &w.d_nn, &w.nn_cap, rows))) return rc;
+    }
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
+    if (!hitems.empty())
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems.data(), hitems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(w.d_counters, 0, 16 * sizeof(uint32_t), w.stream));
+    T.h2d_bytes += nb * sizeof(PairDesc) + hitems.size() * sizeof(WorkItem);
+
+    uint3* d_matches = want_matches ? (uint3*)w.d_matches : nullptr;
+    float4* d_nn = want_matches ? nullptr : (float4*)w.d_nn;
+
+    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[0], w.stream));
+    if (!hitems.empty()) {
+      if ((rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items,
+                                     (uint32_t)hitems.size(), (uint32_t*)w.d_keys, kp, 0))) return rc;
+      T.kernel_launches += 1;
+    }
+    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[1], w.stream));
+    if (keys_dbg) {
+      keys_dbg->resize(rows);
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(keys_dbg->data(), w.d_keys, rows * sizeof(uint4), cudaMemcpyDeviceToHost, w.stream));
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    }
+    if (!hitems.empty()) {
+      if ((rc = launch_rerank(ctx, w, (const PairDesc*)w.d_pairs, nb, max_nJ, (const uint32_t*)w.d_keys, dim, dtype,
+                              ratio2, w.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
+      T.kernel_launches += 1;
+    }
+    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[2], w.stream));
+    bool any_exact = false;
+    for (uint32_t k = 0; k < nb; ++k) any_exact |= (hp[k].use_tc == 0);
+    if (any_exact) {
+      if ((rc = launch_fill_all_queries(ctx, w, (const PairDesc*)w.d_pairs, nb, (uint2*)w.d_fb, &w.d_counters[1]))) return rc;
+      T.kernel_launches += 1;
+    }
+    if ((rc = launch_exact_scan(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_fb, &w.d_counters[1],
+                                (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, w.d_counters,
+                                d_matches, d_nn))) return rc;
+    T.kernel_launches += 1;
+    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[3], w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.h_counters, w.d_counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    float ms;
+    cudaEventElapsedTime(&ms, evt.ev[0], evt.ev[1]); T.ms_candidates += ms;
+    cudaEventElapsedTime(&ms, evt.ev[1], evt.ev[2]); T.ms_rerank += ms;
+    cudaEventElapsedTime(&ms, evt.ev[2], evt.ev[3]); T.ms_fallback += ms;
+    cudaEventElapsedTime(&ms, evt.ev[0], evt.ev[3]); T.ms_device_total += ms;
+    const uint32_t n_matches = w.h_counters[0];
+    T.queries += qtotal;
+    T.fallback_queries += w.h_counters[1];
+    T.third_chunk_queries += w.h_counters[2];
+    T.d2h_bytes += 16 * sizeof(uint32_t);
+
+    if (want_matches) {
+      if (n_matches) {
+        const size_t bytes = (size_t)n_matches * sizeof(uint3);
+        if (w.h_matches_cap < bytes) {
+          if (w.h_matches) cudaFreeHost(w.h_matches);
+          w.h_matches = nullptr;
+          w.h_matches_cap = 0;
+          R3D_CUDA_TRY(ctx, cudaMallocHost(&w.h_matches, bytes + bytes / 2));
+          w.h_matches_cap = bytes + bytes / 2;
+        }
+        R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.h_matches, w.d_matches, bytes, cudaMemcpyDeviceToHost, w.stream));
+        R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+        T.d2h_bytes += bytes;
+      }
+      const double t0 = now_ms();
+      // bucket by pair (counting sort), then per-pair sort + de-duplication on the thread pool
+      const uint3* hm = (const uint3*)w.h_matches;
+      std::vector<uint32_t> cnt(nb + 1, 0);
+      for (uint32_t k = 0; k < n_matches; ++k) cnt[hm[k].x + 1]++;
+      for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] += cnt[k];
+      std::vector<r3d_indmatch> bucket(n_matches);
+      {
+        std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1);
+        for (uint32_t k = 0; k < n_matches; ++k) bucket[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
+      }
+      const bool cd = (flags & R3D_MATCH_NO_COORD_DEDUP) == 0;
+      parallel_for(ctx->host_threads, nb, [&](size_t k) {
+        if (cnt[k + 1] == cnt[k]) return;
+        std::vector<r3d_indmatch> v(bucket.begin() + cnt[k], bucket.begin() + cnt[k + 1]);
+        const ViewDev& vi = w.views.find(hp[k].I)->second;
+        const ViewDev& vj = w.views.find(hp[k].J)->second;
+        post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
+        results[all[b0 + k].src_index] = std::move(v);
+      });
+      T.ms_host_post += now_ms() - t0;
+    } else {
+      nn_out->resize(rows);
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(nn_out->data(), w.d_nn, rows * sizeof(float4), cudaMemcpyDeviceToHost, w.stream));
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+      T.d2h_bytes += rows * sizeof(float4);
+    }
+    b0 = b1;
+  }
+  return R3D_OK;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" {
+
+int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio, uint32_t flags,
+                    r3d_matches** out) {
+  if (!ctx || !out || (n_pairs && !pairs)) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: bad arguments");
+  *out = nullptr;
+  const uint64_t h2d_uploads = ctx->match_timing.h2d_bytes;  // uploads since the previous call belong to this one
+  for (auto& wk : ctx->workers) wk.timing = r3d_match_timing{};
+  const size_t nw = ctx->workers.size();
+  if (nw == 0) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: context has no device");
+  // Shard the (I-sorted) pair list into contiguous, cost-balanced ranges: one per device, no
+  // collective; every device holds all regions.
+  std::vector<uint64_t> cut(nw + 1, 0);
+  if (nw > 1) {
+    std::vector<double> cost(n_pairs + 1, 0.0);
+    DeviceWorker& w0 = ctx->workers[0];
+    for (uint64_t p = 0; p < n_pairs; ++p) {
+      auto a = w0.views.find(pairs[2 * p]), b = w0.views.find(pairs[2 * p + 1]);
+      const double c = (a != w0.views.end() && b != w0.views.end()) ? (double)a->second.n * (double)b->second.n : 0.0;
+      cost[p + 1] = cost[p] + c + 1.0;
+    }
+    for (size_t k = 1; k < nw; ++k) {
+      const double target = cost[n_pairs] * (double)k / (double)nw;
+      cut[k] = (uint64_t)(std::lower_bound(cost.begin(), cost.end(), target) - cost.begin());
+      if (cut[k] > n_pairs) cut[k] = n_pairs;
+    }
+  }
+  cut[nw] = n_pairs;
+  std::vector<std::vector<std::vector<r3d_indmatch>>> res(nw);
+  std::vector<int> rcs(nw, R3D_OK);
+  if (nw == 1) {
+    rcs[0] = match_on_worker(ctx, ctx->workers[0], pairs, n_pairs, dist_ratio, flags, res[0], nullptr);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nw; ++k)
+      th.emplace_back([&, k]() {
+        rcs[k] = match_on_worker(ctx, ctx->workers[k], pairs + 2 * cut[k], cut[k + 1] - cut[k], dist_ratio, flags,
+                                 res[k], nullptr);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int rc : rcs)
+    if (rc) return rc;
+  {
+    r3d_match_timing sum{};
+    for (auto& wk : ctx->workers) {
+      const r3d_match_timing& t = wk.timing;
+      sum.ms_candidates = std::max(sum.ms_candidates, t.ms_candidates);
+      sum.ms_rerank = std::max(sum.ms_rerank, t.ms_rerank);
+      sum.ms_fallback = std::max(sum.ms_fallback, t.ms_fallback);
+      sum.ms_device_total = std::max(sum.ms_device_total, t.ms_device_total);
+      sum.ms_host_post = std::max(sum.ms_host_post, t.ms_host_post);
+      sum.kernel_launches += t.kernel_launches;
+      sum.queries += t.queries;
+      sum.fallback_queries += t.fallback_queries;
+      sum.third_chunk_queries += t.third_chunk_queries;
+      sum.h2d_bytes += t.h2d_bytes;
+      sum.d2h_bytes += t.d2h_bytes;
+    }
+    sum.h2d_bytes += h2d_uploads;
+    ctx->match_timing = sum;
+  }
+  // assemble the PairWiseMatches map (sorted by (I,J); empty pairs are not inserted)
+  struct Entry { uint32_t I, J; std::vector<r3d_indmatch>* v; };
+  std::vector<Entry> entries;
+  for (size_t k = 0; k < nw; ++k)
+    for (uint64_t p = 0; p < res[k].size(); ++p)
+      if (!res[k][p].empty()) entries.push_back(Entry{pairs[2 * (cut[k] + p)], pairs[2 * (cut[k] + p) + 1], &res[k][p]});
+  std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) {
+    return a.I < b.I || (a.I == b.I && a.J < b.J);
+  });
+  r3d_matches* m = new r3d_matches();
+  m->ofs.push_back(0);
+  for (size_t e = 0; e < entries.size(); ++e) {
+    if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
+    m->pairs.push_back(entries[e].I);
+    m->pairs.push_back(entries[e].J);
+    m->m.insert(m->m.end(), entries[e].v->begin(), entries[e].v->end());
+    m->ofs.push_back(m->m.size());
+  }
+  *out = m;
+  return R3D_OK;
+}
+
+int r3d_search_neighbours(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, int32_t* idx, float* dist) {
+  if (!ctx || !idx || !dist) return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: bad arguments");
+  DeviceWorker& w = ctx->workers[0];
+  auto iI = w.views.find(view_db), iJ = w.views.find(view_query);
+  if (iI == w.views.end() || iJ == w.views.end()) return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: unknown view");
+  if (iI->second.n < 2 || iJ->second.n < 1)
+    return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: NN > number of database rows (upstream returns false)");
+  const uint32_t pr[2] = {view_db, view_query};
+  std::vector<std::vector<r3d_indmatch>> dummy;
+  std::vector<float4> nn;
+  if (iI->second.dim != iJ->second.dim || iI->second.dtype != iJ->second.dtype)
+    return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: descriptor type mismatch");
+  w.timing = r3d_match_timing{};
+  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, &nn);
+  if (rc) return rc;
+  ctx->match_timing = w.timing;
+  const uint32_t nq = iJ->second.n;
+  if (nn.size() < nq) return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: no result");
+  for (uint32_t q = 0; q < nq; ++q) {
+    uint32_t i1, i2;
+    std::memcpy(&i1, &nn[q].x, 4);
+    std::memcpy(&i2, &nn[q].y, 4);
+    idx[2 * q] = (int32_t)i1;
+    idx[2 * q + 1] = (int32_t)i2;
+    dist[2 * q] = nn[q].z;
+    dist[2 * q + 1] = nn[q].w;
+  }
+  return R3D_OK;
+}
+
+int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, uint32_t* keys, float* eps_abs) {
+  if (!ctx || !keys) return fail(ctx, R3D_ERR_INVALID, "r3d_debug_candidate_keys: bad arguments");
+  DeviceWorker& w = ctx->workers[0];
+  auto iI = w.views.find(view_db), iJ = w.views.find(view_query);
+  if (iI == w.views.end() || iJ == w.views.end()) return fail(ctx, R3D_ERR_INVALID, "r3d_debug_candidate_keys: unknown view");
+  const uint32_t pr[2] = {view_db, view_query};
+  std::vector<std::vector<r3d_indmatch>> dummy;
+  std::vector<float4> nn;
+  std::vector<uint4> k;
+  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, &nn, &k);
+  if (rc) return rc;
+  std::memcpy(keys, k.data(), k.size() * sizeof(uint4));
+  if (eps_abs) *eps_abs = pair_eps(iI->second, iJ->second);
+  return R3D_OK;
+}
+
+}  // extern "C"

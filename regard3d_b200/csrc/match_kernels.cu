@@ -1,0 +1,409 @@
+// match_kernels.cu -- CUDA-core kernels of the putative-matching path (sm_100a):
+//   k_view_stats / k_view_prepare : build the fp16 tensor-core operands of a view (+ error constants)
+//   k_rerank                      : exact re-rank of the candidate chunks, certification, ratio test
+//   k_exact_scan                  : exact brute-force 2-NN for listed queries (uncertified / forced)
+//
+// "Exact" means: squared L2 accumulated in float in the order of openMVG::matching::L2<T>
+// (4-way unrolled; the metric the reference names at src/R3DComputeMatches.cpp:290-291), using
+// __fsub_rn/__fmul_rn/__fadd_rn so no FMA contraction can change a bit.
+#include "r3d_internal.cuh"
+
+#include <cfloat>
+
+namespace r3d {
+
+// ------------------------------------------------------------------------------------------------
+// exact distance, upstream accumulation order
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float acc4(float acc, float d0, float d1, float d2, float d3) {
+  const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
+                            __fmul_rn(d3, d3));
+  return __fadd_rn(acc, s);
+}
+
+template <int DTYPE>
+__device__ __forceinline__ float exact_l2(const void* __restrict__ qrow, const void* __restrict__ drow,
+                                           uint32_t dim) {
+  float acc = 0.f;
+  if (DTYPE == 0) {
+    const float* q = (const float*)qrow;
+    const float* d = (const float*)drow;
+    uint32_t k = 0;
+    if ((dim & 3u) == 0) {
+      const float4* q4 = (const float4*)q;
+      const float4* d4 = (const float4*)d;
+      const uint32_t g = dim >> 2;
+#pragma unroll 4
+      for (uint32_t t = 0; t < g; ++t) {
+        const float4 a = q4[t];  // may live in shared memory
+        const float4 b = __ldg(d4 + t);
+        acc = acc4(acc, __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
+      }
+      k = dim;
+    } else {
+      for (; k + 3 < dim; k += 4)
+        acc = acc4(acc, __fsub_rn(q[k], d[k]), __fsub_rn(q[k + 1], d[k + 1]), __fsub_rn(q[k + 2], d[k + 2]),
+                   __fsub_rn(q[k + 3], d[k + 3]));
+    }
+    for (; k < dim; ++k) {
+      const float df = __fsub_rn(q[k], d[k]);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+  } else {
+    const uint8_t* q = (const uint8_t*)qrow;
+    const uint8_t* d = (const uint8_t*)drow;
+    uint32_t k = 0;
+    if ((dim & 3u) == 0) {
+      const uint32_t* q4 = (const uint32_t*)q;
+      const uint32_t* d4 = (const uint32_t*)d;
+      const uint32_t g = dim >> 2;
+#pragma unroll 4
+      for (uint32_t t = 0; t < g; ++t) {
+        const uint32_t a = q4[t], b = __ldg(d4 + t);
+        const float d0 = (float)((int)(a & 255u) - (int)(b & 255u));
+        const float d1 = (float)((int)((a >> 8) & 255u) - (int)((b >> 8) & 255u));
+        const float d2 = (float)((int)((a >> 16) & 255u) - (int)((b >> 16) & 255u));
+        const float d3 = (float)((int)(a >> 24) - (int)(b >> 24));
+        acc = acc4(acc, d0, d1, d2, d3);
+      }
+      k = dim;
+    } else {
+      for (; k + 3 < dim; k += 4)
+        acc = acc4(acc, (float)((int)q[k] - (int)d[k]), (float)((int)q[k + 1] - (int)d[k + 1]),
+                   (float)((int)q[k + 2] - (int)d[k + 2]), (float)((int)q[k + 3] - (int)d[k + 3]));
+    }
+    for (; k < dim; ++k) {
+      const float df = (float)((int)q[k] - (int)d[k]);
+      acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ size_t row_bytes(int dtype, uint32_t dim) { return dtype == 0 ? (size_t)dim * 4 : (size_t)dim; }
+
+// lexicographic (value, index) "less" -- symmetric tie-break so butterfly merges agree on all lanes
+__device__ __forceinline__ bool vi_less(float a, uint32_t ia, float b, uint32_t ib) {
+  return (a < b) || (a == b && ia < ib);
+}
+
+struct Top2 {
+  float d1, d2;
+  uint32_t i1, i2;
+};
+
+__device__ __forceinline__ void top2_insert(Top2& t, float d, uint32_t i) {
+  if (vi_less(d, i, t.d1, t.i1)) {
+    t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = i;
+  } else if (vi_less(d, i, t.d2, t.i2)) {
+    t.d2 = d; t.i2 = i;
+  }
+}
+
+__device__ __forceinline__ Top2 top2_merge(const Top2& a, const Top2& b) {
+  Top2 r;
+  if (vi_less(a.d1, a.i1, b.d1, b.i1)) {
+    r.d1 = a.d1; r.i1 = a.i1;
+    if (vi_less(a.d2, a.i2, b.d1, b.i1)) { r.d2 = a.d2; r.i2 = a.i2; } else { r.d2 = b.d1; r.i2 = b.i1; }
+  } else {
+    r.d1 = b.d1; r.i1 = b.i1;
+    if (vi_less(b.d2, b.i2, a.d1, a.i1)) { r.d2 = b.d2; r.i2 = b.i2; } else { r.d2 = a.d1; r.i2 = a.i1; }
+  }
+  return r;
+}
+
+__device__ __forceinline__ Top2 top2_warp_reduce(Top2 t) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    Top2 b;
+    b.d1 = __shfl_xor_sync(0xffffffffu, t.d1, o);
+    b.d2 = __shfl_xor_sync(0xffffffffu, t.d2, o);
+    b.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+    b.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+    t = top2_merge(t, b);
+  }
+  return t;
+}
+
+// Lower bound on the ORACLE-ORDER float distance of any database column whose chunk has packed
+// key `key` (see DESIGN.md "certification").
+__device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, double gamma) {
+  const double kv = (double)__uint_as_float(key);
+  double lb = kv - fabs(kv) * (1.0 / 2048.0) - (double)eps_abs;
+  if (lb > 0.0) lb = lb * (1.0 - gamma);
+  return lb;
+}
+
+__device__ __forceinline__ void emit_result(const PairDesc& pd, uint32_t pair, uint32_t q, const Top2& t,
+                                            float ratio2, uint32_t* counters, uint3* matches, float4* nn) {
+  if (nn) {
+    nn[pd.q_ofs + q] = make_float4(__uint_as_float(t.i1), __uint_as_float(t.i2), t.d1, t.d2);
+  }
+  if (matches && t.d1 < __fmul_rn(ratio2, t.d2)) {  // NNdistanceRatio: strict, float
+    const uint32_t slot = atomicAdd(&counters[0], 1u);
+    matches[slot] = make_uint3(pair, t.i1, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_rerank : one warp per (pair, query)
+// ------------------------------------------------------------------------------------------------
+template <int DTYPE>
+__global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pairs,
+                                                const uint32_t* __restrict__ keys, uint32_t dim, float ratio2,
+                                                uint32_t* counters, uint3* matches, uint2* fallback, float4* nn) {
+  const uint32_t pair = blockIdx.y;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= pd.nJ) return;
+  const uint4 k = __ldg((const uint4*)keys + (pd.q_ofs + q));
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  const uint32_t cmask = (1u << kChunkBits) - 1u;
+  const size_t rb = row_bytes(DTYPE, dim);
+  const char* qrow = (const char*)pd.descJ + (size_t)q * rb;
+  const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
+
+  Top2 t;
+  t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
+  {
+    const uint32_t c = (lane < 16) ? (k.x & cmask) : (k.y & cmask);
+    const uint32_t col = c * kChunk + (lane & 15u);
+    if (c < nchunks && col < pd.nI) {
+      t.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
+      t.i1 = col;
+    }
+  }
+  t = top2_warp_reduce(t);
+  bool ok = key_lower_bound(k.z, pd.eps_abs, gamma) > (double)t.d2;
+  if (!ok) {
+    Top2 u;
+    u.d1 = u.d2 = FLT_MAX; u.i1 = u.i2 = 0xffffffffu;
+    const uint32_t c = k.z & cmask;
+    const uint32_t col = c * kChunk + (lane & 15u);
+    if (lane < 16 && c < nchunks && col < pd.nI) {
+      u.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
+      u.i1 = col;
+    }
+    u = top2_warp_reduce(u);
+    t = top2_merge(t, u);
+    ok = key_lower_bound(k.w, pd.eps_abs, gamma) > (double)t.d2;
+    if (lane == 0) atomicAdd(&counters[2], 1u);
+  }
+  if (lane == 0) {
+    if (ok) {
+      emit_result(pd, pair, q, t, ratio2, counters, matches, nn);
+    } else {
+      const uint32_t slot = atomicAdd(&counters[1], 1u);
+      fallback[slot] = make_uint2(pair, q);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_exact_scan : one block per listed (pair, query)
+// ------------------------------------------------------------------------------------------------
+template <int DTYPE>
+__global__ void __launch_bounds__(256) k_exact_scan(const PairDesc* __restrict__ pairs,
+                                                    const uint2* __restrict__ list,
+                                                    const uint32_t* __restrict__ list_count, uint32_t dim,
+                                                    float ratio2, uint32_t* counters, uint3* matches,
+                                                    float4* nn) {
+  extern __shared__ __align__(16) unsigned char smem_q[];
+  __shared__ Top2 warp_best[8];
+  const uint32_t n_list = *list_count;
+  for (uint32_t item = blockIdx.x; item < n_list; item += gridDim.x) {
+    const uint2 pq = list[item];
+    const PairDesc pd = pairs[pq.x];
+    const size_t rb = row_bytes(DTYPE, dim);
+    const char* qrow = (const char*)pd.descJ + (size_t)pq.y * rb;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < rb; b += blockDim.x) smem_q[b] = qrow[b];
+    __syncthreads();
+    Top2 t;
+    t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
+    for (uint32_t i = threadIdx.x; i < pd.nI; i += blockDim.x) {
+      const float d = exact_l2<DTYPE>(smem_q, (const char*)pd.descI + (size_t)i * rb, dim);
+      top2_insert(t, d, i);
+    }
+    t = top2_warp_reduce(t);
+    if ((threadIdx.x & 31u) == 0) warp_best[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      Top2 u;
+      u.d1 = u.d2 = FLT_MAX; u.i1 = u.i2 = 0xffffffffu;
+      if (threadIdx.x < (blockDim.x >> 5)) u = warp_best[threadIdx.x];
+      u = top2_warp_reduce(u);
+      if (threadIdx.x == 0) emit_result(pd, pq.x, pq.y, u, ratio2, counters, matches, nn);
+    }
+  }
+}
+
+__global__ void k_fill_all_queries(const PairDesc* __restrict__ pairs, uint32_t n_pairs, uint2* list,
+                                   uint32_t* list_count) {
+  const uint32_t pair = blockIdx.y;
+  if (pair >= n_pairs) return;
+  const PairDesc pd = pairs[pair];
+  if (pd.use_tc) return;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < pd.nJ; q += gridDim.x * blockDim.x) {
+    const uint32_t slot = atomicAdd(list_count, 1u);
+    list[slot] = make_uint2(pair, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_desc(const void* base, int dtype, size_t idx) {
+  return dtype == 0 ? ((const float*)base)[idx] : (float)((const uint8_t*)base)[idx];
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// stats[0] = max ||a||^2, [1] = max ||fp16(a)||^2, [2] = max ||a - fp16(a)||^2, [3] = max |a_k|
+__global__ void k_view_stats(const void* __restrict__ desc, int dtype, uint32_t n, uint32_t dim, float* stats) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  double n2 = 0, h2 = 0, d2 = 0;
+  float ma = 0.f;
+  for (uint32_t k = lane; k < dim; k += 32) {
+    const float a = load_desc(desc, dtype, (size_t)row * dim + k);
+    const float h = __half2float(__float2half_rn(a));
+    n2 += (double)a * (double)a;
+    h2 += (double)h * (double)h;
+    const double e = (double)a - (double)h;
+    d2 += e * e;
+    ma = fmaxf(ma, fabsf(a));
+  }
+  n2 = warp_sum(n2); h2 = warp_sum(h2); d2 = warp_sum(d2); ma = warp_max(ma);
+  if (lane == 0) {
+    // non-negative floats order like their bit patterns; round UP so the maxima stay upper bounds
+    atomicMax((unsigned int*)&stats[0], __float_as_uint(__double2float_ru(n2)));
+    atomicMax((unsigned int*)&stats[1], __float_as_uint(__double2float_ru(h2)));
+    atomicMax((unsigned int*)&stats[2], __float_as_uint(__double2float_ru(d2)));
+    atomicMax((unsigned int*)&stats[3], __float_as_uint(ma));
+  }
+}
+
+// Writes both operand matrices of a view.  Row layout (kp = pad16(dim) + 16 halves):
+//   database role opD: [ a_0 .. a_{dim-1} 0.. | p0 p1 S0 S1 0 x12 ]      ||a||^2 ~= p0*S0 + p1*S1
+//   query role    opQ: [ -2a_0 .. -2a_{dim-1} 0.. | S0 S1 p0 p1 0 x12 ]
+// so that  opQ_row . opD_row' = ||a'||^2 + ||a||^2 - 2 a.a'   (the squared distance).
+// Padding rows of the database role get p0 = 65504 (they lose against every real row).
+__global__ void k_view_prepare(const void* __restrict__ desc, int dtype, uint32_t n, uint32_t n_pad,
+                               uint32_t dim, uint32_t kp, int e0, __half* __restrict__ opQ,
+                               __half* __restrict__ opD) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_pad) return;
+  const uint32_t kmain = kp - kBiasCols;
+  const float S0 = ldexpf(1.f, e0), S1 = ldexpf(1.f, e0 - 11);
+  __half* q = opQ + (size_t)row * kp;
+  __half* d = opD + (size_t)row * kp;
+  if (row >= n) {
+    for (uint32_t k = lane; k < kp; k += 32) {
+      q[k] = __float2half_rn(0.f);
+      float v = 0.f;
+      if (k == kmain) v = 65504.f;
+      if (k == kmain + 2) v = S0;
+      if (k == kmain + 3) v = S1;
+      d[k] = __float2half_rn(v);
+    }
+    return;
+  }
+  double n2 = 0;
+  for (uint32_t k = lane; k < kmain; k += 32) {
+    float a = 0.f;
+    if (k < dim) a = load_desc(desc, dtype, (size_t)row * dim + k);
+    const __half h = __float2half_rn(a);
+    d[k] = h;
+    q[k] = __float2half_rn(-2.f * __half2float(h));
+    n2 += (double)a * (double)a;
+  }
+  n2 = warp_sum(n2);
+  if (lane < kBiasCols) {
+    const double dS0 = (double)S0, dS1 = (double)S1;
+    const __half p0 = __double2half(n2 / dS0);
+    const double r = n2 - (double)__half2float(p0) * dS0;
+    const __half p1 = __double2half(r / dS1);
+    const __half z = __float2half_rn(0.f);
+    const __half hS0 = __float2half_rn(S0), hS1 = __float2half_rn(S1);
+    __half dv = z, qv = z;
+    if (lane == 0) { dv = p0; qv = hS0; }
+    if (lane == 1) { dv = p1; qv = hS1; }
+    if (lane == 2) { dv = hS0; qv = p0; }
+    if (lane == 3) { dv = hS1; qv = p1; }
+    d[kmain + lane] = dv;
+    q[kmain + lane] = qv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v) {
+  R3D_CUDA_TRY(ctx, cudaMemsetAsync(v.d_stats, 0, 4 * sizeof(float), w.stream));
+  if (v.n == 0) return R3D_OK;
+  const int wpb = 8;
+  k_view_stats<<<(v.n + wpb - 1) / wpb, wpb * 32, 0, w.stream>>>(v.d_desc, (int)v.dtype, v.n, v.dim, v.d_stats);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0) {
+  const int wpb = 8;
+  k_view_prepare<<<(v.n_pad + wpb - 1) / wpb, wpb * 32, 0, w.stream>>>(v.d_desc, (int)v.dtype, v.n, v.n_pad,
+                                                                     v.dim, v.kp, e0, v.d_opQ, v.d_opD);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_rerank(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
+                  const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2, uint32_t* d_counters,
+                  uint3* d_matches, uint2* d_fallback, float4* d_nn) {
+  if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
+  const int wpb = 8;
+  dim3 grid((max_nJ + wpb - 1) / wpb, n_pairs);
+  if (dtype == 0)
+    k_rerank<0><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+  else
+    k_rerank<1><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
+                      const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype, float ratio2,
+                      uint32_t* d_counters, uint3* d_matches, float4* d_nn) {
+  if (max_list == 0) return R3D_OK;
+  const uint32_t grid = max_list < (uint32_t)(w.sm_count * 8) ? max_list : (uint32_t)(w.sm_count * 8);
+  const size_t smem = (dtype == 0 ? (size_t)dim * 4 : (size_t)dim) + 16;
+  if (dtype == 0)
+    k_exact_scan<0><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn);
+  else
+    k_exact_scan<1><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,
+                            uint2* d_list, uint32_t* d_list_count) {
+  if (n_pairs == 0) return R3D_OK;
+  dim3 grid(64, n_pairs);
+  k_fill_all_queries<<<grid, 256, 0, w.stream>>>(d_pairs, n_pairs, d_list, d_list_count);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+}  // namespace r3d

@@ -1,0 +1,56 @@
+// match_post.cpp -- host-side, order-dependent tail of RegionsMatcherT::MatchDistanceRatio
+// (upstream matching/regions_matcher.hpp, invoked by the reference at src/R3DComputeMatches.cpp:479):
+//   IndMatch::getDeduplicated            -> sort by (i_,j_) + unique
+//   IndMatchDecorator<float>::getDeduplicated -> std::set with the upstream comparator
+// The second step's comparator is not a strict weak ordering, so its result is defined only by
+// the std::set range-insertion algorithm; it therefore runs on the host with the very container
+// the reference uses.  O(#matches) per pair.
+#include <algorithm>
+#include <set>
+#include <vector>
+
+#include "../../include/r3dgpu.h"
+
+namespace r3d {
+
+namespace {
+struct XYMatch {
+  float x1, y1, x2, y2;
+  r3d_indmatch im;
+};
+inline bool same_xy(const XYMatch& a, const XYMatch& b) {
+  return a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2;
+}
+// upstream IndMatchDecoratorStruct::operator< ("lexicographical ordering", verbatim semantics)
+struct XYLess {
+  bool operator()(const XYMatch& m1, const XYMatch& m2) const {
+    if (same_xy(m1, m2)) return false;
+    if (m1.x1 < m2.x1) return m1.y1 < m2.y1;
+    if (m1.x1 > m2.x1) return m1.y1 < m2.y1;
+    return m1.x1 < m2.x1;
+  }
+};
+}  // namespace
+
+void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const float* xyJ, bool coord_dedup) {
+  std::sort(m.begin(), m.end(), [](const r3d_indmatch& a, const r3d_indmatch& b) {
+    return a.i < b.i || (a.i == b.i && a.j < b.j);
+  });
+  m.erase(std::unique(m.begin(), m.end(),
+                      [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }),
+          m.end());
+  if (!coord_dedup || !xyI || !xyJ) return;
+  std::vector<XYMatch> dec(m.size());
+  for (size_t k = 0; k < m.size(); ++k) {
+    dec[k].x1 = xyI[2 * (size_t)m[k].i];
+    dec[k].y1 = xyI[2 * (size_t)m[k].i + 1];
+    dec[k].x2 = xyJ[2 * (size_t)m[k].j];
+    dec[k].y2 = xyJ[2 * (size_t)m[k].j + 1];
+    dec[k].im = m[k];
+  }
+  std::set<XYMatch, XYLess> uniq(dec.begin(), dec.end());
+  m.clear();
+  for (const auto& d : uniq) m.push_back(d.im);
+}
+
+}  // namespace r3d

@@ -1,0 +1,91 @@
+// matches.cpp -- PairWiseMatches container + matching::Save / matching::Load (text format).
+// Reference call sites: Save(map, "matches.putative.txt") src/R3DComputeMatches.cpp:2064,
+// Save(map, matchesFFilename_) :2120; consumers that Load it: src/threads/R3DTriangulationThread.cpp:222,
+// :411 and src/threads/PreviewGeneratorThread.cpp:337-338.  Format: SURVEY.md Appendix B.3.
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "r3d_matches.h"
+
+extern "C" {
+
+uint64_t r3d_matches_num_pairs(const r3d_matches* m) { return m ? m->pairs.size() / 2 : 0; }
+uint64_t r3d_matches_total(const r3d_matches* m) { return m ? m->m.size() : 0; }
+
+int r3d_matches_get_pair(const r3d_matches* m, uint64_t k, uint32_t* I, uint32_t* J, const r3d_indmatch** matches,
+                         uint64_t* count) {
+  if (!m || k >= m->pairs.size() / 2) return R3D_ERR_INVALID;
+  if (I) *I = m->pairs[2 * k];
+  if (J) *J = m->pairs[2 * k + 1];
+  if (matches) *matches = m->m.data() + m->ofs[k];
+  if (count) *count = m->ofs[k + 1] - m->ofs[k];
+  return R3D_OK;
+}
+
+int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t* pair_ofs, const r3d_indmatch* matches,
+                         r3d_matches** out) {
+  if (!out || (n_pairs && (!pairs || !pair_ofs))) return R3D_ERR_INVALID;
+  std::vector<uint64_t> order(n_pairs);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+    return pairs[2 * a] < pairs[2 * b] || (pairs[2 * a] == pairs[2 * b] && pairs[2 * a + 1] < pairs[2 * b + 1]);
+  });
+  r3d_matches* m = new r3d_matches();
+  m->ofs.push_back(0);
+  for (uint64_t t = 0; t < n_pairs; ++t) {
+    const uint64_t p = order[t];
+    if (pair_ofs[p + 1] == pair_ofs[p]) continue;  // empty pairs are never in the map
+    if (!m->pairs.empty() && m->pairs[m->pairs.size() - 2] == pairs[2 * p] && m->pairs.back() == pairs[2 * p + 1]) continue;
+    m->pairs.push_back(pairs[2 * p]);
+    m->pairs.push_back(pairs[2 * p + 1]);
+    m->m.insert(m->m.end(), matches + pair_ofs[p], matches + pair_ofs[p + 1]);
+    m->ofs.push_back(m->m.size());
+  }
+  *out = m;
+  return R3D_OK;
+}
+
+void r3d_free_matches(r3d_matches* m) { delete m; }
+
+int r3d_save_matches_txt(const r3d_matches* m, const char* path) {
+  if (!m || !path) return R3D_ERR_INVALID;
+  std::ofstream stream(path);
+  if (!stream.is_open()) return R3D_ERR_IO;
+  const uint64_t P = m->pairs.size() / 2;
+  for (uint64_t k = 0; k < P; ++k) {
+    stream << m->pairs[2 * k] << " " << m->pairs[2 * k + 1] << '\n' << (m->ofs[k + 1] - m->ofs[k]) << '\n';
+    for (uint64_t t = m->ofs[k]; t < m->ofs[k + 1]; ++t) stream << m->m[t].i << " " << m->m[t].j << "\n";
+  }
+  return stream.good() ? R3D_OK : R3D_ERR_IO;
+}
+
+int r3d_load_matches_txt(const char* path, r3d_matches** out) {
+  if (!path || !out) return R3D_ERR_INVALID;
+  std::ifstream stream(path);
+  if (!stream.is_open()) return R3D_ERR_IO;
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<r3d_indmatch>> mp;
+  uint32_t I, J;
+  uint64_t number;
+  while (stream >> I >> J >> number) {
+    std::vector<r3d_indmatch> v(number);
+    for (uint64_t k = 0; k < number; ++k)
+      if (!(stream >> v[k].i >> v[k].j)) return R3D_ERR_IO;
+    mp[{I, J}] = std::move(v);
+  }
+  r3d_matches* m = new r3d_matches();
+  m->ofs.push_back(0);
+  for (auto& kv : mp) {
+    m->pairs.push_back(kv.first.first);
+    m->pairs.push_back(kv.first.second);
+    m->m.insert(m->m.end(), kv.second.begin(), kv.second.end());
+    m->ofs.push_back(m->m.size());
+  }
+  *out = m;
+  return R3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+// r3d_internal.cuh -- internal declarations of libr3dgpu (B200 / sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/r3dgpu.h"
+#include "r3d_matches.h"
+
+// ------------------------------------------------------------------------------------------------
+// Geometry of the tensor-core candidate kernel (k_l2_candidates.cu) and the operand layout.
+// ------------------------------------------------------------------------------------------------
+namespace r3d {
+
+constexpr int kTileRows = 128;      // rows of one TMA box / one UMMA M or N extent
+constexpr int kKBlock = 64;         // fp16 elements per 128-byte swizzle row
+constexpr int kQB = 2;              // query blocks (of 128 rows) resident per CTA
+constexpr int kSuperRows = kTileRows * kQB;  // 256 query rows per work item
+constexpr int kRowPad = 256;        // every view is padded to a multiple of this many rows
+constexpr int kBiasCols = 16;       // one UMMA K-step holding the norm terms
+constexpr int kChunk = 16;          // database columns summarised by one candidate key
+constexpr int kChunkBits = 12;      // low mantissa bits of a key that hold the chunk id
+constexpr int kNumKeys = 4;         // keys kept per query (3 candidate chunks + 1 bound)
+constexpr int kMaxKBlocks = 4;      // Kp <= 256  (descriptor dim <= 240)
+constexpr uint32_t kMaxDbRowsTC = (1u << kChunkBits) * kChunk;  // 65536
+
+inline int pad_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int operand_cols(int dim) { return pad_up(dim, 16) + kBiasCols; }  // Kp
+
+struct ViewDev {
+  uint32_t n = 0, dim = 0, dtype = 0, n_pad = 0, kp = 0;
+  void* d_desc = nullptr;    // original descriptors [n][dim] (f32 or u8): exact re-rank operand
+  __half* d_opQ = nullptr;   // query-role operand    [n_pad][kp]: -2*b | S0 S1 q0 q1 0...
+  __half* d_opD = nullptr;   // database-role operand [n_pad][kp]:    a  | p0 p1 S0 S1 0...
+  float2* d_xy = nullptr;    // positions [n]
+  std::vector<float> h_xy;   // host copy (coordinate de-duplication, RANSAC set-up)
+  bool has_xy = false;
+  bool prepared = false;
+  int prepared_e0 = 0;
+  // error-bound constants (host copies of device reductions)
+  float max_norm = 0.f;      // max_i ||a_i||
+  float max_hnorm = 0.f;     // max_i ||fp16(a_i)||
+  float max_dnorm = 0.f;     // max_i ||a_i - fp16(a_i)||
+  float max_abs = 0.f;       // max |a_ik|
+  float* d_stats = nullptr;  // 4 floats: max n2, max hn2, max dn2, max abs
+};
+
+struct PairDesc {            // one entry per pair of a batch (device + host)
+  uint32_t I, J;             // view ids
+  uint32_t nI, nJ;           // feature counts
+  uint32_t nI_pad, nJ_pad;
+  uint32_t q_ofs;            // first row of this pair in the per-batch key / nn arrays
+  uint32_t use_tc;           // 1: tensor-core candidates available, 0: exact scan only
+  float eps_abs;             // absolute error bound of a candidate value vs the real-valued distance
+  uint32_t slotI, slotJ;     // tensor-map slots of the two views
+  uint32_t pad_;
+  const void* descI;         // original descriptors of I / J (device)
+  const void* descJ;
+};
+static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
+
+struct WorkItem { uint32_t pair; uint32_t sb; };  // sb: super-block (256 query rows) index
+
+struct DeviceWorker {
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  std::map<uint32_t, ViewDev> views;
+  // tensor maps, indexed by view slot
+  std::map<uint32_t, uint32_t> view_slot;
+  CUtensorMap* d_tmapQ = nullptr;
+  CUtensorMap* d_tmapD = nullptr;
+  uint32_t tmap_cap = 0;
+  // per-context scale exponent of the norm split (S0 = 2^e0, S1 = 2^(e0-11))
+  int e0 = -3;
+  bool e0_fixed = false;
+  // scratch (grown on demand)
+  void* d_pairs = nullptr; size_t pairs_cap = 0;
+  void* d_items = nullptr; size_t items_cap = 0;
+  void* d_keys = nullptr; size_t keys_cap = 0;
+  void* d_matches = nullptr; size_t matches_cap = 0;
+  void* d_fb = nullptr; size_t fb_cap = 0;
+  void* d_nn = nullptr; size_t nn_cap = 0;
+  uint32_t* d_counters = nullptr;  // [0] match count, [1] fallback count, [2] third-chunk count
+  uint32_t* h_counters = nullptr;  // pinned
+  void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
+  r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
+};
+
+}  // namespace r3d
+
+
+struct r3d_ctx {
+  std::vector<r3d::DeviceWorker> workers;
+  std::string last_error;
+  r3d_match_timing match_timing{};
+  r3d_filter_timing filter_timing{};
+  int host_threads = 0;
+};
+
+namespace r3d {
+
+void set_global_error(const std::string& s);
+int fail(r3d_ctx* ctx, int code, const std::string& msg);
+
+#define R3D_CUDA_TRY(ctx, call)                                                            \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return r3d::fail((ctx), R3D_ERR_CUDA,                                                \
+                       std::string(#call) + ": " + cudaGetErrorString(_e) + " (" +         \
+                           __FILE__ + ":" + std::to_string(__LINE__) + ")");               \
+  } while (0)
+
+template <typename T>
+int ensure_capacity(r3d_ctx* ctx, void** p, size_t* cap, size_t need_elems) {
+  const size_t need = need_elems * sizeof(T);
+  if (*cap >= need && *p) return R3D_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t alloc = need + need / 4 + 256;
+  cudaError_t e = cudaMalloc(p, alloc);
+  if (e != cudaSuccess) return fail(ctx, R3D_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  *cap = alloc;
+  return R3D_OK;
+}
+
+int prepare_views(r3d_ctx* ctx, DeviceWorker& w);
+
+// ---- kernels (defined in the .cu files) --------------------------------------------------------
+// operand preparation
+int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v);
+int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0);
+// tensor-core candidate kernel
+int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int grid_limit);
+size_t l2_candidates_smem_bytes(int kp_cols);
+// exact re-rank + ratio
+int launch_rerank(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,
+                  uint32_t max_nJ, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
+                  uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn);
+// exact scan of listed queries
+int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
+                      const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
+                      float ratio2, uint32_t* d_counters, uint3* d_matches, float4* d_nn);
+int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,
+                            uint2* d_list, uint32_t* d_list_count);
+
+// host post-processing (match_post.cpp)
+void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const float* xyJ,
+                       bool coord_dedup);
+
+// driver entry points
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+}  // namespace r3d
