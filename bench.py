@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- matched image-pairs / second on the compute-matches hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload at every N: BASELINE.json configs[1] (C2) PER GPU -- 50 synthetic 1080p images x 10 000
+float descriptors (D = 144, Regard3D's native R3D_AKAZE_LIOP_Regions layout), exhaustive pairs
+(1 225), brute-force L2 2-NN + ratio 0.6 + de-duplications.  One step = one pass over all pairs.
+N > 1: one process per GPU, every rank owns an independent 50-image set (weak scaling; image pairs
+shard with no data-path collective); torch.distributed (NCCL) is only used for the
+barrier and the max-over-ranks of the step time.
+
+value : pairs/s with descriptors already resident in HBM (r3d_match_pairs only; results land in
+        host memory, host de-duplication included).
+e2e   : pairs/s through the C ABI from pinned HOST buffers: r3d_clear_regions + r3d_upload_regions
+        of every view + r3d_match_pairs, every step.
+roofline : the tcgen05 candidate kernel, algorithmic 2*N_I*N_J*D flop per pair over
+        its CUDA-event time on its own stream, against MEASURED_PEAKS.json bf16 TFLOP/s.
+cpu_baseline : the oracle port (same serial-I / omp-J structure as the reference) on a bounded
+        sample of the same pairs, all host threads it can use.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_IMAGES, N_FEATS, DIM, KIND, RATIO = 50, 10000, 144, "liop", 0.6
+METRIC = "matched_image_pairs_per_sec_exhaustive"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        # "under load": samples in the upper half of what was seen
+        if sm:
+            hi = [x for x in sm if x >= 0.5 * max(sm)]
+            med = float(np.median(hi))
+        else:
+            med = None
+        return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def make_workload(seed):
+    from regard3d_b200 import synth
+    sc = synth.make_scene(N_IMAGES, N_FEATS, DIM, KIND, seed=seed)
+    pairs = synth.exhaustive_pairs(N_IMAGES)
+    return sc, pairs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path = the oracle port (the reference's own code cannot
+    be built here: OpenMVG/Ceres/Eigen/wx are neither vendored nor installed)."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    sc, pairs = make_workload(20260924 + 2)
+    nthreads = po.num_threads()
+    # bounded sample: all pairs that share the first image(s) -- the reference parallelises over J
+    # for a fixed I (src/R3DComputeMatches.cpp:465), so one I gives up to 49 concurrent J's.
+    n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "49"))
+    sample = pairs[:n_sample]
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        po.match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(sample) * len(times) / total
+    cores = min(nthreads, len(sample))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d pairs (I=0, J=1..%d) of the C2 set per step, omp over J, %d threads"
+                                   % (len(sample), len(sample), nthreads)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "C2: %d images x %d feats, D=%d float32 unit-norm (LIOP-like), exhaustive %d pairs, ratio %.1f"
+                        % (N_IMAGES, N_FEATS, DIM, N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
+            "images": N_IMAGES, "feats_per_image": N_FEATS, "dim": DIM, "pairs": N_IMAGES * (N_IMAGES - 1) // 2,
+            "parallelism": "pairs sharded per GPU, no collective",
+            "l2_policy": "inputs (descriptors + fp16 operands, ~0.6 GB) exceed the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from regard3d_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = capi.Context((local_rank,))
+    sc, pairs = make_workload(20260924 + 2 + 1000 * rank)
+    n_pairs = len(pairs)
+    # pinned host staging (the e2e leg copies from here every step)
+    pinned_desc, pinned_xy = [], []
+    for v in range(N_IMAGES):
+        d = torch.from_numpy(sc["descs"][v]).pin_memory()
+        x = torch.from_numpy(sc["xys"][v]).pin_memory()
+        pinned_desc.append(d)
+        pinned_xy.append(x)
+
+    def upload_all():
+        for v in range(N_IMAGES):
+            ctx.upload_regions(v, pinned_desc[v].numpy(), pinned_xy[v].numpy())
+
+    # ---------------- resident leg: `value` ----------------
+    upload_all()
+    for _ in range(max(args.warmup, 3)):
+        m = ctx.match_pairs(pairs, RATIO)
+    sampler = ClockSampler(local_rank)
+    cand_ms, rerank_ms, fb_ms, dev_ms, host_ms, launches = [], [], [], [], [], 0
+    fbq = q = 0
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m = ctx.match_pairs(pairs, RATIO)
+        t = ctx.match_timing()
+        cand_ms.append(t["ms_candidates"]); rerank_ms.append(t["ms_rerank"]); fb_ms.append(t["ms_fallback"])
+        dev_ms.append(t["ms_device_total"]); host_ms.append(t["ms_host_post"])
+        launches += t["kernel_launches"]
+        fbq += t["fallback_queries"]; q += t["queries"]
+        d2h_step = t["d2h_bytes"]
+    barrier()
+    t_res = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n_matches = m.total
+    n_match_pairs = m.num_pairs
+
+    # ---------------- end-to-end leg: `e2e` ----------------
+    for _ in range(2):
+        ctx.clear_regions(); upload_all(); ctx.match_pairs(pairs, RATIO)
+    barrier()
+    t0 = time.perf_counter()
+    h2d_step = 0
+    for _ in range(args.steps):
+        ctx.clear_regions()
+        upload_all()
+        m2 = ctx.match_pairs(pairs, RATIO)
+        t = ctx.match_timing()
+        h2d_step = t["h2d_bytes"]
+        d2h_e2e = t["d2h_bytes"]
+        launches_e2e = t["kernel_launches"]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(tt[0]), float(tt[1])
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        total_pairs = n_pairs * world * args.steps
+        value = total_pairs / t_res
+        e2e = total_pairs / t_e2e
+        flop_per_launch = 2.0 * N_FEATS * N_FEATS * DIM * n_pairs          # one launch = all pairs of the step
+        ms_c = float(np.mean(cand_ms))
+        achieved = flop_per_launch / (ms_c * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 exact re-rank over f16 tensor-core candidates",
+            "data": "synthetic", "config": workload_config(), "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
+                    "d2h_bytes_per_step": int(d2h_e2e), "ms_per_step": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "k_l2_candidates (tcgen05 kind::f16)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "peak_source": "%s bf16_tflops (burst; kernel timed alone with CUDA events)" % peak_src,
+                         "ms_per_launch": ms_c, "flop_per_launch": flop_per_launch, "traffic": None},
+            "breakdown_ms": {"candidates": ms_c, "rerank": float(np.mean(rerank_ms)),
+                             "exact_scan_fallback": float(np.mean(fb_ms)), "device_total": float(np.mean(dev_ms)),
+                             "host_dedup": float(np.mean(host_ms))},
+            "result": {"pairs_with_matches": int(n_match_pairs), "matches": int(n_matches),
+                       "fallback_query_frac": fbq / max(q, 1)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            nthreads = po.num_threads()
+            n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "49"))
+            sample = pairs[:n_sample]
+            tc0 = time.perf_counter()
+            o_ofs, o_m = po.match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
+            tc = time.perf_counter() - tc0
+            # the checker doubles as a parity probe on the sampled pairs
+            got = m.to_dict()
+            same = True
+            for k, (I, J) in enumerate(sample):
+                e = o_m[int(o_ofs[k]):int(o_ofs[k + 1])]
+                g = got.get((int(I), int(J)))
+                same &= (g is not None and len(g) == len(e) and set(zip(g["i"].tolist(), g["j"].tolist())) ==
+                         set(zip(e["i"].tolist(), e["j"].tolist()))) or (g is None and len(e) == 0)
+            line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s", "cores": min(nthreads, len(sample)),
+                                    "kind": "port",
+                                    "sample": "%d pairs (I=0) of the same C2 set, one pass, %d omp threads, %.1f s"
+                                              % (len(sample), nthreads, tc),
+                                    "parity_on_sample": bool(same)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
