@@ -192,7 +192,7 @@ typedef struct {
   double ms_device_total;/* first launch -> last kernel of the last r3d_match_pairs */
   double ms_host_post;   /* host de-duplication */
   uint64_t kernel_launches;
-  uint64_t queries, fallback_queries, third_chunk_queries;
+  uint64_t queries, fallback_queries, third_chunk_queries, fifth_chunk_queries;
   uint64_t h2d_bytes, d2h_bytes;
 } r3d_match_timing;
 int r3d_get_match_timing(const r3d_ctx* ctx, r3d_match_timing* out);
@@ -203,7 +203,8 @@ typedef struct {
 } r3d_filter_timing;
 int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out);
 
-/* Diagnostics: the 4 packed candidate keys per query row (n_query padded to 256 rows x 4 uint32)
+/* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
+ * 6 keys ascending + 2 unused)
  * the tensor-core pass produced for (view_db, view_query), and the pair's error bound. */
 int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, uint32_t* keys,
                              float* eps_abs);

@@ -37,7 +37,7 @@ class MatchTiming(C.Structure):
     _fields_ = [("ms_prep", C.c_double), ("ms_candidates", C.c_double), ("ms_rerank", C.c_double),
                 ("ms_fallback", C.c_double), ("ms_device_total", C.c_double), ("ms_host_post", C.c_double),
                 ("kernel_launches", C.c_uint64), ("queries", C.c_uint64), ("fallback_queries", C.c_uint64),
-                ("third_chunk_queries", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("third_chunk_queries", C.c_uint64), ("fifth_chunk_queries", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
 class FilterTiming(C.Structure):
@@ -256,7 +256,7 @@ class Context:
 
     def debug_candidate_keys(self, view_db, view_query, n_query):
         npad = (max(n_query, 1) + 255) // 256 * 256
-        keys = np.zeros((npad, 4), np.uint32)
+        keys = np.zeros((npad, 8), np.uint32)
         eps = C.c_float()
         self._check(lib().r3d_debug_candidate_keys(self._h, C.c_uint32(view_db), C.c_uint32(view_query), _p(keys), C.byref(eps)))
         return keys, eps.value

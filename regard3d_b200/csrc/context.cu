@@ -2,10 +2,20 @@
 #include "r3d_internal.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
 namespace r3d {
+
+int operand_col_align() {
+  static int a = -1;
+  if (a < 0) {
+    const char* e = getenv("R3D_KP_ALIGN");
+    a = (e && atoi(e) == 16) ? 16 : 64;
+  }
+  return a;
+}
 
 static std::mutex g_err_mutex;
 static std::string g_last_error;
@@ -264,7 +274,7 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
       v.h_xy.assign(xy, xy + 2 * (size_t)n);
       v.has_xy = true;
     }
-    ctx->match_timing.h2d_bytes += rb * n + (xy ? (size_t)n * 8 : 0);
+    ctx->pending_h2d += rb * n + (xy ? (size_t)n * 8 : 0);
     uint32_t slot;
     auto sit = w.view_slot.find(view_id);
     if (sit == w.view_slot.end()) {

@@ -130,7 +130,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
 
 // minimum of 16 accumulator columns, packed with the chunk id, inserted into the sorted 4-key set
-__device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_id, float (&key)[4]) {
+__device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_id, uint32_t keep_mask,
+                                             float (&key)[kNumKeys]) {
   float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
   m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
   m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
@@ -139,14 +140,14 @@ __device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_i
   m = fmin3(m, __uint_as_float(v[11]), __uint_as_float(v[12]));
   m = fmin3(m, __uint_as_float(v[13]), __uint_as_float(v[14]));
   m = fminf(m, __uint_as_float(v[15]));
-  const float x = __uint_as_float((__float_as_uint(m) & ~((1u << kChunkBits) - 1u)) | chunk_id);
-  const float t0 = fmaxf(key[0], x);
-  key[0] = fminf(key[0], x);
-  const float t1 = fmaxf(key[1], t0);
-  key[1] = fminf(key[1], t0);
-  const float t2 = fmaxf(key[2], t1);
-  key[2] = fminf(key[2], t1);
-  key[3] = fminf(key[3], t2);
+  float x = __uint_as_float((__float_as_uint(m) & keep_mask) | chunk_id);
+#pragma unroll
+  for (int i = 0; i < kNumKeys - 1; ++i) {  // sorted insertion network: 2 FMNMX per level
+    const float hi = fmaxf(key[i], x);
+    key[i] = fminf(key[i], x);
+    x = hi;
+  }
+  key[kNumKeys - 1] = fminf(key[kNumKeys - 1], x);
 }
 
 struct SmemLayout {
@@ -282,8 +283,10 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
       const WorkItem wi = items[it];
       const PairDesc pd = pairs[wi.pair];
       const uint32_t ntiles = pd.nI_pad / kTileRows;
-      float key[4];
-      key[0] = key[1] = key[2] = key[3] = __uint_as_float(kKeySentinel);
+      float key[kNumKeys];
+#pragma unroll
+      for (int i = 0; i < kNumKeys; ++i) key[i] = __uint_as_float(kKeySentinel);
+      const uint32_t keep_mask = ~((1u << pd.chunk_bits) - 1u);
       for (uint32_t t = 0; t < ntiles; ++t) {
         mbar_wait(bar_tfull + 8 * acc, accphase);
         tc_fence_after();
@@ -293,31 +296,35 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
         tc_ld32(taddr, va);
         tc_wait_ld(va);
         tc_ld32(taddr + 32, vb);
-        chunk_update(va, chunk0 + 0, key);
-        chunk_update(va + 16, chunk0 + 1, key);
+        chunk_update(va, chunk0 + 0, keep_mask, key);
+        chunk_update(va + 16, chunk0 + 1, keep_mask, key);
         tc_wait_ld(vb);
         tc_ld32(taddr + 64, va);
-        chunk_update(vb, chunk0 + 2, key);
-        chunk_update(vb + 16, chunk0 + 3, key);
+        chunk_update(vb, chunk0 + 2, keep_mask, key);
+        chunk_update(vb + 16, chunk0 + 3, keep_mask, key);
         tc_wait_ld(va);
         tc_ld32(taddr + 96, vb);
-        chunk_update(va, chunk0 + 4, key);
-        chunk_update(va + 16, chunk0 + 5, key);
+        chunk_update(va, chunk0 + 4, keep_mask, key);
+        chunk_update(va + 16, chunk0 + 5, keep_mask, key);
         tc_wait_ld(vb);
         // all TMEM reads of this stage are done: hand it back before the last two chunks
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        chunk_update(vb, chunk0 + 6, key);
-        chunk_update(vb + 16, chunk0 + 7, key);
+        chunk_update(vb, chunk0 + 6, keep_mask, key);
+        chunk_update(vb + 16, chunk0 + 7, keep_mask, key);
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
       }
       const uint32_t row = wi.sb * kSuperRows + qb * kTileRows + lane_quarter * 32u + lane;
-      uint4 o;
-      o.x = __float_as_uint(key[0]); o.y = __float_as_uint(key[1]);
-      o.z = __float_as_uint(key[2]); o.w = __float_as_uint(key[3]);
-      ((uint4*)keys_out)[pd.q_ofs + row] = o;
+      uint4 o0, o1;
+      o0.x = __float_as_uint(key[0]); o0.y = __float_as_uint(key[1]);
+      o0.z = __float_as_uint(key[2]); o0.w = __float_as_uint(key[3]);
+      o1.x = __float_as_uint(key[4]); o1.y = __float_as_uint(key[5]);
+      o1.z = kKeySentinel; o1.w = kKeySentinel;
+      uint4* dst = (uint4*)keys_out + (size_t)(pd.q_ofs + row) * (kKeyStride / 4);
+      dst[0] = o0;
+      dst[1] = o1;
     }
   }
 
@@ -337,7 +344,7 @@ size_t l2_candidates_smem_bytes(int kp_cols) {
 }
 
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
-                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int grid_limit) {
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int grid_limit) {
   if (n_items == 0) return R3D_OK;
   const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
   if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
@@ -348,7 +355,7 @@ int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   if (grid_limit > 0 && (uint32_t)grid_limit < grid) grid = (uint32_t)grid_limit;
   if (n_items < grid) grid = n_items;
   k_l2_candidates<<<grid, kThreads, smem, w.stream>>>(w.d_tmapQ, w.d_tmapD, d_pairs, d_items, n_items, d_keys,
-                                                      (uint32_t)nkb, (uint32_t)(kp_cols / 16), (uint32_t)stages);
+                                                      (uint32_t)nkb, (uint32_t)ksteps, (uint32_t)stages);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

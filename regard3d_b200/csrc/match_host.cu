@@ -113,6 +113,11 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     pd.descI = vi.d_desc; pd.descJ = vj.d_desc;
     pd.use_tc = ((flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
     pd.eps_abs = pair_eps(vi, vj);
+    {
+      uint32_t nchunks = vi.n_pad / kChunk, bits = 4;
+      while ((1u << bits) < nchunks) ++bits;
+      pd.chunk_bits = bits;
+    }
     all.push_back(bp);
   }
   if (all.empty()) return R3D_OK;
@@ -148,7 +153,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
 
     if ((rc = ensure_capacity<PairDesc>(ctx, &w.d_pairs, &w.pairs_cap, nb))) return rc;
     if ((rc = ensure_capacity<WorkItem>(ctx, &w.d_items, &w.items_cap, std::max<size_t>(hitems.size(), 1)))) return rc;
-    if ((rc = ensure_capacity<uint4>(ctx, &w.d_keys, &w.keys_cap, rows))) return rc;
+    if ((rc = ensure_capacity<uint4>(ctx, &w.d_keys, &w.keys_cap, rows * (kKeyStride / 4)))) return rc;
     if ((rc = ensure_capacity<uint2>(ctx, &w.d_fb, &w.fb_cap, qtotal))) return rc;
     if (want_matches) {
       if ((rc = ensure_capacity<uint3>(ctx, &w.d_matches, &w.matches_cap, qtotal))) return rc;
@@ -167,13 +172,13 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[0], w.stream));
     if (!hitems.empty()) {
       if ((rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items,
-                                     (uint32_t)hitems.size(), (uint32_t*)w.d_keys, kp, 0))) return rc;
+                                     (uint32_t)hitems.size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), 0))) return rc;
       T.kernel_launches += 1;
     }
     R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[1], w.stream));
     if (keys_dbg) {
-      keys_dbg->resize(rows);
-      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(keys_dbg->data(), w.d_keys, rows * sizeof(uint4), cudaMemcpyDeviceToHost, w.stream));
+      keys_dbg->resize(rows * (kKeyStride / 4));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(keys_dbg->data(), w.d_keys, rows * (kKeyStride / 4) * sizeof(uint4), cudaMemcpyDeviceToHost, w.stream));
       R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
     }
     if (!hitems.empty()) {
@@ -204,6 +209,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     T.queries += qtotal;
     T.fallback_queries += w.h_counters[1];
     T.third_chunk_queries += w.h_counters[2];
+    T.fifth_chunk_queries += w.h_counters[3];
     T.d2h_bytes += 16 * sizeof(uint32_t);
 
     if (want_matches) {
@@ -262,7 +268,8 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
                     r3d_matches** out) {
   if (!ctx || !out || (n_pairs && !pairs)) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: bad arguments");
   *out = nullptr;
-  const uint64_t h2d_uploads = ctx->match_timing.h2d_bytes;  // uploads since the previous call belong to this one
+  const uint64_t h2d_uploads = ctx->pending_h2d;  // uploads since the previous call belong to this one
+  ctx->pending_h2d = 0;
   for (auto& wk : ctx->workers) wk.timing = r3d_match_timing{};
   const size_t nw = ctx->workers.size();
   if (nw == 0) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: context has no device");
@@ -312,6 +319,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
       sum.queries += t.queries;
       sum.fallback_queries += t.fallback_queries;
       sum.third_chunk_queries += t.third_chunk_queries;
+      sum.fifth_chunk_queries += t.fifth_chunk_queries;
       sum.h2d_bytes += t.h2d_bytes;
       sum.d2h_bytes += t.d2h_bytes;
     }
@@ -371,6 +379,7 @@ int r3d_search_neighbours(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, i
 }
 
 int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, uint32_t* keys, float* eps_abs) {
+  // keys: n_query_pad x 8 uint32 (6 keys + 2 unused)
   if (!ctx || !keys) return fail(ctx, R3D_ERR_INVALID, "r3d_debug_candidate_keys: bad arguments");
   DeviceWorker& w = ctx->workers[0];
   auto iI = w.views.find(view_db), iJ = w.views.find(view_query);

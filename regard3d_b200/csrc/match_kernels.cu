@@ -127,9 +127,9 @@ __device__ __forceinline__ Top2 top2_warp_reduce(Top2 t) {
 
 // Lower bound on the ORACLE-ORDER float distance of any database column whose chunk has packed
 // key `key` (see DESIGN.md "certification").
-__device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, double gamma) {
+__device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, double gamma, double pack_rel) {
   const double kv = (double)__uint_as_float(key);
-  double lb = kv - fabs(kv) * (1.0 / 2048.0) - (double)eps_abs;
+  double lb = kv - fabs(kv) * pack_rel - (double)eps_abs;
   if (lb > 0.0) lb = lb * (1.0 - gamma);
   return lb;
 }
@@ -158,38 +158,41 @@ __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pai
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= pd.nJ) return;
-  const uint4 k = __ldg((const uint4*)keys + (pd.q_ofs + q));
+  const uint4 ka = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4));
+  const uint4 kb = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4) + 1);
+  const uint32_t key[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
   const uint32_t nchunks = pd.nI_pad / kChunk;
-  const uint32_t cmask = (1u << kChunkBits) - 1u;
+  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+  const double pack_rel = ldexp(1.0, (int)pd.chunk_bits - 23);
   const size_t rb = row_bytes(DTYPE, dim);
   const char* qrow = (const char*)pd.descJ + (size_t)q * rb;
   const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
 
+  // stage A: chunks of key 0 (lanes 0-15) and key 1 (lanes 16-31); B: key 2; C: keys 3 and 4.
+  // After each stage every column outside the re-ranked chunks is bounded below by the next key.
   Top2 t;
   t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
-  {
-    const uint32_t c = (lane < 16) ? (k.x & cmask) : (k.y & cmask);
-    const uint32_t col = c * kChunk + (lane & 15u);
-    if (c < nchunks && col < pd.nI) {
-      t.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
-      t.i1 = col;
-    }
-  }
-  t = top2_warp_reduce(t);
-  bool ok = key_lower_bound(k.z, pd.eps_abs, gamma) > (double)t.d2;
-  if (!ok) {
+  bool ok = false;
+#pragma unroll
+  for (int stage = 0; stage < 3; ++stage) {
+    uint32_t c;
+    bool active = true;
+    if (stage == 0) c = (lane < 16) ? (key[0] & cmask) : (key[1] & cmask);
+    else if (stage == 1) { c = key[2] & cmask; active = lane < 16; }
+    else c = (lane < 16) ? (key[3] & cmask) : (key[4] & cmask);
     Top2 u;
     u.d1 = u.d2 = FLT_MAX; u.i1 = u.i2 = 0xffffffffu;
-    const uint32_t c = k.z & cmask;
     const uint32_t col = c * kChunk + (lane & 15u);
-    if (lane < 16 && c < nchunks && col < pd.nI) {
+    if (active && c < nchunks && col < pd.nI) {
       u.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
       u.i1 = col;
     }
     u = top2_warp_reduce(u);
     t = top2_merge(t, u);
-    ok = key_lower_bound(k.w, pd.eps_abs, gamma) > (double)t.d2;
-    if (lane == 0) atomicAdd(&counters[2], 1u);
+    const uint32_t bound_key = stage == 0 ? key[2] : (stage == 1 ? key[3] : key[5]);
+    ok = key_lower_bound(bound_key, pd.eps_abs, gamma, pack_rel) > (double)t.d2;
+    if (ok) break;
+    if (lane == 0 && stage < 2) atomicAdd(&counters[2 + stage], 1u);
   }
   if (lane == 0) {
     if (ok) {
@@ -296,18 +299,18 @@ __global__ void k_view_stats(const void* __restrict__ desc, int dtype, uint32_t 
   }
 }
 
-// Writes both operand matrices of a view.  Row layout (kp = pad16(dim) + 16 halves):
+// Writes both operand matrices of a view.  Row layout (kmain = pad16(dim); kp >= kmain + 16 halves,
+// zero padded to the row alignment):
 //   database role opD: [ a_0 .. a_{dim-1} 0.. | p0 p1 S0 S1 0 x12 ]      ||a||^2 ~= p0*S0 + p1*S1
 //   query role    opQ: [ -2a_0 .. -2a_{dim-1} 0.. | S0 S1 p0 p1 0 x12 ]
 // so that  opQ_row . opD_row' = ||a'||^2 + ||a||^2 - 2 a.a'   (the squared distance).
 // Padding rows of the database role get p0 = 65504 (they lose against every real row).
 __global__ void k_view_prepare(const void* __restrict__ desc, int dtype, uint32_t n, uint32_t n_pad,
-                               uint32_t dim, uint32_t kp, int e0, __half* __restrict__ opQ,
-                               __half* __restrict__ opD) {
+                               uint32_t dim, uint32_t kp, uint32_t kmain, int e0,
+                               __half* __restrict__ opQ, __half* __restrict__ opD) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_pad) return;
-  const uint32_t kmain = kp - kBiasCols;
   const float S0 = ldexpf(1.f, e0), S1 = ldexpf(1.f, e0 - 11);
   __half* q = opQ + (size_t)row * kp;
   __half* d = opD + (size_t)row * kp;
@@ -347,6 +350,10 @@ __global__ void k_view_prepare(const void* __restrict__ desc, int dtype, uint32_
     d[kmain + lane] = dv;
     q[kmain + lane] = qv;
   }
+  for (uint32_t k = kmain + kBiasCols + lane; k < kp; k += 32) {  // alignment padding of the row
+    d[k] = __float2half_rn(0.f);
+    q[k] = __float2half_rn(0.f);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,7 +371,7 @@ int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v) {
 int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0) {
   const int wpb = 8;
   k_view_prepare<<<(v.n_pad + wpb - 1) / wpb, wpb * 32, 0, w.stream>>>(v.d_desc, (int)v.dtype, v.n, v.n_pad,
-                                                                     v.dim, v.kp, e0, v.d_opQ, v.d_opD);
+                                                                     v.dim, v.kp, (uint32_t)pad_up((int)(v.dim ? v.dim : 16), 16), e0, v.d_opQ, v.d_opD);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

@@ -26,12 +26,15 @@ constexpr int kRowPad = 256;        // every view is padded to a multiple of thi
 constexpr int kBiasCols = 16;       // one UMMA K-step holding the norm terms
 constexpr int kChunk = 16;          // database columns summarised by one candidate key
 constexpr int kChunkBits = 12;      // low mantissa bits of a key that hold the chunk id
-constexpr int kNumKeys = 4;         // keys kept per query (3 candidate chunks + 1 bound)
+constexpr int kNumKeys = 6;         // keys kept per query (5 candidate chunks + 1 bound)
+constexpr int kKeyStride = 8;       // uint32 per query row in the key array (two 16-byte stores)
 constexpr int kMaxKBlocks = 4;      // Kp <= 256  (descriptor dim <= 240)
 constexpr uint32_t kMaxDbRowsTC = (1u << kChunkBits) * kChunk;  // 65536
 
 inline int pad_up(int x, int m) { return (x + m - 1) / m * m; }
-inline int operand_cols(int dim) { return pad_up(dim, 16) + kBiasCols; }  // Kp
+int operand_col_align();  // 16, or 64 (R3D_KP_ALIGN) to make operand rows 128-byte aligned
+inline int operand_ksteps(int dim) { return (pad_up(dim, 16) + kBiasCols) / 16; }
+inline int operand_cols(int dim) { return pad_up(pad_up(dim, 16) + kBiasCols, operand_col_align()); }  // Kp
 
 struct ViewDev {
   uint32_t n = 0, dim = 0, dtype = 0, n_pad = 0, kp = 0;
@@ -59,7 +62,7 @@ struct PairDesc {            // one entry per pair of a batch (device + host)
   uint32_t use_tc;           // 1: tensor-core candidates available, 0: exact scan only
   float eps_abs;             // absolute error bound of a candidate value vs the real-valued distance
   uint32_t slotI, slotJ;     // tensor-map slots of the two views
-  uint32_t pad_;
+  uint32_t chunk_bits;       // low mantissa bits of a key that hold the chunk id (<= kChunkBits)
   const void* descI;         // original descriptors of I / J (device)
   const void* descJ;
 };
@@ -100,6 +103,7 @@ struct r3d_ctx {
   std::vector<r3d::DeviceWorker> workers;
   std::string last_error;
   r3d_match_timing match_timing{};
+  uint64_t pending_h2d = 0;  // bytes uploaded since the last matching call
   r3d_filter_timing filter_timing{};
   int host_threads = 0;
 };
@@ -140,7 +144,7 @@ int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v);
 int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0);
 // tensor-core candidate kernel
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
-                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int grid_limit);
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int grid_limit);
 size_t l2_candidates_smem_bytes(int kp_cols);
 // exact re-rank + ratio
 int launch_rerank(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,

@@ -74,8 +74,9 @@ def main():
         Dp[:, :nI] = D
         cm = Dp.reshape(nq, npad // 16, 16).min(2)
         order = np.argsort(cm, 1)[:, :4]
-        kv = keys[:nq].view(np.float32)
-        kc = keys[:nq] & 0xFFF
+        bits = int(np.ceil(np.log2(npad // 16)))
+        kv = keys[:nq, :4].view(np.float32)
+        kc = keys[:nq, :4] & ((1 << bits) - 1)
         print("eps_abs", eps)
         print("first rows keys(val,chunk):", [(float(kv[0, t]), int(kc[0, t])) for t in range(4)])
         print("numpy  chunk mins         :", [(float(cm[0, order[0, t]]), int(order[0, t])) for t in range(4)])

@@ -94,13 +94,16 @@ def test_candidate_error_bound_holds(gpu_ctx):
     B = sc["descs"][1].astype(np.float64)
     D = (B * B).sum(1)[:, None] + (A * A).sum(1)[None, :] - 2 * B @ A.T
     cm = D.reshape(2048, 2048 // 16, 16).min(2)
-    kv = keys[:2048].view(np.float32).astype(np.float64)
-    kc = (keys[:2048] & 0xFFF).astype(np.int64)
+    bits = 7                                   # 2048 rows / 16 = 128 chunks
+    kv = keys[:2048, :6].view(np.float32).astype(np.float64)
+    kc = (keys[:2048, :6] & ((1 << bits) - 1)).astype(np.int64)
+    pack = 2.0 ** (bits - 23)
     true_at = np.take_along_axis(cm, kc, 1)
-    assert (np.abs(kv - true_at) <= eps + np.abs(kv) / 2048 + 1e-12).all()
-    # and the keys are the 4 smallest chunk minima up to that slack
-    srt = np.sort(cm, 1)[:, :4]
-    assert (np.abs(kv - srt) <= 2 * (eps + np.abs(srt) / 2048)).all()
+    assert (np.abs(kv - true_at) <= eps + np.abs(kv) * pack + 1e-12).all()
+    # and the keys are the 6 smallest chunk minima up to that slack
+    srt = np.sort(cm, 1)[:, :6]
+    assert (np.abs(kv - srt) <= 2 * (eps + np.abs(srt) * pack)).all()
+    assert (np.diff(kv, axis=1) >= 0).all()
 
 
 def test_full_size_properties_c2_slice(gpu_ctx, r3dlib):
