@@ -57,7 +57,8 @@ static void free_worker(DeviceWorker& w) {
   cudaSetDevice(w.device);
   for (auto& kv : w.views) free_view(kv.second);
   w.views.clear();
-  void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_matches, w.d_fb, w.d_nn, w.d_counters, w.d_tmapQ, w.d_tmapD};
+  void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_matches, w.d_fb, w.d_nn, w.d_counters, w.d_tmapQ, w.d_tmapD,
+                  w.d_cnt, w.d_slot, w.d_list, w.d_parts, w.d_list2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (w.h_counters) cudaFreeHost(w.h_counters);

@@ -119,13 +119,24 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
   return r;
 }
 
+// one lane of a converged warp (all 32 lanes must execute this)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (SM100 "version 1"):
 //   start address >> 4 | LBO (ignored for swizzled K-major) | SBO = 1024 B (8 rows x 128 B) |
 //   version = 1 | layout type = SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)kDescHi << 32) | (uint64_t)lo; }
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128.
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
 
@@ -203,75 +214,90 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, qphase = 0;
-      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const WorkItem wi = items[it];
-        const PairDesc pd = pairs[wi.pair];
-        const CUtensorMap* mq = tmapQ + pd.slotJ;
-        const CUtensorMap* md = tmapD + pd.slotI;
-        const uint32_t nboxes = (pd.nI_pad / kTileRows) * nkb;
-        // Database boxes do not depend on the query tiles: run the ring ahead (it fills as the
-        // previous item's MMAs retire) before blocking on the query buffer.
-        const uint32_t ahead = nboxes < n_stages ? nboxes : n_stages;
-        uint32_t b = 0, t = 0, kb = 0;
-        for (;;) {
-          if (b == ahead) {
-            mbar_wait(bar_qempty, qphase ^ 1u);  // previous item's MMAs no longer read the query tiles
-            qphase ^= 1u;
+    // The whole warp runs the control flow (warp-uniform); one elected lane issues the copies.
+    uint32_t stage = 0, phase = 0, qphase = 0;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem wi = items[it];
+      const PairDesc pd = pairs[wi.pair];
+      const CUtensorMap* mq = tmapQ + pd.slotJ;
+      const CUtensorMap* md = tmapD + pd.slotI;
+      const uint32_t nboxes = (pd.nI_pad / kTileRows) * nkb;
+      // Database boxes do not depend on the query tiles: run the ring ahead (it fills as the
+      // previous item's MMAs retire) before blocking on the query buffer.
+      const uint32_t ahead = nboxes < n_stages ? nboxes : n_stages;
+      uint32_t b = 0, t = 0, kb = 0;
+      for (;;) {
+        if (b == ahead) {
+          mbar_wait(bar_qempty, qphase ^ 1u);  // previous item's MMAs no longer read the query tiles
+          qphase ^= 1u;
+          if (elect_one()) {
             mbar_arrive_expect_tx(bar_qfull, kQB * nkb * kBoxBytes);
             for (uint32_t qb = 0; qb < (uint32_t)kQB; ++qb)
               for (uint32_t k2 = 0; k2 < nkb; ++k2)
                 tma_load_2d(q_base + (qb * nkb + k2) * kBoxBytes, mq, (int)(k2 * kKBlock),
                             (int)(wi.sb * kSuperRows + qb * kTileRows), bar_qfull);
           }
-          if (b == nboxes) break;
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+          __syncwarp();
+        }
+        if (b == nboxes) break;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(bar_full + 8 * stage, kBoxBytes);
           tma_load_2d(d_base + stage * kBoxBytes, md, (int)(kb * kKBlock), (int)(t * kTileRows),
                       bar_full + 8 * stage);
-          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
-          ++b;
-          if (++kb == nkb) { kb = 0; ++t; }
         }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        ++b;
+        if (++kb == nkb) { kb = 0; ++t; }
       }
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ======================================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
-      for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const WorkItem wi = items[it];
-        const PairDesc pd = pairs[wi.pair];
-        const uint32_t ntiles = pd.nI_pad / kTileRows;
-        mbar_wait(bar_qfull, qf);
-        qf ^= 1u;
+    // Warp-uniform control flow; the tcgen05 instructions are issued by one elected lane.  All
+    // descriptor words are uniform values (shared-memory offsets + loop counters).
+    uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
+    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const WorkItem wi = items[it];
+      const PairDesc pd = pairs[wi.pair];
+      const uint32_t ntiles = pd.nI_pad / kTileRows;
+      mbar_wait(bar_qfull, qf);
+      qf ^= 1u;
+      tc_fence_after();
+      for (uint32_t t = 0; t < ntiles; ++t) {
+        mbar_wait(bar_tempty + 8 * acc, accphase ^ 1u);  // epilogue drained this accumulator stage
         tc_fence_after();
-        for (uint32_t t = 0; t < ntiles; ++t) {
-          mbar_wait(bar_tempty + 8 * acc, accphase ^ 1u);  // epilogue drained this accumulator stage
+        const uint32_t d0 = tmem_base + (acc * kQB + 0) * kAccCols;
+        const uint32_t d1 = tmem_base + (acc * kQB + 1) * kAccCols;
+        uint32_t ks_left = ksteps;
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          for (uint32_t kb = 0; kb < nkb; ++kb) {
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
-            const uint32_t ks_here = (ksteps - kb * 4u) < 4u ? (ksteps - kb * 4u) : 4u;
-            for (uint32_t k = 0; k < ks_here; ++k) {
-              const uint64_t bdesc = make_smem_desc(d_base + stage * kBoxBytes + k * 32u);
+          if (elect_one()) {
+            const uint32_t b_lo = desc_lo(d_base + stage * kBoxBytes);
+            const uint32_t a0_lo = desc_lo(q_base + (0 * nkb + kb) * kBoxBytes);
+            const uint32_t a1_lo = desc_lo(q_base + (1 * nkb + kb) * kBoxBytes);
+            const uint32_t ks_here = ks_left < 4u ? ks_left : 4u;
 #pragma unroll
-              for (uint32_t qb = 0; qb < (uint32_t)kQB; ++qb) {
-                const uint64_t adesc = make_smem_desc(q_base + (qb * nkb + kb) * kBoxBytes + k * 32u);
-                tc_mma_f16(tmem_base + (acc * kQB + qb) * kAccCols, adesc, bdesc, kInstrDesc,
-                           (kb | k) != 0u ? 1u : 0u);
+            for (uint32_t k = 0; k < 4; ++k) {
+              if (k < ks_here) {  // +2 per K-step: 32 bytes inside the 128-byte swizzle row
+                const uint32_t accum = (kb | k) != 0u ? 1u : 0u;
+                tc_mma_f16(d0, make_desc(a0_lo + 2 * k), make_desc(b_lo + 2 * k), kInstrDesc, accum);
+                tc_mma_f16(d1, make_desc(a1_lo + 2 * k), make_desc(b_lo + 2 * k), kInstrDesc, accum);
               }
             }
             tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
-            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+            if (kb + 1 == nkb) tc_commit(bar_tfull + 8 * acc);  // accumulator stage complete -> epilogue
           }
-          tc_commit(bar_tfull + 8 * acc);      // accumulator stage complete -> epilogue
-          acc ^= 1u;
-          if (acc == 0) accphase ^= 1u;
+          __syncwarp();
+          ks_left -= 4u;
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(bar_qempty);                 // query tiles may be overwritten
+        acc ^= 1u;
+        if (acc == 0) accphase ^= 1u;
       }
+      if (elect_one()) tc_commit(bar_qempty);  // query tiles may be overwritten
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ======================================= epilogue =======================================

@@ -11,7 +11,9 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <thread>
 
 namespace r3d {
@@ -128,21 +130,39 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   r3d_match_timing& T = w.timing;
 
   // ---- batches ---------------------------------------------------------------------------------
-  const uint64_t kMaxRowsPerBatch = 48ull << 20;  // 48 Mi query rows -> 768 MiB of keys
+  // Batches bound the scratch memory and let the host de-duplication of batch b overlap the
+  // device work of batch b+1 (the reference's order-dependent std::set step stays on the host).
+  static const uint32_t kBatchPairs = []() {
+    const char* e = getenv("R3D_BATCH_PAIRS");
+    const int v = e ? atoi(e) : 0;
+    return (uint32_t)(v > 0 ? v : 192);
+  }();
+  const uint64_t kMaxRowsPerBatch = 24ull << 20;  // 24 Mi query rows -> 768 MiB of keys
+  std::vector<std::thread> post_threads;
+  struct Joiner {
+    std::vector<std::thread>& t;
+    ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
+  } joiner{post_threads};
+  std::atomic<int64_t> host_us{0};
+
   size_t b0 = 0;
   while (b0 < all.size()) {
     size_t b1 = b0;
     uint64_t rows = 0, qtotal = 0, n_items = 0;
-    uint32_t max_nJ = 0;
-    while (b1 < all.size() && (b1 - b0) < 32768 && (rows + all[b1].pd.nJ_pad <= kMaxRowsPerBatch || b1 == b0)) {
+    uint32_t max_nJ = 0, max_chunks = 0;
+    while (b1 < all.size() && (b1 - b0) < kBatchPairs && (rows + all[b1].pd.nJ_pad <= kMaxRowsPerBatch || b1 == b0)) {
       all[b1].pd.q_ofs = (uint32_t)rows;
       rows += all[b1].pd.nJ_pad;
       qtotal += all[b1].pd.nJ;
-      if (all[b1].pd.use_tc) n_items += all[b1].pd.nJ_pad / kSuperRows;
+      if (all[b1].pd.use_tc) {
+        n_items += all[b1].pd.nJ_pad / kSuperRows;
+        max_chunks = std::max(max_chunks, all[b1].pd.nI_pad / (uint32_t)kChunk);
+      }
       max_nJ = std::max(max_nJ, all[b1].pd.nJ);
       ++b1;
     }
     const uint32_t nb = (uint32_t)(b1 - b0);
+    const uint32_t cstride = max_chunks + 1;
     std::vector<PairDesc> hp(nb);
     for (uint32_t k = 0; k < nb; ++k) hp[k] = all[b0 + k].pd;
     std::vector<WorkItem> hitems;
@@ -150,18 +170,26 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     for (uint32_t k = 0; k < nb; ++k)
       if (hp[k].use_tc)
         for (uint32_t sb = 0; sb < hp[k].nJ_pad / kSuperRows; ++sb) hitems.push_back(WorkItem{k, sb});
+    const bool any_tc = !hitems.empty();
 
     if ((rc = ensure_capacity<PairDesc>(ctx, &w.d_pairs, &w.pairs_cap, nb))) return rc;
     if ((rc = ensure_capacity<WorkItem>(ctx, &w.d_items, &w.items_cap, std::max<size_t>(hitems.size(), 1)))) return rc;
     if ((rc = ensure_capacity<uint4>(ctx, &w.d_keys, &w.keys_cap, rows * (kKeyStride / 4)))) return rc;
     if ((rc = ensure_capacity<uint2>(ctx, &w.d_fb, &w.fb_cap, qtotal))) return rc;
+    if (any_tc) {
+      if ((rc = ensure_capacity<uint32_t>(ctx, &w.d_cnt, &w.cnt_cap, (size_t)nb * cstride))) return rc;
+      if ((rc = ensure_capacity<uint32_t>(ctx, &w.d_slot, &w.slot_cap, rows * 2))) return rc;
+      if ((rc = ensure_capacity<uint32_t>(ctx, &w.d_list, &w.list_cap, rows * 2))) return rc;
+      if ((rc = ensure_capacity<uint4>(ctx, &w.d_parts, &w.parts_cap, rows * 2))) return rc;
+      if ((rc = ensure_capacity<uint2>(ctx, &w.d_list2, &w.list2_cap, qtotal))) return rc;
+    }
     if (want_matches) {
       if ((rc = ensure_capacity<uint3>(ctx, &w.d_matches, &w.matches_cap, qtotal))) return rc;
     } else {
       if ((rc = ensure_capacity<float4>(ctx, &w.d_nn, &w.nn_cap, rows))) return rc;
     }
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
-    if (!hitems.empty())
+    if (any_tc)
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems.data(), hitems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(w.d_counters, 0, 16 * sizeof(uint32_t), w.stream));
     T.h2d_bytes += nb * sizeof(PairDesc) + hitems.size() * sizeof(WorkItem);
@@ -170,7 +198,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     float4* d_nn = want_matches ? nullptr : (float4*)w.d_nn;
 
     R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[0], w.stream));
-    if (!hitems.empty()) {
+    if (any_tc) {
       if ((rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items,
                                      (uint32_t)hitems.size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), 0))) return rc;
       T.kernel_launches += 1;
@@ -181,10 +209,14 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(keys_dbg->data(), w.d_keys, rows * (kKeyStride / 4) * sizeof(uint4), cudaMemcpyDeviceToHost, w.stream));
       R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
     }
-    if (!hitems.empty()) {
-      if ((rc = launch_rerank(ctx, w, (const PairDesc*)w.d_pairs, nb, max_nJ, (const uint32_t*)w.d_keys, dim, dtype,
-                              ratio2, w.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
-      T.kernel_launches += 1;
+    if (any_tc) {
+      if ((rc = launch_rerank_binned(ctx, w, (const PairDesc*)w.d_pairs, nb, max_nJ, cstride, (const uint32_t*)w.d_keys,
+                                     dim, dtype, ratio2, (uint32_t*)w.d_cnt, (uint32_t*)w.d_slot, (uint32_t*)w.d_list,
+                                     w.d_parts, w.d_counters, d_matches, (uint2*)w.d_list2, d_nn))) return rc;
+      if ((rc = launch_rerank_list(ctx, w, (const PairDesc*)w.d_pairs, (const uint32_t*)w.d_keys, (const uint2*)w.d_list2,
+                                   &w.d_counters[4], (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2,
+                                   w.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
+      T.kernel_launches += 6;
     }
     R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[2], w.stream));
     bool any_exact = false;
@@ -208,8 +240,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     const uint32_t n_matches = w.h_counters[0];
     T.queries += qtotal;
     T.fallback_queries += w.h_counters[1];
-    T.third_chunk_queries += w.h_counters[2];
-    T.fifth_chunk_queries += w.h_counters[3];
+    T.third_chunk_queries += w.h_counters[4];   // deferred by the binned stage A (-> stage B)
+    T.fifth_chunk_queries += w.h_counters[3];   // needed stage C
     T.d2h_bytes += 16 * sizeof(uint32_t);
 
     if (want_matches) {
@@ -226,27 +258,35 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
         T.d2h_bytes += bytes;
       }
-      const double t0 = now_ms();
-      // bucket by pair (counting sort), then per-pair sort + de-duplication on the thread pool
+      // bucket by pair (counting sort) out of the pinned buffer, then hand the batch to a host
+      // thread: per-pair sort + de-duplication run while the device works on the next batch
+      const double tb0 = now_ms();
       const uint3* hm = (const uint3*)w.h_matches;
-      std::vector<uint32_t> cnt(nb + 1, 0);
-      for (uint32_t k = 0; k < n_matches; ++k) cnt[hm[k].x + 1]++;
-      for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] += cnt[k];
-      std::vector<r3d_indmatch> bucket(n_matches);
+      auto cnt = std::make_shared<std::vector<uint32_t>>(nb + 1, 0u);
+      for (uint32_t k = 0; k < n_matches; ++k) (*cnt)[hm[k].x + 1]++;
+      for (uint32_t k = 0; k < nb; ++k) (*cnt)[k + 1] += (*cnt)[k];
+      auto bucket = std::make_shared<std::vector<r3d_indmatch>>(n_matches);
       {
-        std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1);
-        for (uint32_t k = 0; k < n_matches; ++k) bucket[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
+        std::vector<uint32_t> pos(cnt->begin(), cnt->end() - 1);
+        for (uint32_t k = 0; k < n_matches; ++k) (*bucket)[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
       }
+      host_us += (int64_t)((now_ms() - tb0) * 1e3);
       const bool cd = (flags & R3D_MATCH_NO_COORD_DEDUP) == 0;
-      parallel_for(ctx->host_threads, nb, [&](size_t k) {
-        if (cnt[k + 1] == cnt[k]) return;
-        std::vector<r3d_indmatch> v(bucket.begin() + cnt[k], bucket.begin() + cnt[k + 1]);
-        const ViewDev& vi = w.views.find(hp[k].I)->second;
-        const ViewDev& vj = w.views.find(hp[k].J)->second;
-        post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
-        results[all[b0 + k].src_index] = std::move(v);
+      auto hp_sh = std::make_shared<std::vector<PairDesc>>(std::move(hp));
+      const size_t base = b0;
+      const int nthreads = std::max(1, ctx->host_threads / 2);
+      post_threads.emplace_back([&, cnt, bucket, hp_sh, base, nb, cd, nthreads]() {
+        const double t0 = now_ms();
+        parallel_for(nthreads, nb, [&](size_t k) {
+          if ((*cnt)[k + 1] == (*cnt)[k]) return;
+          std::vector<r3d_indmatch> v(bucket->begin() + (*cnt)[k], bucket->begin() + (*cnt)[k + 1]);
+          const ViewDev& vi = w.views.find((*hp_sh)[k].I)->second;
+          const ViewDev& vj = w.views.find((*hp_sh)[k].J)->second;
+          post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
+          results[all[base + k].src_index] = std::move(v);
+        });
+        host_us += (int64_t)((now_ms() - t0) * 1e3);
       });
-      T.ms_host_post += now_ms() - t0;
     } else {
       nn_out->resize(rows);
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(nn_out->data(), w.d_nn, rows * sizeof(float4), cudaMemcpyDeviceToHost, w.stream));
@@ -255,6 +295,9 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     }
     b0 = b1;
   }
+  for (auto& t : post_threads) t.join();
+  post_threads.clear();
+  T.ms_host_post += (double)host_us.load() * 1e-3;
   return R3D_OK;
 }
 

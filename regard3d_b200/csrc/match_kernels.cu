@@ -7,157 +7,25 @@
 // (4-way unrolled; the metric the reference names at src/R3DComputeMatches.cpp:290-291), using
 // __fsub_rn/__fmul_rn/__fadd_rn so no FMA contraction can change a bit.
 #include "r3d_internal.cuh"
-
-#include <cfloat>
+#include "match_device.cuh"
 
 namespace r3d {
 
 // ------------------------------------------------------------------------------------------------
-// exact distance, upstream accumulation order
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float acc4(float acc, float d0, float d1, float d2, float d3) {
-  const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
-                            __fmul_rn(d3, d3));
-  return __fadd_rn(acc, s);
-}
-
-template <int DTYPE>
-__device__ __forceinline__ float exact_l2(const void* __restrict__ qrow, const void* __restrict__ drow,
-                                           uint32_t dim) {
-  float acc = 0.f;
-  if (DTYPE == 0) {
-    const float* q = (const float*)qrow;
-    const float* d = (const float*)drow;
-    uint32_t k = 0;
-    if ((dim & 3u) == 0) {
-      const float4* q4 = (const float4*)q;
-      const float4* d4 = (const float4*)d;
-      const uint32_t g = dim >> 2;
-#pragma unroll 4
-      for (uint32_t t = 0; t < g; ++t) {
-        const float4 a = q4[t];  // may live in shared memory
-        const float4 b = __ldg(d4 + t);
-        acc = acc4(acc, __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
-      }
-      k = dim;
-    } else {
-      for (; k + 3 < dim; k += 4)
-        acc = acc4(acc, __fsub_rn(q[k], d[k]), __fsub_rn(q[k + 1], d[k + 1]), __fsub_rn(q[k + 2], d[k + 2]),
-                   __fsub_rn(q[k + 3], d[k + 3]));
-    }
-    for (; k < dim; ++k) {
-      const float df = __fsub_rn(q[k], d[k]);
-      acc = __fadd_rn(acc, __fmul_rn(df, df));
-    }
-  } else {
-    const uint8_t* q = (const uint8_t*)qrow;
-    const uint8_t* d = (const uint8_t*)drow;
-    uint32_t k = 0;
-    if ((dim & 3u) == 0) {
-      const uint32_t* q4 = (const uint32_t*)q;
-      const uint32_t* d4 = (const uint32_t*)d;
-      const uint32_t g = dim >> 2;
-#pragma unroll 4
-      for (uint32_t t = 0; t < g; ++t) {
-        const uint32_t a = q4[t], b = __ldg(d4 + t);
-        const float d0 = (float)((int)(a & 255u) - (int)(b & 255u));
-        const float d1 = (float)((int)((a >> 8) & 255u) - (int)((b >> 8) & 255u));
-        const float d2 = (float)((int)((a >> 16) & 255u) - (int)((b >> 16) & 255u));
-        const float d3 = (float)((int)(a >> 24) - (int)(b >> 24));
-        acc = acc4(acc, d0, d1, d2, d3);
-      }
-      k = dim;
-    } else {
-      for (; k + 3 < dim; k += 4)
-        acc = acc4(acc, (float)((int)q[k] - (int)d[k]), (float)((int)q[k + 1] - (int)d[k + 1]),
-                   (float)((int)q[k + 2] - (int)d[k + 2]), (float)((int)q[k + 3] - (int)d[k + 3]));
-    }
-    for (; k < dim; ++k) {
-      const float df = (float)((int)q[k] - (int)d[k]);
-      acc = __fadd_rn(acc, __fmul_rn(df, df));
-    }
-  }
-  return acc;
-}
-
-__device__ __forceinline__ size_t row_bytes(int dtype, uint32_t dim) { return dtype == 0 ? (size_t)dim * 4 : (size_t)dim; }
-
-// lexicographic (value, index) "less" -- symmetric tie-break so butterfly merges agree on all lanes
-__device__ __forceinline__ bool vi_less(float a, uint32_t ia, float b, uint32_t ib) {
-  return (a < b) || (a == b && ia < ib);
-}
-
-struct Top2 {
-  float d1, d2;
-  uint32_t i1, i2;
-};
-
-__device__ __forceinline__ void top2_insert(Top2& t, float d, uint32_t i) {
-  if (vi_less(d, i, t.d1, t.i1)) {
-    t.d2 = t.d1; t.i2 = t.i1; t.d1 = d; t.i1 = i;
-  } else if (vi_less(d, i, t.d2, t.i2)) {
-    t.d2 = d; t.i2 = i;
-  }
-}
-
-__device__ __forceinline__ Top2 top2_merge(const Top2& a, const Top2& b) {
-  Top2 r;
-  if (vi_less(a.d1, a.i1, b.d1, b.i1)) {
-    r.d1 = a.d1; r.i1 = a.i1;
-    if (vi_less(a.d2, a.i2, b.d1, b.i1)) { r.d2 = a.d2; r.i2 = a.i2; } else { r.d2 = b.d1; r.i2 = b.i1; }
-  } else {
-    r.d1 = b.d1; r.i1 = b.i1;
-    if (vi_less(b.d2, b.i2, a.d1, a.i1)) { r.d2 = b.d2; r.i2 = b.i2; } else { r.d2 = a.d1; r.i2 = a.i1; }
-  }
-  return r;
-}
-
-__device__ __forceinline__ Top2 top2_warp_reduce(Top2 t) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    Top2 b;
-    b.d1 = __shfl_xor_sync(0xffffffffu, t.d1, o);
-    b.d2 = __shfl_xor_sync(0xffffffffu, t.d2, o);
-    b.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
-    b.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
-    t = top2_merge(t, b);
-  }
-  return t;
-}
-
-// Lower bound on the ORACLE-ORDER float distance of any database column whose chunk has packed
-// key `key` (see DESIGN.md "certification").
-__device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, double gamma, double pack_rel) {
-  const double kv = (double)__uint_as_float(key);
-  double lb = kv - fabs(kv) * pack_rel - (double)eps_abs;
-  if (lb > 0.0) lb = lb * (1.0 - gamma);
-  return lb;
-}
-
-__device__ __forceinline__ void emit_result(const PairDesc& pd, uint32_t pair, uint32_t q, const Top2& t,
-                                            float ratio2, uint32_t* counters, uint3* matches, float4* nn) {
-  if (nn) {
-    nn[pd.q_ofs + q] = make_float4(__uint_as_float(t.i1), __uint_as_float(t.i2), t.d1, t.d2);
-  }
-  if (matches && t.d1 < __fmul_rn(ratio2, t.d2)) {  // NNdistanceRatio: strict, float
-    const uint32_t slot = atomicAdd(&counters[0], 1u);
-    matches[slot] = make_uint3(pair, t.i1, q);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_rerank : one warp per (pair, query)
+// k_rerank : one warp per listed (pair, query): certification stages A, B, C
 // ------------------------------------------------------------------------------------------------
 template <int DTYPE>
 __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pairs,
-                                                const uint32_t* __restrict__ keys, uint32_t dim, float ratio2,
+                                                const uint32_t* __restrict__ keys, const uint2* __restrict__ list,
+                                                const uint32_t* __restrict__ list_count, uint32_t dim, float ratio2,
                                                 uint32_t* counters, uint3* matches, uint2* fallback, float4* nn) {
-  const uint32_t pair = blockIdx.y;
-  const PairDesc pd = pairs[pair];
-  if (!pd.use_tc) return;
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (q >= pd.nJ) return;
+  const uint32_t n_list = *list_count;
+  for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_list;
+       item += gridDim.x * (blockDim.x >> 5)) {
+  const uint2 pq = list[item];
+  const uint32_t pair = pq.x, q = pq.y;
+  const PairDesc pd = pairs[pair];
   const uint4 ka = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4));
   const uint4 kb = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4) + 1);
   const uint32_t key[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
@@ -201,6 +69,7 @@ __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pai
       const uint32_t slot = atomicAdd(&counters[1], 1u);
       fallback[slot] = make_uint2(pair, q);
     }
+  }
   }
 }
 
@@ -376,16 +245,17 @@ int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0) {
   return R3D_OK;
 }
 
-int launch_rerank(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
-                  const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2, uint32_t* d_counters,
-                  uint3* d_matches, uint2* d_fallback, float4* d_nn) {
-  if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
+int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys,
+                       const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
+                       float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn) {
+  if (max_list == 0) return R3D_OK;
   const int wpb = 8;
-  dim3 grid((max_nJ + wpb - 1) / wpb, n_pairs);
+  uint32_t grid = (max_list + wpb - 1) / wpb;
+  if (grid > (uint32_t)w.sm_count * 16u) grid = (uint32_t)w.sm_count * 16u;
   if (dtype == 0)
-    k_rerank<0><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+    k_rerank<0><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
   else
-    k_rerank<1><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+    k_rerank<1><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

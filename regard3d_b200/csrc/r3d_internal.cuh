@@ -90,6 +90,11 @@ struct DeviceWorker {
   void* d_matches = nullptr; size_t matches_cap = 0;
   void* d_fb = nullptr; size_t fb_cap = 0;
   void* d_nn = nullptr; size_t nn_cap = 0;
+  void* d_cnt = nullptr; size_t cnt_cap = 0;      // binned re-rank scratch
+  void* d_slot = nullptr; size_t slot_cap = 0;
+  void* d_list = nullptr; size_t list_cap = 0;
+  void* d_parts = nullptr; size_t parts_cap = 0;
+  void* d_list2 = nullptr; size_t list2_cap = 0;
   uint32_t* d_counters = nullptr;  // [0] match count, [1] fallback count, [2] third-chunk count
   uint32_t* h_counters = nullptr;  // pinned
   void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
@@ -147,9 +152,14 @@ int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
                          uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int grid_limit);
 size_t l2_candidates_smem_bytes(int kp_cols);
 // exact re-rank + ratio
-int launch_rerank(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,
-                  uint32_t max_nJ, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
-                  uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn);
+int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys,
+                       const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
+                       float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn);
+// binned stage A (rerank_binned.cu); cstride = max chunks per pair + 1
+int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
+                         uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
+                         uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
+                         uint3* d_matches, uint2* d_list2, float4* d_nn);
 // exact scan of listed queries
 int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
                       const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,

@@ -1,0 +1,228 @@
+// rerank_binned.cu -- exact re-rank of the candidate chunks, organised for data reuse.
+//
+// Stage A of the certification needs, for every query, the exact distances to the 2x16
+// database rows of its two best candidate chunks.  Done query-by-query that is 32 scattered row
+// reads per query (L2-bound: 18 KB per query at D=144).  Here the (query, chunk) incidences are
+// binned by chunk first, so one warp stages the 16 rows of a chunk in shared memory ONCE and
+// serves every query that selected it (~2*N_J/n_chunks of them):
+//   k_bin_count  : per (pair, chunk) histogram, remembers each incidence's slot
+//   k_bin_scan   : exclusive scan per pair
+//   k_bin_fill   : per-chunk query lists
+//   k_bin_rerank : warp per (pair, chunk): exact top-2 of the chunk for each listed query
+//   k_bin_merge  : thread per query: merge the two partial top-2s, certify against key[2],
+//                  ratio test + emit, or defer to k_rerank_list (stages B/C, then exact scan)
+// All distances are "exact" in the sense of match_kernels.cu (upstream float accumulation order).
+#include "r3d_internal.cuh"
+#include "match_device.cuh"
+
+namespace r3d {
+
+struct Part {  // partial top-2 of one (query, chunk)
+  float d1, d2;
+  uint32_t i1, i2;
+};
+
+__global__ void __launch_bounds__(256) k_bin_count(const PairDesc* __restrict__ pairs,
+                                                   const uint32_t* __restrict__ keys, uint32_t cstride,
+                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ slot) {
+  const uint32_t pair = blockIdx.y;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= pd.nJ) return;
+  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+  const uint2 k = __ldg((const uint2*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  uint32_t c0 = k.x & cmask, c1 = k.y & cmask;
+  if (c0 >= nchunks) c0 = 0;  // sentinel keys (fewer than 2 real chunks): any valid chunk keeps the
+  if (c1 >= nchunks) c1 = 0;  // bookkeeping regular; certification handles the rest
+  slot[(size_t)(pd.q_ofs + q) * 2 + 0] = atomicAdd(&cnt[(size_t)pair * cstride + c0], 1u);
+  slot[(size_t)(pd.q_ofs + q) * 2 + 1] = atomicAdd(&cnt[(size_t)pair * cstride + c1], 1u);
+}
+
+// in-place exclusive scan of cnt[pair][0..nchunks); one block per pair
+__global__ void __launch_bounds__(256) k_bin_scan(const PairDesc* __restrict__ pairs, uint32_t cstride,
+                                                  uint32_t* __restrict__ cnt) {
+  __shared__ uint32_t part[256];
+  const uint32_t pair = blockIdx.x;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  uint32_t* c = cnt + (size_t)pair * cstride;
+  const uint32_t per = (nchunks + 255u) / 256u;
+  const uint32_t b = threadIdx.x * per, e = min(b + per, nchunks);
+  uint32_t s = 0;
+  for (uint32_t i = b; i < e; ++i) s += c[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (uint32_t o = 1; o < 256; o <<= 1) {
+    uint32_t v = 0;
+    if (threadIdx.x >= o) v = part[threadIdx.x - o];
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;
+  for (uint32_t i = b; i < e; ++i) {
+    const uint32_t v = c[i];
+    c[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 255) c[nchunks] = part[255];  // total = end of the last chunk's list (cstride > nchunks)
+}
+
+__global__ void __launch_bounds__(256) k_bin_fill(const PairDesc* __restrict__ pairs,
+                                                  const uint32_t* __restrict__ keys, uint32_t cstride,
+                                                  const uint32_t* __restrict__ ofs, const uint32_t* __restrict__ slot,
+                                                  uint32_t* __restrict__ list) {
+  const uint32_t pair = blockIdx.y;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= pd.nJ) return;
+  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+  const uint2 k = __ldg((const uint2*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  uint32_t c0 = k.x & cmask, c1 = k.y & cmask;
+  if (c0 >= nchunks) c0 = 0;
+  if (c1 >= nchunks) c1 = 0;
+  uint32_t* l = list + (size_t)pd.q_ofs * 2;
+  l[ofs[(size_t)pair * cstride + c0] + slot[(size_t)(pd.q_ofs + q) * 2 + 0]] = q * 2u + 0u;
+  l[ofs[(size_t)pair * cstride + c1] + slot[(size_t)(pd.q_ofs + q) * 2 + 1]] = q * 2u + 1u;
+}
+
+// warp per (pair, chunk).  Shared memory: kBinWarps x 16 rows x row_stride bytes.
+constexpr int kBinWarps = 8;
+
+template <int DTYPE>
+__global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* __restrict__ pairs, uint32_t cstride,
+                                                               const uint32_t* __restrict__ ofs,
+                                                               const uint32_t* __restrict__ list, uint32_t dim,
+                                                               uint32_t row_stride, Part* __restrict__ parts) {
+  extern __shared__ __align__(16) unsigned char smem_rows[];
+  const uint32_t pair = blockIdx.y;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t chunk = blockIdx.x * kBinWarps + warp;
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  if (chunk >= nchunks) return;
+  const uint32_t* o = ofs + (size_t)pair * cstride;
+  const uint32_t beg = o[chunk];
+  const uint32_t end = o[chunk + 1];
+  if (beg == end) return;
+  const size_t rb = row_bytes(DTYPE, dim);
+  unsigned char* rows = smem_rows + (size_t)warp * kChunk * row_stride;
+  // stage the 16 rows (zero-fill beyond nI; those columns are masked below)
+  {
+    const uint32_t words = (uint32_t)(rb >> 2);  // rb is a multiple of 4 (checked by the launcher)
+    for (uint32_t r = 0; r < (uint32_t)kChunk; ++r) {
+      const uint32_t col = chunk * kChunk + r;
+      const uint32_t* src = (const uint32_t*)((const char*)pd.descI + (size_t)col * rb);
+      uint32_t* dst = (uint32_t*)(rows + (size_t)r * row_stride);
+      for (uint32_t wv = lane; wv < words; wv += 32) dst[wv] = (col < pd.nI) ? __ldg(src + wv) : 0u;
+    }
+  }
+  __syncwarp();
+  const uint32_t half = lane >> 4, r = lane & 15u;
+  const uint32_t col = chunk * kChunk + r;
+  const bool col_ok = col < pd.nI;
+  const uint32_t* l = list + (size_t)pd.q_ofs * 2;
+  const unsigned char* myrow = rows + (size_t)r * row_stride;
+  for (uint32_t e0 = beg; e0 < end; e0 += 2) {  // two list entries per iteration, one per half-warp
+    const uint32_t e = e0 + half;
+    const bool live = e < end;
+    uint32_t qs = 0;
+    if (live) qs = __ldg(l + e);
+    Top2 t;
+    t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
+    if (live && col_ok) {
+      const char* qrow = (const char*)pd.descJ + (size_t)(qs >> 1) * rb;
+      t.d1 = exact_l2_generic<DTYPE>(qrow, myrow, dim);
+      t.i1 = col;
+    }
+#pragma unroll
+    for (int sh = 8; sh >= 1; sh >>= 1) {  // reduce inside each half-warp
+      Top2 b;
+      b.d1 = __shfl_xor_sync(0xffffffffu, t.d1, sh);
+      b.d2 = __shfl_xor_sync(0xffffffffu, t.d2, sh);
+      b.i1 = __shfl_xor_sync(0xffffffffu, t.i1, sh);
+      b.i2 = __shfl_xor_sync(0xffffffffu, t.i2, sh);
+      t = top2_merge(t, b);
+    }
+    if (live && r == 0) {
+      Part p;
+      p.d1 = t.d1; p.d2 = t.d2; p.i1 = t.i1; p.i2 = t.i2;
+      parts[(size_t)(pd.q_ofs + (qs >> 1)) * 2 + (qs & 1u)] = p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ pairs,
+                                                   const uint32_t* __restrict__ keys, const Part* __restrict__ parts,
+                                                   uint32_t dim, float ratio2, uint32_t* counters, uint3* matches,
+                                                   uint2* list2, float4* nn) {
+  const uint32_t pair = blockIdx.y;
+  const PairDesc pd = pairs[pair];
+  if (!pd.use_tc) return;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= pd.nJ) return;
+  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+  const uint4 k = __ldg((const uint4*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
+  const Part a = parts[(size_t)(pd.q_ofs + q) * 2 + 0];
+  const Part b = parts[(size_t)(pd.q_ofs + q) * 2 + 1];
+  Top2 ta, tb;
+  ta.d1 = a.d1; ta.d2 = a.d2; ta.i1 = a.i1; ta.i2 = a.i2;
+  tb.d1 = b.d1; tb.d2 = b.d2; tb.i1 = b.i1; tb.i2 = b.i2;
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  // identical chunks (only possible through the sentinel remap) must not be merged twice
+  const bool dup = ((k.x & cmask) >= nchunks) || ((k.y & cmask) >= nchunks) || ((k.x & cmask) == (k.y & cmask));
+  bool ok = false;
+  Top2 t = ta;
+  if (!dup) {
+    t = top2_merge(ta, tb);
+    const double pack_rel = ldexp(1.0, (int)pd.chunk_bits - 23);
+    const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
+    ok = key_lower_bound(k.z, pd.eps_abs, gamma, pack_rel) > (double)t.d2;
+  }
+  if (ok) {
+    emit_result(pd, pair, q, t, ratio2, counters, matches, nn);
+  } else {
+    const uint32_t s = atomicAdd(&counters[4], 1u);
+    list2[s] = make_uint2(pair, q);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
+                         uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
+                         uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
+                         uint3* d_matches, uint2* d_list2, float4* d_nn) {
+  if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
+  const size_t rb = dtype == 0 ? (size_t)dim * 4 : (size_t)dim;
+  if (rb & 3) return fail(ctx, R3D_ERR_UNSUPPORTED, "binned re-rank needs row bytes % 4 == 0");
+  // row stride: 16-byte aligned and an odd multiple of 16 bytes, so the 16 rows of a chunk start in
+  // different banks for 128-bit shared loads
+  uint32_t row_stride = (uint32_t)((rb + 15) / 16 * 16);
+  if (((row_stride / 16) & 1u) == 0) row_stride += 16;
+  const size_t smem = (size_t)kBinWarps * kChunk * row_stride;
+  R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)n_pairs * cstride * sizeof(uint32_t), w.stream));
+  dim3 gq((max_nJ + 255) / 256, n_pairs);
+  k_bin_count<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot);
+  k_bin_scan<<<n_pairs, 256, 0, w.stream>>>(d_pairs, cstride, d_cnt);
+  k_bin_fill<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot, d_list);
+  dim3 gc((cstride + kBinWarps - 1) / kBinWarps, n_pairs);
+  if (dtype == 0) {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bin_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bin_rerank<0><<<gc, kBinWarps * 32, smem, w.stream>>>(d_pairs, cstride, d_cnt, d_list, dim, row_stride, (Part*)d_parts);
+  } else {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bin_rerank<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bin_rerank<1><<<gc, kBinWarps * 32, smem, w.stream>>>(d_pairs, cstride, d_cnt, d_list, dim, row_stride, (Part*)d_parts);
+  }
+  k_bin_merge<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, (const Part*)d_parts, dim, ratio2, d_counters, d_matches,
+                                        d_list2, d_nn);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+}  // namespace r3d
