@@ -43,26 +43,61 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
-static void free_view(ViewDev& v) {
-  if (v.d_desc) cudaFree(v.d_desc);
-  if (v.d_opQ) cudaFree(v.d_opQ);
-  if (v.d_opD) cudaFree(v.d_opD);
-  if (v.d_xy) cudaFree(v.d_xy);
-  if (v.d_stats) cudaFree(v.d_stats);
+void* pool_alloc(DeviceWorker& w, size_t bytes) {
+  bytes = (bytes + 255) / 256 * 256;
+  auto it = w.pool_free_blocks.lower_bound(bytes);
+  if (it != w.pool_free_blocks.end() && it->first <= bytes + bytes / 4 + 4096) {
+    void* p = it->second;
+    w.pool_free_blocks.erase(it);
+    return p;
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    // give cached blocks back to the driver and retry once
+    for (auto& kv : w.pool_free_blocks) { cudaFree(kv.second); w.pool_sizes.erase(kv.second); }
+    w.pool_free_blocks.clear();
+    if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  }
+  w.pool_sizes[p] = bytes;
+  return p;
+}
+
+void pool_release(DeviceWorker& w, void* p) {
+  if (!p) return;
+  auto it = w.pool_sizes.find(p);
+  if (it == w.pool_sizes.end()) { cudaFree(p); return; }
+  w.pool_free_blocks.insert({it->second, p});
+}
+
+static void free_view(DeviceWorker& w, ViewDev& v) {
+  pool_release(w, v.d_desc);
+  pool_release(w, v.d_opQ);
+  pool_release(w, v.d_opD);
+  pool_release(w, v.d_xy);
+  pool_release(w, v.d_stats);
   v = ViewDev();
 }
 
 static void free_worker(DeviceWorker& w) {
   if (w.device < 0) return;
   cudaSetDevice(w.device);
-  for (auto& kv : w.views) free_view(kv.second);
+  for (auto& kv : w.views) free_view(w, kv.second);
   w.views.clear();
-  void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_matches, w.d_fb, w.d_nn, w.d_counters, w.d_tmapQ, w.d_tmapD,
+  for (auto& kv : w.pool_sizes) cudaFree(kv.first);
+  w.pool_sizes.clear();
+  w.pool_free_blocks.clear();
+  void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_fb, w.d_nn, w.d_tmapQ, w.d_tmapD,
                   w.d_cnt, w.d_slot, w.d_list, w.d_parts, w.d_list2};
   for (void* p : ptrs)
     if (p) cudaFree(p);
-  if (w.h_counters) cudaFreeHost(w.h_counters);
-  if (w.h_matches) cudaFreeHost(w.h_matches);
+  for (auto& o : w.out) {
+    if (o.d_matches) cudaFree(o.d_matches);
+    if (o.d_counters) cudaFree(o.d_counters);
+    if (o.h_counters) cudaFreeHost(o.h_counters);
+    if (o.h_matches) cudaFreeHost(o.h_matches);
+    for (auto& e : o.ev)
+      if (e) cudaEventDestroy(e);
+  }
   if (w.stream) cudaStreamDestroy(w.stream);
   if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
   w = DeviceWorker();
@@ -210,9 +245,7 @@ int r3d_create(const int* device_ids, int n_devices, r3d_ctx** out) {
     w.sm_count = prop.multiProcessorCount;
     cudaSetDevice(id);
     if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc(&w.d_counters, 16 * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMallocHost(&w.h_counters, 16 * sizeof(uint32_t)) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&w.copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete ctx;
       return fail(nullptr, R3D_ERR_CUDA, "r3d_create: stream / counter allocation failed");
     }
@@ -236,7 +269,7 @@ int r3d_clear_regions(r3d_ctx* ctx) {
   for (auto& w : ctx->workers) {
     cudaSetDevice(w.device);
     cudaStreamSynchronize(w.stream);
-    for (auto& kv : w.views) free_view(kv.second);
+    for (auto& kv : w.views) free_view(w, kv.second);
     w.views.clear();
     w.view_slot.clear();
     w.e0_fixed = false;
@@ -256,7 +289,7 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
     auto it = w.views.find(view_id);
     if (it != w.views.end()) {
       R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
-      free_view(it->second);
+      free_view(w, it->second);
       w.views.erase(it);
     }
     ViewDev v;
@@ -264,13 +297,17 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
     v.n_pad = (uint32_t)pad_up((int)(n ? n : 1), kRowPad);
     v.kp = (uint32_t)operand_cols((int)(dim ? dim : 16));
     const size_t rb = dtype == R3D_F32 ? (size_t)dim * 4 : (size_t)dim;
-    R3D_CUDA_TRY(ctx, cudaMalloc(&v.d_desc, std::max<size_t>(rb * n, 16)));
-    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_opQ, (size_t)v.n_pad * v.kp * sizeof(__half)));
-    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_opD, (size_t)v.n_pad * v.kp * sizeof(__half)));
-    R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_stats, 4 * sizeof(float)));
+    v.d_desc = pool_alloc(w, std::max<size_t>(rb * n, 16));
+    v.d_opQ = (__half*)pool_alloc(w, (size_t)v.n_pad * v.kp * sizeof(__half));
+    v.d_opD = (__half*)pool_alloc(w, (size_t)v.n_pad * v.kp * sizeof(__half));
+    v.d_stats = (float*)pool_alloc(w, 4 * sizeof(float));
+    if (xy && n) v.d_xy = (float2*)pool_alloc(w, (size_t)n * sizeof(float2));
+    if (!v.d_desc || !v.d_opQ || !v.d_opD || !v.d_stats || (xy && n && !v.d_xy)) {
+      free_view(w, v);
+      return fail(ctx, R3D_ERR_NOMEM, "r3d_upload_regions: device allocation failed");
+    }
     if (n) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_desc, desc, rb * n, cudaMemcpyHostToDevice, w.stream));
     if (xy && n) {
-      R3D_CUDA_TRY(ctx, cudaMalloc((void**)&v.d_xy, (size_t)n * sizeof(float2)));
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_xy, xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, w.stream));
       v.h_xy.assign(xy, xy + 2 * (size_t)n);
       v.has_xy = true;

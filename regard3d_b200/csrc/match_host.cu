@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <memory>
+#include <mutex>
 #include <thread>
 
 namespace r3d {
@@ -125,27 +127,40 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   if (all.empty()) return R3D_OK;
   const int kp = operand_cols((int)dim);
 
-  EventTimer evt;
-  if (!evt.ok) return fail(ctx, R3D_ERR_CUDA, "cudaEventCreate failed");
   r3d_match_timing& T = w.timing;
+  std::mutex t_mutex;  // T is updated by the batch tail threads
+
+  // ---- output slots (double buffered) ------------------------------------------------------
+  for (int sl = 0; sl < 2; ++sl) {
+    OutSlot& o = w.out[sl];
+    if (!o.d_counters) {
+      R3D_CUDA_TRY(ctx, cudaMalloc(&o.d_counters, 16 * sizeof(uint32_t)));
+      R3D_CUDA_TRY(ctx, cudaMallocHost(&o.h_counters, 16 * sizeof(uint32_t)));
+      for (auto& e : o.ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
+    }
+  }
 
   // ---- batches ---------------------------------------------------------------------------------
-  // Batches bound the scratch memory and let the host de-duplication of batch b overlap the
-  // device work of batch b+1 (the reference's order-dependent std::set step stays on the host).
+  // Batches bound the scratch memory and let the device->host copy, the bucketing and the host
+  // de-duplication of batch b overlap the device work of batch b+1 (the reference's
+  // order-dependent std::set step stays on the host).  Kernels of consecutive batches are stream
+  // ordered; only the OUTPUT buffers (matches, counters) are double buffered.
   static const uint32_t kBatchPairs = []() {
     const char* e = getenv("R3D_BATCH_PAIRS");
     const int v = e ? atoi(e) : 0;
     return (uint32_t)(v > 0 ? v : 192);
   }();
   const uint64_t kMaxRowsPerBatch = 24ull << 20;  // 24 Mi query rows -> 768 MiB of keys
-  std::vector<std::thread> post_threads;
+  std::vector<std::thread> tails;
+  std::shared_future<void> slot_free[2];
+  std::atomic<int> tail_rc{R3D_OK};
   struct Joiner {
     std::vector<std::thread>& t;
     ~Joiner() { for (auto& x : t) if (x.joinable()) x.join(); }
-  } joiner{post_threads};
-  std::atomic<int64_t> host_us{0};
+  } joiner{tails};
 
   size_t b0 = 0;
+  uint32_t batch_no = 0;
   while (b0 < all.size()) {
     size_t b1 = b0;
     uint64_t rows = 0, qtotal = 0, n_items = 0;
@@ -163,17 +178,22 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     }
     const uint32_t nb = (uint32_t)(b1 - b0);
     const uint32_t cstride = max_chunks + 1;
-    std::vector<PairDesc> hp(nb);
-    for (uint32_t k = 0; k < nb; ++k) hp[k] = all[b0 + k].pd;
-    std::vector<WorkItem> hitems;
-    hitems.reserve(n_items);
+    auto hp = std::make_shared<std::vector<PairDesc>>(nb);
+    for (uint32_t k = 0; k < nb; ++k) (*hp)[k] = all[b0 + k].pd;
+    auto hitems = std::make_shared<std::vector<WorkItem>>();
+    hitems->reserve(n_items);
     for (uint32_t k = 0; k < nb; ++k)
-      if (hp[k].use_tc)
-        for (uint32_t sb = 0; sb < hp[k].nJ_pad / kSuperRows; ++sb) hitems.push_back(WorkItem{k, sb});
-    const bool any_tc = !hitems.empty();
+      if ((*hp)[k].use_tc)
+        for (uint32_t sb = 0; sb < (*hp)[k].nJ_pad / kSuperRows; ++sb) hitems->push_back(WorkItem{k, sb});
+    const bool any_tc = !hitems->empty();
+
+    const int sl = (int)(batch_no & 1u);
+    OutSlot& o = w.out[sl];
+    if (slot_free[sl].valid()) slot_free[sl].wait();  // batch b-2 has left this slot's buffers
+    if (tail_rc.load() != R3D_OK) break;
 
     if ((rc = ensure_capacity<PairDesc>(ctx, &w.d_pairs, &w.pairs_cap, nb))) return rc;
-    if ((rc = ensure_capacity<WorkItem>(ctx, &w.d_items, &w.items_cap, std::max<size_t>(hitems.size(), 1)))) return rc;
+    if ((rc = ensure_capacity<WorkItem>(ctx, &w.d_items, &w.items_cap, std::max<size_t>(hitems->size(), 1)))) return rc;
     if ((rc = ensure_capacity<uint4>(ctx, &w.d_keys, &w.keys_cap, rows * (kKeyStride / 4)))) return rc;
     if ((rc = ensure_capacity<uint2>(ctx, &w.d_fb, &w.fb_cap, qtotal))) return rc;
     if (any_tc) {
@@ -184,26 +204,27 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       if ((rc = ensure_capacity<uint2>(ctx, &w.d_list2, &w.list2_cap, qtotal))) return rc;
     }
     if (want_matches) {
-      if ((rc = ensure_capacity<uint3>(ctx, &w.d_matches, &w.matches_cap, qtotal))) return rc;
+      if ((rc = ensure_capacity<uint3>(ctx, &o.d_matches, &o.matches_cap, qtotal))) return rc;
     } else {
       if ((rc = ensure_capacity<float4>(ctx, &w.d_nn, &w.nn_cap, rows))) return rc;
     }
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp.data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
+    // (re)allocations above are synchronous w.r.t. the device: previously enqueued work is done
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp->data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
     if (any_tc)
-      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems.data(), hitems.size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
-    R3D_CUDA_TRY(ctx, cudaMemsetAsync(w.d_counters, 0, 16 * sizeof(uint32_t), w.stream));
-    T.h2d_bytes += nb * sizeof(PairDesc) + hitems.size() * sizeof(WorkItem);
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems->data(), hitems->size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(o.d_counters, 0, 16 * sizeof(uint32_t), w.stream));
+    uint64_t launches = 0;
 
-    uint3* d_matches = want_matches ? (uint3*)w.d_matches : nullptr;
+    uint3* d_matches = want_matches ? (uint3*)o.d_matches : nullptr;
     float4* d_nn = want_matches ? nullptr : (float4*)w.d_nn;
 
-    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[0], w.stream));
+    R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[0], w.stream));
     if (any_tc) {
       if ((rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items,
-                                     (uint32_t)hitems.size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), 0))) return rc;
-      T.kernel_launches += 1;
+                                     (uint32_t)hitems->size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), 0))) return rc;
+      launches += 1;
     }
-    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[1], w.stream));
+    R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[1], w.stream));
     if (keys_dbg) {
       keys_dbg->resize(rows * (kKeyStride / 4));
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(keys_dbg->data(), w.d_keys, rows * (kKeyStride / 4) * sizeof(uint4), cudaMemcpyDeviceToHost, w.stream));
@@ -212,92 +233,119 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     if (any_tc) {
       if ((rc = launch_rerank_binned(ctx, w, (const PairDesc*)w.d_pairs, nb, max_nJ, cstride, (const uint32_t*)w.d_keys,
                                      dim, dtype, ratio2, (uint32_t*)w.d_cnt, (uint32_t*)w.d_slot, (uint32_t*)w.d_list,
-                                     w.d_parts, w.d_counters, d_matches, (uint2*)w.d_list2, d_nn))) return rc;
+                                     w.d_parts, o.d_counters, d_matches, (uint2*)w.d_list2, d_nn))) return rc;
       if ((rc = launch_rerank_list(ctx, w, (const PairDesc*)w.d_pairs, (const uint32_t*)w.d_keys, (const uint2*)w.d_list2,
-                                   &w.d_counters[4], (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2,
-                                   w.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
-      T.kernel_launches += 6;
+                                   &o.d_counters[4], (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2,
+                                   o.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
+      launches += 6;
     }
-    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[2], w.stream));
+    R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[2], w.stream));
     bool any_exact = false;
-    for (uint32_t k = 0; k < nb; ++k) any_exact |= (hp[k].use_tc == 0);
+    for (uint32_t k = 0; k < nb; ++k) any_exact |= ((*hp)[k].use_tc == 0);
     if (any_exact) {
-      if ((rc = launch_fill_all_queries(ctx, w, (const PairDesc*)w.d_pairs, nb, (uint2*)w.d_fb, &w.d_counters[1]))) return rc;
-      T.kernel_launches += 1;
+      if ((rc = launch_fill_all_queries(ctx, w, (const PairDesc*)w.d_pairs, nb, (uint2*)w.d_fb, &o.d_counters[1]))) return rc;
+      launches += 1;
     }
-    if ((rc = launch_exact_scan(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_fb, &w.d_counters[1],
-                                (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, w.d_counters,
+    if ((rc = launch_exact_scan(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_fb, &o.d_counters[1],
+                                (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, o.d_counters,
                                 d_matches, d_nn))) return rc;
-    T.kernel_launches += 1;
-    R3D_CUDA_TRY(ctx, cudaEventRecord(evt.ev[3], w.stream));
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.h_counters, w.d_counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
-    R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
-    float ms;
-    cudaEventElapsedTime(&ms, evt.ev[0], evt.ev[1]); T.ms_candidates += ms;
-    cudaEventElapsedTime(&ms, evt.ev[1], evt.ev[2]); T.ms_rerank += ms;
-    cudaEventElapsedTime(&ms, evt.ev[2], evt.ev[3]); T.ms_fallback += ms;
-    cudaEventElapsedTime(&ms, evt.ev[0], evt.ev[3]); T.ms_device_total += ms;
-    const uint32_t n_matches = w.h_counters[0];
-    T.queries += qtotal;
-    T.fallback_queries += w.h_counters[1];
-    T.third_chunk_queries += w.h_counters[4];   // deferred by the binned stage A (-> stage B)
-    T.fifth_chunk_queries += w.h_counters[3];   // needed stage C
-    T.d2h_bytes += 16 * sizeof(uint32_t);
+    launches += 1;
+    R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[3], w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(o.h_counters, o.d_counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[4], w.stream));
 
-    if (want_matches) {
-      if (n_matches) {
-        const size_t bytes = (size_t)n_matches * sizeof(uint3);
-        if (w.h_matches_cap < bytes) {
-          if (w.h_matches) cudaFreeHost(w.h_matches);
-          w.h_matches = nullptr;
-          w.h_matches_cap = 0;
-          R3D_CUDA_TRY(ctx, cudaMallocHost(&w.h_matches, bytes + bytes / 2));
-          w.h_matches_cap = bytes + bytes / 2;
-        }
-        R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.h_matches, w.d_matches, bytes, cudaMemcpyDeviceToHost, w.stream));
-        R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
-        T.d2h_bytes += bytes;
-      }
-      // bucket by pair (counting sort) out of the pinned buffer, then hand the batch to a host
-      // thread: per-pair sort + de-duplication run while the device works on the next batch
-      const double tb0 = now_ms();
-      const uint3* hm = (const uint3*)w.h_matches;
-      auto cnt = std::make_shared<std::vector<uint32_t>>(nb + 1, 0u);
-      for (uint32_t k = 0; k < n_matches; ++k) (*cnt)[hm[k].x + 1]++;
-      for (uint32_t k = 0; k < nb; ++k) (*cnt)[k + 1] += (*cnt)[k];
-      auto bucket = std::make_shared<std::vector<r3d_indmatch>>(n_matches);
-      {
-        std::vector<uint32_t> pos(cnt->begin(), cnt->end() - 1);
-        for (uint32_t k = 0; k < n_matches; ++k) (*bucket)[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
-      }
-      host_us += (int64_t)((now_ms() - tb0) * 1e3);
-      const bool cd = (flags & R3D_MATCH_NO_COORD_DEDUP) == 0;
-      auto hp_sh = std::make_shared<std::vector<PairDesc>>(std::move(hp));
-      const size_t base = b0;
-      const int nthreads = std::max(1, ctx->host_threads / 2);
-      post_threads.emplace_back([&, cnt, bucket, hp_sh, base, nb, cd, nthreads]() {
-        const double t0 = now_ms();
-        parallel_for(nthreads, nb, [&](size_t k) {
-          if ((*cnt)[k + 1] == (*cnt)[k]) return;
-          std::vector<r3d_indmatch> v(bucket->begin() + (*cnt)[k], bucket->begin() + (*cnt)[k + 1]);
-          const ViewDev& vi = w.views.find((*hp_sh)[k].I)->second;
-          const ViewDev& vj = w.views.find((*hp_sh)[k].J)->second;
-          post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
-          results[all[base + k].src_index] = std::move(v);
-        });
-        host_us += (int64_t)((now_ms() - t0) * 1e3);
-      });
-    } else {
+    if (!want_matches) {  // r3d_search_neighbours / diagnostics: synchronous, single batch
       nn_out->resize(rows);
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(nn_out->data(), w.d_nn, rows * sizeof(float4), cudaMemcpyDeviceToHost, w.stream));
       R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
       T.d2h_bytes += rows * sizeof(float4);
+      T.kernel_launches += launches;
+      T.queries += qtotal;
+      T.fallback_queries += o.h_counters[1];
+      b0 = b1;
+      ++batch_no;
+      continue;
     }
+
+    // ---- tail of the batch on its own host thread -------------------------------------------
+    auto copied = std::make_shared<std::promise<void>>();
+    slot_free[sl] = copied->get_future().share();
+    const size_t base = b0;
+    const bool cd = (flags & R3D_MATCH_NO_COORD_DEDUP) == 0;
+    const int nthreads = std::max(1, ctx->host_threads / 2);
+    const uint64_t h2d_batch = nb * sizeof(PairDesc) + hitems->size() * sizeof(WorkItem);
+    tails.emplace_back([&, hp, hitems, copied, sl, nb, base, cd, nthreads, qtotal, launches, h2d_batch]() {
+      OutSlot& os = w.out[sl];
+      bool released = false;
+      auto release = [&]() { if (!released) { released = true; copied->set_value(); } };
+      auto bail = [&](const char* what, cudaError_t e) {
+        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        tail_rc.store(R3D_ERR_CUDA);
+        release();
+      };
+      cudaError_t e = cudaSetDevice(w.device);
+      if (e != cudaSuccess) return bail("cudaSetDevice", e);
+      e = cudaEventSynchronize(os.ev[4]);
+      if (e != cudaSuccess) return bail("batch kernels", e);
+      float ms_c = 0, ms_r = 0, ms_f = 0, ms_t = 0;
+      cudaEventElapsedTime(&ms_c, os.ev[0], os.ev[1]);
+      cudaEventElapsedTime(&ms_r, os.ev[1], os.ev[2]);
+      cudaEventElapsedTime(&ms_f, os.ev[2], os.ev[3]);
+      cudaEventElapsedTime(&ms_t, os.ev[0], os.ev[3]);
+      const uint32_t n_matches = os.h_counters[0];
+      const uint32_t c_fb = os.h_counters[1], c_b = os.h_counters[4], c_c = os.h_counters[3];
+      size_t bytes = (size_t)n_matches * sizeof(uint3);
+      if (n_matches) {
+        if (os.h_matches_cap < bytes) {
+          if (os.h_matches) cudaFreeHost(os.h_matches);
+          os.h_matches = nullptr;
+          os.h_matches_cap = 0;
+          e = cudaMallocHost(&os.h_matches, bytes + bytes / 2);
+          if (e != cudaSuccess) return bail("cudaMallocHost", e);
+          os.h_matches_cap = bytes + bytes / 2;
+        }
+        e = cudaMemcpyAsync(os.h_matches, os.d_matches, bytes, cudaMemcpyDeviceToHost, w.copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w.copy_stream);
+        if (e != cudaSuccess) return bail("match copy", e);
+      }
+      const double t0 = now_ms();
+      // bucket by pair (counting sort) out of the pinned buffer
+      const uint3* hm = (const uint3*)os.h_matches;
+      std::vector<uint32_t> cnt(nb + 1, 0u);
+      for (uint32_t k = 0; k < n_matches; ++k) cnt[hm[k].x + 1]++;
+      for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] += cnt[k];
+      std::vector<r3d_indmatch> bucket(n_matches);
+      {
+        std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1);
+        for (uint32_t k = 0; k < n_matches; ++k) bucket[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
+      }
+      release();  // the slot's device + pinned buffers may be reused by batch b+2
+      parallel_for(nthreads, nb, [&](size_t k) {
+        if (cnt[k + 1] == cnt[k]) return;
+        std::vector<r3d_indmatch> v(bucket.begin() + cnt[k], bucket.begin() + cnt[k + 1]);
+        const ViewDev& vi = w.views.find((*hp)[k].I)->second;
+        const ViewDev& vj = w.views.find((*hp)[k].J)->second;
+        post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
+        results[all[base + k].src_index] = std::move(v);
+      });
+      const double host_ms = now_ms() - t0;
+      std::lock_guard<std::mutex> lk(t_mutex);
+      T.ms_candidates += ms_c; T.ms_rerank += ms_r; T.ms_fallback += ms_f; T.ms_device_total += ms_t;
+      T.ms_host_post += host_ms;
+      T.kernel_launches += launches;
+      T.queries += qtotal;
+      T.fallback_queries += c_fb;
+      T.third_chunk_queries += c_b;
+      T.fifth_chunk_queries += c_c;
+      T.d2h_bytes += 16 * sizeof(uint32_t) + bytes;
+      T.h2d_bytes += h2d_batch;
+    });
     b0 = b1;
+    ++batch_no;
   }
-  for (auto& t : post_threads) t.join();
-  post_threads.clear();
-  T.ms_host_post += (double)host_us.load() * 1e-3;
+  for (auto& t : tails) t.join();
+  tails.clear();
+  if (tail_rc.load() != R3D_OK) return tail_rc.load();
   return R3D_OK;
 }
 

@@ -70,6 +70,14 @@ static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
 
 struct WorkItem { uint32_t pair; uint32_t sb; };  // sb: super-block (256 query rows) index
 
+struct OutSlot {  // double-buffered outputs of a matching batch
+  void* d_matches = nullptr; size_t matches_cap = 0;
+  uint32_t* d_counters = nullptr;  // [0] matches, [1] exact-scan list, [3] stage C, [4] deferred by stage A
+  uint32_t* h_counters = nullptr;  // pinned
+  void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 struct DeviceWorker {
   int device = -1;
   int sm_count = 0;
@@ -87,7 +95,11 @@ struct DeviceWorker {
   void* d_pairs = nullptr; size_t pairs_cap = 0;
   void* d_items = nullptr; size_t items_cap = 0;
   void* d_keys = nullptr; size_t keys_cap = 0;
-  void* d_matches = nullptr; size_t matches_cap = 0;
+  OutSlot out[2];
+  // size-bucketed cache of device blocks released by r3d_clear_regions / re-uploads: cudaMalloc and
+  // cudaFree synchronise the device and cost ~ms, the upload path must not pay them per view
+  std::multimap<size_t, void*> pool_free_blocks;
+  std::map<void*, size_t> pool_sizes;
   void* d_fb = nullptr; size_t fb_cap = 0;
   void* d_nn = nullptr; size_t nn_cap = 0;
   void* d_cnt = nullptr; size_t cnt_cap = 0;      // binned re-rank scratch
@@ -95,9 +107,6 @@ struct DeviceWorker {
   void* d_list = nullptr; size_t list_cap = 0;
   void* d_parts = nullptr; size_t parts_cap = 0;
   void* d_list2 = nullptr; size_t list2_cap = 0;
-  uint32_t* d_counters = nullptr;  // [0] match count, [1] fallback count, [2] third-chunk count
-  uint32_t* h_counters = nullptr;  // pinned
-  void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
   r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
 };
 
@@ -142,6 +151,8 @@ int ensure_capacity(r3d_ctx* ctx, void** p, size_t* cap, size_t need_elems) {
 }
 
 int prepare_views(r3d_ctx* ctx, DeviceWorker& w);
+void* pool_alloc(DeviceWorker& w, size_t bytes);  // nullptr on failure
+void pool_release(DeviceWorker& w, void* p);
 
 // ---- kernels (defined in the .cu files) --------------------------------------------------------
 // operand preparation

@@ -92,6 +92,10 @@ __global__ void __launch_bounds__(256) k_bin_fill(const PairDesc* __restrict__ p
 }
 
 // warp per (pair, chunk).  Shared memory: kBinWarps x 16 rows x row_stride bytes.
+// Mapping: LANE = QUERY (32 list entries per pass), the 16 database rows of the chunk are read
+// from shared memory as warp-wide broadcasts, and every lane carries 16 independent accumulators
+// (one per row) -- the strictly ordered float accumulation of the upstream metric then has 16-way
+// instruction-level parallelism instead of one dependent chain.
 constexpr int kBinWarps = 8;
 
 template <int DTYPE>
@@ -113,44 +117,80 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
   if (beg == end) return;
   const size_t rb = row_bytes(DTYPE, dim);
   unsigned char* rows = smem_rows + (size_t)warp * kChunk * row_stride;
-  // stage the 16 rows (zero-fill beyond nI; those columns are masked below)
-  {
-    const uint32_t words = (uint32_t)(rb >> 2);  // rb is a multiple of 4 (checked by the launcher)
-    for (uint32_t r = 0; r < (uint32_t)kChunk; ++r) {
+  {  // stage the 16 rows with 128-bit loads (rows beyond nI are zero; masked below)
+    const uint32_t vec_per_row = row_stride >> 4;
+    const uint32_t total = kChunk * vec_per_row;
+    for (uint32_t v = lane; v < total; v += 32) {
+      const uint32_t r = v / vec_per_row, c = v - r * vec_per_row;
       const uint32_t col = chunk * kChunk + r;
-      const uint32_t* src = (const uint32_t*)((const char*)pd.descI + (size_t)col * rb);
-      uint32_t* dst = (uint32_t*)(rows + (size_t)r * row_stride);
-      for (uint32_t wv = lane; wv < words; wv += 32) dst[wv] = (col < pd.nI) ? __ldg(src + wv) : 0u;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (col < pd.nI && (size_t)(c + 1) * 16 <= rb) {
+        val = __ldg((const uint4*)((const char*)pd.descI + (size_t)col * rb) + c);
+      } else if (col < pd.nI && (size_t)c * 16 < rb) {  // ragged tail of the row (rb % 16 != 0)
+        const unsigned char* src = (const unsigned char*)pd.descI + (size_t)col * rb + (size_t)c * 16;
+        unsigned char tmp[16];
+        for (int b = 0; b < 16; ++b) tmp[b] = ((size_t)c * 16 + b < rb) ? src[b] : 0;
+        val = *(const uint4*)tmp;
+      }
+      *(uint4*)(rows + (size_t)r * row_stride + (size_t)c * 16) = val;
     }
   }
   __syncwarp();
-  const uint32_t half = lane >> 4, r = lane & 15u;
-  const uint32_t col = chunk * kChunk + r;
-  const bool col_ok = col < pd.nI;
   const uint32_t* l = list + (size_t)pd.q_ofs * 2;
-  const unsigned char* myrow = rows + (size_t)r * row_stride;
-  for (uint32_t e0 = beg; e0 < end; e0 += 2) {  // two list entries per iteration, one per half-warp
-    const uint32_t e = e0 + half;
+  const uint32_t col0 = chunk * kChunk;
+  const uint32_t nvalid = (pd.nI > col0) ? min((uint32_t)kChunk, pd.nI - col0) : 0u;
+  for (uint32_t e0 = beg; e0 < end; e0 += 32) {
+    const uint32_t e = e0 + lane;
     const bool live = e < end;
-    uint32_t qs = 0;
-    if (live) qs = __ldg(l + e);
+    const uint32_t qs = live ? __ldg(l + e) : __ldg(l + beg);  // dead lanes shadow a valid entry
+    const char* qrow = (const char*)pd.descJ + (size_t)(qs >> 1) * rb;
+    float acc[kChunk];
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) acc[r] = 0.f;
+    if (DTYPE == 0) {
+      const uint32_t groups = dim >> 2;
+      const bool vec_ok = (rb & 15u) == 0;
+      for (uint32_t g = 0; g < groups; ++g) {
+        float4 qv;
+        if (vec_ok) qv = __ldg((const float4*)qrow + g);
+        else {
+          const float* qf = (const float*)qrow + 4 * g;
+          qv = make_float4(__ldg(qf), __ldg(qf + 1), __ldg(qf + 2), __ldg(qf + 3));
+        }
+#pragma unroll
+        for (int r = 0; r < kChunk; ++r) {
+          const float4 a = *(const float4*)(rows + (size_t)r * row_stride + (size_t)g * 16);  // broadcast
+          acc[r] = acc4(acc[r], __fsub_rn(qv.x, a.x), __fsub_rn(qv.y, a.y), __fsub_rn(qv.z, a.z), __fsub_rn(qv.w, a.w));
+        }
+      }
+      for (uint32_t k = groups * 4; k < dim; ++k) {
+        const float qk = __ldg((const float*)qrow + k);
+#pragma unroll
+        for (int r = 0; r < kChunk; ++r) {
+          const float df = __fsub_rn(qk, *(const float*)(rows + (size_t)r * row_stride + (size_t)k * 4));
+          acc[r] = __fadd_rn(acc[r], __fmul_rn(df, df));
+        }
+      }
+    } else {
+      const uint32_t groups = dim >> 2;  // rb % 4 == 0 is guaranteed by the launcher
+      for (uint32_t g = 0; g < groups; ++g) {
+        const uint32_t qv = __ldg((const uint32_t*)qrow + g);
+#pragma unroll
+        for (int r = 0; r < kChunk; ++r) {
+          const uint32_t a = *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4);
+          acc[r] = acc4(acc[r], (float)((int)(qv & 255u) - (int)(a & 255u)),
+                        (float)((int)((qv >> 8) & 255u) - (int)((a >> 8) & 255u)),
+                        (float)((int)((qv >> 16) & 255u) - (int)((a >> 16) & 255u)),
+                        (float)((int)(qv >> 24) - (int)(a >> 24)));
+        }
+      }
+    }
     Top2 t;
     t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
-    if (live && col_ok) {
-      const char* qrow = (const char*)pd.descJ + (size_t)(qs >> 1) * rb;
-      t.d1 = exact_l2_generic<DTYPE>(qrow, myrow, dim);
-      t.i1 = col;
-    }
 #pragma unroll
-    for (int sh = 8; sh >= 1; sh >>= 1) {  // reduce inside each half-warp
-      Top2 b;
-      b.d1 = __shfl_xor_sync(0xffffffffu, t.d1, sh);
-      b.d2 = __shfl_xor_sync(0xffffffffu, t.d2, sh);
-      b.i1 = __shfl_xor_sync(0xffffffffu, t.i1, sh);
-      b.i2 = __shfl_xor_sync(0xffffffffu, t.i2, sh);
-      t = top2_merge(t, b);
-    }
-    if (live && r == 0) {
+    for (int r = 0; r < kChunk; ++r)
+      if ((uint32_t)r < nvalid) top2_insert(t, acc[r], col0 + r);
+    if (live) {
       Part p;
       p.d1 = t.d1; p.d2 = t.d2; p.i1 = t.i1; p.i2 = t.i2;
       parts[(size_t)(pd.q_ofs + (qs >> 1)) * 2 + (qs & 1u)] = p;
@@ -201,10 +241,7 @@ int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
   const size_t rb = dtype == 0 ? (size_t)dim * 4 : (size_t)dim;
   if (rb & 3) return fail(ctx, R3D_ERR_UNSUPPORTED, "binned re-rank needs row bytes % 4 == 0");
-  // row stride: 16-byte aligned and an odd multiple of 16 bytes, so the 16 rows of a chunk start in
-  // different banks for 128-bit shared loads
-  uint32_t row_stride = (uint32_t)((rb + 15) / 16 * 16);
-  if (((row_stride / 16) & 1u) == 0) row_stride += 16;
+  const uint32_t row_stride = (uint32_t)((rb + 15) / 16 * 16);  // rows are only read as broadcasts
   const size_t smem = (size_t)kBinWarps * kChunk * row_stride;
   R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)n_pairs * cstride * sizeof(uint32_t), w.stream));
   dim3 gq((max_nJ + 255) / 256, n_pairs);
