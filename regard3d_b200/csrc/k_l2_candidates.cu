@@ -74,6 +74,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -169,7 +193,7 @@ struct SmemLayout {
 
 __global__ void __launch_bounds__(kThreads, 1)
 k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
-                const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
+                const CUtensorMap* __restrict__ tmapDh, const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
                 uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -188,11 +212,19 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
+  // Cluster of 2 (optional): both CTAs stream the SAME database image (their work items are two
+  // super-blocks of one pair); each CTA loads half of every database box and multicasts it to
+  // both, which halves the L2 -> shared-memory traffic, the measured limiter of this kernel.
+  const uint32_t ncta = cluster_nctarank();
+  const uint32_t crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << ncta) - 1u);
+  const uint32_t cluster_id = blockIdx.x / ncta;
+  const uint32_t n_clusters = gridDim.x / ncta;
 
   if (threadIdx.x == 0) {
     for (uint32_t s = 0; s < kMaxStages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, ncta);  // released by the MMA warps of every CTA in the cluster
     }
     mbar_init(bar_qfull, 1);
     mbar_init(bar_qempty, 1);
@@ -209,6 +241,7 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
   }
   tc_fence_before();
   __syncthreads();
+  if (ncta > 1) cluster_sync_all();  // peer barriers are initialised before any multicast can land
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -216,11 +249,12 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
     // ===================================== TMA producer =====================================
     // The whole warp runs the control flow (warp-uniform); one elected lane issues the copies.
     uint32_t stage = 0, phase = 0, qphase = 0;
-    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (uint32_t it = cluster_id * ncta + crank; it < n_items; it += n_clusters * ncta) {
       const WorkItem wi = items[it];
       const PairDesc pd = pairs[wi.pair];
+      const uint32_t sb = wi.sb & 0x7fffffffu;
       const CUtensorMap* mq = tmapQ + pd.slotJ;
-      const CUtensorMap* md = tmapD + pd.slotI;
+      const CUtensorMap* md = (ncta > 1 ? tmapDh : tmapD) + pd.slotI;
       const uint32_t nboxes = (pd.nI_pad / kTileRows) * nkb;
       // Database boxes do not depend on the query tiles: run the ring ahead (it fills as the
       // previous item's MMAs retire) before blocking on the query buffer.
@@ -235,16 +269,20 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
             for (uint32_t qb = 0; qb < (uint32_t)kQB; ++qb)
               for (uint32_t k2 = 0; k2 < nkb; ++k2)
                 tma_load_2d(q_base + (qb * nkb + k2) * kBoxBytes, mq, (int)(k2 * kKBlock),
-                            (int)(wi.sb * kSuperRows + qb * kTileRows), bar_qfull);
+                            (int)(sb * kSuperRows + qb * kTileRows), bar_qfull);
           }
           __syncwarp();
         }
         if (b == nboxes) break;
         mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
         if (elect_one()) {
-          mbar_arrive_expect_tx(bar_full + 8 * stage, kBoxBytes);
-          tma_load_2d(d_base + stage * kBoxBytes, md, (int)(kb * kKBlock), (int)(t * kTileRows),
-                      bar_full + 8 * stage);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, kBoxBytes);  // own half + the peer's half
+          if (ncta > 1)
+            tma_load_2d_mc(d_base + stage * kBoxBytes + crank * (kBoxBytes / 2), md, (int)(kb * kKBlock),
+                           (int)(t * kTileRows + crank * (kTileRows / 2)), bar_full + 8 * stage, cmask);
+          else
+            tma_load_2d(d_base + stage * kBoxBytes, md, (int)(kb * kKBlock), (int)(t * kTileRows),
+                        bar_full + 8 * stage);
         }
         __syncwarp();
         if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -257,7 +295,7 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
     // Warp-uniform control flow; the tcgen05 instructions are issued by one elected lane.  All
     // descriptor words are uniform values (shared-memory offsets + loop counters).
     uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
-    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (uint32_t it = cluster_id * ncta + crank; it < n_items; it += n_clusters * ncta) {
       const WorkItem wi = items[it];
       const PairDesc pd = pairs[wi.pair];
       const uint32_t ntiles = pd.nI_pad / kTileRows;
@@ -286,7 +324,8 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
                 tc_mma_f16(d1, make_desc(a1_lo + 2 * k), make_desc(b_lo + 2 * k), kInstrDesc, accum);
               }
             }
-            tc_commit(bar_empty + 8 * stage);  // frees the ring slot when these MMAs retire
+            if (ncta > 1) tc_commit_mc(bar_empty + 8 * stage, cmask);  // ring slot free in BOTH CTAs' view
+            else tc_commit(bar_empty + 8 * stage);                     // frees the ring slot when these MMAs retire
             if (kb + 1 == nkb) tc_commit(bar_tfull + 8 * acc);  // accumulator stage complete -> epilogue
           }
           __syncwarp();
@@ -305,7 +344,7 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
     const uint32_t qb = ew >> 2;
     const uint32_t lane_quarter = warp & 3u;  // TMEM lanes this warp may touch
     uint32_t acc = 0, accphase = 0;
-    for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+    for (uint32_t it = cluster_id * ncta + crank; it < n_items; it += n_clusters * ncta) {
       const WorkItem wi = items[it];
       const PairDesc pd = pairs[wi.pair];
       const uint32_t ntiles = pd.nI_pad / kTileRows;
@@ -342,6 +381,7 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
       }
+      if (wi.sb & 0x80000000u) continue;  // padding item (odd super-block count): nothing to store
       const uint32_t row = wi.sb * kSuperRows + qb * kTileRows + lane_quarter * 32u + lane;
       uint4 o0, o1;
       o0.x = __float_as_uint(key[0]); o0.y = __float_as_uint(key[1]);
@@ -356,6 +396,7 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
 
   tc_fence_before();
   __syncthreads();
+  if (ncta > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -370,19 +411,32 @@ size_t l2_candidates_smem_bytes(int kp_cols) {
 }
 
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
-                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int grid_limit) {
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int cluster) {
   if (n_items == 0) return R3D_OK;
   const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
   if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
   const int stages = nkb >= 4 ? 6 : kMaxStages;
   const size_t smem = l2_candidates_smem_bytes(kp_cols);
   R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_l2_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-  uint32_t grid = (uint32_t)w.sm_count;
-  if (grid_limit > 0 && (uint32_t)grid_limit < grid) grid = (uint32_t)grid_limit;
-  if (n_items < grid) grid = n_items;
-  k_l2_candidates<<<grid, kThreads, smem, w.stream>>>(w.d_tmapQ, w.d_tmapD, d_pairs, d_items, n_items, d_keys,
-                                                      (uint32_t)nkb, (uint32_t)ksteps, (uint32_t)stages);
-  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  if (cluster != 2) cluster = 1;
+  uint32_t grid = (uint32_t)w.sm_count / cluster * cluster;
+  const uint32_t need = (n_items + cluster - 1) / cluster * cluster;
+  if (need < grid) grid = need;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = w.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  R3D_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, k_l2_candidates, (const CUtensorMap*)w.d_tmapQ, (const CUtensorMap*)w.d_tmapD,
+                                       (const CUtensorMap*)w.d_tmapDh, d_pairs, d_items, n_items, d_keys, (uint32_t)nkb,
+                                       (uint32_t)ksteps, (uint32_t)stages));
   return R3D_OK;
 }
 

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <future>
@@ -82,6 +83,7 @@ struct EventTimer {
 static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs, uint64_t n_pairs, float ratio,
                            uint32_t flags, std::vector<std::vector<r3d_indmatch>>& results,
                            std::vector<float4>* nn_out, std::vector<uint4>* keys_dbg = nullptr) {
+  const double t_enter = now_ms();
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   int rc = prepare_views(ctx, w);
   if (rc) return rc;
@@ -181,10 +183,18 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     auto hp = std::make_shared<std::vector<PairDesc>>(nb);
     for (uint32_t k = 0; k < nb; ++k) (*hp)[k] = all[b0 + k].pd;
     auto hitems = std::make_shared<std::vector<WorkItem>>();
-    hitems->reserve(n_items);
+    hitems->reserve(n_items + nb);
+    static const int kCluster = []() {
+      const char* e = getenv("R3D_K1_CLUSTER");
+      return (e && atoi(e) == 1) ? 1 : 2;
+    }();
     for (uint32_t k = 0; k < nb; ++k)
-      if ((*hp)[k].use_tc)
-        for (uint32_t sb = 0; sb < (*hp)[k].nJ_pad / kSuperRows; ++sb) hitems->push_back(WorkItem{k, sb});
+      if ((*hp)[k].use_tc) {
+        const uint32_t nsb = (*hp)[k].nJ_pad / kSuperRows;
+        for (uint32_t sb = 0; sb < nsb; ++sb) hitems->push_back(WorkItem{k, sb});
+        // a 2-CTA cluster works on two super-blocks of ONE pair: pad odd counts with a no-store item
+        if (kCluster == 2 && (nsb & 1u)) hitems->push_back(WorkItem{k, 0x80000000u});
+      }
     const bool any_tc = !hitems->empty();
 
     const int sl = (int)(batch_no & 1u);
@@ -221,7 +231,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[0], w.stream));
     if (any_tc) {
       if ((rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items,
-                                     (uint32_t)hitems->size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), 0))) return rc;
+                                     (uint32_t)hitems->size(), (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), kCluster))) return rc;
       launches += 1;
     }
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[1], w.stream));
@@ -343,8 +353,12 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     b0 = b1;
     ++batch_no;
   }
+  const double t_launch_done = now_ms();
   for (auto& t : tails) t.join();
   tails.clear();
+  if (getenv("R3D_DEBUG_TIMING"))
+    fprintf(stderr, "[r3d] match_on_worker: launch loop %.2f ms, tail join %.2f ms\n", t_launch_done - t_enter,
+            now_ms() - t_launch_done);
   if (tail_rc.load() != R3D_OK) return tail_rc.load();
   return R3D_OK;
 }
@@ -359,6 +373,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
                     r3d_matches** out) {
   if (!ctx || !out || (n_pairs && !pairs)) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: bad arguments");
   *out = nullptr;
+  const double t_call = now_ms();
   const uint64_t h2d_uploads = ctx->pending_h2d;  // uploads since the previous call belong to this one
   ctx->pending_h2d = 0;
   for (auto& wk : ctx->workers) wk.timing = r3d_match_timing{};
@@ -435,6 +450,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
     m->m.insert(m->m.end(), entries[e].v->begin(), entries[e].v->end());
     m->ofs.push_back(m->m.size());
   }
+  if (getenv("R3D_DEBUG_TIMING")) fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms\n", now_ms() - t_call);
   *out = m;
   return R3D_OK;
 }

@@ -87,6 +87,7 @@ struct DeviceWorker {
   std::map<uint32_t, uint32_t> view_slot;
   CUtensorMap* d_tmapQ = nullptr;
   CUtensorMap* d_tmapD = nullptr;
+  CUtensorMap* d_tmapDh = nullptr;  // database role, 64-row boxes (2-CTA multicast halves)
   uint32_t tmap_cap = 0;
   // per-context scale exponent of the norm split (S0 = 2^e0, S1 = 2^(e0-11))
   int e0 = -3;
@@ -160,7 +161,7 @@ int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v);
 int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0);
 // tensor-core candidate kernel
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
-                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int grid_limit);
+                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int cluster);
 size_t l2_candidates_smem_bytes(int kp_cols);
 // exact re-rank + ratio
 int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys,

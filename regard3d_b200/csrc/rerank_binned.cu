@@ -117,22 +117,25 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
   if (beg == end) return;
   const size_t rb = row_bytes(DTYPE, dim);
   unsigned char* rows = smem_rows + (size_t)warp * kChunk * row_stride;
-  {  // stage the 16 rows with 128-bit loads (rows beyond nI are zero; masked below)
-    const uint32_t vec_per_row = row_stride >> 4;
+  if ((rb & 15u) == 0) {  // stage the 16 rows with 128-bit loads (rows beyond nI are zero; masked below)
+    const uint32_t vec_per_row = (uint32_t)(rb >> 4);
     const uint32_t total = kChunk * vec_per_row;
     for (uint32_t v = lane; v < total; v += 32) {
       const uint32_t r = v / vec_per_row, c = v - r * vec_per_row;
       const uint32_t col = chunk * kChunk + r;
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (col < pd.nI && (size_t)(c + 1) * 16 <= rb) {
-        val = __ldg((const uint4*)((const char*)pd.descI + (size_t)col * rb) + c);
-      } else if (col < pd.nI && (size_t)c * 16 < rb) {  // ragged tail of the row (rb % 16 != 0)
-        const unsigned char* src = (const unsigned char*)pd.descI + (size_t)col * rb + (size_t)c * 16;
-        unsigned char tmp[16];
-        for (int b = 0; b < 16; ++b) tmp[b] = ((size_t)c * 16 + b < rb) ? src[b] : 0;
-        val = *(const uint4*)tmp;
-      }
+      if (col < pd.nI) val = __ldg((const uint4*)((const char*)pd.descI + (size_t)col * rb) + c);
       *(uint4*)(rows + (size_t)r * row_stride + (size_t)c * 16) = val;
+    }
+  } else {  // rows are only 4-byte aligned (rb % 4 == 0 is guaranteed by the launcher)
+    const uint32_t w_per_row = (uint32_t)(rb >> 2);
+    const uint32_t total = kChunk * w_per_row;
+    for (uint32_t v = lane; v < total; v += 32) {
+      const uint32_t r = v / w_per_row, c = v - r * w_per_row;
+      const uint32_t col = chunk * kChunk + r;
+      uint32_t val = 0u;
+      if (col < pd.nI) val = __ldg((const uint32_t*)((const char*)pd.descI + (size_t)col * rb) + c);
+      *(uint32_t*)(rows + (size_t)r * row_stride + (size_t)c * 4) = val;
     }
   }
   __syncwarp();
