@@ -144,8 +144,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config():
-    return {"workload": "C2: %d images x %d feats, D=%d float32 unit-norm (LIOP-like), exhaustive %d pairs, ratio %.1f"
-                        % (N_IMAGES, N_FEATS, DIM, N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
+    return {"workload": "C2: %d images x %d feats, D=%d float32 (%s-like), exhaustive %d pairs, ratio %.1f"
+                        % (N_IMAGES, N_FEATS, DIM, KIND, N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
             "images": N_IMAGES, "feats_per_image": N_FEATS, "dim": DIM, "pairs": N_IMAGES * (N_IMAGES - 1) // 2,
             "parallelism": "pairs sharded per GPU, no collective",
             "l2_policy": "inputs (descriptors + fp16 operands, ~0.6 GB) exceed the 126 MB L2"}
@@ -158,7 +158,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dim", type=int, default=0, help="experiment only: 64 -> MSURF-like D=64 set")
+    ap.add_argument("--feats", type=int, default=0, help="experiment only")
+    ap.add_argument("--images", type=int, default=0, help="experiment only")
     args = ap.parse_args()
+    global DIM, KIND, N_FEATS, N_IMAGES
+    if args.dim == 64:
+        DIM, KIND = 64, "msurf"
+    elif args.dim == 128:
+        DIM, KIND = 128, "sift"
+    if args.feats:
+        N_FEATS = args.feats
+    if args.images:
+        N_IMAGES = args.images
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

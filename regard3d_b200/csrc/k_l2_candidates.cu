@@ -28,11 +28,13 @@
 // fill the 512 TMEM columns, so the MMAs of tile t+1 overlap the epilogue of tile t.
 #include "r3d_internal.cuh"
 
+#include <cstdlib>
+
 namespace r3d {
 
 namespace {
 
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (4 + kEpiWarps);
 constexpr uint32_t kBoxBytes = kTileRows * kKBlock * 2;  // 16384
@@ -403,11 +405,18 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
   }
 }
 
+static int ring_stages(int nkb) {
+  // as deep as the 227 KB of shared memory allow next to the resident query tiles
+  int stages = (int)((232448 - 2048 - (size_t)kQB * nkb * kBoxBytes) / kBoxBytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  const char* e = getenv("R3D_K1_STAGES");
+  if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e);
+  return stages;
+}
+
 size_t l2_candidates_smem_bytes(int kp_cols) {
   const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
-  int stages = kMaxStages;
-  if (nkb >= 4) stages = 6;
-  return 1024 + (size_t)(kQB * nkb + stages) * kBoxBytes + 8 * (2 * kMaxStages + 2 + 4) + 16;
+  return 1024 + (size_t)(kQB * nkb + ring_stages(nkb)) * kBoxBytes + 8 * (2 * kMaxStages + 2 + 4) + 16;
 }
 
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
@@ -415,7 +424,7 @@ int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   if (n_items == 0) return R3D_OK;
   const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
   if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
-  const int stages = nkb >= 4 ? 6 : kMaxStages;
+  const int stages = ring_stages(nkb);
   const size_t smem = l2_candidates_smem_bytes(kp_cols);
   R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_l2_candidates, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   if (cluster != 2) cluster = 1;

@@ -442,13 +442,26 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
     return a.I < b.I || (a.I == b.I && a.J < b.J);
   });
   r3d_matches* m = new r3d_matches();
-  m->ofs.push_back(0);
-  for (size_t e = 0; e < entries.size(); ++e) {
-    if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
-    m->pairs.push_back(entries[e].I);
-    m->pairs.push_back(entries[e].J);
-    m->m.insert(m->m.end(), entries[e].v->begin(), entries[e].v->end());
-    m->ofs.push_back(m->m.size());
+  {
+    std::vector<size_t> keep;
+    keep.reserve(entries.size());
+    for (size_t e = 0; e < entries.size(); ++e) {
+      if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
+      keep.push_back(e);
+    }
+    m->pairs.resize(2 * keep.size());
+    m->ofs.resize(keep.size() + 1);
+    m->ofs[0] = 0;
+    for (size_t k = 0; k < keep.size(); ++k) {
+      m->pairs[2 * k] = entries[keep[k]].I;
+      m->pairs[2 * k + 1] = entries[keep[k]].J;
+      m->ofs[k + 1] = m->ofs[k] + entries[keep[k]].v->size();
+    }
+    m->m.resize(m->ofs.back());
+    parallel_for(ctx->host_threads, keep.size(), [&](size_t k) {
+      const auto& v = *entries[keep[k]].v;
+      std::memcpy(m->m.data() + m->ofs[k], v.data(), v.size() * sizeof(r3d_indmatch));
+    });
   }
   if (getenv("R3D_DEBUG_TIMING")) fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms\n", now_ms() - t_call);
   *out = m;
