@@ -1,0 +1,44 @@
+// acransac.cuh -- shared declarations of the AC-RANSAC fundamental filter (host + device).
+#pragma once
+#include "r3d_internal.cuh"
+
+namespace r3d {
+
+struct AcPair {          // per image pair (device)
+  uint32_t pt_ofs;       // first point of this pair in x1/x2
+  uint32_t M;            // number of putative matches
+  uint32_t tbl_ofs;      // first entry of this pair's logc_n table
+  uint32_t pad_;
+  double max_thr;        // precision^2 * N2(0,0)^2
+  double logalpha0;      // log10(2 D / A / N2(0,0)), image J
+  double loge0;          // log10(MAX_MODELS * (M - 7))
+};
+
+struct AcHyp {           // one RANSAC iteration of one pair
+  uint32_t pair;
+  uint32_t sample[7];
+};
+
+struct AcScore {         // per (hypothesis, model)
+  double nfa;            // best NFA over k (inf if none)
+  double err;            // residual at the best k (errorMax)
+  uint32_t k;            // best k (number of inliers)
+  uint32_t count;        // residuals <= max_thr (classic-RANSAC phase of ACRANSAC)
+};
+
+struct AcInlierReq {
+  uint32_t pair;
+  uint32_t k;            // number of inliers wanted (prefix of the sorted residuals)
+  uint32_t out_ofs;
+  uint32_t hyp_model;    // hypothesis * 3 + model: where this round's F matrix lives on the device
+};
+
+int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                    const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels);
+int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                    const AcHyp* hyps, uint32_t n_hyp, const double* F, const uint32_t* nmodels, const float* logc_n,
+                    const float* logc_k, uint32_t cap, AcScore* scores);
+int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                      const AcInlierReq* reqs, uint32_t n_req, const double* F, uint32_t cap, uint32_t* out);
+
+}  // namespace r3d

@@ -1,0 +1,383 @@
+// acransac_host.cu -- host orchestration of the AC-RANSAC fundamental filter (r3d_filter_pairs).
+//
+// Replaces ImageCollectionGeometricFilter::Robust_model_estimation(GeometricFilter_FMatrix_AC(4.0,
+// 2048), putatives, false) + Get_geometric_matches() (src/R3DComputeMatches.cpp:2099-2115).
+//
+// ACRANSAC is sequential per pair: the sampling pool shrinks to the inlier set after
+// every improving model.  Between two pool replacements, however, the sample sequence depends only
+// on (RNG state, pool) -- not on the data.  So every active pair draws a batch of samples ahead on
+// the host (with the very std::mt19937 / uniform_int_distribution code of the CPU path -- the
+// distribution algorithm is implementation-defined, never re-implemented on the device), ALL
+// pairs' hypotheses are solved and scored in two launches, and a per-pair sequential scan replays
+// the state machine, discarding the speculative tail after a pool replacement.
+#include "acransac.cuh"
+#include "detmath.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <random>
+
+namespace r3d {
+
+namespace {
+
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct PairState {
+  uint32_t src;  // index in the putative map
+  uint32_t I, J, M;
+  uint32_t pt_ofs, tbl_ofs;
+  // ACRANSAC state
+  std::vector<uint32_t> vec_index;
+  std::mt19937 rng{std::mt19937::default_seed};
+  uint32_t iter = 0, nIter = 0, nIterReserve = 0;
+  bool ac_mode = false;
+  double minNFA = std::numeric_limits<double>::infinity();
+  double errorMax = std::numeric_limits<double>::infinity();
+  bool have_inliers = false;       // vec_inliers non-empty in the reference's sense
+  std::vector<uint32_t> inliers;   // host copy of the best model's inlier list (sorted by residual)
+  uint32_t best_k = 0;
+  // per-round bookkeeping
+  uint32_t hyp_ofs = 0, hyp_n = 0;
+  std::vector<uint32_t> snap_index;
+  std::mt19937 snap_rng;
+  uint32_t since_event = 0;
+  bool best_changed = false, event = false;
+  uint32_t best_hyp = 0, best_model = 0;
+  bool done = false;
+};
+
+// rand_sampling.hpp UniformSample(num_samples, rng, &vec_index, &sample)
+inline void uniform_sample7(std::mt19937& rng, std::vector<uint32_t>& vec_index, uint32_t* sample) {
+  const uint32_t last_idx = (uint32_t)vec_index.size() - 1;
+  for (uint32_t i = 0; i < 7; ++i) {
+    std::uniform_int_distribution<uint32_t> distribution(i, last_idx);
+    const uint32_t sample_idx = distribution(rng);
+    std::swap(vec_index[i], vec_index[sample_idx]);
+  }
+  for (uint32_t i = 0; i < 7; ++i) sample[i] = vec_index[i];
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t c = n + n / 2 + 64;
+    cudaError_t e = cudaMalloc((void**)&p, c * sizeof(T));
+    if (e == cudaSuccess) cap = c;
+    return e;
+  }
+};
+
+}  // namespace
+
+int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t max_iter, const r3d_matches* put,
+                   const r3d_view_info* views, uint32_t n_views, std::vector<std::vector<r3d_indmatch>>& result) {
+  R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+  r3d_filter_timing& T = ctx->filter_timing;
+  T = r3d_filter_timing{};
+  const double t_begin = now_ms();
+  const uint64_t P = put->pairs.size() / 2;
+  result.assign(P, {});
+  const uint32_t sizeSample = 7, MAX_MODELS = 3;
+
+  // ---- per pair set-up (kernel adaptor of SURVEY.md A.5: normalisation, logalpha0, tables) ----
+  std::vector<PairState> st;
+  std::vector<AcPair> hpairs;
+  std::vector<double2> hx1, hx2;
+  std::vector<float> hlogc_n;
+  uint32_t maxM = 0;
+  for (uint64_t p = 0; p < P; ++p) {
+    const uint32_t I = put->pairs[2 * p], J = put->pairs[2 * p + 1];
+    const uint32_t M = (uint32_t)(put->ofs[p + 1] - put->ofs[p]);
+    if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
+    if (I >= n_views || J >= n_views) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: view id outside views[]");
+    auto vi = w.views.find(I), vj = w.views.find(J);
+    if (vi == w.views.end() || vj == w.views.end() || !vi->second.has_xy || !vj->second.has_xy)
+      return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: positions of a view were not uploaded");
+    PairState s;
+    s.src = (uint32_t)p; s.I = I; s.J = J; s.M = M;
+    s.pt_ofs = (uint32_t)hx1.size();
+    s.tbl_ofs = (uint32_t)hlogc_n.size();
+    const int wI = (int)views[I].width, hI = (int)views[I].height, wJ = (int)views[J].width, hJ = (int)views[J].height;
+    const double s1 = 1.0 / std::sqrt((double)(wI * hI));
+    const double s2 = 1.0 / std::sqrt((double)(wJ * hJ));
+    const double c1x = (double)(-.5f * wI) * s1, c1y = -.5 * hI * s1;
+    const double c2x = (double)(-.5f * wJ) * s2, c2y = -.5 * hJ * s2;
+    const float* xyI = vi->second.h_xy.data();
+    const float* xyJ = vj->second.h_xy.data();
+    for (uint32_t k = 0; k < M; ++k) {
+      const r3d_indmatch m = put->m[put->ofs[p] + k];
+      if (m.i >= vi->second.n || m.j >= vj->second.n) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
+      const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
+      const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
+      hx1.push_back(make_double2(s1 * xi + c1x, s1 * yi + c1y));
+      hx2.push_back(make_double2(s2 * xj + c2x, s2 * yj + c2y));
+    }
+    AcPair ap;
+    ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
+    const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
+    ap.max_thr = precision * s2 * s2;
+    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+    const double Aarea = (double)wJ * (double)hJ;
+    ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
+    ap.loge0 = dm::log10_det((double)MAX_MODELS * (double)(M - sizeSample));
+    hpairs.push_back(ap);
+    hlogc_n.resize(hlogc_n.size() + M + 1);
+    s.vec_index.resize(M);
+    std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
+    s.nIterReserve = max_iter / 10;
+    s.nIter = max_iter - s.nIterReserve;
+    s.ac_mode = (precision == std::numeric_limits<double>::infinity());
+    maxM = std::max(maxM, M);
+    st.push_back(std::move(s));
+  }
+  if (st.empty()) return R3D_OK;
+  // log-combinatorial tables (float, upstream makelogcombi_n / makelogcombi_k).  logcombi(k,n) is a
+  // running float sum over i = 1..min(k,n-k): its partial sums ARE the entries for smaller k, so one
+  // O(n) pass reproduces the upstream O(n^2) table bit for bit.
+  std::vector<float> vlog10(maxM + 2);
+  for (uint32_t k = 0; k <= maxM + 1; ++k) vlog10[k] = std::log10((float)k);
+  std::vector<float> hlogc_k(maxM + 1, 0.f);
+  for (uint32_t n = 0; n <= maxM; ++n) {
+    uint32_t k = sizeSample;
+    if (k >= n) { hlogc_k[n] = 0.f; continue; }
+    if (n - k < k) k = n - k;
+    float r = 0.f;
+    for (uint32_t i = 1; i <= k; ++i) r += vlog10[n - i + 1] - vlog10[i];
+    hlogc_k[n] = r;
+  }
+  {
+    std::vector<float> pre;
+    for (const PairState& s : st) {
+      const uint32_t n = s.M;
+      pre.assign(n / 2 + 1, 0.f);
+      float r = 0.f;
+      for (uint32_t i = 1; i <= n / 2; ++i) {
+        r += vlog10[n - i + 1] - vlog10[i];
+        pre[i] = r;
+      }
+      float* t = hlogc_n.data() + s.tbl_ofs;
+      for (uint32_t k = 0; k <= n; ++k) t[k] = (k >= n || k == 0) ? 0.f : pre[std::min(k, n - k)];
+    }
+  }
+  uint32_t cap = 32;
+  while (cap < maxM) cap <<= 1;
+  if ((size_t)cap * 12 > 200 * 1024)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: more than 16384 putative matches in one pair");
+
+  // ---- device buffers -------------------------------------------------------------------------
+  DevBuf<AcPair> d_pairs;
+  DevBuf<double2> d_x1, d_x2;
+  DevBuf<float> d_logc_n, d_logc_k;
+  DevBuf<AcHyp> d_hyp;
+  DevBuf<double> d_F;
+  DevBuf<uint32_t> d_nm, d_inl;
+  DevBuf<AcScore> d_score;
+  DevBuf<AcInlierReq> d_req;
+  R3D_CUDA_TRY(ctx, d_pairs.ensure(hpairs.size()));
+  R3D_CUDA_TRY(ctx, d_x1.ensure(hx1.size()));
+  R3D_CUDA_TRY(ctx, d_x2.ensure(hx2.size()));
+  R3D_CUDA_TRY(ctx, d_logc_n.ensure(hlogc_n.size()));
+  R3D_CUDA_TRY(ctx, d_logc_k.ensure(hlogc_k.size()));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_pairs.p, hpairs.data(), hpairs.size() * sizeof(AcPair), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_x1.p, hx1.data(), hx1.size() * sizeof(double2), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_x2.p, hx2.data(), hx2.size() * sizeof(double2), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_n.p, hlogc_n.data(), hlogc_n.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_k.p, hlogc_k.data(), hlogc_k.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
+
+  cudaEvent_t ev[3];
+  for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 3; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+
+  std::vector<AcHyp> hhyp;
+  std::vector<AcScore> hscore;
+  std::vector<uint32_t> hnm, hinl;
+  std::vector<AcInlierReq> hreq;
+  std::vector<uint32_t> active(st.size());
+  std::iota(active.begin(), active.end(), 0u);
+  const uint32_t kMaxHypPerRound = 1u << 18;
+
+  while (!active.empty()) {
+    T.rounds++;
+    // ---- 1. draw a batch of samples ahead for every active pair -----------------------------
+    hhyp.clear();
+    uint32_t budget = std::max<uint32_t>(8u, kMaxHypPerRound / (uint32_t)active.size());
+    for (uint32_t a : active) {
+      PairState& s = st[a];
+      uint32_t B = std::min<uint32_t>(std::max<uint32_t>(8u, 2u * s.since_event), 128u);
+      B = std::min(B, budget);
+      B = std::min(B, s.nIter - s.iter);
+      s.snap_index = s.vec_index;
+      s.snap_rng = s.rng;
+      s.hyp_ofs = (uint32_t)hhyp.size();
+      s.hyp_n = B;
+      for (uint32_t b = 0; b < B; ++b) {
+        AcHyp h;
+        h.pair = a;
+        uniform_sample7(s.rng, s.vec_index, h.sample);
+        hhyp.push_back(h);
+      }
+    }
+    const uint32_t H = (uint32_t)hhyp.size();
+    T.hypotheses += H;
+    R3D_CUDA_TRY(ctx, d_hyp.ensure(H));
+    R3D_CUDA_TRY(ctx, d_F.ensure((size_t)H * 27));
+    R3D_CUDA_TRY(ctx, d_nm.ensure(H));
+    R3D_CUDA_TRY(ctx, d_score.ensure((size_t)H * 3));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_hyp.p, hhyp.data(), (size_t)H * sizeof(AcHyp), cudaMemcpyHostToDevice, w.stream));
+    // ---- 2. solve + score on the device -------------------------------------------------------
+    R3D_CUDA_TRY(ctx, cudaEventRecord(ev[0], w.stream));
+    int rc = launch_f7_solve(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p);
+    if (rc) return rc;
+    R3D_CUDA_TRY(ctx, cudaEventRecord(ev[1], w.stream));
+    rc = launch_f7_score(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p, d_logc_n.p, d_logc_k.p, cap, d_score.p);
+    if (rc) return rc;
+    R3D_CUDA_TRY(ctx, cudaEventRecord(ev[2], w.stream));
+    T.kernel_launches += 2;
+    hscore.resize((size_t)H * 3);
+    hnm.resize(H);
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hscore.data(), d_score.p, (size_t)H * 3 * sizeof(AcScore), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hnm.data(), d_nm.p, (size_t)H * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    float ms;
+    cudaEventElapsedTime(&ms, ev[0], ev[1]); T.ms_solve += ms;
+    cudaEventElapsedTime(&ms, ev[1], ev[2]); T.ms_score += ms;
+    const double t_host0 = now_ms();
+    // ---- 3. replay the ACRANSAC state machine over the batch ----------------------------------
+    hreq.clear();
+    uint32_t inl_total = 0;
+    for (uint32_t a : active) {
+      PairState& s = st[a];
+      s.best_changed = false;
+      s.event = false;
+      uint32_t consumed = s.hyp_n;
+      for (uint32_t it = 0; it < s.hyp_n; ++it) {
+        const uint32_t h = s.hyp_ofs + it;
+        bool better = false;
+        for (uint32_t mi = 0; mi < hnm[h]; ++mi) {
+          const AcScore& sc = hscore[(size_t)h * 3 + mi];
+          if (!s.ac_mode && (double)sc.count > 2.5 * sizeSample) s.ac_mode = true;
+          if (s.ac_mode && sc.nfa < s.minNFA) {
+            better = true;
+            s.minNFA = sc.nfa;
+            s.errorMax = sc.err;
+            s.best_k = sc.k;
+            s.best_hyp = h;
+            s.best_model = mi;
+            s.best_changed = true;
+            s.have_inliers = true;
+          }
+        }
+        const uint32_t iter_abs = s.iter + it;
+        if ((better && s.minNFA < 0) || (iter_abs + 1 == s.nIter && s.nIterReserve)) {
+          if (!s.have_inliers) {
+            ++s.nIter;
+            --s.nIterReserve;
+          } else {
+            s.event = true;
+            consumed = it + 1;
+            break;
+          }
+        }
+      }
+      if (consumed < s.hyp_n) {  // discard the speculative tail: rewind and replay the sampler
+        s.vec_index = s.snap_index;
+        s.rng = s.snap_rng;
+        uint32_t tmp[7];
+        for (uint32_t b = 0; b < consumed; ++b) uniform_sample7(s.rng, s.vec_index, tmp);
+      }
+      s.iter += consumed;
+      s.since_event = s.event ? 0 : s.since_event + consumed;
+      if (s.best_changed) {  // the best model's inlier list is needed now (event) or possibly later
+        AcInlierReq rq;
+        rq.pair = a; rq.k = s.best_k; rq.out_ofs = inl_total; rq.hyp_model = s.best_hyp * 3 + s.best_model;
+        hreq.push_back(rq);
+        inl_total += s.best_k;
+      }
+    }
+    // ---- 4. fetch the inlier lists of the new best models --------------------------------------
+    if (!hreq.empty()) {
+      // the F matrices of this round are still on the device (d_F); the kernel reads them there
+      R3D_CUDA_TRY(ctx, d_req.ensure(hreq.size()));
+      R3D_CUDA_TRY(ctx, d_inl.ensure(inl_total));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_req.p, hreq.data(), hreq.size() * sizeof(AcInlierReq), cudaMemcpyHostToDevice, w.stream));
+      rc = launch_f7_inliers(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_req.p, (uint32_t)hreq.size(), d_F.p, cap, d_inl.p);
+      if (rc) return rc;
+      T.kernel_launches += 1;
+      hinl.resize(inl_total);
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hinl.data(), d_inl.p, (size_t)inl_total * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+      for (const AcInlierReq& rq : hreq) {
+        PairState& s = st[rq.pair];
+        s.inliers.assign(hinl.begin() + rq.out_ofs, hinl.begin() + rq.out_ofs + rq.k);
+      }
+    }
+    // ---- 5. pool replacement, termination ---------------------------------------------------------
+    std::vector<uint32_t> next;
+    for (uint32_t a : active) {
+      PairState& s = st[a];
+      if (s.event) {
+        s.vec_index = s.inliers;  // ACRANSAC optimisation: draw samples among the best inlier set
+        if (s.nIterReserve) {
+          s.nIter = s.iter + s.nIterReserve;  // (iter + 1 + nIterReserve with the 0-based loop index)
+          s.nIterReserve = 0;
+        }
+      }
+      if (s.iter < s.nIter) next.push_back(a);
+      else s.done = true;
+    }
+    active.swap(next);
+    T.ms_host += now_ms() - t_host0;
+  }
+  // ---- result: GeometricFilter_FMatrix_AC::Robust_estimation keeps the pair iff #inliers > 7*2.5 ----
+  for (const PairState& s : st) {
+    if (!(s.minNFA < 0)) continue;  // "if (minNFA >= 0) vec_inliers.clear()"
+    if (!(s.inliers.size() > sizeSample * 2.5)) continue;
+    auto& out = result[s.src];
+    out.reserve(s.inliers.size());
+    for (uint32_t idx : s.inliers) out.push_back(put->m[put->ofs[s.src] + idx]);
+  }
+  T.ms_device_total = T.ms_solve + T.ms_score;
+  T.ms_host = now_ms() - t_begin - T.ms_device_total;
+  return R3D_OK;
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_iter, const r3d_matches* putative,
+                                const r3d_view_info* views, uint32_t n_views, r3d_matches** out) {
+  if (!ctx || !putative || !views || !out) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: bad arguments");
+  *out = nullptr;
+  if (model != R3D_MODEL_F)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: only the fundamental-matrix filter is implemented (E/H: SURVEY.md 8f)");
+  std::vector<std::vector<r3d_indmatch>> res;
+  int rc = filter_pairs_F(ctx, ctx->workers[0], precision_px, max_iter, putative, views, n_views, res);
+  if (rc) return rc;
+  r3d_matches* m = new r3d_matches();
+  m->ofs.push_back(0);
+  const uint64_t P = putative->pairs.size() / 2;
+  for (uint64_t p = 0; p < P; ++p) {
+    if (res[p].empty()) continue;  // pairs whose estimation failed disappear from the map
+    m->pairs.push_back(putative->pairs[2 * p]);
+    m->pairs.push_back(putative->pairs[2 * p + 1]);
+    m->m.insert(m->m.end(), res[p].begin(), res[p].end());
+    m->ofs.push_back(m->m.size());
+  }
+  *out = m;
+  return R3D_OK;
+}

@@ -1,0 +1,327 @@
+// acransac_kernels.cu -- device side of the a-contrario RANSAC fundamental-matrix filter.
+// COMPILED WITH --fmad=false (regard3d_b200/build.py): every double operation below rounds once,
+// exactly like the host arithmetic, so discrete decisions are reproducible (see detmath.cuh).
+//
+// Replaces the per-pair body of ImageCollectionGeometricFilter::Robust_model_estimation(
+// GeometricFilter_FMatrix_AC(4.0, 2048), ...) (src/R3DComputeMatches.cpp:2099-2115); upstream
+// semantics: SURVEY.md Appendix A.4-A.6.
+//   k_f7_solve   : one thread per hypothesis -- 7-point solver (<= 3 models)
+//   k_f7_score   : one block per (hypothesis, model) -- M symmetric-epipolar residuals, compaction of
+//                  those <= the precision bound, block bitonic sort on (residual, index) in shared
+//                  memory, NFA scan, argmin
+//   k_f7_inliers : one block per request -- the sorted inlier index list of one model
+#include "acransac.cuh"
+#include "detmath.cuh"
+
+#include <cfloat>
+
+namespace r3d {
+
+// ------------------------------------------------------------------------------------------------
+// numeric/poly.h SolveCubicPolynomial (closed form), evaluated with detmath
+// ------------------------------------------------------------------------------------------------
+__device__ int solve_cubic_monic(double a, double b, double c, double* x0, double* x1, double* x2) {
+  const double q = a * a - 3 * b;
+  const double r = 2 * a * a * a - 9 * a * b + 27 * c;
+  const double Q = q / 9;
+  const double R = r / 54;
+  const double Q3 = Q * Q * Q;
+  const double R2 = R * R;
+  const double CR2 = 729 * r * r;
+  const double CQ3 = 2916 * q * q * q;
+  if (R == 0 && Q == 0) {
+    *x0 = *x1 = *x2 = -a / 3;
+    return 3;
+  } else if (CR2 == CQ3) {
+    const double sqrtQ = sqrt(Q);
+    if (R > 0) {
+      *x0 = -2 * sqrtQ - a / 3;
+      *x1 = sqrtQ - a / 3;
+      *x2 = sqrtQ - a / 3;
+    } else {
+      *x0 = -sqrtQ - a / 3;
+      *x1 = -sqrtQ - a / 3;
+      *x2 = 2 * sqrtQ - a / 3;
+    }
+    return 3;
+  } else if (CR2 < CQ3) {
+    const double sqrtQ = sqrt(Q);
+    const double sqrtQ3 = sqrtQ * sqrtQ * sqrtQ;
+    const double theta = dm::acos_det(R / sqrtQ3);
+    const double norm = -2 * sqrtQ;
+    double r0 = norm * dm::cos_det(theta / 3) - a / 3;
+    double r1 = norm * dm::cos_det((theta + 2.0 * R3D_PI) / 3) - a / 3;
+    double r2 = norm * dm::cos_det((theta - 2.0 * R3D_PI) / 3) - a / 3;
+    double t;
+    if (r0 > r1) { t = r0; r0 = r1; r1 = t; }
+    if (r1 > r2) {
+      t = r1; r1 = r2; r2 = t;
+      if (r0 > r1) { t = r0; r0 = r1; r1 = t; }
+    }
+    *x0 = r0; *x1 = r1; *x2 = r2;
+    return 3;
+  }
+  const double sgnR = (R >= 0 ? 1 : -1);
+  const double A = -sgnR * dm::cbrt_det(fabs(R) + sqrt(R2 - Q3));
+  const double B = Q / A;
+  *x0 = A + B - a / 3;
+  return 1;
+}
+
+// 2-D nullspace of the 7x9 epipolar system by Gaussian elimination with complete pivoting +
+// Gram-Schmidt (the pencil F1 + x F2 is what matters; Eigen's JacobiSVD basis is not reproducible
+// across implementations anyway).
+__device__ bool nullspace_7x9(double (*A)[9], double* f1, double* f2) {
+  int colperm[9];
+  for (int j = 0; j < 9; ++j) colperm[j] = j;
+  for (int r = 0; r < 7; ++r) {
+    int pi = r, pj = r;
+    double best = fabs(A[r][r]);
+    for (int i = r; i < 7; ++i)
+      for (int j = r; j < 9; ++j) {
+        const double v = fabs(A[i][j]);
+        if (v > best) { best = v; pi = i; pj = j; }
+      }
+    if (!(best > 0.0)) return false;
+    if (pi != r)
+      for (int j = 0; j < 9; ++j) { const double t = A[r][j]; A[r][j] = A[pi][j]; A[pi][j] = t; }
+    if (pj != r) {
+      for (int i = 0; i < 7; ++i) { const double t = A[i][r]; A[i][r] = A[i][pj]; A[i][pj] = t; }
+      const int t = colperm[r]; colperm[r] = colperm[pj]; colperm[pj] = t;
+    }
+    for (int i = r + 1; i < 7; ++i) {
+      const double f = A[i][r] / A[r][r];
+      for (int j = r + 1; j < 9; ++j) A[i][j] = A[i][j] - f * A[r][j];
+      A[i][r] = 0.0;
+    }
+  }
+  double n[2][9];
+  for (int t = 0; t < 2; ++t) {
+    double z[9];
+    z[7] = (t == 1) ? 1.0 : 0.0;
+    z[8] = (t == 0) ? 1.0 : 0.0;
+    for (int r = 6; r >= 0; --r) {
+      double s = 0.0;
+      for (int j = r + 1; j < 9; ++j) s = s + A[r][j] * z[j];
+      z[r] = -s / A[r][r];
+    }
+    for (int k = 0; k < 9; ++k) n[t][colperm[k]] = z[k];
+  }
+  double nn = 0.0;
+  for (int k = 0; k < 9; ++k) nn = nn + n[0][k] * n[0][k];
+  nn = sqrt(nn);
+  for (int k = 0; k < 9; ++k) f1[k] = n[0][k] / nn;
+  double dp = 0.0;
+  for (int k = 0; k < 9; ++k) dp = dp + n[1][k] * f1[k];
+  double g[9];
+  for (int k = 0; k < 9; ++k) g[k] = n[1][k] - dp * f1[k];
+  double gn = 0.0;
+  for (int k = 0; k < 9; ++k) gn = gn + g[k] * g[k];
+  gn = sqrt(gn);
+  for (int k = 0; k < 9; ++k) f2[k] = g[k] / gn;
+  return true;
+}
+
+// SevenPointSolver::Solve, minimal case
+__device__ int seven_point(const double* x1, const double* x2, double* Fout) {
+  double A[7][9];
+  for (int i = 0; i < 7; ++i) {
+    const double x1x = x1[2 * i], x1y = x1[2 * i + 1], x2x = x2[2 * i], x2y = x2[2 * i + 1];
+    A[i][0] = x2x * x1x;
+    A[i][1] = x2x * x1y;
+    A[i][2] = x2x;
+    A[i][3] = x2y * x1x;
+    A[i][4] = x2y * x1y;
+    A[i][5] = x2y;
+    A[i][6] = x1x;
+    A[i][7] = x1y;
+    A[i][8] = 1.0;
+  }
+  double F1[9], F2[9];
+  if (!nullspace_7x9(A, F1, F2)) return 0;
+  const double a = F1[0], j = F2[0], b = F1[1], k = F2[1], c = F1[2], l = F2[2], d = F1[3], m = F2[3],
+               e = F1[4], n = F2[4], f = F1[5], o = F2[5], g = F1[6], p = F2[6], h = F1[7], q = F2[7],
+               i = F1[8], r = F2[8];
+  double P[4];
+  P[0] = a * e * i + b * f * g + c * d * h - a * f * h - b * d * i - c * e * g;
+  P[1] = a * e * r + a * i * n + b * f * p + b * g * o + c * d * q + c * h * m + d * h * l + e * i * j +
+         f * g * k - a * f * q - a * h * o - b * d * r - b * i * m - c * e * p - c * g * n - d * i * k -
+         e * g * l - f * h * j;
+  P[2] = a * n * r + b * o * p + c * m * q + d * l * q + e * j * r + f * k * p + g * k * o + h * l * m +
+         i * j * n - a * o * q - b * m * r - c * n * p - d * k * r - e * l * p - f * j * q - g * l * n -
+         h * j * o - i * k * m;
+  P[3] = j * n * r + k * o * p + l * m * q - j * o * q - k * m * r - l * n * p;
+  if (P[0] == 0.0) return 0;
+  double roots[3];
+  const int num_roots = solve_cubic_monic(P[2] / P[3], P[1] / P[3], P[0] / P[3], roots, roots + 1, roots + 2);
+  for (int kk = 0; kk < num_roots; ++kk)
+    for (int t = 0; t < 9; ++t) Fout[9 * kk + t] = F1[t] + roots[kk] * F2[t];
+  return num_roots;
+}
+
+__global__ void __launch_bounds__(128) k_f7_solve(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
+                                                  const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
+                                                  uint32_t n_hyp, double* __restrict__ F, uint32_t* __restrict__ nmodels) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hyp) return;
+  const AcHyp hy = hyps[h];
+  const AcPair pr = pairs[hy.pair];
+  double s1[14], s2[14], models[27];
+  for (int t = 0; t < 7; ++t) {
+    const double2 a = x1[pr.pt_ofs + hy.sample[t]];
+    const double2 b = x2[pr.pt_ofs + hy.sample[t]];
+    s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
+    s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
+  }
+  const int nm = seven_point(s1, s2, models);
+  nmodels[h] = (uint32_t)nm;
+  for (int t = 0; t < 9 * nm; ++t) F[(size_t)h * 27 + t] = models[t];
+}
+
+// SymmetricEpipolarDistanceError::Error
+__device__ __forceinline__ double sym_epi_error(const double* F, double x1x, double x1y, double x2x, double x2y) {
+  const double Fx0 = F[0] * x1x + F[1] * x1y + F[2];
+  const double Fx1 = F[3] * x1x + F[4] * x1y + F[5];
+  const double Fx2 = F[6] * x1x + F[7] * x1y + F[8];
+  const double Fty0 = F[0] * x2x + F[3] * x2y + F[6];
+  const double Fty1 = F[1] * x2x + F[4] * x2y + F[7];
+  const double yFx = x2x * Fx0 + x2y * Fx1 + Fx2;
+  return (yFx * yFx) * (1.0 / (Fx0 * Fx0 + Fx1 * Fx1) + 1.0 / (Fty0 * Fty0 + Fty1 * Fty1)) / 4.0;
+}
+
+__device__ __forceinline__ bool key_less(double ea, uint32_t ia, double eb, uint32_t ib) {
+  return (ea < eb) || (ea == eb && ia < ib);
+}
+
+// Compact the residuals <= max_thr of model F into shared memory and sort them ascending by
+// (residual, index).  Returns the count c; se/si hold the sorted keys in [0, c).
+__device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict__ x1, const double2* __restrict__ x2,
+                                     const double* Fm, double* se, uint32_t* si, uint32_t cap, uint32_t* s_count) {
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < pr.M; i += blockDim.x) {
+    const double2 a = x1[pr.pt_ofs + i];
+    const double2 b = x2[pr.pt_ofs + i];
+    const double e = sym_epi_error(Fm, a.x, a.y, b.x, b.y);
+    if (e <= pr.max_thr) {  // false for NaN
+      const uint32_t pos = atomicAdd(s_count, 1u);
+      if (pos < cap) { se[pos] = e; si[pos] = i; }
+    }
+  }
+  __syncthreads();
+  uint32_t c = *s_count;
+  if (c > cap) c = cap;
+  uint32_t p2 = 1;
+  while (p2 < c) p2 <<= 1;
+  for (uint32_t i = c + threadIdx.x; i < p2; i += blockDim.x) { se[i] = DBL_MAX; si[i] = 0xffffffffu; }
+  __syncthreads();
+  for (uint32_t size = 2; size <= p2; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
+        const uint32_t lo = (t / stride) * (stride << 1) + (t % stride);
+        const uint32_t hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const double ea = se[lo], eb = se[hi];
+        const uint32_t ia = si[lo], ib = si[hi];
+        const bool swap = up ? key_less(eb, ib, ea, ia) : key_less(ea, ia, eb, ib);
+        if (swap) { se[lo] = eb; se[hi] = ea; si[lo] = ib; si[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
+                                                  const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
+                                                  const double* __restrict__ F, const uint32_t* __restrict__ nmodels,
+                                                  const float* __restrict__ logc_n, const float* __restrict__ logc_k,
+                                                  uint32_t cap, AcScore* __restrict__ scores) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_count;
+  __shared__ double s_best_nfa[8];
+  __shared__ uint32_t s_best_k[8];
+  const uint32_t h = blockIdx.x / 3, mi = blockIdx.x % 3;
+  if (mi >= nmodels[h]) return;
+  const AcHyp hy = hyps[h];
+  const AcPair pr = pairs[hy.pair];
+  double* se = (double*)smem_raw;
+  uint32_t* si = (uint32_t*)(se + cap);
+  double Fm[9];
+  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)h * 27 + 9 * mi + t];
+  const uint32_t c = residuals_sorted(pr, x1, x2, Fm, se, si, cap, &s_count);
+  // bestNFA: k = sizeSample+1 .. c  (the upstream loop stops at the first residual > maxThreshold)
+  double best = DBL_MAX * 2.0;  // +inf
+  uint32_t best_k = 7;
+  const float* lcn = logc_n + pr.tbl_ofs;
+  for (uint32_t k = 8 + threadIdx.x; k <= c; k += blockDim.x) {
+    const double logalpha = pr.logalpha0 + 0.5 * dm::log10_det(se[k - 1] + (double)FLT_EPSILON);
+    const double nfa = pr.loge0 + logalpha * (double)(k - 7) + (double)lcn[k] + (double)logc_k[k];
+    if (nfa < best) { best = nfa; best_k = k; }  // ascending k per thread: first minimum is kept
+  }
+  // block argmin on (nfa, k)
+  for (int o = 16; o >= 1; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const uint32_t ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+    if (ob < best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+  }
+  if ((threadIdx.x & 31u) == 0) { s_best_nfa[threadIdx.x >> 5] = best; s_best_k[threadIdx.x >> 5] = best_k; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t w = 1; w < (blockDim.x >> 5); ++w)
+      if (s_best_nfa[w] < best || (s_best_nfa[w] == best && s_best_k[w] < best_k)) { best = s_best_nfa[w]; best_k = s_best_k[w]; }
+    AcScore sc;
+    sc.nfa = best;
+    sc.err = (best_k >= 8 && best_k <= c) ? se[best_k - 1] : 0.0;
+    sc.k = best_k;
+    sc.count = s_count;
+    scores[(size_t)h * 3 + mi] = sc;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
+                                                    const double2* __restrict__ x2, const AcInlierReq* __restrict__ reqs,
+                                                    const double* __restrict__ F, uint32_t cap, uint32_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_count;
+  const AcInlierReq rq = reqs[blockIdx.x];
+  const AcPair pr = pairs[rq.pair];
+  double* se = (double*)smem_raw;
+  uint32_t* si = (uint32_t*)(se + cap);
+  double Fm[9];
+  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)(rq.hyp_model / 3) * 27 + (size_t)(rq.hyp_model % 3) * 9 + t];
+  const uint32_t c = residuals_sorted(pr, x1, x2, Fm, se, si, cap, &s_count);
+  for (uint32_t i = threadIdx.x; i < rq.k && i < c; i += blockDim.x) out[rq.out_ofs + i] = si[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                    const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels) {
+  if (!n_hyp) return R3D_OK;
+  k_f7_solve<<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                    const AcHyp* hyps, uint32_t n_hyp, const double* F, const uint32_t* nmodels, const float* logc_n,
+                    const float* logc_k, uint32_t cap, AcScore* scores) {
+  if (!n_hyp) return R3D_OK;
+  const size_t smem = (size_t)cap * 12;
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_f7_score<<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+                      const AcInlierReq* reqs, uint32_t n_req, const double* F, uint32_t cap, uint32_t* out) {
+  if (!n_req) return R3D_OK;
+  const size_t smem = (size_t)cap * 12;
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_f7_inliers<<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+}  // namespace r3d

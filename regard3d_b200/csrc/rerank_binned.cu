@@ -153,18 +153,20 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
     if (DTYPE == 0) {
       const uint32_t groups = dim >> 2;
       const bool vec_ok = (rb & 15u) == 0;
+      auto load_q = [&](uint32_t g) -> float4 {
+        if (vec_ok) return __ldg((const float4*)qrow + g);
+        const float* qf = (const float*)qrow + 4 * g;
+        return make_float4(__ldg(qf), __ldg(qf + 1), __ldg(qf + 2), __ldg(qf + 3));
+      };
+      float4 qv = groups ? load_q(0) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (uint32_t g = 0; g < groups; ++g) {
-        float4 qv;
-        if (vec_ok) qv = __ldg((const float4*)qrow + g);
-        else {
-          const float* qf = (const float*)qrow + 4 * g;
-          qv = make_float4(__ldg(qf), __ldg(qf + 1), __ldg(qf + 2), __ldg(qf + 3));
-        }
+        const float4 qn = (g + 1 < groups) ? load_q(g + 1) : qv;  // prefetch: hide the global-load latency
 #pragma unroll
         for (int r = 0; r < kChunk; ++r) {
           const float4 a = *(const float4*)(rows + (size_t)r * row_stride + (size_t)g * 16);  // broadcast
           acc[r] = acc4(acc[r], __fsub_rn(qv.x, a.x), __fsub_rn(qv.y, a.y), __fsub_rn(qv.z, a.z), __fsub_rn(qv.w, a.w));
         }
+        qv = qn;
       }
       for (uint32_t k = groups * 4; k < dim; ++k) {
         const float qk = __ldg((const float*)qrow + k);

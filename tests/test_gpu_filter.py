@@ -1,0 +1,80 @@
+"""-m gpu: AC-RANSAC fundamental filter through the C ABI vs the CPU oracle: identical inlier
+sequences (same std::mt19937 stream, same decisions)."""
+import numpy as np
+import pytest
+
+from regard3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ctx, sc):
+    ctx.clear_regions()
+    for v, (d, x) in enumerate(zip(sc["descs"], sc["xys"])):
+        ctx.upload_regions(v, d, x)
+
+
+def _check(ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=2048):
+    put = r3dlib.Matches.from_csr(pairs, ofs, m)
+    got = ctx.filter_pairs(put, sc["widths"], sc["heights"], max_iter=max_iter).to_dict()
+    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m, max_iter=max_iter)
+    n_pairs_exp = 0
+    for k, (I, J) in enumerate(pairs):
+        e = fm[int(fo[k]):int(fo[k + 1])]
+        g = got.get((int(I), int(J)))
+        if len(e) == 0:
+            assert g is None
+            continue
+        n_pairs_exp += 1
+        assert g is not None, (I, J)
+        assert np.array_equal(g, e), "pair %s: inlier sequence differs" % ((I, J),)
+    assert len(got) == n_pairs_exp
+    return got
+
+
+def test_filter_equals_oracle_clean_scene(gpu_ctx, oracle, r3dlib):
+    sc = synth.make_scene(4, 2000, 64, "msurf", seed=31)
+    pairs = synth.exhaustive_pairs(4)
+    _setup(gpu_ctx, sc)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.6)
+    _check(gpu_ctx, oracle, r3dlib, sc, pairs, ofs, m)
+    t = gpu_ctx.filter_timing()
+    assert t["kernel_launches"] >= 2 and t["hypotheses"] > 0
+
+
+def test_filter_equals_oracle_with_outliers_and_failures(gpu_ctx, oracle, r3dlib):
+    sc = synth.make_scene(4, 1500, 64, "msurf", seed=32)
+    pairs = synth.exhaustive_pairs(4)
+    _setup(gpu_ctx, sc)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.8)
+    rng = np.random.default_rng(1)
+    m2 = m.copy()
+    # pair 0: 40 % gross outliers; pair 1: all shuffled (must fail); pair 2: only 12 matches
+    s0 = slice(int(ofs[0]), int(ofs[1]))
+    n0 = int(ofs[1] - ofs[0])
+    bad = rng.random(n0) < 0.4
+    j0 = m2["j"][s0].copy()
+    j0[bad] = rng.integers(0, 1500, bad.sum())
+    m2["j"][s0] = j0
+    s1 = slice(int(ofs[1]), int(ofs[2]))
+    m2["j"][s1] = rng.permutation(m2["j"][s1])
+    keep = np.ones(len(m2), bool)
+    keep[int(ofs[2]) + 12:int(ofs[3])] = False
+    new_ofs = np.zeros_like(ofs)
+    for k in range(len(pairs)):
+        new_ofs[k + 1] = new_ofs[k] + keep[int(ofs[k]):int(ofs[k + 1])].sum()
+    m2 = m2[keep]
+    got = _check(gpu_ctx, oracle, r3dlib, sc, pairs, new_ofs, m2)
+    assert (0, 2) not in got
+
+
+def test_filter_small_iteration_budget_and_tiny_pairs(gpu_ctx, oracle, r3dlib):
+    sc = synth.make_scene(3, 400, 32, "msurf", seed=33)
+    pairs = synth.exhaustive_pairs(3)
+    _setup(gpu_ctx, sc)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.9)
+    _check(gpu_ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=64)
+    # pairs with <= 7 putatives are skipped by ACRANSAC
+    small_ofs = np.array([0, 7, 7, 15], np.uint64)
+    small_m = np.concatenate([m[int(ofs[0]):int(ofs[0]) + 7], m[int(ofs[2]):int(ofs[2]) + 8]])
+    _check(gpu_ctx, oracle, r3dlib, sc, pairs, small_ofs, small_m)

@@ -1,0 +1,97 @@
+"""Oracle self-checks for the AC-RANSAC fundamental filter."""
+import math
+
+import numpy as np
+import pytest
+
+from regard3d_b200 import synth
+
+
+def _two_view(seed, n=600, outlier_frac=0.3, noise=0.5):
+    rng = np.random.default_rng(seed)
+    sc = synth.make_scene(2, 1, 8, "msurf", seed=seed, n_points=n)  # cameras only
+    X = rng.uniform([2, 2, 0], [8, 8, 4], size=(n, 3))
+    poses = sc["poses"]
+    xs = []
+    for c in range(2):
+        R = synth._rodrigues(poses[c, :3])
+        uv, _ = synth.project(R, poses[c, 3:], X, sc["f"], 1920, 1080)
+        xs.append(uv + noise * rng.standard_normal(uv.shape))
+    n_out = int(outlier_frac * n)
+    xs[1][:n_out] = rng.uniform([0, 0], [1920, 1080], size=(n_out, 2))
+    good = np.ones(n, bool)
+    good[:n_out] = False
+    return synth.round_sig(xs[0]).astype(np.float32).astype(np.float64), \
+        synth.round_sig(xs[1]).astype(np.float32).astype(np.float64), good
+
+
+def test_seven_point_nullspace_and_rank(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        x1 = rng.uniform(-0.5, 0.5, (7, 2))
+        x2 = rng.uniform(-0.5, 0.5, (7, 2))
+        Fs = oracle.seven_point(x1, x2)
+        assert 1 <= len(Fs) <= 3
+        for F in Fs:
+            r = [np.array([*x2[i], 1]) @ F @ np.array([*x1[i], 1]) for i in range(7)]
+            assert np.abs(r).max() < 1e-10 * max(1.0, np.abs(F).max())
+            assert abs(np.linalg.det(F)) < 1e-10 * max(1.0, np.abs(F).max() ** 3)
+        # the pencil agrees with numpy's SVD nullspace: every solution lies in span(V[-1], V[-2])
+        A = np.array([[x2[i, 0] * x1[i, 0], x2[i, 0] * x1[i, 1], x2[i, 0], x2[i, 1] * x1[i, 0], x2[i, 1] * x1[i, 1],
+                       x2[i, 1], x1[i, 0], x1[i, 1], 1.0] for i in range(7)])
+        V = np.linalg.svd(A)[2][-2:]
+        for F in Fs:
+            f = F.ravel()
+            resid = f - V.T @ (V @ f)
+            assert np.linalg.norm(resid) < 1e-9 * np.linalg.norm(f)
+
+
+def test_acransac_recovers_inliers(oracle):
+    xI, xJ, good = _two_view(3)
+    inl, F, info = oracle.acransac_F(xI, xJ, 1920, 1080, 1920, 1080)
+    assert info[0] < 0                      # meaningful (NFA < 1)
+    assert good[inl].mean() > 0.97          # precision
+    assert good[inl].sum() > 0.9 * good.sum()
+    assert 0.2 < info[1] < 4.0              # a-contrario threshold found below the 4 px bound
+    # epipolar residual of the un-normalised F on the inliers
+    h1 = np.c_[xI[inl], np.ones(len(inl))]
+    h2 = np.c_[xJ[inl], np.ones(len(inl))]
+    l = h1 @ F.T
+    d = np.abs((h2 * l).sum(1)) / np.hypot(l[:, 0], l[:, 1])
+    assert np.median(d) < 1.5
+    cv2 = pytest.importorskip("cv2")
+    _, mask = cv2.findFundamentalMat(xI, xJ, cv2.FM_RANSAC, 2.0, 0.999)
+    ov = (mask.ravel()[inl] > 0).mean()
+    assert ov > 0.85                        # overlap with an independent estimator (not equality)
+
+
+def test_acransac_rejects_pure_noise_and_small_sets(oracle):
+    rng = np.random.default_rng(5)
+    xI = rng.uniform([0, 0], [1920, 1080], (300, 2))
+    xJ = rng.uniform([0, 0], [1920, 1080], (300, 2))
+    inl, _, info = oracle.acransac_F(xI, xJ, 1920, 1080, 1920, 1080)
+    assert len(inl) == 0 and info[2] == 2048       # ran all iterations, nothing meaningful
+    inl, _, _ = oracle.acransac_F(xI[:7], xJ[:7], 1920, 1080, 1920, 1080)
+    assert len(inl) == 0                            # nData <= MINIMUM_SAMPLES
+
+
+def test_acransac_is_deterministic(oracle):
+    xI, xJ, _ = _two_view(8, n=400)
+    a = oracle.acransac_F(xI, xJ, 1920, 1080, 1920, 1080)[0]
+    b = oracle.acransac_F(xI, xJ, 1920, 1080, 1920, 1080)[0]
+    assert np.array_equal(a, b)                     # std::mt19937 default seed per call
+
+
+def test_filter_pairs_drops_failed_pairs(oracle):
+    sc = synth.make_scene(3, 1500, 64, "msurf", seed=21)
+    pairs = synth.exhaustive_pairs(3)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.6)
+    # corrupt pair (0,2): shuffle its second indices -> no consistent geometry
+    m2 = m.copy()
+    seg = slice(int(ofs[1]), int(ofs[2]))
+    rng = np.random.default_rng(0)
+    m2["j"][seg] = rng.permutation(m2["j"][seg])
+    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m2)
+    assert fo[1] - fo[0] > 0.8 * (ofs[1] - ofs[0])
+    assert fo[2] - fo[1] == 0                        # failed estimation -> pair disappears
+    assert fo[3] - fo[2] > 0.8 * (ofs[3] - ofs[2])
