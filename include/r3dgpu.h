@@ -209,6 +209,11 @@ int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out);
 int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, uint32_t* keys,
                              float* eps_abs);
 
+/* Diagnostics (runs on the host, no GPU needed): residual and analytic Jacobian (2 x 15: intrinsics
+ * 0..5, pose 6..11, point 12..14) of one observation, as the BA kernels evaluate them. */
+int r3d_debug_ba_jacobian(const double* intr, const double* pose, const double* X, const double* obs,
+                          double* r, double* J);
+
 #ifdef __cplusplus
 }
 #endif

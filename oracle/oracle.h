@@ -105,6 +105,9 @@ typedef struct {
 
 int orc_bundle_adjust(orc_ba_problem* p, const orc_ba_options* o, orc_ba_summary* s,
                       double* cost_trace /* max_iterations+1 or null */);
+/* residual (2) and Jacobian (2 x 15: intrinsics 0..5, pose 6..11, point 12..14) of one observation
+ * by forward-mode autodiff -- test hook that pins the GPU's analytic derivatives. */
+void orc_ba_jacobian(const double* intr, const double* pose, const double* X, const double* obs, double* r, double* J);
 /* OpenMVGHelper::calculateResiduals twin: |residual| per coordinate, 2 per obs. */
 void orc_ba_residuals(const orc_ba_problem* p, double* res /* n_obs x 2 */);
 

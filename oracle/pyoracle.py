@@ -284,5 +284,13 @@ def ba_residuals(p):
     return res
 
 
+def ba_jacobian(intr, pose, X, obs):
+    intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
+    r = np.zeros(2)
+    J = np.zeros((2, 15))
+    lib().orc_ba_jacobian(_p(intr), _p(pose), _p(X), _p(obs), _p(r), _p(J))
+    return r, J
+
+
 def num_threads():
     return lib().orc_num_threads()

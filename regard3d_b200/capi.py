@@ -23,7 +23,7 @@ EXPORTS = [
     "r3d_matches_total", "r3d_matches_get_pair", "r3d_matches_from_csr", "r3d_free_matches",
     "r3d_save_matches_txt", "r3d_load_matches_txt", "r3d_filter_pairs", "r3d_ba_default_options",
     "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
-    "r3d_get_filter_timing", "r3d_debug_candidate_keys",
+    "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
 ]
 
 
@@ -195,6 +195,15 @@ class Matches:
         if rc:
             raise R3DError(rc, "r3d_matches_from_csr")
         return Matches(h)
+
+
+def debug_ba_jacobian(intr, pose, X, obs):
+    """Host evaluation of the analytic BA model (no GPU needed)."""
+    intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
+    r = np.zeros(2)
+    J = np.zeros((2, 15))
+    lib().r3d_debug_ba_jacobian(_p(intr), _p(pose), _p(X), _p(obs), _p(r), _p(J))
+    return r, J
 
 
 class Context:

@@ -1,0 +1,712 @@
+// ba.cu -- bundle adjustment on the GPU: Levenberg-Marquardt with a point Schur complement.
+//
+// Replaces openMVG::sfm::Bundle_Adjustment_Ceres::Adjust as reached from the SfM engines' Process()
+// (src/threads/R3DTriangulationThread.cpp:441, :512, :250); algorithm restated in SURVEY.md A.7 and
+// mirrored by oracle/oracle_ba.cpp (Ceres' trust-region LM, Jacobi scaling, Huber corrector,
+// SPARSE_SCHUR).  Everything is FP64.  Per LM iteration:
+//   k_ba_eval      one thread per observation: residual, analytic Jacobian, Huber corrector ->
+//                  gradient and diag(J^T J) (atomics), cost (block reduction)
+//   k_ba_schur     one WARP per 3-D point: stages the point's observation Jacobians in shared memory,
+//                  V = sum Jp^T Jp + D^2 (warp-shuffle reduction), V^-1, then the block pairs
+//                  S[a,b] -= W_a V^-1 W_b^T and rhs[a] += W_a V^-1 g_p are spread over the lanes
+//                  (atomicAdd into the dense reduced camera system, upper-triangular block form;
+//                  the intrinsic-intrinsic block is pre-reduced per CTA in shared memory)
+//   k_chol_*       blocked dense Cholesky of the reduced system + triangular solves
+//   k_ba_backsub   one thread per point: delta_p = V^-1 (-g_p - W^T delta_B)
+//   k_ba_update    x + scale*delta -> candidate parameters, ||dx||, ||x||, model cost change
+//   k_ba_cost      cost at the candidate
+// The Jacobian is recomputed where it is needed (300 flop per observation) instead of being stored:
+// the path is bound by the observation stream, not by arithmetic.
+#include "r3d_internal.cuh"
+#include "ba_model.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+namespace r3d {
+namespace ba {
+
+constexpr int kMaxObsPerPoint = 64;  // shared-memory staging of one point's observations
+constexpr int kSchurWarps = 8;
+constexpr int kObsDoubles = 12 + 12 + 6 + 2;  // Jc, Jg, Jp, r
+
+struct Dev {
+  uint32_t n_cams, n_pts, n_intr, nB, refine_intr;
+  uint64_t n_obs;
+  double huber_a;
+  double *poses, *intr, *pts;              // current parameters
+  double *poses_new, *intr_new, *pts_new;  // candidate
+  const uint32_t *obs_cam, *obs_pt, *cam_intr;
+  const double2* obs_xy;
+  const uint32_t *pt_ofs, *pt_obs;         // point -> observation CSR
+  double *scale, *gu, *du, *g, *diag, *delta;  // nparam each (u = unscaled accumulators)
+  double *S, *rhs, *Vinv;
+  double* scal;                            // [0] cost [1] model_cost_change*2 [2] |dx|^2 [3] |x|^2 [4] not-PD flag
+};
+
+__device__ __forceinline__ uint32_t intr_col(const Dev& d, uint32_t g) { return 6 * d.n_cams + 6 * g; }
+
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+  if (threadIdx.x < 32) {
+    t = (threadIdx.x < (blockDim.x >> 5)) ? smem[threadIdx.x] : 0.0;
+    for (int o = 16; o >= 1; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in thread 0
+}
+
+// ---- cost only ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_cost(Dev d, const double* poses, const double* intr, const double* pts,
+                                                 double* out_cost) {
+  __shared__ double sm[8];
+  double c = 0;
+  for (uint64_t o = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; o < d.n_obs; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o];
+    const double2 xy = d.obs_xy[o];
+    double r[2];
+    residual_only(intr + 6 * (size_t)d.cam_intr[cam], poses + 6 * (size_t)cam, pts + 3 * (size_t)pt, xy.x, xy.y, r);
+    double rho1;
+    c += 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
+  }
+  c = block_sum(c, sm);
+  if (threadIdx.x == 0) atomicAdd(out_cost, c);
+}
+
+// |residual| per coordinate (OpenMVGHelper::calculateResiduals)
+__global__ void __launch_bounds__(256) k_ba_abs_residuals(Dev d, double* res) {
+  for (uint64_t o = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; o < d.n_obs; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o];
+    const double2 xy = d.obs_xy[o];
+    double r[2];
+    residual_only(d.intr + 6 * (size_t)d.cam_intr[cam], d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r);
+    res[2 * o] = fabs(r[0]);
+    res[2 * o + 1] = fabs(r[1]);
+  }
+}
+
+// ---- gradient + diag(J^T J), unscaled ----------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_eval(Dev d) {
+  for (uint64_t o = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; o < d.n_obs; o += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o], gi = d.cam_intr[cam];
+    const double2 xy = d.obs_xy[o];
+    double r[2], Ji[12], Jc[12], Jp[6];
+    residual_jacobian(d.intr + 6 * (size_t)gi, d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r, Ji, Jc, Jp);
+    double rho1;
+    huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
+    // Corrector (rho'' <= 0): residual and Jacobian scaled by sqrt(rho') -> J^T r and J^T J scale by rho'
+    for (int k = 0; k < 6; ++k) {
+      atomicAdd(&d.gu[6 * (size_t)cam + k], rho1 * (Jc[k] * r[0] + Jc[6 + k] * r[1]));
+      atomicAdd(&d.du[6 * (size_t)cam + k], rho1 * (Jc[k] * Jc[k] + Jc[6 + k] * Jc[6 + k]));
+    }
+    if (d.refine_intr)
+      for (int k = 0; k < 6; ++k) {
+        atomicAdd(&d.gu[intr_col(d, gi) + k], rho1 * (Ji[k] * r[0] + Ji[6 + k] * r[1]));
+        atomicAdd(&d.du[intr_col(d, gi) + k], rho1 * (Ji[k] * Ji[k] + Ji[6 + k] * Ji[6 + k]));
+      }
+    for (int k = 0; k < 3; ++k) {
+      atomicAdd(&d.gu[(size_t)d.nB + 3 * (size_t)pt + k], rho1 * (Jp[k] * r[0] + Jp[3 + k] * r[1]));
+      atomicAdd(&d.du[(size_t)d.nB + 3 * (size_t)pt + k], rho1 * (Jp[k] * Jp[k] + Jp[3 + k] * Jp[3 + k]));
+    }
+  }
+}
+
+__global__ void k_ba_make_scale(double* scale, const double* du, size_t n) {
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (j < n) scale[j] = 1.0 / (1.0 + sqrt(du[j]));  // Ceres Jacobi scaling: 1 / (1 + ||column||)
+}
+__global__ void k_ba_apply_scale(const double* scale, const double* gu, const double* du, double* g, double* diag, size_t n,
+                                 double* gmax) {
+  __shared__ double sm[8];
+  const size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  double m = 0;
+  if (j < n) {
+    g[j] = gu[j] * scale[j];
+    diag[j] = du[j] * scale[j] * scale[j];
+    m = fabs(gu[j]);  // unscaled gradient for the gradient tolerance
+  }
+  for (int o = 16; o >= 1; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, sm[w]);
+    // non-negative doubles order like their bit patterns
+    atomicMax((unsigned long long*)gmax, (unsigned long long)__double_as_longlong(m));
+  }
+}
+
+// scaled, corrected Jacobian blocks of one observation
+__device__ __forceinline__ void scaled_jacobian(const Dev& d, uint32_t o, double* Jc, double* Jg, double* Jp, double* r,
+                                                uint32_t* colc, int* colg) {
+  const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o], gi = d.cam_intr[cam];
+  const double2 xy = d.obs_xy[o];
+  double Ji[12];
+  residual_jacobian(d.intr + 6 * (size_t)gi, d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r, Ji, Jc, Jp);
+  double rho1;
+  huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
+  const double sq = sqrt(rho1);
+  r[0] *= sq; r[1] *= sq;
+  const double* sc = d.scale + 6 * (size_t)cam;
+  const double* sp = d.scale + (size_t)d.nB + 3 * (size_t)pt;
+  for (int a = 0; a < 2; ++a) {
+    for (int k = 0; k < 6; ++k) Jc[6 * a + k] *= sq * sc[k];
+    for (int k = 0; k < 3; ++k) Jp[3 * a + k] *= sq * sp[k];
+  }
+  *colc = 6 * cam;
+  if (d.refine_intr) {
+    const double* sg = d.scale + intr_col(d, gi);
+    for (int a = 0; a < 2; ++a)
+      for (int k = 0; k < 6; ++k) Jg[6 * a + k] = Ji[6 * a + k] * sq * sg[k];
+    *colg = (int)intr_col(d, gi);
+  } else {
+    for (int k = 0; k < 12; ++k) Jg[k] = 0.0;
+    *colg = -1;
+  }
+}
+
+__device__ __forceinline__ void inv3_sym(const double* V, double* Vi) {
+  const double c00 = V[4] * V[8] - V[5] * V[7], c01 = V[5] * V[6] - V[3] * V[8], c02 = V[3] * V[7] - V[4] * V[6];
+  const double det = V[0] * c00 + V[1] * c01 + V[2] * c02;
+  Vi[0] = c00 / det; Vi[1] = (V[2] * V[7] - V[1] * V[8]) / det; Vi[2] = (V[1] * V[5] - V[2] * V[4]) / det;
+  Vi[3] = c01 / det; Vi[4] = (V[0] * V[8] - V[2] * V[6]) / det; Vi[5] = (V[2] * V[3] - V[0] * V[5]) / det;
+  Vi[6] = c02 / det; Vi[7] = (V[1] * V[6] - V[0] * V[7]) / det; Vi[8] = (V[0] * V[4] - V[1] * V[3]) / det;
+}
+
+// add the 6x6 block `blk` (row-major) at block position (ca, cb) of the upper-triangular block form
+__device__ __forceinline__ void add_block_upper(double* S, uint32_t nB, uint32_t ca, uint32_t cb, const double* blk, double sign) {
+  if (ca <= cb) {
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) atomicAdd(&S[(size_t)(ca + i) * nB + cb + j], sign * blk[6 * i + j]);
+  } else {  // store the transpose at (cb, ca)
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) atomicAdd(&S[(size_t)(cb + j) * nB + ca + i], sign * blk[6 * i + j]);
+  }
+}
+
+// ---- Schur complement: one warp per point ------------------------------------------------------
+__global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv_radius, int obs_cap) {
+  extern __shared__ double sm[];
+  // per warp: obs staging [obs_cap][kObsDoubles] + W blocks [obs_cap][36]; obs_cap = max track length
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* J = sm + (size_t)warp * obs_cap * (kObsDoubles + 36);
+  double* W = J + (size_t)obs_cap * kObsDoubles;
+  __shared__ uint32_t s_colc[kSchurWarps][kMaxObsPerPoint];
+  __shared__ int s_colg[kSchurWarps][kMaxObsPerPoint];
+  const uint32_t ip = blockIdx.x * kSchurWarps + warp;
+  if (ip < d.n_pts) {
+    const uint32_t b = d.pt_ofs[ip], e = d.pt_ofs[ip + 1];
+    const int nobs = (int)(e - b);
+    // 1. stage the scaled Jacobians of this point's observations
+    for (int t = lane; t < nobs; t += 32) {
+      double* jt = J + (size_t)t * kObsDoubles;
+      scaled_jacobian(d, d.pt_obs[b + t], jt, jt + 12, jt + 24, jt + 30, &s_colc[warp][t], &s_colg[warp][t]);
+    }
+    __syncwarp();
+    // 2. V = sum Jp^T Jp + D^2, g_p  (warp reduction)
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    for (int t = lane; t < nobs; t += 32) {
+      const double* jp = J + (size_t)t * kObsDoubles + 24;
+      v[0] += jp[0] * jp[0] + jp[3] * jp[3]; v[1] += jp[0] * jp[1] + jp[3] * jp[4]; v[2] += jp[0] * jp[2] + jp[3] * jp[5];
+      v[3] += jp[1] * jp[1] + jp[4] * jp[4]; v[4] += jp[1] * jp[2] + jp[4] * jp[5]; v[5] += jp[2] * jp[2] + jp[5] * jp[5];
+    }
+    for (int k = 0; k < 6; ++k)
+      for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    const size_t pcol = (size_t)d.nB + 3 * (size_t)ip;
+    double V[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
+    for (int i = 0; i < 3; ++i) V[4 * i] += fmin(fmax(d.diag[pcol + i], 1e-6), 1e32) * inv_radius;
+    double Vi[9];
+    inv3_sym(V, Vi);
+    if (lane == 0)
+      for (int i = 0; i < 9; ++i) d.Vinv[9 * (size_t)ip + i] = Vi[i];
+    const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
+    const double Vg[3] = {Vi[0] * gp[0] + Vi[1] * gp[1] + Vi[2] * gp[2], Vi[3] * gp[0] + Vi[4] * gp[1] + Vi[5] * gp[2],
+                          Vi[6] * gp[0] + Vi[7] * gp[1] + Vi[8] * gp[2]};
+    // 3. W blocks (6x3): camera and intrinsic group of every observation; B part of S
+    for (int t = lane; t < nobs; t += 32) {
+      const double* jt = J + (size_t)t * kObsDoubles;
+      const double *jc = jt, *jg = jt + 12, *jp = jt + 24;
+      double* wc = W + (size_t)t * 36;
+      double* wg = wc + 18;
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 3; ++j) {
+          wc[3 * i + j] = jc[i] * jp[j] + jc[6 + i] * jp[3 + j];
+          wg[3 * i + j] = jg[i] * jp[j] + jg[6 + i] * jp[3 + j];
+        }
+      double blk[36];
+      const uint32_t cc = s_colc[warp][t];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) blk[6 * i + j] = jc[i] * jc[j] + jc[6 + i] * jc[6 + j];
+      add_block_upper(d.S, d.nB, cc, cc, blk, 1.0);
+      const int cg = s_colg[warp][t];
+      if (cg >= 0) {
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) blk[6 * i + j] = jc[i] * jg[j] + jc[6 + i] * jg[6 + j];
+        add_block_upper(d.S, d.nB, cc, (uint32_t)cg, blk, 1.0);
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) blk[6 * i + j] = jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
+        add_block_upper(d.S, d.nB, (uint32_t)cg, (uint32_t)cg, blk, 1.0);
+      }
+    }
+    __syncwarp();
+    // 4. Schur part over the 2*nobs blocks (camera t -> block 2t, group t -> block 2t+1)
+    const int nblk = 2 * nobs;
+    for (int a = lane; a < nblk; a += 32) {  // rhs[a] += W_a V^-1 g_p
+      const int ca = (a & 1) ? s_colg[warp][a >> 1] : (int)s_colc[warp][a >> 1];
+      if (ca < 0) continue;
+      const double* wa = W + (size_t)(a >> 1) * 36 + (a & 1) * 18;
+      for (int i = 0; i < 6; ++i) atomicAdd(&d.rhs[ca + i], wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2]);
+    }
+    const int npairs = nblk * (nblk + 1) / 2;
+    for (int pr = lane; pr < npairs; pr += 32) {
+      // unrank pr -> (a <= bb)
+      int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= pr) ++a;
+      while (a * (a + 1) / 2 > pr) --a;
+      const int bb_ = pr - a * (a + 1) / 2;  // bb_ <= a
+      const int hi = a, lo = bb_;
+      const int ch = (hi & 1) ? s_colg[warp][hi >> 1] : (int)s_colc[warp][hi >> 1];
+      const int cl = (lo & 1) ? s_colg[warp][lo >> 1] : (int)s_colc[warp][lo >> 1];
+      if (ch < 0 || cl < 0) continue;
+      const double* wl = W + (size_t)(lo >> 1) * 36 + (lo & 1) * 18;
+      const double* wh = W + (size_t)(hi >> 1) * 36 + (hi & 1) * 18;
+      double WV[18];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 3; ++j) WV[3 * i + j] = wl[3 * i] * Vi[j] + wl[3 * i + 1] * Vi[3 + j] + wl[3 * i + 2] * Vi[6 + j];
+      double blk[36];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) blk[6 * i + j] = WV[3 * i] * wh[3 * j] + WV[3 * i + 1] * wh[3 * j + 1] + WV[3 * i + 2] * wh[3 * j + 2];
+      // blk = W_lo V^-1 W_hi^T  contributes to S[cl, ch]; for lo != hi the mirrored term S[ch, cl] is
+      // its transpose: in upper-block form both land on the same stored block (doubling when cl == ch).
+      if (lo == hi) {
+        add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
+      } else if (cl == ch) {  // two different observations sharing a block (same intrinsic group / camera)
+        double sym[36];
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) sym[6 * i + j] = blk[6 * i + j] + blk[6 * j + i];
+        add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, sym, -1.0);
+      } else {
+        add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
+      }
+    }
+  }
+}
+
+// mirror the upper-triangular block form into the lower triangle, add D^2 on the diagonal, rhs -= g
+__global__ void k_ba_finish_S(Dev d, double inv_radius) {
+  const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nB || j >= d.nB) return;
+  if (i > j) d.S[(size_t)i * d.nB + j] = d.S[(size_t)j * d.nB + i];
+  if (i == j) {
+    d.S[(size_t)i * d.nB + i] += fmin(fmax(d.diag[i], 1e-6), 1e32) * inv_radius;
+    d.rhs[i] -= d.g[i];
+  }
+}
+
+// ---- dense Cholesky (lower), blocked 32 ----------------------------------------------------------
+constexpr int NB = 32;
+__global__ void __launch_bounds__(1024) k_chol_potrf(double* A, int n, int k0, double* flag) {
+  __shared__ double t[NB][NB + 1];
+  const int kb = min(NB, n - k0);
+  const int r = threadIdx.y, c = threadIdx.x;
+  if (r < kb && c < kb) t[r][c] = A[(size_t)(k0 + r) * n + k0 + c];
+  __syncthreads();
+  for (int j = 0; j < kb; ++j) {
+    if (r == j && c == j) {
+      const double dd = t[j][j];
+      if (!(dd > 0.0)) { *flag = 1.0; t[j][j] = 1.0; } else t[j][j] = sqrt(dd);
+    }
+    __syncthreads();
+    if (c == j && r > j && r < kb) t[r][j] /= t[j][j];
+    __syncthreads();
+    if (r > j && c > j && c <= r && r < kb) t[r][c] -= t[r][j] * t[c][j];
+    __syncthreads();
+  }
+  if (r < kb && c < kb && c <= r) A[(size_t)(k0 + r) * n + k0 + c] = t[r][c];
+}
+// rows below the diagonal block: X L_kk^T = A_ik ; one thread per row
+__global__ void __launch_bounds__(128) k_chol_trsm(double* A, int n, int k0) {
+  __shared__ double L[NB][NB + 1];
+  const int kb = min(NB, n - k0);
+  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) L[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
+  __syncthreads();
+  const int row = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  double x[NB];
+  for (int j = 0; j < kb; ++j) {
+    double s = A[(size_t)row * n + k0 + j];
+    for (int tt = 0; tt < j; ++tt) s -= x[tt] * L[j][tt];
+    x[j] = s / L[j][j];
+  }
+  for (int j = 0; j < kb; ++j) A[(size_t)row * n + k0 + j] = x[j];
+}
+// trailing update of the lower triangle: A_ij -= L_ik L_jk^T ; tiles of 32x32
+__global__ void __launch_bounds__(1024) k_chol_syrk(double* A, int n, int k0) {
+  const int kb = min(NB, n - k0);
+  const int r0 = k0 + kb;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (tj > ti) return;
+  __shared__ double Li[NB][NB + 1], Lj[NB][NB + 1];
+  const int i = r0 + ti * NB + threadIdx.y, j = r0 + tj * NB + threadIdx.x;
+  const int li = r0 + ti * NB + threadIdx.y, lj = r0 + tj * NB + threadIdx.y;
+  Li[threadIdx.y][threadIdx.x] = (li < n && (int)threadIdx.x < kb) ? A[(size_t)li * n + k0 + threadIdx.x] : 0.0;
+  Lj[threadIdx.y][threadIdx.x] = (lj < n && (int)threadIdx.x < kb) ? A[(size_t)lj * n + k0 + threadIdx.x] : 0.0;
+  __syncthreads();
+  if (i < n && j < n && j <= i) {
+    double s = 0;
+    for (int tt = 0; tt < kb; ++tt) s += Li[threadIdx.y][tt] * Lj[threadIdx.x][tt];
+    A[(size_t)i * n + j] -= s;
+  }
+}
+// L y = b ; L^T x = y   (single block)
+__global__ void __launch_bounds__(1024) k_chol_solve(const double* A, int n, double* b) {
+  __shared__ double xs[NB];
+  for (int k0 = 0; k0 < n; k0 += NB) {  // forward
+    const int kb = min(NB, n - k0);
+    if (threadIdx.x == 0)
+      for (int j = 0; j < kb; ++j) {
+        double s = b[k0 + j];
+        for (int tt = 0; tt < j; ++tt) s -= A[(size_t)(k0 + j) * n + k0 + tt] * xs[tt];
+        xs[j] = s / A[(size_t)(k0 + j) * n + k0 + j];
+        b[k0 + j] = xs[j];
+      }
+    __syncthreads();
+    for (int i = k0 + kb + threadIdx.x; i < n; i += blockDim.x) {
+      double s = b[i];
+      for (int tt = 0; tt < kb; ++tt) s -= A[(size_t)i * n + k0 + tt] * xs[tt];
+      b[i] = s;
+    }
+    __syncthreads();
+  }
+  const int nblk = (n + NB - 1) / NB;
+  for (int kbk = nblk - 1; kbk >= 0; --kbk) {  // backward
+    const int k0 = kbk * NB, kb = min(NB, n - k0);
+    if (threadIdx.x == 0)
+      for (int j = kb - 1; j >= 0; --j) {
+        double s = b[k0 + j];
+        for (int tt = j + 1; tt < kb; ++tt) s -= A[(size_t)(k0 + tt) * n + k0 + j] * xs[tt];
+        xs[j] = s / A[(size_t)(k0 + j) * n + k0 + j];
+        b[k0 + j] = xs[j];
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k0; i += blockDim.x) {
+      double s = b[i];
+      for (int tt = 0; tt < kb; ++tt) s -= A[(size_t)(k0 + tt) * n + i] * xs[tt];
+      b[i] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- back substitution ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_ba_backsub(Dev d) {
+  const uint32_t ip = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ip >= d.n_pts) return;
+  const size_t pcol = (size_t)d.nB + 3 * (size_t)ip;
+  double t3[3] = {-d.g[pcol], -d.g[pcol + 1], -d.g[pcol + 2]};
+  for (uint32_t t = d.pt_ofs[ip]; t < d.pt_ofs[ip + 1]; ++t) {
+    double Jc[12], Jg[12], Jp[6], r[2];
+    uint32_t cc;
+    int cg;
+    scaled_jacobian(d, d.pt_obs[t], Jc, Jg, Jp, r, &cc, &cg);
+    double m[2] = {0, 0};
+    for (int a = 0; a < 2; ++a) {
+      for (int k = 0; k < 6; ++k) m[a] += Jc[6 * a + k] * d.delta[cc + k];
+      if (cg >= 0)
+        for (int k = 0; k < 6; ++k) m[a] += Jg[6 * a + k] * d.delta[cg + k];
+    }
+    for (int k = 0; k < 3; ++k) t3[k] -= Jp[k] * m[0] + Jp[3 + k] * m[1];
+  }
+  const double* Vi = d.Vinv + 9 * (size_t)ip;
+  for (int i = 0; i < 3; ++i) d.delta[pcol + i] = Vi[3 * i] * t3[0] + Vi[3 * i + 1] * t3[1] + Vi[3 * i + 2] * t3[2];
+}
+
+// ---- candidate parameters, step norms, model cost change ---------------------------------------------
+__global__ void __launch_bounds__(256) k_ba_update(Dev d, double inv_radius) {
+  __shared__ double sm[8];
+  const size_t nparam = (size_t)d.nB + 3 * (size_t)d.n_pts;
+  double mcc = 0, dn = 0, xn = 0;
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < nparam; j += (size_t)gridDim.x * blockDim.x) {
+    const double D2 = fmin(fmax(d.diag[j], 1e-6), 1e32) * inv_radius;
+    const double dl = d.delta[j];
+    mcc += dl * (D2 * dl - d.g[j]);
+    const double dx = dl * d.scale[j];
+    double x;
+    if (j < 6 * (size_t)d.n_cams) { x = d.poses[j]; d.poses_new[j] = x + dx; }
+    else if (j < d.nB) { x = d.intr[j - 6 * (size_t)d.n_cams]; d.intr_new[j - 6 * (size_t)d.n_cams] = x + dx; }
+    else { x = d.pts[j - d.nB]; d.pts_new[j - d.nB] = x + dx; }
+    dn += dx * dx;
+    xn += x * x;
+  }
+  mcc = block_sum(mcc, sm);
+  dn = block_sum(dn, sm);
+  xn = block_sum(xn, sm);
+  if (threadIdx.x == 0) {
+    atomicAdd(&d.scal[1], mcc);
+    atomicAdd(&d.scal[2], dn);
+    atomicAdd(&d.scal[3], xn);
+  }
+}
+
+}  // namespace ba
+}  // namespace r3d
+
+// ------------------------------------------------------------------------------------------------
+using namespace r3d;
+using r3d::ba::Dev;
+
+namespace {
+
+struct DeviceArrays {
+  std::vector<void*> ptrs;
+  ~DeviceArrays() { for (void* p : ptrs) cudaFree(p); }
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+};
+
+int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, DeviceArrays& mem, Dev& d, bool refine_intr,
+                  double huber_a, bool full, uint32_t* max_obs_out = nullptr) {
+  if (!p || !p->poses || !p->intrinsics || !p->points || !p->obs_cam || !p->obs_pt || !p->cam_intr || !p->obs_xy)
+    return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: NULL array in the problem");
+  for (uint64_t o = 0; o < p->n_obs; ++o)
+    if (p->obs_cam[o] >= p->n_cams || p->obs_pt[o] >= p->n_pts) return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: observation index out of range");
+  for (uint32_t c = 0; c < p->n_cams; ++c)
+    if (p->cam_intr[c] >= p->n_intr) return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: intrinsic group out of range");
+  std::memset(&d, 0, sizeof(d));
+  d.n_cams = p->n_cams; d.n_pts = p->n_pts; d.n_intr = p->n_intr; d.n_obs = p->n_obs;
+  d.refine_intr = refine_intr ? 1u : 0u;
+  d.nB = 6 * p->n_cams + (refine_intr ? 6 * p->n_intr : 0);
+  d.huber_a = huber_a;
+  const size_t nparam = (size_t)d.nB + 3 * (size_t)p->n_pts;
+  uint32_t *oc, *op, *ci, *pofs, *pobs;
+  double2* oxy;
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.poses, 6 * (size_t)p->n_cams));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.intr, 6 * (size_t)p->n_intr));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.pts, 3 * (size_t)p->n_pts));
+  R3D_CUDA_TRY(ctx, mem.alloc(&oc, p->n_obs));
+  R3D_CUDA_TRY(ctx, mem.alloc(&op, p->n_obs));
+  R3D_CUDA_TRY(ctx, mem.alloc(&ci, p->n_cams));
+  R3D_CUDA_TRY(ctx, mem.alloc(&oxy, p->n_obs));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.scal, 8));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.poses, p->poses, 6 * (size_t)p->n_cams * 8, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.intr, p->intrinsics, 6 * (size_t)p->n_intr * 8, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.pts, p->points, 3 * (size_t)p->n_pts * 8, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(oc, p->obs_cam, p->n_obs * 4, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(op, p->obs_pt, p->n_obs * 4, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(ci, p->cam_intr, (size_t)p->n_cams * 4, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(oxy, p->obs_xy, p->n_obs * 16, cudaMemcpyHostToDevice, w.stream));
+  d.obs_cam = oc; d.obs_pt = op; d.cam_intr = ci; d.obs_xy = oxy;
+  if (!full) return R3D_OK;
+  if (p->n_obs > 0xfffffff0ull) return fail(ctx, R3D_ERR_UNSUPPORTED, "bundle adjustment: more than 2^32 observations");
+  // point -> observation CSR (host counting sort)
+  std::vector<uint32_t> hofs((size_t)p->n_pts + 1, 0), hobs(p->n_obs);
+  for (uint64_t o = 0; o < p->n_obs; ++o) hofs[p->obs_pt[o] + 1]++;
+  uint32_t maxobs = 0;
+  for (uint32_t i = 0; i < p->n_pts; ++i) { maxobs = std::max(maxobs, hofs[i + 1]); hofs[i + 1] += hofs[i]; }
+  if (maxobs > (uint32_t)r3d::ba::kMaxObsPerPoint)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "bundle adjustment: a point has more than 64 observations (round-1 limit)");
+  if (max_obs_out) *max_obs_out = maxobs;
+  {
+    std::vector<uint32_t> pos(hofs.begin(), hofs.end() - 1);
+    for (uint64_t o = 0; o < p->n_obs; ++o) hobs[pos[p->obs_pt[o]]++] = (uint32_t)o;
+  }
+  R3D_CUDA_TRY(ctx, mem.alloc(&pofs, hofs.size()));
+  R3D_CUDA_TRY(ctx, mem.alloc(&pobs, hobs.size()));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pofs, hofs.data(), hofs.size() * 4, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pobs, hobs.data(), hobs.size() * 4, cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // hofs / hobs are locals
+  d.pt_ofs = pofs; d.pt_obs = pobs;
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.poses_new, 6 * (size_t)p->n_cams));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.intr_new, 6 * (size_t)p->n_intr));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.pts_new, 3 * (size_t)p->n_pts));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.scale, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.gu, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.du, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.g, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.diag, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.delta, nparam));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.S, (size_t)d.nB * d.nB));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.rhs, d.nB));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.Vinv, 9 * (size_t)p->n_pts));
+  // intrinsics that are not refined never enter the parameter vector: the candidate copy is constant
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.intr_new, d.intr, 6 * (size_t)p->n_intr * 8, cudaMemcpyDeviceToDevice, w.stream));
+  return R3D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void r3d_ba_default_options(r3d_ba_options* o) {
+  if (!o) return;
+  o->max_iterations = 500;      // OpenMVG: ceres_options.max_num_iterations = 500
+  o->huber_a = 16.0;            // new ceres::HuberLoss(Square(4.0))
+  o->refine_intrinsics = 1;     // Intrinsic_Parameter_Type::ADJUST_ALL
+  o->function_tolerance = 1e-6; // Ceres defaults
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->initial_radius = 1e4;
+}
+
+int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res) {
+  if (!ctx || !p || !res) return fail(ctx, R3D_ERR_INVALID, "r3d_ba_residuals: bad arguments");
+  DeviceWorker& w = ctx->workers[0];
+  R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+  DeviceArrays mem;
+  Dev d;
+  int rc = setup_problem(ctx, w, p, mem, d, false, 0.0, false);
+  if (rc) return rc;
+  double* dres;
+  R3D_CUDA_TRY(ctx, mem.alloc(&dres, 2 * p->n_obs));
+  r3d::ba::k_ba_abs_residuals<<<w.sm_count * 4, 256, 0, w.stream>>>(d, dres);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(res, dres, 2 * p->n_obs * 8, cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+  return R3D_OK;
+}
+
+int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt, r3d_ba_summary* sum, double* cost_trace) {
+  if (!ctx || !p || !opt || !sum) return fail(ctx, R3D_ERR_INVALID, "r3d_bundle_adjust: bad arguments");
+  const auto t_begin = std::chrono::steady_clock::now();
+  DeviceWorker& w = ctx->workers[0];
+  R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
+  DeviceArrays mem;
+  Dev d;
+  uint32_t max_obs = 1;
+  int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs);
+  if (rc) return rc;
+  const int obs_cap = (int)std::max<uint32_t>(max_obs, 1u);
+  const size_t nparam = (size_t)d.nB + 3 * (size_t)d.n_pts;
+  const int grid_obs = w.sm_count * 8;
+  const int nB = (int)d.nB;
+  const size_t schur_smem = (size_t)r3d::ba::kSchurWarps * obs_cap * (r3d::ba::kObsDoubles + 36) * sizeof(double);
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem));
+  double h_scal[8];
+  auto read_scal = [&]() -> int {
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_scal, d.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    return R3D_OK;
+  };
+  auto eval_cost = [&](const double* poses, const double* intr, const double* pts, double* out) -> int {
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, sizeof(double), w.stream));
+    r3d::ba::k_ba_cost<<<grid_obs, 256, 0, w.stream>>>(d, poses, intr, pts, d.scal);
+    R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = read_scal())) return rc;
+    *out = h_scal[0];
+    return R3D_OK;
+  };
+  bool have_scale = false;
+  double gmax = 0;
+  auto evaluate = [&]() -> int {  // gradient + diag at the current parameters
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.gu, 0, nparam * 8, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.du, 0, nparam * 8, w.stream));
+    r3d::ba::k_ba_eval<<<grid_obs, 256, 0, w.stream>>>(d);
+    if (!have_scale) {
+      r3d::ba::k_ba_make_scale<<<(unsigned)((nparam + 255) / 256), 256, 0, w.stream>>>(d.scale, d.du, nparam);
+      have_scale = true;
+    }
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal + 5, 0, sizeof(double), w.stream));
+    r3d::ba::k_ba_apply_scale<<<(unsigned)((nparam + 255) / 256), 256, 0, w.stream>>>(d.scale, d.gu, d.du, d.g, d.diag, nparam, d.scal + 5);
+    R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = read_scal())) return rc;
+    gmax = h_scal[5];
+    return R3D_OK;
+  };
+
+  double cost = 0;
+  if ((rc = eval_cost(d.poses, d.intr, d.pts, &cost))) return rc;
+  sum->initial_cost = cost;
+  sum->iterations = 0;
+  sum->successful_steps = 0;
+  sum->termination = 0;
+  sum->seconds_linear = 0;
+  if (cost_trace) cost_trace[0] = cost;
+  double radius = opt->initial_radius, decrease_factor = 2.0;
+  if ((rc = evaluate())) return rc;
+  bool stop = gmax <= opt->gradient_tolerance;
+  if (stop) sum->termination = 2;
+
+  for (uint32_t iter = 1; !stop && iter <= opt->max_iterations; ++iter) {
+    sum->iterations = iter;
+    const auto t_lin = std::chrono::steady_clock::now();
+    const double inv_radius = 1.0 / radius;
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.S, 0, (size_t)nB * nB * 8, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.rhs, 0, (size_t)nB * 8, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, 5 * sizeof(double), w.stream));
+    r3d::ba::k_ba_schur<<<(d.n_pts + r3d::ba::kSchurWarps - 1) / r3d::ba::kSchurWarps, r3d::ba::kSchurWarps * 32, schur_smem, w.stream>>>(d, inv_radius, obs_cap);
+    {
+      dim3 b(32, 8), g((nB + 31) / 32, (nB + 7) / 8);
+      r3d::ba::k_ba_finish_S<<<g, b, 0, w.stream>>>(d, inv_radius);
+    }
+    for (int k0 = 0; k0 < nB; k0 += r3d::ba::NB) {
+      r3d::ba::k_chol_potrf<<<1, dim3(32, 32), 0, w.stream>>>(d.S, nB, k0, d.scal + 4);
+      const int rem = nB - k0 - r3d::ba::NB;
+      if (rem > 0) {
+        r3d::ba::k_chol_trsm<<<(rem + 127) / 128, 128, 0, w.stream>>>(d.S, nB, k0);
+        const int tiles = (rem + r3d::ba::NB - 1) / r3d::ba::NB;
+        r3d::ba::k_chol_syrk<<<dim3(tiles, tiles), dim3(32, 32), 0, w.stream>>>(d.S, nB, k0);
+      }
+    }
+    r3d::ba::k_chol_solve<<<1, 1024, 0, w.stream>>>(d.S, nB, d.rhs);
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.delta, d.rhs, (size_t)nB * 8, cudaMemcpyDeviceToDevice, w.stream));
+    r3d::ba::k_ba_backsub<<<(d.n_pts + 127) / 128, 128, 0, w.stream>>>(d);
+    r3d::ba::k_ba_update<<<w.sm_count * 4, 256, 0, w.stream>>>(d, inv_radius);
+    R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = read_scal())) return rc;
+    sum->seconds_linear += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lin).count();
+    const bool pd = h_scal[4] == 0.0;
+    const double model_cost_change = 0.5 * h_scal[1];
+    bool accepted = false;
+    if (pd && model_cost_change > 0.0 && std::isfinite(model_cost_change)) {
+      if (std::sqrt(h_scal[2]) <= opt->parameter_tolerance * (std::sqrt(h_scal[3]) + opt->parameter_tolerance)) {
+        sum->termination = 3;
+        if (cost_trace) cost_trace[iter] = cost;
+        break;
+      }
+      double new_cost = 0;
+      if ((rc = eval_cost(d.poses_new, d.intr_new, d.pts_new, &new_cost))) return rc;
+      const double relative_decrease = (cost - new_cost) / model_cost_change;
+      if (relative_decrease > 1e-3) {
+        accepted = true;
+        std::swap(d.poses, d.poses_new);
+        std::swap(d.intr, d.intr_new);
+        std::swap(d.pts, d.pts_new);
+        const double cost_change = cost - new_cost;
+        const double t = 2.0 * relative_decrease - 1.0;
+        radius = radius / std::max(1.0 / 3.0, 1.0 - t * t * t);
+        radius = std::min(1e16, radius);
+        decrease_factor = 2.0;
+        sum->successful_steps++;
+        const bool ftol = std::fabs(cost_change) < opt->function_tolerance * cost;
+        cost = new_cost;
+        if (cost_trace) cost_trace[iter] = cost;
+        if ((rc = evaluate())) return rc;
+        if (ftol) { sum->termination = 1; break; }
+        if (gmax <= opt->gradient_tolerance) { sum->termination = 2; break; }
+      }
+    }
+    if (!accepted) {
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      if (cost_trace) cost_trace[iter] = cost;
+      if (radius < 1e-32) { sum->termination = 4; break; }
+    }
+  }
+  sum->final_cost = cost;
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(p->poses, d.poses, 6 * (size_t)p->n_cams * 8, cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(p->intrinsics, d.intr, 6 * (size_t)p->n_intr * 8, cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(p->points, d.pts, 3 * (size_t)p->n_pts * 8, cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+  sum->seconds_total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+  return R3D_OK;
+}
+
+}  // extern "C"
