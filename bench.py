@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment leg")
+    ap.add_argument("--no-filter", action="store_true", help="skip the F-filter leg")
     ap.add_argument("--dim", type=int, default=0, help="experiment only: 64 -> MSURF-like D=64 set")
     ap.add_argument("--feats", type=int, default=0, help="experiment only")
     ap.add_argument("--images", type=int, default=0, help="experiment only")
@@ -250,6 +252,60 @@ def main():
     barrier()
     t_e2e = time.perf_counter() - t0
 
+    # ---------------- geometric filter leg (reported alongside; BASELINE C2 itself stops at putatives) ----------------
+    filt = None
+    if not args.no_filter:
+        ctx.filter_pairs(m2, sc["widths"], sc["heights"])            # warm-up
+        torch.cuda.synchronize()
+        tf0 = time.perf_counter()
+        fm = ctx.filter_pairs(m2, sc["widths"], sc["heights"])
+        tf = time.perf_counter() - tf0
+        ft = ctx.filter_timing()
+        filt = {"pairs_per_s": m2.num_pairs / tf, "ms": 1e3 * tf, "pairs_in": m2.num_pairs, "pairs_kept": fm.num_pairs,
+                "inliers": fm.total, "hypotheses": int(ft["hypotheses"]), "rounds": int(ft["rounds"]),
+                "ms_solve": ft["ms_solve"], "ms_score": ft["ms_score"], "ms_host": ft["ms_host"],
+                "kernel_launches": int(ft["kernel_launches"]),
+                "what": "AC-RANSAC fundamental filter (4 px, 2048 it.) over all putative pairs of the step"}
+
+    # ---------------- bundle-adjustment leg (BASELINE C5, reported alongside; rank 0 only) ----------------
+    ba = None
+    if not args.no_ba and rank == 0:
+        from regard3d_b200 import synth
+        prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
+        arrs = {k: np.ascontiguousarray(v) for k, v in prob.items() if k != "truth"}
+        for k in ("poses", "intrinsics", "points", "obs_xy"):
+            arrs[k] = np.ascontiguousarray(arrs[k], np.float64)
+        for k in ("obs_cam", "obs_pt", "cam_intr"):
+            arrs[k] = np.ascontiguousarray(arrs[k], np.uint32)
+        g = {k: v.copy() for k, v in arrs.items()}
+        ctx.bundle_adjust({k: v.copy() for k, v in arrs.items()}, max_iterations=2)     # warm-up
+        n_it = 10
+        tb0 = time.perf_counter()
+        sg, tg = ctx.bundle_adjust(g, max_iterations=n_it, function_tolerance=0.0)
+        tb = time.perf_counter() - tb0
+        n_obs = int(len(arrs["obs_xy"]))
+        nB = 6 * 200 + 6
+        bytes_iter = 3 * (n_obs * 24 + len(arrs["points"]) * 24) + 2 * nB * nB * 8
+        ba = {"iters_per_s": sg["iterations"] / tb, "iterations": int(sg["iterations"]), "seconds": tb,
+              "seconds_linear": sg["seconds_linear"], "initial_cost": sg["initial_cost"], "final_cost": sg["final_cost"],
+              "config": "C5: 200 cams / %d pts / %d obs, 1 shared radial-K3 intrinsic, Huber(16)" % (len(arrs["points"]), n_obs),
+              "roofline": {"bound": "hbm", "achieved": sg["iterations"] / tb * bytes_iter / 1e9,
+                           "peak": float(load_peaks()[0].get("hbm_gbs", 6650.0)), "unit": "GB/s",
+                           "frac": sg["iterations"] / tb * bytes_iter / 1e9 / float(load_peaks()[0].get("hbm_gbs", 6650.0)),
+                           "bytes_per_iter": bytes_iter}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            c = po.ba_prepare(arrs["poses"], arrs["intrinsics"], arrs["points"], arrs["obs_cam"], arrs["obs_pt"],
+                              arrs["cam_intr"], arrs["obs_xy"])
+            o = po.default_ba_options(max_iterations=3)
+            o.function_tolerance = 0.0
+            tc0 = time.perf_counter()
+            so, to = po.bundle_adjust(c, o)
+            tcb = time.perf_counter() - tc0
+            ba["cpu_baseline"] = {"iters_per_s": so["iterations"] / tcb, "iterations": int(so["iterations"]),
+                                  "cores": po.num_threads(), "kind": "port",
+                                  "cost_trace_rel_diff": float(np.max(np.abs(tg[:len(to)] - to) / to))}
+
     if world > 1:
         tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -282,6 +338,10 @@ def main():
             "result": {"pairs_with_matches": int(n_match_pairs), "matches": int(n_matches),
                        "fallback_query_frac": fbq / max(q, 1)},
         }
+        if filt is not None:
+            line["f_filter"] = filt
+        if ba is not None:
+            line["ba"] = ba
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as po
             nthreads = po.num_threads()

@@ -1,5 +1,121 @@
-// compute_matches.cu -- placeholder until the file-level twin of computeMatches() lands (next commit)
+// compute_matches.cu -- file-level twin of R3DComputeMatches::computeMatches()
+// (src/R3DComputeMatches.cpp:1667-2256), for the steps after feature extraction:
+//   Regions_Provider::load            (:2040)  <img>.feat / <img>.desc  -> r3d_upload_regions
+//   exhaustivePairs(N)                (:2042)
+//   Matcher_Regions::Match            (:2048)  -> r3d_match_pairs
+//   Save(matches.putative.txt)        (:2064)
+//   Robust_model_estimation(F, AC)    (:2113)  -> r3d_filter_pairs
+//   Save(matchesFFilename_)           (:2120)
+// Progress fractions as the reference emits them (0.7 before matching :2000, 0.8 before the F filter
+// :2107).  File formats: SURVEY.md Appendix B.  Feature extraction (AKAZE + LIOP on the CPU thread
+// pool, src/threads/R3DFeaturesThread.cpp) stays with the caller: it is a "next" row.
 #include "r3d_internal.cuh"
-extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params*, const r3d_cm_paths*, r3d_progress_cb, void*, r3d_cm_stats*) {
-  return r3d::fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_compute_matches: not built yet");
+
+#include <chrono>
+#include <fstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// <basename>.feat : "x y scale orientation" per line (src/keypointSet.hpp:61-67 -> saveFeatsToFile)
+bool load_feat(const std::string& path, std::vector<float>& xy) {
+  std::ifstream f(path);
+  if (!f.is_open()) return false;
+  float x, y, s, o;
+  xy.clear();
+  while (f >> x >> y >> s >> o) {
+    xy.push_back(x);
+    xy.push_back(y);
+  }
+  return true;
+}
+
+// <basename>.desc : size_t count + count * dim float32 (saveDescsToBinFile)
+bool load_desc(const std::string& path, uint32_t dim, std::vector<float>& d, uint64_t* n) {
+  std::ifstream f(path, std::ios::in | std::ios::binary);
+  if (!f.is_open()) return false;
+  std::size_t card = 0;
+  f.read((char*)&card, sizeof(std::size_t));
+  if (!f.good()) return false;
+  d.resize((size_t)card * dim);
+  if (card) f.read((char*)d.data(), (std::streamsize)(d.size() * sizeof(float)));
+  if (card && f.gcount() != (std::streamsize)(d.size() * sizeof(float))) return false;
+  *n = card;
+  return true;
+}
+
+}  // namespace
+
+using namespace r3d;
+
+extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, const r3d_cm_paths* paths,
+                                   r3d_progress_cb cb, void* user, r3d_cm_stats* stats) {
+  if (!ctx || !params || !paths || !paths->matches_dir || !paths->image_basenames || !paths->views)
+    return fail(ctx, R3D_ERR_INVALID, "r3d_compute_matches: bad arguments");
+  const uint32_t N = paths->n_views;
+  const uint32_t dim = params->descriptor_dim ? params->descriptor_dim : 144;  // R3D_AKAZE_LIOP_Regions
+  const std::string dir(paths->matches_dir);
+  if (stats) {
+    stats->putative_pairs = stats->putative_matches = stats->f_pairs = stats->f_matches = 0;
+    stats->seconds_load = stats->seconds_match = stats->seconds_filter = 0;
+  }
+  // ---- regions ------------------------------------------------------------------------------------
+  double t0 = now_s();
+  int rc = r3d_clear_regions(ctx);
+  if (rc) return rc;
+  std::vector<float> xy, desc;
+  for (uint32_t v = 0; v < N; ++v) {
+    const std::string base = dir + "/" + paths->image_basenames[v];
+    uint64_t n = 0;
+    if (!load_feat(base + ".feat", xy) || !load_desc(base + ".desc", dim, desc, &n))
+      return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot read regions of " + base);  // "Invalid regions"
+    if (xy.size() / 2 != n) return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: .feat/.desc count mismatch for " + base);
+    rc = r3d_upload_regions(ctx, v, desc.data(), (uint32_t)n, dim, R3D_F32, xy.data());
+    if (rc) return rc;
+    if (stats && stats->number_of_keypoints && v < stats->n_views) stats->number_of_keypoints[v] = (uint32_t)n;
+  }
+  if (stats) stats->seconds_load = now_s() - t0;
+  // ---- putative matches ---------------------------------------------------------------------------
+  if (cb) cb(0.7f, "Computing matches", user);
+  t0 = now_s();
+  std::vector<uint32_t> pairs;
+  for (uint32_t i = 0; i < N; ++i)
+    for (uint32_t j = i + 1; j < N; ++j) { pairs.push_back(i); pairs.push_back(j); }
+  r3d_matches* put = nullptr;
+  // every matchingAlgorithm value of the reference (0 FLANN, 1-3 KGraph, 4 brute force, 5 MRPT, 6-8 HNSW:
+  // src/R3DComputeMatches.cpp:2036-2062) maps to the exact brute-force matcher: the ANN variants are
+  // approximations of it
+  rc = r3d_match_pairs(ctx, pairs.data(), pairs.size() / 2, params->dist_ratio, R3D_MATCH_DEFAULT, &put);
+  if (rc) return rc;
+  if (stats) {
+    stats->seconds_match = now_s() - t0;
+    stats->putative_pairs = r3d_matches_num_pairs(put);
+    stats->putative_matches = r3d_matches_total(put);
+  }
+  rc = r3d_save_matches_txt(put, (dir + "/matches.putative.txt").c_str());
+  if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save matches.putative.txt"); }
+  // ---- geometric filtering -------------------------------------------------------------------------
+  if (params->compute_fundamental) {
+    if (cb) cb(0.8f, "Calculate fundamental matrix", user);
+    t0 = now_s();
+    r3d_matches* fm = nullptr;
+    rc = r3d_filter_pairs(ctx, R3D_MODEL_F, 4.0, 2048, put, paths->views, N, &fm);  // maxResidualError 4.0, 2048 iterations
+    if (rc) { r3d_free_matches(put); return rc; }
+    if (stats) {
+      stats->seconds_filter = now_s() - t0;
+      stats->f_pairs = r3d_matches_num_pairs(fm);
+      stats->f_matches = r3d_matches_total(fm);
+    }
+    const std::string fpath = paths->matches_f_filename ? std::string(paths->matches_f_filename) : dir + "/matches.f.txt";
+    rc = r3d_save_matches_txt(fm, fpath.c_str());
+    r3d_free_matches(fm);
+    if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + fpath); }
+  }
+  // essential / homography filters (src/R3DComputeMatches.cpp:2130-2233) are not built in this round
+  r3d_free_matches(put);
+  if (cb) cb(1.0f, "Done", user);
+  return R3D_OK;
 }

@@ -1,0 +1,69 @@
+"""-m gpu: the file-level twin of R3DComputeMatches::computeMatches() and the C++ shim class:
+.feat/.desc in, matches.putative.txt / matches.f.txt out, byte-identical to the oracle's files."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from regard3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_project(oracle, tmp_path, n_img=4, n_feat=1500):
+    sc = synth.make_scene(n_img, n_feat, 144, "liop", seed=41)
+    names = ["image%06d" % v for v in range(n_img)]
+    for v in range(n_img):
+        assert oracle.save_feat(str(tmp_path / (names[v] + ".feat")), sc["feats"][v]) == 0
+        assert oracle.save_desc(str(tmp_path / (names[v] + ".desc")), sc["descs"][v]) == 0
+    return sc, names
+
+
+def _oracle_files(oracle, sc, tmp_path):
+    pairs = synth.exhaustive_pairs(len(sc["descs"]))
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.6)
+    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m)
+    po = str(tmp_path / "oracle.putative.txt")
+    pf = str(tmp_path / "oracle.f.txt")
+    oracle.save_matches_txt(po, pairs, ofs, m)
+    oracle.save_matches_txt(pf, pairs, fo, fm)
+    return open(po).read(), open(pf).read()
+
+
+def test_compute_matches_files_equal_oracle(gpu_ctx, oracle, tmp_path):
+    sc, names = _write_project(oracle, tmp_path)
+    seen = []
+    stats = gpu_ctx.compute_matches(str(tmp_path), names, sc["widths"], sc["heights"], dist_ratio=0.6, dim=144,
+                                    progress=lambda f, msg, user: seen.append(round(f, 2)))
+    exp_put, exp_f = _oracle_files(oracle, sc, tmp_path)
+    assert open(tmp_path / "matches.putative.txt").read() == exp_put
+    assert open(tmp_path / "matches.f.txt").read() == exp_f
+    assert stats["number_of_keypoints"] == [1500] * 4
+    assert stats["putative_pairs"] == 6 and stats["f_pairs"] == 6
+    assert seen[:2] == [0.7, 0.8]                       # the reference's progress fractions
+
+
+def test_cpp_shim_class(r3dlib, oracle, tmp_path):
+    sc, names = _write_project(oracle, tmp_path, n_img=3, n_feat=1000)
+    lib = r3dlib.lib()
+    n = len(names)
+    files = (C.c_char_p * n)(*[(nm + ".jpg").encode() for nm in names])
+    w = (C.c_uint32 * n)(*[1920] * n)
+    h = (C.c_uint32 * n)(*[1080] * n)
+    kp = (C.c_uint32 * n)()
+    pp, fp = C.c_uint64(), C.c_uint64()
+    last = C.c_float()
+    rc = lib.r3d_shim_compute_matches(str(tmp_path).encode(), files, w, h, n, C.c_float(0.6), 4, kp, C.byref(pp),
+                                      C.byref(fp), C.byref(last))
+    assert rc == 0
+    assert list(kp) == [1000] * 3 and pp.value == 3 and fp.value == 3 and last.value == 1.0
+    exp_put, exp_f = _oracle_files(oracle, sc, tmp_path)
+    assert open(tmp_path / "matches.putative.txt").read() == exp_put
+    assert open(tmp_path / "matches.f.txt").read() == exp_f
+
+
+def test_missing_region_file_is_an_error(gpu_ctx, r3dlib, tmp_path):
+    with pytest.raises(r3dlib.R3DError) as e:
+        gpu_ctx.compute_matches(str(tmp_path), ["image000000", "image000001"], [640, 640], [480, 480])
+    assert e.value.code == -4
