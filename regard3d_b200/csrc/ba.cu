@@ -104,11 +104,29 @@ __global__ void __launch_bounds__(256) k_ba_eval(Dev d) {
       atomicAdd(&d.gu[6 * (size_t)cam + k], rho1 * (Jc[k] * r[0] + Jc[6 + k] * r[1]));
       atomicAdd(&d.du[6 * (size_t)cam + k], rho1 * (Jc[k] * Jc[k] + Jc[6 + k] * Jc[6 + k]));
     }
-    if (d.refine_intr)
+    if (d.refine_intr) {
+      // every observation of a group hits the same 12 addresses: reduce over the warp first when the
+      // active lanes agree on the group (always true for a single shared intrinsic)
+      const unsigned active = __activemask();
+      const bool uniform = __match_any_sync(active, gi) == active;
       for (int k = 0; k < 6; ++k) {
-        atomicAdd(&d.gu[intr_col(d, gi) + k], rho1 * (Ji[k] * r[0] + Ji[6 + k] * r[1]));
-        atomicAdd(&d.du[intr_col(d, gi) + k], rho1 * (Ji[k] * Ji[k] + Ji[6 + k] * Ji[6 + k]));
+        double gv = rho1 * (Ji[k] * r[0] + Ji[6 + k] * r[1]);
+        double dv = rho1 * (Ji[k] * Ji[k] + Ji[6 + k] * Ji[6 + k]);
+        if (uniform && active == 0xffffffffu) {
+          for (int o = 16; o >= 1; o >>= 1) {
+            gv += __shfl_xor_sync(0xffffffffu, gv, o);
+            dv += __shfl_xor_sync(0xffffffffu, dv, o);
+          }
+          if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&d.gu[intr_col(d, gi) + k], gv);
+            atomicAdd(&d.du[intr_col(d, gi) + k], dv);
+          }
+        } else {
+          atomicAdd(&d.gu[intr_col(d, gi) + k], gv);
+          atomicAdd(&d.du[intr_col(d, gi) + k], dv);
+        }
       }
+    }
     for (int k = 0; k < 3; ++k) {
       atomicAdd(&d.gu[(size_t)d.nB + 3 * (size_t)pt + k], rho1 * (Jp[k] * r[0] + Jp[3 + k] * r[1]));
       atomicAdd(&d.du[(size_t)d.nB + 3 * (size_t)pt + k], rho1 * (Jp[k] * Jp[k] + Jp[3 + k] * Jp[3 + k]));
@@ -197,6 +215,13 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
   double* W = J + (size_t)obs_cap * kObsDoubles;
   __shared__ uint32_t s_colc[kSchurWarps][kMaxObsPerPoint];
   __shared__ int s_colg[kSchurWarps][kMaxObsPerPoint];
+  __shared__ double s_gg_warp[kSchurWarps][36];  // (g0,g0) block of each warp's point, g0 = group of its first obs
+  __shared__ double s_rg_warp[kSchurWarps][6];   // rhs of that group
+  __shared__ int s_g0[kSchurWarps];
+  if (lane == 0) s_g0[warp] = -1;
+  for (int e = lane; e < 6; e += 32) s_rg_warp[warp][e] = 0.0;
+  for (int e = lane; e < 36; e += 32) s_gg_warp[warp][e] = 0.0;
+  __syncwarp();
   const uint32_t ip = blockIdx.x * kSchurWarps + warp;
   if (ip < d.n_pts) {
     const uint32_t b = d.pt_ofs[ip], e = d.pt_ofs[ip + 1];
@@ -226,7 +251,9 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
     const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
     const double Vg[3] = {Vi[0] * gp[0] + Vi[1] * gp[1] + Vi[2] * gp[2], Vi[3] * gp[0] + Vi[4] * gp[1] + Vi[5] * gp[2],
                           Vi[6] * gp[0] + Vi[7] * gp[1] + Vi[8] * gp[2]};
-    // 3. W blocks (6x3): camera and intrinsic group of every observation; B part of S
+    // 3. W blocks (6x3): camera and intrinsic group of every observation; B part of S.
+    //    Observations that share an intrinsic group are merged into ONE group block per point
+    //    (W_g = sum W_g,t): the pair loop below then touches the heavily shared group columns once.
     for (int t = lane; t < nobs; t += 32) {
       const double* jt = J + (size_t)t * kObsDoubles;
       const double *jc = jt, *jg = jt + 12, *jp = jt + 24;
@@ -247,19 +274,54 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
         for (int i = 0; i < 6; ++i)
           for (int j = 0; j < 6; ++j) blk[6 * i + j] = jc[i] * jg[j] + jc[6 + i] * jg[6 + j];
         add_block_upper(d.S, d.nB, cc, (uint32_t)cg, blk, 1.0);
-        for (int i = 0; i < 6; ++i)
-          for (int j = 0; j < 6; ++j) blk[6 * i + j] = jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
-        add_block_upper(d.S, d.nB, (uint32_t)cg, (uint32_t)cg, blk, 1.0);
       }
     }
     __syncwarp();
-    // 4. Schur part over the 2*nobs blocks (camera t -> block 2t, group t -> block 2t+1)
+    // group merge: the first observation of each group becomes its leader; GG = sum Jg^T Jg per leader
+    double* GG = s_gg_warp[warp];  // 36 doubles of the (first) leader; other leaders go straight to global
+    for (int e = lane; e < 36; e += 32) GG[e] = 0.0;
+    __syncwarp();
+    if (lane == 0 && d.refine_intr) {
+      for (int t = 0; t < nobs; ++t) {
+        const int cg = s_colg[warp][t];
+        if (cg < 0) continue;
+        int leader = t;
+        for (int u = 0; u < t; ++u)
+          if (s_colg[warp][u] == cg) { leader = u; break; }
+        const double* jg = J + (size_t)t * kObsDoubles + 12;
+        if (leader != t) {
+          double* wl = W + (size_t)leader * 36 + 18;
+          const double* wt = W + (size_t)t * 36 + 18;
+          for (int e = 0; e < 18; ++e) wl[e] += wt[e];
+          s_colg[warp][t] = -1;  // merged away
+        }
+        if (leader == 0 || s_colg[warp][0] == cg) {  // contributions to the first group: warp-local block
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) GG[6 * i + j] += jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
+        } else {
+          double blk[36];
+          for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) blk[6 * i + j] = jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
+          add_block_upper(d.S, d.nB, (uint32_t)cg, (uint32_t)cg, blk, 1.0);
+        }
+      }
+    }
+    __syncwarp();
+    // 4. Schur part over the 2*nobs blocks (camera t -> block 2t, group t -> block 2t+1; merged groups are -1)
     const int nblk = 2 * nobs;
+    int g0 = -1;
+    for (int t = 0; t < nobs; ++t)
+      if (s_colg[warp][t] >= 0) { g0 = s_colg[warp][t]; break; }
+    if (lane == 0) s_g0[warp] = g0;
     for (int a = lane; a < nblk; a += 32) {  // rhs[a] += W_a V^-1 g_p
       const int ca = (a & 1) ? s_colg[warp][a >> 1] : (int)s_colc[warp][a >> 1];
       if (ca < 0) continue;
       const double* wa = W + (size_t)(a >> 1) * 36 + (a & 1) * 18;
-      for (int i = 0; i < 6; ++i) atomicAdd(&d.rhs[ca + i], wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2]);
+      if ((a & 1) && ca == g0) {  // the (merged) first group: unique writer inside this warp
+        for (int i = 0; i < 6; ++i) s_rg_warp[warp][i] += wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2];
+      } else {
+        for (int i = 0; i < 6; ++i) atomicAdd(&d.rhs[ca + i], wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2]);
+      }
     }
     const int npairs = nblk * (nblk + 1) / 2;
     for (int pr = lane; pr < npairs; pr += 32) {
@@ -282,7 +344,9 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
         for (int j = 0; j < 6; ++j) blk[6 * i + j] = WV[3 * i] * wh[3 * j] + WV[3 * i + 1] * wh[3 * j + 1] + WV[3 * i + 2] * wh[3 * j + 2];
       // blk = W_lo V^-1 W_hi^T  contributes to S[cl, ch]; for lo != hi the mirrored term S[ch, cl] is
       // its transpose: in upper-block form both land on the same stored block (doubling when cl == ch).
-      if (lo == hi) {
+      if (lo == hi && (lo & 1) && cl == g0) {  // merged first group: single writer -> shared memory
+        for (int e = 0; e < 36; ++e) s_gg_warp[warp][e] -= blk[e];
+      } else if (lo == hi) {
         add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
       } else if (cl == ch) {  // two different observations sharing a block (same intrinsic group / camera)
         double sym[36];
@@ -291,6 +355,28 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
         add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, sym, -1.0);
       } else {
         add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
+      }
+    }
+  }
+  // CTA-level reduction of the per-warp (g0,g0) blocks and group right-hand sides: one set of global
+  // atomics per CTA and distinct group instead of one per point
+  __syncthreads();
+  if (threadIdx.x < 42) {
+    const int e = threadIdx.x;
+    for (int wv = 0; wv < kSchurWarps; ++wv) {
+      const int g = s_g0[wv];
+      if (g < 0) continue;
+      bool first = true;
+      for (int u = 0; u < wv; ++u)
+        if (s_g0[u] == g) { first = false; break; }
+      if (!first) continue;
+      double acc = 0.0;
+      for (int u = wv; u < kSchurWarps; ++u)
+        if (s_g0[u] == g) acc += (e < 36) ? s_gg_warp[u][e] : s_rg_warp[u][e - 36];
+      if (e < 36) {
+        atomicAdd(&d.S[(size_t)(g + e / 6) * d.nB + g + e % 6], acc);
+      } else {
+        atomicAdd(&d.rhs[g + e - 36], acc);
       }
     }
   }
@@ -362,16 +448,19 @@ __global__ void __launch_bounds__(1024) k_chol_syrk(double* A, int n, int k0) {
     A[(size_t)i * n + j] -= s;
   }
 }
-// L y = b ; L^T x = y   (single block)
+// L y = b ; L^T x = y   (single block; the 32x32 diagonal tiles are staged in shared memory)
 __global__ void __launch_bounds__(1024) k_chol_solve(const double* A, int n, double* b) {
   __shared__ double xs[NB];
+  __shared__ double T[NB][NB + 1];
   for (int k0 = 0; k0 < n; k0 += NB) {  // forward
     const int kb = min(NB, n - k0);
+    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) T[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
+    __syncthreads();
     if (threadIdx.x == 0)
       for (int j = 0; j < kb; ++j) {
         double s = b[k0 + j];
-        for (int tt = 0; tt < j; ++tt) s -= A[(size_t)(k0 + j) * n + k0 + tt] * xs[tt];
-        xs[j] = s / A[(size_t)(k0 + j) * n + k0 + j];
+        for (int tt = 0; tt < j; ++tt) s -= T[j][tt] * xs[tt];
+        xs[j] = s / T[j][j];
         b[k0 + j] = xs[j];
       }
     __syncthreads();
@@ -385,11 +474,13 @@ __global__ void __launch_bounds__(1024) k_chol_solve(const double* A, int n, dou
   const int nblk = (n + NB - 1) / NB;
   for (int kbk = nblk - 1; kbk >= 0; --kbk) {  // backward
     const int k0 = kbk * NB, kb = min(NB, n - k0);
+    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) T[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
+    __syncthreads();
     if (threadIdx.x == 0)
       for (int j = kb - 1; j >= 0; --j) {
         double s = b[k0 + j];
-        for (int tt = j + 1; tt < kb; ++tt) s -= A[(size_t)(k0 + tt) * n + k0 + j] * xs[tt];
-        xs[j] = s / A[(size_t)(k0 + j) * n + k0 + j];
+        for (int tt = j + 1; tt < kb; ++tt) s -= T[tt][j] * xs[tt];
+        xs[j] = s / T[j][j];
         b[k0 + j] = xs[j];
       }
     __syncthreads();
