@@ -140,6 +140,7 @@ typedef struct {
   double initial_cost, final_cost;
   int termination;           /* 0 max iters, 1 function tol, 2 gradient tol, 3 parameter tol, 4 failure */
   double seconds_total, seconds_linear;
+  double seconds_setup;      /* validation, CSR build, uploads (inside seconds_total) */
 } r3d_ba_summary;
 
 void r3d_ba_default_options(r3d_ba_options* o);

@@ -66,7 +66,7 @@ class BAOptions(C.Structure):
 class BASummary(C.Structure):
     _fields_ = [("iterations", C.c_uint32), ("successful_steps", C.c_uint32), ("initial_cost", C.c_double),
                 ("final_cost", C.c_double), ("termination", C.c_int), ("seconds_total", C.c_double),
-                ("seconds_linear", C.c_double)]
+                ("seconds_linear", C.c_double), ("seconds_setup", C.c_double)]
 
 
 class CMParams(C.Structure):

@@ -45,7 +45,7 @@ struct PairState {
   uint32_t best_k = 0;
   // per-round bookkeeping
   uint32_t hyp_ofs = 0, hyp_n = 0;
-  std::vector<uint32_t> snap_index;
+  std::vector<uint32_t> swap_log;  // 7 swap targets per drawn iteration (undo log of the partial Fisher-Yates)
   std::mt19937 snap_rng;
   uint32_t since_event = 0;
   bool best_changed = false, event = false;
@@ -54,14 +54,23 @@ struct PairState {
 };
 
 // rand_sampling.hpp UniformSample(num_samples, rng, &vec_index, &sample)
-inline void uniform_sample7(std::mt19937& rng, std::vector<uint32_t>& vec_index, uint32_t* sample) {
+inline void uniform_sample7(std::mt19937& rng, std::vector<uint32_t>& vec_index, uint32_t* sample, uint32_t* log7) {
   const uint32_t last_idx = (uint32_t)vec_index.size() - 1;
   for (uint32_t i = 0; i < 7; ++i) {
     std::uniform_int_distribution<uint32_t> distribution(i, last_idx);
     const uint32_t sample_idx = distribution(rng);
     std::swap(vec_index[i], vec_index[sample_idx]);
+    log7[i] = sample_idx;
   }
   for (uint32_t i = 0; i < 7; ++i) sample[i] = vec_index[i];
+}
+// advance the generator exactly like uniform_sample7 does, without touching the pool
+inline void skip_sample7(std::mt19937& rng, uint32_t pool_size) {
+  const uint32_t last_idx = pool_size - 1;
+  for (uint32_t i = 0; i < 7; ++i) {
+    std::uniform_int_distribution<uint32_t> distribution(i, last_idx);
+    (void)distribution(rng);
+  }
 }
 
 template <typename T>
@@ -99,52 +108,32 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
   std::vector<double2> hx1, hx2;
   std::vector<float> hlogc_n;
   uint32_t maxM = 0;
-  for (uint64_t p = 0; p < P; ++p) {
-    const uint32_t I = put->pairs[2 * p], J = put->pairs[2 * p + 1];
-    const uint32_t M = (uint32_t)(put->ofs[p + 1] - put->ofs[p]);
-    if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
-    if (I >= n_views || J >= n_views) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: view id outside views[]");
-    auto vi = w.views.find(I), vj = w.views.find(J);
-    if (vi == w.views.end() || vj == w.views.end() || !vi->second.has_xy || !vj->second.has_xy)
-      return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: positions of a view were not uploaded");
-    PairState s;
-    s.src = (uint32_t)p; s.I = I; s.J = J; s.M = M;
-    s.pt_ofs = (uint32_t)hx1.size();
-    s.tbl_ofs = (uint32_t)hlogc_n.size();
-    const int wI = (int)views[I].width, hI = (int)views[I].height, wJ = (int)views[J].width, hJ = (int)views[J].height;
-    const double s1 = 1.0 / std::sqrt((double)(wI * hI));
-    const double s2 = 1.0 / std::sqrt((double)(wJ * hJ));
-    const double c1x = (double)(-.5f * wI) * s1, c1y = -.5 * hI * s1;
-    const double c2x = (double)(-.5f * wJ) * s2, c2y = -.5 * hJ * s2;
-    const float* xyI = vi->second.h_xy.data();
-    const float* xyJ = vj->second.h_xy.data();
-    for (uint32_t k = 0; k < M; ++k) {
-      const r3d_indmatch m = put->m[put->ofs[p] + k];
-      if (m.i >= vi->second.n || m.j >= vj->second.n) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
-      const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
-      const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
-      hx1.push_back(make_double2(s1 * xi + c1x, s1 * yi + c1y));
-      hx2.push_back(make_double2(s2 * xj + c2x, s2 * yj + c2y));
+  {
+    uint64_t pt_total = 0, tbl_total = 0;
+    for (uint64_t p = 0; p < P; ++p) {
+      const uint32_t I = put->pairs[2 * p], J = put->pairs[2 * p + 1];
+      const uint32_t M = (uint32_t)(put->ofs[p + 1] - put->ofs[p]);
+      if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
+      if (I >= n_views || J >= n_views) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: view id outside views[]");
+      auto vi = w.views.find(I), vj = w.views.find(J);
+      if (vi == w.views.end() || vj == w.views.end() || !vi->second.has_xy || !vj->second.has_xy)
+        return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: positions of a view were not uploaded");
+      PairState s;
+      s.src = (uint32_t)p; s.I = I; s.J = J; s.M = M;
+      s.pt_ofs = (uint32_t)pt_total;
+      s.tbl_ofs = (uint32_t)tbl_total;
+      pt_total += M;
+      tbl_total += M + 1;
+      maxM = std::max(maxM, M);
+      st.push_back(std::move(s));
     }
-    AcPair ap;
-    ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
-    const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
-    ap.max_thr = precision * s2 * s2;
-    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
-    const double Aarea = (double)wJ * (double)hJ;
-    ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
-    ap.loge0 = dm::log10_det((double)MAX_MODELS * (double)(M - sizeSample));
-    hpairs.push_back(ap);
-    hlogc_n.resize(hlogc_n.size() + M + 1);
-    s.vec_index.resize(M);
-    std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
-    s.nIterReserve = max_iter / 10;
-    s.nIter = max_iter - s.nIterReserve;
-    s.ac_mode = (precision == std::numeric_limits<double>::infinity());
-    maxM = std::max(maxM, M);
-    st.push_back(std::move(s));
+    if (st.empty()) return R3D_OK;
+    if (pt_total > 0xfffffff0ull) return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: too many putative matches in one call");
+    hx1.resize(pt_total);
+    hx2.resize(pt_total);
+    hlogc_n.resize(tbl_total);
+    hpairs.resize(st.size());
   }
-  if (st.empty()) return R3D_OK;
   // log-combinatorial tables (float, upstream makelogcombi_n / makelogcombi_k).  logcombi(k,n) is a
   // running float sum over i = 1..min(k,n-k): its partial sums ARE the entries for smaller k, so one
   // O(n) pass reproduces the upstream O(n^2) table bit for bit.
@@ -159,20 +148,54 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     for (uint32_t i = 1; i <= k; ++i) r += vlog10[n - i + 1] - vlog10[i];
     hlogc_k[n] = r;
   }
-  {
-    std::vector<float> pre;
-    for (const PairState& s : st) {
-      const uint32_t n = s.M;
-      pre.assign(n / 2 + 1, 0.f);
-      float r = 0.f;
-      for (uint32_t i = 1; i <= n / 2; ++i) {
-        r += vlog10[n - i + 1] - vlog10[i];
-        pre[i] = r;
-      }
-      float* t = hlogc_n.data() + s.tbl_ofs;
-      for (uint32_t k = 0; k <= n; ++k) t[k] = (k >= n || k == 0) ? 0.f : pre[std::min(k, n - k)];
+  std::atomic<int> bad{0};
+  parallel_for(ctx->host_threads, st.size(), [&](size_t a) {
+    PairState& s = st[a];
+    const uint64_t p = s.src;
+    const uint32_t M = s.M;
+    const ViewDev& vi = w.views.find(s.I)->second;
+    const ViewDev& vj = w.views.find(s.J)->second;
+    const int wI = (int)views[s.I].width, hI = (int)views[s.I].height, wJ = (int)views[s.J].width, hJ = (int)views[s.J].height;
+    const double s1 = 1.0 / std::sqrt((double)(wI * hI));
+    const double s2 = 1.0 / std::sqrt((double)(wJ * hJ));
+    const double c1x = (double)(-.5f * wI) * s1, c1y = -.5 * hI * s1;
+    const double c2x = (double)(-.5f * wJ) * s2, c2y = -.5 * hJ * s2;
+    const float* xyI = vi.h_xy.data();
+    const float* xyJ = vj.h_xy.data();
+    for (uint32_t k = 0; k < M; ++k) {
+      const r3d_indmatch m = put->m[put->ofs[p] + k];
+      if (m.i >= vi.n || m.j >= vj.n) { bad.store(1); return; }
+      const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
+      const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
+      hx1[s.pt_ofs + k] = make_double2(s1 * xi + c1x, s1 * yi + c1y);
+      hx2[s.pt_ofs + k] = make_double2(s2 * xj + c2x, s2 * yj + c2y);
     }
-  }
+    AcPair ap;
+    ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
+    const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
+    ap.max_thr = precision * s2 * s2;
+    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+    const double Aarea = (double)wJ * (double)hJ;
+    ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
+    ap.loge0 = dm::log10_det((double)MAX_MODELS * (double)(M - sizeSample));
+    hpairs[a] = ap;
+    s.vec_index.resize(M);
+    std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
+    s.nIterReserve = max_iter / 10;
+    s.nIter = max_iter - s.nIterReserve;
+    s.ac_mode = (precision == std::numeric_limits<double>::infinity());
+    // logc_n table of this pair
+    const uint32_t n = M;
+    float* t = hlogc_n.data() + s.tbl_ofs;
+    t[0] = 0.f;
+    float r = 0.f;
+    for (uint32_t i = 1; i <= n / 2; ++i) {
+      r += vlog10[n - i + 1] - vlog10[i];
+      t[i] = r;
+    }
+    for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
+  });
+  if (bad.load()) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
   uint32_t cap = 32;
   while (cap < maxM) cap <<= 1;
   if ((size_t)cap * 12 > 200 * 1024)
@@ -213,24 +236,29 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
   while (!active.empty()) {
     T.rounds++;
     // ---- 1. draw a batch of samples ahead for every active pair -----------------------------
-    hhyp.clear();
     uint32_t budget = std::max<uint32_t>(8u, kMaxHypPerRound / (uint32_t)active.size());
+    uint32_t Htot = 0;
     for (uint32_t a : active) {
       PairState& s = st[a];
       uint32_t B = std::min<uint32_t>(std::max<uint32_t>(8u, 2u * s.since_event), 128u);
       B = std::min(B, budget);
       B = std::min(B, s.nIter - s.iter);
-      s.snap_index = s.vec_index;
-      s.snap_rng = s.rng;
-      s.hyp_ofs = (uint32_t)hhyp.size();
+      s.hyp_ofs = Htot;
       s.hyp_n = B;
-      for (uint32_t b = 0; b < B; ++b) {
-        AcHyp h;
-        h.pair = a;
-        uniform_sample7(s.rng, s.vec_index, h.sample);
-        hhyp.push_back(h);
-      }
+      Htot += B;
     }
+    hhyp.resize(Htot);
+    parallel_for(ctx->host_threads, active.size(), [&](size_t ai) {
+      const uint32_t a = active[ai];
+      PairState& s = st[a];
+      s.snap_rng = s.rng;
+      s.swap_log.resize((size_t)s.hyp_n * 7);
+      for (uint32_t b = 0; b < s.hyp_n; ++b) {
+        AcHyp& h = hhyp[s.hyp_ofs + b];
+        h.pair = a;
+        uniform_sample7(s.rng, s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
+      }
+    });
     const uint32_t H = (uint32_t)hhyp.size();
     T.hypotheses += H;
     R3D_CUDA_TRY(ctx, d_hyp.ensure(H));
@@ -257,10 +285,8 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     cudaEventElapsedTime(&ms, ev[1], ev[2]); T.ms_score += ms;
     const double t_host0 = now_ms();
     // ---- 3. replay the ACRANSAC state machine over the batch ----------------------------------
-    hreq.clear();
-    uint32_t inl_total = 0;
-    for (uint32_t a : active) {
-      PairState& s = st[a];
+    parallel_for(ctx->host_threads, active.size(), [&](size_t ai) {
+      PairState& s = st[active[ai]];
       s.best_changed = false;
       s.event = false;
       uint32_t consumed = s.hyp_n;
@@ -293,14 +319,19 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
           }
         }
       }
-      if (consumed < s.hyp_n) {  // discard the speculative tail: rewind and replay the sampler
-        s.vec_index = s.snap_index;
+      if (consumed < s.hyp_n) {  // discard the speculative tail: undo its swaps, replay the generator
+        for (uint32_t b = s.hyp_n; b-- > consumed;)
+          for (int i = 6; i >= 0; --i) std::swap(s.vec_index[i], s.vec_index[s.swap_log[(size_t)b * 7 + i]]);
         s.rng = s.snap_rng;
-        uint32_t tmp[7];
-        for (uint32_t b = 0; b < consumed; ++b) uniform_sample7(s.rng, s.vec_index, tmp);
+        for (uint32_t b = 0; b < consumed; ++b) skip_sample7(s.rng, (uint32_t)s.vec_index.size());
       }
       s.iter += consumed;
       s.since_event = s.event ? 0 : s.since_event + consumed;
+    });
+    hreq.clear();
+    uint32_t inl_total = 0;
+    for (uint32_t a : active) {
+      PairState& s = st[a];
       if (s.best_changed) {  // the best model's inlier list is needed now (event) or possibly later
         AcInlierReq rq;
         rq.pair = a; rq.k = s.best_k; rq.out_ofs = inl_total; rq.hyp_model = s.best_hyp * 3 + s.best_model;

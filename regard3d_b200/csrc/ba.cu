@@ -552,14 +552,20 @@ using r3d::ba::Dev;
 
 namespace {
 
-struct DeviceArrays {
+struct DeviceArrays {  // blocks come from (and return to) the worker's size-bucketed pool: no cudaMalloc per call
+  DeviceWorker* w = nullptr;
   std::vector<void*> ptrs;
-  ~DeviceArrays() { for (void* p : ptrs) cudaFree(p); }
+  ~DeviceArrays() {
+    if (!w) return;
+    cudaStreamSynchronize(w->stream);
+    for (void* p : ptrs) pool_release(*w, p);
+  }
   template <typename T>
   cudaError_t alloc(T** p, size_t n) {
-    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(*p);
-    return e;
+    *p = (T*)pool_alloc(*w, std::max<size_t>(n, 1) * sizeof(T));
+    if (!*p) return cudaErrorMemoryAllocation;
+    ptrs.push_back(*p);
+    return cudaSuccess;
   }
 };
 
@@ -652,6 +658,7 @@ int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res) {
   DeviceWorker& w = ctx->workers[0];
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   DeviceArrays mem;
+  mem.w = &w;
   Dev d;
   int rc = setup_problem(ctx, w, p, mem, d, false, 0.0, false);
   if (rc) return rc;
@@ -670,11 +677,13 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   DeviceWorker& w = ctx->workers[0];
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   DeviceArrays mem;
+  mem.w = &w;
   Dev d;
   uint32_t max_obs = 1;
   int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs);
   if (rc) return rc;
   const int obs_cap = (int)std::max<uint32_t>(max_obs, 1u);
+  sum->seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   const size_t nparam = (size_t)d.nB + 3 * (size_t)d.n_pts;
   const int grid_obs = w.sm_count * 8;
   const int nB = (int)d.nB;

@@ -32,27 +32,6 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-template <typename F>
-void parallel_for(int n_threads, size_t n, F&& f) {
-  if (n == 0) return;
-  if (n_threads <= 1 || n == 1) {
-    for (size_t i = 0; i < n; ++i) f(i);
-    return;
-  }
-  std::atomic<size_t> next{0};
-  std::vector<std::thread> th;
-  const int nt = (int)std::min<size_t>((size_t)n_threads, n);
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([&]() {
-      for (;;) {
-        const size_t i = next.fetch_add(1);
-        if (i >= n) break;
-        f(i);
-      }
-    });
-  for (auto& t : th) t.join();
-}
-
 float pair_eps(const ViewDev& vi, const ViewDev& vj) {
   const double nI = vi.max_norm, nJ = vj.max_norm;
   double e = 2.0 * ((double)vi.max_dnorm * nJ + (double)vi.max_hnorm * (double)vj.max_dnorm);

@@ -5,8 +5,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
+#include <thread>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -154,6 +157,28 @@ int ensure_capacity(r3d_ctx* ctx, void** p, size_t* cap, size_t need_elems) {
 int prepare_views(r3d_ctx* ctx, DeviceWorker& w);
 void* pool_alloc(DeviceWorker& w, size_t bytes);  // nullptr on failure
 void pool_release(DeviceWorker& w, void* p);
+
+// dynamic-scheduling parallel loop on std::thread (host post-processing, RANSAC state machines)
+template <typename F>
+inline void parallel_for(int n_threads, size_t n, F&& f) {
+  if (n == 0) return;
+  if (n_threads <= 1 || n == 1) {
+    for (size_t i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  const int nt = (int)std::min<size_t>((size_t)n_threads, n);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
 
 // ---- kernels (defined in the .cu files) --------------------------------------------------------
 // operand preparation
