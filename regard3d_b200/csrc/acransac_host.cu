@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -232,9 +234,13 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
   std::vector<uint32_t> active(st.size());
   std::iota(active.begin(), active.end(), 0u);
   const uint32_t kMaxHypPerRound = 1u << 18;
+  // per-round loops are short (microseconds per pair): a handful of threads beats spawning one per core
+  const int round_threads = std::min(ctx->host_threads, 8);
 
+  double tm_setup = now_ms() - t_begin, tm_sample = 0, tm_gpu_wait = 0, tm_scan = 0, tm_inl = 0, tm_tail = 0;
   while (!active.empty()) {
     T.rounds++;
+    double tq = now_ms();
     // ---- 1. draw a batch of samples ahead for every active pair -----------------------------
     uint32_t budget = std::max<uint32_t>(8u, kMaxHypPerRound / (uint32_t)active.size());
     uint32_t Htot = 0;
@@ -248,7 +254,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
       Htot += B;
     }
     hhyp.resize(Htot);
-    parallel_for(ctx->host_threads, active.size(), [&](size_t ai) {
+    parallel_for(round_threads, active.size(), [&](size_t ai) {
       const uint32_t a = active[ai];
       PairState& s = st[a];
       s.snap_rng = s.rng;
@@ -259,6 +265,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
         uniform_sample7(s.rng, s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
       }
     });
+    tm_sample += now_ms() - tq; tq = now_ms();
     const uint32_t H = (uint32_t)hhyp.size();
     T.hypotheses += H;
     R3D_CUDA_TRY(ctx, d_hyp.ensure(H));
@@ -284,8 +291,9 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     cudaEventElapsedTime(&ms, ev[0], ev[1]); T.ms_solve += ms;
     cudaEventElapsedTime(&ms, ev[1], ev[2]); T.ms_score += ms;
     const double t_host0 = now_ms();
+    tm_gpu_wait += now_ms() - tq; tq = now_ms();
     // ---- 3. replay the ACRANSAC state machine over the batch ----------------------------------
-    parallel_for(ctx->host_threads, active.size(), [&](size_t ai) {
+    parallel_for(round_threads, active.size(), [&](size_t ai) {
       PairState& s = st[active[ai]];
       s.best_changed = false;
       s.event = false;
@@ -339,6 +347,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
         inl_total += s.best_k;
       }
     }
+    tm_scan += now_ms() - tq; tq = now_ms();
     // ---- 4. fetch the inlier lists of the new best models --------------------------------------
     if (!hreq.empty()) {
       // the F matrices of this round are still on the device (d_F); the kernel reads them there
@@ -356,6 +365,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
         s.inliers.assign(hinl.begin() + rq.out_ofs, hinl.begin() + rq.out_ofs + rq.k);
       }
     }
+    tm_inl += now_ms() - tq; tq = now_ms();
     // ---- 5. pool replacement, termination ---------------------------------------------------------
     std::vector<uint32_t> next;
     for (uint32_t a : active) {
@@ -372,7 +382,11 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     }
     active.swap(next);
     T.ms_host += now_ms() - t_host0;
+    tm_tail += now_ms() - tq;
   }
+  if (getenv("R3D_DEBUG_TIMING"))
+    fprintf(stderr, "[r3d] filter: setup %.1f sample %.1f gpu+copies %.1f scan %.1f inliers %.1f tail %.1f ms, rounds %llu\n", tm_setup,
+            tm_sample, tm_gpu_wait, tm_scan, tm_inl, tm_tail, (unsigned long long)T.rounds);
   // ---- result: GeometricFilter_FMatrix_AC::Robust_estimation keeps the pair iff #inliers > 7*2.5 ----
   for (const PairState& s : st) {
     if (!(s.minNFA < 0)) continue;  // "if (minNFA >= 0) vec_inliers.clear()"
