@@ -166,17 +166,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)k
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N = 128, M = 128.
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
 
-// minimum of 16 accumulator columns, packed with the chunk id, inserted into the sorted 4-key set
+// minimum of kChunk accumulator columns, packed with the chunk id, inserted into the sorted key set
 __device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_id, uint32_t keep_mask,
                                              float (&key)[kNumKeys]) {
+  static_assert(kChunk == 8 || kChunk == 16, "chunk width");
   float m = fmin3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
   m = fmin3(m, __uint_as_float(v[3]), __uint_as_float(v[4]));
   m = fmin3(m, __uint_as_float(v[5]), __uint_as_float(v[6]));
-  m = fmin3(m, __uint_as_float(v[7]), __uint_as_float(v[8]));
-  m = fmin3(m, __uint_as_float(v[9]), __uint_as_float(v[10]));
-  m = fmin3(m, __uint_as_float(v[11]), __uint_as_float(v[12]));
-  m = fmin3(m, __uint_as_float(v[13]), __uint_as_float(v[14]));
-  m = fminf(m, __uint_as_float(v[15]));
+  if (kChunk == 16) {
+    m = fmin3(m, __uint_as_float(v[7]), __uint_as_float(v[8]));
+    m = fmin3(m, __uint_as_float(v[9]), __uint_as_float(v[10]));
+    m = fmin3(m, __uint_as_float(v[11]), __uint_as_float(v[12]));
+    m = fmin3(m, __uint_as_float(v[13]), __uint_as_float(v[14]));
+  }
+  m = fminf(m, __uint_as_float(v[kChunk - 1]));
   float x = __uint_as_float((__float_as_uint(m) & keep_mask) | chunk_id);
 #pragma unroll
   for (int i = 0; i < kNumKeys - 1; ++i) {  // sorted insertion network: 2 FMNMX per level
@@ -360,26 +363,27 @@ k_l2_candidates(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __rest
         const uint32_t taddr = tmem_base + ((lane_quarter * 32u) << 16) + (acc * kQB + qb) * kAccCols;
         const uint32_t chunk0 = t * (kTileRows / kChunk);
         uint32_t va[32], vb[32];
+        constexpr uint32_t kCpl = 32 / kChunk;  // chunks per 32-column TMEM load
         tc_ld32(taddr, va);
         tc_wait_ld(va);
         tc_ld32(taddr + 32, vb);
-        chunk_update(va, chunk0 + 0, keep_mask, key);
-        chunk_update(va + 16, chunk0 + 1, keep_mask, key);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + c, keep_mask, key);
         tc_wait_ld(vb);
         tc_ld32(taddr + 64, va);
-        chunk_update(vb, chunk0 + 2, keep_mask, key);
-        chunk_update(vb + 16, chunk0 + 3, keep_mask, key);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + kCpl + c, keep_mask, key);
         tc_wait_ld(va);
         tc_ld32(taddr + 96, vb);
-        chunk_update(va, chunk0 + 4, keep_mask, key);
-        chunk_update(va + 16, chunk0 + 5, keep_mask, key);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + 2 * kCpl + c, keep_mask, key);
         tc_wait_ld(vb);
-        // all TMEM reads of this stage are done: hand it back before the last two chunks
+        // all TMEM reads of this stage are done: hand it back before the last chunks
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-        chunk_update(vb, chunk0 + 6, keep_mask, key);
-        chunk_update(vb + 16, chunk0 + 7, keep_mask, key);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + 3 * kCpl + c, keep_mask, key);
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
       }

@@ -222,8 +222,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     if (any_tc) {
       if ((rc = launch_rerank_binned(ctx, w, (const PairDesc*)w.d_pairs, nb, max_nJ, cstride, (const uint32_t*)w.d_keys,
                                      dim, dtype, ratio2, (uint32_t*)w.d_cnt, (uint32_t*)w.d_slot, (uint32_t*)w.d_list,
-                                     w.d_parts, o.d_counters, d_matches, (uint2*)w.d_list2, d_nn))) return rc;
-      if ((rc = launch_rerank_list(ctx, w, (const PairDesc*)w.d_pairs, (const uint32_t*)w.d_keys, (const uint2*)w.d_list2,
+                                     w.d_parts, o.d_counters, d_matches, (uint2*)w.d_list2, (uint2*)w.d_fb, d_nn))) return rc;
+      if ((rc = launch_rerank_list(ctx, w, (const PairDesc*)w.d_pairs, (const uint32_t*)w.d_keys, w.d_parts, (const uint2*)w.d_list2,
                                    &o.d_counters[4], (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2,
                                    o.d_counters, d_matches, (uint2*)w.d_fb, d_nn))) return rc;
       launches += 6;

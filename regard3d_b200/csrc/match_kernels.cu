@@ -12,64 +12,63 @@
 namespace r3d {
 
 // ------------------------------------------------------------------------------------------------
-// k_rerank : one warp per listed (pair, query): certification stages A, B, C
+// k_rerank : one warp per listed (pair, query) -- stage B of the certification.  The query arrives
+// with the exact top-2 of its two best chunks (stage A, rerank_binned.cu); the warp re-ranks the next
+// kStageBChunks chunks (one lane per database row) and certifies against the key after them.
 // ------------------------------------------------------------------------------------------------
+constexpr int kStageBChunks = (32 / kChunk) < 3 ? (32 / kChunk) : 3;
+struct PartB { float d1, d2; uint32_t i1, i2; };
+
 template <int DTYPE>
 __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pairs,
-                                                const uint32_t* __restrict__ keys, const uint2* __restrict__ list,
-                                                const uint32_t* __restrict__ list_count, uint32_t dim, float ratio2,
-                                                uint32_t* counters, uint3* matches, uint2* fallback, float4* nn) {
+                                                const uint32_t* __restrict__ keys, const PartB* __restrict__ parts,
+                                                const uint2* __restrict__ list, const uint32_t* __restrict__ list_count,
+                                                uint32_t dim, float ratio2, uint32_t* counters, uint3* matches,
+                                                uint2* fallback, float4* nn) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_list = *list_count;
   for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_list;
        item += gridDim.x * (blockDim.x >> 5)) {
-  const uint2 pq = list[item];
-  const uint32_t pair = pq.x, q = pq.y;
-  const PairDesc pd = pairs[pair];
-  const uint4 ka = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4));
-  const uint4 kb = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4) + 1);
-  const uint32_t key[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
-  const uint32_t nchunks = pd.nI_pad / kChunk;
-  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
-  const double pack_rel = ldexp(1.0, (int)pd.chunk_bits - 23);
-  const size_t rb = row_bytes(DTYPE, dim);
-  const char* qrow = (const char*)pd.descJ + (size_t)q * rb;
-  const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
-
-  // stage A: chunks of key 0 (lanes 0-15) and key 1 (lanes 16-31); B: key 2; C: keys 3 and 4.
-  // After each stage every column outside the re-ranked chunks is bounded below by the next key.
-  Top2 t;
-  t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
-  bool ok = false;
-#pragma unroll
-  for (int stage = 0; stage < 3; ++stage) {
-    uint32_t c;
-    bool active = true;
-    if (stage == 0) c = (lane < 16) ? (key[0] & cmask) : (key[1] & cmask);
-    else if (stage == 1) { c = key[2] & cmask; active = lane < 16; }
-    else c = (lane < 16) ? (key[3] & cmask) : (key[4] & cmask);
+    const uint2 pq = list[item];
+    const uint32_t pair = pq.x, q = pq.y;
+    const PairDesc pd = pairs[pair];
+    const uint4 ka = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4));
+    const uint4 kb = __ldg((const uint4*)keys + (size_t)(pd.q_ofs + q) * (kKeyStride / 4) + 1);
+    const uint32_t key[6] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y};
+    const uint32_t nchunks = pd.nI_pad / kChunk;
+    const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+    const double pack_rel = ldexp(1.0, (int)pd.chunk_bits - 23);
+    const size_t rb = row_bytes(DTYPE, dim);
+    const char* qrow = (const char*)pd.descJ + (size_t)q * rb;
+    const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
+    const PartB pa = parts[(size_t)(pd.q_ofs + q) * 2 + 0];
+    const PartB pb = parts[(size_t)(pd.q_ofs + q) * 2 + 1];
+    Top2 t, tb;
+    t.d1 = pa.d1; t.d2 = pa.d2; t.i1 = pa.i1; t.i2 = pa.i2;
+    tb.d1 = pb.d1; tb.d2 = pb.d2; tb.i1 = pb.i1; tb.i2 = pb.i2;
+    t = top2_merge(t, tb);
     Top2 u;
     u.d1 = u.d2 = FLT_MAX; u.i1 = u.i2 = 0xffffffffu;
-    const uint32_t col = c * kChunk + (lane & 15u);
-    if (active && c < nchunks && col < pd.nI) {
-      u.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
-      u.i1 = col;
+    const uint32_t slot = lane / kChunk;  // which of the stage-B chunks this lane works on
+    if (slot < (uint32_t)kStageBChunks) {
+      const uint32_t c = key[2 + slot] & cmask;
+      const uint32_t col = c * kChunk + (lane % kChunk);
+      if (c < nchunks && col < pd.nI) {
+        u.d1 = exact_l2<DTYPE>(qrow, (const char*)pd.descI + (size_t)col * rb, dim);
+        u.i1 = col;
+      }
     }
     u = top2_warp_reduce(u);
     t = top2_merge(t, u);
-    const uint32_t bound_key = stage == 0 ? key[2] : (stage == 1 ? key[3] : key[5]);
-    ok = key_lower_bound(bound_key, pd.eps_abs, gamma, pack_rel) > (double)t.d2;
-    if (ok) break;
-    if (lane == 0 && stage < 2) atomicAdd(&counters[2 + stage], 1u);
-  }
-  if (lane == 0) {
-    if (ok) {
-      emit_result(pd, pair, q, t, ratio2, counters, matches, nn);
-    } else {
-      const uint32_t slot = atomicAdd(&counters[1], 1u);
-      fallback[slot] = make_uint2(pair, q);
+    const bool ok = key_lower_bound(key[2 + kStageBChunks], pd.eps_abs, gamma, pack_rel) > (double)t.d2;
+    if (lane == 0) {
+      if (ok) {
+        emit_result(pd, pair, q, t, ratio2, counters, matches, nn);
+      } else {
+        const uint32_t s2 = atomicAdd(&counters[1], 1u);
+        fallback[s2] = make_uint2(pair, q);
+      }
     }
-  }
   }
 }
 
@@ -245,7 +244,7 @@ int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0) {
   return R3D_OK;
 }
 
-int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys,
+int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys, const void* d_parts,
                        const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
                        float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn) {
   if (max_list == 0) return R3D_OK;
@@ -253,9 +252,11 @@ int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, c
   uint32_t grid = (max_list + wpb - 1) / wpb;
   if (grid > (uint32_t)w.sm_count * 16u) grid = (uint32_t)w.sm_count * 16u;
   if (dtype == 0)
-    k_rerank<0><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+    k_rerank<0><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, (const PartB*)d_parts, d_list, d_list_count, dim, ratio2,
+                                                 d_counters, d_matches, d_fallback, d_nn);
   else
-    k_rerank<1><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_fallback, d_nn);
+    k_rerank<1><<<grid, wpb * 32, 0, w.stream>>>(d_pairs, d_keys, (const PartB*)d_parts, d_list, d_list_count, dim, ratio2,
+                                                 d_counters, d_matches, d_fallback, d_nn);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

@@ -27,8 +27,8 @@ constexpr int kQB = 2;              // query blocks (of 128 rows) resident per C
 constexpr int kSuperRows = kTileRows * kQB;  // 256 query rows per work item
 constexpr int kRowPad = 256;        // every view is padded to a multiple of this many rows
 constexpr int kBiasCols = 16;       // one UMMA K-step holding the norm terms
-constexpr int kChunk = 16;          // database columns summarised by one candidate key
-constexpr int kChunkBits = 12;      // low mantissa bits of a key that hold the chunk id
+constexpr int kChunk = 8;           // database columns summarised by one candidate key
+constexpr int kChunkBits = 13;      // max low mantissa bits of a key that hold the chunk id
 constexpr int kNumKeys = 6;         // keys kept per query (5 candidate chunks + 1 bound)
 constexpr int kKeyStride = 8;       // uint32 per query row in the key array (two 16-byte stores)
 constexpr int kMaxKBlocks = 4;      // Kp <= 256  (descriptor dim <= 240)
@@ -189,14 +189,14 @@ int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
                          uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int cluster);
 size_t l2_candidates_smem_bytes(int kp_cols);
 // exact re-rank + ratio
-int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys,
+int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys, const void* d_parts,
                        const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
                        float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn);
 // binned stage A (rerank_binned.cu); cstride = max chunks per pair + 1
 int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
                          uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
                          uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
-                         uint3* d_matches, uint2* d_list2, float4* d_nn);
+                         uint3* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn);
 // exact scan of listed queries
 int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
                       const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,

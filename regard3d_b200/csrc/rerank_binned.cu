@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
 __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ pairs,
                                                    const uint32_t* __restrict__ keys, const Part* __restrict__ parts,
                                                    uint32_t dim, float ratio2, uint32_t* counters, uint3* matches,
-                                                   uint2* list2, float4* nn) {
+                                                   uint2* list2, uint2* fallback, float4* nn) {
   const uint32_t pair = blockIdx.y;
   const PairDesc pd = pairs[pair];
   if (!pd.use_tc) return;
@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ 
   }
   if (ok) {
     emit_result(pd, pair, q, t, ratio2, counters, matches, nn);
+  } else if (dup) {  // fewer than two real candidate chunks (tiny database): exact scan
+    const uint32_t s = atomicAdd(&counters[1], 1u);
+    fallback[s] = make_uint2(pair, q);
   } else {
     const uint32_t s = atomicAdd(&counters[4], 1u);
     list2[s] = make_uint2(pair, q);
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ 
 int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
                          uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
                          uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
-                         uint3* d_matches, uint2* d_list2, float4* d_nn) {
+                         uint3* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn) {
   if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
   const size_t rb = dtype == 0 ? (size_t)dim * 4 : (size_t)dim;
   if (rb & 3) return fail(ctx, R3D_ERR_UNSUPPORTED, "binned re-rank needs row bytes % 4 == 0");
@@ -262,7 +265,7 @@ int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
     k_bin_rerank<1><<<gc, kBinWarps * 32, smem, w.stream>>>(d_pairs, cstride, d_cnt, d_list, dim, row_stride, (Part*)d_parts);
   }
   k_bin_merge<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, (const Part*)d_parts, dim, ratio2, d_counters, d_matches,
-                                        d_list2, d_nn);
+                                        d_list2, d_fallback, d_nn);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

@@ -93,8 +93,9 @@ def test_candidate_error_bound_holds(gpu_ctx):
     A = sc["descs"][0].astype(np.float64)
     B = sc["descs"][1].astype(np.float64)
     D = (B * B).sum(1)[:, None] + (A * A).sum(1)[None, :] - 2 * B @ A.T
-    cm = D.reshape(2048, 2048 // 16, 16).min(2)
-    bits = 7                                   # 2048 rows / 16 = 128 chunks
+    CH = 8                                     # r3d::kChunk
+    cm = D.reshape(2048, 2048 // CH, CH).min(2)
+    bits = 8                                   # 2048 rows / 8 = 256 chunks
     kv = keys[:2048, :6].view(np.float32).astype(np.float64)
     kc = (keys[:2048, :6] & ((1 << bits) - 1)).astype(np.int64)
     pack = 2.0 ** (bits - 23)
