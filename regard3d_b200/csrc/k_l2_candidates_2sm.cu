@@ -1,0 +1,321 @@
+// k_l2_candidates_2sm.cu -- the candidate kernel on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Why: the single-CTA kernel (k_l2_candidates.cu) is bound by shared-memory operand reads: an
+// M128 x N128 x K16 SS-MMA fetches 8 KB per 64 tensor cycles = the 128 B/clk port
+// (profiles/r01_k_l2_candidates.md).  With cta_group::2 one instruction computes M = 256: each SM of
+// the pair contributes its own 128 query rows (A) and HALF of the database tile (B, 128 of 256
+// rows), and receives a 128 x 256 accumulator.  Per SM that is 8 KB of operands per 128 tensor
+// cycles -- half the shared-memory traffic, half the TMA/L2 traffic per flop.
+//
+// Work item = (pair, 128-query block); a cluster owns two consecutive items of ONE pair.
+// Per CTA: A = 1 query block (nkb boxes, resident), B ring = 128-row boxes of its half of every
+// 256-row database tile, TMEM = 2 accumulator stages x 256 columns.
+// Protocol (leader = CTA rank 0 issues every MMA):
+//   full[s]    local TMA complete                      (each CTA, count 1 + tx)
+//   pfull[s]   peer's full[s] forwarded to the leader  (leader, count 1; remote arrive by the peer's warp 1)
+//   empty[s]   ring slot free in both CTAs             (multicast tcgen05.commit from the leader)
+//   qfull / pqfull / qempty  same scheme for the resident query tiles
+//   tfull[a]   accumulator stage ready in both CTAs    (multicast commit)
+//   tempty[a]  both epilogues drained the stage        (leader, count 2 x 8 warps; the peer arrives remotely)
+// Epilogue: warps 4-7 take accumulator columns 0-127, warps 8-11 columns 128-255 of the same query
+// rows; the two partial key sets of a row are merged through shared memory at the end of an item.
+#include "r3d_internal.cuh"
+#include "tc_ptx.cuh"
+
+#include <cstdlib>
+
+namespace r3d {
+
+using namespace tcx;
+
+namespace {
+
+constexpr int kMaxStages2 = 12;
+constexpr int kEpiWarps2 = 8;
+constexpr int kThreads2 = 32 * (4 + kEpiWarps2);
+constexpr uint32_t kTmemCols2 = 512;
+constexpr uint32_t kTileN = 256;  // database rows per tile (both halves)
+// kind::f16, D = f32, A = B = f16 K-major, N = 256, M = 256 (cta_group::2)
+constexpr uint32_t kInstrDesc2 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads2, 1)
+k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
+                    const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
+                    uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_base = base;                                  // nkb boxes (this CTA's 128 query rows)
+  const uint32_t d_base = q_base + nkb * kBoxBytes;               // n_stages boxes
+  const uint32_t bar_base = d_base + n_stages * kBoxBytes;
+  const uint32_t bar_full = bar_base;                             // [kMaxStages2]
+  const uint32_t bar_pfull = bar_full + 8 * kMaxStages2;          // [kMaxStages2] (leader)
+  const uint32_t bar_empty = bar_pfull + 8 * kMaxStages2;         // [kMaxStages2]
+  const uint32_t bar_qfull = bar_empty + 8 * kMaxStages2;
+  const uint32_t bar_pqfull = bar_qfull + 8;
+  const uint32_t bar_qempty = bar_pqfull + 8;
+  const uint32_t bar_tfull = bar_qempty + 8;                      // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;                     // [2] (leader)
+  const uint32_t tmem_slot = bar_tempty + 16;
+  const uint32_t key_xchg = (tmem_slot + 16 + 15u) & ~15u;        // 128 rows x 8 u32: keys of the upper column half
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(gen_base + (tmem_slot - base));
+  uint32_t* xchg = (uint32_t*)(gen_base + (key_xchg - base));
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const uint32_t cluster_id = blockIdx.x >> 1;
+  const uint32_t n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (uint32_t s = 0; s < (uint32_t)kMaxStages2; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_pfull + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_qfull, 1);
+    mbar_init(bar_pqfull, 1);
+    mbar_init(bar_qempty, 1);
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 2 * kEpiWarps2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols2)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    uint32_t stage = 0, phase = 0, qphase = 0;
+    for (uint32_t it = cluster_id * 2 + crank; it < n_items; it += n_clusters * 2) {
+      const WorkItem wi = items[it];
+      const PairDesc pd = pairs[wi.pair];
+      const CUtensorMap* mq = tmapQ + pd.slotJ;
+      const CUtensorMap* md = tmapD + pd.slotI;
+      const uint32_t nboxes = (pd.nI_pad / kTileN) * nkb;
+      const uint32_t ahead = nboxes < n_stages ? nboxes : n_stages;
+      uint32_t b = 0, t = 0, kb = 0;
+      for (;;) {
+        if (b == ahead) {
+          mbar_wait(bar_qempty, qphase ^ 1u);
+          qphase ^= 1u;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(bar_qfull, nkb * kBoxBytes);
+            for (uint32_t k2 = 0; k2 < nkb; ++k2)
+              tma_load_2d(q_base + k2 * kBoxBytes, mq, (int)(k2 * kKBlock), (int)(wi.sb * kTileRows), bar_qfull);
+          }
+          __syncwarp();
+        }
+        if (b == nboxes) break;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(bar_full + 8 * stage, kBoxBytes);
+          // this CTA's half of the 256-row database tile
+          tma_load_2d(d_base + stage * kBoxBytes, md, (int)(kb * kKBlock), (int)(t * kTileN + crank * kTileRows),
+                      bar_full + 8 * stage);
+        }
+        __syncwarp();
+        if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        ++b;
+        if (++kb == nkb) { kb = 0; ++t; }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
+    if (leader) {
+      // ============================ MMA issuer (leader CTA, cta_group::2) ============================
+      for (uint32_t it = cluster_id * 2; it < n_items; it += n_clusters * 2) {
+        const WorkItem wi = items[it];
+        const PairDesc pd = pairs[wi.pair];
+        const uint32_t ntiles = pd.nI_pad / kTileN;
+        mbar_wait(bar_qfull, qf);
+        mbar_wait(bar_pqfull, qf);
+        qf ^= 1u;
+        tc_fence_after();
+        for (uint32_t t = 0; t < ntiles; ++t) {
+          mbar_wait(bar_tempty + 8 * acc, accphase ^ 1u);  // both epilogues drained this accumulator stage
+          tc_fence_after();
+          const uint32_t d0 = tmem_base + acc * kTileN;
+          uint32_t ks_left = ksteps;
+          for (uint32_t kb = 0; kb < nkb; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            mbar_wait(bar_pfull + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t b_lo = desc_lo(d_base + stage * kBoxBytes);
+              const uint32_t a_lo = desc_lo(q_base + kb * kBoxBytes);
+              const uint32_t ks_here = ks_left < 4u ? ks_left : 4u;
+#pragma unroll
+              for (uint32_t k = 0; k < 4; ++k) {
+                if (k < ks_here)
+                  tc2_mma_f16(d0, make_desc(a_lo + 2 * k), make_desc(b_lo + 2 * k), kInstrDesc2, (kb | k) != 0u ? 1u : 0u);
+              }
+              tc2_commit_mc(bar_empty + 8 * stage, 3);
+              if (kb + 1 == nkb) tc2_commit_mc(bar_tfull + 8 * acc, 3);
+            }
+            __syncwarp();
+            ks_left -= 4u;
+            if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+          }
+          acc ^= 1u;
+          if (acc == 0) accphase ^= 1u;
+        }
+        if (elect_one()) tc2_commit_mc(bar_qempty, 3);
+        __syncwarp();
+      }
+    } else {
+      // ============ peer CTA: forward "my operands have landed" to the leader's barriers ============
+      const uint32_t r_pqfull = mapa_shared(bar_pqfull, 0);
+      for (uint32_t it = cluster_id * 2 + 1; it < n_items; it += n_clusters * 2) {
+        const WorkItem wi = items[it];
+        const PairDesc pd = pairs[wi.pair];
+        const uint32_t nboxes = (pd.nI_pad / kTileN) * nkb;
+        mbar_wait(bar_qfull, qf);
+        qf ^= 1u;
+        if (elect_one()) mbar_arrive_remote(r_pqfull);
+        __syncwarp();
+        for (uint32_t b = 0; b < nboxes; ++b) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          if (elect_one()) mbar_arrive_remote(mapa_shared(bar_pfull + 8 * stage, 0));
+          __syncwarp();
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue (both CTAs) =======================================
+    const uint32_t ew = warp - 4u;
+    const uint32_t half = ew >> 2;            // 0: accumulator columns 0-127, 1: columns 128-255
+    const uint32_t lane_quarter = warp & 3u;
+    const uint32_t r_tempty0 = mapa_shared(bar_tempty, 0);
+    uint32_t acc = 0, accphase = 0;
+    for (uint32_t it = cluster_id * 2 + crank; it < n_items; it += n_clusters * 2) {
+      const WorkItem wi = items[it];
+      const PairDesc pd = pairs[wi.pair];
+      const uint32_t ntiles = pd.nI_pad / kTileN;
+      float key[kNumKeys];
+#pragma unroll
+      for (int i = 0; i < kNumKeys; ++i) key[i] = __uint_as_float(kKeySentinel);
+      const uint32_t keep_mask = ~((1u << pd.chunk_bits) - 1u);
+      for (uint32_t t = 0; t < ntiles; ++t) {
+        mbar_wait(bar_tfull + 8 * acc, accphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((lane_quarter * 32u) << 16) + acc * kTileN + half * 128u;
+        // accumulator column j of the 256-wide tile is database row t*256 + j (rows 0-127 from the leader's
+        // half, 128-255 from the peer's)
+        const uint32_t chunk0 = (t * kTileN + half * 128u) / kChunk;
+        uint32_t va[32], vb[32];
+        constexpr uint32_t kCpl = 32 / kChunk;
+        tc_ld32(taddr, va);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 32, vb);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + c, keep_mask, key);
+        tc_wait_ld(vb);
+        tc_ld32(taddr + 64, va);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + kCpl + c, keep_mask, key);
+        tc_wait_ld(va);
+        tc_ld32(taddr + 96, vb);
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + 2 * kCpl + c, keep_mask, key);
+        tc_wait_ld(vb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
+#pragma unroll
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + 3 * kCpl + c, keep_mask, key);
+        acc ^= 1u;
+        if (acc == 0) accphase ^= 1u;
+      }
+      // merge the two column halves of every query row: the upper half hands its keys over in shared memory
+      const uint32_t r = lane_quarter * 32u + lane;  // row inside the 128-query block
+      if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < kNumKeys; ++i) xchg[r * 8 + i] = __float_as_uint(key[i]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps2 * 32) : "memory");
+      if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < kNumKeys; ++i) {
+          float x = __uint_as_float(xchg[r * 8 + i]);
+#pragma unroll
+          for (int j = 0; j < kNumKeys - 1; ++j) {
+            const float hi = fmaxf(key[j], x);
+            key[j] = fminf(key[j], x);
+            x = hi;
+          }
+          key[kNumKeys - 1] = fminf(key[kNumKeys - 1], x);
+        }
+        const uint32_t row = wi.sb * kTileRows + r;
+        uint4 o0, o1;
+        o0.x = __float_as_uint(key[0]); o0.y = __float_as_uint(key[1]);
+        o0.z = __float_as_uint(key[2]); o0.w = __float_as_uint(key[3]);
+        o1.x = __float_as_uint(key[4]); o1.y = __float_as_uint(key[5]);
+        o1.z = kKeySentinel; o1.w = kKeySentinel;
+        uint4* dst = (uint4*)keys_out + (size_t)(pd.q_ofs + row) * (kKeyStride / 4);
+        dst[0] = o0;
+        dst[1] = o1;
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps2 * 32) : "memory");  // xchg may be reused
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+  }
+}
+
+static int ring_stages2(int nkb) {
+  int stages = (int)((232448 - 8192 - (size_t)nkb * kBoxBytes) / kBoxBytes);
+  if (stages > kMaxStages2) stages = kMaxStages2;
+  const char* e = getenv("R3D_K1_STAGES");
+  if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e);
+  return stages;
+}
+
+int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
+                             uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps) {
+  if (n_items == 0) return R3D_OK;
+  if (n_items & 1u) return fail(ctx, R3D_ERR_INVALID, "2-SM candidate kernel needs an even number of work items");
+  const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
+  if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
+  const int stages = ring_stages2(nkb);
+  const size_t smem = 1024 + (size_t)(nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 3 + 4) + 32 + 16 + 128 * 8 * 4;
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_l2_candidates_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  uint32_t grid = (uint32_t)w.sm_count / 2 * 2;
+  if (n_items < grid) grid = n_items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads2);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = w.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  R3D_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, k_l2_candidates_2sm, (const CUtensorMap*)w.d_tmapQ, (const CUtensorMap*)w.d_tmapD,
+                                       d_pairs, d_items, n_items, d_keys, (uint32_t)nkb, (uint32_t)ksteps, (uint32_t)stages));
+  return R3D_OK;
+}
+
+}  // namespace r3d

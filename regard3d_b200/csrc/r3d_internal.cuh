@@ -188,6 +188,9 @@ int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0);
 int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
                          uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int cluster);
 size_t l2_candidates_smem_bytes(int kp_cols);
+// CTA-pair variant (tcgen05 cta_group::2): work items are 128-query blocks, two consecutive items share a pair
+int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
+                             uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps);
 // exact re-rank + ratio
 int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys, const void* d_parts,
                        const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
