@@ -164,8 +164,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ct
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta_rank));
   return r;
 }
+// RELAXED on purpose: a release at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR per
+// arrive (measured: +65 % kernel time).  The hand-shakes that use it publish no generic-proxy writes:
+// "TMEM stage drained" follows tcgen05.wait::ld + tcgen05.fence::before_thread_sync, and "operands
+// landed" forwards an mbarrier completion of TMA (async-proxy) writes that the tensor core reads.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // ---- cta_group::2 variants -----------------------------------------------------------------------
 __device__ __forceinline__ void tc2_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
