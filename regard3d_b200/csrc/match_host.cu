@@ -168,8 +168,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       return (e && atoi(e) == 1) ? 1 : 2;
     }();
     static const bool k2sm = []() {
-      const char* e = getenv("R3D_K1_MODE");
-      return e && std::string(e) == "2sm";
+      const char* e = getenv("R3D_K1_MODE");  // "1sm": single-CTA kernel (k_l2_candidates.cu); default: CTA pairs
+      return !(e && std::string(e) == "1sm");
     }();
     for (uint32_t k = 0; k < nb && k2sm; ++k)
       if ((*hp)[k].use_tc)  // CTA-pair kernel: 128-query blocks; n_pad is a multiple of 256 -> always an even count per pair
