@@ -129,7 +129,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   static const uint32_t kBatchPairs = []() {
     const char* e = getenv("R3D_BATCH_PAIRS");
     const int v = e ? atoi(e) : 0;
-    return (uint32_t)(v > 0 ? v : 192);
+    return (uint32_t)(v > 0 ? v : 128);
   }();
   const uint64_t kMaxRowsPerBatch = 24ull << 20;  // 24 Mi query rows -> 768 MiB of keys
   std::vector<std::thread> tails;
@@ -146,7 +146,11 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     size_t b1 = b0;
     uint64_t rows = 0, qtotal = 0, n_items = 0;
     uint32_t max_nJ = 0, max_chunks = 0;
-    while (b1 < all.size() && (b1 - b0) < kBatchPairs && (rows + all[b1].pd.nJ_pad <= kMaxRowsPerBatch || b1 == b0)) {
+    // batches shrink geometrically towards the end so that the un-overlapped tail (copy + host
+    // de-duplication of the LAST batch) is short
+    const size_t remaining = all.size() - b0;
+    const size_t this_batch = std::min<size_t>(kBatchPairs, std::max<size_t>(24, remaining / 2));
+    while (b1 < all.size() && (b1 - b0) < this_batch && (rows + all[b1].pd.nJ_pad <= kMaxRowsPerBatch || b1 == b0)) {
       all[b1].pd.q_ofs = (uint32_t)rows;
       rows += all[b1].pd.nJ_pad;
       qtotal += all[b1].pd.nJ;
