@@ -103,8 +103,10 @@ typedef struct { uint32_t width, height; } r3d_view_info;
 /* Replaces ImageCollectionGeometricFilter::Robust_model_estimation(
  *   GeometricFilter_FMatrix_AC(precision_px = 4.0, max_iter = 2048), putative, false)
  * + Get_geometric_matches() (src/R3DComputeMatches.cpp:2099-2115).  Uses the positions uploaded
- * with r3d_upload_regions.  views[v] = image size of view v (sfm_data views).  Only
- * R3D_MODEL_F is implemented in this round (E/H: R3D_ERR_UNSUPPORTED). */
+ * with r3d_upload_regions.  views[v] = image size of view v (sfm_data views).
+ * R3D_MODEL_H: GeometricFilter_HMatrix_AC(4.0, 2048) (src/R3DComputeMatches.cpp:2215-2219; 4-point DLT,
+ * asymmetric transfer error, point-to-point a-contrario model).  R3D_MODEL_E (5-point essential,
+ * :2169) is not implemented: R3D_ERR_UNSUPPORTED. */
 int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_iter,
                      const r3d_matches* putative, const r3d_view_info* views, uint32_t n_views,
                      r3d_matches** out);
@@ -156,8 +158,8 @@ typedef void (*r3d_progress_cb)(float fraction, const char* message, void* user)
 typedef struct {
   float dist_ratio;               /* R3DFParams::distRatio_ (src/Regard3DFeatures.h:52-69) */
   int compute_fundamental;        /* R3DFParams::computeFundalmentalMatrix_ */
-  int compute_essential;          /* accepted, not implemented this round */
-  int compute_homography;         /* accepted, not implemented this round */
+  int compute_essential;          /* accepted, not implemented this round (no matches.e.txt is written) */
+  int compute_homography;         /* R3DFParams::computeHomographyMatrix_ -> matches.h.txt */
   int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher */
   uint32_t descriptor_dim;        /* 144 for R3D_AKAZE_LIOP_Regions */
 } r3d_cm_params;
@@ -168,12 +170,13 @@ typedef struct {
   const r3d_view_info* views;     /* image sizes (sfm_data views) */
   uint32_t n_views;
   const char* matches_f_filename; /* R3DProjectPaths::matchesFFilename_ ; NULL -> <matches_dir>/matches.f.txt */
+  const char* matches_h_filename; /* R3DProjectPaths::matchesHFilename_ ; NULL -> <matches_dir>/matches.h.txt */
 } r3d_cm_paths;
 
 typedef struct {
   uint32_t n_views;
   uint32_t* number_of_keypoints;  /* caller array of n_views (R3DComputeMatchesStatistics::numberOfKeypoints_) */
-  uint64_t putative_pairs, putative_matches, f_pairs, f_matches;
+  uint64_t putative_pairs, putative_matches, f_pairs, f_matches, h_pairs, h_matches;
   double seconds_load, seconds_match, seconds_filter;
 } r3d_cm_stats;
 

@@ -72,6 +72,16 @@ int64_t orc_filter_pairs_F(const float* const* xys, const uint32_t* widths, cons
                            double precision_px, uint32_t max_iter,
                            uint64_t* out_ofs, orc_indmatch* out, int n_threads);
 
+/* homography variants (GeometricFilter_HMatrix_AC: 4-point DLT, asymmetric transfer error) */
+int64_t orc_acransac_H(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI, uint32_t wJ, uint32_t hJ,
+                       double precision_px, uint32_t max_iter, uint32_t* inliers, double* H_out, double* info);
+int64_t orc_filter_pairs_H(const float* const* xys, const uint32_t* widths, const uint32_t* heights,
+                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                           const uint64_t* put_ofs, const orc_indmatch* put,
+                           double precision_px, uint32_t max_iter,
+                           uint64_t* out_ofs, orc_indmatch* out, int n_threads);
+int orc_four_point(const double* x1 /*4x2*/, const double* x2 /*4x2*/, double* H /*9*/);
+
 /* 7-point solver on (already normalised) points: returns #models, F[k*9..] row-major. */
 int orc_seven_point(const double* x1 /*7x2*/, const double* x2 /*7x2*/, double* F /*27*/);
 

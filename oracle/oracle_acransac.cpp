@@ -191,6 +191,70 @@ static inline double sym_epi_error(const double* F, double x1x, double x1y, doub
   return (yFx * yFx) * (1.0 / (Fx0 * Fx0 + Fx1 * Fx1) + 1.0 / (Fty0 * Fty0 + Fty1 * Fty1)) / 4.0;
 }
 
+// ---- homography: FourPointSolver (multiview/solver_homography_kernel.cpp) + AsymmetricError ----
+// 1-D nullspace of the 8x9 DLT system (upstream: 16x9 zero-padded, Eigen JacobiSVD; here complete
+// pivoting elimination, same null vector up to scale/sign and rounding).
+static bool nullspace_8x9(double A[8][9], double h[9]) {
+  int colperm[9];
+  for (int j = 0; j < 9; ++j) colperm[j] = j;
+  for (int r = 0; r < 8; ++r) {
+    int pi = r, pj = r;
+    double best = std::fabs(A[r][r]);
+    for (int i = r; i < 8; ++i)
+      for (int j = r; j < 9; ++j) {
+        const double v = std::fabs(A[i][j]);
+        if (v > best) { best = v; pi = i; pj = j; }
+      }
+    if (!(best > 0.0)) return false;
+    if (pi != r)
+      for (int j = 0; j < 9; ++j) std::swap(A[r][j], A[pi][j]);
+    if (pj != r) {
+      for (int i = 0; i < 8; ++i) std::swap(A[i][r], A[i][pj]);
+      std::swap(colperm[r], colperm[pj]);
+    }
+    for (int i = r + 1; i < 8; ++i) {
+      const double f = A[i][r] / A[r][r];
+      for (int j = r + 1; j < 9; ++j) A[i][j] = A[i][j] - f * A[r][j];
+      A[i][r] = 0.0;
+    }
+  }
+  double z[9];
+  z[8] = 1.0;
+  for (int r = 7; r >= 0; --r) {
+    double s = 0.0;
+    for (int j = r + 1; j < 9; ++j) s = s + A[r][j] * z[j];
+    z[r] = -s / A[r][r];
+  }
+  double nn = 0.0;
+  for (int k = 0; k < 9; ++k) nn = nn + z[k] * z[k];
+  nn = std::sqrt(nn);
+  for (int k = 0; k < 9; ++k) h[colperm[k]] = z[k] / nn;
+  return true;
+}
+
+// x, y: 4x2 normalised points; H row-major, y ~ H x
+int four_point(const double* x, const double* y, double* Hout) {
+  double L[8][9];
+  for (int i = 0; i < 4; ++i) {  // BuildActionMatrix
+    const double xx = x[2 * i], xy = x[2 * i + 1], yx = y[2 * i], yy = y[2 * i + 1];
+    double* a = L[2 * i];
+    double* b = L[2 * i + 1];
+    a[0] = xx; a[1] = xy; a[2] = 1.0; a[3] = 0.0; a[4] = 0.0; a[5] = 0.0; a[6] = -yx * xx; a[7] = -yx * xy; a[8] = -yx;
+    b[0] = 0.0; b[1] = 0.0; b[2] = 0.0; b[3] = xx; b[4] = xy; b[5] = 1.0; b[6] = -yy * xx; b[7] = -yy * xy; b[8] = -yy;
+  }
+  return nullspace_8x9(L, Hout) ? 1 : 0;
+}
+
+// homography::kernel::AsymmetricError::Error(H, x1, x2)
+static inline double asym_error(const double* H, double x1x, double x1y, double x2x, double x2y) {
+  const double hx = H[0] * x1x + H[1] * x1y + H[2];
+  const double hy = H[3] * x1x + H[4] * x1y + H[5];
+  const double hw = H[6] * x1x + H[7] * x1y + H[8];
+  const double ex = x2x - hx / hw;
+  const double ey = x2y - hy / hw;
+  return ex * ex + ey * ey;
+}
+
 // ---- logcombi tables (robust_estimator_ACRansac.hpp) : float, as upstream ----
 static float logcombi(uint32_t k, uint32_t n, const std::vector<float>& vec_log10) {
   if (k >= n || k <= 0) return 0.0f;
@@ -222,12 +286,19 @@ static void uniform_sample(uint32_t num_samples, std::mt19937& rng, std::vector<
   for (uint32_t i = 0; i < num_samples; ++i) sample[i] = vec_index[i];
 }
 
-// ---- ACRANSAC with the ACKernelAdaptor<SevenPointSolver, SymmetricEpipolarDistanceError> ----
-int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
-                   uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,
-                   std::vector<uint32_t>& vec_inliers, double* F_out, double* info) {
-  const uint32_t sizeSample = 7;
-  const uint32_t MAX_MODELS = 3;
+// rand_sampling.hpp UniformSample for any sample size
+static void uniform_sample_n(uint32_t num_samples, std::mt19937& rng, std::vector<uint32_t>& vec_index,
+                             std::vector<uint32_t>& sample) {
+  uniform_sample(num_samples, rng, vec_index, sample);
+}
+
+// ---- ACRANSAC with the ACKernelAdaptor: MODEL 0 = <SevenPointSolver, SymmetricEpipolarDistanceError>
+//      (point-to-line), MODEL 1 = <FourPointSolver, AsymmetricError> (point-to-point) ----
+template <int MODEL>
+int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI, uint32_t wJ, uint32_t hJ,
+                 double precision_px, uint32_t max_iter, std::vector<uint32_t>& vec_inliers, double* M_out, double* info) {
+  const uint32_t sizeSample = MODEL == 0 ? 7 : 4;   // Kernel::MINIMUM_SAMPLES
+  const uint32_t MAX_MODELS = MODEL == 0 ? 3 : 1;   // Kernel::MAX_MODELS
   vec_inliers.clear();
   if (info) { info[0] = std::numeric_limits<double>::infinity(); info[1] = 0; info[2] = 0; }
   const uint32_t nData = M;
@@ -245,11 +316,16 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
     x2k[2 * i] = s2 * xJ[2 * i] + c2x;
     x2k[2 * i + 1] = s2 * xJ[2 * i + 1] + c2y;
   }
-  // point-to-line: logalpha0 = log10(2 D / A / N2(0,0)), D = diag, A = area of image 2
-  const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
-  const double Aarea = (double)wJ * (double)hJ;
-  const double logalpha0 = det::log10(2.0 * D / Aarea / s2);
-  const double multError = 0.5;
+  double logalpha0, multError;
+  if (MODEL == 0) {  // point-to-line: logalpha0 = log10(2 D / A / N2(0,0)), D = diag, A = area of image 2
+    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+    const double Aarea = (double)wJ * (double)hJ;
+    logalpha0 = det::log10(2.0 * D / Aarea / s2);
+    multError = 0.5;
+  } else {           // point-to-point: logalpha0 = log10(pi / (w h) / N2(0,0)^2)
+    logalpha0 = det::log10(det::kPi / ((double)wJ * (double)hJ) / (s2 * s2));
+    multError = 1.0;
+  }
 
   const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
   const double maxThreshold = precision * s2 * s2;
@@ -265,7 +341,7 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
 
   double minNFA = std::numeric_limits<double>::infinity();
   double errorMax = std::numeric_limits<double>::infinity();
-  double bestF[9] = {0};
+  double bestM[9] = {0};
 
   uint32_t nIterReserve = max_iter / 10;
   uint32_t nIter = max_iter - nIterReserve;
@@ -274,7 +350,7 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
 
   uint32_t iter = 0;
   for (iter = 0; iter < nIter; ++iter) {
-    uniform_sample(sizeSample, random_generator, vec_index, vec_sample);
+    uniform_sample_n(sizeSample, random_generator, vec_index, vec_sample);
     double sx1[14], sx2[14], models[27];
     for (uint32_t t = 0; t < sizeSample; ++t) {
       sx1[2 * t] = x1k[2 * vec_sample[t]];
@@ -282,12 +358,13 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
       sx2[2 * t] = x2k[2 * vec_sample[t]];
       sx2[2 * t + 1] = x2k[2 * vec_sample[t] + 1];
     }
-    const int nmodels = seven_point(sx1, sx2, models);
+    const int nmodels = MODEL == 0 ? seven_point(sx1, sx2, models) : four_point(sx1, sx2, models);
     bool better = false;
     for (int mi = 0; mi < nmodels; ++mi) {
-      const double* F = models + 9 * mi;
+      const double* Mm = models + 9 * mi;
       for (uint32_t i = 0; i < nData; ++i) {
-        double e = sym_epi_error(F, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1]);
+        double e = MODEL == 0 ? sym_epi_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1])
+                              : asym_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1]);
         if (!(e == e)) e = std::numeric_limits<double>::infinity();  // NaN never is an inlier
         sorted[i] = {e, i};
       }
@@ -315,7 +392,7 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
           errorMax = sorted[best_k - 1].first;
           vec_inliers.resize(best_k);
           for (uint32_t i = 0; i < best_k; ++i) vec_inliers[i] = sorted[i].second;
-          std::memcpy(bestF, F, sizeof(bestF));
+          std::memcpy(bestM, Mm, sizeof(bestM));
         }
       }
     }
@@ -335,26 +412,54 @@ int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
   if (minNFA >= 0) vec_inliers.clear();
   if (info) { info[0] = minNFA; info[2] = (double)iter; }
   if (!vec_inliers.empty()) {
-    if (F_out) {  // Unnormalize: F = N2^T * F * N1
+    if (M_out) {
       const double N1[9] = {s1, 0, c1x, 0, s1, c1y, 0, 0, 1};
       const double N2[9] = {s2, 0, c2x, 0, s2, c2y, 0, 0, 1};
-      double T[9];
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-          double s = 0;
-          for (int k = 0; k < 3; ++k) s += N2[3 * k + r] * bestF[3 * k + c];
-          T[3 * r + c] = s;
-        }
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) {
-          double s = 0;
-          for (int k = 0; k < 3; ++k) s += T[3 * r + k] * N1[3 * k + c];
-          F_out[3 * r + c] = s;
-        }
+      if (MODEL == 0) {  // UnnormalizerT: F = N2^T * F * N1
+        double T[9];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += N2[3 * k + r] * bestM[3 * k + c];
+            T[3 * r + c] = s;
+          }
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += T[3 * r + k] * N1[3 * k + c];
+            M_out[3 * r + c] = s;
+          }
+      } else {           // UnnormalizerI: H = N2^-1 * H * N1
+        const double N2i[9] = {1.0 / s2, 0, -c2x / s2, 0, 1.0 / s2, -c2y / s2, 0, 0, 1};
+        double T[9];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += N2i[3 * r + k] * bestM[3 * k + c];
+            T[3 * r + c] = s;
+          }
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += T[3 * r + k] * N1[3 * k + c];
+            M_out[3 * r + c] = s;
+          }
+      }
     }
     if (info) info[1] = std::sqrt(errorMax) / s2;  // unormalizeError
   }
   return (int64_t)vec_inliers.size();
+}
+
+int64_t acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
+                   uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,
+                   std::vector<uint32_t>& vec_inliers, double* F_out, double* info) {
+  return acransac<0>(xI, xJ, M, wI, hI, wJ, hJ, precision_px, max_iter, vec_inliers, F_out, info);
+}
+int64_t acransac_H(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
+                   uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,
+                   std::vector<uint32_t>& vec_inliers, double* H_out, double* info) {
+  return acransac<1>(xI, xJ, M, wI, hI, wJ, hJ, precision_px, max_iter, vec_inliers, H_out, info);
 }
 
 }  // namespace orc
@@ -380,11 +485,12 @@ int64_t orc_acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t 
 // the putative map; pairs returning false disappear).  Positions are float in the regions
 // (SIOPointFeature) and promoted to double by MatchesPairToMat; intrinsics carry no distortion
 // in this path (src/R3DProject.cpp:1177-1180 starts radial-K3 at k=0), so no undistortion.
-int64_t orc_filter_pairs_F(const float* const* xys, const uint32_t* widths, const uint32_t* heights,
-                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
-                           const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
-                           uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
+static int64_t filter_pairs_model(int model, const float* const* xys, const uint32_t* widths, const uint32_t* heights,
+                                  uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                                  const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
+                                  uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
   (void)n_views;
+  const double min_samples = model == 0 ? 7.0 : 4.0;
   if (n_threads <= 0) n_threads = omp_get_max_threads();
   std::vector<std::vector<orc_indmatch>> res(P);
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads)
@@ -401,9 +507,13 @@ int64_t orc_filter_pairs_F(const float* const* xys, const uint32_t* widths, cons
       xJ[2 * k + 1] = (double)xys[J][2 * (size_t)put[b + k].j + 1];
     }
     std::vector<uint32_t> inl;
-    orc::acransac_F(xI.data(), xJ.data(), M, widths[I], heights[I], widths[J], heights[J],
-                    precision_px, max_iter, inl, nullptr, nullptr);
-    if (inl.size() > 7 * 2.5) {
+    if (model == 0)
+      orc::acransac_F(xI.data(), xJ.data(), M, widths[I], heights[I], widths[J], heights[J],
+                      precision_px, max_iter, inl, nullptr, nullptr);
+    else
+      orc::acransac_H(xI.data(), xJ.data(), M, widths[I], heights[I], widths[J], heights[J],
+                      precision_px, max_iter, inl, nullptr, nullptr);
+    if (inl.size() > min_samples * 2.5) {
       res[p].reserve(inl.size());
       for (uint32_t idx : inl) res[p].push_back(put[b + idx]);
     }
@@ -416,5 +526,33 @@ int64_t orc_filter_pairs_F(const float* const* xys, const uint32_t* widths, cons
   }
   out_ofs[P] = ofs;
   return (int64_t)ofs;
+}
+
+int64_t orc_filter_pairs_F(const float* const* xys, const uint32_t* widths, const uint32_t* heights,
+                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                           const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
+                           uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
+  return filter_pairs_model(0, xys, widths, heights, n_views, pairs, P, put_ofs, put, precision_px, max_iter, out_ofs, out,
+                            n_threads);
+}
+// GeometricFilter_HMatrix_AC(4.0, 2048) (src/R3DComputeMatches.cpp:2215-2219)
+int64_t orc_filter_pairs_H(const float* const* xys, const uint32_t* widths, const uint32_t* heights,
+                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                           const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
+                           uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
+  return filter_pairs_model(1, xys, widths, heights, n_views, pairs, P, put_ofs, put, precision_px, max_iter, out_ofs, out,
+                            n_threads);
+}
+
+int orc_four_point(const double* x1, const double* x2, double* H) { return orc::four_point(x1, x2, H); }
+
+int64_t orc_acransac_H(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
+                       uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,
+                       uint32_t* inliers, double* H_out, double* info) {
+  std::vector<uint32_t> v;
+  orc::acransac_H(xI, xJ, M, wI, hI, wJ, hJ, precision_px, max_iter, v, H_out, info);
+  if (!(v.size() > 4 * 2.5)) v.clear();
+  std::memcpy(inliers, v.data(), v.size() * sizeof(uint32_t));
+  return (int64_t)v.size();
 }
 }

@@ -69,6 +69,8 @@ def lib():
         _lib.orc_coord_dedup.restype = C.c_int64
         _lib.orc_acransac_F.restype = C.c_int64
         _lib.orc_filter_pairs_F.restype = C.c_int64
+        _lib.orc_filter_pairs_H.restype = C.c_int64
+        _lib.orc_acransac_H.restype = C.c_int64
     return _lib
 
 
@@ -175,7 +177,7 @@ def acransac_F(xI, xJ, wI, hI, wJ, hJ, precision_px=4.0, max_iter=2048):
 
 
 def filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, max_iter=2048,
-                   n_threads=0):
+                   n_threads=0, model="F"):
     xys = [np.ascontiguousarray(x, np.float32) for x in xys]
     pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
     P = pairs.shape[0]
@@ -185,11 +187,37 @@ def filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, 
     put = np.ascontiguousarray(put, indmatch_dtype)
     out = np.zeros(max(1, put.shape[0]), indmatch_dtype)
     out_ofs = np.zeros(P + 1, np.uint64)
-    n = lib().orc_filter_pairs_F(_ptr_array(xys), _p(widths), _p(heights), C.c_uint32(len(xys)),
+    fn = lib().orc_filter_pairs_F if model == "F" else lib().orc_filter_pairs_H
+    n = fn(_ptr_array(xys), _p(widths), _p(heights), C.c_uint32(len(xys)),
                                  _p(pairs), C.c_uint64(P), _p(put_ofs), _p(put),
                                  C.c_double(precision_px), C.c_uint32(max_iter), _p(out_ofs), _p(out),
                                  C.c_int(n_threads))
     return out_ofs, out[:n].copy()
+
+
+def filter_pairs_H(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, max_iter=2048, n_threads=0):
+    return filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px, max_iter, n_threads, model="H")
+
+
+def four_point(x1, x2):
+    x1 = np.ascontiguousarray(x1, np.float64)
+    x2 = np.ascontiguousarray(x2, np.float64)
+    H = np.zeros((3, 3), np.float64)
+    n = lib().orc_four_point(_p(x1), _p(x2), _p(H))
+    return H if n else None
+
+
+def acransac_H(xI, xJ, wI, hI, wJ, hJ, precision_px=4.0, max_iter=2048):
+    xI = np.ascontiguousarray(xI, np.float64)
+    xJ = np.ascontiguousarray(xJ, np.float64)
+    M = xI.shape[0]
+    inl = np.zeros(max(M, 1), np.uint32)
+    H = np.zeros((3, 3), np.float64)
+    info = np.zeros(3, np.float64)
+    n = lib().orc_acransac_H(_p(xI), _p(xJ), C.c_uint32(M), C.c_uint32(wI), C.c_uint32(hI),
+                             C.c_uint32(wJ), C.c_uint32(hJ), C.c_double(precision_px),
+                             C.c_uint32(max_iter), _p(inl), _p(H), _p(info))
+    return inl[:n].copy(), H, info
 
 
 def save_feat(path, xyso):

@@ -76,13 +76,14 @@ class CMParams(C.Structure):
 
 class CMPaths(C.Structure):
     _fields_ = [("matches_dir", C.c_char_p), ("image_basenames", C.POINTER(C.c_char_p)),
-                ("views", C.POINTER(ViewInfo)), ("n_views", C.c_uint32), ("matches_f_filename", C.c_char_p)]
+                ("views", C.POINTER(ViewInfo)), ("n_views", C.c_uint32), ("matches_f_filename", C.c_char_p),
+                ("matches_h_filename", C.c_char_p)]
 
 
 class CMStats(C.Structure):
     _fields_ = [("n_views", C.c_uint32), ("number_of_keypoints", C.POINTER(C.c_uint32)),
                 ("putative_pairs", C.c_uint64), ("putative_matches", C.c_uint64), ("f_pairs", C.c_uint64),
-                ("f_matches", C.c_uint64), ("seconds_load", C.c_double), ("seconds_match", C.c_double),
+                ("f_matches", C.c_uint64), ("h_pairs", C.c_uint64), ("h_matches", C.c_uint64), ("seconds_load", C.c_double), ("seconds_match", C.c_double),
                 ("seconds_filter", C.c_double)]
 
 
@@ -326,15 +327,16 @@ class Context:
         return res
 
     def compute_matches(self, matches_dir, basenames, widths, heights, dist_ratio=0.6, dim=144,
-                        compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None):
+                        compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None,
+                        compute_homography=False):
         n = len(basenames)
         names = (C.c_char_p * n)(*[b.encode() for b in basenames])
         views = (ViewInfo * n)()
         for k in range(n):
             views[k].width = int(widths[k])
             views[k].height = int(heights[k])
-        params = CMParams(dist_ratio, int(compute_fundamental), 0, 0, matching_algorithm, dim)
-        paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None)
+        params = CMParams(dist_ratio, int(compute_fundamental), 0, int(compute_homography), matching_algorithm, dim)
+        paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None, None)
         kp = (C.c_uint32 * n)()
         stats = CMStats()
         stats.n_views = n

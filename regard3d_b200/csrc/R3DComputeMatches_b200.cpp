@@ -74,6 +74,7 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
   cp.views = views.data();
   cp.n_views = n;
   cp.matches_f_filename = paths.matchesFFilename_.empty() ? nullptr : paths.matchesFFilename_.c_str();
+  cp.matches_h_filename = paths.matchesHFilename_.empty() ? nullptr : paths.matchesHFilename_.c_str();
   std::vector<uint32_t> kp(n, 0);
   r3d_cm_stats st;
   std::memset(&st, 0, sizeof(st));
@@ -96,6 +97,13 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
     const std::string f = paths.matchesFFilename_.empty() ? paths.relativeMatchesPath_ + "/matches.f.txt" : paths.matchesFFilename_;
     if (r3d_load_matches_txt(f.c_str(), &m) == R3D_OK) {
       to_map(m, statistics_.fundamentalMatches_);
+      r3d_free_matches(m);
+    }
+  }
+  if (params.computeHomographyMatrix_) {
+    const std::string f = paths.matchesHFilename_.empty() ? paths.relativeMatchesPath_ + "/matches.h.txt" : paths.matchesHFilename_;
+    if (r3d_load_matches_txt(f.c_str(), &m) == R3D_OK) {
+      to_map(m, statistics_.homographyMatches_);
       r3d_free_matches(m);
     }
   }

@@ -10,8 +10,8 @@ struct AcPair {          // per image pair (device)
   uint32_t tbl_ofs;      // first entry of this pair's logc_n table
   uint32_t pad_;
   double max_thr;        // precision^2 * N2(0,0)^2
-  double logalpha0;      // log10(2 D / A / N2(0,0)), image J
-  double loge0;          // log10(MAX_MODELS * (M - 7))
+  double logalpha0;      // F: log10(2 D / A / N2(0,0)) ; H: log10(pi / (w h) / N2(0,0)^2), image J
+  double loge0;          // log10(MAX_MODELS * (M - MINIMUM_SAMPLES))
 };
 
 struct AcHyp {           // one RANSAC iteration of one pair
@@ -33,12 +33,12 @@ struct AcInlierReq {
   uint32_t hyp_model;    // hypothesis * 3 + model: where this round's F matrix lives on the device
 };
 
-int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels);
-int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, const double* F, const uint32_t* nmodels, const float* logc_n,
                     const float* logc_k, uint32_t cap, AcScore* scores);
-int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                       const AcInlierReq* reqs, uint32_t n_req, const double* F, uint32_t cap, uint32_t* out);
 
 }  // namespace r3d

@@ -56,20 +56,20 @@ struct PairState {
 };
 
 // rand_sampling.hpp UniformSample(num_samples, rng, &vec_index, &sample)
-inline void uniform_sample7(std::mt19937& rng, std::vector<uint32_t>& vec_index, uint32_t* sample, uint32_t* log7) {
+inline void uniform_sample7(uint32_t ns, std::mt19937& rng, std::vector<uint32_t>& vec_index, uint32_t* sample, uint32_t* log7) {
   const uint32_t last_idx = (uint32_t)vec_index.size() - 1;
-  for (uint32_t i = 0; i < 7; ++i) {
+  for (uint32_t i = 0; i < ns; ++i) {
     std::uniform_int_distribution<uint32_t> distribution(i, last_idx);
     const uint32_t sample_idx = distribution(rng);
     std::swap(vec_index[i], vec_index[sample_idx]);
     log7[i] = sample_idx;
   }
-  for (uint32_t i = 0; i < 7; ++i) sample[i] = vec_index[i];
+  for (uint32_t i = 0; i < ns; ++i) sample[i] = vec_index[i];
 }
 // advance the generator exactly like uniform_sample7 does, without touching the pool
-inline void skip_sample7(std::mt19937& rng, uint32_t pool_size) {
+inline void skip_sample7(uint32_t ns, std::mt19937& rng, uint32_t pool_size) {
   const uint32_t last_idx = pool_size - 1;
-  for (uint32_t i = 0; i < 7; ++i) {
+  for (uint32_t i = 0; i < ns; ++i) {
     std::uniform_int_distribution<uint32_t> distribution(i, last_idx);
     (void)distribution(rng);
   }
@@ -94,7 +94,7 @@ struct DevBuf {
 
 }  // namespace
 
-int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t max_iter, const r3d_matches* put,
+int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precision_px, uint32_t max_iter, const r3d_matches* put,
                    const r3d_view_info* views, uint32_t n_views, std::vector<std::vector<r3d_indmatch>>& result) {
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   r3d_filter_timing& T = ctx->filter_timing;
@@ -102,7 +102,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
   const double t_begin = now_ms();
   const uint64_t P = put->pairs.size() / 2;
   result.assign(P, {});
-  const uint32_t sizeSample = 7, MAX_MODELS = 3;
+  const uint32_t sizeSample = model == 0 ? 7u : 4u, MAX_MODELS = model == 0 ? 3u : 1u;  // Kernel::MINIMUM_SAMPLES / MAX_MODELS
 
   // ---- per pair set-up (kernel adaptor of SURVEY.md A.5: normalisation, logalpha0, tables) ----
   std::vector<PairState> st;
@@ -176,9 +176,13 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
     const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
     ap.max_thr = precision * s2 * s2;
-    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
-    const double Aarea = (double)wJ * (double)hJ;
-    ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
+    if (model == 0) {  // point-to-line
+      const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+      const double Aarea = (double)wJ * (double)hJ;
+      ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
+    } else {           // point-to-point
+      ap.logalpha0 = dm::log10_det(R3D_PI / ((double)wJ * (double)hJ) / (s2 * s2));
+    }
     ap.loge0 = dm::log10_det((double)MAX_MODELS * (double)(M - sizeSample));
     hpairs[a] = ap;
     s.vec_index.resize(M);
@@ -262,7 +266,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
       for (uint32_t b = 0; b < s.hyp_n; ++b) {
         AcHyp& h = hhyp[s.hyp_ofs + b];
         h.pair = a;
-        uniform_sample7(s.rng, s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
+        uniform_sample7(sizeSample, s.rng, s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
       }
     });
     tm_sample += now_ms() - tq; tq = now_ms();
@@ -275,10 +279,10 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_hyp.p, hhyp.data(), (size_t)H * sizeof(AcHyp), cudaMemcpyHostToDevice, w.stream));
     // ---- 2. solve + score on the device -------------------------------------------------------
     R3D_CUDA_TRY(ctx, cudaEventRecord(ev[0], w.stream));
-    int rc = launch_f7_solve(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p);
+    int rc = launch_f7_solve(ctx, w, model, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p);
     if (rc) return rc;
     R3D_CUDA_TRY(ctx, cudaEventRecord(ev[1], w.stream));
-    rc = launch_f7_score(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p, d_logc_n.p, d_logc_k.p, cap, d_score.p);
+    rc = launch_f7_score(ctx, w, model, d_pairs.p, d_x1.p, d_x2.p, d_hyp.p, H, d_F.p, d_nm.p, d_logc_n.p, d_logc_k.p, cap, d_score.p);
     if (rc) return rc;
     R3D_CUDA_TRY(ctx, cudaEventRecord(ev[2], w.stream));
     T.kernel_launches += 2;
@@ -329,9 +333,9 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
       }
       if (consumed < s.hyp_n) {  // discard the speculative tail: undo its swaps, replay the generator
         for (uint32_t b = s.hyp_n; b-- > consumed;)
-          for (int i = 6; i >= 0; --i) std::swap(s.vec_index[i], s.vec_index[s.swap_log[(size_t)b * 7 + i]]);
+          for (int i = (int)sizeSample - 1; i >= 0; --i) std::swap(s.vec_index[i], s.vec_index[s.swap_log[(size_t)b * 7 + i]]);
         s.rng = s.snap_rng;
-        for (uint32_t b = 0; b < consumed; ++b) skip_sample7(s.rng, (uint32_t)s.vec_index.size());
+        for (uint32_t b = 0; b < consumed; ++b) skip_sample7(sizeSample, s.rng, (uint32_t)s.vec_index.size());
       }
       s.iter += consumed;
       s.since_event = s.event ? 0 : s.since_event + consumed;
@@ -354,7 +358,7 @@ int filter_pairs_F(r3d_ctx* ctx, DeviceWorker& w, double precision_px, uint32_t 
       R3D_CUDA_TRY(ctx, d_req.ensure(hreq.size()));
       R3D_CUDA_TRY(ctx, d_inl.ensure(inl_total));
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_req.p, hreq.data(), hreq.size() * sizeof(AcInlierReq), cudaMemcpyHostToDevice, w.stream));
-      rc = launch_f7_inliers(ctx, w, d_pairs.p, d_x1.p, d_x2.p, d_req.p, (uint32_t)hreq.size(), d_F.p, cap, d_inl.p);
+      rc = launch_f7_inliers(ctx, w, model, d_pairs.p, d_x1.p, d_x2.p, d_req.p, (uint32_t)hreq.size(), d_F.p, cap, d_inl.p);
       if (rc) return rc;
       T.kernel_launches += 1;
       hinl.resize(inl_total);
@@ -408,10 +412,10 @@ extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, ui
                                 const r3d_view_info* views, uint32_t n_views, r3d_matches** out) {
   if (!ctx || !putative || !views || !out) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: bad arguments");
   *out = nullptr;
-  if (model != R3D_MODEL_F)
-    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: only the fundamental-matrix filter is implemented (E/H: SURVEY.md 8f)");
+  if (model != R3D_MODEL_F && model != R3D_MODEL_H)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: the essential-matrix filter (5-point) is not implemented (SURVEY.md 8f)");
   std::vector<std::vector<r3d_indmatch>> res;
-  int rc = filter_pairs_F(ctx, ctx->workers[0], precision_px, max_iter, putative, views, n_views, res);
+  int rc = filter_pairs_model(ctx, ctx->workers[0], model == R3D_MODEL_F ? 0 : 1, precision_px, max_iter, putative, views, n_views, res);
   if (rc) return rc;
   r3d_matches* m = new r3d_matches();
   m->ofs.push_back(0);

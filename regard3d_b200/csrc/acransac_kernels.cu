@@ -159,6 +159,58 @@ __device__ int seven_point(const double* x1, const double* x2, double* Fout) {
   return num_roots;
 }
 
+// FourPointSolver::Solve (minimal case): 1-D nullspace of the 8x9 DLT system
+__device__ bool nullspace_8x9(double (*A)[9], double* h) {
+  int colperm[9];
+  for (int j = 0; j < 9; ++j) colperm[j] = j;
+  for (int r = 0; r < 8; ++r) {
+    int pi = r, pj = r;
+    double best = fabs(A[r][r]);
+    for (int i = r; i < 8; ++i)
+      for (int j = r; j < 9; ++j) {
+        const double v = fabs(A[i][j]);
+        if (v > best) { best = v; pi = i; pj = j; }
+      }
+    if (!(best > 0.0)) return false;
+    if (pi != r)
+      for (int j = 0; j < 9; ++j) { const double t = A[r][j]; A[r][j] = A[pi][j]; A[pi][j] = t; }
+    if (pj != r) {
+      for (int i = 0; i < 8; ++i) { const double t = A[i][r]; A[i][r] = A[i][pj]; A[i][pj] = t; }
+      const int t = colperm[r]; colperm[r] = colperm[pj]; colperm[pj] = t;
+    }
+    for (int i = r + 1; i < 8; ++i) {
+      const double f = A[i][r] / A[r][r];
+      for (int j = r + 1; j < 9; ++j) A[i][j] = A[i][j] - f * A[r][j];
+      A[i][r] = 0.0;
+    }
+  }
+  double z[9];
+  z[8] = 1.0;
+  for (int r = 7; r >= 0; --r) {
+    double s = 0.0;
+    for (int j = r + 1; j < 9; ++j) s = s + A[r][j] * z[j];
+    z[r] = -s / A[r][r];
+  }
+  double nn = 0.0;
+  for (int k = 0; k < 9; ++k) nn = nn + z[k] * z[k];
+  nn = sqrt(nn);
+  for (int k = 0; k < 9; ++k) h[colperm[k]] = z[k] / nn;
+  return true;
+}
+
+__device__ int four_point(const double* x, const double* y, double* Hout) {
+  double L[8][9];
+  for (int i = 0; i < 4; ++i) {
+    const double xx = x[2 * i], xy = x[2 * i + 1], yx = y[2 * i], yy = y[2 * i + 1];
+    double* a = L[2 * i];
+    double* b = L[2 * i + 1];
+    a[0] = xx; a[1] = xy; a[2] = 1.0; a[3] = 0.0; a[4] = 0.0; a[5] = 0.0; a[6] = -yx * xx; a[7] = -yx * xy; a[8] = -yx;
+    b[0] = 0.0; b[1] = 0.0; b[2] = 0.0; b[3] = xx; b[4] = xy; b[5] = 1.0; b[6] = -yy * xx; b[7] = -yy * xy; b[8] = -yy;
+  }
+  return nullspace_8x9(L, Hout) ? 1 : 0;
+}
+
+template <int MODEL>
 __global__ void __launch_bounds__(128) k_f7_solve(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
                                                   const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
                                                   uint32_t n_hyp, double* __restrict__ F, uint32_t* __restrict__ nmodels) {
@@ -167,13 +219,14 @@ __global__ void __launch_bounds__(128) k_f7_solve(const AcPair* __restrict__ pai
   const AcHyp hy = hyps[h];
   const AcPair pr = pairs[hy.pair];
   double s1[14], s2[14], models[27];
-  for (int t = 0; t < 7; ++t) {
+  constexpr int NS = MODEL == 0 ? 7 : 4;
+  for (int t = 0; t < NS; ++t) {
     const double2 a = x1[pr.pt_ofs + hy.sample[t]];
     const double2 b = x2[pr.pt_ofs + hy.sample[t]];
     s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
     s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
   }
-  const int nm = seven_point(s1, s2, models);
+  const int nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
   nmodels[h] = (uint32_t)nm;
   for (int t = 0; t < 9 * nm; ++t) F[(size_t)h * 27 + t] = models[t];
 }
@@ -189,12 +242,23 @@ __device__ __forceinline__ double sym_epi_error(const double* F, double x1x, dou
   return (yFx * yFx) * (1.0 / (Fx0 * Fx0 + Fx1 * Fx1) + 1.0 / (Fty0 * Fty0 + Fty1 * Fty1)) / 4.0;
 }
 
+// homography::kernel::AsymmetricError::Error
+__device__ __forceinline__ double asym_error(const double* H, double x1x, double x1y, double x2x, double x2y) {
+  const double hx = H[0] * x1x + H[1] * x1y + H[2];
+  const double hy = H[3] * x1x + H[4] * x1y + H[5];
+  const double hw = H[6] * x1x + H[7] * x1y + H[8];
+  const double ex = x2x - hx / hw;
+  const double ey = x2y - hy / hw;
+  return ex * ex + ey * ey;
+}
+
 __device__ __forceinline__ bool key_less(double ea, uint32_t ia, double eb, uint32_t ib) {
   return (ea < eb) || (ea == eb && ia < ib);
 }
 
 // Compact the residuals <= max_thr of model F into shared memory and sort them ascending by
 // (residual, index).  Returns the count c; se/si hold the sorted keys in [0, c).
+template <int MODEL>
 __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict__ x1, const double2* __restrict__ x2,
                                      const double* Fm, double* se, uint32_t* si, uint32_t cap, uint32_t* s_count) {
   if (threadIdx.x == 0) *s_count = 0;
@@ -202,7 +266,7 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
   for (uint32_t i = threadIdx.x; i < pr.M; i += blockDim.x) {
     const double2 a = x1[pr.pt_ofs + i];
     const double2 b = x2[pr.pt_ofs + i];
-    const double e = sym_epi_error(Fm, a.x, a.y, b.x, b.y);
+    const double e = MODEL == 0 ? sym_epi_error(Fm, a.x, a.y, b.x, b.y) : asym_error(Fm, a.x, a.y, b.x, b.y);
     if (e <= pr.max_thr) {  // false for NaN
       const uint32_t pos = atomicAdd(s_count, 1u);
       if (pos < cap) { se[pos] = e; si[pos] = i; }
@@ -232,6 +296,7 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
   return c;
 }
 
+template <int MODEL>
 __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
                                                   const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
                                                   const double* __restrict__ F, const uint32_t* __restrict__ nmodels,
@@ -249,14 +314,16 @@ __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pai
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
   for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)h * 27 + 9 * mi + t];
-  const uint32_t c = residuals_sorted(pr, x1, x2, Fm, se, si, cap, &s_count);
+  const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
+  constexpr uint32_t NS = MODEL == 0 ? 7u : 4u;       // Kernel::MINIMUM_SAMPLES
+  const double mult_error = MODEL == 0 ? 0.5 : 1.0;   // point-to-line : point-to-point
   // bestNFA: k = sizeSample+1 .. c  (the upstream loop stops at the first residual > maxThreshold)
   double best = DBL_MAX * 2.0;  // +inf
-  uint32_t best_k = 7;
+  uint32_t best_k = NS;
   const float* lcn = logc_n + pr.tbl_ofs;
-  for (uint32_t k = 8 + threadIdx.x; k <= c; k += blockDim.x) {
-    const double logalpha = pr.logalpha0 + 0.5 * dm::log10_det(se[k - 1] + (double)FLT_EPSILON);
-    const double nfa = pr.loge0 + logalpha * (double)(k - 7) + (double)lcn[k] + (double)logc_k[k];
+  for (uint32_t k = NS + 1 + threadIdx.x; k <= c; k += blockDim.x) {
+    const double logalpha = pr.logalpha0 + mult_error * dm::log10_det(se[k - 1] + (double)FLT_EPSILON);
+    const double nfa = pr.loge0 + logalpha * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
     if (nfa < best) { best = nfa; best_k = k; }  // ascending k per thread: first minimum is kept
   }
   // block argmin on (nfa, k)
@@ -272,13 +339,14 @@ __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pai
       if (s_best_nfa[w] < best || (s_best_nfa[w] == best && s_best_k[w] < best_k)) { best = s_best_nfa[w]; best_k = s_best_k[w]; }
     AcScore sc;
     sc.nfa = best;
-    sc.err = (best_k >= 8 && best_k <= c) ? se[best_k - 1] : 0.0;
+    sc.err = (best_k > NS && best_k <= c) ? se[best_k - 1] : 0.0;
     sc.k = best_k;
     sc.count = s_count;
     scores[(size_t)h * 3 + mi] = sc;
   }
 }
 
+template <int MODEL>
 __global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
                                                     const double2* __restrict__ x2, const AcInlierReq* __restrict__ reqs,
                                                     const double* __restrict__ F, uint32_t cap, uint32_t* __restrict__ out) {
@@ -290,36 +358,47 @@ __global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ p
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
   for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)(rq.hyp_model / 3) * 27 + (size_t)(rq.hyp_model % 3) * 9 + t];
-  const uint32_t c = residuals_sorted(pr, x1, x2, Fm, se, si, cap, &s_count);
+  const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
   for (uint32_t i = threadIdx.x; i < rq.k && i < c; i += blockDim.x) out[rq.out_ofs + i] = si[i];
 }
 
 // ------------------------------------------------------------------------------------------------
-int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels) {
   if (!n_hyp) return R3D_OK;
-  k_f7_solve<<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
+  if (model == 0) k_f7_solve<0><<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
+  else k_f7_solve<1><<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }
 
-int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, const double* F, const uint32_t* nmodels, const float* logc_n,
                     const float* logc_k, uint32_t cap, AcScore* scores) {
   if (!n_hyp) return R3D_OK;
   const size_t smem = (size_t)cap * 12;
-  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_f7_score<<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+  if (model == 0) {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_score<0><<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+  } else {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_score<1><<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+  }
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }
 
-int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const double2* x1, const double2* x2,
+int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                       const AcInlierReq* reqs, uint32_t n_req, const double* F, uint32_t cap, uint32_t* out) {
   if (!n_req) return R3D_OK;
   const size_t smem = (size_t)cap * 12;
-  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_f7_inliers<<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
+  if (model == 0) {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_inliers<0><<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
+  } else {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_inliers<1><<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
+  }
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

@@ -60,6 +60,7 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
   const std::string dir(paths->matches_dir);
   if (stats) {
     stats->putative_pairs = stats->putative_matches = stats->f_pairs = stats->f_matches = 0;
+    stats->h_pairs = stats->h_matches = 0;
     stats->seconds_load = stats->seconds_match = stats->seconds_filter = 0;
   }
   // ---- regions ------------------------------------------------------------------------------------
@@ -114,7 +115,21 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
     r3d_free_matches(fm);
     if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + fpath); }
   }
-  // essential / homography filters (src/R3DComputeMatches.cpp:2130-2233) are not built in this round
+  if (params->compute_homography) {  // src/R3DComputeMatches.cpp:2206-2233
+    if (cb) cb(0.95f, "Calculate homography matrix", user);
+    r3d_matches* hm = nullptr;
+    rc = r3d_filter_pairs(ctx, R3D_MODEL_H, 4.0, 2048, put, paths->views, N, &hm);
+    if (rc) { r3d_free_matches(put); return rc; }
+    if (stats) {
+      stats->h_pairs = r3d_matches_num_pairs(hm);
+      stats->h_matches = r3d_matches_total(hm);
+    }
+    const std::string hpath = paths->matches_h_filename ? std::string(paths->matches_h_filename) : dir + "/matches.h.txt";
+    rc = r3d_save_matches_txt(hm, hpath.c_str());
+    r3d_free_matches(hm);
+    if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + hpath); }
+  }
+  // the essential-matrix filter (src/R3DComputeMatches.cpp:2130-2204) is not built in this round
   r3d_free_matches(put);
   if (cb) cb(1.0f, "Done", user);
   return R3D_OK;

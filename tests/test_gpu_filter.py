@@ -14,10 +14,11 @@ def _setup(ctx, sc):
         ctx.upload_regions(v, d, x)
 
 
-def _check(ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=2048):
+def _check(ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=2048, model="F"):
     put = r3dlib.Matches.from_csr(pairs, ofs, m)
-    got = ctx.filter_pairs(put, sc["widths"], sc["heights"], max_iter=max_iter).to_dict()
-    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m, max_iter=max_iter)
+    got = ctx.filter_pairs(put, sc["widths"], sc["heights"], max_iter=max_iter,
+                           model=r3dlib.MODEL_F if model == "F" else r3dlib.MODEL_H).to_dict()
+    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m, max_iter=max_iter, model=model)
     n_pairs_exp = 0
     for k, (I, J) in enumerate(pairs):
         e = fm[int(fo[k]):int(fo[k + 1])]
@@ -78,3 +79,45 @@ def test_filter_small_iteration_budget_and_tiny_pairs(gpu_ctx, oracle, r3dlib):
     small_ofs = np.array([0, 7, 7, 15], np.uint64)
     small_m = np.concatenate([m[int(ofs[0]):int(ofs[0]) + 7], m[int(ofs[2]):int(ofs[2]) + 8]])
     _check(gpu_ctx, oracle, r3dlib, sc, pairs, small_ofs, small_m)
+
+
+def _planar_scene(seed, n_img=3, n_feat=1200):
+    """Views of one plane: features related by homographies (H is the right model, F is degenerate)."""
+    rng = np.random.default_rng(seed)
+    base = rng.uniform([100, 100], [1800, 980], (n_feat, 2))
+    xys = []
+    for v in range(n_img):
+        H = np.array([[1 + 0.03 * v, 0.02 * v, 12.0 * v], [-0.015 * v, 1 - 0.02 * v, -9.0 * v], [2e-5 * v, -1e-5 * v, 1.0]])
+        q = np.c_[base, np.ones(n_feat)] @ H.T
+        xy = q[:, :2] / q[:, 2:] + 0.5 * rng.standard_normal((n_feat, 2))
+        xys.append(synth.round_sig(xy).astype(np.float32))
+    return xys
+
+
+def test_homography_filter_equals_oracle(gpu_ctx, oracle, r3dlib):
+    xys = _planar_scene(51)
+    n = len(xys[0])
+    rng = np.random.default_rng(2)
+    descs = [np.zeros((n, 16), np.float32) for _ in xys]          # descriptors are irrelevant for the filter
+    gpu_ctx.clear_regions()
+    for v in range(3):
+        gpu_ctx.upload_regions(v, descs[v], xys[v])
+    pairs = synth.exhaustive_pairs(3)
+    ofs = np.array([0, 900, 1800, 2700], np.uint64)
+    chunks = []
+    for _ in range(3):
+        i = rng.permutation(n)[:900].astype(np.uint32)
+        j = i.copy()
+        bad = rng.random(900) < 0.3
+        j[bad] = rng.integers(0, n, bad.sum())
+        chunks.append(np.array(list(zip(i.tolist(), j.tolist())), r3dlib.indmatch_dtype))
+    m = np.concatenate(chunks)
+    sc = {"xys": xys, "widths": np.full(3, 1920, np.uint32), "heights": np.full(3, 1080, np.uint32)}
+    got = _check(gpu_ctx, oracle, r3dlib, sc, pairs, ofs, m, model="H")
+    assert len(got) == 3
+    for k, v in got.items():
+        assert 550 < len(v) < 700
+    # E is not implemented
+    with pytest.raises(r3dlib.R3DError) as e:
+        gpu_ctx.filter_pairs(r3dlib.Matches.from_csr(pairs, ofs, m), sc["widths"], sc["heights"], model=r3dlib.MODEL_E)
+    assert e.value.code == -5

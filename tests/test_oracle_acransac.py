@@ -95,3 +95,22 @@ def test_filter_pairs_drops_failed_pairs(oracle):
     assert fo[1] - fo[0] > 0.8 * (ofs[1] - ofs[0])
     assert fo[2] - fo[1] == 0                        # failed estimation -> pair disappears
     assert fo[3] - fo[2] > 0.8 * (ofs[3] - ofs[2])
+
+
+def test_four_point_and_homography_acransac(oracle):
+    rng = np.random.default_rng(0)
+    Ht = np.array([[1.02, 0.03, 8.0], [-0.02, 0.99, -5.0], [4e-5, -3e-5, 1.0]])
+    n = 500
+    x1 = rng.uniform([0, 0], [640, 480], (n, 2))
+    q = np.c_[x1, np.ones(n)] @ Ht.T
+    x2 = q[:, :2] / q[:, 2:]
+    S = np.diag([1 / 640, 1 / 640, 1])
+    Hn = S @ Ht @ np.linalg.inv(S)
+    H = oracle.four_point(x1[200:204] / 640, x2[200:204] / 640)
+    assert np.abs(H / H[2, 2] - Hn / Hn[2, 2]).max() < 1e-9
+    x2n = x2 + rng.normal(0, 0.5, (n, 2))
+    x2n[:150] = rng.uniform([0, 0], [640, 480], (150, 2))
+    inl, He, info = oracle.acransac_H(x1, x2n, 640, 480, 640, 480)
+    assert info[0] < 0 and (inl >= 150).mean() > 0.98 and len(inl) > 300
+    h = np.c_[x1[inl], np.ones(len(inl))] @ He.T
+    assert np.median(np.linalg.norm(h[:, :2] / h[:, 2:] - x2n[inl], axis=1)) < 1.5
