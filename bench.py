@@ -101,6 +101,21 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def measured_traffic_per_pair():
+    """DRAM bytes per image pair of the candidate kernel, from the committed `ncu --set full` capture of one
+    128-pair launch (profiles/r01_k_l2_candidates_2sm_keymetrics.csv); None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_k_l2_candidates_2sm_keymetrics.csv")
+    if not os.path.exists(p):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in open(p):
+        f = ln.strip().split(",")
+        if len(f) >= 4 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(f[2]) * unit.get(f[3], 1.0)
+    return tot / 128.0 if tot else None
+
+
 def make_workload(seed):
     from regard3d_b200 import synth
     sc = synth.make_scene(N_IMAGES, N_FEATS, DIM, KIND, seed=seed)
@@ -268,30 +283,45 @@ def main():
                 "kernel_launches": int(ft["kernel_launches"]),
                 "what": "AC-RANSAC fundamental filter (4 px, 2048 it.) over all putative pairs of the step"}
 
-    # ---------------- bundle-adjustment leg (BASELINE C5, reported alongside; rank 0 only) ----------------
+    # ---------------- bundle-adjustment leg (BASELINE C5, reported alongside) ----------------
+    # N > 1: STRONG scaling of the one C5 problem -- points (+ their observations) partitioned over the
+    # ranks, cameras replicated, one in-library ncclAllReduce of the reduced camera system per LM iteration.
     ba = None
-    if not args.no_ba and rank == 0:
-        from regard3d_b200 import synth
+    if not args.no_ba:
+        from regard3d_b200 import sharding, synth
         prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
         arrs = {k: np.ascontiguousarray(v) for k, v in prob.items() if k != "truth"}
         for k in ("poses", "intrinsics", "points", "obs_xy"):
             arrs[k] = np.ascontiguousarray(arrs[k], np.float64)
         for k in ("obs_cam", "obs_pt", "cam_intr"):
             arrs[k] = np.ascontiguousarray(arrs[k], np.uint32)
-        g = {k: v.copy() for k, v in arrs.items()}
-        ctx.bundle_adjust({k: v.copy() for k, v in arrs.items()}, max_iterations=2)     # warm-up
+        if world > 1:
+            ids = [ctx.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            ctx.comm_init(world, rank, ids[0])
+        local, _ = sharding.partition_ba(arrs, rank, world)
+        ctx.bundle_adjust({k: v.copy() for k, v in local.items()}, max_iterations=2)     # warm-up
         n_it = 10
+        g = {k: v.copy() for k, v in local.items()}
+        barrier()
         tb0 = time.perf_counter()
         sg, tg = ctx.bundle_adjust(g, max_iterations=n_it, function_tolerance=0.0)
         tb = time.perf_counter() - tb0
+        t_loop = max(sg["seconds_total"] - sg["seconds_setup"], 1e-9)
+        if world > 1:
+            tt = torch.tensor([t_loop, tb], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_loop, tb = float(tt[0]), float(tt[1])
+            ctx.comm_destroy()
         n_obs = int(len(arrs["obs_xy"]))
         nB = 6 * 200 + 6
         bytes_iter = 3 * (n_obs * 24 + len(arrs["points"]) * 24) + 2 * nB * nB * 8
-        t_loop = max(sg["seconds_total"] - sg["seconds_setup"], 1e-9)
         ba = {"iters_per_s": sg["iterations"] / t_loop, "e2e_iters_per_s": sg["iterations"] / tb,
               "iterations": int(sg["iterations"]), "seconds_lm_loop": t_loop, "seconds_call": tb,
               "seconds_setup": sg["seconds_setup"], "seconds_linear": sg["seconds_linear"],
-              "initial_cost": sg["initial_cost"], "final_cost": sg["final_cost"],
+              "initial_cost": sg["initial_cost"], "final_cost": sg["final_cost"], "n_gpus": world,
+              "scaling": "strong", "exchange": "none" if world == 1 else
+              "ncclAllReduce(f64) of S|rhs = %d doubles per LM iteration + 5 scalar/vector reductions" % (nB * nB + nB),
               "config": "C5: 200 cams / %d pts / %d obs, 1 shared radial-K3 intrinsic, Huber(16)" % (len(arrs["points"]), n_obs),
               "roofline": {"bound": "hbm", "achieved": sg["iterations"] / t_loop * bytes_iter / 1e9,
                            "peak": float(load_peaks()[0].get("hbm_gbs", 6650.0)), "unit": "GB/s",
@@ -324,18 +354,24 @@ def main():
         ms_c = float(np.mean(cand_ms))
         achieved = flop_per_launch / (ms_c * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))
+        tpp = measured_traffic_per_pair()
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 exact re-rank over f16 tensor-core candidates",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
                     "d2h_bytes_per_step": int(d2h_e2e), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "k_l2_candidates (tcgen05 kind::f16)",
+            "roofline": {"bound": "tensor", "kernel": "k_l2_candidates_2sm (tcgen05 kind::f16 cta_group::2, f16 candidates; "
+                                                      "every reported distance is re-computed in f32)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "%s bf16_tflops (burst; kernel timed alone with CUDA events)" % peak_src,
-                         "ms_per_launch": ms_c, "flop_per_launch": flop_per_launch, "traffic": None},
+                         "ms_per_launch": ms_c, "flop_per_launch": flop_per_launch,
+                         "launch": "one step = all %d pairs (13 batch launches of <= 128 pairs, summed)" % n_pairs,
+                         "traffic": (tpp * n_pairs if tpp and DIM == 144 and N_FEATS == 10000 else None),
+                         "traffic_unit": "DRAM bytes per step (ncu dram__bytes_read+write of one 128-pair launch, "
+                                         "scaled to the step's pairs; profiles/r01_k_l2_candidates_2sm_keymetrics.csv)"},
             "breakdown_ms": {"candidates": ms_c, "rerank": float(np.mean(rerank_ms)),
                              "exact_scan_fallback": float(np.mean(fb_ms)), "device_total": float(np.mean(dev_ms)),
                              "host_dedup": float(np.mean(host_ms))},

@@ -148,6 +148,24 @@ typedef struct {
 void r3d_ba_default_options(r3d_ba_options* o);
 int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* io, const r3d_ba_options* opt,
                       r3d_ba_summary* summary, double* cost_trace /* max_iterations+1 or NULL */);
+
+/* ---- multi-GPU bundle adjustment (the one path with a real exchange step) -------
+ * One process per GPU.  The 3-D points (with all their observations) are partitioned over the
+ * ranks, cameras and intrinsics are replicated: every rank passes r3d_bundle_adjust ALL cameras /
+ * intrinsics and ITS points + observations.  Per LM iteration the partial reduced camera system
+ * S = U - sum W V^-1 W^T and its right-hand side are summed over the ranks with ONE ncclAllReduce
+ * (double) over NVLink, the dense Cholesky is replicated, back-substitution is local; cost, camera
+ * gradient / Jacobi scaling and the step norms are small all-reduces.  On return poses/intrinsics
+ * are identical on every rank, points hold the rank's own slice.  There is no reference counterpart
+ * (Ceres is single-process); parity is against the single-GPU path / the oracle.
+ * libnccl.so.2 is resolved at run time (the copy already loaded in the process, e.g. torch's, else
+ * $R3D_NCCL_LIB, else the system one).  The id is created on rank 0 and distributed by the host
+ * (torch.distributed / MPI / a file). */
+#define R3D_COMM_ID_BYTES 128
+int r3d_comm_unique_id(r3d_ctx* ctx, uint8_t id[R3D_COMM_ID_BYTES]);
+int r3d_comm_init(r3d_ctx* ctx, int world, int rank, const uint8_t id[R3D_COMM_ID_BYTES]);
+int r3d_comm_destroy(r3d_ctx* ctx);
+int r3d_comm_world(const r3d_ctx* ctx);   /* 1 when no communicator is attached */
 /* OpenMVGHelper::calculateResiduals (src/utils/OpenMVGHelper.cpp:2572-2590): |residual| per
  * coordinate, 2 per observation -- the BA quality metric the GUI reports. */
 int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res /* n_obs x 2 */);

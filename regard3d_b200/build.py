@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libr3dgpu build failed")
     cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++",
-                                               "-Xcompiler", "-pthread", "-lpthread"]
+                                               "-Xcompiler", "-pthread", "-lpthread", "-ldl"]
     subprocess.check_call(cmd)
     return OUT
 

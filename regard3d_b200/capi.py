@@ -24,6 +24,7 @@ EXPORTS = [
     "r3d_save_matches_txt", "r3d_load_matches_txt", "r3d_filter_pairs", "r3d_ba_default_options",
     "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
     "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
+    "r3d_comm_unique_id", "r3d_comm_init", "r3d_comm_destroy", "r3d_comm_world",
 ]
 
 
@@ -108,6 +109,7 @@ def lib():
         L.r3d_matches_total.argtypes = [C.c_void_p]
         L.r3d_free_matches.argtypes = [C.c_void_p]
         L.r3d_destroy.argtypes = [C.c_void_p]
+        L.r3d_comm_world.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -319,6 +321,24 @@ class Context:
         self._check(lib().r3d_bundle_adjust(self._h, C.byref(s), C.byref(o), C.byref(summ), _p(trace)))
         d = {k: getattr(summ, k) for k, _ in BASummary._fields_}
         return d, trace[: summ.iterations + 1].copy()
+
+    # ---- multi-GPU bundle adjustment: one process per GPU, points partitioned (sharding.partition_ba) ----
+    def comm_unique_id(self):
+        """Rank 0 creates the id; the host distributes it (torch.distributed.broadcast_object_list, MPI, a file)."""
+        buf = (C.c_uint8 * 128)()
+        self._check(lib().r3d_comm_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, world, rank, comm_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(comm_id)
+        self._check(lib().r3d_comm_init(self._h, int(world), int(rank), buf))
+
+    def comm_destroy(self):
+        self._check(lib().r3d_comm_destroy(self._h))
+
+    @property
+    def comm_world(self):
+        return int(lib().r3d_comm_world(self._h))
 
     def ba_residuals(self, p):
         s = self._ba_struct(p)

@@ -20,10 +20,14 @@
 #include "r3d_internal.cuh"
 #include "ba_model.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstring>
+
+namespace cg = cooperative_groups;
 
 namespace r3d {
 namespace ba {
@@ -34,6 +38,8 @@ constexpr int kObsDoubles = 12 + 12 + 6 + 2;  // Jc, Jg, Jp, r
 
 struct Dev {
   uint32_t n_cams, n_pts, n_intr, nB, refine_intr;
+  uint32_t owns_shared;                    // multi-rank: 1 on the rank that counts the replicated camera/intrinsic
+                                           // parameters in the step norms and the model cost change
   uint64_t n_obs;
   double huber_a;
   double *poses, *intr, *pts;              // current parameters
@@ -393,101 +399,108 @@ __global__ void k_ba_finish_S(Dev d, double inv_radius) {
   }
 }
 
-// ---- dense Cholesky (lower), blocked 32 ----------------------------------------------------------
+// ---- dense Cholesky + both triangular solves: ONE persistent cooperative kernel -------------------
+// A is (n+1) x n row-major: the reduced camera system S with its right-hand side as row n (the same
+// contiguous S|rhs block the all-reduce sums).  Right-looking blocked factorisation, NB = 32:
+//   per panel k   every CTA factors the 32x32 diagonal block redundantly in shared memory and forms its
+//                 inverse M = L_kk^-1 in the same 32-step loop (no grid sync between potrf and trsm);
+//                 the trailing tiles (i >= j) are dealt round-robin to the CTAs, each tile recomputes
+//                 X_i = A_ik M^T and X_j = A_jk M^T (32^3 MACs each) and applies A_ij -= X_i X_j^T;
+//                 L_ik goes to a SEPARATE matrix Lm, so A_ik stays readable by every CTA during the
+//                 step; one grid.sync() per panel.
+//   rhs row       carrying b as row n makes the forward substitution L y = b part of the panel updates.
+//   backward      L^T x = y by CTA 0, right-looking with the stored inverses of the diagonal blocks.
+// One launch instead of 3 per panel + a single-thread triangular solve.
 constexpr int NB = 32;
-__global__ void __launch_bounds__(1024) k_chol_potrf(double* A, int n, int k0, double* flag) {
-  __shared__ double t[NB][NB + 1];
-  const int kb = min(NB, n - k0);
+__global__ void __launch_bounds__(1024, 1) k_chol_fused(double* A, double* Lm, double* Linv, int n, double* flag,
+                                                        double* x_out) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double T[NB][NB + 1], M[NB][NB + 1], Ai[NB][NB + 1], Aj[NB][NB + 1];
+  __shared__ double xk[NB];
   const int r = threadIdx.y, c = threadIdx.x;
-  if (r < kb && c < kb) t[r][c] = A[(size_t)(k0 + r) * n + k0 + c];
-  __syncthreads();
-  for (int j = 0; j < kb; ++j) {
-    if (r == j && c == j) {
-      const double dd = t[j][j];
-      if (!(dd > 0.0)) { *flag = 1.0; t[j][j] = 1.0; } else t[j][j] = sqrt(dd);
-    }
-    __syncthreads();
-    if (c == j && r > j && r < kb) t[r][j] /= t[j][j];
-    __syncthreads();
-    if (r > j && c > j && c <= r && r < kb) t[r][c] -= t[r][j] * t[c][j];
-    __syncthreads();
-  }
-  if (r < kb && c < kb && c <= r) A[(size_t)(k0 + r) * n + k0 + c] = t[r][c];
-}
-// rows below the diagonal block: X L_kk^T = A_ik ; one thread per row
-__global__ void __launch_bounds__(128) k_chol_trsm(double* A, int n, int k0) {
-  __shared__ double L[NB][NB + 1];
-  const int kb = min(NB, n - k0);
-  for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) L[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
-  __syncthreads();
-  const int row = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= n) return;
-  double x[NB];
-  for (int j = 0; j < kb; ++j) {
-    double s = A[(size_t)row * n + k0 + j];
-    for (int tt = 0; tt < j; ++tt) s -= x[tt] * L[j][tt];
-    x[j] = s / L[j][j];
-  }
-  for (int j = 0; j < kb; ++j) A[(size_t)row * n + k0 + j] = x[j];
-}
-// trailing update of the lower triangle: A_ij -= L_ik L_jk^T ; tiles of 32x32
-__global__ void __launch_bounds__(1024) k_chol_syrk(double* A, int n, int k0) {
-  const int kb = min(NB, n - k0);
-  const int r0 = k0 + kb;
-  const int ti = blockIdx.y, tj = blockIdx.x;
-  if (tj > ti) return;
-  __shared__ double Li[NB][NB + 1], Lj[NB][NB + 1];
-  const int i = r0 + ti * NB + threadIdx.y, j = r0 + tj * NB + threadIdx.x;
-  const int li = r0 + ti * NB + threadIdx.y, lj = r0 + tj * NB + threadIdx.y;
-  Li[threadIdx.y][threadIdx.x] = (li < n && (int)threadIdx.x < kb) ? A[(size_t)li * n + k0 + threadIdx.x] : 0.0;
-  Lj[threadIdx.y][threadIdx.x] = (lj < n && (int)threadIdx.x < kb) ? A[(size_t)lj * n + k0 + threadIdx.x] : 0.0;
-  __syncthreads();
-  if (i < n && j < n && j <= i) {
-    double s = 0;
-    for (int tt = 0; tt < kb; ++tt) s += Li[threadIdx.y][tt] * Lj[threadIdx.x][tt];
-    A[(size_t)i * n + j] -= s;
-  }
-}
-// L y = b ; L^T x = y   (single block; the 32x32 diagonal tiles are staged in shared memory)
-__global__ void __launch_bounds__(1024) k_chol_solve(const double* A, int n, double* b) {
-  __shared__ double xs[NB];
-  __shared__ double T[NB][NB + 1];
-  for (int k0 = 0; k0 < n; k0 += NB) {  // forward
-    const int kb = min(NB, n - k0);
-    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) T[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
-    __syncthreads();
-    if (threadIdx.x == 0)
-      for (int j = 0; j < kb; ++j) {
-        double s = b[k0 + j];
-        for (int tt = 0; tt < j; ++tt) s -= T[j][tt] * xs[tt];
-        xs[j] = s / T[j][j];
-        b[k0 + j] = xs[j];
-      }
-    __syncthreads();
-    for (int i = k0 + kb + threadIdx.x; i < n; i += blockDim.x) {
-      double s = b[i];
-      for (int tt = 0; tt < kb; ++tt) s -= A[(size_t)i * n + k0 + tt] * xs[tt];
-      b[i] = s;
-    }
-    __syncthreads();
-  }
   const int nblk = (n + NB - 1) / NB;
-  for (int kbk = nblk - 1; kbk >= 0; --kbk) {  // backward
-    const int k0 = kbk * NB, kb = min(NB, n - k0);
-    for (int idx = threadIdx.x; idx < kb * kb; idx += blockDim.x) T[idx / kb][idx % kb] = A[(size_t)(k0 + idx / kb) * n + k0 + idx % kb];
+  for (int kbi = 0; kbi < nblk; ++kbi) {
+    const int k0 = kbi * NB, kb = min(NB, n - k0);
+    // ---- diagonal block: L_kk and M = L_kk^-1 (rows/cols >= kb are identity padding) ----
+    T[r][c] = (r < kb && c < kb) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
+    M[r][c] = (r == c) ? 1.0 : 0.0;
     __syncthreads();
-    if (threadIdx.x == 0)
-      for (int j = kb - 1; j >= 0; --j) {
-        double s = b[k0 + j];
-        for (int tt = j + 1; tt < kb; ++tt) s -= T[tt][j] * xs[tt];
-        xs[j] = s / T[j][j];
-        b[k0 + j] = xs[j];
+    for (int j = 0; j < kb; ++j) {
+      const double piv = T[j][j];
+      const bool bad = !(piv > 0.0);
+      const double sq = bad ? 1.0 : sqrt(piv);
+      const double lrj = T[r][j] / sq, lcj = T[c][j] / sq, mjc = M[j][c] / sq;
+      const double trc = T[r][c], mrc = M[r][c];
+      __syncthreads();
+      if (bad && r == 0 && c == 0 && blockIdx.x == 0) *flag = 1.0;
+      if (r == j) {
+        M[j][c] = mjc;
+        if (c == j) T[j][j] = sq;
+      } else if (r > j) {
+        M[r][c] = mrc - lrj * mjc;
+        if (c == j) T[r][j] = lrj;
+        else if (c > j && c <= r) T[r][c] = trc - lrj * lcj;
       }
+      __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+      if (r < kb && c <= r && c < kb) Lm[(size_t)(k0 + r) * n + k0 + c] = T[r][c];
+      Linv[(size_t)kbi * NB * NB + r * NB + c] = (c <= r) ? M[r][c] : 0.0;
+    }
+    // ---- trailing tiles; rows run to n inclusive (the rhs row), columns to n - 1 ----
+    const int r0 = k0 + kb;
+    const int tiles_i = (n + 1 - r0 + NB - 1) / NB;
+    const int ntiles = tiles_i * (tiles_i + 1) / 2;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      const int ri = r0 + ti * NB + r, rj = r0 + tj * NB + r;  // rows staged by this thread (panel column k0 + c)
+      __syncthreads();                                         // previous tile's readers are done
+      Ai[r][c] = (ri <= n && c < kb) ? A[(size_t)ri * n + k0 + c] : 0.0;
+      Aj[r][c] = (rj <= n && c < kb) ? A[(size_t)rj * n + k0 + c] : 0.0;
+      __syncthreads();
+      double xi = 0.0, xj = 0.0;
+      for (int tt = 0; tt < NB; ++tt) {  // X = A_panel * M^T ; M is lower triangular
+        const double m = M[c][tt];
+        xi += Ai[r][tt] * m;
+        xj += Aj[r][tt] * m;
+      }
+      __syncthreads();
+      Ai[r][c] = xi;
+      Aj[r][c] = xj;
+      if (tj == 0 && ri <= n && c < kb) Lm[(size_t)ri * n + k0 + c] = xi;  // L_ik (row n: y_k)
+      __syncthreads();
+      const int row = r0 + ti * NB + r, col = r0 + tj * NB + c;
+      if (row <= n && col < n && col <= row) {
+        double sacc = 0.0;
+        for (int tt = 0; tt < NB; ++tt) sacc += Ai[r][tt] * Aj[c][tt];
+        A[(size_t)row * n + col] -= sacc;
+      }
+    }
+    grid.sync();
+  }
+  if (blockIdx.x != 0) return;
+  // ---- backward substitution L^T x = y (y = row n of Lm) ----
+  const int tid = r * NB + c;
+  for (int j = tid; j < n; j += NB * NB) x_out[j] = Lm[(size_t)n * n + j];
+  __syncthreads();
+  for (int kbi = nblk - 1; kbi >= 0; --kbi) {
+    const int k0 = kbi * NB, kb = min(NB, n - k0);
+    M[r][c] = Linv[(size_t)kbi * NB * NB + r * NB + c];
     __syncthreads();
-    for (int i = threadIdx.x; i < k0; i += blockDim.x) {
-      double s = b[i];
-      for (int tt = 0; tt < kb; ++tt) s -= A[(size_t)(k0 + tt) * n + i] * xs[tt];
-      b[i] = s;
+    if (r == 0) {  // x_k = M^T y_k
+      double sacc = 0.0;
+      for (int tt = 0; tt < kb; ++tt) sacc += M[tt][c] * x_out[k0 + tt];
+      xk[c] = (c < kb) ? sacc : 0.0;
+    }
+    __syncthreads();
+    if (r == 0 && c < kb) x_out[k0 + c] = xk[c];
+    for (int j = tid; j < k0; j += NB * NB) {  // y_j -= L_kj^T x_k
+      double sacc = 0.0;
+      for (int tt = 0; tt < kb; ++tt) sacc += Lm[(size_t)(k0 + tt) * n + j] * xk[tt];
+      x_out[j] -= sacc;
     }
     __syncthreads();
   }
@@ -524,14 +537,17 @@ __global__ void __launch_bounds__(256) k_ba_update(Dev d, double inv_radius) {
   for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < nparam; j += (size_t)gridDim.x * blockDim.x) {
     const double D2 = fmin(fmax(d.diag[j], 1e-6), 1e32) * inv_radius;
     const double dl = d.delta[j];
-    mcc += dl * (D2 * dl - d.g[j]);
     const double dx = dl * d.scale[j];
+    const bool counted = d.owns_shared || j >= d.nB;
+    if (counted) mcc += dl * (D2 * dl - d.g[j]);
     double x;
     if (j < 6 * (size_t)d.n_cams) { x = d.poses[j]; d.poses_new[j] = x + dx; }
     else if (j < d.nB) { x = d.intr[j - 6 * (size_t)d.n_cams]; d.intr_new[j - 6 * (size_t)d.n_cams] = x + dx; }
     else { x = d.pts[j - d.nB]; d.pts_new[j - d.nB] = x + dx; }
-    dn += dx * dx;
-    xn += x * x;
+    if (counted) {
+      dn += dx * dx;
+      xn += x * x;
+    }
   }
   mcc = block_sum(mcc, sm);
   dn = block_sum(dn, sm);
@@ -582,6 +598,7 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   d.refine_intr = refine_intr ? 1u : 0u;
   d.nB = 6 * p->n_cams + (refine_intr ? 6 * p->n_intr : 0);
   d.huber_a = huber_a;
+  d.owns_shared = ctx->comm_rank == 0 ? 1u : 0u;
   const size_t nparam = (size_t)d.nB + 3 * (size_t)p->n_pts;
   uint32_t *oc, *op, *ci, *pofs, *pobs;
   double2* oxy;
@@ -630,8 +647,8 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   R3D_CUDA_TRY(ctx, mem.alloc(&d.g, nparam));
   R3D_CUDA_TRY(ctx, mem.alloc(&d.diag, nparam));
   R3D_CUDA_TRY(ctx, mem.alloc(&d.delta, nparam));
-  R3D_CUDA_TRY(ctx, mem.alloc(&d.S, (size_t)d.nB * d.nB));
-  R3D_CUDA_TRY(ctx, mem.alloc(&d.rhs, d.nB));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.S, (size_t)d.nB * d.nB + d.nB));  // S | rhs contiguous: one all-reduce
+  d.rhs = d.S + (size_t)d.nB * d.nB;
   R3D_CUDA_TRY(ctx, mem.alloc(&d.Vinv, 9 * (size_t)p->n_pts));
   // intrinsics that are not refined never enter the parameter vector: the candidate copy is constant
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.intr_new, d.intr, 6 * (size_t)p->n_intr * 8, cudaMemcpyDeviceToDevice, w.stream));
@@ -689,6 +706,17 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   const int nB = (int)d.nB;
   const size_t schur_smem = (size_t)r3d::ba::kSchurWarps * obs_cap * (r3d::ba::kObsDoubles + 36) * sizeof(double);
   R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem));
+  // Cholesky scratch: L (with the forward-substituted rhs as row nB) and the inverses of its diagonal blocks
+  double *d_Lm = nullptr, *d_Linv = nullptr;
+  const int chol_blocks = (nB + r3d::ba::NB - 1) / r3d::ba::NB;
+  R3D_CUDA_TRY(ctx, mem.alloc(&d_Lm, ((size_t)nB + 1) * nB));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d_Linv, (size_t)chol_blocks * r3d::ba::NB * r3d::ba::NB));
+  int chol_grid = w.sm_count;  // persistent: one CTA per SM, all co-resident (cooperative launch)
+  {
+    int per_sm = 0;
+    R3D_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, r3d::ba::k_chol_fused, 1024, 0));
+    if (per_sm < 1) return fail(ctx, R3D_ERR_CUDA, "bundle adjustment: k_chol_fused does not fit on an SM");
+  }
   double h_scal[8];
   auto read_scal = [&]() -> int {
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_scal, d.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
@@ -699,6 +727,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, sizeof(double), w.stream));
     r3d::ba::k_ba_cost<<<grid_obs, 256, 0, w.stream>>>(d, poses, intr, pts, d.scal);
     R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = comm_allreduce(ctx, w.stream, d.scal, 1, kCommSum))) return rc;
     if ((rc = read_scal())) return rc;
     *out = h_scal[0];
     return R3D_OK;
@@ -709,6 +738,9 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.gu, 0, nparam * 8, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.du, 0, nparam * 8, w.stream));
     r3d::ba::k_ba_eval<<<grid_obs, 256, 0, w.stream>>>(d);
+    // camera / intrinsic gradient and column norms are sums over every rank's observations
+    if ((rc = comm_allreduce(ctx, w.stream, d.gu, nB, kCommSum))) return rc;
+    if ((rc = comm_allreduce(ctx, w.stream, d.du, nB, kCommSum))) return rc;
     if (!have_scale) {
       r3d::ba::k_ba_make_scale<<<(unsigned)((nparam + 255) / 256), 256, 0, w.stream>>>(d.scale, d.du, nparam);
       have_scale = true;
@@ -716,6 +748,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal + 5, 0, sizeof(double), w.stream));
     r3d::ba::k_ba_apply_scale<<<(unsigned)((nparam + 255) / 256), 256, 0, w.stream>>>(d.scale, d.gu, d.du, d.g, d.diag, nparam, d.scal + 5);
     R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = comm_allreduce(ctx, w.stream, d.scal + 5, 1, kCommMax))) return rc;
     if ((rc = read_scal())) return rc;
     gmax = h_scal[5];
     return R3D_OK;
@@ -738,28 +771,25 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     sum->iterations = iter;
     const auto t_lin = std::chrono::steady_clock::now();
     const double inv_radius = 1.0 / radius;
-    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.S, 0, (size_t)nB * nB * 8, w.stream));
-    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.rhs, 0, (size_t)nB * 8, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.S, 0, ((size_t)nB * nB + nB) * 8, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, 5 * sizeof(double), w.stream));
     r3d::ba::k_ba_schur<<<(d.n_pts + r3d::ba::kSchurWarps - 1) / r3d::ba::kSchurWarps, r3d::ba::kSchurWarps * 32, schur_smem, w.stream>>>(d, inv_radius, obs_cap);
+    // the exchange step: partial reduced camera systems of the point partitions -> their sum (NVLink)
+    if ((rc = comm_allreduce(ctx, w.stream, d.S, (size_t)nB * nB + nB, kCommSum))) return rc;
     {
       dim3 b(32, 8), g((nB + 31) / 32, (nB + 7) / 8);
       r3d::ba::k_ba_finish_S<<<g, b, 0, w.stream>>>(d, inv_radius);
     }
-    for (int k0 = 0; k0 < nB; k0 += r3d::ba::NB) {
-      r3d::ba::k_chol_potrf<<<1, dim3(32, 32), 0, w.stream>>>(d.S, nB, k0, d.scal + 4);
-      const int rem = nB - k0 - r3d::ba::NB;
-      if (rem > 0) {
-        r3d::ba::k_chol_trsm<<<(rem + 127) / 128, 128, 0, w.stream>>>(d.S, nB, k0);
-        const int tiles = (rem + r3d::ba::NB - 1) / r3d::ba::NB;
-        r3d::ba::k_chol_syrk<<<dim3(tiles, tiles), dim3(32, 32), 0, w.stream>>>(d.S, nB, k0);
-      }
+    {
+      double *pA = d.S, *pL = d_Lm, *pI = d_Linv, *pflag = d.scal + 4, *px = d.delta;
+      int pn = nB;
+      void* cargs[] = {&pA, &pL, &pI, &pn, &pflag, &px};
+      R3D_CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void*)r3d::ba::k_chol_fused, dim3(chol_grid), dim3(32, 32), cargs, 0, w.stream));
     }
-    r3d::ba::k_chol_solve<<<1, 1024, 0, w.stream>>>(d.S, nB, d.rhs);
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d.delta, d.rhs, (size_t)nB * 8, cudaMemcpyDeviceToDevice, w.stream));
     r3d::ba::k_ba_backsub<<<(d.n_pts + 127) / 128, 128, 0, w.stream>>>(d);
     r3d::ba::k_ba_update<<<w.sm_count * 4, 256, 0, w.stream>>>(d, inv_radius);
     R3D_CUDA_TRY(ctx, cudaGetLastError());
+    if ((rc = comm_allreduce(ctx, w.stream, d.scal + 1, 3, kCommSum))) return rc;
     if ((rc = read_scal())) return rc;
     sum->seconds_linear += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_lin).count();
     const bool pd = h_scal[4] == 0.0;

@@ -265,6 +265,7 @@ int r3d_create(const int* device_ids, int n_devices, r3d_ctx** out) {
 
 void r3d_destroy(r3d_ctx* ctx) {
   if (!ctx) return;
+  r3d_comm_destroy(ctx);
   for (auto& w : ctx->workers) free_worker(w);
   delete ctx;
 }

@@ -124,12 +124,19 @@ struct r3d_ctx {
   uint64_t pending_h2d = 0;  // bytes uploaded since the last matching call
   r3d_filter_timing filter_timing{};
   int host_threads = 0;
+  // optional NCCL communicator (comm.cu): only the bundle adjustment exchanges data between ranks
+  void* nccl_comm = nullptr;
+  int comm_world = 1, comm_rank = 0;
 };
 
 namespace r3d {
 
 void set_global_error(const std::string& s);
 int fail(r3d_ctx* ctx, int code, const std::string& msg);
+
+// comm.cu: in-place all-reduce of `n` doubles on the worker's stream; no-op without a communicator
+enum CommOp { kCommSum = 0, kCommMax = 2 };
+int comm_allreduce(r3d_ctx* ctx, cudaStream_t stream, double* buf, size_t n, CommOp op);
 
 #define R3D_CUDA_TRY(ctx, call)                                                            \
   do {                                                                                     \

@@ -64,3 +64,45 @@ def test_two_gloo_ranks_equal_single_process(oracle, tmp_path):
         got_m.append(g["m"])
     assert np.array_equal(np.concatenate(got_pairs), pairs)            # contiguous shards in pair order
     assert np.array_equal(np.concatenate(got_m), m)                    # concatenation == single-process result
+
+
+def test_partition_ba_tiles_points_and_observations():
+    prob = synth.make_ba_problem(n_cams=6, n_pts=301, obs_per_pt=3, seed=5)
+    for world in (1, 2, 3, 5):
+        seen_pts, n_obs = [], 0
+        for r in range(world):
+            loc, (p0, p1) = sharding.partition_ba(prob, r, world)
+            seen_pts.append((p0, p1))
+            n_obs += len(loc["obs_xy"])
+            assert loc["obs_pt"].max(initial=0) < max(p1 - p0, 1)
+            assert np.array_equal(loc["poses"], prob["poses"]) and len(loc["cam_intr"]) == 6
+        assert seen_pts[0][0] == 0 and seen_pts[-1][1] == 301
+        assert all(seen_pts[k][1] == seen_pts[k + 1][0] for k in range(world - 1))
+        assert n_obs == len(prob["obs_xy"])
+
+
+def _ba_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle as po
+    prob = synth.make_ba_problem(n_cams=6, n_pts=301, obs_per_pt=3, seed=5)
+    loc, _ = sharding.partition_ba(prob, rank, world)
+    # the quantity the ranks exchange is a plain sum over observations: 0.5 * sum |r|^2 here
+    res = po.ba_residuals(po.ba_prepare(**{k: loc[k] for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy")}))
+    t = torch.tensor([0.5 * float((res ** 2).sum())], dtype=torch.float64)
+    dist.all_reduce(t)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "cost.npy"), t.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_sum_partition_costs(oracle, tmp_path):
+    mp = pytest.importorskip("torch.multiprocessing")
+    mp.spawn(_ba_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    prob = synth.make_ba_problem(n_cams=6, n_pts=301, obs_per_pt=3, seed=5)
+    full = oracle.ba_residuals(oracle.ba_prepare(**{k: prob[k] for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy")}))
+    assert np.allclose(np.load(tmp_path / "cost.npy")[0], 0.5 * (full ** 2).sum(), rtol=1e-13)
