@@ -34,6 +34,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_IMAGES, N_FEATS, DIM, KIND, RATIO = 50, 10000, 144, "liop", 0.6
+WORKLOAD, AS_U8 = "C2", False
+# BASELINE.json configs; C2 is the bench line (the metric's single-GPU configuration), the others are
+# selectable for the record: `--workload c3|c4` (C4 = exact GPU matcher in place of CPU cascade hashing, + F filter)
+WORKLOADS = {
+    "c2": dict(images=50, feats=10000, dim=144, kind="liop", u8=False, name="C2"),
+    "c2-msurf64": dict(images=50, feats=10000, dim=64, kind="msurf", u8=False, name="C2 (MSURF-64)"),
+    "c3": dict(images=200, feats=20000, dim=128, kind="sift", u8=True, name="C3"),
+    "c4": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 (exact matcher + F filter)"),
+}
 METRIC = "matched_image_pairs_per_sec_exhaustive"
 
 
@@ -118,12 +127,12 @@ def measured_traffic_per_pair():
 
 def make_workload(seed):
     from regard3d_b200 import synth
-    sc = synth.make_scene(N_IMAGES, N_FEATS, DIM, KIND, seed=seed)
+    sc = synth.make_scene(N_IMAGES, N_FEATS, DIM, KIND, seed=seed, as_u8=AS_U8)
     pairs = synth.exhaustive_pairs(N_IMAGES)
     return sc, pairs
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     """--impl reference: the reference's CPU path = the oracle port (the reference's own code cannot
     be built here: OpenMVG/Ceres/Eigen/wx are neither vendored nor installed)."""
     if rank != 0:
@@ -151,19 +160,21 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d pairs (I=0, J=1..%d) of the C2 set per step, omp over J, %d threads"
+                         "sample": "%d pairs (I=0, J=1..%d) of the set per step, omp over J, %d threads"
                                    % (len(sample), len(sample), nthreads)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config():
-    return {"workload": "C2: %d images x %d feats, D=%d float32 (%s-like), exhaustive %d pairs, ratio %.1f"
-                        % (N_IMAGES, N_FEATS, DIM, KIND, N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
+    return {"workload": "%s: %d images x %d feats, D=%d %s (%s-like), exhaustive %d pairs, ratio %.1f"
+                        % (WORKLOAD, N_IMAGES, N_FEATS, DIM, "uint8" if AS_U8 else "float32", KIND,
+                           N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
             "images": N_IMAGES, "feats_per_image": N_FEATS, "dim": DIM, "pairs": N_IMAGES * (N_IMAGES - 1) // 2,
             "parallelism": "pairs sharded per GPU, no collective",
-            "l2_policy": "inputs (descriptors + fp16 operands, ~0.6 GB) exceed the 126 MB L2"}
+            "l2_policy": "inputs (descriptors + fp16 operands, %.1f GB) exceed the 126 MB L2"
+                         % (N_IMAGES * N_FEATS * (DIM * (1 if AS_U8 else 4) + 2 * 2 * (DIM + 48)) / 1e9)}
 
 
 def main():
@@ -175,11 +186,23 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment leg")
     ap.add_argument("--no-filter", action="store_true", help="skip the F-filter leg")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE config (default c2 = the bench line)")
     ap.add_argument("--dim", type=int, default=0, help="experiment only: 64 -> MSURF-like D=64 set")
     ap.add_argument("--feats", type=int, default=0, help="experiment only")
     ap.add_argument("--images", type=int, default=0, help="experiment only")
     args = ap.parse_args()
-    global DIM, KIND, N_FEATS, N_IMAGES
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (NCCL's version banner
+    # at communicator creation, ...) is sent to stderr instead
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+    global DIM, KIND, N_FEATS, N_IMAGES, WORKLOAD, AS_U8
+    wl = WORKLOADS[args.workload]
+    N_IMAGES, N_FEATS, DIM, KIND, AS_U8, WORKLOAD = wl["images"], wl["feats"], wl["dim"], wl["kind"], wl["u8"], wl["name"]
+    if args.workload != "c2":
+        os.environ.setdefault("R3D_REF_SAMPLE_PAIRS", "16")
     if args.dim == 64:
         DIM, KIND = 64, "msurf"
     elif args.dim == 128:
@@ -193,7 +216,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, emit)
         return 0
 
     import torch
@@ -400,10 +423,10 @@ def main():
                          set(zip(e["i"].tolist(), e["j"].tolist()))) or (g is None and len(e) == 0)
             line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s", "cores": min(nthreads, len(sample)),
                                     "kind": "port",
-                                    "sample": "%d pairs (I=0) of the same C2 set, one pass, %d omp threads, %.1f s"
+                                    "sample": "%d pairs (I=0) of the same set, one pass, %d omp threads, %.1f s"
                                               % (len(sample), nthreads, tc),
                                     "parity_on_sample": bool(same)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 1
+#define R3D_ABI_VERSION 2
 
 typedef enum {
   R3D_OK = 0,
@@ -98,15 +98,21 @@ int r3d_load_matches_txt(const char* path, r3d_matches** out);
 
 /* ---- geometric filtering ------------------------------------------------------------------- */
 typedef enum { R3D_MODEL_F = 0, R3D_MODEL_E = 1, R3D_MODEL_H = 2 } r3d_model;
-typedef struct { uint32_t width, height; } r3d_view_info;
+/* One entry per view id (sfm_data views + their intrinsics).  focal / ppx / ppy: pinhole K of the view as
+ * R3DProject builds it (src/R3DProject.cpp:1149-1159: focal = max(w,h) * focal_mm / sensor_width, else
+ * 1.1 * max(w,h); pp = (w/2, h/2)); only the essential filter reads them, focal <= 0 = "no valid pinhole
+ * intrinsic" (the pair is dropped, as GeometricFilter_EMatrix_AC does). */
+typedef struct { uint32_t width, height; double focal, ppx, ppy; } r3d_view_info;
 
 /* Replaces ImageCollectionGeometricFilter::Robust_model_estimation(
  *   GeometricFilter_FMatrix_AC(precision_px = 4.0, max_iter = 2048), putative, false)
  * + Get_geometric_matches() (src/R3DComputeMatches.cpp:2099-2115).  Uses the positions uploaded
  * with r3d_upload_regions.  views[v] = image size of view v (sfm_data views).
  * R3D_MODEL_H: GeometricFilter_HMatrix_AC(4.0, 2048) (src/R3DComputeMatches.cpp:2215-2219; 4-point DLT,
- * asymmetric transfer error, point-to-point a-contrario model).  R3D_MODEL_E (5-point essential,
- * :2169) is not implemented: R3D_ERR_UNSUPPORTED. */
+ * asymmetric transfer error, point-to-point a-contrario model).
+ * R3D_MODEL_E: GeometricFilter_EMatrix_AC(4.0, 2048) (:2169-2171; Nister/Stewenius 5-point solver on bearing
+ * vectors, <= 10 models per sample, one-sided epipolar distance of F = K2^-T E K1^-1 in pixels). The
+ * poor-overlap post-filter of :2173-2191 belongs to computeMatches() and is applied by r3d_compute_matches. */
 int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_iter,
                      const r3d_matches* putative, const r3d_view_info* views, uint32_t n_views,
                      r3d_matches** out);
@@ -176,7 +182,7 @@ typedef void (*r3d_progress_cb)(float fraction, const char* message, void* user)
 typedef struct {
   float dist_ratio;               /* R3DFParams::distRatio_ (src/Regard3DFeatures.h:52-69) */
   int compute_fundamental;        /* R3DFParams::computeFundalmentalMatrix_ */
-  int compute_essential;          /* accepted, not implemented this round (no matches.e.txt is written) */
+  int compute_essential;          /* R3DFParams::computeEssentialMatrix_ -> matches.e.txt (+ the poor-overlap filter) */
   int compute_homography;         /* R3DFParams::computeHomographyMatrix_ -> matches.h.txt */
   int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher */
   uint32_t descriptor_dim;        /* 144 for R3D_AKAZE_LIOP_Regions */
@@ -189,19 +195,21 @@ typedef struct {
   uint32_t n_views;
   const char* matches_f_filename; /* R3DProjectPaths::matchesFFilename_ ; NULL -> <matches_dir>/matches.f.txt */
   const char* matches_h_filename; /* R3DProjectPaths::matchesHFilename_ ; NULL -> <matches_dir>/matches.h.txt */
+  const char* matches_e_filename; /* R3DProjectPaths::matchesEFilename_ ; NULL -> <matches_dir>/matches.e.txt */
 } r3d_cm_paths;
 
 typedef struct {
   uint32_t n_views;
   uint32_t* number_of_keypoints;  /* caller array of n_views (R3DComputeMatchesStatistics::numberOfKeypoints_) */
-  uint64_t putative_pairs, putative_matches, f_pairs, f_matches, h_pairs, h_matches;
+  uint64_t putative_pairs, putative_matches, f_pairs, f_matches, h_pairs, h_matches, e_pairs, e_matches;
   double seconds_load, seconds_match, seconds_filter;
 } r3d_cm_stats;
 
 /* Steps of R3DComputeMatches::computeMatches() after feature extraction
  * (src/R3DComputeMatches.cpp:2035-2126): load regions, exhaustive pairs, putative matching,
- * Save(matches.putative.txt), F filter, Save(matches.f.txt); progress fractions as the reference
- * emits them (0.7 putative, 0.8 F). */
+ * Save(matches.putative.txt), F filter, Save(matches.f.txt), E filter + poor-overlap removal (< 50 inliers or
+ * < 30 % of the putatives, :2173-2191), Save(matches.e.txt), H filter, Save(matches.h.txt); progress fractions
+ * as the reference emits them (0.7 putative, 0.8 F, 0.9 E, 0.95 H). */
 int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, const r3d_cm_paths* paths,
                         r3d_progress_cb cb, void* user, r3d_cm_stats* stats);
 

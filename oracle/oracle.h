@@ -82,6 +82,21 @@ int64_t orc_filter_pairs_H(const float* const* xys, const uint32_t* widths, cons
                            uint64_t* out_ofs, orc_indmatch* out, int n_threads);
 int orc_four_point(const double* x1 /*4x2*/, const double* x2 /*4x2*/, double* H /*9*/);
 
+/* essential variants (GeometricFilter_EMatrix_AC: 5-point on bearing vectors, one-sided epipolar distance in pixels).
+ * Kpair = f1, ppx1, ppy1, f2, ppx2, ppy2 ; Ks = n_views x (f, ppx, ppy), f <= 0: no pinhole intrinsic.
+ * F_out = K2^-T E K1^-1 of the best model. */
+int64_t orc_acransac_E(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI, uint32_t wJ, uint32_t hJ,
+                       const double* Kpair, double precision_px, uint32_t max_iter, uint32_t* inliers, double* F_out,
+                       double* info);
+int64_t orc_filter_pairs_E(const float* const* xys, const uint32_t* widths, const uint32_t* heights, const double* Ks,
+                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                           const uint64_t* put_ofs, const orc_indmatch* put,
+                           double precision_px, uint32_t max_iter,
+                           uint64_t* out_ofs, orc_indmatch* out, int n_threads);
+/* 5-point essential solver on bearing vectors (Nister / Stewenius): returns #models (<= 10), E[k*9..] row-major,
+ * b2^T E b1 = 0 */
+int orc_five_point(const double* b1 /*5x3*/, const double* b2 /*5x3*/, double* E /*90*/);
+
 /* 7-point solver on (already normalised) points: returns #models, F[k*9..] row-major. */
 int orc_seven_point(const double* x1 /*7x2*/, const double* x2 /*7x2*/, double* F /*27*/);
 

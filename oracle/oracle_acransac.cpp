@@ -255,6 +255,46 @@ static inline double asym_error(const double* H, double x1x, double x1y, double 
   return ex * ex + ey * ey;
 }
 
+// ---- essential: FivePointSolver (oracle_fivepoint.cpp) + EpipolarDistanceError on pixel coordinates ----
+int five_point(const double* b1, const double* b2, double* Eout);
+
+// bearing vector of a pixel: (K^-1 [x y 1]^T).normalized(), K = [f 0 ppx; 0 f ppy; 0 0 1]
+// (Pinhole_Intrinsic::operator(): Kinv * homogeneous, column-normalised)
+static inline void bearing(const double* K, double x, double y, double* b) {
+  const double kinv00 = 1.0 / K[0], kinv02 = -K[1] / K[0], kinv12 = -K[2] / K[0];
+  const double bx = kinv00 * x + kinv02, by = kinv00 * y + kinv12, bz = 1.0;
+  const double n = std::sqrt((bx * bx + by * by) + bz * bz);
+  b[0] = bx / n; b[1] = by / n; b[2] = bz / n;
+}
+
+// FundamentalFromEssential: F = K2^-T E K1^-1
+static inline void fundamental_from_essential(const double* E, const double* K1, const double* K2, double* F) {
+  const double k1[9] = {1.0 / K1[0], 0.0, -K1[1] / K1[0], 0.0, 1.0 / K1[0], -K1[2] / K1[0], 0.0, 0.0, 1.0};
+  const double k2[9] = {1.0 / K2[0], 0.0, -K2[1] / K2[0], 0.0, 1.0 / K2[0], -K2[2] / K2[0], 0.0, 0.0, 1.0};
+  double T[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a = a + k2[3 * k + r] * E[3 * k + c];   // K2^-T E
+      T[3 * r + c] = a;
+    }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a = a + T[3 * r + k] * k1[3 * k + c];
+      F[3 * r + c] = a;
+    }
+}
+
+// fundamental::kernel::EpipolarDistanceError::Error(F, x1, x2): squared distance of x2 to the line F x1
+static inline double epi_dist_error(const double* F, double x1x, double x1y, double x2x, double x2y) {
+  const double Fx0 = F[0] * x1x + F[1] * x1y + F[2];
+  const double Fx1 = F[3] * x1x + F[4] * x1y + F[5];
+  const double Fx2 = F[6] * x1x + F[7] * x1y + F[8];
+  const double yFx = x2x * Fx0 + x2y * Fx1 + Fx2;
+  return (yFx * yFx) / (Fx0 * Fx0 + Fx1 * Fx1);
+}
+
 // ---- logcombi tables (robust_estimator_ACRansac.hpp) : float, as upstream ----
 static float logcombi(uint32_t k, uint32_t n, const std::vector<float>& vec_log10) {
   if (k >= n || k <= 0) return 0.0f;
@@ -293,24 +333,41 @@ static void uniform_sample_n(uint32_t num_samples, std::mt19937& rng, std::vecto
 }
 
 // ---- ACRANSAC with the ACKernelAdaptor: MODEL 0 = <SevenPointSolver, SymmetricEpipolarDistanceError>
-//      (point-to-line), MODEL 1 = <FourPointSolver, AsymmetricError> (point-to-point) ----
+//      (point-to-line), MODEL 1 = <FourPointSolver, AsymmetricError> (point-to-point),
+//      MODEL 2 = ACKernelAdaptorEssential<FivePointSolver, EpipolarDistanceError> (bearing vectors for
+//      the fit, pixel residuals, no normalisation; Kpair = f1,ppx1,ppy1,f2,ppx2,ppy2) ----
 template <int MODEL>
 int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI, uint32_t wJ, uint32_t hJ,
-                 double precision_px, uint32_t max_iter, std::vector<uint32_t>& vec_inliers, double* M_out, double* info) {
-  const uint32_t sizeSample = MODEL == 0 ? 7 : 4;   // Kernel::MINIMUM_SAMPLES
-  const uint32_t MAX_MODELS = MODEL == 0 ? 3 : 1;   // Kernel::MAX_MODELS
+                 double precision_px, uint32_t max_iter, std::vector<uint32_t>& vec_inliers, double* M_out, double* info,
+                 const double* Kpair = nullptr) {
+  const uint32_t sizeSample = MODEL == 0 ? 7 : (MODEL == 1 ? 4 : 5);   // Kernel::MINIMUM_SAMPLES
+  const uint32_t MAX_MODELS = MODEL == 0 ? 3 : (MODEL == 1 ? 1 : 10);  // Kernel::MAX_MODELS
   vec_inliers.clear();
   if (info) { info[0] = std::numeric_limits<double>::infinity(); info[1] = 0; info[2] = 0; }
   const uint32_t nData = M;
   if (nData <= sizeSample) return 0;
 
   // kernel adaptor: PreconditionerFromPoints(w,h) ; ApplyTransformationToPoints
-  const double s1 = 1.0 / std::sqrt((double)((int)wI * (int)hI));
-  const double s2 = 1.0 / std::sqrt((double)((int)wJ * (int)hJ));
-  const double c1x = (double)(-.5f * (int)wI) * s1, c1y = -.5 * (int)hI * s1;
-  const double c2x = (double)(-.5f * (int)wJ) * s2, c2y = -.5 * (int)hJ * s2;
+  const double s1 = MODEL == 2 ? 1.0 : 1.0 / std::sqrt((double)((int)wI * (int)hI));
+  const double s2 = MODEL == 2 ? 1.0 : 1.0 / std::sqrt((double)((int)wJ * (int)hJ));
+  const double c1x = MODEL == 2 ? 0.0 : (double)(-.5f * (int)wI) * s1, c1y = MODEL == 2 ? 0.0 : -.5 * (int)hI * s1;
+  const double c2x = MODEL == 2 ? 0.0 : (double)(-.5f * (int)wJ) * s2, c2y = MODEL == 2 ? 0.0 : -.5 * (int)hJ * s2;
   std::vector<double> x1k(2 * (size_t)M), x2k(2 * (size_t)M);
+  std::vector<double> b1, b2;  // MODEL 2: bearing vectors
+  if (MODEL == 2) {
+    b1.resize(3 * (size_t)M);
+    b2.resize(3 * (size_t)M);
+    for (uint32_t i = 0; i < M; ++i) {
+      bearing(Kpair, xI[2 * i], xI[2 * i + 1], &b1[3 * (size_t)i]);
+      bearing(Kpair + 3, xJ[2 * i], xJ[2 * i + 1], &b2[3 * (size_t)i]);
+    }
+  }
   for (uint32_t i = 0; i < M; ++i) {
+    if (MODEL == 2) {  // the essential adaptor keeps pixel coordinates (normalizer = identity)
+      x1k[2 * i] = xI[2 * i]; x1k[2 * i + 1] = xI[2 * i + 1];
+      x2k[2 * i] = xJ[2 * i]; x2k[2 * i + 1] = xJ[2 * i + 1];
+      continue;
+    }
     x1k[2 * i] = s1 * xI[2 * i] + c1x;
     x1k[2 * i + 1] = s1 * xI[2 * i + 1] + c1y;
     x2k[2 * i] = s2 * xJ[2 * i] + c2x;
@@ -321,6 +378,11 @@ int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, ui
     const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
     const double Aarea = (double)wJ * (double)hJ;
     logalpha0 = det::log10(2.0 * D / Aarea / s2);
+    multError = 0.5;
+  } else if (MODEL == 2) {  // essential adaptor: log10(2 D / A * .5), pixel units
+    const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+    const double Aarea = (double)wJ * (double)hJ;
+    logalpha0 = det::log10(2.0 * D / Aarea * .5);
     multError = 0.5;
   } else {           // point-to-point: logalpha0 = log10(pi / (w h) / N2(0,0)^2)
     logalpha0 = det::log10(det::kPi / ((double)wJ * (double)hJ) / (s2 * s2));
@@ -351,20 +413,33 @@ int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, ui
   uint32_t iter = 0;
   for (iter = 0; iter < nIter; ++iter) {
     uniform_sample_n(sizeSample, random_generator, vec_index, vec_sample);
-    double sx1[14], sx2[14], models[27];
-    for (uint32_t t = 0; t < sizeSample; ++t) {
-      sx1[2 * t] = x1k[2 * vec_sample[t]];
-      sx1[2 * t + 1] = x1k[2 * vec_sample[t] + 1];
-      sx2[2 * t] = x2k[2 * vec_sample[t]];
-      sx2[2 * t + 1] = x2k[2 * vec_sample[t] + 1];
+    double sx1[15], sx2[15], models[90];
+    int nmodels;
+    if (MODEL == 2) {
+      for (uint32_t t = 0; t < sizeSample; ++t)
+        for (int c = 0; c < 3; ++c) {
+          sx1[3 * t + c] = b1[3 * (size_t)vec_sample[t] + c];
+          sx2[3 * t + c] = b2[3 * (size_t)vec_sample[t] + c];
+        }
+      double Es[90];
+      nmodels = five_point(sx1, sx2, Es);
+      for (int mi = 0; mi < nmodels; ++mi) fundamental_from_essential(Es + 9 * mi, Kpair, Kpair + 3, models + 9 * mi);
+    } else {
+      for (uint32_t t = 0; t < sizeSample; ++t) {
+        sx1[2 * t] = x1k[2 * vec_sample[t]];
+        sx1[2 * t + 1] = x1k[2 * vec_sample[t] + 1];
+        sx2[2 * t] = x2k[2 * vec_sample[t]];
+        sx2[2 * t + 1] = x2k[2 * vec_sample[t] + 1];
+      }
+      nmodels = MODEL == 0 ? seven_point(sx1, sx2, models) : four_point(sx1, sx2, models);
     }
-    const int nmodels = MODEL == 0 ? seven_point(sx1, sx2, models) : four_point(sx1, sx2, models);
     bool better = false;
     for (int mi = 0; mi < nmodels; ++mi) {
       const double* Mm = models + 9 * mi;
       for (uint32_t i = 0; i < nData; ++i) {
-        double e = MODEL == 0 ? sym_epi_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1])
-                              : asym_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1]);
+        double e = MODEL == 0   ? sym_epi_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1])
+                   : MODEL == 1 ? asym_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1])
+                                : epi_dist_error(Mm, x1k[2 * i], x1k[2 * i + 1], x2k[2 * i], x2k[2 * i + 1]);
         if (!(e == e)) e = std::numeric_limits<double>::infinity();  // NaN never is an inlier
         sorted[i] = {e, i};
       }
@@ -415,7 +490,9 @@ int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, ui
     if (M_out) {
       const double N1[9] = {s1, 0, c1x, 0, s1, c1y, 0, 0, 1};
       const double N2[9] = {s2, 0, c2x, 0, s2, c2y, 0, 0, 1};
-      if (MODEL == 0) {  // UnnormalizerT: F = N2^T * F * N1
+      if (MODEL == 2) {  // residual model of the essential adaptor: F = K2^-T E K1^-1 in pixel coordinates
+        std::memcpy(M_out, bestM, sizeof(bestM));
+      } else if (MODEL == 0) {  // UnnormalizerT: F = N2^T * F * N1
         double T[9];
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c) {
@@ -446,7 +523,7 @@ int64_t acransac(const double* xI, const double* xJ, uint32_t M, uint32_t wI, ui
           }
       }
     }
-    if (info) info[1] = std::sqrt(errorMax) / s2;  // unormalizeError
+    if (info) info[1] = std::sqrt(errorMax) / s2;  // unormalizeError (s2 = 1 for the essential adaptor)
   }
   return (int64_t)vec_inliers.size();
 }
@@ -460,6 +537,11 @@ int64_t acransac_H(const double* xI, const double* xJ, uint32_t M, uint32_t wI, 
                    uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,
                    std::vector<uint32_t>& vec_inliers, double* H_out, double* info) {
   return acransac<1>(xI, xJ, M, wI, hI, wJ, hJ, precision_px, max_iter, vec_inliers, H_out, info);
+}
+int64_t acransac_E(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
+                   uint32_t wJ, uint32_t hJ, const double* Kpair, double precision_px, uint32_t max_iter,
+                   std::vector<uint32_t>& vec_inliers, double* F_out, double* info) {
+  return acransac<2>(xI, xJ, M, wI, hI, wJ, hJ, precision_px, max_iter, vec_inliers, F_out, info, Kpair);
 }
 
 }  // namespace orc
@@ -488,9 +570,10 @@ int64_t orc_acransac_F(const double* xI, const double* xJ, uint32_t M, uint32_t 
 static int64_t filter_pairs_model(int model, const float* const* xys, const uint32_t* widths, const uint32_t* heights,
                                   uint32_t n_views, const uint32_t* pairs, uint64_t P,
                                   const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
-                                  uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
+                                  uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads,
+                                  const double* Ks = nullptr /* n_views x 3: f, ppx, ppy (model 2) */) {
   (void)n_views;
-  const double min_samples = model == 0 ? 7.0 : 4.0;
+  const double min_samples = model == 0 ? 7.0 : (model == 1 ? 4.0 : 5.0);
   if (n_threads <= 0) n_threads = omp_get_max_threads();
   std::vector<std::vector<orc_indmatch>> res(P);
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads)
@@ -507,7 +590,13 @@ static int64_t filter_pairs_model(int model, const float* const* xys, const uint
       xJ[2 * k + 1] = (double)xys[J][2 * (size_t)put[b + k].j + 1];
     }
     std::vector<uint32_t> inl;
-    if (model == 0)
+    if (model == 2) {
+      // GeometricFilter_EMatrix_AC::Robust_estimation: both views need a valid pinhole intrinsic
+      if (!(Ks[3 * I] > 0.0) || !(Ks[3 * J] > 0.0)) continue;
+      const double Kpair[6] = {Ks[3 * I], Ks[3 * I + 1], Ks[3 * I + 2], Ks[3 * J], Ks[3 * J + 1], Ks[3 * J + 2]};
+      orc::acransac_E(xI.data(), xJ.data(), M, widths[I], heights[I], widths[J], heights[J], Kpair,
+                      precision_px, max_iter, inl, nullptr, nullptr);
+    } else if (model == 0)
       orc::acransac_F(xI.data(), xJ.data(), M, widths[I], heights[I], widths[J], heights[J],
                       precision_px, max_iter, inl, nullptr, nullptr);
     else
@@ -545,6 +634,26 @@ int64_t orc_filter_pairs_H(const float* const* xys, const uint32_t* widths, cons
 }
 
 int orc_four_point(const double* x1, const double* x2, double* H) { return orc::four_point(x1, x2, H); }
+
+// GeometricFilter_EMatrix_AC(4.0, 2048) (src/R3DComputeMatches.cpp:2169-2171); Ks = n_views x (f, ppx, ppy),
+// f <= 0 marks a view without a valid pinhole intrinsic (its pairs are dropped)
+int64_t orc_filter_pairs_E(const float* const* xys, const uint32_t* widths, const uint32_t* heights, const double* Ks,
+                           uint32_t n_views, const uint32_t* pairs, uint64_t P,
+                           const uint64_t* put_ofs, const orc_indmatch* put, double precision_px,
+                           uint32_t max_iter, uint64_t* out_ofs, orc_indmatch* out, int n_threads) {
+  return filter_pairs_model(2, xys, widths, heights, n_views, pairs, P, put_ofs, put, precision_px, max_iter, out_ofs, out,
+                            n_threads, Ks);
+}
+
+int64_t orc_acransac_E(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
+                       uint32_t wJ, uint32_t hJ, const double* Kpair, double precision_px, uint32_t max_iter,
+                       uint32_t* inliers, double* F_out, double* info) {
+  std::vector<uint32_t> v;
+  orc::acransac_E(xI, xJ, M, wI, hI, wJ, hJ, Kpair, precision_px, max_iter, v, F_out, info);
+  if (!(v.size() > 5 * 2.5)) v.clear();
+  std::memcpy(inliers, v.data(), v.size() * sizeof(uint32_t));
+  return (int64_t)v.size();
+}
 
 int64_t orc_acransac_H(const double* xI, const double* xJ, uint32_t M, uint32_t wI, uint32_t hI,
                        uint32_t wJ, uint32_t hJ, double precision_px, uint32_t max_iter,

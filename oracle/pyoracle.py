@@ -71,6 +71,8 @@ def lib():
         _lib.orc_filter_pairs_F.restype = C.c_int64
         _lib.orc_filter_pairs_H.restype = C.c_int64
         _lib.orc_acransac_H.restype = C.c_int64
+        _lib.orc_acransac_E.restype = C.c_int64
+        _lib.orc_filter_pairs_E.restype = C.c_int64
     return _lib
 
 
@@ -197,6 +199,49 @@ def filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, 
 
 def filter_pairs_H(xys, widths, heights, pairs, put_ofs, put, precision_px=4.0, max_iter=2048, n_threads=0):
     return filter_pairs_F(xys, widths, heights, pairs, put_ofs, put, precision_px, max_iter, n_threads, model="H")
+
+
+def filter_pairs_E(xys, widths, heights, Ks, pairs, put_ofs, put, precision_px=4.0, max_iter=2048, n_threads=0):
+    """Ks: n_views x 3 (f, ppx, ppy); f <= 0 = no valid pinhole intrinsic."""
+    xys = [np.ascontiguousarray(x, np.float32) for x in xys]
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    P = pairs.shape[0]
+    widths = np.ascontiguousarray(widths, np.uint32)
+    heights = np.ascontiguousarray(heights, np.uint32)
+    Ks = np.ascontiguousarray(Ks, np.float64)
+    put_ofs = np.ascontiguousarray(put_ofs, np.uint64)
+    put = np.ascontiguousarray(put, indmatch_dtype)
+    out = np.zeros(max(1, put.shape[0]), indmatch_dtype)
+    out_ofs = np.zeros(P + 1, np.uint64)
+    n = lib().orc_filter_pairs_E(_ptr_array(xys), _p(widths), _p(heights), _p(Ks), C.c_uint32(len(xys)),
+                                 _p(pairs), C.c_uint64(P), _p(put_ofs), _p(put),
+                                 C.c_double(precision_px), C.c_uint32(max_iter), _p(out_ofs), _p(out),
+                                 C.c_int(n_threads))
+    return out_ofs, out[:n].copy()
+
+
+def acransac_E(xI, xJ, wI, hI, wJ, hJ, Kpair, precision_px=4.0, max_iter=2048):
+    """Kpair = (f1, ppx1, ppy1, f2, ppx2, ppy2).  Returns inliers, F (= K2^-T E K1^-1), info."""
+    xI = np.ascontiguousarray(xI, np.float64)
+    xJ = np.ascontiguousarray(xJ, np.float64)
+    Kpair = np.ascontiguousarray(Kpair, np.float64)
+    M = xI.shape[0]
+    inl = np.zeros(max(M, 1), np.uint32)
+    F = np.zeros((3, 3), np.float64)
+    info = np.zeros(3, np.float64)
+    n = lib().orc_acransac_E(_p(xI), _p(xJ), C.c_uint32(M), C.c_uint32(wI), C.c_uint32(hI),
+                             C.c_uint32(wJ), C.c_uint32(hJ), _p(Kpair), C.c_double(precision_px),
+                             C.c_uint32(max_iter), _p(inl), _p(F), _p(info))
+    return inl[:n].copy(), F, info
+
+
+def five_point(b1, b2):
+    """Bearing vectors (5x3 each) -> list of 3x3 essential matrices (b2^T E b1 = 0)."""
+    b1 = np.ascontiguousarray(b1, np.float64)
+    b2 = np.ascontiguousarray(b2, np.float64)
+    E = np.zeros((10, 3, 3), np.float64)
+    n = lib().orc_five_point(_p(b1), _p(b2), _p(E))
+    return [E[k].copy() for k in range(n)]
 
 
 def four_point(x1, x2):

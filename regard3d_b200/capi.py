@@ -48,7 +48,23 @@ class FilterTiming(C.Structure):
 
 
 class ViewInfo(C.Structure):
-    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32)]
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("focal", C.c_double), ("ppx", C.c_double),
+                ("ppy", C.c_double)]
+
+
+def make_views(widths, heights, Ks=None):
+    """r3d_view_info array.  Ks: n x 3 (focal, ppx, ppy); default = R3DProject's approximation
+    (src/R3DProject.cpp:1149-1159): focal = 1.1 * max(w, h), principal point at the image centre."""
+    n = len(widths)
+    views = (ViewInfo * n)()
+    for k in range(n):
+        w, h = int(widths[k]), int(heights[k])
+        views[k].width, views[k].height = w, h
+        if Ks is None:
+            views[k].focal, views[k].ppx, views[k].ppy = 1.1 * max(w, h), w / 2.0, h / 2.0
+        else:
+            views[k].focal, views[k].ppx, views[k].ppy = float(Ks[k][0]), float(Ks[k][1]), float(Ks[k][2])
+    return views
 
 
 class BAProblem(C.Structure):
@@ -78,13 +94,14 @@ class CMParams(C.Structure):
 class CMPaths(C.Structure):
     _fields_ = [("matches_dir", C.c_char_p), ("image_basenames", C.POINTER(C.c_char_p)),
                 ("views", C.POINTER(ViewInfo)), ("n_views", C.c_uint32), ("matches_f_filename", C.c_char_p),
-                ("matches_h_filename", C.c_char_p)]
+                ("matches_h_filename", C.c_char_p), ("matches_e_filename", C.c_char_p)]
 
 
 class CMStats(C.Structure):
     _fields_ = [("n_views", C.c_uint32), ("number_of_keypoints", C.POINTER(C.c_uint32)),
                 ("putative_pairs", C.c_uint64), ("putative_matches", C.c_uint64), ("f_pairs", C.c_uint64),
-                ("f_matches", C.c_uint64), ("h_pairs", C.c_uint64), ("h_matches", C.c_uint64), ("seconds_load", C.c_double), ("seconds_match", C.c_double),
+                ("f_matches", C.c_uint64), ("h_pairs", C.c_uint64), ("h_matches", C.c_uint64), ("e_pairs", C.c_uint64),
+                ("e_matches", C.c_uint64), ("seconds_load", C.c_double), ("seconds_match", C.c_double),
                 ("seconds_filter", C.c_double)]
 
 
@@ -273,12 +290,9 @@ class Context:
         self._check(lib().r3d_debug_candidate_keys(self._h, C.c_uint32(view_db), C.c_uint32(view_query), _p(keys), C.byref(eps)))
         return keys, eps.value
 
-    def filter_pairs(self, putative, widths, heights, model=MODEL_F, precision_px=4.0, max_iter=2048):
+    def filter_pairs(self, putative, widths, heights, model=MODEL_F, precision_px=4.0, max_iter=2048, Ks=None):
         n = len(widths)
-        views = (ViewInfo * n)()
-        for k in range(n):
-            views[k].width = int(widths[k])
-            views[k].height = int(heights[k])
+        views = make_views(widths, heights, Ks)
         h = C.c_void_p()
         self._check(lib().r3d_filter_pairs(self._h, C.c_int(model), C.c_double(precision_px), C.c_uint32(max_iter),
                                            putative.handle, views, C.c_uint32(n), C.byref(h)))
@@ -348,15 +362,13 @@ class Context:
 
     def compute_matches(self, matches_dir, basenames, widths, heights, dist_ratio=0.6, dim=144,
                         compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None,
-                        compute_homography=False):
+                        compute_homography=False, compute_essential=False, Ks=None):
         n = len(basenames)
         names = (C.c_char_p * n)(*[b.encode() for b in basenames])
-        views = (ViewInfo * n)()
-        for k in range(n):
-            views[k].width = int(widths[k])
-            views[k].height = int(heights[k])
-        params = CMParams(dist_ratio, int(compute_fundamental), 0, int(compute_homography), matching_algorithm, dim)
-        paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None, None)
+        views = make_views(widths, heights, Ks)
+        params = CMParams(dist_ratio, int(compute_fundamental), int(compute_essential), int(compute_homography),
+                          matching_algorithm, dim)
+        paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None, None, None)
         kp = (C.c_uint32 * n)()
         stats = CMStats()
         stats.n_views = n

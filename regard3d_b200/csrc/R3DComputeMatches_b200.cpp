@@ -4,6 +4,7 @@
 // and computeMatches() returns false).
 #include "R3DComputeMatches_b200.h"
 
+#include <algorithm>
 #include <cstring>
 
 namespace r3d_shim {
@@ -60,6 +61,12 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
     base_ptrs[v] = bases[v].c_str();
     views[v].width = (uint32_t)imageInfoVector_[v].imageWidth_;
     views[v].height = (uint32_t)imageInfoVector_[v].imageHeight_;
+    // pinhole K of the view exactly as R3DProject::writeSfmData builds it (src/R3DProject.cpp:1143-1159)
+    const ImageInfo& ii = imageInfoVector_[v];
+    const int wmax = std::max(ii.imageWidth_, ii.imageHeight_);
+    views[v].focal = (ii.focalLength_ > 0 && ii.sensorWidth_ > 0) ? wmax * ii.focalLength_ / ii.sensorWidth_ : wmax * 1.1;
+    views[v].ppx = static_cast<double>(ii.imageWidth_) / 2.0;
+    views[v].ppy = static_cast<double>(ii.imageHeight_) / 2.0;
   }
   r3d_cm_params p;
   p.dist_ratio = params.distRatio_;
@@ -75,6 +82,7 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
   cp.n_views = n;
   cp.matches_f_filename = paths.matchesFFilename_.empty() ? nullptr : paths.matchesFFilename_.c_str();
   cp.matches_h_filename = paths.matchesHFilename_.empty() ? nullptr : paths.matchesHFilename_.c_str();
+  cp.matches_e_filename = paths.matchesEFilename_.empty() ? nullptr : paths.matchesEFilename_.c_str();
   std::vector<uint32_t> kp(n, 0);
   r3d_cm_stats st;
   std::memset(&st, 0, sizeof(st));
@@ -97,6 +105,13 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
     const std::string f = paths.matchesFFilename_.empty() ? paths.relativeMatchesPath_ + "/matches.f.txt" : paths.matchesFFilename_;
     if (r3d_load_matches_txt(f.c_str(), &m) == R3D_OK) {
       to_map(m, statistics_.fundamentalMatches_);
+      r3d_free_matches(m);
+    }
+  }
+  if (params.computeEssentialMatrix_) {
+    const std::string f = paths.matchesEFilename_.empty() ? paths.relativeMatchesPath_ + "/matches.e.txt" : paths.matchesEFilename_;
+    if (r3d_load_matches_txt(f.c_str(), &m) == R3D_OK) {
+      to_map(m, statistics_.essentialMatches_);
       r3d_free_matches(m);
     }
   }

@@ -44,6 +44,7 @@ struct R3DProjectPaths {
 struct ImageInfo {
   std::string filename_;  // image%06d.jpg inside relativeImagePath_ (src/R3DProject.cpp:1042)
   int imageWidth_ = 0, imageHeight_ = 0;
+  double focalLength_ = 0.0, sensorWidth_ = 0.0;  // mm, from EXIF + camera database; 0 = unknown (ImageInfo, src/R3DProject.h)
 };
 typedef std::vector<ImageInfo> ImageInfoVector;
 

@@ -12,7 +12,12 @@ struct AcPair {          // per image pair (device)
   double max_thr;        // precision^2 * N2(0,0)^2
   double logalpha0;      // F: log10(2 D / A / N2(0,0)) ; H: log10(pi / (w h) / N2(0,0)^2), image J
   double loge0;          // log10(MAX_MODELS * (M - MINIMUM_SAMPLES))
+  double K[6];           // essential model only: f, ppx, ppy of image I, then of image J (pinhole K)
 };
+
+// internal model ids: 0 = F (7-point), 1 = H (4-point), 2 = E (5-point); Kernel::MINIMUM_SAMPLES / MAX_MODELS
+__host__ __device__ constexpr uint32_t ac_min_samples(int model) { return model == 0 ? 7u : (model == 1 ? 4u : 5u); }
+__host__ __device__ constexpr uint32_t ac_max_models(int model) { return model == 0 ? 3u : (model == 1 ? 1u : 10u); }
 
 struct AcHyp {           // one RANSAC iteration of one pair
   uint32_t pair;
@@ -30,7 +35,7 @@ struct AcInlierReq {
   uint32_t pair;
   uint32_t k;            // number of inliers wanted (prefix of the sorted residuals)
   uint32_t out_ofs;
-  uint32_t hyp_model;    // hypothesis * 3 + model: where this round's F matrix lives on the device
+  uint32_t hyp_model;    // hypothesis * MAX_MODELS + model: where this round's model matrix lives on the device
 };
 
 int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,

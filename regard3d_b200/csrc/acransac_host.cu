@@ -75,20 +75,28 @@ inline void skip_sample7(uint32_t ns, std::mt19937& rng, uint32_t pool_size) {
   }
 }
 
+// device scratch out of the worker's size-bucketed pool (context.cu): no cudaMalloc / cudaFree per call --
+// both synchronise the device and cost up to a second per call on multi-GPU boxes.  Everything that
+// touches these buffers is ordered on w.stream, so a released block may be handed out again at once.
 template <typename T>
 struct DevBuf {
+  DeviceWorker* w;
   T* p = nullptr;
   size_t cap = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
+  explicit DevBuf(DeviceWorker& worker) : w(&worker) {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) pool_release(*w, p); }
   cudaError_t ensure(size_t n) {
     if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p) pool_release(*w, p);
     p = nullptr;
     cap = 0;
     const size_t c = n + n / 2 + 64;
-    cudaError_t e = cudaMalloc((void**)&p, c * sizeof(T));
-    if (e == cudaSuccess) cap = c;
-    return e;
+    p = (T*)pool_alloc(*w, c * sizeof(T));
+    if (!p) return cudaErrorMemoryAllocation;
+    cap = c;
+    return cudaSuccess;
   }
 };
 
@@ -102,7 +110,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   const double t_begin = now_ms();
   const uint64_t P = put->pairs.size() / 2;
   result.assign(P, {});
-  const uint32_t sizeSample = model == 0 ? 7u : 4u, MAX_MODELS = model == 0 ? 3u : 1u;  // Kernel::MINIMUM_SAMPLES / MAX_MODELS
+  const uint32_t sizeSample = ac_min_samples(model), MAX_MODELS = ac_max_models(model);  // Kernel::MINIMUM_SAMPLES / MAX_MODELS
 
   // ---- per pair set-up (kernel adaptor of SURVEY.md A.5: normalisation, logalpha0, tables) ----
   std::vector<PairState> st;
@@ -117,6 +125,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       const uint32_t M = (uint32_t)(put->ofs[p + 1] - put->ofs[p]);
       if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
       if (I >= n_views || J >= n_views) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: view id outside views[]");
+      // GeometricFilter_EMatrix_AC::Robust_estimation returns false without two valid pinhole intrinsics
+      if (model == 2 && (!(views[I].focal > 0.0) || !(views[J].focal > 0.0))) continue;
       auto vi = w.views.find(I), vj = w.views.find(J);
       if (vi == w.views.end() || vj == w.views.end() || !vi->second.has_xy || !vj->second.has_xy)
         return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: positions of a view were not uploaded");
@@ -158,10 +168,11 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     const ViewDev& vi = w.views.find(s.I)->second;
     const ViewDev& vj = w.views.find(s.J)->second;
     const int wI = (int)views[s.I].width, hI = (int)views[s.I].height, wJ = (int)views[s.J].width, hJ = (int)views[s.J].height;
-    const double s1 = 1.0 / std::sqrt((double)(wI * hI));
-    const double s2 = 1.0 / std::sqrt((double)(wJ * hJ));
-    const double c1x = (double)(-.5f * wI) * s1, c1y = -.5 * hI * s1;
-    const double c2x = (double)(-.5f * wJ) * s2, c2y = -.5 * hJ * s2;
+    // the essential adaptor keeps pixel coordinates (normalizer = identity)
+    const double s1 = model == 2 ? 1.0 : 1.0 / std::sqrt((double)(wI * hI));
+    const double s2 = model == 2 ? 1.0 : 1.0 / std::sqrt((double)(wJ * hJ));
+    const double c1x = model == 2 ? 0.0 : (double)(-.5f * wI) * s1, c1y = model == 2 ? 0.0 : -.5 * hI * s1;
+    const double c2x = model == 2 ? 0.0 : (double)(-.5f * wJ) * s2, c2y = model == 2 ? 0.0 : -.5 * hJ * s2;
     const float* xyI = vi.h_xy.data();
     const float* xyJ = vj.h_xy.data();
     for (uint32_t k = 0; k < M; ++k) {
@@ -169,8 +180,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       if (m.i >= vi.n || m.j >= vj.n) { bad.store(1); return; }
       const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
       const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
-      hx1[s.pt_ofs + k] = make_double2(s1 * xi + c1x, s1 * yi + c1y);
-      hx2[s.pt_ofs + k] = make_double2(s2 * xj + c2x, s2 * yj + c2y);
+      hx1[s.pt_ofs + k] = model == 2 ? make_double2(xi, yi) : make_double2(s1 * xi + c1x, s1 * yi + c1y);
+      hx2[s.pt_ofs + k] = model == 2 ? make_double2(xj, yj) : make_double2(s2 * xj + c2x, s2 * yj + c2y);
     }
     AcPair ap;
     ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
@@ -180,10 +191,16 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
       const double Aarea = (double)wJ * (double)hJ;
       ap.logalpha0 = dm::log10_det(2.0 * D / Aarea / s2);
+    } else if (model == 2) {  // ACKernelAdaptorEssential: log10(2 D / A * .5), pixel units
+      const double D = std::sqrt((double)wJ * (double)wJ + (double)hJ * (double)hJ);
+      const double Aarea = (double)wJ * (double)hJ;
+      ap.logalpha0 = dm::log10_det(2.0 * D / Aarea * .5);
     } else {           // point-to-point
       ap.logalpha0 = dm::log10_det(R3D_PI / ((double)wJ * (double)hJ) / (s2 * s2));
     }
     ap.loge0 = dm::log10_det((double)MAX_MODELS * (double)(M - sizeSample));
+    ap.K[0] = views[s.I].focal; ap.K[1] = views[s.I].ppx; ap.K[2] = views[s.I].ppy;
+    ap.K[3] = views[s.J].focal; ap.K[4] = views[s.J].ppx; ap.K[5] = views[s.J].ppy;
     hpairs[a] = ap;
     s.vec_index.resize(M);
     std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
@@ -208,14 +225,14 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: more than 16384 putative matches in one pair");
 
   // ---- device buffers -------------------------------------------------------------------------
-  DevBuf<AcPair> d_pairs;
-  DevBuf<double2> d_x1, d_x2;
-  DevBuf<float> d_logc_n, d_logc_k;
-  DevBuf<AcHyp> d_hyp;
-  DevBuf<double> d_F;
-  DevBuf<uint32_t> d_nm, d_inl;
-  DevBuf<AcScore> d_score;
-  DevBuf<AcInlierReq> d_req;
+  DevBuf<AcPair> d_pairs(w);
+  DevBuf<double2> d_x1(w), d_x2(w);
+  DevBuf<float> d_logc_n(w), d_logc_k(w);
+  DevBuf<AcHyp> d_hyp(w);
+  DevBuf<double> d_F(w);
+  DevBuf<uint32_t> d_nm(w), d_inl(w);
+  DevBuf<AcScore> d_score(w);
+  DevBuf<AcInlierReq> d_req(w);
   R3D_CUDA_TRY(ctx, d_pairs.ensure(hpairs.size()));
   R3D_CUDA_TRY(ctx, d_x1.ensure(hx1.size()));
   R3D_CUDA_TRY(ctx, d_x2.ensure(hx2.size()));
@@ -273,9 +290,9 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     const uint32_t H = (uint32_t)hhyp.size();
     T.hypotheses += H;
     R3D_CUDA_TRY(ctx, d_hyp.ensure(H));
-    R3D_CUDA_TRY(ctx, d_F.ensure((size_t)H * 27));
+    R3D_CUDA_TRY(ctx, d_F.ensure((size_t)H * 9 * MAX_MODELS));
     R3D_CUDA_TRY(ctx, d_nm.ensure(H));
-    R3D_CUDA_TRY(ctx, d_score.ensure((size_t)H * 3));
+    R3D_CUDA_TRY(ctx, d_score.ensure((size_t)H * MAX_MODELS));
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_hyp.p, hhyp.data(), (size_t)H * sizeof(AcHyp), cudaMemcpyHostToDevice, w.stream));
     // ---- 2. solve + score on the device -------------------------------------------------------
     R3D_CUDA_TRY(ctx, cudaEventRecord(ev[0], w.stream));
@@ -286,9 +303,9 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     if (rc) return rc;
     R3D_CUDA_TRY(ctx, cudaEventRecord(ev[2], w.stream));
     T.kernel_launches += 2;
-    hscore.resize((size_t)H * 3);
+    hscore.resize((size_t)H * MAX_MODELS);
     hnm.resize(H);
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hscore.data(), d_score.p, (size_t)H * 3 * sizeof(AcScore), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hscore.data(), d_score.p, (size_t)H * MAX_MODELS * sizeof(AcScore), cudaMemcpyDeviceToHost, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hnm.data(), d_nm.p, (size_t)H * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
     R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
     float ms;
@@ -306,7 +323,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
         const uint32_t h = s.hyp_ofs + it;
         bool better = false;
         for (uint32_t mi = 0; mi < hnm[h]; ++mi) {
-          const AcScore& sc = hscore[(size_t)h * 3 + mi];
+          const AcScore& sc = hscore[(size_t)h * MAX_MODELS + mi];
           if (!s.ac_mode && (double)sc.count > 2.5 * sizeSample) s.ac_mode = true;
           if (s.ac_mode && sc.nfa < s.minNFA) {
             better = true;
@@ -346,7 +363,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       PairState& s = st[a];
       if (s.best_changed) {  // the best model's inlier list is needed now (event) or possibly later
         AcInlierReq rq;
-        rq.pair = a; rq.k = s.best_k; rq.out_ofs = inl_total; rq.hyp_model = s.best_hyp * 3 + s.best_model;
+        rq.pair = a; rq.k = s.best_k; rq.out_ofs = inl_total; rq.hyp_model = s.best_hyp * MAX_MODELS + s.best_model;
         hreq.push_back(rq);
         inl_total += s.best_k;
       }
@@ -412,10 +429,11 @@ extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, ui
                                 const r3d_view_info* views, uint32_t n_views, r3d_matches** out) {
   if (!ctx || !putative || !views || !out) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: bad arguments");
   *out = nullptr;
-  if (model != R3D_MODEL_F && model != R3D_MODEL_H)
-    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: the essential-matrix filter (5-point) is not implemented (SURVEY.md 8f)");
+  if (model != R3D_MODEL_F && model != R3D_MODEL_H && model != R3D_MODEL_E)
+    return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: unknown model");
   std::vector<std::vector<r3d_indmatch>> res;
-  int rc = filter_pairs_model(ctx, ctx->workers[0], model == R3D_MODEL_F ? 0 : 1, precision_px, max_iter, putative, views, n_views, res);
+  const int internal = model == R3D_MODEL_F ? 0 : (model == R3D_MODEL_H ? 1 : 2);
+  int rc = filter_pairs_model(ctx, ctx->workers[0], internal, precision_px, max_iter, putative, views, n_views, res);
   if (rc) return rc;
   r3d_matches* m = new r3d_matches();
   m->ofs.push_back(0);

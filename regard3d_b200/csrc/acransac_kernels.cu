@@ -12,6 +12,7 @@
 //   k_f7_inliers : one block per request -- the sorted inlier index list of one model
 #include "acransac.cuh"
 #include "detmath.cuh"
+#include "fivepoint.cuh"
 
 #include <cfloat>
 
@@ -210,6 +211,59 @@ __device__ int four_point(const double* x, const double* y, double* Hout) {
   return nullspace_8x9(L, Hout) ? 1 : 0;
 }
 
+// bearing vector of a pixel: (K^-1 [x y 1]^T).normalized(), K = [f 0 ppx; 0 f ppy; 0 0 1]
+// (openMVG Pinhole_Intrinsic::operator())
+__device__ __forceinline__ void bearing(const double* K, double x, double y, double* b) {
+  const double kinv00 = 1.0 / K[0], kinv02 = -K[1] / K[0], kinv12 = -K[2] / K[0];
+  const double bx = kinv00 * x + kinv02, by = kinv00 * y + kinv12, bz = 1.0;
+  const double n = sqrt((bx * bx + by * by) + bz * bz);
+  b[0] = bx / n; b[1] = by / n; b[2] = bz / n;
+}
+
+// FundamentalFromEssential: F = K2^-T E K1^-1
+__device__ void fundamental_from_essential(const double* E, const double* K1, const double* K2, double* F) {
+  const double k1[9] = {1.0 / K1[0], 0.0, -K1[1] / K1[0], 0.0, 1.0 / K1[0], -K1[2] / K1[0], 0.0, 0.0, 1.0};
+  const double k2[9] = {1.0 / K2[0], 0.0, -K2[1] / K2[0], 0.0, 1.0 / K2[0], -K2[2] / K2[0], 0.0, 0.0, 1.0};
+  double T[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a = a + k2[3 * k + r] * E[3 * k + c];
+      T[3 * r + c] = a;
+    }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double a = 0.0;
+      for (int k = 0; k < 3; ++k) a = a + T[3 * r + k] * k1[3 * k + c];
+      F[3 * r + c] = a;
+    }
+}
+
+// one thread per hypothesis of the essential model: bearings of the 5 sampled matches -> 5-point solver ->
+// every E turned into the pixel-space F = K2^-T E K1^-1 the residuals are measured with
+__global__ void __launch_bounds__(64) k_e5_solve(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
+                                                 const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
+                                                 uint32_t n_hyp, double* __restrict__ F, uint32_t* __restrict__ nmodels) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= n_hyp) return;
+  const AcHyp hy = hyps[h];
+  const AcPair pr = pairs[hy.pair];
+  double b1[15], b2[15], Es[90];
+  for (int t = 0; t < 5; ++t) {
+    const double2 a = x1[pr.pt_ofs + hy.sample[t]];
+    const double2 b = x2[pr.pt_ofs + hy.sample[t]];
+    bearing(pr.K, a.x, a.y, b1 + 3 * t);
+    bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
+  }
+  const int nm = fp::five_point(b1, b2, Es);
+  nmodels[h] = (uint32_t)nm;
+  for (int mi = 0; mi < nm; ++mi) {
+    double Fm[9];
+    fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, Fm);
+    for (int t = 0; t < 9; ++t) F[(size_t)h * 90 + 9 * mi + t] = Fm[t];
+  }
+}
+
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_f7_solve(const AcPair* __restrict__ pairs, const double2* __restrict__ x1,
                                                   const double2* __restrict__ x2, const AcHyp* __restrict__ hyps,
@@ -228,7 +282,7 @@ __global__ void __launch_bounds__(128) k_f7_solve(const AcPair* __restrict__ pai
   }
   const int nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
   nmodels[h] = (uint32_t)nm;
-  for (int t = 0; t < 9 * nm; ++t) F[(size_t)h * 27 + t] = models[t];
+  for (int t = 0; t < 9 * nm; ++t) F[(size_t)h * (9 * ac_max_models(MODEL)) + t] = models[t];
 }
 
 // SymmetricEpipolarDistanceError::Error
@@ -240,6 +294,15 @@ __device__ __forceinline__ double sym_epi_error(const double* F, double x1x, dou
   const double Fty1 = F[1] * x2x + F[4] * x2y + F[7];
   const double yFx = x2x * Fx0 + x2y * Fx1 + Fx2;
   return (yFx * yFx) * (1.0 / (Fx0 * Fx0 + Fx1 * Fx1) + 1.0 / (Fty0 * Fty0 + Fty1 * Fty1)) / 4.0;
+}
+
+// fundamental::kernel::EpipolarDistanceError::Error: squared distance of x2 to the epipolar line F x1 (pixels^2)
+__device__ __forceinline__ double epi_dist_error(const double* F, double x1x, double x1y, double x2x, double x2y) {
+  const double Fx0 = F[0] * x1x + F[1] * x1y + F[2];
+  const double Fx1 = F[3] * x1x + F[4] * x1y + F[5];
+  const double Fx2 = F[6] * x1x + F[7] * x1y + F[8];
+  const double yFx = x2x * Fx0 + x2y * Fx1 + Fx2;
+  return (yFx * yFx) / (Fx0 * Fx0 + Fx1 * Fx1);
 }
 
 // homography::kernel::AsymmetricError::Error
@@ -266,7 +329,9 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
   for (uint32_t i = threadIdx.x; i < pr.M; i += blockDim.x) {
     const double2 a = x1[pr.pt_ofs + i];
     const double2 b = x2[pr.pt_ofs + i];
-    const double e = MODEL == 0 ? sym_epi_error(Fm, a.x, a.y, b.x, b.y) : asym_error(Fm, a.x, a.y, b.x, b.y);
+    const double e = MODEL == 0   ? sym_epi_error(Fm, a.x, a.y, b.x, b.y)
+                     : MODEL == 1 ? asym_error(Fm, a.x, a.y, b.x, b.y)
+                                  : epi_dist_error(Fm, a.x, a.y, b.x, b.y);
     if (e <= pr.max_thr) {  // false for NaN
       const uint32_t pos = atomicAdd(s_count, 1u);
       if (pos < cap) { se[pos] = e; si[pos] = i; }
@@ -306,17 +371,18 @@ __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pai
   __shared__ uint32_t s_count;
   __shared__ double s_best_nfa[8];
   __shared__ uint32_t s_best_k[8];
-  const uint32_t h = blockIdx.x / 3, mi = blockIdx.x % 3;
+  constexpr uint32_t MAXM = ac_max_models(MODEL);
+  const uint32_t h = blockIdx.x / MAXM, mi = blockIdx.x % MAXM;
   if (mi >= nmodels[h]) return;
   const AcHyp hy = hyps[h];
   const AcPair pr = pairs[hy.pair];
   double* se = (double*)smem_raw;
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
-  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)h * 27 + 9 * mi + t];
+  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)h * (9 * MAXM) + 9 * mi + t];
   const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
-  constexpr uint32_t NS = MODEL == 0 ? 7u : 4u;       // Kernel::MINIMUM_SAMPLES
-  const double mult_error = MODEL == 0 ? 0.5 : 1.0;   // point-to-line : point-to-point
+  constexpr uint32_t NS = ac_min_samples(MODEL);      // Kernel::MINIMUM_SAMPLES
+  const double mult_error = MODEL == 1 ? 1.0 : 0.5;   // point-to-point : point-to-line
   // bestNFA: k = sizeSample+1 .. c  (the upstream loop stops at the first residual > maxThreshold)
   double best = DBL_MAX * 2.0;  // +inf
   uint32_t best_k = NS;
@@ -342,7 +408,7 @@ __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pai
     sc.err = (best_k > NS && best_k <= c) ? se[best_k - 1] : 0.0;
     sc.k = best_k;
     sc.count = s_count;
-    scores[(size_t)h * 3 + mi] = sc;
+    scores[(size_t)h * MAXM + mi] = sc;
   }
 }
 
@@ -357,7 +423,7 @@ __global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ p
   double* se = (double*)smem_raw;
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
-  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)(rq.hyp_model / 3) * 27 + (size_t)(rq.hyp_model % 3) * 9 + t];
+  for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)rq.hyp_model * 9 + t];  // hyp_model = hypothesis * MAX_MODELS + model
   const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
   for (uint32_t i = threadIdx.x; i < rq.k && i < c; i += blockDim.x) out[rq.out_ofs + i] = si[i];
 }
@@ -367,7 +433,8 @@ int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pair
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels) {
   if (!n_hyp) return R3D_OK;
   if (model == 0) k_f7_solve<0><<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
-  else k_f7_solve<1><<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
+  else if (model == 1) k_f7_solve<1><<<(n_hyp + 127) / 128, 128, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
+  else k_e5_solve<<<(n_hyp + 63) / 64, 64, 0, w.stream>>>(pairs, x1, x2, hyps, n_hyp, F, nmodels);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }
@@ -380,9 +447,12 @@ int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pair
   if (model == 0) {
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_f7_score<0><<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
-  } else {
+  } else if (model == 1) {
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_f7_score<1><<<n_hyp * 3, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+    k_f7_score<1><<<n_hyp * 1, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
+  } else {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_score<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_score<2><<<n_hyp * 10, 256, smem, w.stream>>>(pairs, x1, x2, hyps, F, nmodels, logc_n, logc_k, cap, scores);
   }
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
@@ -395,9 +465,12 @@ int launch_f7_inliers(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pa
   if (model == 0) {
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_f7_inliers<0><<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
-  } else {
+  } else if (model == 1) {
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_f7_inliers<1><<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
+  } else {
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_f7_inliers<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_f7_inliers<2><<<n_req, 256, smem, w.stream>>>(pairs, x1, x2, reqs, F, cap, out);
   }
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;

@@ -6,6 +6,8 @@
 //   Save(matches.putative.txt)        (:2064)
 //   Robust_model_estimation(F, AC)    (:2113)  -> r3d_filter_pairs
 //   Save(matchesFFilename_)           (:2120)
+//   Robust_model_estimation(E, AC)    (:2169)  -> r3d_filter_pairs + poor-overlap removal (:2173-2191), Save(:2196)
+//   Robust_model_estimation(H, AC)    (:2216)  -> r3d_filter_pairs, Save(:2224)
 // Progress fractions as the reference emits them (0.7 before matching :2000, 0.8 before the F filter
 // :2107).  File formats: SURVEY.md Appendix B.  Feature extraction (AKAZE + LIOP on the CPU thread
 // pool, src/threads/R3DFeaturesThread.cpp) stays with the caller: it is a "next" row.
@@ -61,6 +63,7 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
   if (stats) {
     stats->putative_pairs = stats->putative_matches = stats->f_pairs = stats->f_matches = 0;
     stats->h_pairs = stats->h_matches = 0;
+    stats->e_pairs = stats->e_matches = 0;
     stats->seconds_load = stats->seconds_match = stats->seconds_filter = 0;
   }
   // ---- regions ------------------------------------------------------------------------------------
@@ -115,6 +118,50 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
     r3d_free_matches(fm);
     if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + fpath); }
   }
+  if (params->compute_essential) {  // src/R3DComputeMatches.cpp:2130-2204
+    if (cb) cb(0.9f, "Calculate essential matrix", user);
+    r3d_matches* em = nullptr;
+    rc = r3d_filter_pairs(ctx, R3D_MODEL_E, 4.0, 2048, put, paths->views, N, &em);
+    if (rc) { r3d_free_matches(put); return rc; }
+    // "Perform an additional check to remove pairs with poor overlap" (:2173-2191): drop a pair when it keeps
+    // fewer than 50 matches or less than 30 % (float ratio) of its putative matches
+    {
+      std::vector<uint32_t> kp;
+      std::vector<uint64_t> kofs(1, 0);
+      std::vector<r3d_indmatch> km;
+      const uint64_t ne = r3d_matches_num_pairs(em), np = r3d_matches_num_pairs(put);
+      uint64_t q = 0;  // both maps are sorted by (I,J): merge walk
+      for (uint64_t k = 0; k < ne; ++k) {
+        uint32_t I, J, PI = 0, PJ = 0;
+        const r3d_indmatch* mm;
+        const r3d_indmatch* pm;
+        uint64_t cnt, pcnt = 0;
+        r3d_matches_get_pair(em, k, &I, &J, &mm, &cnt);
+        for (; q < np; ++q) {
+          r3d_matches_get_pair(put, q, &PI, &PJ, &pm, &pcnt);
+          if (PI == I && PJ == J) break;
+        }
+        const float ratio = cnt / (float)pcnt;
+        if (cnt < 50 || ratio < .3f) continue;
+        kp.push_back(I);
+        kp.push_back(J);
+        km.insert(km.end(), mm, mm + cnt);
+        kofs.push_back(km.size());
+      }
+      r3d_free_matches(em);
+      em = nullptr;
+      rc = r3d_matches_from_csr(kp.data(), kp.size() / 2, kofs.data(), km.data(), &em);
+      if (rc) { r3d_free_matches(put); return fail(ctx, rc, "r3d_compute_matches: essential overlap filter"); }
+    }
+    if (stats) {
+      stats->e_pairs = r3d_matches_num_pairs(em);
+      stats->e_matches = r3d_matches_total(em);
+    }
+    const std::string epath = paths->matches_e_filename ? std::string(paths->matches_e_filename) : dir + "/matches.e.txt";
+    rc = r3d_save_matches_txt(em, epath.c_str());
+    r3d_free_matches(em);
+    if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + epath); }
+  }
   if (params->compute_homography) {  // src/R3DComputeMatches.cpp:2206-2233
     if (cb) cb(0.95f, "Calculate homography matrix", user);
     r3d_matches* hm = nullptr;
@@ -129,7 +176,6 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
     r3d_free_matches(hm);
     if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + hpath); }
   }
-  // the essential-matrix filter (src/R3DComputeMatches.cpp:2130-2204) is not built in this round
   r3d_free_matches(put);
   if (cb) cb(1.0f, "Done", user);
   return R3D_OK;

@@ -107,6 +107,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   }
   if (all.empty()) return R3D_OK;
   const int kp = operand_cols((int)dim);
+  const double t_prepared = now_ms();
 
   r3d_match_timing& T = w.timing;
   std::mutex t_mutex;  // T is updated by the batch tail threads
@@ -352,8 +353,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   for (auto& t : tails) t.join();
   tails.clear();
   if (getenv("R3D_DEBUG_TIMING"))
-    fprintf(stderr, "[r3d] match_on_worker: launch loop %.2f ms, tail join %.2f ms\n", t_launch_done - t_enter,
-            now_ms() - t_launch_done);
+    fprintf(stderr, "[r3d] match_on_worker: prepare %.2f ms, launch loop %.2f ms, tail join %.2f ms\n",
+            t_prepared - t_enter, t_launch_done - t_prepared, now_ms() - t_launch_done);
   if (tail_rc.load() != R3D_OK) return tail_rc.load();
   return R3D_OK;
 }
@@ -428,6 +429,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
     ctx->match_timing = sum;
   }
   // assemble the PairWiseMatches map (sorted by (I,J); empty pairs are not inserted)
+  const double t_assemble = now_ms();
   struct Entry { uint32_t I, J; std::vector<r3d_indmatch>* v; };
   std::vector<Entry> entries;
   for (size_t k = 0; k < nw; ++k)
@@ -458,7 +460,8 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
       std::memcpy(m->m.data() + m->ofs[k], v.data(), v.size() * sizeof(r3d_indmatch));
     });
   }
-  if (getenv("R3D_DEBUG_TIMING")) fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms\n", now_ms() - t_call);
+  if (getenv("R3D_DEBUG_TIMING"))
+    fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms (assembly %.2f ms)\n", now_ms() - t_call, now_ms() - t_assemble);
   *out = m;
   return R3D_OK;
 }

@@ -1,0 +1,13 @@
+# 1-GPU session B: full GPU tests, host-timing breakdown, BA launch list, C3 / C4 workloads
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+R3D_DEBUG_TIMING=1 timeout 600 python bench.py --steps 3 --no-cpu-baseline --no-ba > gpurun_out/bench_dbg.json 2> gpurun_out/bench_dbg.err
+grep "r3d\]" gpurun_out/bench_dbg.err | tail -12
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_ba.csv python tests/gpu_ba_profile.py > gpurun_out/ba_prof.log 2>&1
+timeout 900 python bench.py --workload c3 --steps 2 --warmup 1 --no-ba --no-filter > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "c3 rc=$?"
+head -c 400 gpurun_out/bench_c3.json
+timeout 900 python bench.py --workload c4 --steps 1 --warmup 1 --no-ba --no-filter --no-cpu-baseline > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?"
+head -c 400 gpurun_out/bench_c4.json
+free -g | head -2; nproc

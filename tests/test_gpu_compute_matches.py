@@ -44,6 +44,37 @@ def test_compute_matches_files_equal_oracle(gpu_ctx, oracle, tmp_path):
     assert seen[:2] == [0.7, 0.8]                       # the reference's progress fractions
 
 
+def test_compute_matches_essential_and_homography_files(gpu_ctx, oracle, tmp_path):
+    """computeEssentialMatrix_ / computeHomographyMatrix_: matches.e.txt (after the reference's poor-overlap
+    removal, src/R3DComputeMatches.cpp:2173-2191) and matches.h.txt equal the oracle's."""
+    sc, names = _write_project(oracle, tmp_path)
+    seen = []
+    stats = gpu_ctx.compute_matches(str(tmp_path), names, sc["widths"], sc["heights"], dist_ratio=0.6, dim=144,
+                                    compute_essential=True, compute_homography=True,
+                                    progress=lambda f, msg, user: seen.append(round(f, 2)))
+    pairs = synth.exhaustive_pairs(len(names))
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.6)
+    Ks = np.array([[1.1 * 1920, 960.0, 540.0]] * len(names))
+    eo, em = oracle.filter_pairs_E(sc["xys"], sc["widths"], sc["heights"], Ks, pairs, ofs, m)
+    keep_ofs, keep_m = [0], []
+    for k in range(len(pairs)):
+        ne, npu = int(eo[k + 1] - eo[k]), int(ofs[k + 1] - ofs[k])
+        if ne == 0 or ne < 50 or np.float32(ne) / np.float32(npu) < np.float32(0.3):
+            keep_ofs.append(keep_ofs[-1])
+            continue
+        keep_m.append(em[int(eo[k]):int(eo[k + 1])])
+        keep_ofs.append(keep_ofs[-1] + ne)
+    pe = str(tmp_path / "oracle.e.txt")
+    oracle.save_matches_txt(pe, pairs, np.array(keep_ofs, np.uint64), np.concatenate(keep_m))
+    assert open(tmp_path / "matches.e.txt").read() == open(pe).read()
+    ho, hm = oracle.filter_pairs_H(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m)
+    ph = str(tmp_path / "oracle.h.txt")
+    oracle.save_matches_txt(ph, pairs, ho, hm)
+    assert open(tmp_path / "matches.h.txt").read() == open(ph).read()
+    assert stats["e_pairs"] == sum(1 for k in range(len(pairs)) if keep_ofs[k + 1] > keep_ofs[k]) and stats["e_pairs"] > 0
+    assert seen[:4] == [0.7, 0.8, 0.9, 0.95]
+
+
 def test_cpp_shim_class(r3dlib, oracle, tmp_path):
     sc, names = _write_project(oracle, tmp_path, n_img=3, n_feat=1000)
     lib = r3dlib.lib()

@@ -14,11 +14,21 @@ def _setup(ctx, sc):
         ctx.upload_regions(v, d, x)
 
 
-def _check(ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=2048, model="F"):
+def _default_Ks(sc):
+    # R3DProject's approximation (src/R3DProject.cpp:1149-1159): f = 1.1 max(w,h), pp at the image centre
+    return np.array([[1.1 * max(int(w), int(h)), w / 2.0, h / 2.0] for w, h in zip(sc["widths"], sc["heights"])])
+
+
+def _check(ctx, oracle, r3dlib, sc, pairs, ofs, m, max_iter=2048, model="F", Ks=None):
     put = r3dlib.Matches.from_csr(pairs, ofs, m)
-    got = ctx.filter_pairs(put, sc["widths"], sc["heights"], max_iter=max_iter,
-                           model=r3dlib.MODEL_F if model == "F" else r3dlib.MODEL_H).to_dict()
-    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m, max_iter=max_iter, model=model)
+    mid = {"F": r3dlib.MODEL_F, "H": r3dlib.MODEL_H, "E": r3dlib.MODEL_E}[model]
+    if model == "E" and Ks is None:
+        Ks = _default_Ks(sc)
+    got = ctx.filter_pairs(put, sc["widths"], sc["heights"], max_iter=max_iter, model=mid, Ks=Ks).to_dict()
+    if model == "E":
+        fo, fm = oracle.filter_pairs_E(sc["xys"], sc["widths"], sc["heights"], Ks, pairs, ofs, m, max_iter=max_iter)
+    else:
+        fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m, max_iter=max_iter, model=model)
     n_pairs_exp = 0
     for k, (I, J) in enumerate(pairs):
         e = fm[int(fo[k]):int(fo[k + 1])]
@@ -117,7 +127,31 @@ def test_homography_filter_equals_oracle(gpu_ctx, oracle, r3dlib):
     assert len(got) == 3
     for k, v in got.items():
         assert 550 < len(v) < 700
-    # E is not implemented
-    with pytest.raises(r3dlib.R3DError) as e:
-        gpu_ctx.filter_pairs(r3dlib.Matches.from_csr(pairs, ofs, m), sc["widths"], sc["heights"], model=r3dlib.MODEL_E)
-    assert e.value.code == -5
+
+
+def test_essential_filter_equals_oracle(gpu_ctx, oracle, r3dlib):
+    """GeometricFilter_EMatrix_AC: 5-point solver on bearing vectors, <= 10 models per sample -- identical inlier
+    sequences, including a pair with gross outliers, a hopeless pair and a view without intrinsics."""
+    sc = synth.make_scene(4, 1500, 64, "msurf", seed=33)
+    pairs = synth.exhaustive_pairs(4)
+    _setup(gpu_ctx, sc)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.8)
+    rng = np.random.default_rng(4)
+    m2 = m.copy()
+    s0 = slice(int(ofs[0]), int(ofs[1]))
+    bad = rng.random(int(ofs[1] - ofs[0])) < 0.35
+    j0 = m2["j"][s0].copy()
+    j0[bad] = rng.integers(0, 1500, bad.sum())
+    m2["j"][s0] = j0
+    s1 = slice(int(ofs[1]), int(ofs[2]))
+    m2["j"][s1] = rng.permutation(1500)[: int(ofs[2] - ofs[1])]      # all wrong: must fail
+    Ks = _default_Ks(sc)
+    got = _check(gpu_ctx, oracle, r3dlib, sc, pairs, ofs, m2, model="E", Ks=Ks)
+    assert (0, 1) in got and (0, 2) not in got
+    truth = sc["truth"]
+    g = got[(0, 1)]
+    assert (truth[0][g["i"]] == truth[1][g["j"]]).mean() > 0.97       # the kept matches are true correspondences
+    Ks[3, 0] = 0.0                                                    # view 3 has no pinhole intrinsic
+    got = _check(gpu_ctx, oracle, r3dlib, sc, pairs, ofs, m2, model="E", Ks=Ks)
+    assert all(3 not in k for k in got)
+    assert gpu_ctx.filter_timing()["hypotheses"] > 0

@@ -114,3 +114,69 @@ def test_four_point_and_homography_acransac(oracle):
     assert info[0] < 0 and (inl >= 150).mean() > 0.98 and len(inl) > 300
     h = np.c_[x1[inl], np.ones(len(inl))] @ He.T
     assert np.median(np.linalg.norm(h[:, :2] / h[:, 2:] - x2n[inl], axis=1)) < 1.5
+
+
+# ---- essential matrix: 5-point solver + ACKernelAdaptorEssential (GeometricFilter_EMatrix_AC) ----
+def _rot(w):
+    th = np.linalg.norm(w)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def test_five_point_solutions_satisfy_the_constraints_and_contain_the_truth(oracle):
+    rng = np.random.default_rng(1)
+    found = 0
+    for _ in range(60):
+        R = _rot(rng.normal(size=3) * 0.3)
+        t = rng.normal(size=3)
+        t /= np.linalg.norm(t)
+        X = rng.uniform(-1, 1, (5, 3)) + np.array([0, 0, 5])
+        b1 = X / np.linalg.norm(X, axis=1, keepdims=True)
+        X2 = X @ R.T + t
+        b2 = X2 / np.linalg.norm(X2, axis=1, keepdims=True)
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        Et = tx @ R
+        Et /= np.linalg.norm(Et)
+        Es = oracle.five_point(b1, b2)
+        assert 1 <= len(Es) <= 10 and len(Es) % 2 == 0      # real roots of the degree-10 polynomial come in pairs
+        best = np.inf
+        for E in Es:
+            n = np.linalg.norm(E)
+            assert np.abs(np.einsum("ni,ij,nj->n", b2, E, b1)).max() < 1e-9 * n          # epipolar constraints
+            assert np.abs(2 * E @ E.T @ E - np.trace(E @ E.T) * E).max() < 1e-6 * n ** 3  # trace constraint
+            assert abs(np.linalg.det(E)) < 1e-6 * n ** 3
+            best = min(best, np.linalg.norm(E / n - Et), np.linalg.norm(E / n + Et))
+        found += best < 1e-6
+    assert found == 60
+
+
+def test_acransac_E_recovers_inliers(oracle):
+    xI, xJ, good = _two_view(3)
+    f = 1.1 * 1920
+    K = np.array([f, 960.0, 540.0, f, 960.0, 540.0])
+    inl, F, info = oracle.acransac_E(xI, xJ, 1920, 1080, 1920, 1080, K)
+    assert info[0] < 0
+    assert good[inl].mean() > 0.97 and good[inl].sum() > 0.9 * good.sum()
+    h1 = np.c_[xI[inl], np.ones(len(inl))]
+    h2 = np.c_[xJ[inl], np.ones(len(inl))]
+    l = h1 @ F.T
+    d = np.abs((h2 * l).sum(1)) / np.hypot(l[:, 0], l[:, 1])
+    assert d.max() <= 4.0 + 1e-9 and np.median(d) < 1.5      # squared residual bound = Square(4.0) px^2
+    # F = K2^-T E K1^-1 has the two equal singular values of an essential matrix once the Ks are removed
+    Kmat = np.array([[f, 0, 960.0], [0, f, 540.0], [0, 0, 1]])
+    sv = np.linalg.svd(Kmat.T @ F @ Kmat)[1]
+    assert abs(sv[0] - sv[1]) < 1e-6 * sv[0] and sv[2] < 1e-6 * sv[0]
+    # deterministic
+    assert np.array_equal(inl, oracle.acransac_E(xI, xJ, 1920, 1080, 1920, 1080, K)[0])
+
+
+def test_filter_pairs_E_skips_views_without_intrinsics(oracle):
+    sc = synth.make_scene(3, 500, 32, "msurf", seed=9)
+    pairs = synth.exhaustive_pairs(3)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.8)
+    f = sc["f"]
+    Ks = np.array([[f, 960.0, 540.0], [f, 960.0, 540.0], [0.0, 0.0, 0.0]])
+    eo, em = oracle.filter_pairs_E(sc["xys"], sc["widths"], sc["heights"], Ks, pairs, ofs, m)
+    assert eo[1] - eo[0] > 5 * 2.5            # pair (0,1) kept
+    assert eo[2] == eo[1] and eo[3] == eo[2]  # pairs with view 2 dropped
