@@ -122,7 +122,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     uint64_t pt_total = 0, tbl_total = 0;
     for (uint64_t p = 0; p < P; ++p) {
       const uint32_t I = put->pairs[2 * p], J = put->pairs[2 * p + 1];
-      const uint32_t M = (uint32_t)(put->ofs[p + 1] - put->ofs[p]);
+      const uint32_t M = (uint32_t)put->per[p].size();
       if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
       if (I >= n_views || J >= n_views) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: view id outside views[]");
       // GeometricFilter_EMatrix_AC::Robust_estimation returns false without two valid pinhole intrinsics
@@ -176,7 +176,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     const float* xyI = vi.h_xy.data();
     const float* xyJ = vj.h_xy.data();
     for (uint32_t k = 0; k < M; ++k) {
-      const r3d_indmatch m = put->m[put->ofs[p] + k];
+      const r3d_indmatch m = put->per[p][k];
       if (m.i >= vi.n || m.j >= vj.n) { bad.store(1); return; }
       const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
       const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
@@ -414,7 +414,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     if (!(s.inliers.size() > sizeSample * 2.5)) continue;
     auto& out = result[s.src];
     out.reserve(s.inliers.size());
-    for (uint32_t idx : s.inliers) out.push_back(put->m[put->ofs[s.src] + idx]);
+    for (uint32_t idx : s.inliers) out.push_back(put->per[s.src][idx]);
   }
   T.ms_device_total = T.ms_solve + T.ms_score;
   T.ms_host = now_ms() - t_begin - T.ms_device_total;
@@ -436,14 +436,10 @@ extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, ui
   int rc = filter_pairs_model(ctx, ctx->workers[0], internal, precision_px, max_iter, putative, views, n_views, res);
   if (rc) return rc;
   r3d_matches* m = new r3d_matches();
-  m->ofs.push_back(0);
   const uint64_t P = putative->pairs.size() / 2;
   for (uint64_t p = 0; p < P; ++p) {
     if (res[p].empty()) continue;  // pairs whose estimation failed disappear from the map
-    m->pairs.push_back(putative->pairs[2 * p]);
-    m->pairs.push_back(putative->pairs[2 * p + 1]);
-    m->m.insert(m->m.end(), res[p].begin(), res[p].end());
-    m->ofs.push_back(m->m.size());
+    m->push(putative->pairs[2 * p], putative->pairs[2 * p + 1], std::move(res[p]));
   }
   *out = m;
   return R3D_OK;

@@ -321,7 +321,9 @@ __device__ __forceinline__ bool key_less(double ea, uint32_t ia, double eb, uint
 
 // Compact the residuals <= max_thr of model F into shared memory and sort them ascending by
 // (residual, index).  Returns the count c; se/si hold the sorted keys in [0, c).
-template <int MODEL>
+// WITH_INDEX = false (scoring): only the residual VALUES are sorted -- the NFA scan reads nothing else and
+// ties are indistinguishable there -- which halves the shared-memory traffic of the bitonic network.
+template <int MODEL, bool WITH_INDEX>
 __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict__ x1, const double2* __restrict__ x2,
                                      const double* Fm, double* se, uint32_t* si, uint32_t cap, uint32_t* s_count) {
   if (threadIdx.x == 0) *s_count = 0;
@@ -334,7 +336,10 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
                                   : epi_dist_error(Fm, a.x, a.y, b.x, b.y);
     if (e <= pr.max_thr) {  // false for NaN
       const uint32_t pos = atomicAdd(s_count, 1u);
-      if (pos < cap) { se[pos] = e; si[pos] = i; }
+      if (pos < cap) {
+        se[pos] = e;
+        if (WITH_INDEX) si[pos] = i;
+      }
     }
   }
   __syncthreads();
@@ -342,7 +347,10 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
   if (c > cap) c = cap;
   uint32_t p2 = 1;
   while (p2 < c) p2 <<= 1;
-  for (uint32_t i = c + threadIdx.x; i < p2; i += blockDim.x) { se[i] = DBL_MAX; si[i] = 0xffffffffu; }
+  for (uint32_t i = c + threadIdx.x; i < p2; i += blockDim.x) {
+    se[i] = DBL_MAX;
+    if (WITH_INDEX) si[i] = 0xffffffffu;
+  }
   __syncthreads();
   for (uint32_t size = 2; size <= p2; size <<= 1) {
     for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -351,9 +359,14 @@ __device__ uint32_t residuals_sorted(const AcPair& pr, const double2* __restrict
         const uint32_t hi = lo + stride;
         const bool up = ((lo & size) == 0);
         const double ea = se[lo], eb = se[hi];
-        const uint32_t ia = si[lo], ib = si[hi];
-        const bool swap = up ? key_less(eb, ib, ea, ia) : key_less(ea, ia, eb, ib);
-        if (swap) { se[lo] = eb; se[hi] = ea; si[lo] = ib; si[hi] = ia; }
+        if (WITH_INDEX) {
+          const uint32_t ia = si[lo], ib = si[hi];
+          const bool swap = up ? key_less(eb, ib, ea, ia) : key_less(ea, ia, eb, ib);
+          if (swap) { se[lo] = eb; se[hi] = ea; si[lo] = ib; si[hi] = ia; }
+        } else {
+          const bool swap = up ? (eb < ea) : (ea < eb);
+          if (swap) { se[lo] = eb; se[hi] = ea; }
+        }
       }
       __syncthreads();
     }
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(256) k_f7_score(const AcPair* __restrict__ pai
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
   for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)h * (9 * MAXM) + 9 * mi + t];
-  const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
+  const uint32_t c = residuals_sorted<MODEL, false>(pr, x1, x2, Fm, se, si, cap, &s_count);
   constexpr uint32_t NS = ac_min_samples(MODEL);      // Kernel::MINIMUM_SAMPLES
   const double mult_error = MODEL == 1 ? 1.0 : 0.5;   // point-to-point : point-to-line
   // bestNFA: k = sizeSample+1 .. c  (the upstream loop stops at the first residual > maxThreshold)
@@ -424,7 +437,7 @@ __global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ p
   uint32_t* si = (uint32_t*)(se + cap);
   double Fm[9];
   for (int t = 0; t < 9; ++t) Fm[t] = F[(size_t)rq.hyp_model * 9 + t];  // hyp_model = hypothesis * MAX_MODELS + model
-  const uint32_t c = residuals_sorted<MODEL>(pr, x1, x2, Fm, se, si, cap, &s_count);
+  const uint32_t c = residuals_sorted<MODEL, true>(pr, x1, x2, Fm, se, si, cap, &s_count);
   for (uint32_t i = threadIdx.x; i < rq.k && i < c; i += blockDim.x) out[rq.out_ofs + i] = si[i];
 }
 

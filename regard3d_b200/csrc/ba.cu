@@ -402,40 +402,48 @@ __global__ void k_ba_finish_S(Dev d, double inv_radius) {
 // ---- dense Cholesky + both triangular solves: ONE persistent cooperative kernel -------------------
 // A is (n+1) x n row-major: the reduced camera system S with its right-hand side as row n (the same
 // contiguous S|rhs block the all-reduce sums).  Right-looking blocked factorisation, NB = 32:
-//   per panel k   every CTA factors the 32x32 diagonal block redundantly in shared memory and forms its
-//                 inverse M = L_kk^-1 in the same 32-step loop (no grid sync between potrf and trsm);
-//                 the trailing tiles (i >= j) are dealt round-robin to the CTAs, each tile recomputes
-//                 X_i = A_ik M^T and X_j = A_jk M^T (32^3 MACs each) and applies A_ij -= X_i X_j^T;
-//                 L_ik goes to a SEPARATE matrix Lm, so A_ik stays readable by every CTA during the
-//                 step; one grid.sync() per panel.
+//   per panel k   potrf   every CTA factors the 32x32 diagonal block redundantly in shared memory and
+//                         forms its inverse M = L_kk^-1 in the same 32-step loop (one rsqrt per step)
+//                 trsm    row tile i (one per CTA): L_ik = A_ik M^T (32^3 MACs) -> Lm      | grid.sync
+//                 syrk    trailing tiles (i >= j), four per CTA at a time (256 threads each, 2x2
+//                         outputs per thread: one shared-memory operand read per DFMA instead of
+//                         three): A_ij -= L_ik L_jk^T                                        | grid.sync
+//                 L goes to a SEPARATE matrix Lm, the trailing matrix stays in A.
 //   rhs row       carrying b as row n makes the forward substitution L y = b part of the panel updates.
 //   backward      L^T x = y by CTA 0, right-looking with the stored inverses of the diagonal blocks.
 // One launch instead of 3 per panel + a single-thread triangular solve.
 constexpr int NB = 32;
+constexpr int kCholGroups = 4;  // syrk tiles in flight per CTA
+constexpr size_t kCholSmemBytes = (size_t)(2 + 2 * kCholGroups) * NB * (NB + 1) * sizeof(double) + NB * sizeof(double);
 __global__ void __launch_bounds__(1024, 1) k_chol_fused(double* A, double* Lm, double* Linv, int n, double* flag,
                                                         double* x_out) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double T[NB][NB + 1], M[NB][NB + 1], Ai[NB][NB + 1], Aj[NB][NB + 1];
-  __shared__ double xk[NB];
+  extern __shared__ __align__(16) double chol_smem[];
+  typedef double Tile[NB][NB + 1];
+  Tile& T = *(Tile*)(chol_smem);
+  Tile& M = *(Tile*)(chol_smem + NB * (NB + 1));
+  Tile* G = (Tile*)(chol_smem + 2 * NB * (NB + 1));  // G[2g], G[2g+1]: operand tiles of group g
+  double* xk = chol_smem + (size_t)(2 + 2 * kCholGroups) * NB * (NB + 1);
   const int r = threadIdx.y, c = threadIdx.x;
+  const int tid = r * NB + c;
   const int nblk = (n + NB - 1) / NB;
   for (int kbi = 0; kbi < nblk; ++kbi) {
     const int k0 = kbi * NB, kb = min(NB, n - k0);
-    // ---- diagonal block: L_kk and M = L_kk^-1 (rows/cols >= kb are identity padding) ----
+    // ---- potrf: L_kk and M = L_kk^-1 (rows/cols >= kb are identity padding) ----
     T[r][c] = (r < kb && c < kb) ? A[(size_t)(k0 + r) * n + k0 + c] : (r == c ? 1.0 : 0.0);
     M[r][c] = (r == c) ? 1.0 : 0.0;
     __syncthreads();
     for (int j = 0; j < kb; ++j) {
       const double piv = T[j][j];
       const bool bad = !(piv > 0.0);
-      const double sq = bad ? 1.0 : sqrt(piv);
-      const double lrj = T[r][j] / sq, lcj = T[c][j] / sq, mjc = M[j][c] / sq;
+      const double rs = bad ? 1.0 : rsqrt(piv);
+      const double lrj = T[r][j] * rs, lcj = T[c][j] * rs, mjc = M[j][c] * rs;
       const double trc = T[r][c], mrc = M[r][c];
       __syncthreads();
-      if (bad && r == 0 && c == 0 && blockIdx.x == 0) *flag = 1.0;
+      if (bad && tid == 0 && blockIdx.x == 0) *flag = 1.0;
       if (r == j) {
         M[j][c] = mjc;
-        if (c == j) T[j][j] = sq;
+        if (c == j) T[j][j] = bad ? 1.0 : piv * rs;
       } else if (r > j) {
         M[r][c] = mrc - lrj * mjc;
         if (c == j) T[r][j] = lrj;
@@ -447,43 +455,64 @@ __global__ void __launch_bounds__(1024, 1) k_chol_fused(double* A, double* Lm, d
       if (r < kb && c <= r && c < kb) Lm[(size_t)(k0 + r) * n + k0 + c] = T[r][c];
       Linv[(size_t)kbi * NB * NB + r * NB + c] = (c <= r) ? M[r][c] : 0.0;
     }
-    // ---- trailing tiles; rows run to n inclusive (the rhs row), columns to n - 1 ----
+    // ---- trsm: rows r0 .. n (n = the rhs row), one 32-row tile per CTA ----
     const int r0 = k0 + kb;
     const int tiles_i = (n + 1 - r0 + NB - 1) / NB;
-    const int ntiles = tiles_i * (tiles_i + 1) / 2;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      int ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      while (ti * (ti + 1) / 2 > t) --ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      const int ri = r0 + ti * NB + r, rj = r0 + tj * NB + r;  // rows staged by this thread (panel column k0 + c)
-      __syncthreads();                                         // previous tile's readers are done
-      Ai[r][c] = (ri <= n && c < kb) ? A[(size_t)ri * n + k0 + c] : 0.0;
-      Aj[r][c] = (rj <= n && c < kb) ? A[(size_t)rj * n + k0 + c] : 0.0;
+    for (int ti = blockIdx.x; ti < tiles_i; ti += gridDim.x) {
+      const int ri = r0 + ti * NB + r;
       __syncthreads();
-      double xi = 0.0, xj = 0.0;
-      for (int tt = 0; tt < NB; ++tt) {  // X = A_panel * M^T ; M is lower triangular
-        const double m = M[c][tt];
-        xi += Ai[r][tt] * m;
-        xj += Aj[r][tt] * m;
-      }
+      G[0][r][c] = (ri <= n && c < kb) ? A[(size_t)ri * n + k0 + c] : 0.0;
       __syncthreads();
-      Ai[r][c] = xi;
-      Aj[r][c] = xj;
-      if (tj == 0 && ri <= n && c < kb) Lm[(size_t)ri * n + k0 + c] = xi;  // L_ik (row n: y_k)
-      __syncthreads();
-      const int row = r0 + ti * NB + r, col = r0 + tj * NB + c;
-      if (row <= n && col < n && col <= row) {
-        double sacc = 0.0;
-        for (int tt = 0; tt < NB; ++tt) sacc += Ai[r][tt] * Aj[c][tt];
-        A[(size_t)row * n + col] -= sacc;
+      double x = 0.0;
+      for (int tt = 0; tt < NB; ++tt) x += G[0][r][tt] * M[c][tt];  // X = A_panel * M^T
+      if (ri <= n && c < kb) Lm[(size_t)ri * n + k0 + c] = x;      // L_ik (row n: y_k)
+    }
+    grid.sync();
+    // ---- syrk: A_ij -= L_ik L_jk^T over the trailing tiles; group g = 256 threads works on its own tile ----
+    {
+      const int g = tid >> 8, gt = tid & 255;
+      const int tr = gt >> 4, tc = gt & 15;
+      Tile& Xi = G[2 * g];
+      Tile& Xj = G[2 * g + 1];
+      const int ntiles = tiles_i * (tiles_i + 1) / 2;
+      const int stride = gridDim.x * kCholGroups;
+      for (int t0 = blockIdx.x * kCholGroups; t0 < ntiles; t0 += stride) {
+        const int t = t0 + g;
+        int ti = 0, tj = 0;
+        if (t < ntiles) {
+          ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+          while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+          while (ti * (ti + 1) / 2 > t) --ti;
+          tj = t - ti * (ti + 1) / 2;
+        }
+        __syncthreads();  // the previous round's readers are done
+        if (t < ntiles) {
+          for (int e = gt; e < NB * NB; e += 256) {
+            const int rr = e >> 5, cc = e & 31;
+            const int ri = r0 + ti * NB + rr, rj = r0 + tj * NB + rr;
+            Xi[rr][cc] = (ri <= n && cc < kb) ? Lm[(size_t)ri * n + k0 + cc] : 0.0;
+            Xj[rr][cc] = (rj <= n && cc < kb) ? Lm[(size_t)rj * n + k0 + cc] : 0.0;
+          }
+        }
+        __syncthreads();
+        if (t < ntiles) {
+          double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+          for (int tt = 0; tt < NB; ++tt) {
+            const double a0 = Xi[tr][tt], a1 = Xi[tr + 16][tt], b0 = Xj[tc][tt], b1 = Xj[tc + 16][tt];
+            s00 += a0 * b0; s01 += a0 * b1; s10 += a1 * b0; s11 += a1 * b1;
+          }
+          const int row0 = r0 + ti * NB + tr, col0 = r0 + tj * NB + tc;
+          if (row0 <= n && col0 < n && col0 <= row0) A[(size_t)row0 * n + col0] -= s00;
+          if (row0 <= n && col0 + 16 < n && col0 + 16 <= row0) A[(size_t)row0 * n + col0 + 16] -= s01;
+          if (row0 + 16 <= n && col0 < n && col0 <= row0 + 16) A[(size_t)(row0 + 16) * n + col0] -= s10;
+          if (row0 + 16 <= n && col0 + 16 < n && col0 + 16 <= row0 + 16) A[(size_t)(row0 + 16) * n + col0 + 16] -= s11;
+        }
       }
     }
     grid.sync();
   }
   if (blockIdx.x != 0) return;
   // ---- backward substitution L^T x = y (y = row n of Lm) ----
-  const int tid = r * NB + c;
   for (int j = tid; j < n; j += NB * NB) x_out[j] = Lm[(size_t)n * n + j];
   __syncthreads();
   for (int kbi = nblk - 1; kbi >= 0; --kbi) {
@@ -714,7 +743,8 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   int chol_grid = w.sm_count;  // persistent: one CTA per SM, all co-resident (cooperative launch)
   {
     int per_sm = 0;
-    R3D_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, r3d::ba::k_chol_fused, 1024, 0));
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_chol_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r3d::ba::kCholSmemBytes));
+    R3D_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, r3d::ba::k_chol_fused, 1024, r3d::ba::kCholSmemBytes));
     if (per_sm < 1) return fail(ctx, R3D_ERR_CUDA, "bundle adjustment: k_chol_fused does not fit on an SM");
   }
   double h_scal[8];
@@ -784,7 +814,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
       double *pA = d.S, *pL = d_Lm, *pI = d_Linv, *pflag = d.scal + 4, *px = d.delta;
       int pn = nB;
       void* cargs[] = {&pA, &pL, &pI, &pn, &pflag, &px};
-      R3D_CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void*)r3d::ba::k_chol_fused, dim3(chol_grid), dim3(32, 32), cargs, 0, w.stream));
+      R3D_CUDA_TRY(ctx, cudaLaunchCooperativeKernel((void*)r3d::ba::k_chol_fused, dim3(chol_grid), dim3(32, 32), cargs, r3d::ba::kCholSmemBytes, w.stream));
     }
     r3d::ba::k_ba_backsub<<<(d.n_pts + 127) / 128, 128, 0, w.stream>>>(d);
     r3d::ba::k_ba_update<<<w.sm_count * 4, 256, 0, w.stream>>>(d, inv_radius);

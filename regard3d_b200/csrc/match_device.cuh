@@ -53,14 +53,14 @@ __device__ __forceinline__ float exact_l2(const void* __restrict__ qrow, const v
       const uint32_t* d4 = (const uint32_t*)d;
       const uint32_t g = dim >> 2;
 #pragma unroll 4
+      // integer form: all partial sums of the upstream float accumulation are integers < 2^24 (dim <= 240),
+      // so the float result equals the exact integer sum of squared byte differences
+      uint32_t isum = 0u;
       for (uint32_t t = 0; t < g; ++t) {
-        const uint32_t a = q4[t], b = __ldg(d4 + t);
-        const float d0 = (float)((int)(a & 255u) - (int)(b & 255u));
-        const float d1 = (float)((int)((a >> 8) & 255u) - (int)((b >> 8) & 255u));
-        const float d2 = (float)((int)((a >> 16) & 255u) - (int)((b >> 16) & 255u));
-        const float d3 = (float)((int)(a >> 24) - (int)(b >> 24));
-        acc = acc4(acc, d0, d1, d2, d3);
+        const uint32_t ad = __vabsdiffu4(q4[t], __ldg(d4 + t));
+        isum = __dp4a(ad, ad, isum);
       }
+      acc = (float)isum;
       k = dim;
     } else {
       for (; k + 3 < dim; k += 4)
@@ -112,14 +112,14 @@ __device__ __forceinline__ float exact_l2_generic(const void* __restrict__ qrow,
       const uint32_t* d4 = (const uint32_t*)d;
       const uint32_t g = dim >> 2;
 #pragma unroll 4
+      // integer form: all partial sums of the upstream float accumulation are integers < 2^24 (dim <= 240),
+      // so the float result equals the exact integer sum of squared byte differences
+      uint32_t isum = 0u;
       for (uint32_t t = 0; t < g; ++t) {
-        const uint32_t a = q4[t], b = d4[t];
-        const float d0 = (float)((int)(a & 255u) - (int)(b & 255u));
-        const float d1 = (float)((int)((a >> 8) & 255u) - (int)((b >> 8) & 255u));
-        const float d2 = (float)((int)((a >> 16) & 255u) - (int)((b >> 16) & 255u));
-        const float d3 = (float)((int)(a >> 24) - (int)(b >> 24));
-        acc = acc4(acc, d0, d1, d2, d3);
+        const uint32_t ad = __vabsdiffu4(q4[t], d4[t]);
+        isum = __dp4a(ad, ad, isum);
       }
+      acc = (float)isum;
       k = dim;
     } else {
       for (; k + 3 < dim; k += 4)
@@ -188,14 +188,19 @@ __device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, d
   return lb;
 }
 
+// A query that passes the ratio test appends IndMatch(i in I, j = q in J) to ITS PAIR's segment of the
+// dense match array (segment = the pair's query rows, so it can never overflow); the per-pair counters
+// live behind the 16 scalar counters.  k_pack_matches then packs the segments for the host copy: the
+// matches arrive on the host already bucketed by pair.
+constexpr uint32_t kPairCounterBase = 16;
 __device__ __forceinline__ void emit_result(const PairDesc& pd, uint32_t pair, uint32_t q, const Top2& t,
-                                            float ratio2, uint32_t* counters, uint3* matches, float4* nn) {
+                                            float ratio2, uint32_t* counters, uint2* matches, float4* nn) {
   if (nn) {
     nn[pd.q_ofs + q] = make_float4(__uint_as_float(t.i1), __uint_as_float(t.i2), t.d1, t.d2);
   }
   if (matches && t.d1 < __fmul_rn(ratio2, t.d2)) {  // NNdistanceRatio: strict, float
-    const uint32_t slot = atomicAdd(&counters[0], 1u);
-    matches[slot] = make_uint3(pair, t.i1, q);
+    const uint32_t slot = atomicAdd(&counters[kPairCounterBase + pair], 1u);
+    matches[pd.q_ofs + slot] = make_uint2(t.i1, q);
   }
 }
 

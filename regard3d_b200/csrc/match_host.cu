@@ -116,8 +116,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   for (int sl = 0; sl < 2; ++sl) {
     OutSlot& o = w.out[sl];
     if (!o.d_counters) {
-      R3D_CUDA_TRY(ctx, cudaMalloc(&o.d_counters, 16 * sizeof(uint32_t)));
-      R3D_CUDA_TRY(ctx, cudaMallocHost(&o.h_counters, 16 * sizeof(uint32_t)));
+      R3D_CUDA_TRY(ctx, cudaMalloc(&o.d_counters, kCounterWords * sizeof(uint32_t)));
+      R3D_CUDA_TRY(ctx, cudaMallocHost(&o.h_counters, kCounterWords * sizeof(uint32_t)));
       for (auto& e : o.ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
     }
   }
@@ -130,7 +130,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   static const uint32_t kBatchPairs = []() {
     const char* e = getenv("R3D_BATCH_PAIRS");
     const int v = e ? atoi(e) : 0;
-    return (uint32_t)(v > 0 ? v : 128);
+    return (uint32_t)std::min<int>(v > 0 ? v : 128, (int)kCounterWords - 16);
   }();
   const uint64_t kMaxRowsPerBatch = 24ull << 20;  // 24 Mi query rows -> 768 MiB of keys
   std::vector<std::thread> tails;
@@ -205,7 +205,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       if ((rc = ensure_capacity<uint2>(ctx, &w.d_list2, &w.list2_cap, qtotal))) return rc;
     }
     if (want_matches) {
-      if ((rc = ensure_capacity<uint3>(ctx, &o.d_matches, &o.matches_cap, qtotal))) return rc;
+      if ((rc = ensure_capacity<uint2>(ctx, &o.d_matches, &o.matches_cap, qtotal))) return rc;
+      if ((rc = ensure_capacity<uint2>(ctx, &w.d_mdense, &w.mdense_cap, rows))) return rc;
     } else {
       if ((rc = ensure_capacity<float4>(ctx, &w.d_nn, &w.nn_cap, rows))) return rc;
     }
@@ -213,10 +214,10 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp->data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
     if (any_tc)
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems->data(), hitems->size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
-    R3D_CUDA_TRY(ctx, cudaMemsetAsync(o.d_counters, 0, 16 * sizeof(uint32_t), w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemsetAsync(o.d_counters, 0, (16 + nb) * sizeof(uint32_t), w.stream));
     uint64_t launches = 0;
 
-    uint3* d_matches = want_matches ? (uint3*)o.d_matches : nullptr;
+    uint2* d_matches = want_matches ? (uint2*)w.d_mdense : nullptr;  // per-pair segments; packed into o.d_matches below
     float4* d_nn = want_matches ? nullptr : (float4*)w.d_nn;
 
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[0], w.stream));
@@ -256,8 +257,13 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
                                 (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, o.d_counters,
                                 d_matches, d_nn))) return rc;
     launches += 1;
+    if (want_matches) {
+      if ((rc = launch_pack_matches(ctx, w, (const PairDesc*)w.d_pairs, nb, o.d_counters + 16, (const uint2*)w.d_mdense,
+                                    (uint2*)o.d_matches))) return rc;
+      launches += 1;
+    }
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[3], w.stream));
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(o.h_counters, o.d_counters, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(o.h_counters, o.d_counters, (16 + nb) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[4], w.stream));
 
     if (!want_matches) {  // r3d_search_neighbours / diagnostics: synchronous, single batch
@@ -298,9 +304,12 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       cudaEventElapsedTime(&ms_r, os.ev[1], os.ev[2]);
       cudaEventElapsedTime(&ms_f, os.ev[2], os.ev[3]);
       cudaEventElapsedTime(&ms_t, os.ev[0], os.ev[3]);
-      const uint32_t n_matches = os.h_counters[0];
+      // the matches arrive bucketed by pair: cnt = prefix sums of the per-pair counters
+      std::vector<uint32_t> cnt(nb + 1, 0u);
+      for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] = cnt[k] + os.h_counters[16 + k];
+      const uint32_t n_matches = cnt[nb];
       const uint32_t c_fb = os.h_counters[1], c_b = os.h_counters[4], c_c = os.h_counters[3];
-      size_t bytes = (size_t)n_matches * sizeof(uint3);
+      size_t bytes = (size_t)n_matches * sizeof(uint2);
       if (n_matches) {
         if (os.h_matches_cap < bytes) {
           if (os.h_matches) cudaFreeHost(os.h_matches);
@@ -315,16 +324,9 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         if (e != cudaSuccess) return bail("match copy", e);
       }
       const double t0 = now_ms();
-      // bucket by pair (counting sort) out of the pinned buffer
-      const uint3* hm = (const uint3*)os.h_matches;
-      std::vector<uint32_t> cnt(nb + 1, 0u);
-      for (uint32_t k = 0; k < n_matches; ++k) cnt[hm[k].x + 1]++;
-      for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] += cnt[k];
+      // out of the pinned buffer (uint2 (i, j) == r3d_indmatch), so that the slot can be handed to batch b+2
       std::vector<r3d_indmatch> bucket(n_matches);
-      {
-        std::vector<uint32_t> pos(cnt.begin(), cnt.end() - 1);
-        for (uint32_t k = 0; k < n_matches; ++k) bucket[pos[hm[k].x]++] = r3d_indmatch{hm[k].y, hm[k].z};
-      }
+      if (n_matches) std::memcpy(bucket.data(), os.h_matches, bytes);
       release();  // the slot's device + pinned buffers may be reused by batch b+2
       parallel_for(nthreads, nb, [&](size_t k) {
         if (cnt[k + 1] == cnt[k]) return;
@@ -343,7 +345,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       T.fallback_queries += c_fb;
       T.third_chunk_queries += c_b;
       T.fifth_chunk_queries += c_c;
-      T.d2h_bytes += 16 * sizeof(uint32_t) + bytes;
+      T.d2h_bytes += (16 + nb) * sizeof(uint32_t) + bytes;
       T.h2d_bytes += h2d_batch;
     });
     b0 = b1;
@@ -439,26 +441,11 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
     return a.I < b.I || (a.I == b.I && a.J < b.J);
   });
   r3d_matches* m = new r3d_matches();
-  {
-    std::vector<size_t> keep;
-    keep.reserve(entries.size());
-    for (size_t e = 0; e < entries.size(); ++e) {
-      if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
-      keep.push_back(e);
-    }
-    m->pairs.resize(2 * keep.size());
-    m->ofs.resize(keep.size() + 1);
-    m->ofs[0] = 0;
-    for (size_t k = 0; k < keep.size(); ++k) {
-      m->pairs[2 * k] = entries[keep[k]].I;
-      m->pairs[2 * k + 1] = entries[keep[k]].J;
-      m->ofs[k + 1] = m->ofs[k] + entries[keep[k]].v->size();
-    }
-    m->m.resize(m->ofs.back());
-    parallel_for(ctx->host_threads, keep.size(), [&](size_t k) {
-      const auto& v = *entries[keep[k]].v;
-      std::memcpy(m->m.data() + m->ofs[k], v.data(), v.size() * sizeof(r3d_indmatch));
-    });
+  m->pairs.reserve(2 * entries.size());
+  m->per.reserve(entries.size());
+  for (size_t e = 0; e < entries.size(); ++e) {
+    if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
+    m->push(entries[e].I, entries[e].J, std::move(*entries[e].v));
   }
   if (getenv("R3D_DEBUG_TIMING"))
     fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms (assembly %.2f ms)\n", now_ms() - t_call, now_ms() - t_assemble);

@@ -23,7 +23,7 @@ template <int DTYPE>
 __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pairs,
                                                 const uint32_t* __restrict__ keys, const PartB* __restrict__ parts,
                                                 const uint2* __restrict__ list, const uint32_t* __restrict__ list_count,
-                                                uint32_t dim, float ratio2, uint32_t* counters, uint3* matches,
+                                                uint32_t dim, float ratio2, uint32_t* counters, uint2* matches,
                                                 uint2* fallback, float4* nn) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_list = *list_count;
@@ -79,7 +79,7 @@ template <int DTYPE>
 __global__ void __launch_bounds__(256) k_exact_scan(const PairDesc* __restrict__ pairs,
                                                     const uint2* __restrict__ list,
                                                     const uint32_t* __restrict__ list_count, uint32_t dim,
-                                                    float ratio2, uint32_t* counters, uint3* matches,
+                                                    float ratio2, uint32_t* counters, uint2* matches,
                                                     float4* nn) {
   extern __shared__ __align__(16) unsigned char smem_q[];
   __shared__ Top2 warp_best[8];
@@ -246,7 +246,7 @@ int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0) {
 
 int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys, const void* d_parts,
                        const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
-                       float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn) {
+                       float ratio2, uint32_t* d_counters, uint2* d_matches, uint2* d_fallback, float4* d_nn) {
   if (max_list == 0) return R3D_OK;
   const int wpb = 8;
   uint32_t grid = (max_list + wpb - 1) / wpb;
@@ -261,9 +261,41 @@ int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, c
   return R3D_OK;
 }
 
+// ---- pack the per-pair match segments for the host copy ----------------------------------------------
+// one block per pair: offset = sum of the counts of the pairs before it (<= a few thousand values), then
+// a coalesced copy of the pair's segment.  Order inside a pair is irrelevant: the host sorts by (i, j)
+// (IndMatch::getDeduplicated) before the order-dependent coordinate de-duplication.
+__global__ void __launch_bounds__(256) k_pack_matches(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ pair_cnt,
+                                                      const uint2* __restrict__ dense, uint2* __restrict__ packed) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_ofs;
+  const uint32_t p = blockIdx.x;
+  uint32_t acc = 0;
+  for (uint32_t k = threadIdx.x; k < p; k += blockDim.x) acc += pair_cnt[k];
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31u) == 0) s_part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    s_ofs = t;
+  }
+  __syncthreads();
+  const uint32_t n = pair_cnt[p], src = pairs[p].q_ofs, dst = s_ofs;
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) packed[dst + k] = dense[src + k];
+}
+
+int launch_pack_matches(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, const uint32_t* d_pair_cnt,
+                        const uint2* d_dense, uint2* d_packed) {
+  if (!n_pairs) return R3D_OK;
+  k_pack_matches<<<n_pairs, 256, 0, w.stream>>>(d_pairs, d_pair_cnt, d_dense, d_packed);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
 int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
                       const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype, float ratio2,
-                      uint32_t* d_counters, uint3* d_matches, float4* d_nn) {
+                      uint32_t* d_counters, uint2* d_matches, float4* d_nn) {
   if (max_list == 0) return R3D_OK;
   const uint32_t grid = max_list < (uint32_t)(w.sm_count * 8) ? max_list : (uint32_t)(w.sm_count * 8);
   const size_t smem = (dtype == 0 ? (size_t)dim * 4 : (size_t)dim) + 16;

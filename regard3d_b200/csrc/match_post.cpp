@@ -4,8 +4,11 @@
 //   IndMatchDecorator<float>::getDeduplicated -> std::set with the upstream comparator
 // The second step's comparator is not a strict weak ordering, so its result is defined only by
 // the std::set range-insertion algorithm; it therefore runs on the host with the very container
-// the reference uses.  O(#matches) per pair.
+// the reference uses.  The set's nodes come from a per-thread monotonic arena
+// (std::pmr): the allocator does not take part in the tree algorithm, so the result is the one of
+// std::set<.., std::allocator>, without a malloc/free per match.  O(#matches log #matches) per pair.
 #include <algorithm>
+#include <memory_resource>
 #include <set>
 #include <vector>
 
@@ -48,9 +51,15 @@ void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const flo
     dec[k].y2 = xyJ[2 * (size_t)m[k].j + 1];
     dec[k].im = m[k];
   }
-  std::set<XYMatch, XYLess> uniq(dec.begin(), dec.end());
-  m.clear();
-  for (const auto& d : uniq) m.push_back(d.im);
+  thread_local std::vector<unsigned char> arena_buf;
+  const size_t need = dec.size() * (sizeof(XYMatch) + 48) + 1024;  // red-black node = 32-byte header + payload
+  if (arena_buf.size() < need) arena_buf.resize(need + need / 2);
+  std::pmr::monotonic_buffer_resource arena(arena_buf.data(), arena_buf.size());
+  {
+    std::pmr::set<XYMatch, XYLess> uniq(dec.begin(), dec.end(), XYLess(), &arena);
+    m.clear();
+    for (const auto& d : uniq) m.push_back(d.im);
+  }
 }
 
 }  // namespace r3d

@@ -14,15 +14,15 @@
 extern "C" {
 
 uint64_t r3d_matches_num_pairs(const r3d_matches* m) { return m ? m->pairs.size() / 2 : 0; }
-uint64_t r3d_matches_total(const r3d_matches* m) { return m ? m->m.size() : 0; }
+uint64_t r3d_matches_total(const r3d_matches* m) { return m ? m->total : 0; }
 
 int r3d_matches_get_pair(const r3d_matches* m, uint64_t k, uint32_t* I, uint32_t* J, const r3d_indmatch** matches,
                          uint64_t* count) {
   if (!m || k >= m->pairs.size() / 2) return R3D_ERR_INVALID;
   if (I) *I = m->pairs[2 * k];
   if (J) *J = m->pairs[2 * k + 1];
-  if (matches) *matches = m->m.data() + m->ofs[k];
-  if (count) *count = m->ofs[k + 1] - m->ofs[k];
+  if (matches) *matches = m->per[k].data();
+  if (count) *count = m->per[k].size();
   return R3D_OK;
 }
 
@@ -35,15 +35,11 @@ int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t
     return pairs[2 * a] < pairs[2 * b] || (pairs[2 * a] == pairs[2 * b] && pairs[2 * a + 1] < pairs[2 * b + 1]);
   });
   r3d_matches* m = new r3d_matches();
-  m->ofs.push_back(0);
   for (uint64_t t = 0; t < n_pairs; ++t) {
     const uint64_t p = order[t];
     if (pair_ofs[p + 1] == pair_ofs[p]) continue;  // empty pairs are never in the map
     if (!m->pairs.empty() && m->pairs[m->pairs.size() - 2] == pairs[2 * p] && m->pairs.back() == pairs[2 * p + 1]) continue;
-    m->pairs.push_back(pairs[2 * p]);
-    m->pairs.push_back(pairs[2 * p + 1]);
-    m->m.insert(m->m.end(), matches + pair_ofs[p], matches + pair_ofs[p + 1]);
-    m->ofs.push_back(m->m.size());
+    m->push(pairs[2 * p], pairs[2 * p + 1], std::vector<r3d_indmatch>(matches + pair_ofs[p], matches + pair_ofs[p + 1]));
   }
   *out = m;
   return R3D_OK;
@@ -57,8 +53,8 @@ int r3d_save_matches_txt(const r3d_matches* m, const char* path) {
   if (!stream.is_open()) return R3D_ERR_IO;
   const uint64_t P = m->pairs.size() / 2;
   for (uint64_t k = 0; k < P; ++k) {
-    stream << m->pairs[2 * k] << " " << m->pairs[2 * k + 1] << '\n' << (m->ofs[k + 1] - m->ofs[k]) << '\n';
-    for (uint64_t t = m->ofs[k]; t < m->ofs[k + 1]; ++t) stream << m->m[t].i << " " << m->m[t].j << "\n";
+    stream << m->pairs[2 * k] << " " << m->pairs[2 * k + 1] << '\n' << m->per[k].size() << '\n';
+    for (const r3d_indmatch& im : m->per[k]) stream << im.i << " " << im.j << "\n";
   }
   return stream.good() ? R3D_OK : R3D_ERR_IO;
 }
@@ -77,13 +73,8 @@ int r3d_load_matches_txt(const char* path, r3d_matches** out) {
     mp[{I, J}] = std::move(v);
   }
   r3d_matches* m = new r3d_matches();
-  m->ofs.push_back(0);
-  for (auto& kv : mp) {
-    m->pairs.push_back(kv.first.first);
-    m->pairs.push_back(kv.first.second);
-    m->m.insert(m->m.end(), kv.second.begin(), kv.second.end());
-    m->ofs.push_back(m->m.size());
-  }
+  for (auto& kv : mp)
+    m->push(kv.first.first, kv.first.second, std::move(kv.second));  // matching::Load keeps what the file lists
   *out = m;
   return R3D_OK;
 }

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -73,9 +74,10 @@ static_assert(sizeof(PairDesc) == 64, "PairDesc layout");
 
 struct WorkItem { uint32_t pair; uint32_t sb; };  // sb: super-block (256 query rows) index
 
+constexpr uint32_t kCounterWords = 16 + 4096;  // 16 scalar counters + one match counter per pair of the batch
 struct OutSlot {  // double-buffered outputs of a matching batch
-  void* d_matches = nullptr; size_t matches_cap = 0;
-  uint32_t* d_counters = nullptr;  // [0] matches, [1] exact-scan list, [3] stage C, [4] deferred by stage A
+  void* d_matches = nullptr; size_t matches_cap = 0;  // packed (i, j) of the batch, bucketed by pair
+  uint32_t* d_counters = nullptr;  // [1] exact-scan list, [3] stage C, [4] deferred by stage A, [16 + k] matches of pair k
   uint32_t* h_counters = nullptr;  // pinned
   void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -111,6 +113,7 @@ struct DeviceWorker {
   void* d_list = nullptr; size_t list_cap = 0;
   void* d_parts = nullptr; size_t parts_cap = 0;
   void* d_list2 = nullptr; size_t list2_cap = 0;
+  void* d_mdense = nullptr; size_t mdense_cap = 0;  // (i, j) per pair segment, before packing
   r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
 };
 
@@ -165,7 +168,9 @@ int prepare_views(r3d_ctx* ctx, DeviceWorker& w);
 void* pool_alloc(DeviceWorker& w, size_t bytes);  // nullptr on failure
 void pool_release(DeviceWorker& w, void* p);
 
-// dynamic-scheduling parallel loop on std::thread (host post-processing, RANSAC state machines)
+// dynamic-scheduling parallel loop on the persistent host pool (host_pool.cpp); n_threads bounds the
+// concurrency of THIS loop (the caller counts as one)
+void pool_parallel_for(int n_threads, size_t n, const std::function<void(size_t)>& f);
 template <typename F>
 inline void parallel_for(int n_threads, size_t n, F&& f) {
   if (n == 0) return;
@@ -173,18 +178,8 @@ inline void parallel_for(int n_threads, size_t n, F&& f) {
     for (size_t i = 0; i < n; ++i) f(i);
     return;
   }
-  std::atomic<size_t> next{0};
-  std::vector<std::thread> th;
-  const int nt = (int)std::min<size_t>((size_t)n_threads, n);
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([&]() {
-      for (;;) {
-        const size_t i = next.fetch_add(1);
-        if (i >= n) break;
-        f(i);
-      }
-    });
-  for (auto& t : th) t.join();
+  const std::function<void(size_t)> fn = [&f](size_t i) { f(i); };
+  pool_parallel_for(n_threads, n, fn);
 }
 
 // ---- kernels (defined in the .cu files) --------------------------------------------------------
@@ -201,16 +196,18 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
 // exact re-rank + ratio
 int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint32_t* d_keys, const void* d_parts,
                        const uint2* d_list, const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
-                       float ratio2, uint32_t* d_counters, uint3* d_matches, uint2* d_fallback, float4* d_nn);
+                       float ratio2, uint32_t* d_counters, uint2* d_matches, uint2* d_fallback, float4* d_nn);
 // binned stage A (rerank_binned.cu); cstride = max chunks per pair + 1
 int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
                          uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
                          uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
-                         uint3* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn);
+                         uint2* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn);
 // exact scan of listed queries
+int launch_pack_matches(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, const uint32_t* d_pair_cnt,
+                        const uint2* d_dense, uint2* d_packed);
 int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const uint2* d_list,
                       const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype,
-                      float ratio2, uint32_t* d_counters, uint3* d_matches, float4* d_nn);
+                      float ratio2, uint32_t* d_counters, uint2* d_matches, float4* d_nn);
 int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs,
                             uint2* d_list, uint32_t* d_list_count);
 

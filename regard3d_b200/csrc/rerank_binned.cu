@@ -139,6 +139,18 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
     }
   }
   __syncwarp();
+  uint32_t row_norm[kChunk];  // uint8 only: |a_r|^2 of the staged rows (every lane computes all kChunk of them)
+  if (DTYPE != 0) {
+#pragma unroll
+    for (int r = 0; r < kChunk; ++r) {
+      uint32_t s = 0u;
+      for (uint32_t g = 0; g < (dim >> 2); ++g) {
+        const uint32_t a = *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4);
+        s = __dp4a(a, a, s);
+      }
+      row_norm[r] = s;
+    }
+  }
   const uint32_t* l = list + (size_t)pd.q_ofs * 2;
   const uint32_t col0 = chunk * kChunk;
   const uint32_t nvalid = (pd.nI > col0) ? min((uint32_t)kChunk, pd.nI - col0) : 0u;
@@ -177,18 +189,38 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
         }
       }
     } else {
-      const uint32_t groups = dim >> 2;  // rb % 4 == 0 is guaranteed by the launcher
-      for (uint32_t g = 0; g < groups; ++g) {
-        const uint32_t qv = __ldg((const uint32_t*)qrow + g);
+      // uint8 descriptors: every partial sum of the upstream float accumulation is an integer below 2^24
+      // (dim <= 240: 240 * 255^2 < 2^24), so the float result IS the integer sum -- computed here as
+      // |q|^2 + |a|^2 - 2 q.a with one IDP4A per 4 dimensions and row instead of 4 x (I2F, FSUB, FMUL, FADD)
+      uint32_t dot[kChunk];
 #pragma unroll
-        for (int r = 0; r < kChunk; ++r) {
-          const uint32_t a = *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4);
-          acc[r] = acc4(acc[r], (float)((int)(qv & 255u) - (int)(a & 255u)),
-                        (float)((int)((qv >> 8) & 255u) - (int)((a >> 8) & 255u)),
-                        (float)((int)((qv >> 16) & 255u) - (int)((a >> 16) & 255u)),
-                        (float)((int)(qv >> 24) - (int)(a >> 24)));
+      for (int r = 0; r < kChunk; ++r) dot[r] = 0u;
+      uint32_t qn = 0u;
+      if ((rb & 15u) == 0) {
+        const uint32_t g16 = (uint32_t)(rb >> 4);
+        for (uint32_t g = 0; g < g16; ++g) {
+          const uint4 qv = __ldg((const uint4*)qrow + g);
+          qn = __dp4a(qv.x, qv.x, qn); qn = __dp4a(qv.y, qv.y, qn); qn = __dp4a(qv.z, qv.z, qn); qn = __dp4a(qv.w, qv.w, qn);
+#pragma unroll
+          for (int r = 0; r < kChunk; ++r) {
+            const uint4 a = *(const uint4*)(rows + (size_t)r * row_stride + (size_t)g * 16);  // broadcast
+            uint32_t d = dot[r];
+            d = __dp4a(qv.x, a.x, d); d = __dp4a(qv.y, a.y, d); d = __dp4a(qv.z, a.z, d); d = __dp4a(qv.w, a.w, d);
+            dot[r] = d;
+          }
+        }
+      } else {
+        const uint32_t groups = dim >> 2;  // rb % 4 == 0 is guaranteed by the launcher
+        for (uint32_t g = 0; g < groups; ++g) {
+          const uint32_t qv = __ldg((const uint32_t*)qrow + g);
+          qn = __dp4a(qv, qv, qn);
+#pragma unroll
+          for (int r = 0; r < kChunk; ++r)
+            dot[r] = __dp4a(qv, *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4), dot[r]);
         }
       }
+#pragma unroll
+      for (int r = 0; r < kChunk; ++r) acc[r] = (float)(qn + row_norm[r] - 2u * dot[r]);
     }
     Top2 t;
     t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
 
 __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ pairs,
                                                    const uint32_t* __restrict__ keys, const Part* __restrict__ parts,
-                                                   uint32_t dim, float ratio2, uint32_t* counters, uint3* matches,
+                                                   uint32_t dim, float ratio2, uint32_t* counters, uint2* matches,
                                                    uint2* list2, uint2* fallback, float4* nn) {
   const uint32_t pair = blockIdx.y;
   const PairDesc pd = pairs[pair];
@@ -245,7 +277,7 @@ __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ 
 int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, uint32_t max_nJ,
                          uint32_t cstride, const uint32_t* d_keys, uint32_t dim, int dtype, float ratio2,
                          uint32_t* d_cnt, uint32_t* d_slot, uint32_t* d_list, void* d_parts, uint32_t* d_counters,
-                         uint3* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn) {
+                         uint2* d_matches, uint2* d_list2, uint2* d_fallback, float4* d_nn) {
   if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
   const size_t rb = dtype == 0 ? (size_t)dim * 4 : (size_t)dim;
   if (rb & 3) return fail(ctx, R3D_ERR_UNSUPPORTED, "binned re-rank needs row bytes % 4 == 0");
