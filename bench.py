@@ -256,7 +256,7 @@ def main():
         m = ctx.match_pairs(pairs, RATIO)
     sampler = ClockSampler(local_rank)
     cand_ms, rerank_ms, fb_ms, dev_ms, host_ms, launches = [], [], [], [], [], 0
-    fbq = q = 0
+    fbq = q = rejq = 0
     barrier()
     sampler.start()
     t0 = time.perf_counter()
@@ -266,7 +266,7 @@ def main():
         cand_ms.append(t["ms_candidates"]); rerank_ms.append(t["ms_rerank"]); fb_ms.append(t["ms_fallback"])
         dev_ms.append(t["ms_device_total"]); host_ms.append(t["ms_host_post"])
         launches += t["kernel_launches"]
-        fbq += t["fallback_queries"]; q += t["queries"]
+        fbq += t["fallback_queries"]; q += t["queries"]; rejq += t["rejected_queries"]
         d2h_step = t["d2h_bytes"]
     barrier()
     t_res = time.perf_counter() - t0
@@ -399,7 +399,7 @@ def main():
                              "exact_scan_fallback": float(np.mean(fb_ms)), "device_total": float(np.mean(dev_ms)),
                              "host_dedup": float(np.mean(host_ms))},
             "result": {"pairs_with_matches": int(n_match_pairs), "matches": int(n_matches),
-                       "fallback_query_frac": fbq / max(q, 1)},
+                       "fallback_query_frac": fbq / max(q, 1), "early_rejected_query_frac": rejq / max(q, 1)},
         }
         if filt is not None:
             line["f_filter"] = filt

@@ -224,6 +224,7 @@ typedef struct {
   uint64_t kernel_launches;
   uint64_t queries, fallback_queries, third_chunk_queries, fifth_chunk_queries;
   uint64_t h2d_bytes, d2h_bytes;
+  uint64_t rejected_queries; /* dropped before any exact distance: the ratio test provably cannot pass */
 } r3d_match_timing;
 int r3d_get_match_timing(const r3d_ctx* ctx, r3d_match_timing* out);
 

@@ -38,7 +38,8 @@ class MatchTiming(C.Structure):
     _fields_ = [("ms_prep", C.c_double), ("ms_candidates", C.c_double), ("ms_rerank", C.c_double),
                 ("ms_fallback", C.c_double), ("ms_device_total", C.c_double), ("ms_host_post", C.c_double),
                 ("kernel_launches", C.c_uint64), ("queries", C.c_uint64), ("fallback_queries", C.c_uint64),
-                ("third_chunk_queries", C.c_uint64), ("fifth_chunk_queries", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("third_chunk_queries", C.c_uint64), ("fifth_chunk_queries", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("rejected_queries", C.c_uint64)]
 
 
 class FilterTiming(C.Structure):

@@ -19,6 +19,14 @@ struct AcPair {          // per image pair (device)
 __host__ __device__ constexpr uint32_t ac_min_samples(int model) { return model == 0 ? 7u : (model == 1 ? 4u : 5u); }
 __host__ __device__ constexpr uint32_t ac_max_models(int model) { return model == 0 ? 3u : (model == 1 ? 1u : 10u); }
 
+struct AcPointSrc {      // per pair: where its matched positions come from and how they are normalised
+  const float2* xyI;     // positions of view I / J on the device (uploaded with the regions)
+  const float2* xyJ;
+  double s1, c1x, c1y;   // x1 = s1 * x + c1  (ACKernelAdaptor normalisation; identity for the essential model)
+  double s2, c2x, c2y;
+  uint32_t nI, nJ, identity, pad_;
+};
+
 struct AcHyp {           // one RANSAC iteration of one pair
   uint32_t pair;
   uint32_t sample[7];
@@ -38,6 +46,9 @@ struct AcInlierReq {
   uint32_t hyp_model;    // hypothesis * MAX_MODELS + model: where this round's model matrix lives on the device
 };
 
+// x1/x2[pt_ofs + k] = normalised positions of putative match k of every pair (double, like MatchesPairToMat)
+int launch_ac_points(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const AcPointSrc* src, uint32_t n_pairs,
+                     const uint2* matches, double2* x1, double2* x2, uint32_t* bad_flag);
 int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels);
 int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,

@@ -115,7 +115,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   // ---- per pair set-up (kernel adaptor of SURVEY.md A.5: normalisation, logalpha0, tables) ----
   std::vector<PairState> st;
   std::vector<AcPair> hpairs;
-  std::vector<double2> hx1, hx2;
+  std::vector<AcPointSrc> hsrc;
+  std::vector<uint2> hmatch;  // (i, j) of every putative match, pair after pair: the device looks the positions up
   std::vector<float> hlogc_n;
   uint32_t maxM = 0;
   {
@@ -141,8 +142,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     }
     if (st.empty()) return R3D_OK;
     if (pt_total > 0xfffffff0ull) return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: too many putative matches in one call");
-    hx1.resize(pt_total);
-    hx2.resize(pt_total);
+    hmatch.resize(pt_total);
+    hsrc.resize(st.size());
     hlogc_n.resize(tbl_total);
     hpairs.resize(st.size());
   }
@@ -173,16 +174,14 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     const double s2 = model == 2 ? 1.0 : 1.0 / std::sqrt((double)(wJ * hJ));
     const double c1x = model == 2 ? 0.0 : (double)(-.5f * wI) * s1, c1y = model == 2 ? 0.0 : -.5 * hI * s1;
     const double c2x = model == 2 ? 0.0 : (double)(-.5f * wJ) * s2, c2y = model == 2 ? 0.0 : -.5 * hJ * s2;
-    const float* xyI = vi.h_xy.data();
-    const float* xyJ = vj.h_xy.data();
-    for (uint32_t k = 0; k < M; ++k) {
-      const r3d_indmatch m = put->per[p][k];
-      if (m.i >= vi.n || m.j >= vj.n) { bad.store(1); return; }
-      const double xi = (double)xyI[2 * (size_t)m.i], yi = (double)xyI[2 * (size_t)m.i + 1];
-      const double xj = (double)xyJ[2 * (size_t)m.j], yj = (double)xyJ[2 * (size_t)m.j + 1];
-      hx1[s.pt_ofs + k] = model == 2 ? make_double2(xi, yi) : make_double2(s1 * xi + c1x, s1 * yi + c1y);
-      hx2[s.pt_ofs + k] = model == 2 ? make_double2(xj, yj) : make_double2(s2 * xj + c2x, s2 * yj + c2y);
-    }
+    // the matched positions are looked up, promoted to double and normalised on the device (k_ac_points):
+    // the host only ships the (i, j) list
+    static_assert(sizeof(r3d_indmatch) == sizeof(uint2), "IndMatch layout");
+    std::memcpy(hmatch.data() + s.pt_ofs, put->per[p].data(), (size_t)M * sizeof(uint2));
+    AcPointSrc& ps = hsrc[a];
+    ps.xyI = vi.d_xy; ps.xyJ = vj.d_xy;
+    ps.s1 = s1; ps.c1x = c1x; ps.c1y = c1y; ps.s2 = s2; ps.c2x = c2x; ps.c2y = c2y;
+    ps.nI = vi.n; ps.nJ = vj.n; ps.identity = model == 2 ? 1u : 0u; ps.pad_ = 0;
     AcPair ap;
     ap.pt_ofs = s.pt_ofs; ap.M = M; ap.tbl_ofs = s.tbl_ofs; ap.pad_ = 0;
     const double precision = precision_px * precision_px;  // upper_bound_precision = Square(dPrecision)
@@ -218,7 +217,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     }
     for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
   });
-  if (bad.load()) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
+  (void)bad;
   uint32_t cap = 32;
   while (cap < maxM) cap <<= 1;
   if ((size_t)cap * 12 > 200 * 1024)
@@ -227,6 +226,9 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   // ---- device buffers -------------------------------------------------------------------------
   DevBuf<AcPair> d_pairs(w);
   DevBuf<double2> d_x1(w), d_x2(w);
+  DevBuf<AcPointSrc> d_src(w);
+  DevBuf<uint2> d_match(w);
+  DevBuf<uint32_t> d_bad(w);
   DevBuf<float> d_logc_n(w), d_logc_k(w);
   DevBuf<AcHyp> d_hyp(w);
   DevBuf<double> d_F(w);
@@ -234,13 +236,26 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   DevBuf<AcScore> d_score(w);
   DevBuf<AcInlierReq> d_req(w);
   R3D_CUDA_TRY(ctx, d_pairs.ensure(hpairs.size()));
-  R3D_CUDA_TRY(ctx, d_x1.ensure(hx1.size()));
-  R3D_CUDA_TRY(ctx, d_x2.ensure(hx2.size()));
+  R3D_CUDA_TRY(ctx, d_x1.ensure(hmatch.size()));
+  R3D_CUDA_TRY(ctx, d_x2.ensure(hmatch.size()));
+  R3D_CUDA_TRY(ctx, d_src.ensure(hsrc.size()));
+  R3D_CUDA_TRY(ctx, d_match.ensure(hmatch.size()));
+  R3D_CUDA_TRY(ctx, d_bad.ensure(1));
   R3D_CUDA_TRY(ctx, d_logc_n.ensure(hlogc_n.size()));
   R3D_CUDA_TRY(ctx, d_logc_k.ensure(hlogc_k.size()));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_pairs.p, hpairs.data(), hpairs.size() * sizeof(AcPair), cudaMemcpyHostToDevice, w.stream));
-  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_x1.p, hx1.data(), hx1.size() * sizeof(double2), cudaMemcpyHostToDevice, w.stream));
-  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_x2.p, hx2.data(), hx2.size() * sizeof(double2), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_src.p, hsrc.data(), hsrc.size() * sizeof(AcPointSrc), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_match.p, hmatch.data(), hmatch.size() * sizeof(uint2), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), w.stream));
+  {
+    int rcp = launch_ac_points(ctx, w, d_pairs.p, d_src.p, (uint32_t)hpairs.size(), d_match.p, d_x1.p, d_x2.p, d_bad.p);
+    if (rcp) return rcp;
+    uint32_t hbad = 0;
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(&hbad, d_bad.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, w.stream));
+    R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    if (hbad) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
+    T.kernel_launches += 1;
+  }
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_n.p, hlogc_n.data(), hlogc_n.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_k.p, hlogc_k.data(), hlogc_k.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
 

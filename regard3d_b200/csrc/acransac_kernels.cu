@@ -441,6 +441,33 @@ __global__ void __launch_bounds__(256) k_f7_inliers(const AcPair* __restrict__ p
   for (uint32_t i = threadIdx.x; i < rq.k && i < c; i += blockDim.x) out[rq.out_ofs + i] = si[i];
 }
 
+// ---- positions of the putative matches, promoted to double and normalised exactly like the host would ----
+__global__ void __launch_bounds__(256) k_ac_points(const AcPair* __restrict__ pairs, const AcPointSrc* __restrict__ src,
+                                                   const uint2* __restrict__ matches, double2* __restrict__ x1,
+                                                   double2* __restrict__ x2, uint32_t* __restrict__ bad_flag) {
+  const AcPair pr = pairs[blockIdx.y];
+  const AcPointSrc ps = src[blockIdx.y];
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < pr.M; k += gridDim.x * blockDim.x) {
+    const uint2 m = matches[pr.pt_ofs + k];
+    if (m.x >= ps.nI || m.y >= ps.nJ) { atomicExch(bad_flag, 1u); continue; }
+    const float2 a = ps.xyI[m.x], b = ps.xyJ[m.y];
+    const double xi = (double)a.x, yi = (double)a.y, xj = (double)b.x, yj = (double)b.y;
+    x1[pr.pt_ofs + k] = ps.identity ? make_double2(xi, yi) : make_double2(ps.s1 * xi + ps.c1x, ps.s1 * yi + ps.c1y);
+    x2[pr.pt_ofs + k] = ps.identity ? make_double2(xj, yj) : make_double2(ps.s2 * xj + ps.c2x, ps.s2 * yj + ps.c2y);
+  }
+}
+
+int launch_ac_points(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const AcPointSrc* src, uint32_t n_pairs,
+                     const uint2* matches, double2* x1, double2* x2, uint32_t* bad_flag) {
+  if (!n_pairs) return R3D_OK;
+  for (uint32_t p0 = 0; p0 < n_pairs; p0 += 65535u) {  // gridDim.y limit
+    const uint32_t np = std::min(65535u, n_pairs - p0);
+    k_ac_points<<<dim3(8, np), 256, 0, w.stream>>>(pairs + p0, src + p0, matches, x1, x2, bad_flag);
+  }
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels) {

@@ -188,6 +188,36 @@ __device__ __forceinline__ double key_lower_bound(uint32_t key, float eps_abs, d
   return lb;
 }
 
+// Early rejection (matching mode only; r3d_search_neighbours needs every neighbour): the ratio test
+// d1 < fl(ratio2 * d2) cannot pass when a LOWER bound of the nearest distance already reaches ratio2 times an
+// UPPER bound of the second-nearest.  E1 >= LB(key0) because key0 is the smallest chunk key; E2 <= UB(key1)
+// because the minima of the two best chunks are two distinct database rows whose exact distances are at most
+// UB(key0) <= UB(key1).  Same two-sided error model as the certification: |key value - real distance| <=
+// eps_abs + |key| * pack_rel (tests/test_gpu_match.py::test_candidate_error_bound_holds), float recipe within
+// gamma of the real number, one more rounding for the product.  Such a query needs no exact distance at all.
+__device__ __forceinline__ bool ratio_test_cannot_pass(uint32_t key0, uint32_t key1, float eps_abs, double gamma,
+                                                       double pack_rel, float ratio2) {
+  const double lb = key_lower_bound(key0, eps_abs, gamma, pack_rel);
+  const double kv1 = (double)__uint_as_float(key1);
+  double ub = (kv1 + fabs(kv1) * pack_rel + (double)eps_abs) * (1.0 + gamma);
+  if (!(ub > 0.0)) ub = 0.0;
+  return lb >= (double)ratio2 * ub * (1.0 + 1.2e-7);
+}
+
+// the (query, chunk) bookkeeping of stage A and this test, shared by k_bin_count / k_bin_fill / k_bin_merge so that
+// the three kernels take the same decision
+__device__ __forceinline__ bool stage_a_skips_query(const PairDesc& pd, uint32_t key0, uint32_t key1, uint32_t dim,
+                                                    float ratio2, int allow_reject) {
+  if (!allow_reject) return false;
+  const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
+  const uint32_t nchunks = pd.nI_pad / kChunk;
+  const uint32_t c0 = key0 & cmask, c1 = key1 & cmask;
+  if (c0 >= nchunks || c1 >= nchunks || c0 == c1) return false;  // sentinel keys: the regular path sorts it out
+  const double pack_rel = ldexp(1.0, (int)pd.chunk_bits - 23);
+  const double gamma = (double)(dim + 16) * (1.0 / 16777216.0);
+  return ratio_test_cannot_pass(key0, key1, pd.eps_abs, gamma, pack_rel, ratio2);
+}
+
 // A query that passes the ratio test appends IndMatch(i in I, j = q in J) to ITS PAIR's segment of the
 // dense match array (segment = the pair's query rows, so it can never overflow); the per-pair counters
 // live behind the 16 scalar counters.  k_pack_matches then packs the segments for the host copy: the

@@ -308,7 +308,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       std::vector<uint32_t> cnt(nb + 1, 0u);
       for (uint32_t k = 0; k < nb; ++k) cnt[k + 1] = cnt[k] + os.h_counters[16 + k];
       const uint32_t n_matches = cnt[nb];
-      const uint32_t c_fb = os.h_counters[1], c_b = os.h_counters[4], c_c = os.h_counters[3];
+      const uint32_t c_fb = os.h_counters[1], c_b = os.h_counters[4], c_c = os.h_counters[3], c_rej = os.h_counters[5];
       size_t bytes = (size_t)n_matches * sizeof(uint2);
       if (n_matches) {
         if (os.h_matches_cap < bytes) {
@@ -345,6 +345,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       T.fallback_queries += c_fb;
       T.third_chunk_queries += c_b;
       T.fifth_chunk_queries += c_c;
+      T.rejected_queries += c_rej;
       T.d2h_bytes += (16 + nb) * sizeof(uint32_t) + bytes;
       T.h2d_bytes += h2d_batch;
     });
@@ -424,6 +425,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
       sum.fallback_queries += t.fallback_queries;
       sum.third_chunk_queries += t.third_chunk_queries;
       sum.fifth_chunk_queries += t.fifth_chunk_queries;
+      sum.rejected_queries += t.rejected_queries;
       sum.h2d_bytes += t.h2d_bytes;
       sum.d2h_bytes += t.d2h_bytes;
     }

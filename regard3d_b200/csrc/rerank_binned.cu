@@ -24,7 +24,8 @@ struct Part {  // partial top-2 of one (query, chunk)
 
 __global__ void __launch_bounds__(256) k_bin_count(const PairDesc* __restrict__ pairs,
                                                    const uint32_t* __restrict__ keys, uint32_t cstride,
-                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ slot) {
+                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ slot,
+                                                   uint32_t dim, float ratio2, int allow_reject) {
   const uint32_t pair = blockIdx.y;
   const PairDesc pd = pairs[pair];
   if (!pd.use_tc) return;
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256) k_bin_count(const PairDesc* __restrict__ 
   const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
   const uint2 k = __ldg((const uint2*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
   const uint32_t nchunks = pd.nI_pad / kChunk;
+  if (stage_a_skips_query(pd, k.x, k.y, dim, ratio2, allow_reject)) return;  // cannot pass the ratio test
   uint32_t c0 = k.x & cmask, c1 = k.y & cmask;
   if (c0 >= nchunks) c0 = 0;  // sentinel keys (fewer than 2 real chunks): any valid chunk keeps the
   if (c1 >= nchunks) c1 = 0;  // bookkeeping regular; certification handles the rest
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(256) k_bin_scan(const PairDesc* __restrict__ p
 __global__ void __launch_bounds__(256) k_bin_fill(const PairDesc* __restrict__ pairs,
                                                   const uint32_t* __restrict__ keys, uint32_t cstride,
                                                   const uint32_t* __restrict__ ofs, const uint32_t* __restrict__ slot,
-                                                  uint32_t* __restrict__ list) {
+                                                  uint32_t* __restrict__ list, uint32_t dim, float ratio2,
+                                                  int allow_reject) {
   const uint32_t pair = blockIdx.y;
   const PairDesc pd = pairs[pair];
   if (!pd.use_tc) return;
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(256) k_bin_fill(const PairDesc* __restrict__ p
   const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
   const uint2 k = __ldg((const uint2*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
   const uint32_t nchunks = pd.nI_pad / kChunk;
+  if (stage_a_skips_query(pd, k.x, k.y, dim, ratio2, allow_reject)) return;
   uint32_t c0 = k.x & cmask, c1 = k.y & cmask;
   if (c0 >= nchunks) c0 = 0;
   if (c1 >= nchunks) c1 = 0;
@@ -246,6 +250,10 @@ __global__ void __launch_bounds__(256) k_bin_merge(const PairDesc* __restrict__ 
   if (q >= pd.nJ) return;
   const uint32_t cmask = (1u << pd.chunk_bits) - 1u;
   const uint4 k = __ldg((const uint4*)(keys + (size_t)(pd.q_ofs + q) * kKeyStride));
+  if (stage_a_skips_query(pd, k.x, k.y, dim, ratio2, nn == nullptr)) {  // no match can come out of this query
+    atomicAdd(&counters[5], 1u);
+    return;
+  }
   const Part a = parts[(size_t)(pd.q_ofs + q) * 2 + 0];
   const Part b = parts[(size_t)(pd.q_ofs + q) * 2 + 1];
   Top2 ta, tb;
@@ -285,9 +293,10 @@ int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   const size_t smem = (size_t)kBinWarps * kChunk * row_stride;
   R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)n_pairs * cstride * sizeof(uint32_t), w.stream));
   dim3 gq((max_nJ + 255) / 256, n_pairs);
-  k_bin_count<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot);
+  const int allow_reject = d_nn == nullptr ? 1 : 0;
+  k_bin_count<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot, dim, ratio2, allow_reject);
   k_bin_scan<<<n_pairs, 256, 0, w.stream>>>(d_pairs, cstride, d_cnt);
-  k_bin_fill<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot, d_list);
+  k_bin_fill<<<gq, 256, 0, w.stream>>>(d_pairs, d_keys, cstride, d_cnt, d_slot, d_list, dim, ratio2, allow_reject);
   dim3 gc((cstride + kBinWarps - 1) / kBinWarps, n_pairs);
   if (dtype == 0) {
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_bin_rerank<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
