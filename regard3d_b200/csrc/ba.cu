@@ -26,6 +26,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <string>
 
 namespace cg = cooperative_groups;
 
@@ -388,6 +389,183 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
   }
 }
 
+// ---- Schur complement, batched and atomic-free inside a CTA (the default path) --------------------------
+// The warp-per-point kernel above spends its time in ~1 100 fp64 global atomics per point.  Here a CTA takes a
+// BATCH of consecutive points of a camera-sorted processing order (host: setup_problem), so that the batch touches
+// only a few distinct 6-wide blocks of S (its cameras + intrinsic groups):
+//   stage 1  warp per point, lane per observation: scaled Jacobians, V^-1, and one shared-memory ENTRY per block
+//            of the point: W (6x3), W V^-1, W V^-1 g_p, and for camera entries Jc, Jg (the U terms)
+//   stage 2  OUTPUT-centric: 36 threads own one 6x6 block pair (lo, hi) of the batch's local block table, walk the
+//            batch's points and accumulate  [U term] - (W_lo V^-1) W_hi^T  in a register; 6 threads own a block's
+//            right-hand side.  No atomics, no conflicts.
+//   flush    one global atomicAdd per non-zero output: a few thousand per batch instead of ~1 100 per POINT.
+// Limits of this path (else the host selects the per-point kernel): <= kBatchEntries entries and <= kBatchBlocks
+// distinct blocks per batch, <= 32 observations and <= 2 intrinsic groups per point, no point observed twice by
+// one camera.
+constexpr int kBatchPoints = 24;    // points per CTA batch (upper bound; the host cuts batches)
+constexpr int kBatchEntries = 144;  // entries per batch
+constexpr int kBatchBlocks = 40;    // distinct 6-wide blocks per batch
+constexpr int kEntryDoubles = 66;   // W 18 | WV 18 | WVg 6 | Jc 12 | Jg 12
+constexpr size_t kBatchSmemBytes = ((size_t)kBatchEntries * kEntryDoubles + (size_t)kBatchPoints * 2 * 36) * sizeof(double);
+// Static structure of a batch, built once per problem on the host (setup_problem): the processing order, the
+// first entry of every ordered point (entries of a point: its observations in CSR order, then its distinct
+// intrinsic groups in order of first appearance), the batch's sorted distinct block columns and every entry's
+// index into them.
+struct BatchDesc { uint32_t first, count, ent_first, nblk; };
+struct BatchTables {
+  const BatchDesc* batches;
+  const uint32_t* pt_order;    // [n_pts]
+  const uint32_t* ent_start;   // [n_pts + 1] by ordered position
+  const int* cols;             // [n_batches][kBatchBlocks]
+  const unsigned char* lblk;   // [total entries]
+};
+
+__global__ void __launch_bounds__(256, 2) k_ba_schur_batched(Dev d, BatchTables bt, double inv_radius) {
+  extern __shared__ __align__(16) double bsm[];
+  double* ent = bsm;                                            // [kBatchEntries][kEntryDoubles]
+  double* gg = ent + (size_t)kBatchEntries * kEntryDoubles;      // [kBatchPoints * 2][36]  sum Jg^T Jg of the group entries
+  __shared__ int s_col[kBatchBlocks];                            // local block -> first column in S
+  __shared__ unsigned char s_lblk[kBatchEntries];                // per entry: local block
+  __shared__ int s_ggidx[kBatchEntries];                         // group entries: GG slot ; camera entries: -2 - (own group column, -1 if none)
+  __shared__ unsigned char s_slot[kBatchPoints][kBatchBlocks];   // entry of (point, local block), 255 = absent
+  __shared__ uint32_t s_pent[kBatchPoints + 1];                  // first entry of each point, relative to the batch
+  const BatchDesc bd = bt.batches[blockIdx.x];
+  const uint32_t* pt_order = bt.pt_order;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = (int)bd.count;
+  const int L = (int)bd.nblk;
+  for (int k = threadIdx.x; k <= P; k += blockDim.x) s_pent[k] = bt.ent_start[bd.first + k] - bd.ent_first;
+  for (int k = threadIdx.x; k < L; k += blockDim.x) s_col[k] = bt.cols[(size_t)blockIdx.x * kBatchBlocks + k];
+  for (int k = threadIdx.x; k < kBatchPoints * kBatchBlocks; k += blockDim.x) ((unsigned char*)s_slot)[k] = 255;
+  __syncthreads();
+  const int nent = (int)s_pent[P];
+  for (int q = threadIdx.x; q < nent; q += blockDim.x) s_lblk[q] = bt.lblk[bd.ent_first + q];
+  // ---- stage 1: warp per point ----
+  for (int k = warp; k < P; k += 8) {
+    const uint32_t ip = pt_order[bd.first + k];
+    const uint32_t b = d.pt_ofs[ip], e = d.pt_ofs[ip + 1];
+    const int nobs = (int)(e - b);
+    const uint32_t e0 = s_pent[k];
+    double Jc[12], Jg[12], Jp[6], r[2];
+    uint32_t colc = 0;
+    int colg = -1;
+    const bool has = lane < nobs;
+    if (has) scaled_jacobian(d, d.pt_obs[b + lane], Jc, Jg, Jp, r, &colc, &colg);
+    else {
+      for (int i = 0; i < 6; ++i) Jp[i] = 0.0;
+    }
+    double v[6] = {Jp[0] * Jp[0] + Jp[3] * Jp[3], Jp[0] * Jp[1] + Jp[3] * Jp[4], Jp[0] * Jp[2] + Jp[3] * Jp[5],
+                   Jp[1] * Jp[1] + Jp[4] * Jp[4], Jp[1] * Jp[2] + Jp[4] * Jp[5], Jp[2] * Jp[2] + Jp[5] * Jp[5]};
+    for (int q = 0; q < 6; ++q)
+      for (int o = 16; o >= 1; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    const size_t pcol = (size_t)d.nB + 3 * (size_t)ip;
+    double V[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
+    for (int i = 0; i < 3; ++i) V[4 * i] += fmin(fmax(d.diag[pcol + i], 1e-6), 1e32) * inv_radius;
+    double Vi[9];
+    inv3_sym(V, Vi);
+    if (lane == 0)
+      for (int i = 0; i < 9; ++i) d.Vinv[9 * (size_t)ip + i] = Vi[i];
+    const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
+    const double Vg[3] = {Vi[0] * gp[0] + Vi[1] * gp[1] + Vi[2] * gp[2], Vi[3] * gp[0] + Vi[4] * gp[1] + Vi[5] * gp[2],
+                          Vi[6] * gp[0] + Vi[7] * gp[1] + Vi[8] * gp[2]};
+    double Wg[18];  // this observation's group block (zero for absent lanes / fixed intrinsics)
+    for (int q = 0; q < 18; ++q) Wg[q] = 0.0;
+    if (has) {  // camera entry of observation `lane`
+      double* en = ent + (size_t)(e0 + lane) * kEntryDoubles;
+      for (int i = 0; i < 6; ++i) {
+        double w3[3];
+        for (int j = 0; j < 3; ++j) {
+          w3[j] = Jc[i] * Jp[j] + Jc[6 + i] * Jp[3 + j];
+          en[3 * i + j] = w3[j];
+          if (colg >= 0) Wg[3 * i + j] = Jg[i] * Jp[j] + Jg[6 + i] * Jp[3 + j];
+        }
+        for (int j = 0; j < 3; ++j) en[18 + 3 * i + j] = w3[0] * Vi[j] + w3[1] * Vi[3 + j] + w3[2] * Vi[6 + j];
+        en[36 + i] = w3[0] * Vg[0] + w3[1] * Vg[1] + w3[2] * Vg[2];
+      }
+      for (int q = 0; q < 12; ++q) { en[42 + q] = Jc[q]; en[54 + q] = Jg[q]; }
+      s_ggidx[e0 + lane] = -2 - colg;
+    }
+    // group entries: masked warp reductions of Wg and Jg^T Jg over the lanes of each distinct group (<= 2)
+    if (d.refine_intr) {
+      unsigned todo = __ballot_sync(0xffffffffu, has);
+      int gslot = 0;
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int gcol = __shfl_sync(0xffffffffu, colg, leader);
+        const bool mine = has && colg == gcol;
+        const unsigned members = __ballot_sync(0xffffffffu, mine);
+        todo &= ~members;
+        double* en = ent + (size_t)(e0 + nobs + gslot) * kEntryDoubles;
+        double* G = gg + (size_t)(2 * k + gslot) * 36;
+        for (int q = 0; q < 18; ++q) {
+          double x = mine ? Wg[q] : 0.0;
+          for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (lane == 0) en[q] = x;
+        }
+        for (int q = 0; q < 36; ++q) {
+          const int i = q / 6, j = q % 6;
+          double x = mine ? (Jg[i] * Jg[j] + Jg[6 + i] * Jg[6 + j]) : 0.0;
+          for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+          if (lane == 0) G[q] = x;
+        }
+        __syncwarp();
+        if (lane < 6) {  // WV and WVg of the merged group block
+          const int i = lane;
+          const double w0 = en[3 * i], w1 = en[3 * i + 1], w2 = en[3 * i + 2];
+          for (int j = 0; j < 3; ++j) en[18 + 3 * i + j] = w0 * Vi[j] + w1 * Vi[3 + j] + w2 * Vi[6 + j];
+          en[36 + i] = w0 * Vg[0] + w1 * Vg[1] + w2 * Vg[2];
+        }
+        if (lane == 0) s_ggidx[e0 + nobs + gslot] = 2 * k + gslot;
+        ++gslot;
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < P; k += blockDim.x)
+    for (uint32_t q = s_pent[k]; q < s_pent[k + 1]; ++q) s_slot[k][s_lblk[q]] = (unsigned char)q;
+  __syncthreads();
+  // ---- stage 2: output-centric accumulation; item = block pair (lo <= hi) or a block's right-hand side ----
+  const int grp = threadIdx.x / 36, el = threadIdx.x % 36;
+  const int npairs = L * (L + 1) / 2;
+  if (grp < 7) {
+    const int i = el / 6, j = el % 6;
+    for (int item = grp; item < npairs + L; item += 7) {
+      if (item >= npairs) {  // right-hand side of local block l
+        if (el >= 6) continue;
+        const int l = item - npairs;
+        double acc = 0.0;
+        for (int k = 0; k < P; ++k) {
+          const unsigned char sa = s_slot[k][l];
+          if (sa != 255) acc += ent[(size_t)sa * kEntryDoubles + 36 + el];
+        }
+        if (acc != 0.0) atomicAdd(&d.rhs[s_col[l] + el], acc);
+        continue;
+      }
+      int hi = (int)((sqrt(8.0 * item + 1.0) - 1.0) * 0.5);
+      while ((hi + 1) * (hi + 2) / 2 <= item) ++hi;
+      while (hi * (hi + 1) / 2 > item) --hi;
+      const int lo = item - hi * (hi + 1) / 2;  // lo <= hi, columns ascending: the block sits in S's upper triangle
+      const int col_hi = s_col[hi];
+      double acc = 0.0;
+      for (int k = 0; k < P; ++k) {
+        const unsigned char sa = s_slot[k][lo], sb = s_slot[k][hi];
+        if (sa == 255 || sb == 255) continue;
+        const double* ea = ent + (size_t)sa * kEntryDoubles;
+        const double* eb = ent + (size_t)sb * kEntryDoubles;
+        acc -= ea[18 + 3 * i] * eb[3 * j] + ea[18 + 3 * i + 1] * eb[3 * j + 1] + ea[18 + 3 * i + 2] * eb[3 * j + 2];
+        const int ga = s_ggidx[sa];
+        if (lo == hi) {
+          if (ga >= 0) acc += gg[(size_t)ga * 36 + el];                                   // group: sum Jg^T Jg
+          else acc += ea[42 + i] * ea[42 + j] + ea[48 + i] * ea[48 + j];                   // camera: Jc^T Jc
+        } else if (ga < 0 && -2 - ga == col_hi) {                                          // camera x its own group: Jc^T Jg
+          acc += ea[42 + i] * ea[54 + j] + ea[48 + i] * ea[60 + j];
+        }
+      }
+      if (acc != 0.0) atomicAdd(&d.S[(size_t)(s_col[lo] + i) * d.nB + col_hi + j], acc);
+    }
+  }
+}
+
 // mirror the upper-triangular block form into the lower triangle, add D^2 on the diagonal, rhs -= g
 __global__ void k_ba_finish_S(Dev d, double inv_radius) {
   const uint32_t i = blockIdx.y * blockDim.y + threadIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -614,8 +792,13 @@ struct DeviceArrays {  // blocks come from (and return to) the worker's size-buc
   }
 };
 
+struct BatchPlan {  // device tables of the batched Schur kernel; n_batches == 0: use the per-point kernel
+  r3d::ba::BatchTables t{};
+  uint32_t n_batches = 0;
+};
+
 int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, DeviceArrays& mem, Dev& d, bool refine_intr,
-                  double huber_a, bool full, uint32_t* max_obs_out = nullptr) {
+                  double huber_a, bool full, uint32_t* max_obs_out = nullptr, BatchPlan* plan = nullptr) {
   if (!p || !p->poses || !p->intrinsics || !p->points || !p->obs_cam || !p->obs_pt || !p->cam_intr || !p->obs_xy)
     return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: NULL array in the problem");
   for (uint64_t o = 0; o < p->n_obs; ++o)
@@ -665,7 +848,106 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   R3D_CUDA_TRY(ctx, mem.alloc(&pobs, hobs.size()));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pofs, hofs.data(), hofs.size() * 4, cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pobs, hobs.data(), hobs.size() * 4, cudaMemcpyHostToDevice, w.stream));
-  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // hofs / hobs are locals
+  // ---- plan of the batched Schur kernel (static per problem): camera-sorted processing order, batches that
+  //      respect the kernel's shared-memory limits, each batch's sorted block columns, every entry's local block
+  std::vector<uint32_t> h_order, h_ent_start;
+  std::vector<r3d::ba::BatchDesc> h_batches;
+  std::vector<int> h_cols;
+  std::vector<unsigned char> h_lblk;
+  if (plan) {
+    using namespace r3d::ba;
+    const uint32_t n_pts = p->n_pts;
+    bool ok = maxobs <= 32 && n_pts > 0;
+    // counting sort of the points by the smallest camera that sees them
+    std::vector<uint32_t> key(n_pts, 0), bucket((size_t)p->n_cams + 2, 0);
+    for (uint32_t i = 0; i < n_pts; ++i) {
+      uint32_t mn = p->n_cams;
+      for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) mn = std::min(mn, p->obs_cam[hobs[t]]);
+      key[i] = mn;
+      bucket[mn + 1]++;
+    }
+    for (size_t c = 0; c + 1 < bucket.size(); ++c) bucket[c + 1] += bucket[c];
+    h_order.resize(n_pts);
+    for (uint32_t i = 0; i < n_pts; ++i) h_order[bucket[key[i]]++] = i;
+    h_ent_start.assign((size_t)n_pts + 1, 0);
+    std::vector<int> cols, pcols;  // sorted distinct columns of the open batch / of one point
+    BatchDesc cur{0, 0, 0, 0};
+    uint32_t ent_run = 0;
+    auto close_batch = [&]() {
+      if (!cur.count) return;
+      cur.nblk = (uint32_t)cols.size();
+      h_batches.push_back(cur);
+      h_cols.resize(h_batches.size() * kBatchBlocks, 0);
+      std::copy(cols.begin(), cols.end(), h_cols.begin() + (h_batches.size() - 1) * kBatchBlocks);
+      for (uint32_t k = 0; k < cur.count; ++k) {  // local block of every entry of the batch
+        const uint32_t ip = h_order[cur.first + k];
+        int g0 = -1, g1 = -1;
+        for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+          const uint32_t cam = p->obs_cam[hobs[t]];
+          h_lblk.push_back((unsigned char)(std::lower_bound(cols.begin(), cols.end(), (int)(6 * cam)) - cols.begin()));
+          if (refine_intr) {
+            const int gc = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
+            if (gc != g0 && gc != g1) { if (g0 < 0) g0 = gc; else g1 = gc; }
+          }
+        }
+        for (int gc : {g0, g1})
+          if (gc >= 0) h_lblk.push_back((unsigned char)(std::lower_bound(cols.begin(), cols.end(), gc) - cols.begin()));
+      }
+      cols.clear();
+      cur = BatchDesc{cur.first + cur.count, 0, ent_run, 0};
+    };
+    for (uint32_t k = 0; k < n_pts && ok; ++k) {
+      const uint32_t ip = h_order[k];
+      pcols.clear();
+      int ngroups = 0;
+      for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+        const uint32_t cam = p->obs_cam[hobs[t]];
+        pcols.push_back((int)(6 * cam));
+        if (refine_intr) pcols.push_back((int)(6 * p->n_cams + 6 * p->cam_intr[cam]));
+      }
+      std::sort(pcols.begin(), pcols.end());
+      for (size_t q = 1; q < pcols.size(); ++q)
+        if (pcols[q] == pcols[q - 1] && pcols[q] < (int)(6 * p->n_cams)) ok = false;  // a camera sees the point twice
+      pcols.erase(std::unique(pcols.begin(), pcols.end()), pcols.end());
+      for (int c : pcols) ngroups += c >= (int)(6 * p->n_cams);
+      if (ngroups > 2) ok = false;
+      const uint32_t nent = (hofs[ip + 1] - hofs[ip]) + (uint32_t)ngroups;
+      if (nent > (uint32_t)kBatchEntries || pcols.size() > (size_t)kBatchBlocks) ok = false;
+      if (!ok) break;
+      // would the point still fit into the open batch?
+      size_t merged = cols.size();
+      for (int c : pcols) merged += !std::binary_search(cols.begin(), cols.end(), c);
+      if (cur.count == (uint32_t)kBatchPoints || (ent_run - cur.ent_first) + nent > (uint32_t)kBatchEntries ||
+          merged > (size_t)kBatchBlocks)
+        close_batch();
+      for (int c : pcols)
+        if (!std::binary_search(cols.begin(), cols.end(), c)) cols.insert(std::lower_bound(cols.begin(), cols.end(), c), c);
+      h_ent_start[k] = ent_run;
+      ent_run += nent;
+      cur.count++;
+    }
+    if (ok) {
+      h_ent_start[n_pts] = ent_run;
+      close_batch();
+      uint32_t *d_order, *d_ent_start;
+      BatchDesc* d_batches;
+      int* d_cols;
+      unsigned char* d_lblk;
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_order, h_order.size()));
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_ent_start, h_ent_start.size()));
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_batches, h_batches.size()));
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_cols, h_cols.size()));
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_lblk, h_lblk.size()));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_order, h_order.data(), h_order.size() * 4, cudaMemcpyHostToDevice, w.stream));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_ent_start, h_ent_start.data(), h_ent_start.size() * 4, cudaMemcpyHostToDevice, w.stream));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_batches, h_batches.data(), h_batches.size() * sizeof(BatchDesc), cudaMemcpyHostToDevice, w.stream));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_cols, h_cols.data(), h_cols.size() * sizeof(int), cudaMemcpyHostToDevice, w.stream));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_lblk, h_lblk.data(), h_lblk.size(), cudaMemcpyHostToDevice, w.stream));
+      plan->t = BatchTables{d_batches, d_order, d_ent_start, d_cols, d_lblk};
+      plan->n_batches = (uint32_t)h_batches.size();
+    }
+  }
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // hofs / hobs and the plan vectors are locals
   d.pt_ofs = pofs; d.pt_obs = pobs;
   R3D_CUDA_TRY(ctx, mem.alloc(&d.poses_new, 6 * (size_t)p->n_cams));
   R3D_CUDA_TRY(ctx, mem.alloc(&d.intr_new, 6 * (size_t)p->n_intr));
@@ -726,8 +1008,14 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   mem.w = &w;
   Dev d;
   uint32_t max_obs = 1;
-  int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs);
+  BatchPlan plan;
+  static const bool per_point_schur = getenv("R3D_BA_SCHUR") && std::string(getenv("R3D_BA_SCHUR")) == "point";
+  int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs,
+                         per_point_schur ? nullptr : &plan);
   if (rc) return rc;
+  if (plan.n_batches)
+    R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur_batched, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)r3d::ba::kBatchSmemBytes));
   const int obs_cap = (int)std::max<uint32_t>(max_obs, 1u);
   sum->seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   const size_t nparam = (size_t)d.nB + 3 * (size_t)d.n_pts;
@@ -803,7 +1091,10 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     const double inv_radius = 1.0 / radius;
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.S, 0, ((size_t)nB * nB + nB) * 8, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, 5 * sizeof(double), w.stream));
-    r3d::ba::k_ba_schur<<<(d.n_pts + r3d::ba::kSchurWarps - 1) / r3d::ba::kSchurWarps, r3d::ba::kSchurWarps * 32, schur_smem, w.stream>>>(d, inv_radius, obs_cap);
+    if (plan.n_batches)
+      r3d::ba::k_ba_schur_batched<<<plan.n_batches, 256, r3d::ba::kBatchSmemBytes, w.stream>>>(d, plan.t, inv_radius);
+    else
+      r3d::ba::k_ba_schur<<<(d.n_pts + r3d::ba::kSchurWarps - 1) / r3d::ba::kSchurWarps, r3d::ba::kSchurWarps * 32, schur_smem, w.stream>>>(d, inv_radius, obs_cap);
     // the exchange step: partial reduced camera systems of the point partitions -> their sum (NVLink)
     if ((rc = comm_allreduce(ctx, w.stream, d.S, (size_t)nB * nB + nB, kCommSum))) return rc;
     {

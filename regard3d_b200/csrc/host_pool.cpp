@@ -6,6 +6,7 @@
 // std::threads per loop cost more than the loop bodies; this pool keeps the threads alive and lets
 // concurrent loops share them.  A loop may be entered from any thread, including from inside another
 // pooled loop (the caller always works on its own loop, so nesting cannot deadlock).
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdlib>
@@ -35,8 +36,14 @@ class HostPool {
   HostPool() {
     unsigned hw = std::thread::hardware_concurrency();
     if (hw < 2) hw = 2;
+    // one process per GPU (torchrun / mpirun): share the host cores between the local ranks
+    unsigned local_world = 1;
+    for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
+      const char* v = std::getenv(name);
+      if (v && std::atoi(v) > 0) { local_world = (unsigned)std::atoi(v); break; }
+    }
     const char* e = std::getenv("R3D_HOST_THREADS");
-    unsigned n = e && std::atoi(e) > 0 ? (unsigned)std::atoi(e) : std::min(hw, 96u);
+    unsigned n = e && std::atoi(e) > 0 ? (unsigned)std::atoi(e) : std::max(4u, std::min(hw / local_world, 96u));
     for (unsigned t = 0; t + 1 < n; ++t) threads_.emplace_back([this]() { worker(); });
   }
   ~HostPool() {

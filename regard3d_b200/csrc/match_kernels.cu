@@ -73,17 +73,69 @@ __global__ void __launch_bounds__(256) k_rerank(const PairDesc* __restrict__ pai
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_exact_scan : one block per listed (pair, query)
+// k_exact_scan : exact brute force for the listed (pair, query) items.
+//   long lists (whole pairs that bypass the tensor-core pass): one block per item;
+//   short lists (the handful of uncertified queries per batch): every item is cut into kScanSlices row
+//   slices handled by different blocks -- a 10 000-row scan by ONE block is a 0.3 ms latency chain per
+//   launch -- the last slice to finish (per-item arrival counter) merges the partial top-2s and emits.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t kScanSlices = 32;
+constexpr uint32_t kScanSplitMaxItems = 2048;
 template <int DTYPE>
 __global__ void __launch_bounds__(256) k_exact_scan(const PairDesc* __restrict__ pairs,
                                                     const uint2* __restrict__ list,
                                                     const uint32_t* __restrict__ list_count, uint32_t dim,
                                                     float ratio2, uint32_t* counters, uint2* matches,
-                                                    float4* nn) {
+                                                    float4* nn, Top2* __restrict__ slice_best,
+                                                    uint32_t* __restrict__ slice_done) {
   extern __shared__ __align__(16) unsigned char smem_q[];
   __shared__ Top2 warp_best[8];
+  __shared__ uint32_t s_last;
   const uint32_t n_list = *list_count;
+  if (n_list <= kScanSplitMaxItems && slice_best != nullptr) {
+    for (uint32_t vb = blockIdx.x; vb < n_list * kScanSlices; vb += gridDim.x) {
+      const uint32_t item = vb / kScanSlices, slice = vb % kScanSlices;
+      const uint2 pq = list[item];
+      const PairDesc pd = pairs[pq.x];
+      const size_t rb = row_bytes(DTYPE, dim);
+      const char* qrow = (const char*)pd.descJ + (size_t)pq.y * rb;
+      __syncthreads();
+      for (uint32_t b = threadIdx.x; b < rb; b += blockDim.x) smem_q[b] = qrow[b];
+      __syncthreads();
+      const uint32_t per = (pd.nI + kScanSlices - 1) / kScanSlices;
+      const uint32_t r0 = slice * per, r1 = min(pd.nI, r0 + per);
+      Top2 t;
+      t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
+      for (uint32_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+        const float dd = exact_l2<DTYPE>(smem_q, (const char*)pd.descI + (size_t)i * rb, dim);
+        top2_insert(t, dd, i);
+      }
+      t = top2_warp_reduce(t);
+      if ((threadIdx.x & 31u) == 0) warp_best[threadIdx.x >> 5] = t;
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        Top2 u;
+        u.d1 = u.d2 = FLT_MAX; u.i1 = u.i2 = 0xffffffffu;
+        if (threadIdx.x < (blockDim.x >> 5)) u = warp_best[threadIdx.x];
+        u = top2_warp_reduce(u);
+        if (threadIdx.x == 0) {
+          slice_best[(size_t)item * kScanSlices + slice] = u;
+          __threadfence();
+          s_last = (atomicAdd(&slice_done[item], 1u) == kScanSlices - 1u) ? 1u : 0u;
+        }
+      }
+      __syncthreads();
+      if (s_last && threadIdx.x < 32) {  // every slice of the item has been published
+        __threadfence();
+        Top2 u = ((volatile Top2*)slice_best)[(size_t)item * kScanSlices + threadIdx.x % kScanSlices].d1 == 0.f
+                     ? slice_best[(size_t)item * kScanSlices + threadIdx.x % kScanSlices]
+                     : slice_best[(size_t)item * kScanSlices + threadIdx.x % kScanSlices];
+        u = top2_warp_reduce(u);
+        if (threadIdx.x == 0) emit_result(pd, pq.x, pq.y, u, ratio2, counters, matches, nn);
+      }
+    }
+    return;
+  }
   for (uint32_t item = blockIdx.x; item < n_list; item += gridDim.x) {
     const uint2 pq = list[item];
     const PairDesc pd = pairs[pq.x];

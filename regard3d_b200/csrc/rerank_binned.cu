@@ -95,11 +95,8 @@ __global__ void __launch_bounds__(256) k_bin_fill(const PairDesc* __restrict__ p
   l[ofs[(size_t)pair * cstride + c1] + slot[(size_t)(pd.q_ofs + q) * 2 + 1]] = q * 2u + 1u;
 }
 
-// warp per (pair, chunk).  Shared memory: kBinWarps x 16 rows x row_stride bytes.
-// Mapping: LANE = QUERY (32 list entries per pass), the 16 database rows of the chunk are read
-// from shared memory as warp-wide broadcasts, and every lane carries 16 independent accumulators
-// (one per row) -- the strictly ordered float accumulation of the upstream metric then has 16-way
-// instruction-level parallelism instead of one dependent chain.
+// warp per (pair, chunk).  Shared memory: kBinWarps x kChunk rows x row_stride bytes, staged once per chunk and
+// shared by every query that selected it; lane mapping: see the comment inside the kernel.
 constexpr int kBinWarps = 8;
 
 template <int DTYPE>
@@ -143,95 +140,88 @@ __global__ void __launch_bounds__(kBinWarps * 32) k_bin_rerank(const PairDesc* _
     }
   }
   __syncwarp();
-  uint32_t row_norm[kChunk];  // uint8 only: |a_r|^2 of the staged rows (every lane computes all kChunk of them)
+  // Mapping: lane = (query slot, row): 32 / kChunk queries per pass, every lane accumulates ONE exact distance
+  // (its query against row `r` of the chunk) in the strict upstream order; the chunk's top-2 of a query is a
+  // butterfly merge over its kChunk lanes ((value, index)-lexicographic, hence order independent).  Cost per pass is
+  // 1 / kChunk of a "lane = query, kChunk rows per lane" pass, so sparsely selected chunks -- the normal case once
+  // the early rejection has removed the queries that cannot match -- no longer pay for 32 query slots.
+  static_assert(kChunk == 8 || kChunk == 16, "lane mapping");
+  constexpr uint32_t kQPerPass = 32 / kChunk;
+  const uint32_t r = lane % kChunk, qslot = lane / kChunk;
+  const unsigned char* arow = rows + (size_t)r * row_stride;
+  uint32_t row_norm = 0u;  // uint8 only: |a_r|^2
   if (DTYPE != 0) {
-#pragma unroll
-    for (int r = 0; r < kChunk; ++r) {
-      uint32_t s = 0u;
-      for (uint32_t g = 0; g < (dim >> 2); ++g) {
-        const uint32_t a = *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4);
-        s = __dp4a(a, a, s);
-      }
-      row_norm[r] = s;
+    for (uint32_t g = 0; g < (dim >> 2); ++g) {
+      const uint32_t a = *(const uint32_t*)(arow + (size_t)g * 4);
+      row_norm = __dp4a(a, a, row_norm);
     }
   }
   const uint32_t* l = list + (size_t)pd.q_ofs * 2;
   const uint32_t col0 = chunk * kChunk;
   const uint32_t nvalid = (pd.nI > col0) ? min((uint32_t)kChunk, pd.nI - col0) : 0u;
-  for (uint32_t e0 = beg; e0 < end; e0 += 32) {
-    const uint32_t e = e0 + lane;
+  for (uint32_t e0 = beg; e0 < end; e0 += kQPerPass) {
+    const uint32_t e = e0 + qslot;
     const bool live = e < end;
-    const uint32_t qs = live ? __ldg(l + e) : __ldg(l + beg);  // dead lanes shadow a valid entry
+    const uint32_t qs = live ? __ldg(l + e) : __ldg(l + beg);  // dead slots shadow a valid entry
     const char* qrow = (const char*)pd.descJ + (size_t)(qs >> 1) * rb;
-    float acc[kChunk];
-#pragma unroll
-    for (int r = 0; r < kChunk; ++r) acc[r] = 0.f;
+    float acc = 0.f;
     if (DTYPE == 0) {
       const uint32_t groups = dim >> 2;
-      const bool vec_ok = (rb & 15u) == 0;
-      auto load_q = [&](uint32_t g) -> float4 {
-        if (vec_ok) return __ldg((const float4*)qrow + g);
-        const float* qf = (const float*)qrow + 4 * g;
-        return make_float4(__ldg(qf), __ldg(qf + 1), __ldg(qf + 2), __ldg(qf + 3));
-      };
-      float4 qv = groups ? load_q(0) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (uint32_t g = 0; g < groups; ++g) {
-        const float4 qn = (g + 1 < groups) ? load_q(g + 1) : qv;  // prefetch: hide the global-load latency
-#pragma unroll
-        for (int r = 0; r < kChunk; ++r) {
-          const float4 a = *(const float4*)(rows + (size_t)r * row_stride + (size_t)g * 16);  // broadcast
-          acc[r] = acc4(acc[r], __fsub_rn(qv.x, a.x), __fsub_rn(qv.y, a.y), __fsub_rn(qv.z, a.z), __fsub_rn(qv.w, a.w));
+      if ((rb & 15u) == 0) {
+#pragma unroll 4
+        for (uint32_t g = 0; g < groups; ++g) {
+          const float4 qv = __ldg((const float4*)qrow + g);
+          const float4 a = *(const float4*)(arow + (size_t)g * 16);
+          acc = acc4(acc, __fsub_rn(qv.x, a.x), __fsub_rn(qv.y, a.y), __fsub_rn(qv.z, a.z), __fsub_rn(qv.w, a.w));
         }
-        qv = qn;
+      } else {
+        for (uint32_t g = 0; g < groups; ++g) {
+          const float* qf = (const float*)qrow + 4 * g;
+          const float* af = (const float*)(arow + (size_t)g * 16);
+          acc = acc4(acc, __fsub_rn(__ldg(qf), af[0]), __fsub_rn(__ldg(qf + 1), af[1]), __fsub_rn(__ldg(qf + 2), af[2]),
+                     __fsub_rn(__ldg(qf + 3), af[3]));
+        }
       }
       for (uint32_t k = groups * 4; k < dim; ++k) {
-        const float qk = __ldg((const float*)qrow + k);
-#pragma unroll
-        for (int r = 0; r < kChunk; ++r) {
-          const float df = __fsub_rn(qk, *(const float*)(rows + (size_t)r * row_stride + (size_t)k * 4));
-          acc[r] = __fadd_rn(acc[r], __fmul_rn(df, df));
-        }
+        const float df = __fsub_rn(__ldg((const float*)qrow + k), *(const float*)(arow + (size_t)k * 4));
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
       }
     } else {
       // uint8 descriptors: every partial sum of the upstream float accumulation is an integer below 2^24
       // (dim <= 240: 240 * 255^2 < 2^24), so the float result IS the integer sum -- computed here as
-      // |q|^2 + |a|^2 - 2 q.a with one IDP4A per 4 dimensions and row instead of 4 x (I2F, FSUB, FMUL, FADD)
-      uint32_t dot[kChunk];
-#pragma unroll
-      for (int r = 0; r < kChunk; ++r) dot[r] = 0u;
-      uint32_t qn = 0u;
+      // |q|^2 + |a|^2 - 2 q.a with IDP4A instead of I2F / FSUB / FMUL / FADD per element
+      uint32_t dot = 0u, qn = 0u;
       if ((rb & 15u) == 0) {
         const uint32_t g16 = (uint32_t)(rb >> 4);
         for (uint32_t g = 0; g < g16; ++g) {
           const uint4 qv = __ldg((const uint4*)qrow + g);
+          const uint4 a = *(const uint4*)(arow + (size_t)g * 16);
           qn = __dp4a(qv.x, qv.x, qn); qn = __dp4a(qv.y, qv.y, qn); qn = __dp4a(qv.z, qv.z, qn); qn = __dp4a(qv.w, qv.w, qn);
-#pragma unroll
-          for (int r = 0; r < kChunk; ++r) {
-            const uint4 a = *(const uint4*)(rows + (size_t)r * row_stride + (size_t)g * 16);  // broadcast
-            uint32_t d = dot[r];
-            d = __dp4a(qv.x, a.x, d); d = __dp4a(qv.y, a.y, d); d = __dp4a(qv.z, a.z, d); d = __dp4a(qv.w, a.w, d);
-            dot[r] = d;
-          }
+          dot = __dp4a(qv.x, a.x, dot); dot = __dp4a(qv.y, a.y, dot); dot = __dp4a(qv.z, a.z, dot); dot = __dp4a(qv.w, a.w, dot);
         }
       } else {
         const uint32_t groups = dim >> 2;  // rb % 4 == 0 is guaranteed by the launcher
         for (uint32_t g = 0; g < groups; ++g) {
           const uint32_t qv = __ldg((const uint32_t*)qrow + g);
           qn = __dp4a(qv, qv, qn);
-#pragma unroll
-          for (int r = 0; r < kChunk; ++r)
-            dot[r] = __dp4a(qv, *(const uint32_t*)(rows + (size_t)r * row_stride + (size_t)g * 4), dot[r]);
+          dot = __dp4a(qv, *(const uint32_t*)(arow + (size_t)g * 4), dot);
         }
       }
-#pragma unroll
-      for (int r = 0; r < kChunk; ++r) acc[r] = (float)(qn + row_norm[r] - 2u * dot[r]);
+      acc = (float)(qn + row_norm - 2u * dot);
     }
     Top2 t;
     t.d1 = t.d2 = FLT_MAX; t.i1 = t.i2 = 0xffffffffu;
+    if (r < nvalid) { t.d1 = acc; t.i1 = col0 + r; }
 #pragma unroll
-    for (int r = 0; r < kChunk; ++r)
-      if ((uint32_t)r < nvalid) top2_insert(t, acc[r], col0 + r);
-    if (live) {
+    for (uint32_t o = kChunk / 2; o >= 1; o >>= 1) {
+      Top2 u;
+      u.d1 = __shfl_xor_sync(0xffffffffu, t.d1, o);
+      u.d2 = __shfl_xor_sync(0xffffffffu, t.d2, o);
+      u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o);
+      u.i2 = __shfl_xor_sync(0xffffffffu, t.i2, o);
+      t = top2_merge(t, u);
+    }
+    if (live && r == 0) {
       Part p;
       p.d1 = t.d1; p.d2 = t.d2; p.i1 = t.i1; p.i2 = t.i2;
       parts[(size_t)(pd.q_ofs + (qs >> 1)) * 2 + (qs & 1u)] = p;
