@@ -857,78 +857,94 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   if (plan) {
     using namespace r3d::ba;
     const uint32_t n_pts = p->n_pts;
-    bool ok = maxobs <= 32 && n_pts > 0;
-    // counting sort of the points by the smallest camera that sees them
-    std::vector<uint32_t> key(n_pts, 0), bucket((size_t)p->n_cams + 2, 0);
-    for (uint32_t i = 0; i < n_pts; ++i) {
-      uint32_t mn = p->n_cams;
-      for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) mn = std::min(mn, p->obs_cam[hobs[t]]);
-      key[i] = mn;
-      bucket[mn + 1]++;
-    }
-    for (size_t c = 0; c + 1 < bucket.size(); ++c) bucket[c + 1] += bucket[c];
-    h_order.resize(n_pts);
-    for (uint32_t i = 0; i < n_pts; ++i) h_order[bucket[key[i]]++] = i;
-    h_ent_start.assign((size_t)n_pts + 1, 0);
-    std::vector<int> cols, pcols;  // sorted distinct columns of the open batch / of one point
-    BatchDesc cur{0, 0, 0, 0};
-    uint32_t ent_run = 0;
-    auto close_batch = [&]() {
-      if (!cur.count) return;
-      cur.nblk = (uint32_t)cols.size();
-      h_batches.push_back(cur);
-      h_cols.resize(h_batches.size() * kBatchBlocks, 0);
-      std::copy(cols.begin(), cols.end(), h_cols.begin() + (h_batches.size() - 1) * kBatchBlocks);
-      for (uint32_t k = 0; k < cur.count; ++k) {  // local block of every entry of the batch
-        const uint32_t ip = h_order[cur.first + k];
-        int g0 = -1, g1 = -1;
-        for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+    std::atomic<int> ok{(maxobs <= 32 && n_pts > 0) ? 1 : 0};
+    const int threads = std::max(1, ctx->host_threads);
+    // (1) processing order: counting sort of the points by the smallest camera that sees them
+    std::vector<uint32_t> key(n_pts, 0), nent(n_pts, 0);
+    const uint32_t kSlab = 4096;
+    const size_t n_slabs = ((size_t)n_pts + kSlab - 1) / kSlab;
+    parallel_for(threads, n_slabs, [&](size_t sl) {
+      const uint32_t i1 = (uint32_t)std::min<size_t>((sl + 1) * kSlab, n_pts);
+      for (uint32_t i = (uint32_t)(sl * kSlab); i < i1; ++i) {
+        uint32_t mn = p->n_cams;
+        int g0 = -1, g1 = -1, ng = 0;
+        for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) {
           const uint32_t cam = p->obs_cam[hobs[t]];
-          h_lblk.push_back((unsigned char)(std::lower_bound(cols.begin(), cols.end(), (int)(6 * cam)) - cols.begin()));
+          mn = std::min(mn, cam);
+          for (uint32_t u = hofs[i]; u < t; ++u)
+            if (p->obs_cam[hobs[u]] == cam) ok.store(0);  // a camera sees the point twice
           if (refine_intr) {
-            const int gc = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
-            if (gc != g0 && gc != g1) { if (g0 < 0) g0 = gc; else g1 = gc; }
+            const int g = (int)p->cam_intr[cam];
+            if (g != g0 && g != g1) {
+              if (g0 < 0) g0 = g; else if (g1 < 0) g1 = g; else ok.store(0);  // > 2 groups
+              ++ng;
+            }
           }
         }
-        for (int gc : {g0, g1})
-          if (gc >= 0) h_lblk.push_back((unsigned char)(std::lower_bound(cols.begin(), cols.end(), gc) - cols.begin()));
+        key[i] = mn;
+        nent[i] = (hofs[i + 1] - hofs[i]) + (uint32_t)ng;
       }
-      cols.clear();
-      cur = BatchDesc{cur.first + cur.count, 0, ent_run, 0};
-    };
-    for (uint32_t k = 0; k < n_pts && ok; ++k) {
-      const uint32_t ip = h_order[k];
-      pcols.clear();
-      int ngroups = 0;
-      for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
-        const uint32_t cam = p->obs_cam[hobs[t]];
-        pcols.push_back((int)(6 * cam));
-        if (refine_intr) pcols.push_back((int)(6 * p->n_cams + 6 * p->cam_intr[cam]));
+    });
+    if (ok.load()) {
+      std::vector<uint32_t> bucket((size_t)p->n_cams + 2, 0);
+      for (uint32_t i = 0; i < n_pts; ++i) bucket[key[i] + 1]++;
+      for (size_t c = 0; c + 1 < bucket.size(); ++c) bucket[c + 1] += bucket[c];
+      h_order.resize(n_pts);
+      for (uint32_t i = 0; i < n_pts; ++i) h_order[bucket[key[i]]++] = i;
+      // (2) batches: consecutive ordered points, cut by the point and entry capacities
+      h_ent_start.assign((size_t)n_pts + 1, 0);
+      BatchDesc cur{0, 0, 0, 0};
+      uint32_t ent_run = 0;
+      for (uint32_t k = 0; k < n_pts; ++k) {
+        const uint32_t ne = nent[h_order[k]];
+        if (cur.count == (uint32_t)kBatchPoints || (ent_run - cur.ent_first) + ne > (uint32_t)kBatchEntries) {
+          h_batches.push_back(cur);
+          cur = BatchDesc{k, 0, ent_run, 0};
+        }
+        h_ent_start[k] = ent_run;
+        ent_run += ne;
+        cur.count++;
       }
-      std::sort(pcols.begin(), pcols.end());
-      for (size_t q = 1; q < pcols.size(); ++q)
-        if (pcols[q] == pcols[q - 1] && pcols[q] < (int)(6 * p->n_cams)) ok = false;  // a camera sees the point twice
-      pcols.erase(std::unique(pcols.begin(), pcols.end()), pcols.end());
-      for (int c : pcols) ngroups += c >= (int)(6 * p->n_cams);
-      if (ngroups > 2) ok = false;
-      const uint32_t nent = (hofs[ip + 1] - hofs[ip]) + (uint32_t)ngroups;
-      if (nent > (uint32_t)kBatchEntries || pcols.size() > (size_t)kBatchBlocks) ok = false;
-      if (!ok) break;
-      // would the point still fit into the open batch?
-      size_t merged = cols.size();
-      for (int c : pcols) merged += !std::binary_search(cols.begin(), cols.end(), c);
-      if (cur.count == (uint32_t)kBatchPoints || (ent_run - cur.ent_first) + nent > (uint32_t)kBatchEntries ||
-          merged > (size_t)kBatchBlocks)
-        close_batch();
-      for (int c : pcols)
-        if (!std::binary_search(cols.begin(), cols.end(), c)) cols.insert(std::lower_bound(cols.begin(), cols.end(), c), c);
-      h_ent_start[k] = ent_run;
-      ent_run += nent;
-      cur.count++;
-    }
-    if (ok) {
       h_ent_start[n_pts] = ent_run;
-      close_batch();
+      if (cur.count) h_batches.push_back(cur);
+      // (3) per batch, in parallel: sorted distinct block columns and every entry's index into them
+      h_cols.assign(h_batches.size() * kBatchBlocks, 0);
+      h_lblk.assign(ent_run, 0);
+      parallel_for(threads, h_batches.size(), [&](size_t bi) {
+        BatchDesc& bd = h_batches[bi];
+        int cols[kBatchEntries * 2];
+        int nc = 0;
+        for (uint32_t k = 0; k < bd.count; ++k) {
+          const uint32_t ip = h_order[bd.first + k];
+          for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+            const uint32_t cam = p->obs_cam[hobs[t]];
+            cols[nc++] = (int)(6 * cam);
+            if (refine_intr) cols[nc++] = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
+          }
+        }
+        std::sort(cols, cols + nc);
+        nc = (int)(std::unique(cols, cols + nc) - cols);
+        if (nc > kBatchBlocks) { ok.store(0); return; }
+        bd.nblk = (uint32_t)nc;
+        std::copy(cols, cols + nc, h_cols.begin() + bi * kBatchBlocks);
+        unsigned char* lb = h_lblk.data() + bd.ent_first;
+        for (uint32_t k = 0; k < bd.count; ++k) {
+          const uint32_t ip = h_order[bd.first + k];
+          int g0 = -1, g1 = -1;
+          for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+            const uint32_t cam = p->obs_cam[hobs[t]];
+            *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, (int)(6 * cam)) - cols);
+            if (refine_intr) {
+              const int gc = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
+              if (gc != g0 && gc != g1) { if (g0 < 0) g0 = gc; else g1 = gc; }
+            }
+          }
+          for (int gc : {g0, g1})
+            if (gc >= 0) *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, gc) - cols);
+        }
+      });
+    }
+    if (ok.load()) {
       uint32_t *d_order, *d_ent_start;
       BatchDesc* d_batches;
       int* d_cols;

@@ -87,7 +87,7 @@ static void free_worker(DeviceWorker& w) {
   w.pool_sizes.clear();
   w.pool_free_blocks.clear();
   void* ptrs[] = {w.d_pairs, w.d_items, w.d_keys, w.d_fb, w.d_nn, w.d_tmapQ, w.d_tmapD, w.d_tmapDh,
-                  w.d_cnt, w.d_slot, w.d_list, w.d_parts, w.d_list2, w.d_mdense};
+                  w.d_cnt, w.d_slot, w.d_list, w.d_parts, w.d_list2, w.d_mdense, w.d_scan};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& o : w.out) {

@@ -40,22 +40,27 @@ constexpr uint32_t kInstrDesc2 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | (
 
 }  // namespace
 
+template <bool kVote>
 __global__ void __launch_bounds__(kThreads2, 1)
 k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
                     const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
-                    uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages) {
+                    uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages,
+                    uint32_t n_qbuf) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_base = base;                                  // nkb boxes (this CTA's 128 query rows)
-  const uint32_t d_base = q_base + nkb * kBoxBytes;               // n_stages boxes
+  // n_qbuf (1 or 2) x nkb boxes: this CTA's 128 query rows.  With two buffers the next work item's query block is
+  // loaded while the current item's last tiles are still in the tensor pipe (no bubble at item boundaries).
+  const uint32_t q_base = base;
+  const uint32_t q_bytes = nkb * kBoxBytes;
+  const uint32_t d_base = q_base + n_qbuf * q_bytes;              // n_stages boxes
   const uint32_t bar_base = d_base + n_stages * kBoxBytes;
   const uint32_t bar_full = bar_base;                             // [kMaxStages2]
   const uint32_t bar_pfull = bar_full + 8 * kMaxStages2;          // [kMaxStages2] (leader)
   const uint32_t bar_empty = bar_pfull + 8 * kMaxStages2;         // [kMaxStages2]
-  const uint32_t bar_qfull = bar_empty + 8 * kMaxStages2;
-  const uint32_t bar_pqfull = bar_qfull + 8;
-  const uint32_t bar_qempty = bar_pqfull + 8;
-  const uint32_t bar_tfull = bar_qempty + 8;                      // [2]
+  const uint32_t bar_qfull = bar_empty + 8 * kMaxStages2;         // [2]
+  const uint32_t bar_pqfull = bar_qfull + 16;                     // [2] (leader)
+  const uint32_t bar_qempty = bar_pqfull + 16;                    // [2]
+  const uint32_t bar_tfull = bar_qempty + 16;                     // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                     // [2] (leader)
   const uint32_t tmem_slot = bar_tempty + 16;
   const uint32_t key_xchg = (tmem_slot + 16 + 15u) & ~15u;        // 128 rows x 8 u32: keys of the upper column half
@@ -76,9 +81,11 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
       mbar_init(bar_pfull + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_qfull, 1);
-    mbar_init(bar_pqfull, 1);
-    mbar_init(bar_qempty, 1);
+    for (uint32_t qb = 0; qb < 2; ++qb) {
+      mbar_init(bar_qfull + 8 * qb, 1);
+      mbar_init(bar_pqfull + 8 * qb, 1);
+      mbar_init(bar_qempty + 8 * qb, 1);
+    }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, 2 * kEpiWarps2);
@@ -98,23 +105,29 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
 
   if (warp == 0) {
     // ===================================== TMA producer (both CTAs) =====================================
-    uint32_t stage = 0, phase = 0, qphase = 0;
-    for (uint32_t it = cluster_id * 2 + crank; it < n_items; it += n_clusters * 2) {
+    uint32_t stage = 0, phase = 0, qi = 0;
+    for (uint32_t it = cluster_id * 2 + crank; it < n_items; it += n_clusters * 2, ++qi) {
       const WorkItem wi = items[it];
       const PairDesc pd = pairs[wi.pair];
       const CUtensorMap* mq = tmapQ + pd.slotJ;
       const CUtensorMap* md = tmapD + pd.slotI;
       const uint32_t nboxes = (pd.nI_pad / kTileN) * nkb;
       const uint32_t ahead = nboxes < n_stages ? nboxes : n_stages;
+      // query buffer of this item and how often it has been used before (barrier parity)
+      const uint32_t qb = n_qbuf == 2 ? (qi & 1u) : 0u;
+      const uint32_t quse = n_qbuf == 2 ? (qi >> 1) : qi;
+      // one buffer: run the database ring ahead first, the buffer is released by the previous item's last MMA;
+      // two buffers: the buffer was released an item ago, load it before anything else
+      const uint32_t q_at = n_qbuf == 2 ? 0u : ahead;
       uint32_t b = 0, t = 0, kb = 0;
       for (;;) {
-        if (b == ahead) {
-          mbar_wait(bar_qempty, qphase ^ 1u);
-          qphase ^= 1u;
+        if (b == q_at) {
+          mbar_wait(bar_qempty + 8 * qb, (quse & 1u) ^ 1u);
           if (elect_one()) {
-            mbar_arrive_expect_tx(bar_qfull, nkb * kBoxBytes);
+            mbar_arrive_expect_tx(bar_qfull + 8 * qb, nkb * kBoxBytes);
             for (uint32_t k2 = 0; k2 < nkb; ++k2)
-              tma_load_2d(q_base + k2 * kBoxBytes, mq, (int)(k2 * kKBlock), (int)(wi.sb * kTileRows), bar_qfull);
+              tma_load_2d(q_base + qb * q_bytes + k2 * kBoxBytes, mq, (int)(k2 * kKBlock), (int)(wi.sb * kTileRows),
+                          bar_qfull + 8 * qb);
           }
           __syncwarp();
         }
@@ -133,16 +146,17 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
       }
     }
   } else if (warp == 1) {
-    uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qf = 0;
+    uint32_t stage = 0, phase = 0, acc = 0, accphase = 0, qi = 0;
     if (leader) {
       // ============================ MMA issuer (leader CTA, cta_group::2) ============================
-      for (uint32_t it = cluster_id * 2; it < n_items; it += n_clusters * 2) {
+      for (uint32_t it = cluster_id * 2; it < n_items; it += n_clusters * 2, ++qi) {
         const WorkItem wi = items[it];
         const PairDesc pd = pairs[wi.pair];
         const uint32_t ntiles = pd.nI_pad / kTileN;
-        mbar_wait(bar_qfull, qf);
-        mbar_wait(bar_pqfull, qf);
-        qf ^= 1u;
+        const uint32_t qb = n_qbuf == 2 ? (qi & 1u) : 0u;
+        const uint32_t qf = (n_qbuf == 2 ? (qi >> 1) : qi) & 1u;
+        mbar_wait(bar_qfull + 8 * qb, qf);
+        mbar_wait(bar_pqfull + 8 * qb, qf);
         tc_fence_after();
         for (uint32_t t = 0; t < ntiles; ++t) {
           mbar_wait(bar_tempty + 8 * acc, accphase ^ 1u);  // both epilogues drained this accumulator stage
@@ -155,7 +169,7 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
             tc_fence_after();
             if (elect_one()) {
               const uint32_t b_lo = desc_lo(d_base + stage * kBoxBytes);
-              const uint32_t a_lo = desc_lo(q_base + kb * kBoxBytes);
+              const uint32_t a_lo = desc_lo(q_base + qb * q_bytes + kb * kBoxBytes);
               const uint32_t ks_here = ks_left < 4u ? ks_left : 4u;
 #pragma unroll
               for (uint32_t k = 0; k < 4; ++k) {
@@ -172,19 +186,20 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
           acc ^= 1u;
           if (acc == 0) accphase ^= 1u;
         }
-        if (elect_one()) tc2_commit_mc(bar_qempty, 3);
+        if (elect_one()) tc2_commit_mc(bar_qempty + 8 * qb, 3);
         __syncwarp();
       }
     } else {
       // ============ peer CTA: forward "my operands have landed" to the leader's barriers ============
       const uint32_t r_pqfull = mapa_shared(bar_pqfull, 0);
-      for (uint32_t it = cluster_id * 2 + 1; it < n_items; it += n_clusters * 2) {
+      for (uint32_t it = cluster_id * 2 + 1; it < n_items; it += n_clusters * 2, ++qi) {
         const WorkItem wi = items[it];
         const PairDesc pd = pairs[wi.pair];
         const uint32_t nboxes = (pd.nI_pad / kTileN) * nkb;
-        mbar_wait(bar_qfull, qf);
-        qf ^= 1u;
-        if (elect_one()) mbar_arrive_remote(r_pqfull);
+        const uint32_t qb = n_qbuf == 2 ? (qi & 1u) : 0u;
+        const uint32_t qf = (n_qbuf == 2 ? (qi >> 1) : qi) & 1u;
+        mbar_wait(bar_qfull + 8 * qb, qf);
+        if (elect_one()) mbar_arrive_remote(r_pqfull + 8 * qb);
         __syncwarp();
         for (uint32_t b = 0; b < nboxes; ++b) {
           mbar_wait(bar_full + 8 * stage, phase);
@@ -222,21 +237,21 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
         tc_wait_ld(va);
         tc_ld32(taddr + 32, vb);
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + c, keep_mask, key);
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(va + c * kChunk, chunk0 + c, keep_mask, key);
         tc_wait_ld(vb);
         tc_ld32(taddr + 64, va);
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + kCpl + c, keep_mask, key);
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(vb + c * kChunk, chunk0 + kCpl + c, keep_mask, key);
         tc_wait_ld(va);
         tc_ld32(taddr + 96, vb);
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(va + c * kChunk, chunk0 + 2 * kCpl + c, keep_mask, key);
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(va + c * kChunk, chunk0 + 2 * kCpl + c, keep_mask, key);
         tc_wait_ld(vb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update(vb + c * kChunk, chunk0 + 3 * kCpl + c, keep_mask, key);
+        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(vb + c * kChunk, chunk0 + 3 * kCpl + c, keep_mask, key);
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
       }
@@ -282,8 +297,8 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
   }
 }
 
-static int ring_stages2(int nkb) {
-  int stages = (int)((232448 - 8192 - (size_t)nkb * kBoxBytes) / kBoxBytes);
+static int ring_stages2(int nkb, int n_qbuf) {
+  int stages = (int)((232448 - 8192 - (size_t)n_qbuf * nkb * kBoxBytes) / kBoxBytes);
   if (stages > kMaxStages2) stages = kMaxStages2;
   const char* e = getenv("R3D_K1_STAGES");
   if (e && atoi(e) >= 2 && atoi(e) < stages) stages = atoi(e);
@@ -296,9 +311,20 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
   if (n_items & 1u) return fail(ctx, R3D_ERR_INVALID, "2-SM candidate kernel needs an even number of work items");
   const int nkb = (kp_cols + kKBlock - 1) / kKBlock;
   if (nkb > kMaxKBlocks) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor dimension too large for the tensor-core path");
-  const int stages = ring_stages2(nkb);
-  const size_t smem = 1024 + (size_t)(nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 3 + 4) + 32 + 16 + 128 * 8 * 4;
-  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_l2_candidates_2sm, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+  static const int want_qbuf = []() {  // R3D_K1_QBUF=1: single query buffer (A/B switch)
+    const char* e = getenv("R3D_K1_QBUF");
+    return (e && atoi(e) == 1) ? 1 : 2;
+  }();
+  int n_qbuf = want_qbuf;
+  if (ring_stages2(nkb, n_qbuf) < 4) n_qbuf = 1;  // very wide descriptors: keep the ring deep enough instead
+  const int stages = ring_stages2(nkb, n_qbuf);
+  const size_t smem = 1024 + (size_t)(n_qbuf * nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 6 + 4) + 32 + 16 + 128 * 8 * 4;
+  static const bool vote = []() {  // R3D_K1_VOTE=0: always run the insertion network (A/B switch)
+    const char* e = getenv("R3D_K1_VOTE");
+    return !(e && atoi(e) == 0);
+  }();
+  auto kernel = vote ? k_l2_candidates_2sm<true> : k_l2_candidates_2sm<false>;
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   uint32_t grid = (uint32_t)w.sm_count / 2 * 2;
   if (n_items < grid) grid = n_items;
   cudaLaunchConfig_t cfg{};
@@ -313,8 +339,9 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  R3D_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, k_l2_candidates_2sm, (const CUtensorMap*)w.d_tmapQ, (const CUtensorMap*)w.d_tmapD,
-                                       d_pairs, d_items, n_items, d_keys, (uint32_t)nkb, (uint32_t)ksteps, (uint32_t)stages));
+  R3D_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kernel, (const CUtensorMap*)w.d_tmapQ, (const CUtensorMap*)w.d_tmapD,
+                                       d_pairs, d_items, n_items, d_keys, (uint32_t)nkb, (uint32_t)ksteps, (uint32_t)stages,
+                                       (uint32_t)n_qbuf));
   return R3D_OK;
 }
 

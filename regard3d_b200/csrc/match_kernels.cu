@@ -127,9 +127,10 @@ __global__ void __launch_bounds__(256) k_exact_scan(const PairDesc* __restrict__
       __syncthreads();
       if (s_last && threadIdx.x < 32) {  // every slice of the item has been published
         __threadfence();
-        Top2 u = ((volatile Top2*)slice_best)[(size_t)item * kScanSlices + threadIdx.x % kScanSlices].d1 == 0.f
-                     ? slice_best[(size_t)item * kScanSlices + threadIdx.x % kScanSlices]
-                     : slice_best[(size_t)item * kScanSlices + threadIdx.x % kScanSlices];
+        static_assert(sizeof(Top2) == sizeof(uint4) && kScanSlices == 32, "one slice per lane");
+        const uint4 raw = __ldcg((const uint4*)slice_best + (size_t)item * kScanSlices + threadIdx.x);  // L2, not L1
+        Top2 u;
+        u.d1 = __uint_as_float(raw.x); u.d2 = __uint_as_float(raw.y); u.i1 = raw.z; u.i2 = raw.w;
         u = top2_warp_reduce(u);
         if (threadIdx.x == 0) emit_result(pd, pq.x, pq.y, u, ratio2, counters, matches, nn);
       }
@@ -349,12 +350,23 @@ int launch_exact_scan(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, co
                       const uint32_t* d_list_count, uint32_t max_list, uint32_t dim, int dtype, float ratio2,
                       uint32_t* d_counters, uint2* d_matches, float4* d_nn) {
   if (max_list == 0) return R3D_OK;
-  const uint32_t grid = max_list < (uint32_t)(w.sm_count * 8) ? max_list : (uint32_t)(w.sm_count * 8);
+  // scratch of the split mode: partial top-2 per (item, slice) + per-item arrival counters (zeroed per launch)
+  const size_t best_bytes = (size_t)kScanSplitMaxItems * kScanSlices * sizeof(Top2);
+  const size_t need = best_bytes + (size_t)kScanSplitMaxItems * sizeof(uint32_t);
+  int rc = ensure_capacity<unsigned char>(ctx, &w.d_scan, &w.scan_cap, need);
+  if (rc) return rc;
+  Top2* slice_best = (Top2*)w.d_scan;
+  uint32_t* slice_done = (uint32_t*)((unsigned char*)w.d_scan + best_bytes);
+  R3D_CUDA_TRY(ctx, cudaMemsetAsync(slice_done, 0, (size_t)kScanSplitMaxItems * sizeof(uint32_t), w.stream));
+  const uint32_t want = max_list < kScanSplitMaxItems ? max_list * kScanSlices : max_list;
+  const uint32_t grid = want < (uint32_t)(w.sm_count * 8) ? want : (uint32_t)(w.sm_count * 8);
   const size_t smem = (dtype == 0 ? (size_t)dim * 4 : (size_t)dim) + 16;
   if (dtype == 0)
-    k_exact_scan<0><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn);
+    k_exact_scan<0><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn,
+                                                   slice_best, slice_done);
   else
-    k_exact_scan<1><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn);
+    k_exact_scan<1><<<grid, 256, smem, w.stream>>>(d_pairs, d_list, d_list_count, dim, ratio2, d_counters, d_matches, d_nn,
+                                                   slice_best, slice_done);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

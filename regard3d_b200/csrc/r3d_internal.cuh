@@ -113,7 +113,8 @@ struct DeviceWorker {
   void* d_list = nullptr; size_t list_cap = 0;
   void* d_parts = nullptr; size_t parts_cap = 0;
   void* d_list2 = nullptr; size_t list2_cap = 0;
-  void* d_mdense = nullptr; size_t mdense_cap = 0;  // (i, j) per pair segment, before packing
+  void* d_mdense = nullptr; size_t mdense_cap = 0;
+  void* d_scan = nullptr; size_t scan_cap = 0;      // split exact scan: partial top-2s + arrival counters  // (i, j) per pair segment, before packing
   r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
 };
 

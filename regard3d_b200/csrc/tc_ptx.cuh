@@ -134,6 +134,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t lo) { return ((uint64_t)k
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(kTileRows >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
 
 // minimum of kChunk accumulator columns, packed with the chunk id, inserted into the sorted key set
+template <bool kVote = false>
 __device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_id, uint32_t keep_mask,
                                              float (&key)[kNumKeys]) {
   static_assert(kChunk == 8 || kChunk == 16, "chunk width");
@@ -148,6 +149,10 @@ __device__ __forceinline__ void chunk_update(const uint32_t* v, uint32_t chunk_i
   }
   m = fminf(m, __uint_as_float(v[kChunk - 1]));
   float x = __uint_as_float((__float_as_uint(m) & keep_mask) | chunk_id);
+  // A key that is not below the current largest kept key leaves the set unchanged (the network would carry it
+  // through every level).  After t chunks a lane inserts with probability ~ kNumKeys / t, so most chunks need no
+  // insertion in ANY lane of the warp: one vote skips the 11-instruction network (warp-uniform branch).
+  if (kVote && !__any_sync(0xffffffffu, x < key[kNumKeys - 1])) return;
 #pragma unroll
   for (int i = 0; i < kNumKeys - 1; ++i) {  // sorted insertion network: 2 FMNMX per level
     const float hi = fmaxf(key[i], x);
