@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
 constexpr int kBatchPoints = 24;    // points per CTA batch (upper bound; the host cuts batches)
 constexpr int kBatchEntries = 144;  // entries per batch
 constexpr int kBatchBlocks = 40;    // distinct 6-wide blocks per batch
-constexpr int kEntryDoubles = 66;   // W 18 | WV 18 | WVg 6 | Jc 12 | Jg 12
+constexpr int kEntryDoubles = 72;   // W 18 | WV 18 | WVg 6 | Jc 12 | Jg 12 | Jp 6
 constexpr size_t kBatchSmemBytes = ((size_t)kBatchEntries * kEntryDoubles + (size_t)kBatchPoints * 2 * 36) * sizeof(double);
 // Static structure of a batch, built once per problem on the host (setup_problem): the processing order, the
 // first entry of every ordered point (entries of a point: its observations in CSR order, then its distinct
@@ -468,45 +468,57 @@ __global__ void __launch_bounds__(256, 2) k_ba_schur_batched(Dev d, BatchTables 
     const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
     const double Vg[3] = {Vi[0] * gp[0] + Vi[1] * gp[1] + Vi[2] * gp[2], Vi[3] * gp[0] + Vi[4] * gp[1] + Vi[5] * gp[2],
                           Vi[6] * gp[0] + Vi[7] * gp[1] + Vi[8] * gp[2]};
-    double Wg[18];  // this observation's group block (zero for absent lanes / fixed intrinsics)
-    for (int q = 0; q < 18; ++q) Wg[q] = 0.0;
     if (has) {  // camera entry of observation `lane`
       double* en = ent + (size_t)(e0 + lane) * kEntryDoubles;
+#pragma unroll
       for (int i = 0; i < 6; ++i) {
         double w3[3];
+#pragma unroll
         for (int j = 0; j < 3; ++j) {
           w3[j] = Jc[i] * Jp[j] + Jc[6 + i] * Jp[3 + j];
           en[3 * i + j] = w3[j];
-          if (colg >= 0) Wg[3 * i + j] = Jg[i] * Jp[j] + Jg[6 + i] * Jp[3 + j];
         }
+#pragma unroll
         for (int j = 0; j < 3; ++j) en[18 + 3 * i + j] = w3[0] * Vi[j] + w3[1] * Vi[3 + j] + w3[2] * Vi[6 + j];
         en[36 + i] = w3[0] * Vg[0] + w3[1] * Vg[1] + w3[2] * Vg[2];
       }
+#pragma unroll
       for (int q = 0; q < 12; ++q) { en[42 + q] = Jc[q]; en[54 + q] = Jg[q]; }
+#pragma unroll
+      for (int q = 0; q < 6; ++q) en[66 + q] = Jp[q];
       s_ggidx[e0 + lane] = -2 - colg;
     }
-    // group entries: masked warp reductions of Wg and Jg^T Jg over the lanes of each distinct group (<= 2)
+    __syncwarp();
+    // group entries (<= 2 distinct groups per point): W_g = sum_t Jg_t^T Jp_t and GG = sum_t Jg_t^T Jg_t over the
+    // observations of the group, ONE output element per lane, reading the camera entries just written
     if (d.refine_intr) {
       unsigned todo = __ballot_sync(0xffffffffu, has);
       int gslot = 0;
       while (todo) {
         const int leader = __ffs(todo) - 1;
         const int gcol = __shfl_sync(0xffffffffu, colg, leader);
-        const bool mine = has && colg == gcol;
-        const unsigned members = __ballot_sync(0xffffffffu, mine);
-        todo &= ~members;
+        todo &= ~__ballot_sync(0xffffffffu, has && colg == gcol);
         double* en = ent + (size_t)(e0 + nobs + gslot) * kEntryDoubles;
         double* G = gg + (size_t)(2 * k + gslot) * 36;
-        for (int q = 0; q < 18; ++q) {
-          double x = mine ? Wg[q] : 0.0;
-          for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-          if (lane == 0) en[q] = x;
-        }
-        for (int q = 0; q < 36; ++q) {
-          const int i = q / 6, j = q % 6;
-          double x = mine ? (Jg[i] * Jg[j] + Jg[6 + i] * Jg[6 + j]) : 0.0;
-          for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-          if (lane == 0) G[q] = x;
+        for (int q = lane; q < 54; q += 32) {  // 18 elements of W_g, then 36 of GG
+          double acc = 0.0;
+          if (q < 18) {
+            const int i = q / 3, j = q % 3;
+            for (int t = 0; t < nobs; ++t) {
+              if (s_ggidx[e0 + t] != -2 - gcol) continue;
+              const double* et = ent + (size_t)(e0 + t) * kEntryDoubles;
+              acc += et[54 + i] * et[66 + j] + et[60 + i] * et[69 + j];
+            }
+            en[q] = acc;
+          } else {
+            const int i = (q - 18) / 6, j = (q - 18) % 6;
+            for (int t = 0; t < nobs; ++t) {
+              if (s_ggidx[e0 + t] != -2 - gcol) continue;
+              const double* et = ent + (size_t)(e0 + t) * kEntryDoubles;
+              acc += et[54 + i] * et[54 + j] + et[60 + i] * et[60 + j];
+            }
+            G[q - 18] = acc;
+          }
         }
         __syncwarp();
         if (lane < 6) {  // WV and WVg of the merged group block

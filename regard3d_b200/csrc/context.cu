@@ -95,6 +95,7 @@ static void free_worker(DeviceWorker& w) {
     if (o.d_counters) cudaFree(o.d_counters);
     if (o.h_counters) cudaFreeHost(o.h_counters);
     if (o.h_matches) cudaFreeHost(o.h_matches);
+    if (o.h_stage) cudaFreeHost(o.h_stage);
     for (auto& e : o.ev)
       if (e) cudaEventDestroy(e);
   }

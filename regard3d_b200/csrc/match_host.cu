@@ -211,9 +211,20 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       if ((rc = ensure_capacity<float4>(ctx, &w.d_nn, &w.nn_cap, rows))) return rc;
     }
     // (re)allocations above are synchronous w.r.t. the device: previously enqueued work is done
-    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, hp->data(), nb * sizeof(PairDesc), cudaMemcpyHostToDevice, w.stream));
-    if (any_tc)
-      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, hitems->data(), hitems->size() * sizeof(WorkItem), cudaMemcpyHostToDevice, w.stream));
+    {  // uploads out of the slot's pinned staging buffer: truly asynchronous, the GPU keeps two batches queued
+      const size_t pb = (size_t)nb * sizeof(PairDesc), ib = hitems->size() * sizeof(WorkItem);
+      if (o.h_stage_cap < pb + ib) {
+        if (o.h_stage) cudaFreeHost(o.h_stage);
+        o.h_stage = nullptr;
+        o.h_stage_cap = 0;
+        R3D_CUDA_TRY(ctx, cudaMallocHost(&o.h_stage, (pb + ib) * 2));
+        o.h_stage_cap = (pb + ib) * 2;
+      }
+      std::memcpy(o.h_stage, hp->data(), pb);
+      std::memcpy((char*)o.h_stage + pb, hitems->data(), ib);
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, o.h_stage, pb, cudaMemcpyHostToDevice, w.stream));
+      if (any_tc) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, (char*)o.h_stage + pb, ib, cudaMemcpyHostToDevice, w.stream));
+    }
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(o.d_counters, 0, (16 + nb) * sizeof(uint32_t), w.stream));
     uint64_t launches = 0;
 

@@ -80,6 +80,8 @@ struct OutSlot {  // double-buffered outputs of a matching batch
   uint32_t* d_counters = nullptr;  // [1] exact-scan list, [3] stage C, [4] deferred by stage A, [16 + k] matches of pair k
   uint32_t* h_counters = nullptr;  // pinned
   void* h_matches = nullptr; size_t h_matches_cap = 0;  // pinned
+  void* h_stage = nullptr; size_t h_stage_cap = 0;      // pinned: PairDesc[] + WorkItem[] of the batch (a pageable
+                                                        // source would make the "async" upload wait for the stream)
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

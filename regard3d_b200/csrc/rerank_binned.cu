@@ -279,7 +279,11 @@ int launch_rerank_binned(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   if (n_pairs == 0 || max_nJ == 0) return R3D_OK;
   const size_t rb = dtype == 0 ? (size_t)dim * 4 : (size_t)dim;
   if (rb & 3) return fail(ctx, R3D_ERR_UNSUPPORTED, "binned re-rank needs row bytes % 4 == 0");
-  const uint32_t row_stride = (uint32_t)((rb + 15) / 16 * 16);  // rows are only read as broadcasts
+  // Row pitch in shared memory: a quarter-warp (8 lanes) reads 16 bytes of 8 DIFFERENT rows per LDS.128, so the pitch
+  // in 4-byte words must be 4 * odd (mod 32) for the eight 4-bank groups to be distinct (a pitch of 576 B = 144
+  // words = 16 mod 32 was a 4-way bank conflict and made the kernel L1/shared-pipe bound at 98 %).
+  uint32_t row_stride = (uint32_t)((rb + 15) / 16 * 16);
+  while (((row_stride / 4) % 32) % 8 != 4) row_stride += 16;
   const size_t smem = (size_t)kBinWarps * kChunk * row_stride;
   R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_cnt, 0, (size_t)n_pairs * cstride * sizeof(uint32_t), w.stream));
   dim3 gq((max_nJ + 255) / 256, n_pairs);
