@@ -60,13 +60,14 @@ struct EventTimer {
 //  results[k]   : matches of pairs[k] (empty if none)
 //  nn_out       : optional, for r3d_search_neighbours (single pair): float4 per query
 static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs, uint64_t n_pairs, float ratio,
-                           uint32_t flags, std::vector<std::vector<r3d_indmatch>>& results,
+                           uint32_t flags, std::vector<r3d_span>& results, std::vector<r3d_slab>& slabs,
                            std::vector<float4>* nn_out, std::vector<uint4>* keys_dbg = nullptr) {
   const double t_enter = now_ms();
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   int rc = prepare_views(ctx, w);
   if (rc) return rc;
-  results.assign(n_pairs, {});
+  results.assign(n_pairs, r3d_span{});
+  std::mutex slab_mutex;
   const float ratio2 = ratio * ratio;  // Square(fDistRatio): b_squared_metric = true for BRUTE_FORCE_L2
   const bool want_matches = (nn_out == nullptr);
 
@@ -335,17 +336,25 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         if (e != cudaSuccess) return bail("match copy", e);
       }
       const double t0 = now_ms();
-      // out of the pinned buffer (uint2 (i, j) == r3d_indmatch), so that the slot can be handed to batch b+2
-      std::vector<r3d_indmatch> bucket(n_matches);
-      if (n_matches) std::memcpy(bucket.data(), os.h_matches, bytes);
+      // out of the pinned buffer (uint2 (i, j) == r3d_indmatch) into the batch's result slab, so that the slot can
+      // be handed to batch b+2; the pairs are de-duplicated in place and the result spans point into the slab
+      std::shared_ptr<r3d_indmatch[]> bucket_owner(new r3d_indmatch[std::max<size_t>(n_matches, 1)]);  // not zero-filled
+      r3d_indmatch* bucket = bucket_owner.get();
+      r3d_slab slab = bucket_owner;
+      if (n_matches) std::memcpy(bucket, os.h_matches, bytes);
       release();  // the slot's device + pinned buffers may be reused by batch b+2
+      {
+        std::lock_guard<std::mutex> lk(slab_mutex);
+        slabs.push_back(slab);
+      }
       parallel_for(nthreads, nb, [&](size_t k) {
         if (cnt[k + 1] == cnt[k]) return;
-        std::vector<r3d_indmatch> v(bucket.begin() + cnt[k], bucket.begin() + cnt[k + 1]);
         const ViewDev& vi = w.views.find((*hp)[k].I)->second;
         const ViewDev& vj = w.views.find((*hp)[k].J)->second;
-        post_process_pair(v, vi.has_xy ? vi.h_xy.data() : nullptr, vj.has_xy ? vj.h_xy.data() : nullptr, cd);
-        results[all[base + k].src_index] = std::move(v);
+        r3d_indmatch* seg = bucket + cnt[k];
+        const size_t n = post_process_pair(seg, cnt[k + 1] - cnt[k], vi.has_xy ? vi.h_xy.data() : nullptr,
+                                           vj.has_xy ? vj.h_xy.data() : nullptr, cd);
+        results[all[base + k].src_index] = r3d_span{seg, n};
       });
       const double host_ms = now_ms() - t0;
       std::lock_guard<std::mutex> lk(t_mutex);
@@ -407,16 +416,17 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
     }
   }
   cut[nw] = n_pairs;
-  std::vector<std::vector<std::vector<r3d_indmatch>>> res(nw);
+  std::vector<std::vector<r3d_span>> res(nw);
+  std::vector<std::vector<r3d_slab>> res_slabs(nw);
   std::vector<int> rcs(nw, R3D_OK);
   if (nw == 1) {
-    rcs[0] = match_on_worker(ctx, ctx->workers[0], pairs, n_pairs, dist_ratio, flags, res[0], nullptr);
+    rcs[0] = match_on_worker(ctx, ctx->workers[0], pairs, n_pairs, dist_ratio, flags, res[0], res_slabs[0], nullptr);
   } else {
     std::vector<std::thread> th;
     for (size_t k = 0; k < nw; ++k)
       th.emplace_back([&, k]() {
         rcs[k] = match_on_worker(ctx, ctx->workers[k], pairs + 2 * cut[k], cut[k + 1] - cut[k], dist_ratio, flags,
-                                 res[k], nullptr);
+                                 res[k], res_slabs[k], nullptr);
       });
     for (auto& t : th) t.join();
   }
@@ -445,7 +455,7 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
   }
   // assemble the PairWiseMatches map (sorted by (I,J); empty pairs are not inserted)
   const double t_assemble = now_ms();
-  struct Entry { uint32_t I, J; std::vector<r3d_indmatch>* v; };
+  struct Entry { uint32_t I, J; r3d_span* v; };
   std::vector<Entry> entries;
   for (size_t k = 0; k < nw; ++k)
     for (uint64_t p = 0; p < res[k].size(); ++p)
@@ -458,8 +468,9 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
   m->per.reserve(entries.size());
   for (size_t e = 0; e < entries.size(); ++e) {
     if (e > 0 && entries[e].I == entries[e - 1].I && entries[e].J == entries[e - 1].J) continue;  // map::insert keeps the first
-    m->push(entries[e].I, entries[e].J, std::move(*entries[e].v));
+    m->push_span(entries[e].I, entries[e].J, *entries[e].v);
   }
+  for (auto& sl : res_slabs) m->slabs.insert(m->slabs.end(), sl.begin(), sl.end());
   if (getenv("R3D_DEBUG_TIMING"))
     fprintf(stderr, "[r3d] r3d_match_pairs total %.2f ms (assembly %.2f ms)\n", now_ms() - t_call, now_ms() - t_assemble);
   *out = m;
@@ -474,12 +485,13 @@ int r3d_search_neighbours(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query, i
   if (iI->second.n < 2 || iJ->second.n < 1)
     return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: NN > number of database rows (upstream returns false)");
   const uint32_t pr[2] = {view_db, view_query};
-  std::vector<std::vector<r3d_indmatch>> dummy;
+  std::vector<r3d_span> dummy;
+  std::vector<r3d_slab> dummy_slabs;
   std::vector<float4> nn;
   if (iI->second.dim != iJ->second.dim || iI->second.dtype != iJ->second.dtype)
     return fail(ctx, R3D_ERR_INVALID, "r3d_search_neighbours: descriptor type mismatch");
   w.timing = r3d_match_timing{};
-  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, &nn);
+  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, dummy_slabs, &nn);
   if (rc) return rc;
   ctx->match_timing = w.timing;
   const uint32_t nq = iJ->second.n;
@@ -503,10 +515,11 @@ int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query
   auto iI = w.views.find(view_db), iJ = w.views.find(view_query);
   if (iI == w.views.end() || iJ == w.views.end()) return fail(ctx, R3D_ERR_INVALID, "r3d_debug_candidate_keys: unknown view");
   const uint32_t pr[2] = {view_db, view_query};
-  std::vector<std::vector<r3d_indmatch>> dummy;
+  std::vector<r3d_span> dummy;
+  std::vector<r3d_slab> dummy_slabs;
   std::vector<float4> nn;
   std::vector<uint4> k;
-  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, &nn, &k);
+  int rc = match_on_worker(ctx, w, pr, 1, 1.0f, R3D_MATCH_DEFAULT, dummy, dummy_slabs, &nn, &k);
   if (rc) return rc;
   std::memcpy(keys, k.data(), k.size() * sizeof(uint4));
   if (eps_abs) *eps_abs = pair_eps(iI->second, iJ->second);

@@ -35,16 +35,16 @@ struct XYLess {
 };
 }  // namespace
 
-void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const float* xyJ, bool coord_dedup) {
-  std::sort(m.begin(), m.end(), [](const r3d_indmatch& a, const r3d_indmatch& b) {
+// in place on m[0..n); returns the new count
+size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ, bool coord_dedup) {
+  std::sort(m, m + n, [](const r3d_indmatch& a, const r3d_indmatch& b) {
     return a.i < b.i || (a.i == b.i && a.j < b.j);
   });
-  m.erase(std::unique(m.begin(), m.end(),
-                      [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }),
-          m.end());
-  if (!coord_dedup || !xyI || !xyJ) return;
-  std::vector<XYMatch> dec(m.size());
-  for (size_t k = 0; k < m.size(); ++k) {
+  n = (size_t)(std::unique(m, m + n, [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }) - m);
+  if (!coord_dedup || !xyI || !xyJ) return n;
+  thread_local std::vector<XYMatch> dec;  // scratch reused across pairs: no allocation per pair
+  dec.resize(n);
+  for (size_t k = 0; k < n; ++k) {
     dec[k].x1 = xyI[2 * (size_t)m[k].i];
     dec[k].y1 = xyI[2 * (size_t)m[k].i + 1];
     dec[k].x2 = xyJ[2 * (size_t)m[k].j];
@@ -57,9 +57,10 @@ void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const flo
   std::pmr::monotonic_buffer_resource arena(arena_buf.data(), arena_buf.size());
   {
     std::pmr::set<XYMatch, XYLess> uniq(dec.begin(), dec.end(), XYLess(), &arena);
-    m.clear();
-    for (const auto& d : uniq) m.push_back(d.im);
+    n = 0;
+    for (const auto& d : uniq) m[n++] = d.im;
   }
+  return n;
 }
 
 }  // namespace r3d

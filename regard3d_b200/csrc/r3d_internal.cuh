@@ -215,7 +215,7 @@ int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pai
                             uint2* d_list, uint32_t* d_list_count);
 
 // host post-processing (match_post.cpp)
-void post_process_pair(std::vector<r3d_indmatch>& m, const float* xyI, const float* xyJ,
+size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ,
                        bool coord_dedup);
 
 // driver entry points
