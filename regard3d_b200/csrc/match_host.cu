@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <future>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -55,6 +56,57 @@ struct EventTimer {
 };
 
 }  // namespace
+
+// ---- result slabs ------------------------------------------------------------------------------------
+// Every batch hands its de-duplicated matches over in one buffer that the returned r3d_matches keeps alive.
+// Allocating these (3 MB each at C2, mmap-sized) afresh on every call made every other call 15-25 ms slower
+// (page faults + munmap under the process-wide mm lock, with 30+ host threads running): buffers are recycled
+// through a bounded process-wide free list instead; the shared_ptr deleter returns them.
+namespace {
+struct SlabPool {
+  std::mutex mu;
+  std::multimap<size_t, r3d_indmatch*> free_list;  // capacity (elements) -> buffer
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCachedBytes = (size_t)2 << 30;
+  r3d_indmatch* take(size_t n, size_t* cap) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto it = free_list.lower_bound(n);
+      if (it != free_list.end() && it->first <= 2 * n + 4096) {
+        r3d_indmatch* p = it->second;
+        *cap = it->first;
+        cached_bytes -= it->first * sizeof(r3d_indmatch);
+        free_list.erase(it);
+        return p;
+      }
+    }
+    *cap = n + n / 4 + 1024;
+    return new r3d_indmatch[*cap];  // not zero-filled
+  }
+  void give(r3d_indmatch* p, size_t cap) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (cached_bytes + cap * sizeof(r3d_indmatch) <= kMaxCachedBytes) {
+        free_list.insert({cap, p});
+        cached_bytes += cap * sizeof(r3d_indmatch);
+        return;
+      }
+    }
+    delete[] p;
+  }
+};
+SlabPool& slab_pool() {
+  static SlabPool* p = new SlabPool();  // leaked on purpose: results may outlive static destruction order
+  return *p;
+}
+r3d_slab acquire_slab(size_t n, r3d_indmatch** out) {
+  size_t cap = 0;
+  r3d_indmatch* p = slab_pool().take(std::max<size_t>(n, 1), &cap);
+  *out = p;
+  return r3d_slab((void*)p, [cap](void* q) { slab_pool().give((r3d_indmatch*)q, cap); });
+}
+}  // namespace
+
 
 // Runs the device pipeline for a list of pairs on one worker.
 //  results[k]   : matches of pairs[k] (empty if none)
@@ -338,9 +390,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       const double t0 = now_ms();
       // out of the pinned buffer (uint2 (i, j) == r3d_indmatch) into the batch's result slab, so that the slot can
       // be handed to batch b+2; the pairs are de-duplicated in place and the result spans point into the slab
-      std::shared_ptr<r3d_indmatch[]> bucket_owner(new r3d_indmatch[std::max<size_t>(n_matches, 1)]);  // not zero-filled
-      r3d_indmatch* bucket = bucket_owner.get();
-      r3d_slab slab = bucket_owner;
+      r3d_indmatch* bucket = nullptr;
+      r3d_slab slab = acquire_slab(n_matches, &bucket);  // recycled storage: no mmap / page faults in steady state
       if (n_matches) std::memcpy(bucket, os.h_matches, bytes);
       release();  // the slot's device + pinned buffers may be reused by batch b+2
       {
