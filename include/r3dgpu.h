@@ -234,6 +234,10 @@ typedef struct {
 } r3d_filter_timing;
 int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out);
 
+/* Diagnostics (host only, no GPU needed): IndMatch::getDeduplicated + IndMatchDecorator::getDeduplicated of one
+ * pair, in place; returns the new count.  The CPU test pins it against std::set. */
+int64_t r3d_debug_post_process(r3d_indmatch* m, int64_t n, const float* xyI, const float* xyJ, int coord_dedup);
+
 /* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
  * 6 keys ascending + 2 unused)
  * the tensor-core pass produced for (view_db, view_query), and the pair's error bound. */

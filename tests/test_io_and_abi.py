@@ -86,3 +86,32 @@ def test_matches_txt_format_and_roundtrip(oracle, r3dlib, tmp_path):
     back = r3dlib.Matches.load_txt(p_r3).to_dict()
     assert sorted(back.keys()) == [(0, 2), (1, 2)]
     assert back[(1, 2)]["j"].tolist() == [2, 4, 9]
+
+
+def test_coordinate_dedup_replay_equals_std_set(r3dlib, oracle):
+    """The host tail replays libstdc++'s std::set range insertion on a compact node array (match_post.cpp).  The
+    comparator is not a strict weak ordering, so the outcome depends on the exact tree procedure: pin the replay
+    against the real std::set (the oracle's coord_dedup) on adversarial inputs -- few distinct x / y values, shared
+    keypoints, exact duplicates -- and on plain random ones."""
+    import ctypes as C
+    lib = r3dlib.lib()
+    rng = np.random.default_rng(12)
+    for trial in range(300):
+        n_feat = int(rng.integers(2, 400))
+        levels = int(rng.choice([2, 3, 5, 17, 1000]))
+        xyI = (rng.integers(0, levels, (n_feat, 2)) * 1.5).astype(np.float32)
+        xyJ = (rng.integers(0, levels, (n_feat, 2)) * 0.75).astype(np.float32)
+        n = int(rng.integers(1, 1200))
+        m = np.zeros(n, r3dlib.indmatch_dtype)
+        m["i"] = rng.integers(0, n_feat, n)
+        m["j"] = rng.integers(0, n_feat, n)
+        # the reference's order of operations: (i,j) sort + unique, then the coordinate set
+        exp = np.unique(np.stack([m["i"], m["j"]], 1), axis=0)
+        e = np.zeros(len(exp), r3dlib.indmatch_dtype)
+        e["i"], e["j"] = exp[:, 0], exp[:, 1]
+        want = oracle.coord_dedup(e, xyI, xyJ)
+        got = m.copy()
+        k = lib.r3d_debug_post_process(got.ctypes.data_as(C.c_void_p), C.c_int64(n), xyI.ctypes.data_as(C.c_void_p),
+                                       xyJ.ctypes.data_as(C.c_void_p), 1)
+        assert k == len(want), (trial, k, len(want))
+        assert np.array_equal(got[:k], want), trial
