@@ -110,6 +110,19 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def effective_cpus():
+    """Host CPUs this process may actually use: the affinity mask, cut by the cgroup CPU-time quota (the GPU boxes
+    give a container ~16 CPUs of quota per GPU although 128 hardware threads are visible)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(round(int(q) / int(per)))))
+    except Exception:
+        pass
+    return n
+
+
 def measured_traffic_per_pair():
     """DRAM bytes per image pair of the candidate kernel, from the committed `ncu --set full` capture of one
     128-pair launch (profiles/r01_k_l2_candidates_2sm_keymetrics.csv); None when the file is absent."""
@@ -153,15 +166,15 @@ def run_reference(args, rank, world, emit):
             times.append(dt)
     total = sum(times)
     value = len(sample) * len(times) / total
-    cores = min(nthreads, len(sample))
+    cores = min(nthreads, len(sample), effective_cpus())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d pairs (I=0, J=1..%d) of the set per step, omp over J, %d threads"
-                                   % (len(sample), len(sample), nthreads)},
+                         "sample": "%d pairs (I=0, J=1..%d) of the set per step, omp over J, %d threads on %d usable CPUs "
+                                   "(cgroup quota)" % (len(sample), len(sample), nthreads, effective_cpus())},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -360,7 +373,7 @@ def main():
             so, to = po.bundle_adjust(c, o)
             tcb = time.perf_counter() - tc0
             ba["cpu_baseline"] = {"iters_per_s": so["iterations"] / tcb, "iterations": int(so["iterations"]),
-                                  "cores": po.num_threads(), "kind": "port",
+                                  "cores": min(po.num_threads(), effective_cpus()), "kind": "port",
                                   "cost_trace_rel_diff": float(np.max(np.abs(tg[:len(to)] - to) / to))}
 
     if world > 1:
@@ -421,10 +434,11 @@ def main():
                 g = got.get((int(I), int(J)))
                 same &= (g is not None and len(g) == len(e) and set(zip(g["i"].tolist(), g["j"].tolist())) ==
                          set(zip(e["i"].tolist(), e["j"].tolist()))) or (g is None and len(e) == 0)
-            line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s", "cores": min(nthreads, len(sample)),
+            line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s",
+                                    "cores": min(nthreads, len(sample), effective_cpus()),
                                     "kind": "port",
-                                    "sample": "%d pairs (I=0) of the same set, one pass, %d omp threads, %.1f s"
-                                              % (len(sample), nthreads, tc),
+                                    "sample": "%d pairs (I=0) of the same set, one pass, %d omp threads on %d usable CPUs "
+                                              "(cgroup quota), %.1f s" % (len(sample), nthreads, effective_cpus(), tc),
                                     "parity_on_sample": bool(same)}
         emit(line)
     if world > 1:

@@ -237,6 +237,9 @@ int r3d_get_filter_timing(const r3d_ctx* ctx, r3d_filter_timing* out);
 /* Diagnostics (host only, no GPU needed): IndMatch::getDeduplicated + IndMatchDecorator::getDeduplicated of one
  * pair, in place; returns the new count.  The CPU test pins it against std::set. */
 int64_t r3d_debug_post_process(r3d_indmatch* m, int64_t n, const float* xyI, const float* xyJ, int coord_dedup);
+/* the same for up to 4 pairs advanced in lockstep by one thread (what the batch tails call) */
+int r3d_debug_post_process_many(int lanes, r3d_indmatch* const* ms, uint64_t* counts, const float* const* xyIs,
+                                const float* const* xyJs, int coord_dedup);
 
 /* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
  * 6 keys ascending + 2 unused)

@@ -11,9 +11,11 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <deque>
+#include <fstream>
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -41,6 +43,17 @@ class HostPool {
     for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE"}) {
       const char* v = std::getenv(name);
       if (v && std::atoi(v) > 0) { local_world = (unsigned)std::atoi(v); break; }
+    }
+    // a container may see every hardware thread but own only a CPU-time quota (cgroup v2 cpu.max = "quota period"):
+    // more runnable threads than that burn the period's quota in a burst and are then throttled for the rest of it
+    {
+      std::ifstream f("/sys/fs/cgroup/cpu.max");
+      std::string q;
+      long long period = 0;
+      if (f >> q >> period && q != "max" && period > 0) {
+        const long long cpus = (std::atoll(q.c_str()) + period - 1) / period;
+        if (cpus >= 1 && (unsigned long long)cpus < hw) hw = (unsigned)cpus;
+      }
     }
     const char* e = std::getenv("R3D_HOST_THREADS");
     unsigned n = e && std::atoi(e) > 0 ? (unsigned)std::atoi(e) : std::max(4u, std::min(hw / local_world, 96u));

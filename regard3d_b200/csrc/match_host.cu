@@ -398,14 +398,28 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         std::lock_guard<std::mutex> lk(slab_mutex);
         slabs.push_back(slab);
       }
-      parallel_for(nthreads, nb, [&](size_t k) {
-        if (cnt[k + 1] == cnt[k]) return;
-        const ViewDev& vi = w.views.find((*hp)[k].I)->second;
-        const ViewDev& vj = w.views.find((*hp)[k].J)->second;
-        r3d_indmatch* seg = bucket + cnt[k];
-        const size_t n = post_process_pair(seg, cnt[k + 1] - cnt[k], vi.has_xy ? vi.h_xy.data() : nullptr,
-                                           vj.has_xy ? vj.h_xy.data() : nullptr, cd);
-        results[all[base + k].src_index] = r3d_span{seg, n};
+      const size_t n_groups = ((size_t)nb + kPostLanes - 1) / kPostLanes;
+      parallel_for(nthreads, n_groups, [&](size_t g) {  // kPostLanes pairs per work item, advanced in lockstep
+        r3d_indmatch* seg[kPostLanes];
+        size_t n[kPostLanes];
+        const float* xi[kPostLanes];
+        const float* xj[kPostLanes];
+        uint32_t idx[kPostLanes];
+        int lanes = 0;
+        for (size_t k = g * kPostLanes; k < std::min<size_t>((g + 1) * kPostLanes, nb); ++k) {
+          if (cnt[k + 1] == cnt[k]) continue;
+          const ViewDev& vi = w.views.find((*hp)[k].I)->second;
+          const ViewDev& vj = w.views.find((*hp)[k].J)->second;
+          seg[lanes] = bucket + cnt[k];
+          n[lanes] = cnt[k + 1] - cnt[k];
+          xi[lanes] = vi.has_xy ? vi.h_xy.data() : nullptr;
+          xj[lanes] = vj.has_xy ? vj.h_xy.data() : nullptr;
+          idx[lanes] = (uint32_t)k;
+          ++lanes;
+        }
+        if (!lanes) return;
+        post_process_pairs(lanes, seg, n, xi, xj, cd);
+        for (int t = 0; t < lanes; ++t) results[all[base + idx[t]].src_index] = r3d_span{seg[t], n[t]};
       });
       const double host_ms = now_ms() - t0;
       std::lock_guard<std::mutex> lk(t_mutex);

@@ -13,6 +13,8 @@
 
 namespace r3d {
 
+constexpr int kPostLanes = 4;  // keep in sync with r3d_internal.cuh
+
 namespace {
 struct XYMatch {
   float x1, y1, x2, y2;
@@ -145,29 +147,40 @@ struct RbTreeT {
     }
     n[root()].red = 0;
   }
-  // _M_insert_unique_(end(), v)
-  void insert_unique_hint_end(const RbNode& v, const r3d_indmatch& im) {
+  // _M_insert_unique_(end(), v), cut into begin / one descent level / finish so that several independent trees can
+  // be advanced in lockstep by one thread (the descent is a chain of dependent loads; interleaving hides its latency)
+  struct Cursor { Idx x, y; bool comp; };
+  // returns true when a descent is needed; false: the hint path applied and the element has been appended
+  bool begin_insert(const RbNode& v, const r3d_indmatch& im, Cursor& c) {
     const Idx count = (Idx)(n.size() - 1);
-    Idx p;
-    if (count > 0 && less(n[n[0].child[1]], v)) {
-      p = n[0].child[1];  // {0, rightmost}
-    } else {           // _M_get_insert_unique_pos
-      Idx x = count ? root() : kNil, y = 0;
-      bool comp = true;
-      while (x != kNil) {
-        y = x;
-        comp = less(v, n[x]);
-        x = n[x].child[comp ? 0 : 1];  // branch-free descent
-      }
-      Idx j = y;
-      bool check = true;
-      if (comp) {
-        if (y == n[0].child[0] || count == 0) check = false;  // j == begin(): insert
-        else j = decrement(y);
-      }
-      if (check && !less(n[j], v)) return;  // an "equivalent" key is already there
-      p = y;
+    if (count > 0 && less(n[n[0].child[1]], v)) {  // {0, rightmost}
+      const Idx p = n[0].child[1];
+      link(v, im, p);
+      return false;
     }
+    c.x = count ? root() : kNil;
+    c.y = 0;
+    c.comp = true;
+    return true;
+  }
+  bool descending(const Cursor& c) const { return c.x != kNil; }
+  void step(const RbNode& v, Cursor& c) const {  // one level of _M_get_insert_unique_pos
+    c.y = c.x;
+    c.comp = less(v, n[c.x]);
+    c.x = n[c.x].child[c.comp ? 0 : 1];
+  }
+  void finish_insert(const RbNode& v, const r3d_indmatch& im, const Cursor& c) {
+    const Idx count = (Idx)(n.size() - 1);
+    Idx j = c.y;
+    bool check = true;
+    if (c.comp) {
+      if (c.y == n[0].child[0] || count == 0) check = false;  // j == begin(): insert
+      else j = decrement(c.y);
+    }
+    if (check && !less(n[j], v)) return;  // an "equivalent" key is already there
+    link(v, im, c.y);
+  }
+  void link(const RbNode& v, const r3d_indmatch& im, Idx p) {  // _M_insert_(0, p, v)
     const bool insert_left = (p == 0) || less(v, n[p]);
     n.push_back(v);
     payload.push_back(im);
@@ -197,19 +210,52 @@ struct RbTreeT {
 };
 }  // namespace
 
+// up to kLanes pairs advanced in lockstep by the calling thread; counts[t] is updated in place
+constexpr int kLanes = kPostLanes;
 template <typename Idx>
-static size_t coord_dedup_replay(r3d_indmatch* m, size_t n, const float* xyI) {
-  thread_local RbTreeT<Idx> tree;  // arrays reused across pairs: no allocation per pair
-  tree.reset(n);
-  for (size_t k = 0; k < n; ++k) {
-    typename RbTreeT<Idx>::RbNode v{};
-    v.x1 = xyI[2 * (size_t)m[k].i];
-    v.y1 = xyI[2 * (size_t)m[k].i + 1];
-    tree.insert_unique_hint_end(v, m[k]);
+static void coord_dedup_replay(int lanes, r3d_indmatch* const* ms, size_t* counts, const float* const* xyIs) {
+  typedef RbTreeT<Idx> Tree;
+  thread_local Tree trees[kLanes];  // arrays reused across pairs: no allocation per pair
+  typename Tree::Cursor cur[kLanes];
+  typename Tree::RbNode val[kLanes];
+  size_t pos[kLanes];
+  bool busy[kLanes], done[kLanes];
+  int active = 0;
+  for (int t = 0; t < lanes; ++t) {
+    trees[t].reset(counts[t]);
+    pos[t] = 0;
+    busy[t] = false;
+    done[t] = counts[t] == 0;
+    if (!done[t]) ++active;
   }
-  size_t out = 0;
-  tree.in_order([&](const r3d_indmatch& im) { m[out++] = im; });
-  return out;
+  while (active) {
+    for (int t = 0; t < lanes; ++t) {
+      if (done[t]) continue;
+      Tree& tr = trees[t];
+      const r3d_indmatch* m = ms[t];
+      if (busy[t]) {
+        if (tr.descending(cur[t])) { tr.step(val[t], cur[t]); continue; }
+        tr.finish_insert(val[t], m[pos[t] - 1], cur[t]);
+        busy[t] = false;
+      }
+      // next element of this pair; an element with the same i as its predecessor shares its coordinates and its fate is
+      // "rejected" either way (predecessor accepted: an equal key is present; rejected: same descent on the same tree)
+      size_t k = pos[t];
+      const size_t n = counts[t];
+      while (k < n && k > 0 && m[k].i == m[k - 1].i) ++k;
+      if (k >= n) { done[t] = true; --active; continue; }
+      val[t].x1 = xyIs[t][2 * (size_t)m[k].i];
+      val[t].y1 = xyIs[t][2 * (size_t)m[k].i + 1];
+      pos[t] = k + 1;
+      busy[t] = tr.begin_insert(val[t], m[k], cur[t]);
+    }
+  }
+  for (int t = 0; t < lanes; ++t) {
+    size_t out = 0;
+    r3d_indmatch* m = ms[t];
+    trees[t].in_order([&](const r3d_indmatch& im) { m[out++] = im; });
+    counts[t] = out;
+  }
 }
 
 // ascending (i, j): LSD radix sort on the 64-bit key i << 32 | j, 8 bits per pass, passes whose digit is the same in
@@ -243,13 +289,32 @@ static void sort_ij(r3d_indmatch* m, size_t n) {
   for (size_t k = 0; k < n; ++k) { m[k].i = (uint32_t)(src[k] >> 32); m[k].j = (uint32_t)src[k]; }
 }
 
-// in place on m[0..n); returns the new count
+// `lanes` (<= kPostLanes) pairs, each in place on ms[t][0..counts[t]); counts[] receives the new sizes.
+// xyIs[t] == nullptr or coord_dedup == false: only the (i, j) de-duplication.
+void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, const float* const* xyIs, const float* const* xyJs,
+                        bool coord_dedup) {
+  bool all_xy = coord_dedup;
+  size_t nmax = 0;
+  for (int t = 0; t < lanes; ++t) {
+    sort_ij(ms[t], counts[t]);
+    counts[t] = (size_t)(std::unique(ms[t], ms[t] + counts[t],
+                                     [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }) - ms[t]);
+    all_xy = all_xy && xyIs[t] && xyJs[t];
+    nmax = std::max(nmax, counts[t]);
+  }
+  if (!all_xy) {  // mixed: fall back to one pair at a time
+    if (!coord_dedup) return;
+    for (int t = 0; t < lanes; ++t)
+      if (xyIs[t] && xyJs[t]) post_process_pairs(1, ms + t, counts + t, xyIs + t, xyJs + t, true);
+    return;
+  }
+  if (nmax < 65000) coord_dedup_replay<uint16_t>(lanes, ms, counts, xyIs);
+  else coord_dedup_replay<uint32_t>(lanes, ms, counts, xyIs);
+}
+
 size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ, bool coord_dedup) {
-  sort_ij(m, n);
-  n = (size_t)(std::unique(m, m + n, [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }) - m);
-  if (!coord_dedup || !xyI || !xyJ) return n;
-  if (n < 65000) return coord_dedup_replay<uint16_t>(m, n, xyI);
-  return coord_dedup_replay<uint32_t>(m, n, xyI);
+  post_process_pairs(1, &m, &n, &xyI, &xyJ, coord_dedup);
+  return n;
 }
 
 }  // namespace r3d
@@ -258,4 +323,14 @@ size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const floa
 extern "C" int64_t r3d_debug_post_process(r3d_indmatch* m, int64_t n, const float* xyI, const float* xyJ, int coord_dedup) {
   if (!m || n < 0) return -1;
   return (int64_t)r3d::post_process_pair(m, (size_t)n, xyI, xyJ, coord_dedup != 0);
+}
+
+extern "C" int r3d_debug_post_process_many(int lanes, r3d_indmatch* const* ms, uint64_t* counts, const float* const* xyIs,
+                                           const float* const* xyJs, int coord_dedup) {
+  if (lanes < 1 || lanes > r3d::kPostLanes || !ms || !counts) return -1;
+  size_t c[r3d::kPostLanes];
+  for (int t = 0; t < lanes; ++t) c[t] = (size_t)counts[t];
+  r3d::post_process_pairs(lanes, ms, c, xyIs, xyJs, coord_dedup != 0);
+  for (int t = 0; t < lanes; ++t) counts[t] = c[t];
+  return 0;
 }

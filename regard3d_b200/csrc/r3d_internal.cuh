@@ -217,6 +217,9 @@ int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pai
 // host post-processing (match_post.cpp)
 size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ,
                        bool coord_dedup);
+constexpr int kPostLanes = 4;  // pairs one host thread advances in lockstep (independent trees hide each other's latency)
+void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, const float* const* xyIs, const float* const* xyJs,
+                        bool coord_dedup);
 
 // driver entry points
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -115,3 +115,35 @@ def test_coordinate_dedup_replay_equals_std_set(r3dlib, oracle):
                                        xyJ.ctypes.data_as(C.c_void_p), 1)
         assert k == len(want), (trial, k, len(want))
         assert np.array_equal(got[:k], want), trial
+
+
+def test_lockstep_replay_of_several_pairs_equals_std_set(r3dlib, oracle):
+    """The batch tails advance up to 4 pairs per host thread in lockstep: same results as pair by pair."""
+    import ctypes as C
+    lib = r3dlib.lib()
+    rng = np.random.default_rng(21)
+    for trial in range(60):
+        lanes = int(rng.integers(1, 5))
+        ms, xyIs, xyJs, wants = [], [], [], []
+        for t in range(lanes):
+            n_feat = int(rng.integers(2, 300))
+            levels = int(rng.choice([2, 4, 9, 1000]))
+            xyI = (rng.integers(0, levels, (n_feat, 2)) * 1.25).astype(np.float32)
+            xyJ = (rng.integers(0, levels, (n_feat, 2)) * 0.5).astype(np.float32)
+            n = int(rng.integers(0, 900))
+            m = np.zeros(n, r3dlib.indmatch_dtype)
+            m["i"] = rng.integers(0, n_feat, n)
+            m["j"] = rng.integers(0, n_feat, n)
+            exp = np.unique(np.stack([m["i"], m["j"]], 1), axis=0) if n else np.zeros((0, 2), np.uint32)
+            e = np.zeros(len(exp), r3dlib.indmatch_dtype)
+            e["i"], e["j"] = exp[:, 0], exp[:, 1]
+            wants.append(oracle.coord_dedup(e, xyI, xyJ) if len(e) else e)
+            ms.append(m.copy()); xyIs.append(xyI); xyJs.append(xyJ)
+        mp = (C.c_void_p * lanes)(*[m.ctypes.data for m in ms])
+        ip = (C.c_void_p * lanes)(*[x.ctypes.data for x in xyIs])
+        jp = (C.c_void_p * lanes)(*[x.ctypes.data for x in xyJs])
+        counts = (C.c_uint64 * lanes)(*[len(m) for m in ms])
+        assert lib.r3d_debug_post_process_many(lanes, mp, counts, ip, jp, 1) == 0
+        for t in range(lanes):
+            assert counts[t] == len(wants[t]), (trial, t)
+            assert np.array_equal(ms[t][:counts[t]], wants[t]), (trial, t)
