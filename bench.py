@@ -101,6 +101,14 @@ class ClockSampler:
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         # "under load": samples in the upper half of what was seen
+        if not sm:  # the region was shorter than one sampling period: one synchronous reading
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except Exception:
+                pass
         if sm:
             hi = [x for x in sm if x >= 0.5 * max(sm)]
             med = float(np.median(hi))
@@ -283,7 +291,6 @@ def main():
         d2h_step = t["d2h_bytes"]
     barrier()
     t_res = time.perf_counter() - t0
-    clocks = sampler.stop()
     n_matches = m.total
     n_match_pairs = m.num_pairs
 
@@ -303,6 +310,7 @@ def main():
         launches_e2e = t["kernel_launches"]
     barrier()
     t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()   # sampled over both timed regions (resident + end-to-end), all of it under load
 
     # ---------------- geometric filter leg (reported alongside; BASELINE C2 itself stops at putatives) ----------------
     filt = None
