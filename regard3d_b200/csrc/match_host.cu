@@ -171,7 +171,9 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     if (!o.d_counters) {
       R3D_CUDA_TRY(ctx, cudaMalloc(&o.d_counters, kCounterWords * sizeof(uint32_t)));
       R3D_CUDA_TRY(ctx, cudaMallocHost(&o.h_counters, kCounterWords * sizeof(uint32_t)));
-      for (auto& e : o.ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
+      // blocking-sync events: the batch tails SLEEP in cudaEventSynchronize instead of spinning -- with two or three
+      // batches in flight the default (spin) burned 2-3 CPUs per rank, a quarter of a 12-CPU-per-GPU container quota
+      for (auto& e : o.ev) R3D_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventBlockingSync));
     }
   }
 
