@@ -147,3 +147,22 @@ def test_lockstep_replay_of_several_pairs_equals_std_set(r3dlib, oracle):
         for t in range(lanes):
             assert counts[t] == len(wants[t]), (trial, t)
             assert np.array_equal(ms[t][:counts[t]], wants[t]), (trial, t)
+
+
+def test_bench_reference_arm_prints_one_json_line(oracle):
+    """`bench.py --impl reference` (the driver's reference arm) needs no GPU: one JSON line on stdout with the contract's
+    keys; a 2-pair sample keeps it short."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = dict(os.environ, R3D_REF_SAMPLE_PAIRS="2")
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "matched_image_pairs_per_sec_exhaustive" and d["unit"] == "pairs/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
