@@ -240,6 +240,9 @@ int64_t r3d_debug_post_process(r3d_indmatch* m, int64_t n, const float* xyI, con
 /* the same for up to 4 pairs advanced in lockstep by one thread (what the batch tails call) */
 int r3d_debug_post_process_many(int lanes, r3d_indmatch* const* ms, uint64_t* counts, const float* const* xyIs,
                                 const float* const* xyJs, int coord_dedup);
+/* the descent-free replay the batch tails use (per-view y-rank / shared-x tables, built here from the n_keypoints
+ * positions of view I) */
+int64_t r3d_debug_post_process_ranked(r3d_indmatch* m, int64_t n, const float* xyI, uint32_t n_keypoints, const float* xyJ);
 
 /* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
  * 6 keys ascending + 2 unused)

@@ -160,6 +160,16 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   }
   if (all.empty()) return R3D_OK;
   const int kp = operand_cols((int)dim);
+  if (want_matches && (flags & R3D_MATCH_NO_COORD_DEDUP) == 0) {
+    // per-view tables of the descent-free coordinate de-duplication (match_post.cpp), built once per upload
+    std::vector<ViewDev*> need;
+    for (auto& kv : w.views)
+      if (kv.second.has_xy && kv.second.h_yrank.size() != kv.second.n) need.push_back(&kv.second);
+    parallel_for(ctx->host_threads, need.size(), [&](size_t k) {
+      ViewDev& v = *need[k];
+      build_view_ranks(v.h_xy.data(), v.n, v.h_yrank, v.h_xshared, &v.n_slots);
+    });
+  }
   const double t_prepared = now_ms();
 
   r3d_match_timing& T = w.timing;
@@ -406,6 +416,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         size_t n[kPostLanes];
         const float* xi[kPostLanes];
         const float* xj[kPostLanes];
+        ViewRankRef rk[kPostLanes];
         uint32_t idx[kPostLanes];
         int lanes = 0;
         for (size_t k = g * kPostLanes; k < std::min<size_t>((g + 1) * kPostLanes, nb); ++k) {
@@ -416,11 +427,14 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
           n[lanes] = cnt[k + 1] - cnt[k];
           xi[lanes] = vi.has_xy ? vi.h_xy.data() : nullptr;
           xj[lanes] = vj.has_xy ? vj.h_xy.data() : nullptr;
+          rk[lanes] = (vi.has_xy && vi.h_yrank.size() == vi.n) ? ViewRankRef{vi.h_yrank.data(), vi.h_xshared.data(), vi.n_slots}
+                                                                : ViewRankRef{nullptr, nullptr, 0};
           idx[lanes] = (uint32_t)k;
           ++lanes;
         }
         if (!lanes) return;
-        post_process_pairs(lanes, seg, n, xi, xj, cd);
+        static const bool classic = getenv("R3D_DEDUP_CLASSIC") != nullptr;  // A/B: lockstep classic replay
+        post_process_pairs(lanes, seg, n, xi, xj, cd, classic ? nullptr : rk);
         for (int t = 0; t < lanes; ++t) results[all[base + idx[t]].src_index] = r3d_span{seg[t], n[t]};
       });
       const double host_ms = now_ms() - t0;

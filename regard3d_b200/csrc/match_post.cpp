@@ -7,6 +7,7 @@
 // (libstdc++'s, the reference's toolchain).  O(#matches log #matches) per pair.
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "../../include/r3dgpu.h"
@@ -14,6 +15,7 @@
 namespace r3d {
 
 constexpr int kPostLanes = 4;  // keep in sync with r3d_internal.cuh
+struct ViewRankRef { const uint32_t* yrank; const uint8_t* xshared; uint32_t n_slots; };  // idem
 
 namespace {
 struct XYMatch {
@@ -258,6 +260,129 @@ static void coord_dedup_replay(int lanes, r3d_indmatch* const* ms, size_t* count
   }
 }
 
+// ---- per-view tables for the O(1) landing-slot replay ---------------------------------------------------
+// yrank[i]  : dense rank of keypoint i's y coordinate among the view's keypoints (equal y share a rank)
+// xshared[i]: some OTHER keypoint of the view has the same x coordinate
+static inline uint32_t float_key(float f) {  // monotonic float -> uint32 (f finite; -0 is folded into +0)
+  f += 0.0f;
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static void sort_by_key(std::vector<uint64_t>& a, std::vector<uint64_t>& tmp) {  // LSD radix on the high 32 bits
+  const size_t n = a.size();
+  tmp.resize(n);
+  uint64_t* src = a.data();
+  uint64_t* dst = tmp.data();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int sh = 32 + 8 * pass;
+    size_t hist[257] = {0};
+    for (size_t k = 0; k < n; ++k) hist[((src[k] >> sh) & 0xffu) + 1]++;
+    for (int d = 0; d < 256; ++d) hist[d + 1] += hist[d];
+    for (size_t k = 0; k < n; ++k) dst[hist[(src[k] >> sh) & 0xffu]++] = src[k];
+    std::swap(src, dst);
+  }  // 4 passes: the result is back in a
+}
+void build_view_ranks(const float* xy, uint32_t n, std::vector<uint32_t>& yrank, std::vector<uint8_t>& xshared,
+                      uint32_t* n_slots) {
+  yrank.assign(n, 0);
+  xshared.assign(n, 0);
+  std::vector<uint64_t> a(n), tmp;
+  for (uint32_t i = 0; i < n; ++i) a[i] = ((uint64_t)float_key(xy[2 * (size_t)i + 1]) << 32) | i;
+  sort_by_key(a, tmp);
+  uint32_t rank = 0;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t i = (uint32_t)a[k];
+    if (k > 0 && xy[2 * (size_t)i + 1] != xy[2 * (size_t)(uint32_t)a[k - 1] + 1]) ++rank;
+    yrank[i] = rank;
+  }
+  *n_slots = n ? rank + 1 : 0;
+  for (uint32_t i = 0; i < n; ++i) a[i] = ((uint64_t)float_key(xy[2 * (size_t)i]) << 32) | i;
+  sort_by_key(a, tmp);
+  for (uint32_t k = 0; k + 1 < n; ++k) {
+    const uint32_t i = (uint32_t)a[k], j = (uint32_t)a[k + 1];
+    if (xy[2 * (size_t)i] == xy[2 * (size_t)j]) { xshared[i] = 1; xshared[j] = 1; }
+  }
+}
+
+// The replay without the descents.  The set's in-order sequence is always strictly increasing in y (an element is
+// only linked where its in-order predecessor has a smaller y -- see the insertion rule), so for an element v:
+//   * a present element with the SAME y: the search path reaches it, turns right, and every later predecessor has
+//     y >= v.y                                                                                   -> rejected;
+//   * otherwise the descent is the plain BST descent by y EXCEPT at a node with the same x and a larger y, where
+//     less(v, node) is false and the descent turns right (and v is then rejected).  If no other keypoint of the view
+//     shares v's x (xshared == 0) that cannot happen: v lands in THE slot between its y-predecessor and y-successor
+//     among the present elements -- the right child of the predecessor when that is free, else the left child of
+//     the successor -- and is accepted (its predecessor has a different x).
+// Predecessor / successor come from a bitset over the view's y ranks; elements with xshared (a few percent) take the
+// classic descent on the very same tree.  Same tree, same rotations, same result -- minus ~12 dependent loads per match.
+template <typename Idx>
+static size_t ranked_replay(r3d_indmatch* m, size_t n, const float* xyI, const uint32_t* yrank, const uint8_t* xshared,
+                            uint32_t n_slots) {
+  typedef RbTreeT<Idx> Tree;
+  thread_local Tree tree;
+  thread_local std::vector<uint64_t> occ;
+  thread_local std::vector<Idx> slot_node;
+  tree.reset(n);
+  const size_t words = ((size_t)n_slots + 63) / 64 + 1;
+  occ.assign(words, 0ull);
+  if (slot_node.size() < n_slots) slot_node.resize(n_slots);
+  for (size_t k = 0; k < n; ++k) {
+    if (k > 0 && m[k].i == m[k - 1].i) continue;  // same keypoint as its predecessor: rejected either way (see above)
+    const uint32_t i = m[k].i, s = yrank[i];
+    if ((occ[s >> 6] >> (s & 63)) & 1ull) continue;
+    typename Tree::RbNode v{};
+    v.x1 = xyI[2 * (size_t)i];
+    v.y1 = xyI[2 * (size_t)i + 1];
+    const size_t before = tree.n.size();
+    if (xshared[i]) {
+      typename Tree::Cursor c;
+      if (tree.begin_insert(v, m[k], c)) {
+        while (tree.descending(c)) tree.step(v, c);
+        tree.finish_insert(v, m[k], c);
+      }
+    } else {
+      // predecessor: highest occupied rank below s ; successor: lowest occupied rank above s
+      long pred = -1, succ = -1;
+      {
+        long wi = (long)(s >> 6);
+        uint64_t w = occ[wi] & ((1ull << (s & 63)) - 1ull);
+        for (;;) {
+          if (w) { pred = wi * 64 + 63 - __builtin_clzll(w); break; }
+          if (--wi < 0) break;
+          w = occ[wi];
+        }
+        wi = (long)(s >> 6);
+        w = (s & 63) == 63 ? 0ull : (occ[wi] & ~((2ull << (s & 63)) - 1ull));
+        for (;;) {
+          if (w) { succ = wi * 64 + __builtin_ctzll(w); break; }
+          if (++wi >= (long)words) break;
+          w = occ[wi];
+        }
+      }
+      Idx parent = 0;  // header: empty tree
+      if (pred >= 0 && tree.n[slot_node[pred]].child[1] == Tree::kNil) parent = slot_node[pred];
+      else if (succ >= 0) parent = slot_node[succ];
+      else if (pred >= 0) parent = slot_node[pred];  // unreachable in a consistent tree; keeps the code total
+      tree.link(v, m[k], parent);
+    }
+    if (tree.n.size() != before) {
+      occ[s >> 6] |= 1ull << (s & 63);
+      slot_node[s] = (Idx)(tree.n.size() - 1);
+    }
+  }
+  size_t out = 0;
+  for (size_t wi = 0; wi < words; ++wi) {  // in-order == increasing y rank
+    uint64_t w = occ[wi];
+    while (w) {
+      const int b = __builtin_ctzll(w);
+      w &= w - 1;
+      m[out++] = tree.payload[slot_node[wi * 64 + b]];
+    }
+  }
+  return out;
+}
+
 // ascending (i, j): LSD radix sort on the 64-bit key i << 32 | j, 8 bits per pass, passes whose digit is the same in
 // every key are skipped (indices rarely need more than 2 bytes each)
 static void sort_ij(r3d_indmatch* m, size_t n) {
@@ -290,9 +415,10 @@ static void sort_ij(r3d_indmatch* m, size_t n) {
 }
 
 // `lanes` (<= kPostLanes) pairs, each in place on ms[t][0..counts[t]); counts[] receives the new sizes.
-// xyIs[t] == nullptr or coord_dedup == false: only the (i, j) de-duplication.
+// xyIs[t] == nullptr or coord_dedup == false: only the (i, j) de-duplication.  ranks (optional): per lane the
+// build_view_ranks() tables of view I -- with them the coordinate step runs without tree descents.
 void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, const float* const* xyIs, const float* const* xyJs,
-                        bool coord_dedup) {
+                        bool coord_dedup, const ViewRankRef* ranks) {
   bool all_xy = coord_dedup;
   size_t nmax = 0;
   for (int t = 0; t < lanes; ++t) {
@@ -302,10 +428,20 @@ void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, cons
     all_xy = all_xy && xyIs[t] && xyJs[t];
     nmax = std::max(nmax, counts[t]);
   }
-  if (!all_xy) {  // mixed: fall back to one pair at a time
-    if (!coord_dedup) return;
+  if (!coord_dedup) return;
+  if (ranks) {
+    for (int t = 0; t < lanes; ++t) {
+      if (!xyIs[t] || !xyJs[t]) continue;
+      if (!ranks[t].yrank) { post_process_pairs(1, ms + t, counts + t, xyIs + t, xyJs + t, true, nullptr); continue; }
+      counts[t] = counts[t] < 65000
+                      ? ranked_replay<uint16_t>(ms[t], counts[t], xyIs[t], ranks[t].yrank, ranks[t].xshared, ranks[t].n_slots)
+                      : ranked_replay<uint32_t>(ms[t], counts[t], xyIs[t], ranks[t].yrank, ranks[t].xshared, ranks[t].n_slots);
+    }
+    return;
+  }
+  if (!all_xy) {  // mixed: one pair at a time
     for (int t = 0; t < lanes; ++t)
-      if (xyIs[t] && xyJs[t]) post_process_pairs(1, ms + t, counts + t, xyIs + t, xyJs + t, true);
+      if (xyIs[t] && xyJs[t]) post_process_pairs(1, ms + t, counts + t, xyIs + t, xyJs + t, true, nullptr);
     return;
   }
   if (nmax < 65000) coord_dedup_replay<uint16_t>(lanes, ms, counts, xyIs);
@@ -313,7 +449,7 @@ void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, cons
 }
 
 size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ, bool coord_dedup) {
-  post_process_pairs(1, &m, &n, &xyI, &xyJ, coord_dedup);
+  post_process_pairs(1, &m, &n, &xyI, &xyJ, coord_dedup, nullptr);
   return n;
 }
 
@@ -330,7 +466,22 @@ extern "C" int r3d_debug_post_process_many(int lanes, r3d_indmatch* const* ms, u
   if (lanes < 1 || lanes > r3d::kPostLanes || !ms || !counts) return -1;
   size_t c[r3d::kPostLanes];
   for (int t = 0; t < lanes; ++t) c[t] = (size_t)counts[t];
-  r3d::post_process_pairs(lanes, ms, c, xyIs, xyJs, coord_dedup != 0);
+  // mode 1: lockstep classic replay ; mode 2: ranked replay with tables built here from xyI (n_keypoints needed)
+  r3d::post_process_pairs(lanes, ms, c, xyIs, xyJs, coord_dedup != 0, nullptr);
   for (int t = 0; t < lanes; ++t) counts[t] = c[t];
   return 0;
+}
+
+// host-only diagnostic: the ranked (descent-free) replay of one pair, tables built from xyI (n_keypoints rows)
+extern "C" int64_t r3d_debug_post_process_ranked(r3d_indmatch* m, int64_t n, const float* xyI, uint32_t n_keypoints,
+                                                 const float* xyJ) {
+  if (!m || n < 0 || !xyI || !xyJ) return -1;
+  std::vector<uint32_t> yrank;
+  std::vector<uint8_t> xshared;
+  uint32_t n_slots = 0;
+  r3d::build_view_ranks(xyI, n_keypoints, yrank, xshared, &n_slots);
+  r3d::ViewRankRef ref{yrank.data(), xshared.data(), n_slots};
+  size_t c = (size_t)n;
+  r3d::post_process_pairs(1, &m, &c, &xyI, &xyJ, true, &ref);
+  return (int64_t)c;
 }

@@ -47,6 +47,9 @@ struct ViewDev {
   __half* d_opD = nullptr;   // database-role operand [n_pad][kp]:    a  | p0 p1 S0 S1 0...
   float2* d_xy = nullptr;    // positions [n]
   std::vector<float> h_xy;   // host copy (coordinate de-duplication, RANSAC set-up)
+  std::vector<uint32_t> h_yrank;   // build_view_ranks(): tables of the descent-free coordinate de-duplication
+  std::vector<uint8_t> h_xshared;
+  uint32_t n_slots = 0;
   bool has_xy = false;
   bool prepared = false;
   int prepared_e0 = 0;
@@ -218,8 +221,11 @@ int launch_fill_all_queries(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pai
 size_t post_process_pair(r3d_indmatch* m, size_t n, const float* xyI, const float* xyJ,
                        bool coord_dedup);
 constexpr int kPostLanes = 4;  // pairs one host thread advances in lockstep (independent trees hide each other's latency)
+struct ViewRankRef { const uint32_t* yrank; const uint8_t* xshared; uint32_t n_slots; };
+void build_view_ranks(const float* xy, uint32_t n, std::vector<uint32_t>& yrank, std::vector<uint8_t>& xshared,
+                      uint32_t* n_slots);
 void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, const float* const* xyIs, const float* const* xyJs,
-                        bool coord_dedup);
+                        bool coord_dedup, const ViewRankRef* ranks);
 
 // driver entry points
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -166,3 +166,32 @@ def test_bench_reference_arm_prints_one_json_line(oracle):
     assert d["impl"] == "reference" and d["metric"] == "matched_image_pairs_per_sec_exhaustive" and d["unit"] == "pairs/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_ranked_descent_free_replay_equals_std_set(r3dlib, oracle):
+    """The batch tails replace the tree descents by a bitset over the view's y ranks (match_post.cpp::ranked_replay) and
+    keep the classic descent only for keypoints whose x is shared.  Same adversarial inputs as above (few distinct x / y,
+    shared keypoints, exact duplicates, negative and zero coordinates) plus realistic sparse ones, against std::set."""
+    import ctypes as C
+    lib = r3dlib.lib()
+    rng = np.random.default_rng(33)
+    for trial in range(400):
+        n_feat = int(rng.integers(2, 500))
+        levels = int(rng.choice([2, 3, 5, 17, 200, 100000]))
+        xyI = ((rng.integers(0, levels, (n_feat, 2)) - levels // 3) * 1.5).astype(np.float32)
+        if trial % 7 == 0:
+            xyI[rng.integers(0, n_feat)] = (-0.0, 0.0)      # signed zeros compare equal
+        xyJ = (rng.integers(0, levels, (n_feat, 2)) * 0.75).astype(np.float32)
+        n = int(rng.integers(1, 1500))
+        m = np.zeros(n, r3dlib.indmatch_dtype)
+        m["i"] = rng.integers(0, n_feat, n)
+        m["j"] = rng.integers(0, n_feat, n)
+        exp = np.unique(np.stack([m["i"], m["j"]], 1), axis=0)
+        e = np.zeros(len(exp), r3dlib.indmatch_dtype)
+        e["i"], e["j"] = exp[:, 0], exp[:, 1]
+        want = oracle.coord_dedup(e, xyI, xyJ)
+        got = m.copy()
+        k = lib.r3d_debug_post_process_ranked(got.ctypes.data_as(C.c_void_p), C.c_int64(n), xyI.ctypes.data_as(C.c_void_p),
+                                              C.c_uint32(n_feat), xyJ.ctypes.data_as(C.c_void_p))
+        assert k == len(want), (trial, levels, k, len(want))
+        assert np.array_equal(got[:k], want), (trial, levels)
