@@ -17,24 +17,13 @@ namespace r3d {
 constexpr int kPostLanes = 4;  // keep in sync with r3d_internal.cuh
 struct ViewRankRef { const uint32_t* yrank; const uint8_t* xshared; uint32_t n_slots; };  // idem
 
-namespace {
-struct XYMatch {
-  float x1, y1, x2, y2;
-  r3d_indmatch im;
-};
-inline bool same_xy(const XYMatch& a, const XYMatch& b) {
-  return a.x1 == b.x1 && a.y1 == b.y1 && a.x2 == b.x2 && a.y2 == b.y2;
-}
-// upstream IndMatchDecoratorStruct::operator< ("lexicographical ordering", verbatim semantics)
-struct XYLess {
-  bool operator()(const XYMatch& m1, const XYMatch& m2) const {
-    if (same_xy(m1, m2)) return false;
-    if (m1.x1 < m2.x1) return m1.y1 < m2.y1;
-    if (m1.x1 > m2.x1) return m1.y1 < m2.y1;
-    return m1.x1 < m2.x1;
-  }
-};
-}  // namespace
+// upstream IndMatchDecoratorStruct::operator< ("lexicographical ordering"), verbatim semantics, on records
+// (x1, y1, x2, y2, IndMatch):
+//     if (m1 == m2) return false;                       // all four coordinates equal
+//     if (m1.x1 < m2.x1) return m1.y1 < m2.y1;
+//     if (m1.x1 > m2.x1) return m1.y1 < m2.y1;
+//     return m1.x1 < m2.x1;                             // equal x1: false
+// i.e. less(a, b) == (a.x1 != b.x1) && (a.y1 < b.y1): only the position in image I takes part.
 
 // ---- the std::set range insertion, replayed on a compact node array ------------------------------------
 // std::set<XYMatch, XYLess>(first, last) in libstdc++ is, element by element,
