@@ -315,11 +315,15 @@ int launch_rerank_list(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, c
 }
 
 // ---- pack the per-pair match segments for the host copy ----------------------------------------------
-// one block per pair: offset = sum of the counts of the pairs before it (<= a few thousand values), then
-// a coalesced copy of the pair's segment.  Order inside a pair is irrelevant: the host sorts by (i, j)
-// (IndMatch::getDeduplicated) before the order-dependent coordinate de-duplication.
+// one block per pair: offset = sum of the counts of the pairs before it (<= a few thousand values), then the pair's
+// segment goes to the packed array -- SORTED by (i, j) when it fits the shared-memory bitonic network
+// (<= kPackSortCap matches): IndMatch::getDeduplicated wants that order, and the sort is microseconds here but a
+// third of the host tail's CPU time.  Larger segments are copied as they are (the host checks the order and sorts
+// when needed, so the order is a performance matter only).
+constexpr uint32_t kPackSortCap = 8192;
 __global__ void __launch_bounds__(256) k_pack_matches(const PairDesc* __restrict__ pairs, const uint32_t* __restrict__ pair_cnt,
                                                       const uint2* __restrict__ dense, uint2* __restrict__ packed) {
+  extern __shared__ __align__(16) unsigned long long s_key[];  // kPackSortCap keys: i << 32 | j
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_ofs;
   const uint32_t p = blockIdx.x;
@@ -335,13 +339,45 @@ __global__ void __launch_bounds__(256) k_pack_matches(const PairDesc* __restrict
   }
   __syncthreads();
   const uint32_t n = pair_cnt[p], src = pairs[p].q_ofs, dst = s_ofs;
-  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) packed[dst + k] = dense[src + k];
+  if (n < 2 || n > kPackSortCap) {
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) packed[dst + k] = dense[src + k];
+    return;
+  }
+  uint32_t P = 2;
+  while (P < n) P <<= 1;
+  for (uint32_t k = threadIdx.x; k < P; k += blockDim.x) {
+    unsigned long long key = ~0ull;  // padding sorts last
+    if (k < n) {
+      const uint2 m = dense[src + k];
+      key = ((unsigned long long)m.x << 32) | m.y;
+    }
+    s_key[k] = key;
+  }
+  __syncthreads();
+  for (uint32_t size = 2; size <= P; size <<= 1) {
+    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+        const uint32_t lo = (t / stride) * (stride << 1) + (t % stride);
+        const uint32_t hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long a = s_key[lo], b = s_key[hi];
+        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+    const unsigned long long key = s_key[k];
+    packed[dst + k] = make_uint2((uint32_t)(key >> 32), (uint32_t)key);
+  }
 }
 
 int launch_pack_matches(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, uint32_t n_pairs, const uint32_t* d_pair_cnt,
                         const uint2* d_dense, uint2* d_packed) {
   if (!n_pairs) return R3D_OK;
-  k_pack_matches<<<n_pairs, 256, 0, w.stream>>>(d_pairs, d_pair_cnt, d_dense, d_packed);
+  const size_t smem = (size_t)kPackSortCap * sizeof(unsigned long long);
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_pack_matches, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_pack_matches<<<n_pairs, 256, smem, w.stream>>>(d_pairs, d_pair_cnt, d_dense, d_packed);
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   return R3D_OK;
 }

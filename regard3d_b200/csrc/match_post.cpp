@@ -411,7 +411,11 @@ void post_process_pairs(int lanes, r3d_indmatch* const* ms, size_t* counts, cons
   bool all_xy = coord_dedup;
   size_t nmax = 0;
   for (int t = 0; t < lanes; ++t) {
-    sort_ij(ms[t], counts[t]);
+    // the device hands most pairs over already sorted (k_pack_matches); the check makes the order a performance
+    // matter only, never a correctness one
+    if (!std::is_sorted(ms[t], ms[t] + counts[t],
+                        [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i < b.i || (a.i == b.i && a.j < b.j); }))
+      sort_ij(ms[t], counts[t]);
     counts[t] = (size_t)(std::unique(ms[t], ms[t] + counts[t],
                                      [](const r3d_indmatch& a, const r3d_indmatch& b) { return a.i == b.i && a.j == b.j; }) - ms[t]);
     all_xy = all_xy && xyIs[t] && xyJs[t];
