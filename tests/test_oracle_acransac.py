@@ -180,3 +180,28 @@ def test_filter_pairs_E_skips_views_without_intrinsics(oracle):
     eo, em = oracle.filter_pairs_E(sc["xys"], sc["widths"], sc["heights"], Ks, pairs, ofs, m)
     assert eo[1] - eo[0] > 5 * 2.5            # pair (0,1) kept
     assert eo[2] == eo[1] and eo[3] == eo[2]  # pairs with view 2 dropped
+
+
+def test_acransac_E_overlaps_an_independent_estimator(oracle):
+    """cv2.findEssentialMat (RANSAC, its own 5-point solver) on the same two-view data: inlier-set overlap, not equality."""
+    cv2 = pytest.importorskip("cv2")
+    xI, xJ, good = _two_view(11, n=700, outlier_frac=0.25)
+    f = 1.1 * 1920
+    K = np.array([f, 960.0, 540.0, f, 960.0, 540.0])
+    inl, F, info = oracle.acransac_E(xI, xJ, 1920, 1080, 1920, 1080, K)
+    assert info[0] < 0 and good[inl].mean() > 0.97
+    Kmat = np.array([[f, 0, 960.0], [0, f, 540.0], [0, 0, 1]])
+    E, mask = cv2.findEssentialMat(xI, xJ, Kmat, method=cv2.RANSAC, prob=0.999, threshold=2.0)
+    mask = mask.ravel() > 0
+    assert mask[inl].mean() > 0.85                      # our inliers are (mostly) cv2's inliers
+    assert (good & mask).sum() > 0.8 * good.sum()       # and cv2 found the same structure
+    # the oracle's F equals cv2's E up to the intrinsics, scale and sign: compare the epipolar geometry on the inliers
+    E_ours = Kmat.T @ F @ Kmat
+    def sampson(Em):
+        x1 = np.linalg.solve(Kmat, np.c_[xI[inl], np.ones(len(inl))].T).T
+        x2 = np.linalg.solve(Kmat, np.c_[xJ[inl], np.ones(len(inl))].T).T
+        Ex1 = x1 @ Em.T
+        Etx2 = x2 @ Em
+        num = (x2 * Ex1).sum(1) ** 2
+        return num / (Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2)
+    assert np.median(sampson(E_ours)) < 4 * max(np.median(sampson(E[:3])), 1e-9) + 1e-6
