@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 from regard3d_b200 import synth
 
@@ -195,3 +196,21 @@ def test_ranked_descent_free_replay_equals_std_set(r3dlib, oracle):
                                               C.c_uint32(n_feat), xyJ.ctypes.data_as(C.c_void_p))
         assert k == len(want), (trial, levels, k, len(want))
         assert np.array_equal(got[:k], want), (trial, levels)
+
+
+def test_matches_container_spans_and_edge_cases(r3dlib, tmp_path):
+    """r3d_matches holds spans into slabs: duplicate pairs keep the first (map::insert), empty lists vanish, a loaded
+    file with a zero-count pair keeps it (matching::Load), and handles stay valid while any view of them is alive."""
+    pairs = np.array([[3, 4], [0, 1], [3, 4], [2, 5]], np.uint32)
+    ofs = np.array([0, 2, 3, 5, 5], np.uint64)                      # (3,4) twice, (2,5) empty
+    m = np.array([(1, 1), (2, 2), (7, 7), (8, 8), (9, 9)], r3dlib.indmatch_dtype)
+    mm = r3dlib.Matches.from_csr(pairs, ofs, m)
+    d = mm.to_dict()
+    assert sorted(d) == [(0, 1), (3, 4)] and d[(3, 4)]["i"].tolist() == [1, 2] and mm.total == 3
+    p = tmp_path / "z.txt"
+    p.write_text("5 6\n0\n1 2\n1\n4 4\n")
+    back = r3dlib.Matches.load_txt(str(p))
+    assert back.num_pairs == 2 and back.total == 1
+    assert back.to_dict()[(1, 2)]["j"].tolist() == [4]
+    with pytest.raises(r3dlib.R3DError):
+        r3dlib.Matches.load_txt(str(tmp_path / "missing.txt"))

@@ -205,3 +205,25 @@ def test_acransac_E_overlaps_an_independent_estimator(oracle):
         num = (x2 * Ex1).sum(1) ** 2
         return num / (Ex1[:, 0] ** 2 + Ex1[:, 1] ** 2 + Etx2[:, 0] ** 2 + Etx2[:, 1] ** 2)
     assert np.median(sampson(E_ours)) < 4 * max(np.median(sampson(E[:3])), 1e-9) + 1e-6
+
+
+def test_acransac_H_overlaps_cv2_findHomography(oracle):
+    """cv2.findHomography (RANSAC) as the independent estimator for the homography adaptor: inlier overlap and the
+    same transfer error on the inliers."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6)
+    Ht = np.array([[0.97, -0.05, 30.0], [0.04, 1.03, -12.0], [2e-5, 5e-5, 1.0]])
+    n = 600
+    x1 = rng.uniform([0, 0], [1920, 1080], (n, 2))
+    q = np.c_[x1, np.ones(n)] @ Ht.T
+    x2 = q[:, :2] / q[:, 2:] + rng.normal(0, 0.6, (n, 2))
+    x2[:180] = rng.uniform([0, 0], [1920, 1080], (180, 2))
+    inl, He, info = oracle.acransac_H(x1, x2, 1920, 1080, 1920, 1080)
+    assert info[0] < 0 and (inl >= 180).mean() > 0.98
+    Hc, mask = cv2.findHomography(x1, x2, cv2.RANSAC, 3.0)
+    mask = mask.ravel() > 0
+    assert mask[inl].mean() > 0.9 and (mask[180:].sum() > 0.85 * (n - 180))
+    def err(H):
+        h = np.c_[x1[inl], np.ones(len(inl))] @ H.T
+        return np.median(np.linalg.norm(h[:, :2] / h[:, 2:] - x2[inl], axis=1))
+    assert err(He) < 1.5 * err(Hc) + 0.2
