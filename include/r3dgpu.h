@@ -218,7 +218,7 @@ typedef struct {
   double ms_prep;        /* upload-time operand preparation kernels */
   double ms_candidates;  /* tcgen05 candidate kernel(s), CUDA-event time on their stream */
   double ms_rerank;      /* exact re-rank + ratio kernel(s) */
-  double ms_fallback;    /* exact-scan kernel for uncertified queries */
+  double ms_fallback;    /* exact-scan kernel for uncertified queries + the per-pair pack / (i,j) sort kernel */
   double ms_device_total;/* first launch -> last kernel of the last r3d_match_pairs */
   double ms_host_post;   /* host de-duplication */
   uint64_t kernel_launches;
