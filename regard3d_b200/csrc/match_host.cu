@@ -164,10 +164,11 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     // per-view tables of the descent-free coordinate de-duplication (match_post.cpp), built once per upload
     std::vector<ViewDev*> need;
     for (auto& kv : w.views)
-      if (kv.second.has_xy && kv.second.h_yrank.size() != kv.second.n) need.push_back(&kv.second);
+      if (kv.second.has_xy && !kv.second.ranks_tried) need.push_back(&kv.second);
     parallel_for(ctx->host_threads, need.size(), [&](size_t k) {
       ViewDev& v = *need[k];
       build_view_ranks(v.h_xy.data(), v.n, v.h_yrank, v.h_xshared, &v.n_slots);
+      v.ranks_tried = true;
     });
   }
   const double t_prepared = now_ms();
@@ -427,7 +428,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
           n[lanes] = cnt[k + 1] - cnt[k];
           xi[lanes] = vi.has_xy ? vi.h_xy.data() : nullptr;
           xj[lanes] = vj.has_xy ? vj.h_xy.data() : nullptr;
-          rk[lanes] = (vi.has_xy && vi.h_yrank.size() == vi.n) ? ViewRankRef{vi.h_yrank.data(), vi.h_xshared.data(), vi.n_slots}
+          rk[lanes] = (vi.has_xy && vi.n > 0 && vi.h_yrank.size() == vi.n) ? ViewRankRef{vi.h_yrank.data(), vi.h_xshared.data(), vi.n_slots}
                                                                 : ViewRankRef{nullptr, nullptr, 0};
           idx[lanes] = (uint32_t)k;
           ++lanes;

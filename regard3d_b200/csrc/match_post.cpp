@@ -274,6 +274,13 @@ static void sort_by_key(std::vector<uint64_t>& a, std::vector<uint64_t>& tmp) { 
 }
 void build_view_ranks(const float* xy, uint32_t n, std::vector<uint32_t>& yrank, std::vector<uint8_t>& xshared,
                       uint32_t* n_slots) {
+  yrank.clear();
+  xshared.clear();
+  *n_slots = 0;
+  // non-finite positions: the rank tables assume totally ordered coordinates; leave them empty and the tails fall back
+  // to the classic replay, which evaluates the comparator exactly like std::set does (NaN compares false everywhere)
+  for (size_t k = 0; k < 2 * (size_t)n; ++k)
+    if (!(xy[k] - xy[k] == 0.0f)) return;
   yrank.assign(n, 0);
   xshared.assign(n, 0);
   std::vector<uint64_t> a(n), tmp;
@@ -473,7 +480,7 @@ extern "C" int64_t r3d_debug_post_process_ranked(r3d_indmatch* m, int64_t n, con
   std::vector<uint8_t> xshared;
   uint32_t n_slots = 0;
   r3d::build_view_ranks(xyI, n_keypoints, yrank, xshared, &n_slots);
-  r3d::ViewRankRef ref{yrank.data(), xshared.data(), n_slots};
+  r3d::ViewRankRef ref{yrank.empty() ? nullptr : yrank.data(), xshared.empty() ? nullptr : xshared.data(), n_slots};
   size_t c = (size_t)n;
   r3d::post_process_pairs(1, &m, &c, &xyI, &xyJ, true, &ref);
   return (int64_t)c;

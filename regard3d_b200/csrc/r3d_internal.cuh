@@ -50,6 +50,7 @@ struct ViewDev {
   std::vector<uint32_t> h_yrank;   // build_view_ranks(): tables of the descent-free coordinate de-duplication
   std::vector<uint8_t> h_xshared;
   uint32_t n_slots = 0;
+  bool ranks_tried = false;  // tables stay empty for views with non-finite positions (classic replay then)
   bool has_xy = false;
   bool prepared = false;
   int prepared_e0 = 0;
