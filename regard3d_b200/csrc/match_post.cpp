@@ -23,7 +23,8 @@ struct ViewRankRef { const uint32_t* yrank; const uint8_t* xshared; uint32_t n_s
 //     if (m1.x1 < m2.x1) return m1.y1 < m2.y1;
 //     if (m1.x1 > m2.x1) return m1.y1 < m2.y1;
 //     return m1.x1 < m2.x1;                             // equal x1: false
-// i.e. less(a, b) == (a.x1 != b.x1) && (a.y1 < b.y1): only the position in image I takes part.
+// i.e. less(a, b) == (a.x1 < b.x1 || a.x1 > b.x1) && (a.y1 < b.y1): only the position in image I takes part
+// (NOT `x1 != x1'`: an unordered (NaN) x1 fails both branches and lands on `return m1.x1 < m2.x1` = false).
 
 // ---- the std::set range insertion, replayed on a compact node array ------------------------------------
 // std::set<XYMatch, XYLess>(first, last) in libstdc++ is, element by element,
@@ -38,7 +39,7 @@ struct ViewRankRef { const uint32_t* yrank; const uint8_t* xshared; uint32_t n_s
 // (40-byte nodes, no allocator, no virtual calls) instead of 56-byte heap nodes.  tests/test_io_and_abi.py pins the
 // replay against std::set (through the oracle) on adversarial inputs (many equal x1 / y1 / full duplicates).
 namespace {
-// XYLess(a, b) reduces to (a.x1 != b.x1) && (a.y1 < b.y1): with equal x1 it returns a.x1 < b.x1 = false whether or
+// XYLess(a, b) reduces to (a.x1 <> b.x1) && (a.y1 < b.y1): with equal x1 it returns a.x1 < b.x1 = false whether or
 // not the other coordinates agree, with different x1 the "same coordinates" test is false and both branches return
 // a.y1 < b.y1.  So only (x1, y1) of image I take part, and the test is branch-free.
 // Nodes are 16 bytes with 16-bit links whenever a pair has fewer than 65 535 matches (always, in practice): the
@@ -56,7 +57,8 @@ struct RbTreeT {
   static constexpr Idx kNil = (Idx)~(Idx)0;
   std::vector<RbNode> n;  // n[0] is the header: parent = root, left = leftmost, right = rightmost
   std::vector<r3d_indmatch> payload;  // payload[k] belongs to node k
-  static bool less(const RbNode& a, const RbNode& b) { return (a.x1 != b.x1) & (a.y1 < b.y1); }
+  // (x1 < | x1 >) rather than x1 != : with a NaN x1 the upstream comparator falls through to `m1.x1 < m2.x1` = false
+  static bool less(const RbNode& a, const RbNode& b) { return ((a.x1 < b.x1) | (a.x1 > b.x1)) & (a.y1 < b.y1); }
   void reset(size_t cap) {
     n.clear();
     n.reserve(cap + 1);
