@@ -1,24 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- matched image-pairs / second on the compute-matches hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c3|c2|c2-msurf64|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload at every N: BASELINE.json configs[1] (C2) PER GPU -- 50 synthetic 1080p images x 10 000
-float descriptors (D = 144, Regard3D's native R3D_AKAZE_LIOP_Regions layout), exhaustive pairs
-(1 225), brute-force L2 2-NN + ratio 0.6 + de-duplications.  One step = one pass over all pairs.
-N > 1: one process per GPU, every rank owns an independent 50-image set (weak scaling; image pairs
-shard with no data-path collective); torch.distributed (NCCL) is only used for the
-barrier and the max-over-ranks of the step time.
+Workload (default): BASELINE.json configs[2] = **C3**, the configuration the north_star target is quoted on:
+200 synthetic images x 20 000 SIFT-128 uint8 descriptors, exhaustive pairs (19 900), brute-force L2 2-NN +
+ratio 0.6 + (i,j) and coordinate de-duplication.  It fits one B200 (0.5 GB of descriptors + 1.4 GB of fp16
+operands), so N = 1 runs the whole set.  One step = one pass over ALL 19 900 pairs.
 
-value : pairs/s with descriptors already resident in HBM (r3d_match_pairs only; results land in
-        host memory, host de-duplication included).
-e2e   : pairs/s through the C ABI from pinned HOST buffers: r3d_clear_regions + r3d_upload_regions
-        of every view + r3d_match_pairs, every step.
-roofline : the tcgen05 candidate kernel, algorithmic 2*N_I*N_J*D flop per pair over
-        its CUDA-event time on its own stream, against MEASURED_PEAKS.json bf16 TFLOP/s.
-cpu_baseline : the oracle port (same serial-I / omp-J structure as the reference) on a bounded
-        sample of the same pairs, all host threads it can use.
+N > 1 = STRONG scaling of that one set: every rank holds the regions its shard touches, the I-sorted pair list
+is cut into cost-balanced contiguous ranges (regard3d_b200/sharding.py), no data-path collective;
+the per-rank PairWiseMatches are gathered to rank 0 IN PAIR ORDER INSIDE THE TIMED REGION (CSR export -> NCCL
+send/recv over NVLink -> rank 0's pinned host buffer), so the clock stops when rank 0 holds every match list in
+host memory -- the reference's `map_PutativesMatches` (src/R3DComputeMatches.cpp:437-488).
+
+value : pairs/s, descriptors already resident in HBM (r3d_match_pairs on the shard + gather).
+e2e   : pairs/s through the C ABI from pinned HOST buffers: r3d_clear_regions + r3d_upload_regions of every view
+        the shard touches + r3d_match_pairs + gather, every step.
+roofline : the tcgen05 candidate kernel, algorithmic 2*N_I*N_J*D flop per pair over its
+        CUDA-event time on its own stream, against MEASURED_PEAKS.json bf16 TFLOP/s.
+cpu_baseline : the oracle port on a bounded sample of the same pairs with all usable host threads (N = 1 only).
+f_filter / ba : the F AC-RANSAC leg over the step's putatives and the C5 bundle adjustment, reported alongside.
+--impl reference : the reference's CPU path (oracle port; the reference itself cannot be built here) on a
+        bounded sample of the same workload per step, explicit OMP team = the usable CPUs (torchrun exports
+        OMP_NUM_THREADS=1, which is ignored on purpose).
 """
 import argparse
 import json
@@ -33,15 +39,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_IMAGES, N_FEATS, DIM, KIND, RATIO = 50, 10000, 144, "liop", 0.6
-WORKLOAD, AS_U8 = "C2", False
-# BASELINE.json configs; C2 is the bench line (the metric's single-GPU configuration), the others are
-# selectable for the record: `--workload c3|c4` (C4 = exact GPU matcher in place of CPU cascade hashing, + F filter)
+RATIO = 0.6
 WORKLOADS = {
-    "c2": dict(images=50, feats=10000, dim=144, kind="liop", u8=False, name="C2"),
-    "c2-msurf64": dict(images=50, feats=10000, dim=64, kind="msurf", u8=False, name="C2 (MSURF-64)"),
-    "c3": dict(images=200, feats=20000, dim=128, kind="sift", u8=True, name="C3"),
-    "c4": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 (exact matcher + F filter)"),
+    "c2": dict(images=50, feats=10000, dim=144, kind="liop", u8=False, name="C2 (LIOP-144)", seed=2),
+    "c2-msurf64": dict(images=50, feats=10000, dim=64, kind="msurf", u8=False, name="C2 (MSURF-64 = AKAZE-float)", seed=2),
+    "c3": dict(images=200, feats=20000, dim=128, kind="sift", u8=True, name="C3", seed=3),
+    "c4": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 (exact matcher + F filter)", seed=4),
 }
 METRIC = "matched_image_pairs_per_sec_exhaustive"
 
@@ -49,8 +52,7 @@ METRIC = "matched_image_pairs_per_sec_exhaustive"
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return d, "measured"
+        return json.load(open(p)), "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
@@ -100,7 +102,6 @@ class ClockSampler:
             for k, nm in enumerate(names):
                 if f[3 + k].lower().startswith("active"):
                     reasons.add(nm)
-        # "under load": samples in the upper half of what was seen
         if not sm:  # the region was shorter than one sampling period: one synchronous reading
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
@@ -109,11 +110,7 @@ class ClockSampler:
                 sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
             except Exception:
                 pass
-        if sm:
-            hi = [x for x in sm if x >= 0.5 * max(sm)]
-            med = float(np.median(hi))
-        else:
-            med = None
+        med = float(np.median([x for x in sm if x >= 0.5 * max(sm)])) if sm else None  # "under load" samples
         return {"sm_mhz": med, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
@@ -131,71 +128,98 @@ def effective_cpus():
     return n
 
 
-def measured_traffic_per_pair():
+def measured_traffic_per_pair(wl_key):
     """DRAM bytes per image pair of the candidate kernel, from the committed `ncu --set full` capture of one
-    128-pair launch (profiles/r01_k_l2_candidates_2sm_keymetrics.csv); None when the file is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_k_l2_candidates_2sm_keymetrics.csv")
+    batch launch of THIS workload (profiles/*_keymetrics.csv: dram__bytes_read/write + the pairs the launch held);
+    None when no capture of this workload is committed."""
+    name = {"c3": "r02_k_l2_candidates_2sm_c3_keymetrics.csv", "c2": "r01_k_l2_candidates_2sm_keymetrics.csv"}.get(wl_key)
+    if not name:
+        return None, None
+    p = os.path.join(ROOT, "profiles", name)
     if not os.path.exists(p):
-        return None
+        return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
+    tot, pairs = 0.0, 128.0
     for ln in open(p):
         f = ln.strip().split(",")
         if len(f) >= 4 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(f[2]) * unit.get(f[3], 1.0)
-    return tot / 128.0 if tot else None
+        if len(f) >= 3 and f[1] == "pairs_in_launch":
+            pairs = float(f[2])
+    return (tot / pairs if tot else None), "profiles/" + name
 
 
-def make_workload(seed):
+def make_workload(wl):
     from regard3d_b200 import synth
-    sc = synth.make_scene(N_IMAGES, N_FEATS, DIM, KIND, seed=seed, as_u8=AS_U8)
-    pairs = synth.exhaustive_pairs(N_IMAGES)
-    return sc, pairs
+    sc = synth.make_scene(wl["images"], wl["feats"], wl["dim"], wl["kind"], seed=20260924 + wl["seed"], as_u8=wl["u8"])
+    return sc, synth.exhaustive_pairs(wl["images"])
 
 
-def run_reference(args, rank, world, emit):
-    """--impl reference: the reference's CPU path = the oracle port (the reference's own code cannot
-    be built here: OpenMVG/Ceres/Eigen/wx are neither vendored nor installed)."""
+def workload_config(wl, world):
+    P = wl["images"] * (wl["images"] - 1) // 2
+    esz = 1 if wl["u8"] else 4
+    return {"workload": "%s: %d images x %d feats, D=%d %s (%s-like), exhaustive %d pairs, ratio %.1f"
+                        % (wl["name"], wl["images"], wl["feats"], wl["dim"], "uint8" if wl["u8"] else "float32",
+                           wl["kind"], P, RATIO),
+            "images": wl["images"], "feats_per_image": wl["feats"], "dim": wl["dim"], "pairs": P,
+            "parallelism": ("one GPU, all pairs" if world == 1 else
+                            "ONE pair list cut into %d cost-balanced contiguous shards (sharding.my_shard), no data-path "
+                            "collective, per-rank results gathered to rank 0 in pair order inside the timed region" % world),
+            "l2_policy": "inputs (descriptors + fp16 operands, %.1f GB) exceed the 126 MB L2"
+                         % (wl["images"] * wl["feats"] * (wl["dim"] * esz + 2 * 2 * (wl["dim"] + 48)) / 1e9)}
+
+
+def first_pairs(m, n):
+    """The first n entries of a PairWiseMatches map as {(I, J): matches}."""
+    out = {}
+    for k in range(min(m.num_pairs, n)):
+        I, J, mm = m.pair(k)
+        out[(I, J)] = mm
+    return out
+
+
+def cpu_match_sample(po, sc, sample, n_threads):
+    """The oracle port on `sample` pairs, one pair after another, upstream's own `#pragma omp parallel for` over the
+    queries of SearchNeighbours using all n_threads (the outer omp-over-J team of src/R3DComputeMatches.cpp:465 would
+    leave threads idle on a sample smaller than the team; this is the CPU's best case)."""
+    out = []
+    t0 = time.perf_counter()
+    for I, J in sample:
+        out.append(po.match_distance_ratio(sc["descs"][int(I)], sc["xys"][int(I)], sc["descs"][int(J)],
+                                           sc["xys"][int(J)], RATIO, n_threads=n_threads))
+    return time.perf_counter() - t0, out
+
+
+def run_reference(args, wl, rank, emit):
+    """--impl reference: the reference's CPU path = the oracle port (the reference's own code cannot be built
+    here: OpenMVG/Ceres/Eigen/wx are neither vendored nor installed)."""
     if rank != 0:
         return
     from oracle import pyoracle as po
-    sc, pairs = make_workload(20260924 + 2)
-    nthreads = po.num_threads()
-    # bounded sample: all pairs that share the first image(s) -- the reference parallelises over J
-    # for a fixed I (src/R3DComputeMatches.cpp:465), so one I gives up to 49 concurrent J's.
-    n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "49"))
+    sc, pairs = make_workload(wl)
+    nthreads = effective_cpus()          # explicit team: torchrun's OMP_NUM_THREADS=1 must not shrink the CPU arm
+    pair_cost = wl["feats"] * wl["feats"] * wl["dim"] / (20000.0 * 20000.0 * 128.0)     # relative to a C3 pair
+    n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "0")) or int(np.clip(round(nthreads / 4.0 / pair_cost), 2, 64))
     sample = pairs[:n_sample]
     times = []
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        po.match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
-        dt = time.perf_counter() - t0
+        dt, _ = cpu_match_sample(po, sc, sample, nthreads)
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
     value = len(sample) * len(times) / total
-    cores = min(nthreads, len(sample), effective_cpus())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(),
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d pairs (I=0, J=1..%d) of the set per step, omp over J, %d threads on %d usable CPUs "
-                                   "(cgroup quota)" % (len(sample), len(sample), nthreads, effective_cpus())},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, max(args.gpus, 1)),
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": nthreads, "kind": "port",
+                         "sample": "%d pairs (I=0, J=1..%d) of the set per step, pairs in sequence, omp over the queries "
+                                   "of SearchNeighbours with %d threads = usable CPUs (cgroup quota; OMP_NUM_THREADS "
+                                   "ignored)" % (len(sample), len(sample), nthreads)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
-
-
-def workload_config():
-    return {"workload": "%s: %d images x %d feats, D=%d %s (%s-like), exhaustive %d pairs, ratio %.1f"
-                        % (WORKLOAD, N_IMAGES, N_FEATS, DIM, "uint8" if AS_U8 else "float32", KIND,
-                           N_IMAGES * (N_IMAGES - 1) // 2, RATIO),
-            "images": N_IMAGES, "feats_per_image": N_FEATS, "dim": DIM, "pairs": N_IMAGES * (N_IMAGES - 1) // 2,
-            "parallelism": "pairs sharded per GPU, no collective",
-            "l2_policy": "inputs (descriptors + fp16 operands, %.1f GB) exceed the 126 MB L2"
-                         % (N_IMAGES * N_FEATS * (DIM * (1 if AS_U8 else 4) + 2 * 2 * (DIM + 48)) / 1e9)}
 
 
 def main():
@@ -207,8 +231,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ba", action="store_true", help="skip the bundle-adjustment leg")
     ap.add_argument("--no-filter", action="store_true", help="skip the F-filter leg")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE config (default c2 = the bench line)")
-    ap.add_argument("--dim", type=int, default=0, help="experiment only: 64 -> MSURF-like D=64 set")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 D=64 / D=144 side lines (N = 1)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="BASELINE config (default c3 = the north-star set)")
     ap.add_argument("--feats", type=int, default=0, help="experiment only")
     ap.add_argument("--images", type=int, default=0, help="experiment only")
     args = ap.parse_args()
@@ -219,239 +243,315 @@ def main():
 
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
-    global DIM, KIND, N_FEATS, N_IMAGES, WORKLOAD, AS_U8
-    wl = WORKLOADS[args.workload]
-    N_IMAGES, N_FEATS, DIM, KIND, AS_U8, WORKLOAD = wl["images"], wl["feats"], wl["dim"], wl["kind"], wl["u8"], wl["name"]
-    if args.workload != "c2":
-        os.environ.setdefault("R3D_REF_SAMPLE_PAIRS", "16")
-    if args.dim == 64:
-        DIM, KIND = 64, "msurf"
-    elif args.dim == 128:
-        DIM, KIND = 128, "sift"
+    wl = dict(WORKLOADS[args.workload])
     if args.feats:
-        N_FEATS = args.feats
+        wl["feats"] = args.feats
     if args.images:
-        N_IMAGES = args.images
+        wl["images"] = args.images
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world, emit)
+        run_reference(args, wl, rank, emit)
         return 0
 
     import torch
     import torch.distributed as dist
-    from regard3d_b200 import capi
+    from regard3d_b200 import capi, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=device)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def sum_over_ranks(*vals):
+        if world == 1:
+            return list(vals)
+        t = torch.tensor(vals, dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    warmup = max(args.warmup, 3)
     ctx = capi.Context((local_rank,))
-    sc, pairs = make_workload(20260924 + 2 + 1000 * rank)
+    sc, pairs = make_workload(wl)
+    n_img, n_feats, dim = wl["images"], wl["feats"], wl["dim"]
+    counts = np.array([len(d) for d in sc["descs"]], np.int64)
+    my_pairs, my_ofs = sharding.my_shard(pairs, counts, rank, world)
+    my_pairs = np.ascontiguousarray(my_pairs, np.uint32)
+    my_views = sorted(set(np.unique(my_pairs).tolist()))
     n_pairs = len(pairs)
     # pinned host staging (the e2e leg copies from here every step)
-    pinned_desc, pinned_xy = [], []
-    for v in range(N_IMAGES):
-        d = torch.from_numpy(sc["descs"][v]).pin_memory()
-        x = torch.from_numpy(sc["xys"][v]).pin_memory()
-        pinned_desc.append(d)
-        pinned_xy.append(x)
+    pinned_desc = {v: torch.from_numpy(sc["descs"][v]).pin_memory() for v in my_views}
+    pinned_xy = {v: torch.from_numpy(sc["xys"][v]).pin_memory() for v in my_views}
+    gather = sharding.Gather(rank, world, device) if world > 1 else None
 
     def upload_all():
-        for v in range(N_IMAGES):
+        for v in my_views:
             ctx.upload_regions(v, pinned_desc[v].numpy(), pinned_xy[v].numpy())
+
+    def step_resident():
+        m = ctx.match_pairs(my_pairs, RATIO)
+        if gather is not None:
+            gather(m)
+        return m
 
     # ---------------- resident leg: `value` ----------------
     upload_all()
-    for _ in range(max(args.warmup, 3)):
-        m = ctx.match_pairs(pairs, RATIO)
+    for _ in range(warmup):
+        m = step_resident()
     sampler = ClockSampler(local_rank)
     cand_ms, rerank_ms, fb_ms, dev_ms, host_ms, launches = [], [], [], [], [], 0
     fbq = q = rejq = 0
+    d2h_lib = 0
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        m = ctx.match_pairs(pairs, RATIO)
+        m = step_resident()
         t = ctx.match_timing()
         cand_ms.append(t["ms_candidates"]); rerank_ms.append(t["ms_rerank"]); fb_ms.append(t["ms_fallback"])
         dev_ms.append(t["ms_device_total"]); host_ms.append(t["ms_host_post"])
         launches += t["kernel_launches"]
         fbq += t["fallback_queries"]; q += t["queries"]; rejq += t["rejected_queries"]
-        d2h_step = t["d2h_bytes"]
     barrier()
     t_res = time.perf_counter() - t0
-    n_matches = m.total
-    n_match_pairs = m.num_pairs
+    n_matches, n_match_pairs = sum_over_ranks(m.total, m.num_pairs)
 
     # ---------------- end-to-end leg: `e2e` ----------------
     for _ in range(2):
-        ctx.clear_regions(); upload_all(); ctx.match_pairs(pairs, RATIO)
+        ctx.clear_regions(); upload_all(); step_resident()
     barrier()
     t0 = time.perf_counter()
-    h2d_step = 0
+    h2d_step = d2h_step = 0
     for _ in range(args.steps):
         ctx.clear_regions()
         upload_all()
-        m2 = ctx.match_pairs(pairs, RATIO)
+        m2 = step_resident()
         t = ctx.match_timing()
-        h2d_step = t["h2d_bytes"]
-        d2h_e2e = t["d2h_bytes"]
-        launches_e2e = t["kernel_launches"]
+        h2d_step = t["h2d_bytes"] + (gather.h2d if gather else 0)
+        d2h_step = t["d2h_bytes"] + (gather.d2h if gather else 0)
     barrier()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop()   # sampled over both timed regions (resident + end-to-end), all of it under load
+    t_res, t_e2e = max_over_ranks(t_res, t_e2e)
+    h2d_step, d2h_step, launches_all = sum_over_ranks(h2d_step, d2h_step, launches)
 
-    # ---------------- geometric filter leg (reported alongside; BASELINE C2 itself stops at putatives) ----------------
+    # gathered result == what the ranks hold (rank 0, outside the timed region): pair order and totals
+    gather_ok = None
+    if gather is not None and rank == 0:
+        parts = gather.result()
+        allp = np.concatenate([p[0] for p in parts], 0).astype(np.int64)
+        key = allp[:, 0] * (1 << 32) + allp[:, 1]
+        gather_ok = bool(np.all(np.diff(key) > 0)) and sum(int(p[1][-1]) for p in parts) == int(n_matches) \
+            and all(int(p[1][-1]) == len(p[2]) for p in parts)
+
+    # ---------------- geometric filter leg (sharded like the matching; reported alongside) ----------------
     filt = None
     if not args.no_filter:
         ctx.filter_pairs(m2, sc["widths"], sc["heights"])            # warm-up
-        torch.cuda.synchronize()
+        barrier()
         tf0 = time.perf_counter()
         fm = ctx.filter_pairs(m2, sc["widths"], sc["heights"])
+        torch.cuda.synchronize()
         tf = time.perf_counter() - tf0
         ft = ctx.filter_timing()
-        filt = {"pairs_per_s": m2.num_pairs / tf, "ms": 1e3 * tf, "pairs_in": m2.num_pairs, "pairs_kept": fm.num_pairs,
-                "inliers": fm.total, "hypotheses": int(ft["hypotheses"]), "rounds": int(ft["rounds"]),
+        (tf,) = max_over_ranks(tf)
+        pin, pkept, inl, hyp = sum_over_ranks(m2.num_pairs, fm.num_pairs, fm.total, ft["hypotheses"])
+        filt = {"pairs_per_s": pin / tf, "ms": 1e3 * tf, "pairs_in": int(pin), "pairs_kept": int(pkept),
+                "inliers": int(inl), "hypotheses": int(hyp), "rounds": int(ft["rounds"]),
                 "ms_solve": ft["ms_solve"], "ms_score": ft["ms_score"], "ms_host": ft["ms_host"],
-                "kernel_launches": int(ft["kernel_launches"]),
-                "what": "AC-RANSAC fundamental filter (4 px, 2048 it.) over all putative pairs of the step"}
+                "ms_device_total": ft["ms_device_total"], "kernel_launches": int(ft["kernel_launches"]), "n_gpus": world,
+                "what": "AC-RANSAC fundamental filter (4 px, 2048 it.) over all putative pairs of the step, each rank "
+                        "filtering its own shard; max over ranks"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as po
+            nthreads = effective_cpus()
+            ns = int(np.clip(4 * nthreads, 32, 256))
+            put_d = first_pairs(m2, 2 * ns)
+            sp = np.array(sorted(put_d)[:ns], np.uint32).reshape(-1, 2)
+            ns = len(sp)
+            sofs = np.zeros(ns + 1, np.uint64)
+            sofs[1:] = np.cumsum([len(put_d[(int(I), int(J))]) for I, J in sp])
+            sm = np.concatenate([put_d[(int(I), int(J))] for I, J in sp]) if ns else np.zeros(0, capi.indmatch_dtype)
+            tc0 = time.perf_counter()
+            o_ofs, o_m = po.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], sp, sofs, sm, n_threads=nthreads)
+            tc = time.perf_counter() - tc0
+            fd = first_pairs(fm, 2 * ns)
+            same = True
+            for k, (I, J) in enumerate(sp):
+                e = o_m[int(o_ofs[k]):int(o_ofs[k + 1])]
+                g = fd.get((int(I), int(J)))
+                same &= (len(e) == 0 and g is None) or (g is not None and len(g) == len(e) and
+                                                         np.array_equal(g["i"], e["i"]) and np.array_equal(g["j"], e["j"]))
+            filt["cpu_baseline"] = {"value": ns / tc, "unit": "pairs/s", "cores": nthreads, "kind": "port",
+                                    "sample": "first %d pairs of the step's putatives, omp over pairs, %.1f s" % (ns, tc),
+                                    "parity_on_sample": bool(same)}
 
     # ---------------- bundle-adjustment leg (BASELINE C5, reported alongside) ----------------
     # N > 1: STRONG scaling of the one C5 problem -- points (+ their observations) partitioned over the
-    # ranks, cameras replicated, one in-library ncclAllReduce of the reduced camera system per LM iteration.
+    # ranks, cameras replicated, in-library ncclAllReduce of the reduced camera system per LM iteration.
     ba = None
     if not args.no_ba:
-        from regard3d_b200 import sharding, synth
-        prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
-        arrs = {k: np.ascontiguousarray(v) for k, v in prob.items() if k != "truth"}
-        for k in ("poses", "intrinsics", "points", "obs_xy"):
-            arrs[k] = np.ascontiguousarray(arrs[k], np.float64)
-        for k in ("obs_cam", "obs_pt", "cam_intr"):
-            arrs[k] = np.ascontiguousarray(arrs[k], np.uint32)
-        if world > 1:
-            ids = [ctx.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            ctx.comm_init(world, rank, ids[0])
-        local, _ = sharding.partition_ba(arrs, rank, world)
-        ctx.bundle_adjust({k: v.copy() for k, v in local.items()}, max_iterations=2)     # warm-up
-        n_it = 10
-        g = {k: v.copy() for k, v in local.items()}
-        barrier()
-        tb0 = time.perf_counter()
-        sg, tg = ctx.bundle_adjust(g, max_iterations=n_it, function_tolerance=0.0)
-        tb = time.perf_counter() - tb0
-        t_loop = max(sg["seconds_total"] - sg["seconds_setup"], 1e-9)
-        if world > 1:
-            tt = torch.tensor([t_loop, tb], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            t_loop, tb = float(tt[0]), float(tt[1])
-            ctx.comm_destroy()
-        n_obs = int(len(arrs["obs_xy"]))
-        nB = 6 * 200 + 6
-        bytes_iter = 3 * (n_obs * 24 + len(arrs["points"]) * 24) + 2 * nB * nB * 8
-        ba = {"iters_per_s": sg["iterations"] / t_loop, "e2e_iters_per_s": sg["iterations"] / tb,
-              "iterations": int(sg["iterations"]), "seconds_lm_loop": t_loop, "seconds_call": tb,
-              "seconds_setup": sg["seconds_setup"], "seconds_linear": sg["seconds_linear"],
-              "initial_cost": sg["initial_cost"], "final_cost": sg["final_cost"], "n_gpus": world,
-              "scaling": "strong", "exchange": "none" if world == 1 else
-              "ncclAllReduce(f64) of S|rhs = %d doubles per LM iteration + 5 scalar/vector reductions" % (nB * nB + nB),
-              "config": "C5: 200 cams / %d pts / %d obs, 1 shared radial-K3 intrinsic, Huber(16)" % (len(arrs["points"]), n_obs),
-              "roofline": {"bound": "hbm", "achieved": sg["iterations"] / t_loop * bytes_iter / 1e9,
-                           "peak": float(load_peaks()[0].get("hbm_gbs", 6650.0)), "unit": "GB/s",
-                           "frac": sg["iterations"] / t_loop * bytes_iter / 1e9 / float(load_peaks()[0].get("hbm_gbs", 6650.0)),
-                           "bytes_per_iter": bytes_iter}}
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import pyoracle as po
-            c = po.ba_prepare(arrs["poses"], arrs["intrinsics"], arrs["points"], arrs["obs_cam"], arrs["obs_pt"],
-                              arrs["cam_intr"], arrs["obs_xy"])
-            o = po.default_ba_options(max_iterations=3)
-            o.function_tolerance = 0.0
-            tc0 = time.perf_counter()
-            so, to = po.bundle_adjust(c, o)
-            tcb = time.perf_counter() - tc0
-            ba["cpu_baseline"] = {"iters_per_s": so["iterations"] / tcb, "iterations": int(so["iterations"]),
-                                  "cores": min(po.num_threads(), effective_cpus()), "kind": "port",
-                                  "cost_trace_rel_diff": float(np.max(np.abs(tg[:len(to)] - to) / to))}
+        ba = ba_leg(args, ctx, torch, dist, rank, world, barrier, max_over_ranks)
 
-    if world > 1:
-        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_res, t_e2e = float(tt[0]), float(tt[1])
+    # ---------------- side lines: C2 at D = 64 (AKAZE-float / MSURF) and D = 144 (LIOP), N = 1 ----------------
+    extras = None
+    if world == 1 and not args.no_extras and args.workload == "c3":
+        extras = {}
+        for key in ("c2-msurf64", "c2"):
+            w2 = WORKLOADS[key]
+            sc2, pairs2 = make_workload(w2)
+            ctx.clear_regions()
+            for v in range(w2["images"]):
+                ctx.upload_regions(v, sc2["descs"][v], sc2["xys"][v])
+            for _ in range(3):
+                ctx.match_pairs(pairs2, RATIO)
+            torch.cuda.synchronize()
+            c_ms = []
+            te0 = time.perf_counter()
+            for _ in range(5):
+                mm = ctx.match_pairs(pairs2, RATIO)
+                c_ms.append(ctx.match_timing()["ms_candidates"])
+            torch.cuda.synchronize()
+            te = time.perf_counter() - te0
+            fl = 2.0 * w2["feats"] * w2["feats"] * w2["dim"] * len(pairs2)
+            peak = float(load_peaks()[0].get("bf16_tflops", 1590.0))
+            extras[key] = {"workload": workload_config(w2, 1)["workload"], "pairs_per_s": 5 * len(pairs2) / te,
+                           "ms_candidates": float(np.mean(c_ms)),
+                           "roofline_frac": fl / (np.mean(c_ms) * 1e-3) / 1e12 / peak, "matches": mm.total}
+            del sc2
 
     if rank == 0:
         peaks, peak_src = load_peaks()
-        total_pairs = n_pairs * world * args.steps
-        value = total_pairs / t_res
-        e2e = total_pairs / t_e2e
-        flop_per_launch = 2.0 * N_FEATS * N_FEATS * DIM * n_pairs          # one launch = all pairs of the step
+        value = n_pairs * args.steps / t_res
+        e2e = n_pairs * args.steps / t_e2e
+        my_flop = 2.0 * float(np.sum(counts[my_pairs[:, 0].astype(np.int64)] * counts[my_pairs[:, 1].astype(np.int64)])) * dim
         ms_c = float(np.mean(cand_ms))
-        achieved = flop_per_launch / (ms_c * 1e-3) / 1e12
+        achieved = my_flop / (ms_c * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))
-        tpp = measured_traffic_per_pair()
+        tpp, tsrc = measured_traffic_per_pair(args.workload)
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(), "clocks": clocks,
+            "warmup": warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8" if wl["u8"] else "f32",
+            "data": "synthetic", "config": workload_config(wl, world), "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
-                    "d2h_bytes_per_step": int(d2h_e2e), "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches),
+                    "d2h_bytes_per_step": int(d2h_step), "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "bytes": "whole job (sum over ranks): r3d_upload_regions of the views each shard touches + packed "
+                             "matches back" + (" + the gather's H2D on the senders / D2H on rank 0" if world > 1 else "")},
+            "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor", "kernel": "k_l2_candidates_2sm (tcgen05 kind::f16 cta_group::2, f16 candidates; "
-                                                      "every reported distance is re-computed in f32)",
+                                                      "every reported distance is re-computed exactly)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "peak_source": "%s bf16_tflops (burst; kernel timed alone with CUDA events)" % peak_src,
-                         "ms_per_launch": ms_c, "flop_per_launch": flop_per_launch,
-                         "launch": "one step = all %d pairs (13 batch launches of <= 128 pairs, summed)" % n_pairs,
-                         "traffic": (tpp * n_pairs if tpp and DIM == 144 and N_FEATS == 10000 else None),
-                         "traffic_unit": "DRAM bytes per step (ncu dram__bytes_read+write of one 128-pair launch, "
-                                         "scaled to the step's pairs; profiles/r01_k_l2_candidates_2sm_keymetrics.csv)"},
+                         "ms_per_launch": ms_c, "flop_per_launch": my_flop,
+                         "launch": "rank 0's shard of the step = %d pairs (batch launches of <= 128 pairs, summed)" % len(my_pairs),
+                         "traffic": (tpp * len(my_pairs) if tpp else None),
+                         "traffic_unit": "DRAM bytes per step of rank 0 (ncu dram__bytes_read+write of one batch launch, "
+                                         "scaled to the shard's pairs; %s)" % tsrc},
             "breakdown_ms": {"candidates": ms_c, "rerank": float(np.mean(rerank_ms)),
                              "exact_scan_and_pack": float(np.mean(fb_ms)), "device_total": float(np.mean(dev_ms)),
-                             "host_dedup": float(np.mean(host_ms))},
+                             "host_dedup": float(np.mean(host_ms)), "of": "rank 0's shard"},
             "result": {"pairs_with_matches": int(n_match_pairs), "matches": int(n_matches),
-                       "fallback_query_frac": fbq / max(q, 1), "early_rejected_query_frac": rejq / max(q, 1)},
+                       "fallback_query_frac": fbq / max(q, 1), "early_rejected_query_frac": rejq / max(q, 1),
+                       "gathered_in_pair_order": gather_ok},
         }
         if filt is not None:
             line["f_filter"] = filt
         if ba is not None:
             line["ba"] = ba
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as po
-            nthreads = po.num_threads()
-            n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "49"))
+            nthreads = effective_cpus()
+            n_sample = int(os.environ.get("R3D_CPU_SAMPLE_PAIRS", "0")) or int(np.clip(nthreads, 8, 32))
             sample = pairs[:n_sample]
-            tc0 = time.perf_counter()
-            o_ofs, o_m = po.match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
-            tc = time.perf_counter() - tc0
-            # the checker doubles as a parity probe on the sampled pairs
-            got = m.to_dict()
+            tc, outs = cpu_match_sample(po, sc, sample, nthreads)
+            got = first_pairs(m, 4 * n_sample)
             same = True
-            for k, (I, J) in enumerate(sample):
-                e = o_m[int(o_ofs[k]):int(o_ofs[k + 1])]
+            for (I, J), e in zip(sample, outs):
                 g = got.get((int(I), int(J)))
-                same &= (g is not None and len(g) == len(e) and set(zip(g["i"].tolist(), g["j"].tolist())) ==
-                         set(zip(e["i"].tolist(), e["j"].tolist()))) or (g is None and len(e) == 0)
-            line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s",
-                                    "cores": min(nthreads, len(sample), effective_cpus()),
-                                    "kind": "port",
-                                    "sample": "%d pairs (I=0) of the same set, one pass, %d omp threads on %d usable CPUs "
-                                              "(cgroup quota), %.1f s" % (len(sample), nthreads, effective_cpus(), tc),
+                same &= (g is None and len(e) == 0) or (g is not None and len(g) == len(e) and
+                                                         np.array_equal(g["i"], e["i"]) and np.array_equal(g["j"], e["j"]))
+            line["cpu_baseline"] = {"value": len(sample) / tc, "unit": "pairs/s", "cores": nthreads, "kind": "port",
+                                    "sample": "%d pairs (I=0) of the same set, one pass, pairs in sequence, omp over the "
+                                              "queries with %d threads = usable CPUs (cgroup quota), %.1f s"
+                                              % (len(sample), nthreads, tc),
                                     "parity_on_sample": bool(same)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ba_leg(args, ctx, torch, dist, rank, world, barrier, max_over_ranks):
+    from regard3d_b200 import sharding, synth
+    prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
+    arrs = {k: np.ascontiguousarray(v) for k, v in prob.items() if k != "truth"}
+    for k in ("poses", "intrinsics", "points", "obs_xy"):
+        arrs[k] = np.ascontiguousarray(arrs[k], np.float64)
+    for k in ("obs_cam", "obs_pt", "cam_intr"):
+        arrs[k] = np.ascontiguousarray(arrs[k], np.uint32)
+    if world > 1:
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(world, rank, ids[0])
+    local, _ = sharding.partition_ba(arrs, rank, world)
+    ctx.bundle_adjust({k: v.copy() for k, v in local.items()}, max_iterations=2)     # warm-up
+    n_it = 10
+    g = {k: v.copy() for k, v in local.items()}
+    barrier()
+    tb0 = time.perf_counter()
+    sg, tg = ctx.bundle_adjust(g, max_iterations=n_it, function_tolerance=0.0)
+    tb = time.perf_counter() - tb0
+    t_loop = max(sg["seconds_total"] - sg["seconds_setup"], 1e-9)
+    t_loop, tb = max_over_ranks(t_loop, tb)
+    if world > 1:
+        ctx.comm_destroy()
+    n_obs = int(len(arrs["obs_xy"]))
+    nB = 6 * 200 + 6
+    bytes_iter = 3 * (n_obs * 24 + len(arrs["points"]) * 24) + 2 * nB * nB * 8
+    peak_hbm = float(load_peaks()[0].get("hbm_gbs", 6650.0))
+    ba = {"iters_per_s": sg["iterations"] / t_loop, "e2e_iters_per_s": sg["iterations"] / tb,
+          "iterations": int(sg["iterations"]), "seconds_lm_loop": t_loop, "seconds_call": tb,
+          "seconds_setup": sg["seconds_setup"], "seconds_linear": sg["seconds_linear"],
+          "initial_cost": sg["initial_cost"], "final_cost": sg["final_cost"], "n_gpus": world,
+          "scaling": "strong", "exchange": "none" if world == 1 else
+          "in-library ncclAllReduce(f64) of the reduced camera system per LM iteration",
+          "config": "C5: 200 cams / %d pts / %d obs, 1 shared radial-K3 intrinsic, Huber(16)" % (len(arrs["points"]), n_obs),
+          "roofline": {"bound": "hbm", "achieved": sg["iterations"] / t_loop * bytes_iter / 1e9,
+                       "peak": peak_hbm, "unit": "GB/s",
+                       "frac": sg["iterations"] / t_loop * bytes_iter / 1e9 / peak_hbm, "bytes_per_iter": bytes_iter}}
+    if world == 1 and rank == 0 and not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        c = po.ba_prepare(arrs["poses"], arrs["intrinsics"], arrs["points"], arrs["obs_cam"], arrs["obs_pt"],
+                          arrs["cam_intr"], arrs["obs_xy"])
+        o = po.default_ba_options(max_iterations=3, n_threads=effective_cpus())
+        o.function_tolerance = 0.0
+        tc0 = time.perf_counter()
+        so, to = po.bundle_adjust(c, o)
+        tcb = time.perf_counter() - tc0
+        ba["cpu_baseline"] = {"iters_per_s": so["iterations"] / tcb, "iterations": int(so["iterations"]),
+                              "cores": effective_cpus(), "kind": "port",
+                              "cost_trace_rel_diff": float(np.max(np.abs(tg[:len(to)] - to) / to))}
+    return ba
 
 
 if __name__ == "__main__":

@@ -90,6 +90,12 @@ int r3d_matches_get_pair(const r3d_matches* m, uint64_t k, uint32_t* I, uint32_t
 /* Build a PairWiseMatches from CSR arrays (pair_ofs has n_pairs+1 entries). */
 int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t* pair_ofs,
                          const r3d_indmatch* matches, r3d_matches** out);
+/* Flat copy of the map in std::map order: pairs_out 2 x num_pairs view ids, ofs_out num_pairs + 1 prefix offsets,
+ * matches_out r3d_matches_total() entries; any output may be NULL.  This is what a per-GPU process ships when the
+ * pair list is sharded over ranks and the PairWiseMatches map is re-assembled on one of them (SURVEY.md 8e:
+ * "results concatenated on host in pair order"; the reference's map insert is src/R3DComputeMatches.cpp:483-486). */
+int r3d_matches_export_csr(const r3d_matches* m, uint32_t* pairs_out, uint64_t* ofs_out,
+                           r3d_indmatch* matches_out);
 void r3d_free_matches(r3d_matches* m);
 /* matching::Save / matching::Load, text format (src/R3DComputeMatches.cpp:2064, :2120;
  * SURVEY.md Appendix B.3). */

@@ -25,7 +25,7 @@ EXPORTS = [
     "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
     "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
     "r3d_comm_unique_id", "r3d_comm_init", "r3d_comm_destroy", "r3d_comm_world", "r3d_debug_post_process",
-    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked",
+    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr",
 ]
 
 
@@ -195,6 +195,22 @@ class Matches:
                 chunks.append(m)
         allm = np.concatenate(chunks) if chunks else np.zeros(0, indmatch_dtype)
         return ofs, allm
+
+    def export_csr(self, pairs_out=None, ofs_out=None, matches_out=None):
+        """(pairs[P,2] u32, ofs[P+1] u64, matches[total]) in map order -- one memcpy per pair inside the library.
+        Caller buffers (e.g. pinned torch tensors viewed as numpy) may be passed to avoid allocations."""
+        P, T = self.num_pairs, self.total
+        if pairs_out is None:
+            pairs_out = np.empty((P, 2), np.uint32)
+        if ofs_out is None:
+            ofs_out = np.empty(P + 1, np.uint64)
+        if matches_out is None:
+            matches_out = np.empty(T, indmatch_dtype)
+        assert pairs_out.size >= 2 * P and ofs_out.size >= P + 1 and matches_out.size >= T
+        rc = lib().r3d_matches_export_csr(self.handle, _p(pairs_out), _p(ofs_out), _p(matches_out))
+        if rc:
+            raise R3DError(rc, "r3d_matches_export_csr")
+        return pairs_out, ofs_out, matches_out
 
     def save_txt(self, path):
         rc = lib().r3d_save_matches_txt(self.handle, path.encode())

@@ -3,8 +3,10 @@
 // Save(map, matchesFFilename_) :2120; consumers that Load it: src/threads/R3DTriangulationThread.cpp:222,
 // :411 and src/threads/PreviewGeneratorThread.cpp:337-338.  Format: SURVEY.md Appendix B.3.
 #include <algorithm>
+#include <cstring>
 #include <fstream>
 #include <map>
+#include <new>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -27,7 +29,7 @@ int r3d_matches_get_pair(const r3d_matches* m, uint64_t k, uint32_t* I, uint32_t
 }
 
 int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t* pair_ofs, const r3d_indmatch* matches,
-                         r3d_matches** out) {
+                         r3d_matches** out) try {
   if (!out || (n_pairs && (!pairs || !pair_ofs))) return R3D_ERR_INVALID;
   std::vector<uint64_t> order(n_pairs);
   std::iota(order.begin(), order.end(), 0);
@@ -43,11 +45,27 @@ int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t
   }
   *out = m;
   return R3D_OK;
+} catch (const std::bad_alloc&) { return R3D_ERR_NOMEM; } catch (...) { return R3D_ERR_INVALID; }
+
+/* Flat copy of the map (what a host gather across ranks ships): pairs_out 2 x num_pairs view ids in map order,
+ * ofs_out num_pairs + 1 prefix offsets, matches_out total entries.  Any output may be NULL. */
+int r3d_matches_export_csr(const r3d_matches* m, uint32_t* pairs_out, uint64_t* ofs_out, r3d_indmatch* matches_out) {
+  if (!m) return R3D_ERR_INVALID;
+  const uint64_t P = m->pairs.size() / 2;
+  if (pairs_out && P) std::memcpy(pairs_out, m->pairs.data(), sizeof(uint32_t) * 2 * P);
+  uint64_t acc = 0;
+  for (uint64_t k = 0; k < P; ++k) {
+    if (ofs_out) ofs_out[k] = acc;
+    if (matches_out && m->per[k].n) std::memcpy(matches_out + acc, m->per[k].p, sizeof(r3d_indmatch) * m->per[k].n);
+    acc += m->per[k].n;
+  }
+  if (ofs_out) ofs_out[P] = acc;
+  return R3D_OK;
 }
 
 void r3d_free_matches(r3d_matches* m) { delete m; }
 
-int r3d_save_matches_txt(const r3d_matches* m, const char* path) {
+int r3d_save_matches_txt(const r3d_matches* m, const char* path) try {
   if (!m || !path) return R3D_ERR_INVALID;
   std::ofstream stream(path);
   if (!stream.is_open()) return R3D_ERR_IO;
@@ -57,19 +75,25 @@ int r3d_save_matches_txt(const r3d_matches* m, const char* path) {
     for (const r3d_indmatch& im : m->per[k]) stream << im.i << " " << im.j << "\n";
   }
   return stream.good() ? R3D_OK : R3D_ERR_IO;
-}
+} catch (...) { return R3D_ERR_IO; }
 
-int r3d_load_matches_txt(const char* path, r3d_matches** out) {
+int r3d_load_matches_txt(const char* path, r3d_matches** out) try {
   if (!path || !out) return R3D_ERR_INVALID;
   std::ifstream stream(path);
   if (!stream.is_open()) return R3D_ERR_IO;
+  stream.seekg(0, std::ios::end);
+  const uint64_t file_bytes = (uint64_t)std::max<std::streamoff>(0, stream.tellg());
+  stream.seekg(0, std::ios::beg);
   std::map<std::pair<uint32_t, uint32_t>, std::vector<r3d_indmatch>> mp;
   uint32_t I, J;
   uint64_t number;
   while (stream >> I >> J >> number) {
+    // a match line is at least "i j\n" = 4 bytes: a count the rest of the file cannot hold is a corrupt file, not
+    // an allocation request
+    if (number > file_bytes / 4) return R3D_ERR_IO;
     std::vector<r3d_indmatch> v(number);
     for (uint64_t k = 0; k < number; ++k)
-      if (!(stream >> v[k].i >> v[k].j)) return R3D_ERR_IO;
+      if (!(stream >> v[k].i >> v[k].j)) return R3D_ERR_IO;  // truncated inside pair (I, J)
     mp[{I, J}] = std::move(v);
   }
   r3d_matches* m = new r3d_matches();
@@ -77,6 +101,6 @@ int r3d_load_matches_txt(const char* path, r3d_matches** out) {
     m->push(kv.first.first, kv.first.second, std::move(kv.second));  // matching::Load keeps what the file lists
   *out = m;
   return R3D_OK;
-}
+} catch (const std::bad_alloc&) { return R3D_ERR_NOMEM; } catch (...) { return R3D_ERR_IO; }
 
 }  // extern "C"

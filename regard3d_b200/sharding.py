@@ -52,3 +52,94 @@ def partition_ba(prob, rank, world):
         "obs_xy": np.ascontiguousarray(np.asarray(prob["obs_xy"], np.float64)[sel]),
     }
     return local, (p0, p1)
+
+
+class Gather:
+    """Per-rank PairWiseMatches -> rank 0, in pair order (shards are contiguous ranges of the I-sorted pair list, so
+    rank order = pair order; the reference inserts into one std::map, src/R3DComputeMatches.cpp:483-486).
+    Wire format per rank, 8-byte words: P pair ids (2 x u32) | P + 1 prefix offsets (u64) | T matches (2 x u32).
+    CUDA route: r3d_matches_export_csr into pinned host memory -> H2D -> NCCL send/recv over NVLink -> D2H into
+    rank 0's pinned result buffer; rank 0's own shard is exported straight into that buffer.  With a CPU device
+    (gloo) the same code runs without the staging copies -- that is what the CPU tests exercise."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.h_send = self.d_send = self.h_result = None
+        self.d_recv = [None] * world
+        self.sizes = None
+        self.words = None
+        self.h2d = self.d2h = 0
+
+    def _grow(self, t, n, **kw):
+        if t is None or t.numel() < n:
+            return self.torch.empty(int(n * 1.25) + 1024, dtype=self.torch.int64, **kw)
+        return t
+
+    def _wait(self, ops):
+        for req in (self.dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+
+    def __call__(self, m):
+        torch, dist = self.torch, self.dist
+        P, T = m.num_pairs, m.total
+        mine = torch.tensor([P, T], dtype=torch.int64, device=self.device)
+        lst = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        dist.all_gather(lst, mine)
+        self.sizes = np.stack([t.cpu().numpy() for t in lst])
+        words = self.sizes[:, 0] * 2 + 1 + self.sizes[:, 1]
+        self.words = words
+        self.h2d = self.d2h = 0
+
+        def export(buf):
+            m.export_csr(buf[0:P].view(np.uint32), buf[P:2 * P + 1].view(np.uint64), buf[2 * P + 1:2 * P + 1 + T])
+        if self.rank == 0:
+            self.h_result = self._grow(self.h_result, int(words.sum()), pin_memory=self.cuda)
+            export(self.h_result.numpy())
+            ops, off = [], int(words[0])
+            for r in range(1, self.world):
+                w = int(words[r])
+                if self.cuda:
+                    self.d_recv[r] = self._grow(self.d_recv[r], w, device=self.device)
+                    ops.append(dist.P2POp(dist.irecv, self.d_recv[r][:w], r))
+                else:
+                    ops.append(dist.P2POp(dist.irecv, self.h_result[off:off + w], r))
+                off += w
+            self._wait(ops)
+            if self.cuda:
+                off = int(words[0])
+                for r in range(1, self.world):
+                    w = int(words[r])
+                    self.h_result[off:off + w].copy_(self.d_recv[r][:w], non_blocking=True)
+                    off += w
+                    self.d2h += 8 * w
+                torch.cuda.current_stream().synchronize()
+        else:
+            w = int(words[self.rank])
+            self.h_send = self._grow(self.h_send, w, pin_memory=self.cuda)
+            export(self.h_send.numpy())
+            src = self.h_send
+            if self.cuda:
+                self.d_send = self._grow(self.d_send, w, device=self.device)
+                self.d_send[:w].copy_(self.h_send[:w], non_blocking=True)
+                self.h2d += 8 * w
+                src = self.d_send
+            self._wait([dist.P2POp(dist.isend, src[:w], 0)])
+            if self.cuda:
+                torch.cuda.current_stream().synchronize()
+
+    def result(self):
+        """Rank 0: [(pairs[P,2] u32, ofs[P+1] u64, matches[T]) per rank], views into the gathered host buffer."""
+        from regard3d_b200 import capi
+        out, off = [], 0
+        buf = self.h_result.numpy()
+        for r in range(self.world):
+            w, P, T = int(self.words[r]), int(self.sizes[r, 0]), int(self.sizes[r, 1])
+            b = buf[off:off + w]
+            out.append((b[0:P].view(np.uint32).reshape(-1, 2), b[P:2 * P + 1].view(np.uint64),
+                        b[2 * P + 1:2 * P + 1 + T].view(capi.indmatch_dtype)))
+            off += w
+        return out

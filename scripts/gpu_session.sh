@@ -1,11 +1,25 @@
-# One GPU-box session: GPU parity tests, bench line, ncu captures (run: gpurun -- bash scripts/gpu_session.sh)
+# One GPU-box session (run: gpurun --timeout T -- bash scripts/gpu_session.sh STEP [STEP...]); outputs in gpurun_out/.
+# Steps: smoke tests bench bench_ref sanitize ncu_k1 ncu_launches ncu_ba c2 c4
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_l2_candidates_2sm -s 13 -c 1 -f -o gpurun_out/prof_k1_2sm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-filter > gpurun_out/b_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_f7_score -s 30 -c 1 -f -o gpurun_out/prof_f7_score python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba > gpurun_out/b_ncu2.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_bin_rerank -s 13 -c 1 -f -o gpurun_out/prof_bin_rerank python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-filter > gpurun_out/b_ncu3.log 2>&1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ba > gpurun_out/b_ncu4.log 2>&1
-head -c 600 gpurun_out/bench.json
+for step in "$@"; do
+case $step in
+smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log ;;
+tests) timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -5 gpurun_out/pytest_gpu.log ;;
+bench) timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err; head -c 1500 gpurun_out/bench.json ;;
+bench_ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json ;;
+c2) timeout 600 python bench.py --workload c2 --no-ba > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "c2 rc=$?" ;;
+c4) timeout 900 python bench.py --workload c4 --steps 1 --warmup 1 --no-ba > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?" ;;
+sanitize)
+  for tool in memcheck racecheck synccheck; do
+    for part in match filter ba; do
+      timeout 200 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_small.py $part > gpurun_out/sanitizer_${tool}_${part}.log 2>&1
+      echo "$tool $part rc=$?"; tail -3 gpurun_out/sanitizer_${tool}_${part}.log
+    done
+  done ;;
+ncu_k1) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_l2_candidates_2sm -s 4 -c 1 -f -o gpurun_out/prof_k1_2sm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-filter --no-extras ${NCU_BENCH_ARGS:-} > gpurun_out/b_ncu.log 2>&1; echo "ncu_k1 rc=$?" ;;
+ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-extras ${NCU_BENCH_ARGS:-} > gpurun_out/b_ncu4.log 2>&1; echo "ncu_launches rc=$?" ;;
+ncu_ba) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_ba.csv python tests/gpu_ba_profile.py > gpurun_out/ba_prof.log 2>&1; echo "ncu_ba rc=$?" ;;
+*) echo "unknown step $step" ;;
+esac
+done

@@ -66,6 +66,48 @@ def test_two_gloo_ranks_equal_single_process(oracle, tmp_path):
     assert np.array_equal(np.concatenate(got_m), m)                    # concatenation == single-process result
 
 
+def _gather_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle as po
+    from regard3d_b200 import capi
+    sc = synth.make_scene(6, 300, 32, "msurf", seed=78)
+    pairs = synth.exhaustive_pairs(6)
+    counts = [len(d) for d in sc["descs"]]
+    mine, _ = sharding.my_shard(pairs, counts, rank, world)
+    ofs, m = po.match_pairs(sc["descs"], sc["xys"], mine, 0.8, n_threads=2)
+    handle = capi.Matches.from_csr(mine, ofs, m)        # the rank's PairWiseMatches (host container of the C ABI)
+    g = sharding.Gather(rank, world, "cpu")
+    for _ in range(2):                                  # twice: buffers are reused
+        g(handle)
+    if rank == 0:
+        parts = g.result()
+        np.savez(os.path.join(out_dir, "g.npz"), pairs=np.concatenate([p[0] for p in parts]),
+                 counts=np.concatenate([np.diff(p[1].astype(np.int64)) for p in parts]),
+                 m=np.concatenate([p[2] for p in parts]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_to_rank0_in_pair_order(r3dlib, oracle, tmp_path, world):
+    """The bench's strong-scaling gather (sharding.Gather: export CSR -> send/recv -> rank 0's buffer) returns the
+    single-process PairWiseMatches: same pairs in std::map order, same match sequences."""
+    mp = pytest.importorskip("torch.multiprocessing")
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = np.load(tmp_path / "g.npz")
+    sc = synth.make_scene(6, 300, 32, "msurf", seed=78)
+    pairs = synth.exhaustive_pairs(6)
+    ofs, m = oracle.match_pairs(sc["descs"], sc["xys"], pairs, 0.8)
+    cnt = np.diff(ofs.astype(np.int64))
+    keep = cnt > 0                                       # empty pairs are absent from the map
+    assert np.array_equal(got["pairs"], pairs[keep]) and np.array_equal(got["counts"], cnt[keep])
+    assert np.array_equal(got["m"], m)
+
+
 def test_partition_ba_tiles_points_and_observations():
     prob = synth.make_ba_problem(n_cams=6, n_pts=301, obs_per_pt=3, seed=5)
     for world in (1, 2, 3, 5):
