@@ -250,6 +250,11 @@ int r3d_debug_post_process_many(int lanes, r3d_indmatch* const* ms, uint64_t* co
  * positions of view I) */
 int64_t r3d_debug_post_process_ranked(r3d_indmatch* m, int64_t n, const float* xyI, uint32_t n_keypoints, const float* xyJ);
 
+/* Diagnostics (host only): 1 when the library's device-side restatement of std::mt19937 +
+ * std::uniform_int_distribution<uint32_t> (the ACRANSAC sample stream) reproduces this process's <random>; the
+ * filters then run entirely on the device, otherwise samples are drawn on the host, round by round. */
+int r3d_debug_rng_selftest(void);
+
 /* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
  * 6 keys ascending + 2 unused)
  * the tensor-core pass produced for (view_db, view_query), and the pair's error bound. */

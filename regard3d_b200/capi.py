@@ -25,7 +25,7 @@ EXPORTS = [
     "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
     "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
     "r3d_comm_unique_id", "r3d_comm_init", "r3d_comm_destroy", "r3d_comm_world", "r3d_debug_post_process",
-    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr",
+    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr", "r3d_debug_rng_selftest",
 ]
 
 

@@ -46,6 +46,25 @@ struct AcInlierReq {
   uint32_t hyp_model;    // hypothesis * MAX_MODELS + model: where this round's model matrix lives on the device
 };
 
+struct AcFusedOut {      // per pair, written by the persistent kernel (acransac_fused.cu)
+  double minNFA, errorMax;
+  uint32_t n_inliers;    // 0 when minNFA >= 0; else the best model's inliers, listed in residual order
+  uint32_t iterations;   // RANSAC iterations the state machine consumed
+  uint32_t exact_scores; // models that needed the sort + exact NFA scan (tier 2)
+  uint32_t models;       // models scored
+  uint32_t events;       // pool replacements
+  uint32_t pad_;
+};
+
+// persistent one-CTA-per-pair ACRANSAC (acransac_fused.cu); `order`: pair ids of one size class, largest first;
+// huge: sort buffers / pool in global scratch (cap entries per CTA of the grid)
+size_t acransac_fused_smem_bytes(int model, uint32_t cap, bool huge);
+int acransac_fused_ctas_per_sm(int model, uint32_t cap, bool huge);
+int launch_acransac_fused(r3d_ctx* ctx, DeviceWorker& w, int model, bool huge, const AcPair* pairs, const uint32_t* order,
+                          uint32_t n_order, uint32_t* work_counter, const double2* x1, const double2* x2, const float* logc_n,
+                          const float* logc_k, uint32_t cap, uint32_t max_iter, double* g_se, uint32_t* g_si, uint32_t* g_pool,
+                          const uint2* matches, uint2* out_matches, AcFusedOut* out, uint32_t grid);
+
 // x1/x2[pt_ofs + k] = normalised positions of putative match k of every pair (double, like MatchesPairToMat)
 int launch_ac_points(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const AcPointSrc* src, uint32_t n_pairs,
                      const uint2* matches, double2* x1, double2* x2, uint32_t* bad_flag);

@@ -1,0 +1,394 @@
+// acransac_fused.cu -- the whole a-contrario RANSAC of one image pair inside ONE persistent CTA.
+// COMPILED WITH --fmad=false (regard3d_b200/build.py), like acransac_kernels.cu.
+//
+// Replaces the per-pair body of ImageCollectionGeometricFilter::Robust_model_estimation(GeometricFilter_{F,E,H}Matrix_AC
+// (4.0, 2048), ...) (src/R3DComputeMatches.cpp:2099-2115, :2169-2171, :2215-2219); upstream semantics: SURVEY.md A.4-A.6.
+//
+// Round 1 ran ACRANSAC as ~25 host<->device rounds (samples drawn on the host, two kernels, state machine replayed on
+// the host): 54 % of the filter's time was host work and every hypothesis paid a shared-memory sort of its residuals.
+// Here a CTA owns a pair from the first sample to the final inlier list:
+//   * the sample stream is drawn on the device (acransac_rng.cuh: mt19937 + libstdc++'s uniform_int_distribution,
+//     self-checked against the host's <random> at r3d_create());
+//   * kBatch iterations are drawn / solved / scored speculatively, then the state machine is replayed in order; an
+//     improving model ("event") replaces the sampling pool and discards the speculative tail (generator rewound);
+//   * scoring is two-tier.  Tier 1, one warp per model: M residuals -> count of those <= the precision bound and a
+//     geometric histogram of them (exponent + 5 mantissa bits); with e_(k) >= the lower edge of the bin that holds
+//     rank k, LB = min_k NFA_k(lower edge) is a rigorous lower bound of the model's best NFA (every operation of
+//     the NFA formula is monotone under rounding).  Tier 2, the whole CTA, only when LB < minNFA (the model may
+//     improve on the best so far): compaction + bitonic sort + the exact NFA scan of round 1.  After the first few
+//     models of a pair almost every hypothesis is settled by tier 1 -- no sort.
+// The decisions taken are exactly those of the sequential algorithm: tier 1 only skips work whose outcome
+// (nfa >= minNFA: "not better") is already certain.
+#include "acransac_device.cuh"
+#include "acransac_rng.cuh"
+
+#include <random>
+
+namespace r3d {
+
+namespace {
+
+constexpr int kFThreads = 256;
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kBatch = 16;            // iterations drawn, solved and tier-1-scored ahead
+constexpr int kBins = 1024;           // tier-1 histogram: binades split in 32 (exponent + 5 mantissa bits)
+constexpr int kBinShift = 52 - 5;
+
+template <int MODEL>
+struct FusedSmem {                    // fixed part of the shared memory (the sort / histogram region follows)
+  Mt19937 rng, snap;
+  double la[kBins];                   // logalpha of every bin's lower edge
+  double models[kBatch][ac_max_models(MODEL)][9];
+  double lb[kBatch][ac_max_models(MODEL)];
+  double bestF[9];
+  double s_nfa[kFWarps];
+  uint32_t s_k[kFWarps];
+  uint32_t cnt[kBatch][ac_max_models(MODEL)];
+  uint32_t nm[kBatch];
+  uint32_t sample[kBatch][8];
+  uint32_t used[kBatch];              // generator outputs consumed up to and including iteration b of the batch
+  uint32_t s_count;
+  uint32_t work;
+};
+
+template <int MODEL>
+__device__ __forceinline__ double model_error(const double* F, const double2 a, const double2 b) {
+  return MODEL == 0 ? sym_epi_error(F, a.x, a.y, b.x, b.y)
+                    : MODEL == 1 ? asym_error(F, a.x, a.y, b.x, b.y) : epi_dist_error(F, a.x, a.y, b.x, b.y);
+}
+
+}  // namespace
+
+size_t acransac_fused_smem_bytes(int model, uint32_t cap, bool huge) {
+  const size_t fixed = model == 0 ? sizeof(FusedSmem<0>) : (model == 1 ? sizeof(FusedSmem<1>) : sizeof(FusedSmem<2>));
+  const size_t hist = (size_t)kFWarps * kBins * sizeof(uint32_t);
+  const size_t sortb = huge ? 0 : (size_t)cap * 12;
+  const size_t pool = huge ? 0 : (size_t)cap * 4;
+  return ((fixed + 15) & ~(size_t)15) + std::max(hist, sortb) + pool;
+}
+
+// One persistent CTA per image pair.  order[]: the pairs of this launch (one size class), largest first.
+// HUGE: sort buffers and sampling pool in global scratch (g_se / g_si / g_pool, `cap` entries per CTA) instead of
+// shared memory -- the slow-but-correct path for pairs with more putative matches than shared memory can sort.
+template <int MODEL, bool HUGE>
+__global__ void __launch_bounds__(kFThreads) k_acransac_fused(
+    const AcPair* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t n_order, uint32_t* __restrict__ work_counter,
+    const double2* __restrict__ x1, const double2* __restrict__ x2, const float* __restrict__ logc_n,
+    const float* __restrict__ logc_k, uint32_t cap, uint32_t max_iter, double* __restrict__ g_se, uint32_t* __restrict__ g_si,
+    uint32_t* __restrict__ g_pool, const uint2* __restrict__ matches, uint2* __restrict__ out_matches,
+    AcFusedOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr uint32_t NS = ac_min_samples(MODEL), MAXM = ac_max_models(MODEL);
+  const double mult_error = MODEL == 1 ? 1.0 : 0.5;
+  FusedSmem<MODEL>& S = *reinterpret_cast<FusedSmem<MODEL>*>(smem_raw);
+  unsigned char* region = smem_raw + ((sizeof(FusedSmem<MODEL>) + 15) & ~(size_t)15);
+  uint32_t* hist_all = reinterpret_cast<uint32_t*>(region);                 // tier 1: kFWarps x kBins
+  const size_t region_bytes = HUGE ? (size_t)kFWarps * kBins * 4
+                                   : ((size_t)cap * 12 > (size_t)kFWarps * kBins * 4 ? (size_t)cap * 12 : (size_t)kFWarps * kBins * 4);
+  double* se = HUGE ? g_se + (size_t)blockIdx.x * cap : reinterpret_cast<double*>(region);   // tier 2 (aliases hist)
+  uint32_t* si = HUGE ? g_si + (size_t)blockIdx.x * cap : reinterpret_cast<uint32_t*>(se + cap);
+  uint32_t* pool = HUGE ? g_pool + (size_t)blockIdx.x * cap : reinterpret_cast<uint32_t*>(region + region_bytes);
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) S.work = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t wk = S.work;
+    if (wk >= n_order) break;
+    const uint32_t pair_id = order[wk];
+    const AcPair pr = pairs[pair_id];
+    const uint32_t M = pr.M;
+    const float* lcn = logc_n + pr.tbl_ofs;
+    const double2* p1 = x1 + pr.pt_ofs;
+    const double2* p2 = x2 + pr.pt_ofs;
+
+    // ---- per-pair set-up: sampling pool, generator, bin edges ---------------------------------------------
+    for (uint32_t i = tid; i < M; i += kFThreads) pool[i] = i;
+    // bin(e) = clamp((bits(e) >> kBinShift) - bin_base, 0, kBins - 1): the precision bound falls in the top bin
+    const long long thr_key = __double_as_longlong(pr.max_thr) >> kBinShift;
+    const long long bin_base = thr_key - (kBins - 1);
+    for (uint32_t b = tid; b < (uint32_t)kBins; b += kFThreads) {
+      const long long kb = bin_base + (long long)b;
+      const double lo = (b == 0 || kb <= 0) ? 0.0 : __longlong_as_double(kb << kBinShift);
+      S.la[b] = pr.logalpha0 + mult_error * dm::log10_det(lo + (double)FLT_EPSILON);
+    }
+    if (tid == 0) mt_seed(S.rng);
+    // ACRANSAC state, replicated in the registers of every thread (updated identically from shared data)
+    uint32_t iter = 0, nIterReserve = max_iter / 10, nIter = max_iter - nIterReserve;
+    bool ac_mode = !(pr.max_thr < DBL_MAX);  // bACRansacMode = (precision == infinity)
+    double minNFA = DBL_MAX * 2.0, errorMax = DBL_MAX * 2.0;
+    uint32_t best_k = 0, pool_size = M;
+    bool have_inliers = false;
+    uint32_t n_exact = 0, n_models = 0, n_events = 0;
+    __syncthreads();
+
+    while (iter < nIter) {
+      const uint32_t B = min((uint32_t)kBatch, nIter - iter);
+      // ---- 1. snapshot the generator, draw B samples (UniformSample: partial Fisher-Yates on the pool) ----
+      {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&S.snap);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.rng);
+        for (uint32_t i = tid; i < sizeof(Mt19937) / 4; i += kFThreads) dst[i] = src[i];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t used = 0;
+        const uint32_t last_idx = pool_size - 1;
+        for (uint32_t b = 0; b < B; ++b) {
+          for (uint32_t i = 0; i < NS; ++i) {
+            const uint32_t r = uniform_u32(S.rng, i, last_idx, &used);
+            const uint32_t t = pool[i]; pool[i] = pool[r]; pool[r] = t;
+          }
+          for (uint32_t i = 0; i < NS; ++i) S.sample[b][i] = pool[i];
+          S.used[b] = used;
+        }
+      }
+      __syncthreads();
+      // ---- 2. minimal solver: one thread per iteration of the batch --------------------------------------
+      if (tid < B) {
+        double models[9 * MAXM];
+        int nm;
+        if (MODEL == 2) {
+          double b1[15], b2[15], Es[90];
+          for (int t = 0; t < 5; ++t) {
+            const double2 a = p1[S.sample[tid][t]];
+            const double2 b = p2[S.sample[tid][t]];
+            bearing(pr.K, a.x, a.y, b1 + 3 * t);
+            bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
+          }
+          nm = fp::five_point(b1, b2, Es);
+          for (int mi = 0; mi < nm; ++mi) fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, models + 9 * mi);
+        } else {
+          double s1[14], s2[14];
+          for (uint32_t t = 0; t < NS; ++t) {
+            const double2 a = p1[S.sample[tid][t]];
+            const double2 b = p2[S.sample[tid][t]];
+            s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
+            s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
+          }
+          nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
+        }
+        S.nm[tid] = (uint32_t)nm;
+        for (int mi = 0; mi < nm; ++mi)
+          for (int t = 0; t < 9; ++t) S.models[tid][mi][t] = models[9 * mi + t];
+      }
+      __syncthreads();
+      // ---- 3. tier 1: one warp per model -- count, histogram, lower bound of the best NFA ------------------
+      {
+        uint32_t* hist = hist_all + (size_t)warp * kBins;
+        for (uint32_t slot = warp; slot < B * MAXM; slot += kFWarps) {
+          const uint32_t b = slot / MAXM, mi = slot % MAXM;
+          if (mi >= S.nm[b]) continue;
+          double Fm[9];
+          for (int t = 0; t < 9; ++t) Fm[t] = S.models[b][mi][t];
+          for (uint32_t i = lane; i < (uint32_t)kBins; i += 32) hist[i] = 0;
+          __syncwarp();
+          uint32_t c = 0;
+          for (uint32_t i = lane; i < M; i += 32) {
+            const double e = model_error<MODEL>(Fm, p1[i], p2[i]);
+            if (e <= pr.max_thr) {  // false for NaN
+              long long bin = (__double_as_longlong(e) >> kBinShift) - bin_base;
+              bin = bin < 0 ? 0 : (bin > kBins - 1 ? kBins - 1 : bin);
+              atomicAdd(&hist[bin], 1u);
+              ++c;
+            }
+          }
+          for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          __syncwarp();
+          double lbv = DBL_MAX * 2.0;
+          if (c > NS) {
+            // exclusive prefix over the bins, 32 at a time (conflict-free rows + a running carry)
+            uint32_t carry = 0;
+            for (uint32_t j = 0; j < (uint32_t)kBins; j += 32) {
+              const uint32_t v = hist[j + lane];
+              uint32_t incl = v;
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += u;
+              }
+              hist[j + lane] = carry + incl - v;
+              carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+            // ranks (lo, hi] live in bin bb: NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]
+            for (uint32_t bb = lane; bb < (uint32_t)kBins; bb += 32) {
+              const uint32_t lo = hist[bb];
+              const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : c;
+              const double la = S.la[bb];
+              for (uint32_t k = max(lo + 1, NS + 1); k <= hi; ++k) {
+                const double g = pr.loge0 + la * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
+                lbv = g < lbv ? g : lbv;
+              }
+            }
+            for (int o = 16; o >= 1; o >>= 1) {
+              const double ov = __shfl_xor_sync(0xffffffffu, lbv, o);
+              lbv = ov < lbv ? ov : lbv;
+            }
+            // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
+            lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
+          }
+          if (lane == 0) { S.cnt[b][mi] = c; S.lb[b][mi] = lbv; }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // ---- 4. replay the ACRANSAC state machine over the batch (uniform control flow) ---------------------
+      uint32_t consumed = B;
+      bool event = false;
+      for (uint32_t it = 0; it < B; ++it) {
+        bool better = false;
+        const uint32_t nm = S.nm[it];
+        for (uint32_t mi = 0; mi < nm; ++mi) {
+          ++n_models;
+          if (!ac_mode && (double)S.cnt[it][mi] > 2.5 * NS) ac_mode = true;
+          if (ac_mode && S.lb[it][mi] < minNFA) {  // the model may improve on the best one: exact NFA (tier 2)
+            ++n_exact;
+            double Fm[9];
+            for (int t = 0; t < 9; ++t) Fm[t] = S.models[it][mi][t];
+            const uint32_t c = residuals_sorted<MODEL, false>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
+            const NfaBest r = nfa_scan_sorted<MODEL>(pr, se, c, lcn, logc_k, S.s_nfa, S.s_k);
+            if (r.nfa < minNFA) {
+              better = true;
+              minNFA = r.nfa;
+              errorMax = r.err;
+              best_k = r.k;
+              have_inliers = true;
+              if (tid < 9) S.bestF[tid] = Fm[tid];
+            }
+          }
+        }
+        const uint32_t iter_abs = iter + it;
+        if ((better && minNFA < 0) || (iter_abs + 1 == nIter && nIterReserve)) {
+          if (!have_inliers) {
+            ++nIter;
+            --nIterReserve;
+          } else {
+            event = true;
+            consumed = it + 1;
+            break;
+          }
+        }
+      }
+      iter += consumed;
+      // ---- 5. pool replacement: draw the next samples among the best model's inliers -------------------------
+      if (event) {
+        ++n_events;
+        __syncthreads();  // bestF
+        double Fm[9];
+        for (int t = 0; t < 9; ++t) Fm[t] = S.bestF[t];
+        const uint32_t c = residuals_sorted<MODEL, true>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
+        pool_size = best_k < c ? best_k : c;
+        for (uint32_t i = tid; i < pool_size; i += kFThreads) pool[i] = si[i];
+        if (nIterReserve) {
+          nIter = iter + nIterReserve;
+          nIterReserve = 0;
+        }
+        if (consumed < B) {  // rewind the generator to the end of iteration `consumed - 1`
+          uint32_t* dst = reinterpret_cast<uint32_t*>(&S.rng);
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.snap);
+          for (uint32_t i = tid; i < sizeof(Mt19937) / 4; i += kFThreads) dst[i] = src[i];
+          __syncthreads();
+          if (tid == 0)
+            for (uint32_t u = 0; u < S.used[consumed - 1]; ++u) (void)mt_next(S.rng);
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- result: "if (minNFA >= 0) vec_inliers.clear()"; the inlier list in residual order ------------------
+    uint32_t n_out = 0;
+    if (have_inliers && minNFA < 0) {
+      __syncthreads();
+      double Fm[9];
+      for (int t = 0; t < 9; ++t) Fm[t] = S.bestF[t];
+      const uint32_t c = residuals_sorted<MODEL, true>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
+      n_out = best_k < c ? best_k : c;
+      for (uint32_t i = tid; i < n_out; i += kFThreads) out_matches[pr.pt_ofs + i] = matches[pr.pt_ofs + si[i]];
+    }
+    if (tid == 0) {
+      AcFusedOut o;
+      o.minNFA = minNFA;
+      o.errorMax = errorMax;
+      o.n_inliers = n_out;
+      o.iterations = iter;
+      o.exact_scores = n_exact;
+      o.models = n_models;
+      o.events = n_events;
+      o.pad_ = 0;
+      out[pair_id] = o;
+    }
+  }
+}
+
+template <int MODEL, bool HUGE>
+static int launch_fused_t(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const uint32_t* order, uint32_t n_order,
+                          uint32_t* work_counter, const double2* x1, const double2* x2, const float* logc_n, const float* logc_k,
+                          uint32_t cap, uint32_t max_iter, double* g_se, uint32_t* g_si, uint32_t* g_pool, const uint2* matches,
+                          uint2* out_matches, AcFusedOut* out, uint32_t grid) {
+  const size_t smem = acransac_fused_smem_bytes(MODEL, cap, HUGE);
+  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(k_acransac_fused<MODEL, HUGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_acransac_fused<MODEL, HUGE><<<grid, kFThreads, smem, w.stream>>>(pairs, order, n_order, work_counter, x1, x2, logc_n, logc_k,
+                                                                      cap, max_iter, g_se, g_si, g_pool, matches, out_matches, out);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
+int acransac_fused_ctas_per_sm(int model, uint32_t cap, bool huge) {
+  const size_t smem = acransac_fused_smem_bytes(model, cap, huge);
+  const size_t per_sm = 227 * 1024;
+  int n = (int)(per_sm / (smem + 1024));
+  if (n < 1) n = 1;
+  if (n > 4) n = 4;  // 256 threads x ~128 registers
+  return n;
+}
+
+int launch_acransac_fused(r3d_ctx* ctx, DeviceWorker& w, int model, bool huge, const AcPair* pairs, const uint32_t* order,
+                          uint32_t n_order, uint32_t* work_counter, const double2* x1, const double2* x2, const float* logc_n,
+                          const float* logc_k, uint32_t cap, uint32_t max_iter, double* g_se, uint32_t* g_si, uint32_t* g_pool,
+                          const uint2* matches, uint2* out_matches, AcFusedOut* out, uint32_t grid) {
+  if (!n_order) return R3D_OK;
+#define R3D_FUSED_CASE(MD, HG)                                                                                          \
+  if (model == MD && huge == HG)                                                                                        \
+    return launch_fused_t<MD, HG>(ctx, w, pairs, order, n_order, work_counter, x1, x2, logc_n, logc_k, cap, max_iter, \
+                                  g_se, g_si, g_pool, matches, out_matches, out, grid);
+  R3D_FUSED_CASE(0, false) R3D_FUSED_CASE(0, true) R3D_FUSED_CASE(1, false) R3D_FUSED_CASE(1, true)
+  R3D_FUSED_CASE(2, false) R3D_FUSED_CASE(2, true)
+#undef R3D_FUSED_CASE
+  return fail(ctx, R3D_ERR_INVALID, "launch_acransac_fused: unknown model");
+}
+
+// ---- the restated sample stream against this process's <random> -------------------------------------------------
+bool rng_selftest() {
+  static int cached = -1;
+  if (cached >= 0) return cached == 1;
+  std::mt19937 ref;
+  Mt19937* mine = new Mt19937;
+  mt_seed(*mine);
+  bool ok = true;
+  // pool sizes as ACRANSAC sees them, tiny and huge ranges, the full range
+  const uint32_t sizes[] = {8, 9, 17, 100, 1000, 4097, 65536, 1000003, 0x7fffffffu, 0xfffffff0u};
+  for (int round = 0; round < 400 && ok; ++round) {
+    for (uint32_t sz : sizes) {
+      for (uint32_t i = 0; i < 7 && i < sz; ++i) {
+        std::uniform_int_distribution<uint32_t> d(i, sz - 1);
+        uint32_t used = 0;
+        if (d(ref) != uniform_u32(*mine, i, sz - 1, &used)) { ok = false; break; }
+      }
+      if (!ok) break;
+    }
+    std::uniform_int_distribution<uint32_t> full(0u, 0xffffffffu);
+    uint32_t used = 0;
+    if (ok && full(ref) != uniform_u32(*mine, 0u, 0xffffffffu, &used)) ok = false;
+  }
+  // both generators must also sit at the same position afterwards
+  if (ok) {
+    uint32_t a = (uint32_t)ref();
+    if (a != mt_next(*mine)) ok = false;
+  }
+  delete mine;
+  cached = ok ? 1 : 0;
+  return ok;
+}
+
+}  // namespace r3d

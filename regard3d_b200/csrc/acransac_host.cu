@@ -11,6 +11,7 @@
 // pairs' hypotheses are solved and scored in two launches, and a per-pair sequential scan replays
 // the state machine, discarding the speculative tail after a pool replacement.
 #include "acransac.cuh"
+#include "acransac_rng.cuh"
 #include "detmath.cuh"
 
 #include <algorithm>
@@ -99,6 +100,155 @@ struct DevBuf {
     return cudaSuccess;
   }
 };
+
+std::vector<uint32_t> st_src(const std::vector<PairState>& st) {
+  std::vector<uint32_t> v(st.size());
+  for (size_t a = 0; a < st.size(); ++a) v[a] = st[a].src;
+  return v;
+}
+
+// The device-resident ACRANSAC (acransac_fused.cu): the pairs are cut into size classes (shared-memory sort capacity
+// 1024 ... 16384 putative matches; beyond that the "huge" class sorts in global scratch), one persistent launch per
+// class, largest pairs first; ONE synchronisation, then the inlier lists come back through pinned staging.
+int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const r3d_matches* put, const std::vector<uint32_t>& src,
+              const std::vector<AcPair>& hpairs, const AcPair* d_pairs, const double2* d_x1, const double2* d_x2,
+              const uint2* d_match, const float* d_logc_n, const float* d_logc_k, uint32_t pt_total, uint32_t sizeSample,
+              double t_begin, std::vector<std::vector<r3d_indmatch>>& result) {
+  r3d_filter_timing& T = ctx->filter_timing;
+  const uint32_t n = (uint32_t)hpairs.size();
+  constexpr int kClasses = 6;  // caps 1024, 2048, 4096, 8192, 16384, huge
+  std::vector<uint32_t> order[kClasses];
+  uint32_t huge_maxM = 0;
+  for (uint32_t a = 0; a < n; ++a) {
+    const uint32_t M = hpairs[a].M;
+    int c = 0;
+    while (c < 5 && (1024u << c) < M) ++c;
+    if (M > 16384u) { c = 5; huge_maxM = std::max(huge_maxM, M); }
+    order[c].push_back(a);
+  }
+  std::vector<uint32_t> horder;
+  uint32_t class_ofs[kClasses + 1] = {0};
+  for (int c = 0; c < kClasses; ++c) {
+    std::stable_sort(order[c].begin(), order[c].end(), [&](uint32_t x, uint32_t y) { return hpairs[x].M > hpairs[y].M; });
+    class_ofs[c] = (uint32_t)horder.size();
+    horder.insert(horder.end(), order[c].begin(), order[c].end());
+  }
+  class_ofs[kClasses] = (uint32_t)horder.size();
+  DevBuf<uint32_t> d_order(w), d_work(w), d_si(w), d_pool(w);
+  DevBuf<double> d_se(w);
+  DevBuf<AcFusedOut> d_out(w);
+  DevBuf<uint2> d_outm(w);
+  R3D_CUDA_TRY(ctx, d_order.ensure(horder.size()));
+  R3D_CUDA_TRY(ctx, d_work.ensure(kClasses));
+  R3D_CUDA_TRY(ctx, d_out.ensure(n));
+  R3D_CUDA_TRY(ctx, d_outm.ensure(pt_total));
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_order.p, horder.data(), horder.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w.stream));
+  R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_work.p, 0, kClasses * sizeof(uint32_t), w.stream));
+  cudaEvent_t ev[2];
+  for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
+  struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 2; ++i) cudaEventDestroy(e[i]); } } evg{ev};
+  R3D_CUDA_TRY(ctx, cudaEventRecord(ev[0], w.stream));
+  for (int c = kClasses - 1; c >= 0; --c) {  // the long-running classes first
+    const uint32_t cnt = class_ofs[c + 1] - class_ofs[c];
+    if (!cnt) continue;
+    const bool huge = c == 5;
+    uint32_t cap = 1024u << c;
+    if (huge) {
+      cap = 32768;
+      while (cap < huge_maxM) cap <<= 1;
+    }
+    uint32_t grid = std::min<uint32_t>(cnt, (uint32_t)w.sm_count * (uint32_t)acransac_fused_ctas_per_sm(model, cap, huge));
+    if (huge) {
+      grid = std::min<uint32_t>(grid, (uint32_t)w.sm_count);
+      R3D_CUDA_TRY(ctx, d_se.ensure((size_t)grid * cap));
+      R3D_CUDA_TRY(ctx, d_si.ensure((size_t)grid * cap));
+      R3D_CUDA_TRY(ctx, d_pool.ensure((size_t)grid * cap));
+    }
+    int rc = launch_acransac_fused(ctx, w, model, huge, d_pairs, d_order.p + class_ofs[c], cnt, d_work.p + c, d_x1, d_x2, d_logc_n,
+                                   d_logc_k, cap, max_iter, d_se.p, d_si.p, d_pool.p, d_match, d_outm.p, d_out.p, grid);
+    if (rc) return rc;
+    T.kernel_launches += 1;
+  }
+  R3D_CUDA_TRY(ctx, cudaEventRecord(ev[1], w.stream));
+  std::vector<AcFusedOut> hout(n);
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(hout.data(), d_out.p, (size_t)n * sizeof(AcFusedOut), cudaMemcpyDeviceToHost, w.stream));
+  R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev[0], ev[1]);
+  T.ms_score = ms;
+  T.ms_solve = 0.0;
+  T.rounds = 1;
+  for (const AcFusedOut& o : hout) T.hypotheses += o.iterations;
+  if (getenv("R3D_DEBUG_TIMING")) {
+    uint64_t ex = 0, mo = 0, evs = 0;
+    for (const AcFusedOut& o : hout) { ex += o.exact_scores; mo += o.models; evs += o.events; }
+    fprintf(stderr, "[r3d] fused filter: %u pairs, kernel %.2f ms, %llu iterations, %llu models, %llu exact (%.2f %%), %llu events\n", n, ms,
+            (unsigned long long)T.hypotheses, (unsigned long long)mo, (unsigned long long)ex, 100.0 * (double)ex / (double)std::max<uint64_t>(mo, 1),
+            (unsigned long long)evs);
+  }
+  // ---- inlier lists back: chunks of whole pairs through two pinned staging buffers, copied out by the host pool ----
+  // GeometricFilter_*Matrix_AC::Robust_estimation keeps the pair iff #inliers > MINIMUM_SAMPLES * 2.5
+  const size_t kStageElems = (size_t)4 << 20;  // 32 MB of (i, j) per buffer
+  if (w.h_fstage_cap < kStageElems) {
+    for (void*& hp : w.h_fstage) {
+      if (hp) cudaFreeHost(hp);
+      hp = nullptr;
+      R3D_CUDA_TRY(ctx, cudaMallocHost(&hp, kStageElems * sizeof(uint2)));
+    }
+    w.h_fstage_cap = kStageElems;
+  }
+  struct Chunk { uint32_t a0, a1; size_t lo, hi; };
+  std::vector<Chunk> chunks;
+  {  // pairs are laid out in pt_ofs order (a ascending)
+    uint32_t a = 0;
+    while (a < n) {
+      Chunk c{a, a, hpairs[a].pt_ofs, hpairs[a].pt_ofs};
+      while (c.a1 < n && ((size_t)hpairs[c.a1].pt_ofs + hpairs[c.a1].M - c.lo <= kStageElems || c.a1 == c.a0)) {
+        c.hi = (size_t)hpairs[c.a1].pt_ofs + hpairs[c.a1].M;
+        ++c.a1;
+      }
+      chunks.push_back(c);
+      a = c.a1;
+    }
+  }
+  std::vector<uint2> big;  // a single pair larger than the staging buffer
+  cudaEvent_t cev[2];
+  for (auto& e : cev) R3D_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  struct EvGuard2 { cudaEvent_t* e; ~EvGuard2() { for (int i = 0; i < 2; ++i) cudaEventDestroy(e[i]); } } evg2{cev};
+  auto issue = [&](size_t ci) -> cudaError_t {
+    const Chunk& c = chunks[ci];
+    if (c.hi - c.lo > kStageElems) return cudaSuccess;  // handled synchronously below
+    // only the inlier prefix of each pair is meaningful, but one contiguous copy beats thousands of small ones
+    cudaError_t e = cudaMemcpyAsync(w.h_fstage[ci & 1], d_outm.p + c.lo, (c.hi - c.lo) * sizeof(uint2), cudaMemcpyDeviceToHost, w.stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventRecord(cev[ci & 1], w.stream);
+  };
+  if (!chunks.empty()) R3D_CUDA_TRY(ctx, issue(0));
+  for (size_t ci = 0; ci < chunks.size(); ++ci) {
+    const Chunk& c = chunks[ci];
+    const uint2* base;
+    if (c.hi - c.lo > kStageElems) {
+      big.resize(c.hi - c.lo);
+      R3D_CUDA_TRY(ctx, cudaMemcpy(big.data(), d_outm.p + c.lo, (c.hi - c.lo) * sizeof(uint2), cudaMemcpyDeviceToHost));
+      base = big.data();
+    } else {
+      R3D_CUDA_TRY(ctx, cudaEventSynchronize(cev[ci & 1]));
+      base = (const uint2*)w.h_fstage[ci & 1];
+    }
+    if (ci + 1 < chunks.size()) R3D_CUDA_TRY(ctx, issue(ci + 1));  // the other buffer: free since chunk ci - 1 was consumed
+    parallel_for(ctx->host_threads, c.a1 - c.a0, [&](size_t k) {
+      const uint32_t a = c.a0 + (uint32_t)k;
+      const AcFusedOut& o = hout[a];
+      if (!(o.minNFA < 0) || !((double)o.n_inliers > sizeSample * 2.5)) return;
+      const r3d_indmatch* sp = (const r3d_indmatch*)(base + (hpairs[a].pt_ofs - c.lo));
+      result[src[a]].assign(sp, sp + o.n_inliers);
+    });
+  }
+  (void)put;
+  T.ms_device_total = T.ms_score;
+  T.ms_host = now_ms() - t_begin - T.ms_device_total;
+  return R3D_OK;
+}
 
 }  // namespace
 
@@ -220,8 +370,11 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   (void)bad;
   uint32_t cap = 32;
   while (cap < maxM) cap <<= 1;
-  if ((size_t)cap * 12 > 200 * 1024)
-    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: more than 16384 putative matches in one pair");
+  // the persistent per-pair kernel draws the sample stream on the device; it needs the restated
+  // std::uniform_int_distribution to agree with this process's <random> (acransac_rng.cuh)
+  const bool use_fused = rng_selftest() && !getenv("R3D_FILTER_HOST_ROUNDS");
+  if (!use_fused && (size_t)cap * 12 > 200 * 1024)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: more than 16384 putative matches in one pair (host-round path)");
 
   // ---- device buffers -------------------------------------------------------------------------
   DevBuf<AcPair> d_pairs(w);
@@ -258,6 +411,10 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   }
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_n.p, hlogc_n.data(), hlogc_n.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_k.p, hlogc_k.data(), hlogc_k.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
+
+  if (use_fused)
+    return run_fused(ctx, w, model, max_iter, put, st_src(st), hpairs, d_pairs.p, d_x1.p, d_x2.p, d_match.p, d_logc_n.p, d_logc_k.p,
+                     (uint32_t)hmatch.size(), sizeSample, t_begin, result);
 
   cudaEvent_t ev[3];
   for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
@@ -439,6 +596,10 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
 }  // namespace r3d
 
 using namespace r3d;
+
+// Diagnostics (host only): 1 when the device-side restatement of std::mt19937 + std::uniform_int_distribution
+// (acransac_rng.cuh) reproduces this process's <random>, i.e. when the filter runs fully on the device.
+extern "C" int r3d_debug_rng_selftest(void) { return rng_selftest() ? 1 : 0; }
 
 extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_iter, const r3d_matches* putative,
                                 const r3d_view_info* views, uint32_t n_views, r3d_matches** out) {

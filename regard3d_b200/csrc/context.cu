@@ -99,6 +99,8 @@ static void free_worker(DeviceWorker& w) {
     for (auto& e : o.ev)
       if (e) cudaEventDestroy(e);
   }
+  for (void*& hp : w.h_fstage)
+    if (hp) { cudaFreeHost(hp); hp = nullptr; }
   if (w.stream) cudaStreamDestroy(w.stream);
   if (w.copy_stream) cudaStreamDestroy(w.copy_stream);
   w = DeviceWorker();

@@ -21,18 +21,18 @@ __device__ constexpr int kP3[10][4] = {{0, 1, 2, 10}, {1, 3, 4, 11}, {2, 4, 5, 1
                             {5, 8, 9, 15}, {10, 11, 12, 16}, {11, 13, 14, 17}, {12, 14, 15, 18}, {16, 17, 18, 19}};
 
 // degree-1 x degree-1 -> degree-2 (10 coefficients), accumulated into out with sign
-__device__ void mul11(const double* a, const double* b, double sign, double* out) {
+__device__ inline void mul11(const double* a, const double* b, double sign, double* out) {
   for (int i = 0; i < 4; ++i)
     for (int j = 0; j < 4; ++j) out[kP2[i][j]] = out[kP2[i][j]] + sign * (a[i] * b[j]);
 }
 // degree-2 x degree-1 -> degree-3 (20 coefficients), accumulated into out with sign
-__device__ void mul21(const double* a, const double* b, double sign, double* out) {
+__device__ inline void mul21(const double* a, const double* b, double sign, double* out) {
   for (int i = 0; i < 10; ++i)
     for (int j = 0; j < 4; ++j) out[kP3[i][j]] = out[kP3[i][j]] + sign * (a[i] * b[j]);
 }
 
 // 4-D nullspace of the 5x9 system, orthonormalised (modified Gram-Schmidt in the order found)
-__device__ bool nullspace_5x9(double A[5][9], double basis[4][9]) {
+__device__ inline bool nullspace_5x9(double A[5][9], double basis[4][9]) {
   int colperm[9];
   for (int j = 0; j < 9; ++j) colperm[j] = j;
   for (int r = 0; r < 5; ++r) {
@@ -81,7 +81,7 @@ __device__ bool nullspace_5x9(double A[5][9], double basis[4][9]) {
 }
 
 // the ten cubic constraints: M is 10 x 20
-__device__ void constraints(const double basis[4][9], double M[10][20]) {
+__device__ inline void constraints(const double basis[4][9], double M[10][20]) {
   double E[3][3][4];  // entry (r,c) as a degree-1 polynomial in (x, y, z, 1)
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c)
@@ -123,7 +123,7 @@ __device__ void constraints(const double basis[4][9], double M[10][20]) {
 }
 
 // [A | C] (10 x 20) -> A = I by Gauss-Jordan with partial pivoting; C becomes B
-__device__ bool gauss_jordan(double M[10][20]) {
+__device__ inline bool gauss_jordan(double M[10][20]) {
   for (int c = 0; c < 10; ++c) {
     int pi = c;
     double best = fabs(M[c][c]);
@@ -146,7 +146,7 @@ __device__ bool gauss_jordan(double M[10][20]) {
 
 // reduction to upper Hessenberg form by stabilised elementary similarity transformations
 // (EISPACK elmhes); a is 1-indexed [11][11]
-__device__ void elmhes(double a[11][11], int n) {
+__device__ inline void elmhes(double a[11][11], int n) {
   for (int m = 2; m < n; ++m) {
     double x = 0.0;
     int i = m;
@@ -172,11 +172,11 @@ __device__ void elmhes(double a[11][11], int n) {
     for (int j = 1; j <= i - 2; ++j) a[i][j] = 0.0;
 }
 
-__device__ double sign_of(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+__device__ inline double sign_of(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
 
 // eigenvalues of an upper Hessenberg matrix (EISPACK hqr: Francis double-shift QR); 1-indexed.
 // returns false when 30 iterations do not deflate an eigenvalue.
-__device__ bool hqr(double a[11][11], int n, double* wr, double* wi) {
+__device__ inline bool hqr(double a[11][11], int n, double* wr, double* wi) {
   int nn, m, l, k, j, its, i, mmin;
   double z, y, x, w, v, u, t, s, r = 0.0, q = 0.0, p = 0.0, anorm = 0.0;
   for (i = 1; i <= n; ++i)
@@ -303,7 +303,7 @@ __device__ bool hqr(double a[11][11], int n, double* wr, double* wi) {
 
 // null vector of the (numerically) singular 10x10 matrix A: complete-pivoting elimination of 9
 // columns, free variable = 1
-__device__ bool null_vector_10(double A[10][10], double* v) {
+__device__ inline bool null_vector_10(double A[10][10], double* v) {
   int colperm[10];
   for (int j = 0; j < 10; ++j) colperm[j] = j;
   for (int r = 0; r < 9; ++r) {
@@ -340,7 +340,7 @@ __device__ bool null_vector_10(double A[10][10], double* v) {
 
 // FivePointSolver::Solve.  b1, b2: 5 bearing vectors each (row k = (x,y,z) of point k); Eout: up to 10
 // row-major 3x3 essential matrices with b2^T E b1 = 0.  Returns the number of models.
-__device__ int five_point(const double* b1, const double* b2, double* Eout) {
+__device__ inline int five_point(const double* b1, const double* b2, double* Eout) {
   double A[5][9];
   for (int i = 0; i < 5; ++i) {  // EncodeEpipolarEquation on homogeneous (3-D) points
     const double* x1 = b1 + 3 * i;

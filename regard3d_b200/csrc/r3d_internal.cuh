@@ -121,6 +121,7 @@ struct DeviceWorker {
   void* d_list2 = nullptr; size_t list2_cap = 0;
   void* d_mdense = nullptr; size_t mdense_cap = 0;
   void* d_scan = nullptr; size_t scan_cap = 0;      // split exact scan: partial top-2s + arrival counters  // (i, j) per pair segment, before packing
+  void* h_fstage[2] = {nullptr, nullptr}; size_t h_fstage_cap = 0;  // pinned staging of the filter's result download
   r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
 };
 

@@ -249,3 +249,9 @@ def test_ranked_replay_falls_back_for_non_finite_positions(r3dlib, oracle):
             k = lib.r3d_debug_post_process(got.ctypes.data_as(C.c_void_p), C.c_int64(n), xyI.ctypes.data_as(C.c_void_p),
                                            xyJ.ctypes.data_as(C.c_void_p), C.c_int(1))
             assert k == len(want) and np.array_equal(got[:k], want), (name, seed, "classic")
+
+
+def test_device_sample_stream_matches_host_random(r3dlib):
+    """The ACRANSAC sample stream drawn on the device (mt19937 + libstdc++'s uniform_int_distribution restated in
+    acransac_rng.cuh) is checked against this process's <random>: 400 rounds over pool sizes 8 ... 2^32."""
+    assert r3dlib.lib().r3d_debug_rng_selftest() == 1
