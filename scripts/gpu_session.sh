@@ -20,6 +20,10 @@ sanitize)
 ncu_k1) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_l2_candidates_2sm -s 4 -c 1 -f -o gpurun_out/prof_k1_2sm python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-filter --no-extras ${NCU_BENCH_ARGS:-} > gpurun_out/b_ncu.log 2>&1; echo "ncu_k1 rc=$?" ;;
 ncu_launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-extras ${NCU_BENCH_ARGS:-} > gpurun_out/b_ncu4.log 2>&1; echo "ncu_launches rc=$?" ;;
 ncu_ba) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_ba.csv python tests/gpu_ba_profile.py > gpurun_out/ba_prof.log 2>&1; echo "ncu_ba rc=$?" ;;
+filter) timeout 600 python -m pytest tests -x -q -m gpu -k "filter or compute_matches or golden" > gpurun_out/pytest_filter.log 2>&1; tail -15 gpurun_out/pytest_filter.log
+  R3D_DEBUG_TIMING=1 timeout 500 python bench.py --workload c2 --steps 3 --no-ba --no-extras > gpurun_out/bench_c2f.json 2> gpurun_out/bench_c2f.err; tail -5 gpurun_out/bench_c2f.err
+  python -c "import json; d=json.load(open('gpurun_out/bench_c2f.json')); print(json.dumps(d['f_filter']))" ;;
+ncu_filter) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_acransac_fused -s 1 -c 1 -f -o gpurun_out/prof_acransac_fused python bench.py --workload c2 --steps 1 --warmup 1 --no-cpu-baseline --no-ba --no-extras > gpurun_out/b_ncu_f.log 2>&1; echo "ncu_filter rc=$?" ;;
 *) echo "unknown step $step" ;;
 esac
 done
