@@ -174,8 +174,9 @@ void liop_process(const float* patch, float* desc) {
   }
   float norm = 0;
   for (int i = 0; i < dimension; ++i) norm += desc[i] * desc[i];
-  const double dn = std::sqrt((double)norm) > 1e-12 ? std::sqrt((double)norm) : 1e-12;  // VL_MAX(sqrt(norm), 1e-12)
-  for (int i = 0; i < dimension; ++i) desc[i] = (float)(desc[i] / dn);
+  // `float norm ... norm = VL_MAX(sqrt(norm), 1e-12)`: the double square root is stored back into the FLOAT
+  norm = (float)(std::sqrt((double)norm) > 1e-12 ? std::sqrt((double)norm) : 1e-12);
+  for (int i = 0; i < dimension; ++i) desc[i] /= norm;
 }
 
 // cv::getGaussianKernel(11, 1.2, CV_32F) of OpenCV 4.x (bit-exact softdouble kernel, rounded to float);

@@ -14,11 +14,24 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 
+_REF_LIOP_PATH = os.path.join(_HERE, "_ref", "libvlliop_ref.so")
+REFERENCE_ROOT = os.environ.get("R3D_REFERENCE", "/root/reference")
+
+
 def build(force=False):
-    """Compile the oracle with the committed Makefile (g++ -O3 -fopenmp -ffp-contract=off)."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    """Compile the oracle with the committed Makefile (g++ -O3 -fopenmp -ffp-contract=off; make tracks the sources)
+    and, when the reference tree is present (the build container; never on the GPU box), oracle/_ref."""
+    subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    build_ref()
     return _LIB_PATH
+
+
+def build_ref():
+    """oracle/_ref/libvlliop_ref.so: the reference's own vendored LIOP (src/thirdparty/liop/vl_liop.c) compiled from
+    the source where it lies.  Returns the path, or None when neither the reference tree nor a prebuilt file exists."""
+    if os.path.exists(os.path.join(REFERENCE_ROOT, "src", "thirdparty", "liop", "vl_liop.c")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref", "REFERENCE=" + REFERENCE_ROOT])
+    return _REF_LIOP_PATH if os.path.exists(_REF_LIOP_PATH) else None
 
 
 _lib = None
@@ -367,3 +380,82 @@ def ba_jacobian(intr, pose, X, obs):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+# ---- LIOP-144 descriptor stage --------------------------------------------------------------
+LIOP_SIDE = 41
+
+
+def liop_process(patch):
+    """Restatement of r3d_vl_liopdesc_process on one 41x41 float32 patch -> desc[144]."""
+    patch = np.ascontiguousarray(patch, np.float32).reshape(LIOP_SIDE * LIOP_SIDE)
+    desc = np.zeros(144, np.float32)
+    lib().orc_liop_process(_p(patch), _p(desc))
+    return desc
+
+
+_ref_liop = None
+
+
+def liop_ref_available():
+    return build_ref() is not None
+
+
+def liop_ref_process(patches):
+    """THE REFERENCE ITSELF: r3d_vl_liopdesc_new_basic(41) + r3d_vl_liopdesc_process of oracle/_ref (compiled from
+    /root/reference/src/thirdparty/liop/vl_liop.c) on n patches -> (n, 144)."""
+    global _ref_liop
+    if _ref_liop is None:
+        path = build_ref()
+        if path is None:
+            raise RuntimeError("oracle/_ref/libvlliop_ref.so is not built and the reference tree is absent")
+        L = C.CDLL(path)
+        L.r3d_vl_liopdesc_new_basic.restype = C.c_void_p
+        L.r3d_vl_liopdesc_new_basic.argtypes = [C.c_size_t]
+        L.r3d_vl_liopdesc_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.r3d_vl_liopdesc_delete.argtypes = [C.c_void_p]
+        L.r3d_vl_liopdesc_get_dimension.restype = C.c_size_t
+        L.r3d_vl_liopdesc_get_dimension.argtypes = [C.c_void_p]
+        _ref_liop = L
+    L = _ref_liop
+    patches = np.ascontiguousarray(patches, np.float32).reshape(-1, LIOP_SIDE * LIOP_SIDE)
+    h = L.r3d_vl_liopdesc_new_basic(LIOP_SIDE)
+    assert L.r3d_vl_liopdesc_get_dimension(h) == 144
+    out = np.zeros((len(patches), 144), np.float32)
+    for k in range(len(patches)):
+        L.r3d_vl_liopdesc_process(h, out[k].ctypes.data, patches[k].ctypes.data)
+    L.r3d_vl_liopdesc_delete(h)
+    return out
+
+
+def liop_affine(x, y, size, angle, factor):
+    M = np.zeros(6, np.float32)
+    lib().orc_liop_affine(C.c_float(x), C.c_float(y), C.c_float(size), C.c_float(angle), C.c_float(factor), _p(M))
+    return M.reshape(2, 3)
+
+
+def liop_warp(img, M):
+    img = np.ascontiguousarray(img, np.float32)
+    M = np.ascontiguousarray(M, np.float32).reshape(6)
+    out = np.zeros((LIOP_SIDE, LIOP_SIDE), np.float32)
+    lib().orc_liop_warp(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(M), _p(out))
+    return out
+
+
+def liop_blur(patch):
+    patch = np.ascontiguousarray(patch, np.float32).reshape(LIOP_SIDE, LIOP_SIDE)
+    out = np.zeros((LIOP_SIDE, LIOP_SIDE), np.float32)
+    lib().orc_liop_blur(_p(patch), _p(out))
+    return out
+
+
+def liop_describe(img, kps, factor, want_patches=False):
+    """extractLIOPFeatures twin: kps (n, 4) = x, y, size (diameter), angle (degrees) -> (n, 144) [, (n, 41, 41)]."""
+    img = np.ascontiguousarray(img, np.float32)
+    kps = np.ascontiguousarray(kps, np.float32).reshape(-1, 4)
+    n = len(kps)
+    desc = np.zeros((n, 144), np.float32)
+    patches = np.zeros((n, LIOP_SIDE, LIOP_SIDE), np.float32) if want_patches else None
+    lib().orc_liop_describe(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_uint64(n), C.c_float(factor),
+                            _p(desc), _p(patches) if want_patches else None)
+    return (desc, patches) if want_patches else desc
