@@ -25,7 +25,7 @@ EXPORTS = [
     "r3d_bundle_adjust", "r3d_ba_residuals", "r3d_compute_matches", "r3d_get_match_timing",
     "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
     "r3d_comm_unique_id", "r3d_comm_init", "r3d_comm_destroy", "r3d_comm_world", "r3d_debug_post_process",
-    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr", "r3d_debug_rng_selftest",
+    "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr", "r3d_debug_rng_selftest", "r3d_liop_describe", "r3d_debug_liop_process",
 ]
 
 
@@ -286,6 +286,21 @@ class Context:
             xyp = _p(xy)
         self._check(lib().r3d_upload_regions(self._h, C.c_uint32(view_id), _p(desc), C.c_uint32(n), C.c_uint32(dim),
                                              C.c_int(dt), xyp))
+
+    def liop_describe(self, image, keypoints, kp_size_factor=8.0):
+        """image (h, w) float32; keypoints (n, 4) = x, y, size (diameter), angle (degrees) -> (n, 144) float32."""
+        image = np.ascontiguousarray(image, np.float32)
+        kps = np.ascontiguousarray(keypoints, np.float32).reshape(-1, 4)
+        desc = np.zeros((len(kps), 144), np.float32)
+        self._check(lib().r3d_liop_describe(self._h, _p(image), C.c_uint32(image.shape[1]), C.c_uint32(image.shape[0]),
+                                            _p(kps), C.c_uint32(len(kps)), C.c_float(kp_size_factor), _p(desc)))
+        return desc
+
+    def debug_liop_process(self, patches):
+        patches = np.ascontiguousarray(patches, np.float32).reshape(-1, 41 * 41)
+        desc = np.zeros((len(patches), 144), np.float32)
+        self._check(lib().r3d_debug_liop_process(self._h, _p(patches), C.c_uint32(len(patches)), _p(desc)))
+        return desc
 
     def clear_regions(self):
         self._check(lib().r3d_clear_regions(self._h))

@@ -12,7 +12,7 @@ c2) timeout 600 python bench.py --workload c2 --no-ba > gpurun_out/bench_c2.json
 c4) timeout 900 python bench.py --workload c4 --steps 1 --warmup 1 --no-ba > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?" ;;
 sanitize)
   for tool in memcheck racecheck synccheck; do
-    for part in match filter ba; do
+    for part in match filter ba liop; do
       timeout 200 compute-sanitizer --tool $tool --print-limit 20 python scripts/sanitize_small.py $part > gpurun_out/sanitizer_${tool}_${part}.log 2>&1
       echo "$tool $part rc=$?"; tail -3 gpurun_out/sanitizer_${tool}_${part}.log
     done

@@ -50,5 +50,11 @@ if what in ("ba", "all"):
     s, trace = ctx.bundle_adjust(arrs, max_iterations=3)
     print("ba:", s["iterations"], "iterations, cost", trace[0], "->", trace[-1])
     ctx.ba_residuals(arrs)
+if what in ("liop", "all"):
+    rng = np.random.default_rng(1)
+    img = rng.random((120, 160)).astype(np.float32)
+    kps = np.stack([rng.uniform(-5, 165, 40), rng.uniform(-5, 125, 40), rng.uniform(3, 30, 40), rng.uniform(0, 360, 40)], 1)
+    d = ctx.liop_describe(img, kps.astype(np.float32), 8.0)
+    print("liop:", d.shape, float(np.linalg.norm(d, axis=1).mean()))
 ctx.close()
 print("sanitize_small: done")
