@@ -66,13 +66,13 @@ int r3d_clear_regions(r3d_ctx* ctx);
 typedef struct { float x, y, size, angle; } r3d_keypoint;
 /* Replaces Regard3DFeatures::extractLIOPFeatures (src/Regard3DFeatures.cpp:719-861) for one image: per keypoint a
  * 41x41 patch (cv::warpAffine with the inverse map of :766-800, cv::GaussianBlur sigma 1.2) and its LIOP descriptor
- * r3d_vl_liopdesc_process (src/thirdparty/liop/vl_liop.c:434-575; 4 neighbours, 6 spatial bins, radius 6 -> 144
+ * r3d_vl_liopdesc_process [src/thirdparty/liop/vl_liop.c:434-575] (4 neighbours, 6 spatial bins, radius 6 -> 144
  * floats, unit L2 norm).  image: height x width float32 row-major (openMVG::image::Image<float>, cv::eigen2cv);
  * kp_size_factor: Regard3DFeatures::getKpSizeFactor (:691-716; 8 for AKAZE / Fast-AKAZE); desc_out: n x 144, in
  * keypoint order (the reference appends in thread-completion order, :838-851). */
 int r3d_liop_describe(r3d_ctx* ctx, const float* image, uint32_t width, uint32_t height,
                       const r3d_keypoint* keypoints, uint32_t n, float kp_size_factor, float* desc_out);
-/* Diagnostics: r3d_vl_liopdesc_process alone on n ready 41x41 float32 patches. */
+/* Diagnostics: the descriptor function alone (vl_liop.c:434-575) on n ready 41x41 float32 patches. */
 int r3d_debug_liop_process(r3d_ctx* ctx, const float* patches, uint32_t n, float* desc_out);
 
 /* ---- putative matching --------------------------------------------------------------------- */
