@@ -26,8 +26,12 @@ void set_global_error(const std::string& s) {
 }
 
 int fail(r3d_ctx* ctx, int code, const std::string& msg) {
-  if (ctx) ctx->last_error = msg;
-  set_global_error(msg);
+  // workers and batch tails report from several threads: the context's message is written under the same lock
+  {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    if (ctx) ctx->last_error = msg;
+    g_last_error = msg;
+  }
   return code;
 }
 
@@ -114,7 +118,7 @@ static int encode_view_maps(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, uint32_t 
   CUtensorMap maps[3];
   void* bases[3] = {(void*)v.d_opQ, (void*)v.d_opD, (void*)v.d_opD};
   for (int m = 0; m < 3; ++m) {
-    cuuint64_t gdim[2] = {(cuuint64_t)v.kp, (cuuint64_t)v.n_pad};
+    cuuint64_t gdim[2] = {(cuuint64_t)v.kp, (cuuint64_t)(v.tc_ok ? v.n_pad : (uint32_t)kRowPad)};
     cuuint64_t gstride[1] = {(cuuint64_t)v.kp * sizeof(__half)};
     cuuint32_t box[2] = {(cuuint32_t)kKBlock, (cuuint32_t)(m == 2 ? kTileRows / 2 : kTileRows)};
     cuuint32_t estr[2] = {1, 1};
@@ -176,12 +180,17 @@ int prepare_views(r3d_ctx* ctx, DeviceWorker& w) {
     v->max_hnorm = std::sqrt(stats[4 * i + 1]) * (1.f + 1e-6f);
     v->max_dnorm = std::sqrt(stats[4 * i + 2]) * (1.f + 1e-6f);
     v->max_abs = stats[4 * i + 3];
-    if (v->max_abs > 32000.f)
-      return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor magnitude exceeds the fp16 operand range");
+    // a view the fp16 operands cannot represent (|a_k| > 32000, or ||a||^2 >= 2^28 for the two-piece norm split)
+    // keeps its exact descriptors only: its pairs take the exact scan (slower, same results)
+    if (!v->tc_ok || !(v->max_abs <= 32000.f) || !(stats[4 * i + 0] < 2.6e8f)) {
+      v->tc_ok = false;
+      v->prepared = true;
+      continue;
+    }
     max_n2 = std::fmax(max_n2, stats[4 * i + 0]);
   }
   for (auto& kv : w.views)
-    if (kv.second.prepared) max_n2 = std::fmax(max_n2, kv.second.max_norm * kv.second.max_norm);
+    if (kv.second.prepared && kv.second.tc_ok) max_n2 = std::fmax(max_n2, kv.second.max_norm * kv.second.max_norm);
   // Norm split scale: ||a||^2 ~= p0*2^e0 + p1*2^(e0-11) with p0 <= 2^13 and 2^(e0-11) a normal fp16.
   int e0 = -3;
   if (max_n2 > 0.f) {
@@ -189,13 +198,14 @@ int prepare_views(r3d_ctx* ctx, DeviceWorker& w) {
     std::frexp(max_n2 * 1.0001f, &ex);  // max_n2 < 2^ex
     e0 = std::max(-3, ex - 13);
   }
-  if (e0 > 15) return fail(ctx, R3D_ERR_UNSUPPORTED, "descriptor norms exceed the fp16 operand range");
+  if (e0 > 15) e0 = 15;  // unreachable: norms that large were routed to the exact scan above
   if (w.e0_fixed && e0 < w.e0) e0 = w.e0;  // never shrink: keeps already prepared views valid
   const bool redo_all = w.e0_fixed && e0 != w.e0;
   w.e0 = e0;
   w.e0_fixed = true;
   for (auto& kv : w.views) {
     ViewDev& v = kv.second;
+    if (!v.tc_ok) continue;
     if (v.prepared && !redo_all) continue;
     int rc = launch_view_prepare(ctx, w, v, e0);
     if (rc) return rc;
@@ -292,7 +302,6 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
   if (!ctx) return R3D_ERR_INVALID;
   if (dtype != R3D_F32 && dtype != R3D_U8) return fail(ctx, R3D_ERR_INVALID, "r3d_upload_regions: bad dtype");
   if (n > 0 && (!desc || dim == 0)) return fail(ctx, R3D_ERR_INVALID, "r3d_upload_regions: NULL descriptors");
-  if (dim > 240) return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_upload_regions: descriptor dimension > 240");
   for (auto& w : ctx->workers) {
     R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
     auto it = w.views.find(view_id);
@@ -304,17 +313,24 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
     ViewDev v;
     v.n = n; v.dim = dim; v.dtype = (uint32_t)dtype;
     v.n_pad = (uint32_t)pad_up((int)(n ? n : 1), kRowPad);
-    v.kp = (uint32_t)operand_cols((int)(dim ? dim : 16));
+    v.tc_ok = dim <= 240;  // Kp <= 256 columns; wider descriptors are matched by the exact scan only
+    v.kp = (uint32_t)operand_cols((int)(dim && v.tc_ok ? dim : 16));
     const size_t rb = dtype == R3D_F32 ? (size_t)dim * 4 : (size_t)dim;
     v.d_desc = pool_alloc(w, std::max<size_t>(rb * n, 16));
-    v.d_opQ = (__half*)pool_alloc(w, (size_t)v.n_pad * v.kp * sizeof(__half));
-    v.d_opD = (__half*)pool_alloc(w, (size_t)v.n_pad * v.kp * sizeof(__half));
+    const size_t op_rows = v.tc_ok ? v.n_pad : (uint32_t)kRowPad;  // a token block keeps the tensor maps valid
+    v.d_opQ = (__half*)pool_alloc(w, op_rows * v.kp * sizeof(__half));
+    v.d_opD = (__half*)pool_alloc(w, op_rows * v.kp * sizeof(__half));
     v.d_stats = (float*)pool_alloc(w, 4 * sizeof(float));
     if (xy && n) v.d_xy = (float2*)pool_alloc(w, (size_t)n * sizeof(float2));
     if (!v.d_desc || !v.d_opQ || !v.d_opD || !v.d_stats || (xy && n && !v.d_xy)) {
       free_view(w, v);
       return fail(ctx, R3D_ERR_NOMEM, "r3d_upload_regions: device allocation failed");
     }
+    // every error exit below returns the view's device blocks to the pool
+    struct ViewGuard {
+      DeviceWorker& w; ViewDev& v; bool armed = true;
+      ~ViewGuard() { if (armed) { cudaStreamSynchronize(w.stream); free_view(w, v); } }
+    } guard{w, v};
     if (n) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_desc, desc, rb * n, cudaMemcpyHostToDevice, w.stream));
     if (xy && n) {
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(v.d_xy, xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, w.stream));
@@ -324,16 +340,14 @@ int r3d_upload_regions(r3d_ctx* ctx, uint32_t view_id, const void* desc, uint32_
     ctx->pending_h2d += rb * n + (xy ? (size_t)n * 8 : 0);
     uint32_t slot;
     auto sit = w.view_slot.find(view_id);
-    if (sit == w.view_slot.end()) {
-      slot = (uint32_t)w.view_slot.size();
-      w.view_slot[view_id] = slot;
-    } else {
-      slot = sit->second;
-    }
+    const bool new_slot = sit == w.view_slot.end();
+    slot = new_slot ? (uint32_t)w.view_slot.size() : sit->second;
     int rc = ensure_tmap_capacity(ctx, w, slot + 1);
     if (rc) return rc;
     rc = encode_view_maps(ctx, w, v, slot);  // synchronises the stream: host buffers are consumed
     if (rc) return rc;
+    if (new_slot) w.view_slot[view_id] = slot;  // only a stored view keeps a slot
+    guard.armed = false;
     w.views[view_id] = std::move(v);
   }
   return R3D_OK;

@@ -48,75 +48,16 @@ __device__ __forceinline__ float exact_l2(const void* __restrict__ qrow, const v
     const uint8_t* q = (const uint8_t*)qrow;
     const uint8_t* d = (const uint8_t*)drow;
     uint32_t k = 0;
-    if ((dim & 3u) == 0) {
+    if ((dim & 3u) == 0 && dim <= 256u) {  // 255^2 * 256 < 2^24: beyond that the float accumulation may round
       const uint32_t* q4 = (const uint32_t*)q;
       const uint32_t* d4 = (const uint32_t*)d;
       const uint32_t g = dim >> 2;
 #pragma unroll 4
-      // integer form: all partial sums of the upstream float accumulation are integers < 2^24 (dim <= 240),
+      // integer form: all partial sums of the upstream float accumulation are integers < 2^24 (dim <= 256),
       // so the float result equals the exact integer sum of squared byte differences
       uint32_t isum = 0u;
       for (uint32_t t = 0; t < g; ++t) {
         const uint32_t ad = __vabsdiffu4(q4[t], __ldg(d4 + t));
-        isum = __dp4a(ad, ad, isum);
-      }
-      acc = (float)isum;
-      k = dim;
-    } else {
-      for (; k + 3 < dim; k += 4)
-        acc = acc4(acc, (float)((int)q[k] - (int)d[k]), (float)((int)q[k + 1] - (int)d[k + 1]),
-                   (float)((int)q[k + 2] - (int)d[k + 2]), (float)((int)q[k + 3] - (int)d[k + 3]));
-    }
-    for (; k < dim; ++k) {
-      const float df = (float)((int)q[k] - (int)d[k]);
-      acc = __fadd_rn(acc, __fmul_rn(df, df));
-    }
-  }
-  return acc;
-}
-
-template <int DTYPE>
-__device__ __forceinline__ float exact_l2_generic(const void* __restrict__ qrow, const void* __restrict__ drow,
-                                           uint32_t dim) {
-  float acc = 0.f;
-  if (DTYPE == 0) {
-    const float* q = (const float*)qrow;
-    const float* d = (const float*)drow;
-    uint32_t k = 0;
-    if ((dim & 3u) == 0) {
-      const float4* q4 = (const float4*)q;
-      const float4* d4 = (const float4*)d;
-      const uint32_t g = dim >> 2;
-#pragma unroll 4
-      for (uint32_t t = 0; t < g; ++t) {
-        const float4 a = q4[t];  // may live in shared memory
-        const float4 b = d4[t];
-        acc = acc4(acc, __fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w));
-      }
-      k = dim;
-    } else {
-      for (; k + 3 < dim; k += 4)
-        acc = acc4(acc, __fsub_rn(q[k], d[k]), __fsub_rn(q[k + 1], d[k + 1]), __fsub_rn(q[k + 2], d[k + 2]),
-                   __fsub_rn(q[k + 3], d[k + 3]));
-    }
-    for (; k < dim; ++k) {
-      const float df = __fsub_rn(q[k], d[k]);
-      acc = __fadd_rn(acc, __fmul_rn(df, df));
-    }
-  } else {
-    const uint8_t* q = (const uint8_t*)qrow;
-    const uint8_t* d = (const uint8_t*)drow;
-    uint32_t k = 0;
-    if ((dim & 3u) == 0) {
-      const uint32_t* q4 = (const uint32_t*)q;
-      const uint32_t* d4 = (const uint32_t*)d;
-      const uint32_t g = dim >> 2;
-#pragma unroll 4
-      // integer form: all partial sums of the upstream float accumulation are integers < 2^24 (dim <= 240),
-      // so the float result equals the exact integer sum of squared byte differences
-      uint32_t isum = 0u;
-      for (uint32_t t = 0; t < g; ++t) {
-        const uint32_t ad = __vabsdiffu4(q4[t], d4[t]);
         isum = __dp4a(ad, ad, isum);
       }
       acc = (float)isum;

@@ -149,7 +149,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     pd.I = I; pd.J = J; pd.nI = vi.n; pd.nJ = vj.n; pd.nI_pad = vi.n_pad; pd.nJ_pad = vj.n_pad;
     pd.slotI = w.view_slot[I]; pd.slotJ = w.view_slot[J];
     pd.descI = vi.d_desc; pd.descJ = vj.d_desc;
-    pd.use_tc = ((flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
+    pd.use_tc = ((flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.tc_ok && vj.tc_ok && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
     pd.eps_abs = pair_eps(vi, vj);
     {
       uint32_t nchunks = vi.n_pad / kChunk, bits = 4;
@@ -368,8 +368,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       bool released = false;
       auto release = [&]() { if (!released) { released = true; copied->set_value(); } };
       auto bail = [&](const char* what, cudaError_t e) {
-        ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
-        tail_rc.store(R3D_ERR_CUDA);
+        tail_rc.store(fail(ctx, R3D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)));
         release();
       };
       cudaError_t e = cudaSetDevice(w.device);

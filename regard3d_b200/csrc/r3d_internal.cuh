@@ -53,6 +53,8 @@ struct ViewDev {
   bool ranks_tried = false;  // tables stay empty for views with non-finite positions (classic replay then)
   bool has_xy = false;
   bool prepared = false;
+  bool tc_ok = true;         // false: no fp16 operands (dim > 240 or values outside the fp16 operand range):
+                             // pairs touching this view are matched by the exact CUDA-core scan only
   int prepared_e0 = 0;
   // error-bound constants (host copies of device reductions)
   float max_norm = 0.f;      // max_i ||a_i||

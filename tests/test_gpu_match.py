@@ -122,3 +122,35 @@ def test_full_size_properties_c2_slice(gpu_ctx, r3dlib):
     for (I, J), s in a.items():
         ok = sum(1 for (i, j) in s if truth[I][i] == truth[J][j] and truth[I][i] >= 0)
         assert ok >= 0.98 * len(s)
+
+
+@pytest.mark.parametrize("case", ["dim256_f32", "dim300_u8", "huge_values", "mixed_range"])
+def test_descriptors_outside_the_fp16_operand_range_take_the_exact_scan(gpu_ctx, oracle, r3dlib, case):
+    """Round 1 returned R3D_ERR_UNSUPPORTED for descriptor dimensions > 240 and values beyond the fp16 operands;
+    such views now keep their exact descriptors only and their pairs are matched by the exact CUDA-core scan."""
+    rng = np.random.default_rng(17)
+    n, nv = 600, 3
+    if case == "dim256_f32":
+        descs = [rng.standard_normal((n, 256)).astype(np.float32) for _ in range(nv)]
+    elif case == "dim300_u8":
+        descs = [rng.integers(0, 256, (n, 300)).astype(np.uint8) for _ in range(nv)]
+    elif case == "huge_values":
+        descs = [(rng.standard_normal((n, 64)) * 1e5).astype(np.float32) for _ in range(nv)]
+    else:                                                    # one view out of range, the others on the tensor path
+        descs = [rng.standard_normal((n, 64)).astype(np.float32) for _ in range(nv)]
+        descs[1] = (descs[1] * 5e4).astype(np.float32)
+    for v in range(1, nv):                                   # plant true correspondences so the ratio test passes
+        descs[v][:200] = descs[0][:200]
+        if descs[v].dtype != np.uint8:
+            descs[v][:200] += (0.01 * np.abs(descs[0][:200]).mean() * rng.standard_normal((200, descs[v].shape[1]))).astype(np.float32)
+    if case == "mixed_range":
+        descs[1] = descs[1].astype(np.float32)
+    xys = [rng.uniform(0, 900, (n, 2)).astype(np.float32) for _ in range(nv)]
+    pairs = synth.exhaustive_pairs(nv)
+    gpu_ctx.clear_regions()
+    for v in range(nv):
+        gpu_ctx.upload_regions(v, descs[v], xys[v])
+    ofs, m = oracle.match_pairs(descs, xys, pairs, 0.8)
+    got = dict_sets(gpu_ctx.match_pairs(pairs, 0.8).to_dict())
+    assert got == match_sets(ofs, m, pairs) and sum(len(s) for s in got.values()) > 100
+    gpu_ctx.clear_regions()
