@@ -33,8 +33,6 @@ namespace cg = cooperative_groups;
 namespace r3d {
 namespace ba {
 
-constexpr int kMaxObsPerPoint = 64;  // shared-memory staging of one point's observations
-constexpr int kSchurWarps = 8;
 constexpr int kObsDoubles = 12 + 12 + 6 + 2;  // Jc, Jg, Jp, r
 
 struct Dev {
@@ -213,55 +211,73 @@ __device__ __forceinline__ void add_block_upper(double* S, uint32_t nB, uint32_t
   }
 }
 
-// ---- Schur complement: one warp per point ------------------------------------------------------
-__global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv_radius, int obs_cap) {
-  extern __shared__ double sm[];
-  // per warp: obs staging [obs_cap][kObsDoubles] + W blocks [obs_cap][36]; obs_cap = max track length
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* J = sm + (size_t)warp * obs_cap * (kObsDoubles + 36);
-  double* W = J + (size_t)obs_cap * kObsDoubles;
-  __shared__ uint32_t s_colc[kSchurWarps][kMaxObsPerPoint];
-  __shared__ int s_colg[kSchurWarps][kMaxObsPerPoint];
-  __shared__ double s_gg_warp[kSchurWarps][36];  // (g0,g0) block of each warp's point, g0 = group of its first obs
-  __shared__ double s_rg_warp[kSchurWarps][6];   // rhs of that group
-  __shared__ int s_g0[kSchurWarps];
-  if (lane == 0) s_g0[warp] = -1;
-  for (int e = lane; e < 6; e += 32) s_rg_warp[warp][e] = 0.0;
-  for (int e = lane; e < 36; e += 32) s_gg_warp[warp][e] = 0.0;
-  __syncwarp();
-  const uint32_t ip = blockIdx.x * kSchurWarps + warp;
-  if (ip < d.n_pts) {
+// ---- Schur complement: one CTA per point, any track length (the general path) ---------------------------
+// Points the batched kernel below cannot take (more than 32 observations -- real tracks span hundreds of views --,
+// more than 2 intrinsic groups, a camera that sees the point twice) are listed and handled here: the scaled Jacobians
+// and W blocks of the point's observations are staged in a per-CTA slice of GLOBAL scratch (`cap` observations), so
+// there is no limit on the track length (round 1 staged them in shared memory and returned R3D_ERR_UNSUPPORTED beyond
+// 64).  Same algebra as the batched kernel: V = sum Jp^T Jp + D^2, W_c = Jc^T Jp per camera, W_g = sum over the
+// observations of an intrinsic group, S -= W_a V^-1 W_b^T over all entry pairs, U terms added directly.
+constexpr int kCtaThreads = 128;
+__global__ void __launch_bounds__(kCtaThreads) k_ba_schur_cta(Dev d, const uint32_t* __restrict__ list, uint32_t n_list,
+                                                              double inv_radius, double* __restrict__ scratch,
+                                                              int* __restrict__ cols, uint32_t cap) {
+  __shared__ double s_red[6][kCtaThreads / 32];
+  __shared__ double s_Vi[9], s_Vg[3];
+  double* J = scratch + (size_t)blockIdx.x * cap * (kObsDoubles + 36);
+  double* W = J + (size_t)cap * kObsDoubles;
+  int* colc = cols + (size_t)blockIdx.x * cap * 3;
+  int* colg = colc + cap;
+  int* lead = colg + cap;
+  const int tid = threadIdx.x;
+  for (uint32_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+    const uint32_t ip = list[li];
     const uint32_t b = d.pt_ofs[ip], e = d.pt_ofs[ip + 1];
     const int nobs = (int)(e - b);
+    __syncthreads();  // the previous point's readers are done with the scratch slice
     // 1. stage the scaled Jacobians of this point's observations
-    for (int t = lane; t < nobs; t += 32) {
+    for (int t = tid; t < nobs; t += kCtaThreads) {
       double* jt = J + (size_t)t * kObsDoubles;
-      scaled_jacobian(d, d.pt_obs[b + t], jt, jt + 12, jt + 24, jt + 30, &s_colc[warp][t], &s_colg[warp][t]);
+      uint32_t cc;
+      int cg;
+      scaled_jacobian(d, d.pt_obs[b + t], jt, jt + 12, jt + 24, jt + 30, &cc, &cg);
+      colc[t] = (int)cc;
+      colg[t] = cg;
     }
-    __syncwarp();
-    // 2. V = sum Jp^T Jp + D^2, g_p  (warp reduction)
+    __syncthreads();
+    // 2. V = sum Jp^T Jp + D^2, V^-1, V^-1 g_p
     double v[6] = {0, 0, 0, 0, 0, 0};
-    for (int t = lane; t < nobs; t += 32) {
+    for (int t = tid; t < nobs; t += kCtaThreads) {
       const double* jp = J + (size_t)t * kObsDoubles + 24;
       v[0] += jp[0] * jp[0] + jp[3] * jp[3]; v[1] += jp[0] * jp[1] + jp[3] * jp[4]; v[2] += jp[0] * jp[2] + jp[3] * jp[5];
       v[3] += jp[1] * jp[1] + jp[4] * jp[4]; v[4] += jp[1] * jp[2] + jp[4] * jp[5]; v[5] += jp[2] * jp[2] + jp[5] * jp[5];
     }
-    for (int k = 0; k < 6; ++k)
+    for (int k = 0; k < 6; ++k) {
       for (int o = 16; o >= 1; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+      if ((tid & 31) == 0) s_red[k][tid >> 5] = v[k];
+    }
+    __syncthreads();
     const size_t pcol = (size_t)d.nB + 3 * (size_t)ip;
-    double V[9] = {v[0], v[1], v[2], v[1], v[3], v[4], v[2], v[4], v[5]};
-    for (int i = 0; i < 3; ++i) V[4 * i] += fmin(fmax(d.diag[pcol + i], 1e-6), 1e32) * inv_radius;
-    double Vi[9];
-    inv3_sym(V, Vi);
-    if (lane == 0)
-      for (int i = 0; i < 9; ++i) d.Vinv[9 * (size_t)ip + i] = Vi[i];
-    const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
-    const double Vg[3] = {Vi[0] * gp[0] + Vi[1] * gp[1] + Vi[2] * gp[2], Vi[3] * gp[0] + Vi[4] * gp[1] + Vi[5] * gp[2],
-                          Vi[6] * gp[0] + Vi[7] * gp[1] + Vi[8] * gp[2]};
-    // 3. W blocks (6x3): camera and intrinsic group of every observation; B part of S.
-    //    Observations that share an intrinsic group are merged into ONE group block per point
-    //    (W_g = sum W_g,t): the pair loop below then touches the heavily shared group columns once.
-    for (int t = lane; t < nobs; t += 32) {
+    if (tid == 0) {
+      double vv[6];
+      for (int k = 0; k < 6; ++k) {
+        vv[k] = 0.0;
+        for (int wv = 0; wv < kCtaThreads / 32; ++wv) vv[k] += s_red[k][wv];
+      }
+      double V[9] = {vv[0], vv[1], vv[2], vv[1], vv[3], vv[4], vv[2], vv[4], vv[5]};
+      for (int i = 0; i < 3; ++i) V[4 * i] += fmin(fmax(d.diag[pcol + i], 1e-6), 1e32) * inv_radius;
+      double Vi[9];
+      inv3_sym(V, Vi);
+      for (int i = 0; i < 9; ++i) { d.Vinv[9 * (size_t)ip + i] = Vi[i]; s_Vi[i] = Vi[i]; }
+      const double gp[3] = {d.g[pcol], d.g[pcol + 1], d.g[pcol + 2]};
+      for (int i = 0; i < 3; ++i) s_Vg[i] = Vi[3 * i] * gp[0] + Vi[3 * i + 1] * gp[1] + Vi[3 * i + 2] * gp[2];
+    }
+    __syncthreads();
+    double Vi[9], Vg[3];
+    for (int i = 0; i < 9; ++i) Vi[i] = s_Vi[i];
+    for (int i = 0; i < 3; ++i) Vg[i] = s_Vg[i];
+    // 3. W blocks (6x3) of every observation's camera and intrinsic group; the U part of S
+    for (int t = tid; t < nobs; t += kCtaThreads) {
       const double* jt = J + (size_t)t * kObsDoubles;
       const double *jc = jt, *jg = jt + 12, *jp = jt + 24;
       double* wc = W + (size_t)t * 36;
@@ -272,74 +288,55 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
           wg[3 * i + j] = jg[i] * jp[j] + jg[6 + i] * jp[3 + j];
         }
       double blk[36];
-      const uint32_t cc = s_colc[warp][t];
+      const uint32_t cc = (uint32_t)colc[t];
       for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) blk[6 * i + j] = jc[i] * jc[j] + jc[6 + i] * jc[6 + j];
       add_block_upper(d.S, d.nB, cc, cc, blk, 1.0);
-      const int cg = s_colg[warp][t];
+      const int cg = colg[t];
       if (cg >= 0) {
         for (int i = 0; i < 6; ++i)
           for (int j = 0; j < 6; ++j) blk[6 * i + j] = jc[i] * jg[j] + jc[6 + i] * jg[6 + j];
         add_block_upper(d.S, d.nB, cc, (uint32_t)cg, blk, 1.0);
+        for (int i = 0; i < 6; ++i)
+          for (int j = 0; j < 6; ++j) blk[6 * i + j] = jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
+        add_block_upper(d.S, d.nB, (uint32_t)cg, (uint32_t)cg, blk, 1.0);
       }
-    }
-    __syncwarp();
-    // group merge: the first observation of each group becomes its leader; GG = sum Jg^T Jg per leader
-    double* GG = s_gg_warp[warp];  // 36 doubles of the (first) leader; other leaders go straight to global
-    for (int e = lane; e < 36; e += 32) GG[e] = 0.0;
-    __syncwarp();
-    if (lane == 0 && d.refine_intr) {
-      for (int t = 0; t < nobs; ++t) {
-        const int cg = s_colg[warp][t];
-        if (cg < 0) continue;
-        int leader = t;
+      // the first observation of each intrinsic group leads it
+      int ld = t;
+      if (cg >= 0)
         for (int u = 0; u < t; ++u)
-          if (s_colg[warp][u] == cg) { leader = u; break; }
-        const double* jg = J + (size_t)t * kObsDoubles + 12;
-        if (leader != t) {
-          double* wl = W + (size_t)leader * 36 + 18;
-          const double* wt = W + (size_t)t * 36 + 18;
-          for (int e = 0; e < 18; ++e) wl[e] += wt[e];
-          s_colg[warp][t] = -1;  // merged away
-        }
-        if (leader == 0 || s_colg[warp][0] == cg) {  // contributions to the first group: warp-local block
-          for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) GG[6 * i + j] += jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
-        } else {
-          double blk[36];
-          for (int i = 0; i < 6; ++i)
-            for (int j = 0; j < 6; ++j) blk[6 * i + j] = jg[i] * jg[j] + jg[6 + i] * jg[6 + j];
-          add_block_upper(d.S, d.nB, (uint32_t)cg, (uint32_t)cg, blk, 1.0);
-        }
+          if (colg[u] == cg) { ld = u; break; }
+      lead[t] = ld;
+    }
+    __syncthreads();
+    // merge the group blocks into their leaders (W_g = sum over the group's observations), retire the others
+    for (int t = tid; t < nobs; t += kCtaThreads) {
+      if (colg[t] >= 0 && lead[t] != t) {
+        double* wl = W + (size_t)lead[t] * 36 + 18;
+        const double* wt = W + (size_t)t * 36 + 18;
+        for (int q = 0; q < 18; ++q) atomicAdd(&wl[q], wt[q]);
       }
     }
-    __syncwarp();
-    // 4. Schur part over the 2*nobs blocks (camera t -> block 2t, group t -> block 2t+1; merged groups are -1)
-    const int nblk = 2 * nobs;
-    int g0 = -1;
-    for (int t = 0; t < nobs; ++t)
-      if (s_colg[warp][t] >= 0) { g0 = s_colg[warp][t]; break; }
-    if (lane == 0) s_g0[warp] = g0;
-    for (int a = lane; a < nblk; a += 32) {  // rhs[a] += W_a V^-1 g_p
-      const int ca = (a & 1) ? s_colg[warp][a >> 1] : (int)s_colc[warp][a >> 1];
+    __syncthreads();
+    for (int t = tid; t < nobs; t += kCtaThreads)
+      if (colg[t] >= 0 && lead[t] != t) colg[t] = -1;
+    __syncthreads();
+    // 4. Schur part over the 2 * nobs entries (camera t -> entry 2t, group t -> entry 2t + 1; merged groups are -1)
+    const long long nblk = 2LL * nobs;
+    for (long long a = tid; a < nblk; a += kCtaThreads) {  // rhs[a] += W_a V^-1 g_p
+      const int ca = (a & 1) ? colg[a >> 1] : colc[a >> 1];
       if (ca < 0) continue;
       const double* wa = W + (size_t)(a >> 1) * 36 + (a & 1) * 18;
-      if ((a & 1) && ca == g0) {  // the (merged) first group: unique writer inside this warp
-        for (int i = 0; i < 6; ++i) s_rg_warp[warp][i] += wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2];
-      } else {
-        for (int i = 0; i < 6; ++i) atomicAdd(&d.rhs[ca + i], wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2]);
-      }
+      for (int i = 0; i < 6; ++i) atomicAdd(&d.rhs[ca + i], wa[3 * i] * Vg[0] + wa[3 * i + 1] * Vg[1] + wa[3 * i + 2] * Vg[2]);
     }
-    const int npairs = nblk * (nblk + 1) / 2;
-    for (int pr = lane; pr < npairs; pr += 32) {
-      // unrank pr -> (a <= bb)
-      int a = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
-      while ((a + 1) * (a + 2) / 2 <= pr) ++a;
-      while (a * (a + 1) / 2 > pr) --a;
-      const int bb_ = pr - a * (a + 1) / 2;  // bb_ <= a
-      const int hi = a, lo = bb_;
-      const int ch = (hi & 1) ? s_colg[warp][hi >> 1] : (int)s_colc[warp][hi >> 1];
-      const int cl = (lo & 1) ? s_colg[warp][lo >> 1] : (int)s_colc[warp][lo >> 1];
+    const long long npairs = nblk * (nblk + 1) / 2;
+    for (long long pr = tid; pr < npairs; pr += kCtaThreads) {
+      long long hi = (long long)((sqrt(8.0 * (double)pr + 1.0) - 1.0) * 0.5);
+      while ((hi + 1) * (hi + 2) / 2 <= pr) ++hi;
+      while (hi * (hi + 1) / 2 > pr) --hi;
+      const long long lo = pr - hi * (hi + 1) / 2;  // lo <= hi
+      const int ch = (hi & 1) ? colg[hi >> 1] : colc[hi >> 1];
+      const int cl = (lo & 1) ? colg[lo >> 1] : colc[lo >> 1];
       if (ch < 0 || cl < 0) continue;
       const double* wl = W + (size_t)(lo >> 1) * 36 + (lo & 1) * 18;
       const double* wh = W + (size_t)(hi >> 1) * 36 + (hi & 1) * 18;
@@ -349,41 +346,15 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_ba_schur(Dev d, double inv
       double blk[36];
       for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 6; ++j) blk[6 * i + j] = WV[3 * i] * wh[3 * j] + WV[3 * i + 1] * wh[3 * j + 1] + WV[3 * i + 2] * wh[3 * j + 2];
-      // blk = W_lo V^-1 W_hi^T  contributes to S[cl, ch]; for lo != hi the mirrored term S[ch, cl] is
-      // its transpose: in upper-block form both land on the same stored block (doubling when cl == ch).
-      if (lo == hi && (lo & 1) && cl == g0) {  // merged first group: single writer -> shared memory
-        for (int e = 0; e < 36; ++e) s_gg_warp[warp][e] -= blk[e];
-      } else if (lo == hi) {
-        add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
-      } else if (cl == ch) {  // two different observations sharing a block (same intrinsic group / camera)
+      // blk = W_lo V^-1 W_hi^T contributes to S[cl, ch]; for lo != hi the mirrored term S[ch, cl] is its transpose: in
+      // upper-block form both land on the same stored block (so a block shared by two different entries gets blk + blk^T)
+      if (lo != hi && cl == ch) {
         double sym[36];
         for (int i = 0; i < 6; ++i)
           for (int j = 0; j < 6; ++j) sym[6 * i + j] = blk[6 * i + j] + blk[6 * j + i];
         add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, sym, -1.0);
       } else {
         add_block_upper(d.S, d.nB, (uint32_t)cl, (uint32_t)ch, blk, -1.0);
-      }
-    }
-  }
-  // CTA-level reduction of the per-warp (g0,g0) blocks and group right-hand sides: one set of global
-  // atomics per CTA and distinct group instead of one per point
-  __syncthreads();
-  if (threadIdx.x < 42) {
-    const int e = threadIdx.x;
-    for (int wv = 0; wv < kSchurWarps; ++wv) {
-      const int g = s_g0[wv];
-      if (g < 0) continue;
-      bool first = true;
-      for (int u = 0; u < wv; ++u)
-        if (s_g0[u] == g) { first = false; break; }
-      if (!first) continue;
-      double acc = 0.0;
-      for (int u = wv; u < kSchurWarps; ++u)
-        if (s_g0[u] == g) acc += (e < 36) ? s_gg_warp[u][e] : s_rg_warp[u][e - 36];
-      if (e < 36) {
-        atomicAdd(&d.S[(size_t)(g + e / 6) * d.nB + g + e % 6], acc);
-      } else {
-        atomicAdd(&d.rhs[g + e - 36], acc);
       }
     }
   }
@@ -804,9 +775,12 @@ struct DeviceArrays {  // blocks come from (and return to) the worker's size-buc
   }
 };
 
-struct BatchPlan {  // device tables of the batched Schur kernel; n_batches == 0: use the per-point kernel
+struct BatchPlan {  // device tables of the batched Schur kernel + the points that go through the general CTA kernel
   r3d::ba::BatchTables t{};
   uint32_t n_batches = 0;
+  const uint32_t* d_long = nullptr;  // point ids for k_ba_schur_cta
+  uint32_t n_long = 0, long_cap = 1; // their number and longest track
+  bool want_batched = true;          // false: every point takes the CTA kernel (R3D_BA_SCHUR=point)
 };
 
 int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, DeviceArrays& mem, Dev& d, bool refine_intr,
@@ -849,8 +823,6 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   for (uint64_t o = 0; o < p->n_obs; ++o) hofs[p->obs_pt[o] + 1]++;
   uint32_t maxobs = 0;
   for (uint32_t i = 0; i < p->n_pts; ++i) { maxobs = std::max(maxobs, hofs[i + 1]); hofs[i + 1] += hofs[i]; }
-  if (maxobs > (uint32_t)r3d::ba::kMaxObsPerPoint)
-    return fail(ctx, R3D_ERR_UNSUPPORTED, "bundle adjustment: a point has more than 64 observations (round-1 limit)");
   if (max_obs_out) *max_obs_out = maxobs;
   {
     std::vector<uint32_t> pos(hofs.begin(), hofs.end() - 1);
@@ -866,97 +838,146 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   std::vector<r3d::ba::BatchDesc> h_batches;
   std::vector<int> h_cols;
   std::vector<unsigned char> h_lblk;
+  std::vector<uint32_t> h_long;
   if (plan) {
     using namespace r3d::ba;
     const uint32_t n_pts = p->n_pts;
-    std::atomic<int> ok{(maxobs <= 32 && n_pts > 0) ? 1 : 0};
     const int threads = std::max(1, ctx->host_threads);
-    // (1) processing order: counting sort of the points by the smallest camera that sees them
+    // (0) which points the batched kernel can take: <= 32 observations, <= 2 intrinsic groups, no camera twice.
+    //     Everything else (long tracks first of all) goes to the general CTA-per-point kernel.
     std::vector<uint32_t> key(n_pts, 0), nent(n_pts, 0);
+    std::vector<uint8_t> elig(n_pts, 0);
     const uint32_t kSlab = 4096;
     const size_t n_slabs = ((size_t)n_pts + kSlab - 1) / kSlab;
     parallel_for(threads, n_slabs, [&](size_t sl) {
       const uint32_t i1 = (uint32_t)std::min<size_t>((sl + 1) * kSlab, n_pts);
       for (uint32_t i = (uint32_t)(sl * kSlab); i < i1; ++i) {
+        const uint32_t nobs = hofs[i + 1] - hofs[i];
+        if (!plan->want_batched || nobs > 32 || nobs == 0) continue;
         uint32_t mn = p->n_cams;
         int g0 = -1, g1 = -1, ng = 0;
-        for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) {
+        bool ok = true;
+        for (uint32_t t = hofs[i]; t < hofs[i + 1] && ok; ++t) {
           const uint32_t cam = p->obs_cam[hobs[t]];
           mn = std::min(mn, cam);
           for (uint32_t u = hofs[i]; u < t; ++u)
-            if (p->obs_cam[hobs[u]] == cam) ok.store(0);  // a camera sees the point twice
+            if (p->obs_cam[hobs[u]] == cam) ok = false;  // a camera sees the point twice
           if (refine_intr) {
             const int g = (int)p->cam_intr[cam];
             if (g != g0 && g != g1) {
-              if (g0 < 0) g0 = g; else if (g1 < 0) g1 = g; else ok.store(0);  // > 2 groups
+              if (g0 < 0) g0 = g; else if (g1 < 0) g1 = g; else ok = false;  // > 2 groups
               ++ng;
             }
           }
         }
+        if (!ok) continue;
+        elig[i] = 1;
         key[i] = mn;
-        nent[i] = (hofs[i + 1] - hofs[i]) + (uint32_t)ng;
+        nent[i] = nobs + (uint32_t)ng;
       }
     });
-    if (ok.load()) {
+    // (1) processing order of the eligible points: counting sort by the smallest camera that sees them
+    {
       std::vector<uint32_t> bucket((size_t)p->n_cams + 2, 0);
-      for (uint32_t i = 0; i < n_pts; ++i) bucket[key[i] + 1]++;
+      uint32_t n_el = 0;
+      for (uint32_t i = 0; i < n_pts; ++i)
+        if (elig[i]) { bucket[key[i] + 1]++; ++n_el; }
       for (size_t c = 0; c + 1 < bucket.size(); ++c) bucket[c + 1] += bucket[c];
-      h_order.resize(n_pts);
-      for (uint32_t i = 0; i < n_pts; ++i) h_order[bucket[key[i]]++] = i;
-      // (2) batches: consecutive ordered points, cut by the point and entry capacities
-      h_ent_start.assign((size_t)n_pts + 1, 0);
+      h_order.resize(n_el);
+      for (uint32_t i = 0; i < n_pts; ++i)
+        if (elig[i]) h_order[bucket[key[i]]++] = i;
+    }
+    const uint32_t n_el = (uint32_t)h_order.size();
+    // (2) batches: consecutive ordered points, cut by the point, entry and distinct-block capacities of the kernel
+    //     (a stamp per 6-wide block tells whether the open batch already holds it)
+    h_ent_start.assign((size_t)n_el + 1, 0);
+    {
+      std::vector<uint32_t> stamp((size_t)p->n_cams + p->n_intr, 0xffffffffu);
       BatchDesc cur{0, 0, 0, 0};
-      uint32_t ent_run = 0;
-      for (uint32_t k = 0; k < n_pts; ++k) {
-        const uint32_t ne = nent[h_order[k]];
-        if (cur.count == (uint32_t)kBatchPoints || (ent_run - cur.ent_first) + ne > (uint32_t)kBatchEntries) {
+      uint32_t ent_run = 0, cur_blocks = 0, batch_id = 0;
+      for (uint32_t k = 0; k < n_el; ++k) {
+        const uint32_t ip = h_order[k];
+        const uint32_t ne = nent[ip];
+        auto count_new = [&](bool mark) {
+          uint32_t fresh = 0;
+          for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+            const uint32_t cam = p->obs_cam[hobs[t]];
+            const uint32_t blocks[2] = {cam, p->n_cams + p->cam_intr[cam]};
+            for (int q = 0; q < (refine_intr ? 2 : 1); ++q)
+              if (stamp[blocks[q]] != batch_id && stamp[blocks[q]] != (batch_id | 0x80000000u)) {
+                ++fresh;
+                if (mark) stamp[blocks[q]] = batch_id;
+                else stamp[blocks[q]] = batch_id | 0x80000000u;  // provisional: counted once within this point
+              }
+          }
+          if (!mark)  // undo the provisional marks
+            for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+              const uint32_t cam = p->obs_cam[hobs[t]];
+              const uint32_t blocks[2] = {cam, p->n_cams + p->cam_intr[cam]};
+              for (int q = 0; q < (refine_intr ? 2 : 1); ++q)
+                if (stamp[blocks[q]] == (batch_id | 0x80000000u)) stamp[blocks[q]] = 0xffffffffu;
+            }
+          return fresh;
+        };
+        const uint32_t fresh = count_new(false);
+        if (cur.count && (cur.count == (uint32_t)kBatchPoints || (ent_run - cur.ent_first) + ne > (uint32_t)kBatchEntries ||
+                          cur_blocks + fresh > (uint32_t)kBatchBlocks)) {
           h_batches.push_back(cur);
           cur = BatchDesc{k, 0, ent_run, 0};
+          cur_blocks = 0;
+          ++batch_id;
         }
+        cur_blocks += count_new(true);
         h_ent_start[k] = ent_run;
         ent_run += ne;
         cur.count++;
       }
-      h_ent_start[n_pts] = ent_run;
+      h_ent_start[n_el] = ent_run;
       if (cur.count) h_batches.push_back(cur);
-      // (3) per batch, in parallel: sorted distinct block columns and every entry's index into them
-      h_cols.assign(h_batches.size() * kBatchBlocks, 0);
       h_lblk.assign(ent_run, 0);
-      parallel_for(threads, h_batches.size(), [&](size_t bi) {
-        BatchDesc& bd = h_batches[bi];
-        int cols[kBatchEntries * 2];
-        int nc = 0;
-        for (uint32_t k = 0; k < bd.count; ++k) {
-          const uint32_t ip = h_order[bd.first + k];
-          for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
-            const uint32_t cam = p->obs_cam[hobs[t]];
-            cols[nc++] = (int)(6 * cam);
-            if (refine_intr) cols[nc++] = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
-          }
-        }
-        std::sort(cols, cols + nc);
-        nc = (int)(std::unique(cols, cols + nc) - cols);
-        if (nc > kBatchBlocks) { ok.store(0); return; }
-        bd.nblk = (uint32_t)nc;
-        std::copy(cols, cols + nc, h_cols.begin() + bi * kBatchBlocks);
-        unsigned char* lb = h_lblk.data() + bd.ent_first;
-        for (uint32_t k = 0; k < bd.count; ++k) {
-          const uint32_t ip = h_order[bd.first + k];
-          int g0 = -1, g1 = -1;
-          for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
-            const uint32_t cam = p->obs_cam[hobs[t]];
-            *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, (int)(6 * cam)) - cols);
-            if (refine_intr) {
-              const int gc = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
-              if (gc != g0 && gc != g1) { if (g0 < 0) g0 = gc; else g1 = gc; }
-            }
-          }
-          for (int gc : {g0, g1})
-            if (gc >= 0) *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, gc) - cols);
-        }
-      });
     }
-    if (ok.load()) {
+    // (3) per batch, in parallel: sorted distinct block columns and every entry's index into them
+    h_cols.assign(h_batches.size() * kBatchBlocks, 0);
+    parallel_for(threads, h_batches.size(), [&](size_t bi) {
+      BatchDesc& bd = h_batches[bi];
+      int cols[kBatchEntries * 2];
+      int nc = 0;
+      for (uint32_t k = 0; k < bd.count; ++k) {
+        const uint32_t ip = h_order[bd.first + k];
+        for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+          const uint32_t cam = p->obs_cam[hobs[t]];
+          cols[nc++] = (int)(6 * cam);
+          if (refine_intr) cols[nc++] = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
+        }
+      }
+      std::sort(cols, cols + nc);
+      nc = (int)(std::unique(cols, cols + nc) - cols);  // <= kBatchBlocks by construction of the batches
+      bd.nblk = (uint32_t)nc;
+      std::copy(cols, cols + nc, h_cols.begin() + bi * kBatchBlocks);
+      unsigned char* lb = h_lblk.data() + bd.ent_first;
+      for (uint32_t k = 0; k < bd.count; ++k) {
+        const uint32_t ip = h_order[bd.first + k];
+        int g0 = -1, g1 = -1;
+        for (uint32_t t = hofs[ip]; t < hofs[ip + 1]; ++t) {
+          const uint32_t cam = p->obs_cam[hobs[t]];
+          *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, (int)(6 * cam)) - cols);
+          if (refine_intr) {
+            const int gc = (int)(6 * p->n_cams + 6 * p->cam_intr[cam]);
+            if (gc != g0 && gc != g1) { if (g0 < 0) g0 = gc; else g1 = gc; }
+          }
+        }
+        for (int gc : {g0, g1})
+          if (gc >= 0) *lb++ = (unsigned char)(std::lower_bound(cols, cols + nc, gc) - cols);
+      }
+    });
+    // (4) the rest: listed for the CTA-per-point kernel, longest tracks first
+    for (uint32_t i = 0; i < n_pts; ++i)
+      if (!elig[i] && hofs[i + 1] > hofs[i]) {
+        h_long.push_back(i);
+        plan->long_cap = std::max(plan->long_cap, hofs[i + 1] - hofs[i]);
+      }
+    std::stable_sort(h_long.begin(), h_long.end(), [&](uint32_t a, uint32_t b) { return hofs[a + 1] - hofs[a] > hofs[b + 1] - hofs[b]; });
+    if (!h_batches.empty()) {
       uint32_t *d_order, *d_ent_start;
       BatchDesc* d_batches;
       int* d_cols;
@@ -973,6 +994,13 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_lblk, h_lblk.data(), h_lblk.size(), cudaMemcpyHostToDevice, w.stream));
       plan->t = BatchTables{d_batches, d_order, d_ent_start, d_cols, d_lblk};
       plan->n_batches = (uint32_t)h_batches.size();
+    }
+    if (!h_long.empty()) {
+      uint32_t* d_long;
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_long, h_long.size()));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_long, h_long.data(), h_long.size() * 4, cudaMemcpyHostToDevice, w.stream));
+      plan->d_long = d_long;
+      plan->n_long = (uint32_t)h_long.size();
     }
   }
   R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // hofs / hobs and the plan vectors are locals
@@ -1038,19 +1066,28 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   uint32_t max_obs = 1;
   BatchPlan plan;
   static const bool per_point_schur = getenv("R3D_BA_SCHUR") && std::string(getenv("R3D_BA_SCHUR")) == "point";
-  int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs,
-                         per_point_schur ? nullptr : &plan);
+  plan.want_batched = !per_point_schur;
+  int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs, &plan);
   if (rc) return rc;
   if (plan.n_batches)
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur_batched, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)r3d::ba::kBatchSmemBytes));
-  const int obs_cap = (int)std::max<uint32_t>(max_obs, 1u);
+  // scratch of the CTA-per-point kernel: one slice of `long_cap` observations per CTA of its (persistent) grid
+  uint32_t long_grid = 0;
+  double* d_long_scr = nullptr;
+  int* d_long_cols = nullptr;
+  if (plan.n_long) {
+    long_grid = std::min<uint32_t>(plan.n_long, (uint32_t)w.sm_count * 8u);
+    const size_t per_cta = (size_t)plan.long_cap * (r3d::ba::kObsDoubles + 36);
+    // keep the scratch within ~1 GB whatever the track length
+    while (long_grid > 1 && per_cta * long_grid * sizeof(double) > ((size_t)1 << 30)) long_grid /= 2;
+    R3D_CUDA_TRY(ctx, mem.alloc(&d_long_scr, per_cta * long_grid));
+    R3D_CUDA_TRY(ctx, mem.alloc(&d_long_cols, (size_t)plan.long_cap * 3 * long_grid));
+  }
   sum->seconds_setup = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
   const size_t nparam = (size_t)d.nB + 3 * (size_t)d.n_pts;
   const int grid_obs = w.sm_count * 8;
   const int nB = (int)d.nB;
-  const size_t schur_smem = (size_t)r3d::ba::kSchurWarps * obs_cap * (r3d::ba::kObsDoubles + 36) * sizeof(double);
-  R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem));
   // Cholesky scratch: L (with the forward-substituted rhs as row nB) and the inverses of its diagonal blocks
   double *d_Lm = nullptr, *d_Linv = nullptr;
   const int chol_blocks = (nB + r3d::ba::NB - 1) / r3d::ba::NB;
@@ -1121,8 +1158,9 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, 5 * sizeof(double), w.stream));
     if (plan.n_batches)
       r3d::ba::k_ba_schur_batched<<<plan.n_batches, 256, r3d::ba::kBatchSmemBytes, w.stream>>>(d, plan.t, inv_radius);
-    else
-      r3d::ba::k_ba_schur<<<(d.n_pts + r3d::ba::kSchurWarps - 1) / r3d::ba::kSchurWarps, r3d::ba::kSchurWarps * 32, schur_smem, w.stream>>>(d, inv_radius, obs_cap);
+    if (plan.n_long)  // long tracks and whatever else the batched kernel cannot take
+      r3d::ba::k_ba_schur_cta<<<long_grid, r3d::ba::kCtaThreads, 0, w.stream>>>(d, plan.d_long, plan.n_long, inv_radius, d_long_scr,
+                                                                             d_long_cols, plan.long_cap);
     // the exchange step: partial reduced camera systems of the point partitions -> their sum (NVLink)
     if ((rc = comm_allreduce(ctx, w.stream, d.S, (size_t)nB * nB + nB, kCommSum))) return rc;
     {

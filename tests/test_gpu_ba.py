@@ -58,3 +58,61 @@ def test_ba_two_intrinsic_groups(gpu_ctx, oracle):
     prob["intrinsics"][1, 0] *= 1.01
     prob["cam_intr"] = (np.arange(10) % 2).astype(np.uint32)
     _compare(gpu_ctx, oracle, prob, iters=15)
+
+
+def _long_track_problem(n_cams, n_pts, n_long, seed):
+    """Every camera on the ring sees the first `n_long` points (tracks of n_cams observations); the others keep 4."""
+    prob = synth.make_ba_problem(n_cams=n_cams, n_pts=n_pts, obs_per_pt=4, seed=seed, outlier_frac=0.01)
+    rng = np.random.default_rng(seed)
+    truth = prob["truth"]
+    f, w, h = truth["intrinsics"][0][0], 1920, 1080
+    oc, op, oxy = [prob["obs_cam"]], [prob["obs_pt"]], [prob["obs_xy"]]
+    P = len(prob["points"])
+    for ip in range(min(n_long, P)):
+        have = set(prob["obs_cam"][prob["obs_pt"] == ip].tolist())
+        X = truth["points"][ip]
+        for c in range(n_cams):
+            if c in have:
+                continue
+            aa, t = truth["poses"][c, :3], truth["poses"][c, 3:]
+            R = synth._rodrigues(aa)
+            pc = R @ X + t
+            if pc[2] <= 0.1:
+                continue
+            uv = np.array([f * pc[0] / pc[2] + w / 2, f * pc[1] / pc[2] + h / 2]) + 0.5 * rng.standard_normal(2)
+            oc.append(np.array([c], np.uint32)); op.append(np.array([ip], np.uint32)); oxy.append(uv[None, :])
+    prob["obs_cam"] = np.concatenate(oc).astype(np.uint32)
+    prob["obs_pt"] = np.concatenate(op).astype(np.uint32)
+    prob["obs_xy"] = np.concatenate(oxy).astype(np.float64)
+    return prob
+
+
+def test_ba_long_tracks_equal_oracle(gpu_ctx, oracle):
+    """Tracks of 200 observations (a point seen from every view of a turntable set): round 1 refused anything beyond 64.
+    The long points go through the CTA-per-point kernel, the rest through the batched kernel, in the same solve."""
+    prob = _long_track_problem(n_cams=200, n_pts=600, n_long=12, seed=21)
+    per_pt = np.bincount(prob["obs_pt"])
+    assert per_pt.max() >= 150 and np.sum(per_pt > 64) >= 10
+    _compare(gpu_ctx, oracle, prob, iters=8)
+
+
+def test_ba_medium_tracks_33_to_64(gpu_ctx, oracle):
+    prob = _long_track_problem(n_cams=48, n_pts=400, n_long=40, seed=22)
+    per_pt = np.bincount(prob["obs_pt"])
+    assert 33 <= per_pt.max() <= 64
+    _compare(gpu_ctx, oracle, prob, iters=8)
+
+
+def test_ba_camera_sees_point_twice_and_three_groups(gpu_ctx, oracle):
+    """Structures the batched kernel does not take: a duplicated observation and a point seen through 3 intrinsic groups."""
+    prob = synth.make_ba_problem(n_cams=9, n_pts=300, obs_per_pt=4, seed=23, outlier_frac=0.0)
+    prob["intrinsics"] = np.repeat(prob["intrinsics"], 3, 0).copy()
+    prob["intrinsics"][1, 0] *= 1.005
+    prob["intrinsics"][2, 0] *= 0.995
+    prob["cam_intr"] = (np.arange(9) % 3).astype(np.uint32)
+    # duplicate the first observation of 20 points (same camera, slightly different measurement)
+    dup = np.arange(0, 80, 4)
+    prob["obs_cam"] = np.concatenate([prob["obs_cam"], prob["obs_cam"][dup]]).astype(np.uint32)
+    prob["obs_pt"] = np.concatenate([prob["obs_pt"], prob["obs_pt"][dup]]).astype(np.uint32)
+    prob["obs_xy"] = np.concatenate([prob["obs_xy"], prob["obs_xy"][dup] + 0.3])
+    _compare(gpu_ctx, oracle, prob, iters=10)
