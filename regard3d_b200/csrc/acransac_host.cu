@@ -113,8 +113,7 @@ std::vector<uint32_t> st_src(const std::vector<PairState>& st) {
 int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const r3d_matches* put, const std::vector<uint32_t>& src,
               const std::vector<AcPair>& hpairs, const AcPair* d_pairs, const double2* d_x1, const double2* d_x2,
               const uint2* d_match, const float* d_logc_n, const float* d_logc_k, uint32_t pt_total, uint32_t sizeSample,
-              double t_begin, std::vector<std::vector<r3d_indmatch>>& result) {
-  r3d_filter_timing& T = ctx->filter_timing;
+              double t_begin, r3d_filter_timing& T, std::vector<std::vector<r3d_indmatch>>& result) {
   const uint32_t n = (uint32_t)hpairs.size();
   constexpr int kClasses = 6;  // caps 1024, 2048, 4096, 8192, 16384, huge
   std::vector<uint32_t> order[kClasses];
@@ -252,14 +251,13 @@ int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const
 
 }  // namespace
 
+// pairs [p0, p1) of the putative map on worker w; result (sized by the caller to the whole map) is indexed by pair
 int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precision_px, uint32_t max_iter, const r3d_matches* put,
-                   const r3d_view_info* views, uint32_t n_views, std::vector<std::vector<r3d_indmatch>>& result) {
+                   const r3d_view_info* views, uint32_t n_views, uint64_t p0, uint64_t p1, r3d_filter_timing& T,
+                   std::vector<std::vector<r3d_indmatch>>& result) {
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
-  r3d_filter_timing& T = ctx->filter_timing;
   T = r3d_filter_timing{};
   const double t_begin = now_ms();
-  const uint64_t P = put->pairs.size() / 2;
-  result.assign(P, {});
   const uint32_t sizeSample = ac_min_samples(model), MAX_MODELS = ac_max_models(model);  // Kernel::MINIMUM_SAMPLES / MAX_MODELS
 
   // ---- per pair set-up (kernel adaptor of SURVEY.md A.5: normalisation, logalpha0, tables) ----
@@ -271,7 +269,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   uint32_t maxM = 0;
   {
     uint64_t pt_total = 0, tbl_total = 0;
-    for (uint64_t p = 0; p < P; ++p) {
+    for (uint64_t p = p0; p < p1; ++p) {
       const uint32_t I = put->pairs[2 * p], J = put->pairs[2 * p + 1];
       const uint32_t M = (uint32_t)put->per[p].size();
       if (M <= sizeSample) continue;  // ACRANSAC returns at once: nData <= MINIMUM_SAMPLES
@@ -414,7 +412,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
 
   if (use_fused)
     return run_fused(ctx, w, model, max_iter, put, st_src(st), hpairs, d_pairs.p, d_x1.p, d_x2.p, d_match.p, d_logc_n.p, d_logc_k.p,
-                     (uint32_t)hmatch.size(), sizeSample, t_begin, result);
+                     (uint32_t)hmatch.size(), sizeSample, t_begin, T, result);
 
   cudaEvent_t ev[3];
   for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
@@ -607,10 +605,48 @@ extern "C" int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, ui
   *out = nullptr;
   if (model != R3D_MODEL_F && model != R3D_MODEL_H && model != R3D_MODEL_E)
     return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: unknown model");
-  std::vector<std::vector<r3d_indmatch>> res;
   const int internal = model == R3D_MODEL_F ? 0 : (model == R3D_MODEL_H ? 1 : 2);
-  int rc = filter_pairs_model(ctx, ctx->workers[0], internal, precision_px, max_iter, putative, views, n_views, res);
-  if (rc) return rc;
+  const uint64_t P_all = putative->pairs.size() / 2;
+  std::vector<std::vector<r3d_indmatch>> res(P_all);
+  // image pairs are independent: cut the map into contiguous ranges of equal putative-match counts, one per device
+  // of the context (every device holds all positions), no collective -- the same rule as r3d_match_pairs
+  const size_t nw = ctx->workers.size();
+  std::vector<uint64_t> cut(nw + 1, 0);
+  {
+    std::vector<double> cost(P_all + 1, 0.0);
+    for (uint64_t p = 0; p < P_all; ++p) cost[p + 1] = cost[p] + (double)putative->per[p].size() + 1.0;
+    for (size_t k = 1; k < nw; ++k)
+      cut[k] = std::min<uint64_t>(P_all, (uint64_t)(std::lower_bound(cost.begin(), cost.end(), cost[P_all] * (double)k / (double)nw) - cost.begin()));
+    cut[nw] = P_all;
+  }
+  std::vector<int> rcs(nw, R3D_OK);
+  std::vector<r3d_filter_timing> tms(nw);
+  if (nw == 1) {
+    rcs[0] = filter_pairs_model(ctx, ctx->workers[0], internal, precision_px, max_iter, putative, views, n_views, 0, P_all, tms[0], res);
+  } else {
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < nw; ++k)
+      th.emplace_back([&, k]() {
+        rcs[k] = filter_pairs_model(ctx, ctx->workers[k], internal, precision_px, max_iter, putative, views, n_views, cut[k], cut[k + 1],
+                                    tms[k], res);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int rc : rcs)
+    if (rc) return rc;
+  {
+    r3d_filter_timing sum{};
+    for (const r3d_filter_timing& t : tms) {
+      sum.ms_solve = std::max(sum.ms_solve, t.ms_solve);
+      sum.ms_score = std::max(sum.ms_score, t.ms_score);
+      sum.ms_device_total = std::max(sum.ms_device_total, t.ms_device_total);
+      sum.ms_host = std::max(sum.ms_host, t.ms_host);
+      sum.kernel_launches += t.kernel_launches;
+      sum.hypotheses += t.hypotheses;
+      sum.rounds = std::max(sum.rounds, t.rounds);
+    }
+    ctx->filter_timing = sum;
+  }
   r3d_matches* m = new r3d_matches();
   const uint64_t P = putative->pairs.size() / 2;
   for (uint64_t p = 0; p < P; ++p) {

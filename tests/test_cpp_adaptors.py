@@ -5,6 +5,8 @@ import os
 import subprocess
 import textwrap
 
+import pytest
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 SRC = textwrap.dedent(r'''
@@ -41,7 +43,7 @@ SRC = textwrap.dedent(r'''
 ''')
 
 
-def test_array_matcher_adaptor_compiles_links_and_fails_loudly_without_gpu(r3dlib, tmp_path):
+def _build_and_run(tmp_path):
     src = tmp_path / "adaptor.cpp"
     src.write_text(SRC)
     exe = tmp_path / "adaptor"
@@ -52,8 +54,19 @@ def test_array_matcher_adaptor_compiles_links_and_fails_loudly_without_gpu(r3dli
     assert p.returncode == 0, p.stderr[-3000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-2000:]
+    return r.stdout
+
+
+def test_array_matcher_adaptor_compiles_links_and_fails_loudly_without_gpu(r3dlib, tmp_path):
+    out = _build_and_run(tmp_path)
     import torch
     if torch.cuda.is_available():
-        assert "built=1 searched=1 n=4" in r.stdout
+        assert "built=1 searched=1 n=4" in out
     else:
-        assert "built=0 searched=0" in r.stdout and "no CPU fallback" in r.stdout
+        assert "built=0 searched=0" in out and "no CPU fallback" in out
+
+
+@pytest.mark.gpu
+def test_array_matcher_adaptor_runs_on_the_gpu(r3dlib, tmp_path):
+    """The adaptor's GPU branch (Build -> r3d_upload_regions, SearchNeighbours -> r3d_search_neighbours) on hardware."""
+    assert "built=1 searched=1 n=4" in _build_and_run(tmp_path)
