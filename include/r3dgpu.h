@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define R3D_ABI_VERSION 2
+#define R3D_ABI_VERSION 3
 
 typedef enum {
   R3D_OK = 0,
@@ -115,6 +115,71 @@ void r3d_free_matches(r3d_matches* m);
  * SURVEY.md Appendix B.3). */
 int r3d_save_matches_txt(const r3d_matches* m, const char* path);
 int r3d_load_matches_txt(const char* path, r3d_matches** out);
+
+/* matching::Save / matching::Load as the reference calls them: the extension picks the format -- ".txt" (above) or
+ * ".bin" = cereal PortableBinary of std::map<Pair, std::vector<IndMatch>> (layout restated in
+ * regard3d_b200/csrc/sfm_data_io.cpp). */
+int r3d_save_matches_bin(const r3d_matches* m, const char* path);
+int r3d_load_matches_bin(const char* path, r3d_matches** out);
+int r3d_save_matches(const r3d_matches* m, const char* path);
+int r3d_load_matches(const char* path, r3d_matches** out);
+
+/* ---- sfm_data.bin ------------------------------------------------------------------------
+ * openMVG::sfm::SfM_Data as the reference stores it: cereal PortableBinary "sfm_data.bin", written by
+ * R3DProject::writeSfmData (src/R3DProject.cpp:1118-1306: views / view priors + intrinsics), read by
+ * R3DComputeMatches::computeMatches (src/R3DComputeMatches.cpp:1755) and R3DTriangulationThread
+ * (src/threads/R3DTriangulationThread.cpp:403), written back with poses + structure (:453-455).  Opaque handle +
+ * plain-struct accessors; maps are walked in key order (k-th element). */
+typedef struct r3d_sfm_data r3d_sfm_data;
+/* openMVG::sfm::ESfM_Data */
+#define R3D_SFM_VIEWS 1u
+#define R3D_SFM_EXTRINSICS 2u
+#define R3D_SFM_INTRINSICS 4u
+#define R3D_SFM_STRUCTURE 8u
+#define R3D_SFM_CONTROL_POINTS 16u
+#define R3D_SFM_ALL 31u
+/* openMVG::cameras::EINTRINSIC (the `cameraModel` argument of computeMatches, src/R3DProject.cpp:1167-1191) */
+#define R3D_CAM_PINHOLE 1
+#define R3D_CAM_PINHOLE_RADIAL1 2
+#define R3D_CAM_PINHOLE_RADIAL3 3
+#define R3D_CAM_PINHOLE_BROWN 4
+#define R3D_CAM_PINHOLE_FISHEYE 5
+typedef struct {
+  uint32_t id_view, id_intrinsic, id_pose, width, height;
+  const char* local_path;  /* folder part of View::s_Img_path */
+  const char* filename;    /* file part */
+  int has_prior;           /* openMVG::sfm::ViewPriors with b_use_pose_center_ (GPS; src/R3DProject.cpp:1194-1220) */
+  double center_weight[3], pose_center[3];
+} r3d_sfm_view;
+typedef struct {
+  uint32_t id;
+  int model;               /* R3D_CAM_* */
+  uint32_t width, height;
+  double focal, ppx, ppy;
+  double disto[5];         /* K1: k1 | K3: k1 k2 k3 | Brown T2: k1 k2 k3 t1 t2 | fisheye: k1 k2 k3 k4 */
+} r3d_sfm_intrinsic;
+typedef struct { uint32_t id; double rotation[9]; double center[3]; } r3d_sfm_pose;  /* geometry::Pose3: R row-major, C */
+typedef struct { uint32_t id_view, id_feat; double x[2]; } r3d_sfm_observation;
+int r3d_sfm_data_create(r3d_sfm_data** out);
+void r3d_sfm_data_free(r3d_sfm_data* sd);
+int r3d_sfm_data_load(const char* path, r3d_sfm_data** out);                       /* Load(sfm_data, path, ALL) */
+int r3d_sfm_data_save(const r3d_sfm_data* sd, const char* path, uint32_t parts);   /* Save(sfm_data, path, parts) */
+const char* r3d_sfm_root_path(const r3d_sfm_data* sd);
+int r3d_sfm_set_root_path(r3d_sfm_data* sd, const char* root_path);
+uint32_t r3d_sfm_num_views(const r3d_sfm_data* sd);
+uint32_t r3d_sfm_num_intrinsics(const r3d_sfm_data* sd);
+uint32_t r3d_sfm_num_poses(const r3d_sfm_data* sd);
+uint32_t r3d_sfm_num_landmarks(const r3d_sfm_data* sd, int control_points);
+int r3d_sfm_add_view(r3d_sfm_data* sd, const r3d_sfm_view* v);                     /* strings are copied */
+int r3d_sfm_get_view(const r3d_sfm_data* sd, uint32_t k, r3d_sfm_view* out);       /* strings owned by sd */
+int r3d_sfm_add_intrinsic(r3d_sfm_data* sd, const r3d_sfm_intrinsic* in);
+int r3d_sfm_get_intrinsic(const r3d_sfm_data* sd, uint32_t k, r3d_sfm_intrinsic* out);
+int r3d_sfm_add_pose(r3d_sfm_data* sd, const r3d_sfm_pose* p);
+int r3d_sfm_get_pose(const r3d_sfm_data* sd, uint32_t k, r3d_sfm_pose* out);
+int r3d_sfm_add_landmark(r3d_sfm_data* sd, int control_point, uint32_t id, const double X[3],
+                         const r3d_sfm_observation* obs, uint32_t n_obs);
+int r3d_sfm_get_landmark(const r3d_sfm_data* sd, int control_point, uint32_t k, uint32_t* id, double X[3],
+                         r3d_sfm_observation* obs, uint32_t obs_cap, uint32_t* n_obs);
 
 /* ---- geometric filtering ------------------------------------------------------------------- */
 typedef enum { R3D_MODEL_F = 0, R3D_MODEL_E = 1, R3D_MODEL_H = 2 } r3d_model;

@@ -26,6 +26,11 @@ EXPORTS = [
     "r3d_get_filter_timing", "r3d_debug_candidate_keys", "r3d_debug_ba_jacobian",
     "r3d_comm_unique_id", "r3d_comm_init", "r3d_comm_destroy", "r3d_comm_world", "r3d_debug_post_process",
     "r3d_debug_post_process_many", "r3d_debug_post_process_ranked", "r3d_matches_export_csr", "r3d_debug_rng_selftest", "r3d_liop_describe", "r3d_debug_liop_process",
+    "r3d_save_matches_bin", "r3d_load_matches_bin", "r3d_save_matches", "r3d_load_matches", "r3d_sfm_data_create",
+    "r3d_sfm_data_free", "r3d_sfm_data_load", "r3d_sfm_data_save", "r3d_sfm_root_path", "r3d_sfm_set_root_path",
+    "r3d_sfm_num_views", "r3d_sfm_num_intrinsics", "r3d_sfm_num_poses", "r3d_sfm_num_landmarks", "r3d_sfm_add_view",
+    "r3d_sfm_get_view", "r3d_sfm_add_intrinsic", "r3d_sfm_get_intrinsic", "r3d_sfm_add_pose", "r3d_sfm_get_pose",
+    "r3d_sfm_add_landmark", "r3d_sfm_get_landmark",
 ]
 
 
@@ -128,6 +133,26 @@ def lib():
         L.r3d_matches_total.argtypes = [C.c_void_p]
         L.r3d_free_matches.argtypes = [C.c_void_p]
         L.r3d_destroy.argtypes = [C.c_void_p]
+        L.r3d_sfm_data_free.argtypes = [C.c_void_p]
+        L.r3d_sfm_root_path.restype = C.c_char_p
+        L.r3d_sfm_root_path.argtypes = [C.c_void_p]
+        for fn in (L.r3d_sfm_num_views, L.r3d_sfm_num_intrinsics, L.r3d_sfm_num_poses):
+            fn.restype = C.c_uint32
+            fn.argtypes = [C.c_void_p]
+        L.r3d_sfm_num_landmarks.restype = C.c_uint32
+        L.r3d_sfm_num_landmarks.argtypes = [C.c_void_p, C.c_int]
+        L.r3d_sfm_data_save.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+        L.r3d_sfm_set_root_path.argtypes = [C.c_void_p, C.c_char_p]
+        L.r3d_sfm_add_view.argtypes = [C.c_void_p, C.c_void_p]
+        L.r3d_sfm_get_view.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_sfm_add_intrinsic.argtypes = [C.c_void_p, C.c_void_p]
+        L.r3d_sfm_get_intrinsic.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_sfm_add_pose.argtypes = [C.c_void_p, C.c_void_p]
+        L.r3d_sfm_get_pose.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_sfm_add_landmark.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.r3d_sfm_get_landmark.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_save_matches.argtypes = [C.c_void_p, C.c_char_p]
+        L.r3d_save_matches_bin.argtypes = [C.c_void_p, C.c_char_p]
         L.r3d_comm_world.argtypes = [C.c_void_p]
         L.r3d_debug_post_process.restype = C.c_int64
         L.r3d_debug_post_process_ranked.restype = C.c_int64
@@ -212,6 +237,20 @@ class Matches:
             raise R3DError(rc, "r3d_matches_export_csr")
         return pairs_out, ofs_out, matches_out
 
+    def save(self, path):
+        """matching::Save: '.txt' or '.bin' (cereal portable binary) by extension."""
+        rc = lib().r3d_save_matches(self.handle, path.encode())
+        if rc:
+            raise R3DError(rc, "r3d_save_matches(%s)" % path)
+
+    @staticmethod
+    def load(path):
+        h = C.c_void_p()
+        rc = lib().r3d_load_matches(path.encode(), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_load_matches(%s)" % path)
+        return Matches(h)
+
     def save_txt(self, path):
         rc = lib().r3d_save_matches_txt(self.handle, path.encode())
         if rc:
@@ -235,6 +274,143 @@ class Matches:
         if rc:
             raise R3DError(rc, "r3d_matches_from_csr")
         return Matches(h)
+
+
+class SfmView(C.Structure):
+    _fields_ = [("id_view", C.c_uint32), ("id_intrinsic", C.c_uint32), ("id_pose", C.c_uint32), ("width", C.c_uint32),
+                ("height", C.c_uint32), ("local_path", C.c_char_p), ("filename", C.c_char_p), ("has_prior", C.c_int),
+                ("center_weight", C.c_double * 3), ("pose_center", C.c_double * 3)]
+
+
+class SfmIntrinsic(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("model", C.c_int), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("focal", C.c_double), ("ppx", C.c_double), ("ppy", C.c_double), ("disto", C.c_double * 5)]
+
+
+class SfmPose(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("rotation", C.c_double * 9), ("center", C.c_double * 3)]
+
+
+class SfmObservation(C.Structure):
+    _fields_ = [("id_view", C.c_uint32), ("id_feat", C.c_uint32), ("x", C.c_double * 2)]
+
+
+SFM_VIEWS, SFM_EXTRINSICS, SFM_INTRINSICS, SFM_STRUCTURE, SFM_CONTROL_POINTS, SFM_ALL = 1, 2, 4, 8, 16, 31
+CAM_PINHOLE, CAM_RADIAL1, CAM_RADIAL3, CAM_BROWN, CAM_FISHEYE = 1, 2, 3, 4, 5
+
+
+class SfmData:
+    """openMVG::sfm::SfM_Data handle (sfm_data.bin: cereal portable binary, no OpenMVG needed)."""
+
+    def __init__(self, handle=None):
+        if handle is None:
+            handle = C.c_void_p()
+            rc = lib().r3d_sfm_data_create(C.byref(handle))
+            if rc:
+                raise R3DError(rc, "r3d_sfm_data_create")
+        self.h = handle
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().r3d_sfm_data_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def load(path):
+        h = C.c_void_p()
+        rc = lib().r3d_sfm_data_load(path.encode(), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_data_load(%s)" % path)
+        return SfmData(h)
+
+    def save(self, path, parts=SFM_ALL):
+        rc = lib().r3d_sfm_data_save(self.h, path.encode(), C.c_uint32(parts))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_data_save(%s)" % path)
+
+    @property
+    def root_path(self):
+        return lib().r3d_sfm_root_path(self.h).decode()
+
+    @root_path.setter
+    def root_path(self, p):
+        lib().r3d_sfm_set_root_path(self.h, p.encode())
+
+    def add_view(self, id_view, filename, width, height, id_intrinsic=None, id_pose=None, local_path="", prior_center=None,
+                 prior_weight=(1.0, 1.0, 1.0)):
+        v = SfmView(id_view, id_view if id_intrinsic is None else id_intrinsic, id_view if id_pose is None else id_pose,
+                    width, height, local_path.encode(), filename.encode(), 0 if prior_center is None else 1,
+                    (C.c_double * 3)(*prior_weight), (C.c_double * 3)(*(prior_center or (0.0, 0.0, 0.0))))
+        rc = lib().r3d_sfm_add_view(self.h, C.byref(v))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_add_view")
+
+    def add_intrinsic(self, id, model, width, height, focal, ppx, ppy, disto=()):
+        d = list(disto) + [0.0] * (5 - len(disto))
+        s = SfmIntrinsic(id, model, width, height, focal, ppx, ppy, (C.c_double * 5)(*d))
+        rc = lib().r3d_sfm_add_intrinsic(self.h, C.byref(s))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_add_intrinsic")
+
+    def add_pose(self, id, R, center):
+        s = SfmPose(id, (C.c_double * 9)(*np.asarray(R, float).reshape(9)), (C.c_double * 3)(*np.asarray(center, float)))
+        rc = lib().r3d_sfm_add_pose(self.h, C.byref(s))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_add_pose")
+
+    def add_landmark(self, id, X, obs, control_point=False):
+        """obs: list of (id_view, id_feat, x, y)."""
+        arr = (SfmObservation * max(len(obs), 1))()
+        for k, (v, f, x, y) in enumerate(obs):
+            arr[k] = SfmObservation(v, f, (C.c_double * 2)(x, y))
+        rc = lib().r3d_sfm_add_landmark(self.h, C.c_int(int(control_point)), C.c_uint32(id), (C.c_double * 3)(*X), arr,
+                                        C.c_uint32(len(obs)))
+        if rc:
+            raise R3DError(rc, "r3d_sfm_add_landmark")
+
+    def views(self):
+        out = []
+        for k in range(lib().r3d_sfm_num_views(self.h)):
+            v = SfmView()
+            lib().r3d_sfm_get_view(self.h, C.c_uint32(k), C.byref(v))
+            out.append(dict(id_view=v.id_view, id_intrinsic=v.id_intrinsic, id_pose=v.id_pose, width=v.width, height=v.height,
+                            local_path=v.local_path.decode(), filename=v.filename.decode(), has_prior=bool(v.has_prior),
+                            center_weight=list(v.center_weight), pose_center=list(v.pose_center)))
+        return out
+
+    def intrinsics(self):
+        out = []
+        for k in range(lib().r3d_sfm_num_intrinsics(self.h)):
+            s = SfmIntrinsic()
+            lib().r3d_sfm_get_intrinsic(self.h, C.c_uint32(k), C.byref(s))
+            out.append(dict(id=s.id, model=s.model, width=s.width, height=s.height, focal=s.focal, ppx=s.ppx, ppy=s.ppy,
+                            disto=list(s.disto)))
+        return out
+
+    def poses(self):
+        out = []
+        for k in range(lib().r3d_sfm_num_poses(self.h)):
+            s = SfmPose()
+            lib().r3d_sfm_get_pose(self.h, C.c_uint32(k), C.byref(s))
+            out.append(dict(id=s.id, R=np.array(list(s.rotation)).reshape(3, 3), center=np.array(list(s.center))))
+        return out
+
+    def landmarks(self, control_points=False):
+        out = []
+        cp = C.c_int(int(control_points))
+        for k in range(lib().r3d_sfm_num_landmarks(self.h, cp)):
+            n = C.c_uint32()
+            lid = C.c_uint32()
+            X = (C.c_double * 3)()
+            lib().r3d_sfm_get_landmark(self.h, cp, C.c_uint32(k), C.byref(lid), X, None, C.c_uint32(0), C.byref(n))
+            arr = (SfmObservation * max(n.value, 1))()
+            lib().r3d_sfm_get_landmark(self.h, cp, C.c_uint32(k), None, None, arr, n, None)
+            out.append(dict(id=lid.value, X=list(X), obs=[(arr[q].id_view, arr[q].id_feat, arr[q].x[0], arr[q].x[1])
+                                                          for q in range(n.value)]))
+        return out
 
 
 def debug_ba_jacobian(intr, pose, X, obs):

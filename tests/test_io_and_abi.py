@@ -19,7 +19,7 @@ def test_header_symbols_are_exported(r3dlib):
     missing = [n for n in sorted(names) if not hasattr(lib, n)]
     assert not missing, missing
     assert set(r3dlib.EXPORTS) <= names
-    assert lib.r3d_abi_version() == 2
+    assert lib.r3d_abi_version() == 3
 
 
 def test_create_fails_loudly_without_gpu(r3dlib):
