@@ -204,8 +204,9 @@ int r3d_filter_pairs(r3d_ctx* ctx, int model, double precision_px, uint32_t max_
 
 /* ---- bundle adjustment --------------------------------------------------------------------- */
 /* Replaces openMVG::sfm::Bundle_Adjustment_Ceres::Adjust as driven by the SfM engines' Process()
- * (src/threads/R3DTriangulationThread.cpp:441, :512, :250).  Pinhole radial-K3 cameras
- * (model chosen at :398, built at src/R3DProject.cpp:1177-1180). */
+ * (src/threads/R3DTriangulationThread.cpp:441, :512, :250).  Default camera model: pinhole radial-K3 (chosen at :398,
+ * built at src/R3DProject.cpp:1177-1180); the four other models the reference can store are selected per intrinsic
+ * group with intr_model.  Tracks may have any length. */
 typedef struct {
   uint32_t n_cams, n_pts, n_intr;
   uint64_t n_obs;
@@ -216,6 +217,17 @@ typedef struct {
   const uint32_t* obs_pt;    /* n_obs */
   const uint32_t* cam_intr;  /* n_cams: intrinsic group of each camera */
   const double* obs_xy;      /* n_obs x 2 */
+  /* --- ABI 3 (all optional: NULL / 0 = round-1 behaviour) --- */
+  const uint8_t* intr_model; /* n_intr: camera model of each group, R3D_CAM_* (src/R3DProject.cpp:1167-1191); NULL = radial K3.
+                              * intrinsics[g] = f, ppx, ppy, then the model's first three distortion coefficients
+                              * (pinhole: none, K1: k1, K3 / Brown: k1 k2 k3, fisheye: k1 k2 k3); slots a model does not
+                              * own are ignored and never change */
+  const double* intrinsics_ext; /* n_intr x 2 or NULL: Brown T2: t1 t2, fisheye: k4 -- read, HELD FIXED by the solve
+                              * (intrinsic blocks of the reduced camera system are 6 wide) */
+  uint32_t n_priors;         /* pose-centre priors = openMVG ViewPriors with b_use_pose_center_ (GPS) */
+  const uint32_t* prior_cam; /* n_priors: camera (pose) index */
+  const double* prior_center;/* n_priors x 3 */
+  const double* prior_weight;/* n_priors x 3 (ViewPriors::center_weight_) */
 } r3d_ba_problem;
 
 typedef struct {
@@ -226,6 +238,8 @@ typedef struct {
   double gradient_tolerance; /* 1e-10 */
   double parameter_tolerance;/* 1e-8 */
   double initial_radius;     /* 1e4 */
+  double prior_huber_a;      /* ABI 3: HuberLoss(a) of the pose-centre prior blocks (OpenMVG: Square(pose_center_robust_
+                              * fitting_error)); <= 0: trivial loss */
 } r3d_ba_options;
 
 typedef struct {
@@ -344,6 +358,11 @@ int r3d_debug_candidate_keys(r3d_ctx* ctx, uint32_t view_db, uint32_t view_query
  * 0..5, pose 6..11, point 12..14) of one observation, as the BA kernels evaluate them. */
 int r3d_debug_ba_jacobian(const double* intr, const double* pose, const double* X, const double* obs,
                           double* r, double* J);
+/* the same for any of the five camera models (ext: the model's coefficients 4, 5 or NULL) */
+int r3d_debug_ba_jacobian_model(int model, const double* intr, const double* ext, const double* pose, const double* X,
+                                const double* obs, double* r, double* J);
+/* pose-centre prior block: r[3] = weight .* (C(pose) - center), J[3 x 6] = d r / d (angle-axis, t) */
+int r3d_debug_ba_prior(const double* pose, const double* center, const double* weight, double* r, double* J);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,11 @@ typedef struct {
   const uint32_t* obs_cam; const uint32_t* obs_pt; /* n_obs */
   const uint32_t* cam_intr;                         /* n_cams: intrinsic group of each camera */
   const double* obs_xy;                             /* n_obs x 2 */
+  /* optional (NULL / 0 = radial K3, no priors) */
+  const uint8_t* intr_model;     /* n_intr: openMVG EINTRINSIC 1..5 */
+  const double* intrinsics_ext;  /* n_intr x 2: Brown t1 t2 / fisheye k4 (held fixed) */
+  uint32_t n_priors;             /* pose-centre priors (ViewPriors) */
+  const uint32_t* prior_cam; const double* prior_center; const double* prior_weight; /* n_priors [x 3] */
 } orc_ba_problem;
 
 typedef struct {
@@ -119,6 +124,7 @@ typedef struct {
   double function_tolerance, gradient_tolerance, parameter_tolerance;
   double initial_radius;       /* 1e4 */
   int n_threads;
+  double prior_huber_a;        /* HuberLoss(a) of the pose-centre prior blocks; <= 0 trivial */
 } orc_ba_options;
 
 typedef struct {
@@ -133,6 +139,10 @@ int orc_bundle_adjust(orc_ba_problem* p, const orc_ba_options* o, orc_ba_summary
 /* residual (2) and Jacobian (2 x 15: intrinsics 0..5, pose 6..11, point 12..14) of one observation
  * by forward-mode autodiff -- test hook that pins the GPU's analytic derivatives. */
 void orc_ba_jacobian(const double* intr, const double* pose, const double* X, const double* obs, double* r, double* J);
+void orc_ba_jacobian_model(int model, const double* intr, const double* ext, const double* pose, const double* X,
+                           const double* obs, double* r, double* J);
+/* pose-centre prior block by autodiff: r[3], J[3 x 6] */
+void orc_ba_prior(const double* pose, const double* center, const double* weight, double* r, double* J);
 /* OpenMVGHelper::calculateResiduals twin: |residual| per coordinate, 2 per obs. */
 void orc_ba_residuals(const orc_ba_problem* p, double* res /* n_obs x 2 */);
 

@@ -51,6 +51,8 @@ template <int N> Jet<N> operator-(double s, const Jet<N>& x) { return (-x) + s; 
 template <int N> Jet<N> sqrt(const Jet<N>& x) { Jet<N> r; r.a = std::sqrt(x.a); const double d = 0.5 / r.a; for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * d; return r; }
 template <int N> Jet<N> sin(const Jet<N>& x) { Jet<N> r; r.a = std::sin(x.a); const double c = std::cos(x.a); for (int i = 0; i < N; ++i) r.v[i] = c * x.v[i]; return r; }
 template <int N> Jet<N> cos(const Jet<N>& x) { Jet<N> r; r.a = std::cos(x.a); const double s = -std::sin(x.a); for (int i = 0; i < N; ++i) r.v[i] = s * x.v[i]; return r; }
+template <int N> Jet<N> atan(const Jet<N>& x) { Jet<N> r; r.a = std::atan(x.a); const double d = 1.0 / (1.0 + x.a * x.a); for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * d; return r; }
+inline double atan(double x) { return std::atan(x); }
 inline double sqrt(double x) { return std::sqrt(x); }
 inline double sin(double x) { return std::sin(x); }
 inline double cos(double x) { return std::cos(x); }
@@ -81,8 +83,11 @@ void angle_axis_rotate_point(const T aa[3], const T pt[3], T result[3]) {
 }
 
 // ResidualErrorFunctor_Pinhole_Intrinsic_Radial_K3::operator()
+// OpenMVG's residual functors of the five camera models Regard3D can store (sfm_data_BA_ceres_camera_functor.hpp;
+// model chosen per intrinsic group: src/R3DProject.cpp:1167-1191): 1 pinhole, 2 radial K1, 3 radial K3, 4 Brown T2
+// (k1 k2 k3 in intr[3..5], t1 t2 in ext), 5 fisheye (k1 k2 k3 in intr[3..5], k4 in ext).  ext is constant.
 template <typename T>
-void residual_radial_k3(const T intr[6], const T pose[6], const T X[3], const double obs[2], T out[2]) {
+void residual_model(int model, const T intr[6], const double* ext, const T pose[6], const T X[3], const double obs[2], T out[2]) {
   T p[3];
   angle_axis_rotate_point(pose, X, p);
   p[0] = p[0] + pose[3];
@@ -91,31 +96,80 @@ void residual_radial_k3(const T intr[6], const T pose[6], const T X[3], const do
   const T x_u = p[0] / p[2];
   const T y_u = p[1] / p[2];
   const T r2 = x_u * x_u + y_u * y_u;
-  const T r4 = r2 * r2;
-  const T r6 = r4 * r2;
-  const T r_coeff = T(1.0) + intr[3] * r2 + intr[4] * r4 + intr[5] * r6;
-  const T x_d = x_u * r_coeff;
-  const T y_d = y_u * r_coeff;
+  T x_d = x_u, y_d = y_u;
+  if (model == 2) {
+    const T r_coeff = T(1.0) + intr[3] * r2;
+    x_d = x_u * r_coeff;
+    y_d = y_u * r_coeff;
+  } else if (model == 3 || model == 4) {
+    const T r4 = r2 * r2;
+    const T r6 = r4 * r2;
+    const T r_coeff = T(1.0) + intr[3] * r2 + intr[4] * r4 + intr[5] * r6;
+    x_d = x_u * r_coeff;
+    y_d = y_u * r_coeff;
+    if (model == 4) {
+      const double t1 = ext ? ext[0] : 0.0, t2 = ext ? ext[1] : 0.0;
+      const T t_x = t2 * (r2 + 2.0 * (x_u * x_u)) + 2.0 * t1 * (x_u * y_u);
+      const T t_y = t1 * (r2 + 2.0 * (y_u * y_u)) + 2.0 * t2 * (x_u * y_u);
+      x_d = x_d + t_x;
+      y_d = y_d + t_y;
+    }
+  } else if (model == 5) {
+    const double k4 = ext ? ext[0] : 0.0;
+    if (value(r2) > 1e-16) {
+      const T r = sqrt(r2);
+      const T theta = atan(r);
+      const T theta2 = theta * theta, theta3 = theta2 * theta, theta4 = theta2 * theta2, theta5 = theta4 * theta,
+              theta7 = theta3 * theta3 * theta, theta8 = theta4 * theta4, theta9 = theta8 * theta;
+      const T theta_dist = theta + intr[3] * theta3 + intr[4] * theta5 + intr[5] * theta7 + k4 * theta9;
+      const T cdist = theta_dist / r;
+      x_d = x_u * cdist;
+      y_d = y_u * cdist;
+    }
+  }
   out[0] = intr[1] + intr[0] * x_d - obs[0];
   out[1] = intr[2] + intr[0] * y_d - obs[1];
 }
+inline int model_params6(int model) { return model == 1 ? 3 : (model == 2 ? 4 : 6); }
 
-inline void residual_only(const double* intr, const double* pose, const double* X, const double* obs, double* r) {
-  residual_radial_k3<double>(intr, pose, X, obs, r);
+inline void residual_only(int model, const double* intr, const double* ext, const double* pose, const double* X, const double* obs,
+                          double* r) {
+  residual_model<double>(model, intr, ext, pose, X, obs, r);
 }
 
-// residual + Jacobian (2 x 15: intr 0..5, pose 6..11, point 12..14), column-major-by-parameter
-inline void residual_jacobian(const double* intr, const double* pose, const double* X, const double* obs, double* r,
-                              double J[2][15]) {
+// residual + Jacobian (2 x 15: intr 0..5, pose 6..11, point 12..14); intrinsic slots the model does not own: zero
+inline void residual_jacobian(int model, const double* intr, const double* ext, const double* pose, const double* X,
+                              const double* obs, double* r, double J[2][15]) {
   typedef Jet<15> J15;
   J15 ji[6], jp[6], jx[3], out[2];
   for (int k = 0; k < 6; ++k) ji[k] = J15(intr[k], k);
   for (int k = 0; k < 6; ++k) jp[k] = J15(pose[k], 6 + k);
   for (int k = 0; k < 3; ++k) jx[k] = J15(X[k], 12 + k);
-  residual_radial_k3<J15>(ji, jp, jx, obs, out);
+  residual_model<J15>(model, ji, ext, jp, jx, obs, out);
+  const int np = model_params6(model);
   for (int c = 0; c < 2; ++c) {
     r[c] = out[c].a;
-    for (int k = 0; k < 15; ++k) J[c][k] = out[c].v[k];
+    for (int k = 0; k < 15; ++k) J[c][k] = (k < 6 && k >= np) ? 0.0 : out[c].v[k];
+  }
+}
+
+// openMVG PoseCenterConstraintCostFunction: residual = weight .* (C - prior), C = -R(aa)^T t
+template <typename T>
+void prior_residual(const T pose[6], const double* center, const double* weight, T out[3]) {
+  const T maa[3] = {-pose[0], -pose[1], -pose[2]};
+  const T t[3] = {pose[3], pose[4], pose[5]};
+  T c[3];
+  angle_axis_rotate_point(maa, t, c);
+  for (int i = 0; i < 3; ++i) out[i] = weight[i] * ((-c[i]) - center[i]);
+}
+inline void prior_residual_jacobian(const double* pose, const double* center, const double* weight, double* r, double J[3][6]) {
+  typedef Jet<6> J6;
+  J6 jp[6], out[3];
+  for (int k = 0; k < 6; ++k) jp[k] = J6(pose[k], k);
+  prior_residual<J6>(jp, center, weight, out);
+  for (int i = 0; i < 3; ++i) {
+    r[i] = out[i].a;
+    for (int k = 0; k < 6; ++k) J[i][k] = out[i].v[k];
   }
 }
 
@@ -192,6 +246,9 @@ struct Problem {
   std::vector<uint32_t> pt_obs;
   int nB() const { return 6 * (int)p->n_cams + (refine_intr ? 6 * (int)p->n_intr : 0); }
   int intr_col(uint32_t g) const { return 6 * (int)p->n_cams + 6 * (int)g; }
+  int model(uint32_t g) const { return p->intr_model ? (int)p->intr_model[g] : 3; }
+  const double* ext(uint32_t g) const { return p->intrinsics_ext ? p->intrinsics_ext + 2 * (size_t)g : nullptr; }
+  double prior_huber_a = 0.0;
 };
 
 static double total_cost(const Problem& P, const double* poses, const double* intr, const double* pts) {
@@ -201,9 +258,16 @@ static double total_cost(const Problem& P, const double* poses, const double* in
   for (int64_t o = 0; o < (int64_t)p.n_obs; ++o) {
     const uint32_t c = p.obs_cam[o], pt = p.obs_pt[o];
     double r[2];
-    residual_only(intr + 6 * (size_t)p.cam_intr[c], poses + 6 * (size_t)c, pts + 3 * (size_t)pt, p.obs_xy + 2 * o, r);
+    const uint32_t gi = p.cam_intr[c];
+    residual_only(P.model(gi), intr + 6 * (size_t)gi, P.ext(gi), poses + 6 * (size_t)c, pts + 3 * (size_t)pt, p.obs_xy + 2 * o, r);
     double rho1;
     cost += 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], P.huber_a, &rho1);
+  }
+  for (uint32_t k = 0; k < p.n_priors; ++k) {  // pose-centre priors
+    double r[3];
+    prior_residual<double>(poses + 6 * (size_t)p.prior_cam[k], p.prior_center + 3 * (size_t)k, p.prior_weight + 3 * (size_t)k, r);
+    double rho1;
+    cost += 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], P.prior_huber_a, &rho1);
   }
   return cost;
 }
@@ -220,17 +284,31 @@ void orc_ba_residuals(const orc_ba_problem* p, double* res) {
   for (int64_t o = 0; o < (int64_t)p->n_obs; ++o) {
     const uint32_t c = p->obs_cam[o], pt = p->obs_pt[o];
     double r[2];
-    residual_only(p->intrinsics + 6 * (size_t)p->cam_intr[c], p->poses + 6 * (size_t)c, p->points + 3 * (size_t)pt,
-                  p->obs_xy + 2 * o, r);
+    const uint32_t gi = p->cam_intr[c];
+    residual_only(p->intr_model ? (int)p->intr_model[gi] : 3, p->intrinsics + 6 * (size_t)gi,
+                  p->intrinsics_ext ? p->intrinsics_ext + 2 * (size_t)gi : nullptr, p->poses + 6 * (size_t)c,
+                  p->points + 3 * (size_t)pt, p->obs_xy + 2 * o, r);
     res[2 * o] = std::fabs(r[0]);  // OpenMVGHelper::calculateResiduals: abs per coordinate
     res[2 * o + 1] = std::fabs(r[1]);
   }
 }
 
 // residual + Jacobian of one observation (test hook: pins the GPU's analytic derivatives)
+void orc_ba_prior(const double* pose, const double* center, const double* weight, double* r, double* J) {
+  double Jm[3][6];
+  prior_residual_jacobian(pose, center, weight, r, Jm);
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 6; ++k) J[6 * i + k] = Jm[i][k];
+}
+
 void orc_ba_jacobian(const double* intr, const double* pose, const double* X, const double* obs, double* r, double* J) {
+  orc_ba_jacobian_model(3, intr, nullptr, pose, X, obs, r, J);
+}
+
+void orc_ba_jacobian_model(int model, const double* intr, const double* ext, const double* pose, const double* X,
+                           const double* obs, double* r, double* J) {
   double Jm[2][15];
-  residual_jacobian(intr, pose, X, obs, r, Jm);
+  residual_jacobian(model, intr, ext, pose, X, obs, r, Jm);
   for (int c = 0; c < 2; ++c)
     for (int k = 0; k < 15; ++k) J[c * 15 + k] = Jm[c][k];
 }
@@ -242,6 +320,7 @@ int orc_bundle_adjust(orc_ba_problem* pp, const orc_ba_options* opt, orc_ba_summ
   P.n_threads = opt->n_threads > 0 ? opt->n_threads : omp_get_max_threads();
   P.refine_intr = opt->refine_intrinsics != 0;
   P.huber_a = opt->huber_a;
+  P.prior_huber_a = opt->prior_huber_a;
   const orc_ba_problem& p = *pp;
   const int nB = P.nB();
   const size_t npt = p.n_pts;
@@ -272,12 +351,14 @@ int orc_bundle_adjust(orc_ba_problem* pp, const orc_ba_options* opt, orc_ba_summ
 
   // per-observation scaled Jacobian blocks, recomputed whenever x changes
   std::vector<double> Jc(12 * p.n_obs), Jg(12 * p.n_obs), Jp(6 * p.n_obs), rr(2 * p.n_obs);
+  std::vector<double> Jpr(18 * (size_t)p.n_priors), rpr(3 * (size_t)p.n_priors);  // pose-centre prior blocks (3 x 6)
   auto evaluate = [&]() {
 #pragma omp parallel for schedule(static) num_threads(P.n_threads)
     for (int64_t o = 0; o < (int64_t)p.n_obs; ++o) {
       const uint32_t c = p.obs_cam[o], pt = p.obs_pt[o], gi = p.cam_intr[c];
       double r[2], J[2][15];
-      residual_jacobian(p.intrinsics + 6 * (size_t)gi, p.poses + 6 * (size_t)c, p.points + 3 * (size_t)pt, p.obs_xy + 2 * o, r, J);
+      residual_jacobian(P.model(gi), p.intrinsics + 6 * (size_t)gi, P.ext(gi), p.poses + 6 * (size_t)c, p.points + 3 * (size_t)pt,
+                        p.obs_xy + 2 * o, r, J);
       double rho1;
       huber_rho(r[0] * r[0] + r[1] * r[1], P.huber_a, &rho1);
       const double sq = std::sqrt(rho1);  // Corrector, rho'' <= 0 branch
@@ -288,8 +369,22 @@ int orc_bundle_adjust(orc_ba_problem* pp, const orc_ba_options* opt, orc_ba_summ
         for (int k = 0; k < 3; ++k) Jp[6 * o + 3 * a + k] = J[a][12 + k] * sq;
       }
     }
+    for (uint32_t k = 0; k < p.n_priors; ++k) {
+      double r[3], J[3][6];
+      prior_residual_jacobian(p.poses + 6 * (size_t)p.prior_cam[k], p.prior_center + 3 * (size_t)k, p.prior_weight + 3 * (size_t)k, r, J);
+      double rho1;
+      huber_rho(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], P.prior_huber_a, &rho1);
+      const double sq = std::sqrt(rho1);
+      for (int a = 0; a < 3; ++a) {
+        rpr[3 * (size_t)k + a] = r[a] * sq;
+        for (int q = 0; q < 6; ++q) Jpr[18 * (size_t)k + 6 * a + q] = J[a][q] * sq;
+      }
+    }
     if (!have_scale) {  // Jacobi scaling from the initial Jacobian: 1 / (1 + ||column||)
       std::vector<double> n2(nparam, 0.0);
+      for (uint32_t k = 0; k < p.n_priors; ++k)
+        for (int a = 0; a < 3; ++a)
+          for (int q = 0; q < 6; ++q) n2[6 * (size_t)p.prior_cam[k] + q] += Jpr[18 * (size_t)k + 6 * a + q] * Jpr[18 * (size_t)k + 6 * a + q];
       for (uint64_t o = 0; o < p.n_obs; ++o) {
         const uint32_t c = p.obs_cam[o], pt = p.obs_pt[o], gi = p.cam_intr[c];
         for (int a = 0; a < 2; ++a) {
@@ -311,9 +406,18 @@ int orc_bundle_adjust(orc_ba_problem* pp, const orc_ba_options* opt, orc_ba_summ
         for (int k = 0; k < 3; ++k) Jp[6 * o + 3 * a + k] *= scale[(size_t)nB + 3 * (size_t)pt + k];
       }
     }
+    for (uint32_t k = 0; k < p.n_priors; ++k)
+      for (int a = 0; a < 3; ++a)
+        for (int q = 0; q < 6; ++q) Jpr[18 * (size_t)k + 6 * a + q] *= scale[6 * (size_t)p.prior_cam[k] + q];
     // gradient g = J^T r and diag(J^T J)
     std::fill(g.begin(), g.end(), 0.0);
     std::fill(diag.begin(), diag.end(), 0.0);
+    for (uint32_t k = 0; k < p.n_priors; ++k)
+      for (int a = 0; a < 3; ++a)
+        for (int q = 0; q < 6; ++q) {
+          g[6 * (size_t)p.prior_cam[k] + q] += Jpr[18 * (size_t)k + 6 * a + q] * rpr[3 * (size_t)k + a];
+          diag[6 * (size_t)p.prior_cam[k] + q] += Jpr[18 * (size_t)k + 6 * a + q] * Jpr[18 * (size_t)k + 6 * a + q];
+        }
     for (uint64_t o = 0; o < p.n_obs; ++o) {
       const uint32_t c = p.obs_cam[o], pt = p.obs_pt[o], gi = p.cam_intr[c];
       for (int a = 0; a < 2; ++a) {
@@ -431,6 +535,15 @@ int orc_bundle_adjust(orc_ba_problem* pp, const orc_ba_options* opt, orc_ba_summ
             }
         }
       }
+    }
+    for (uint32_t k = 0; k < p.n_priors; ++k) {  // U blocks of the pose-centre priors
+      const size_t c0 = 6 * (size_t)p.prior_cam[k];
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) {
+          double v = 0;
+          for (int a = 0; a < 3; ++a) v += Jpr[18 * (size_t)k + 6 * a + i] * Jpr[18 * (size_t)k + 6 * a + j];
+          S[(c0 + i) * nB + c0 + j] += v;
+        }
     }
     for (int j = 0; j < nB; ++j) S[(size_t)j * nB + j] += D2[j];
     std::vector<double> dB(rhs);

@@ -51,6 +51,8 @@ class BAProblem(C.Structure):
         ("poses", C.c_void_p), ("intrinsics", C.c_void_p), ("points", C.c_void_p),
         ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_intr", C.c_void_p),
         ("obs_xy", C.c_void_p),
+        ("intr_model", C.c_void_p), ("intrinsics_ext", C.c_void_p), ("n_priors", C.c_uint32),
+        ("prior_cam", C.c_void_p), ("prior_center", C.c_void_p), ("prior_weight", C.c_void_p),
     ]
 
 
@@ -59,6 +61,7 @@ class BAOptions(C.Structure):
         ("max_iterations", C.c_uint32), ("huber_a", C.c_double), ("refine_intrinsics", C.c_int),
         ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
         ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("n_threads", C.c_int),
+        ("prior_huber_a", C.c_double),
     ]
 
 
@@ -322,7 +325,26 @@ def _ba_struct(p):
     s.n_obs = p["obs_xy"].shape[0]
     for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy"):
         setattr(s, k, p[k].ctypes.data)
+    ba_optional_fields(s, p)
     return s
+
+
+def ba_optional_fields(s, p):
+    """intr_model / intrinsics_ext / priors of a BA problem dict (all optional) -> the C struct."""
+    if p.get("intr_model") is not None:
+        p["intr_model"] = np.ascontiguousarray(p["intr_model"], np.uint8)
+        s.intr_model = p["intr_model"].ctypes.data
+    if p.get("intrinsics_ext") is not None:
+        p["intrinsics_ext"] = np.ascontiguousarray(p["intrinsics_ext"], np.float64)
+        s.intrinsics_ext = p["intrinsics_ext"].ctypes.data
+    if p.get("prior_cam") is not None and len(p["prior_cam"]):
+        p["prior_cam"] = np.ascontiguousarray(p["prior_cam"], np.uint32)
+        p["prior_center"] = np.ascontiguousarray(p["prior_center"], np.float64)
+        p["prior_weight"] = np.ascontiguousarray(p["prior_weight"], np.float64)
+        s.n_priors = len(p["prior_cam"])
+        s.prior_cam = p["prior_cam"].ctypes.data
+        s.prior_center = p["prior_center"].ctypes.data
+        s.prior_weight = p["prior_weight"].ctypes.data
 
 
 def ba_prepare(poses, intrinsics, points, obs_cam, obs_pt, cam_intr, obs_xy):
@@ -337,7 +359,7 @@ def ba_prepare(poses, intrinsics, points, obs_cam, obs_pt, cam_intr, obs_xy):
     }
 
 
-def default_ba_options(max_iterations=500, huber_a=16.0, refine_intrinsics=1, n_threads=0):
+def default_ba_options(max_iterations=500, huber_a=16.0, refine_intrinsics=1, n_threads=0, prior_huber_a=0.0):
     o = BAOptions()
     o.max_iterations = max_iterations
     o.huber_a = huber_a
@@ -347,6 +369,7 @@ def default_ba_options(max_iterations=500, huber_a=16.0, refine_intrinsics=1, n_
     o.parameter_tolerance = 1e-8
     o.initial_radius = 1e4
     o.n_threads = n_threads
+    o.prior_huber_a = prior_huber_a
     return o
 
 
@@ -368,6 +391,23 @@ def ba_residuals(p):
     res = np.zeros((p["obs_xy"].shape[0], 2), np.float64)
     lib().orc_ba_residuals(C.byref(s), _p(res))
     return res
+
+
+def ba_jacobian_model(model, intr, ext, pose, X, obs):
+    intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
+    ext = None if ext is None else np.ascontiguousarray(ext, np.float64)
+    r = np.zeros(2)
+    J = np.zeros((2, 15))
+    lib().orc_ba_jacobian_model(C.c_int(model), _p(intr), None if ext is None else _p(ext), _p(pose), _p(X), _p(obs), _p(r), _p(J))
+    return r, J
+
+
+def ba_prior(pose, center, weight):
+    pose, center, weight = [np.ascontiguousarray(a, np.float64) for a in (pose, center, weight)]
+    r = np.zeros(3)
+    J = np.zeros((3, 6))
+    lib().orc_ba_prior(_p(pose), _p(center), _p(weight), _p(r), _p(J))
+    return r, J
 
 
 def ba_jacobian(intr, pose, X, obs):

@@ -30,7 +30,7 @@ EXPORTS = [
     "r3d_sfm_data_free", "r3d_sfm_data_load", "r3d_sfm_data_save", "r3d_sfm_root_path", "r3d_sfm_set_root_path",
     "r3d_sfm_num_views", "r3d_sfm_num_intrinsics", "r3d_sfm_num_poses", "r3d_sfm_num_landmarks", "r3d_sfm_add_view",
     "r3d_sfm_get_view", "r3d_sfm_add_intrinsic", "r3d_sfm_get_intrinsic", "r3d_sfm_add_pose", "r3d_sfm_get_pose",
-    "r3d_sfm_add_landmark", "r3d_sfm_get_landmark",
+    "r3d_sfm_add_landmark", "r3d_sfm_get_landmark", "r3d_debug_ba_jacobian_model", "r3d_debug_ba_prior",
 ]
 
 
@@ -78,13 +78,15 @@ class BAProblem(C.Structure):
     _fields_ = [("n_cams", C.c_uint32), ("n_pts", C.c_uint32), ("n_intr", C.c_uint32), ("n_obs", C.c_uint64),
                 ("poses", C.c_void_p), ("intrinsics", C.c_void_p), ("points", C.c_void_p),
                 ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("cam_intr", C.c_void_p),
-                ("obs_xy", C.c_void_p)]
+                ("obs_xy", C.c_void_p),
+                ("intr_model", C.c_void_p), ("intrinsics_ext", C.c_void_p), ("n_priors", C.c_uint32),
+                ("prior_cam", C.c_void_p), ("prior_center", C.c_void_p), ("prior_weight", C.c_void_p)]
 
 
 class BAOptions(C.Structure):
     _fields_ = [("max_iterations", C.c_uint32), ("huber_a", C.c_double), ("refine_intrinsics", C.c_int),
                 ("function_tolerance", C.c_double), ("gradient_tolerance", C.c_double),
-                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double)]
+                ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double), ("prior_huber_a", C.c_double)]
 
 
 class BASummary(C.Structure):
@@ -413,6 +415,27 @@ class SfmData:
         return out
 
 
+def debug_ba_jacobian_model(model, intr, ext, pose, X, obs):
+    """Host evaluation of the analytic model of any of the five camera types (no GPU needed)."""
+    intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
+    ext = None if ext is None else np.ascontiguousarray(ext, np.float64)
+    r = np.zeros(2)
+    J = np.zeros((2, 15))
+    rc = lib().r3d_debug_ba_jacobian_model(C.c_int(model), _p(intr), None if ext is None else _p(ext), _p(pose), _p(X), _p(obs),
+                                           _p(r), _p(J))
+    if rc:
+        raise R3DError(rc, "r3d_debug_ba_jacobian_model")
+    return r, J
+
+
+def debug_ba_prior(pose, center, weight):
+    pose, center, weight = [np.ascontiguousarray(a, np.float64) for a in (pose, center, weight)]
+    r = np.zeros(3)
+    J = np.zeros((3, 6))
+    lib().r3d_debug_ba_prior(_p(pose), _p(center), _p(weight), _p(r), _p(J))
+    return r, J
+
+
 def debug_ba_jacobian(intr, pose, X, obs):
     """Host evaluation of the analytic BA model (no GPU needed)."""
     intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
@@ -529,6 +552,20 @@ class Context:
         s.n_obs = p["obs_xy"].shape[0]
         for k in ("poses", "intrinsics", "points", "obs_cam", "obs_pt", "cam_intr", "obs_xy"):
             setattr(s, k, p[k].ctypes.data)
+        if p.get("intr_model") is not None:
+            p["intr_model"] = np.ascontiguousarray(p["intr_model"], np.uint8)
+            s.intr_model = p["intr_model"].ctypes.data
+        if p.get("intrinsics_ext") is not None:
+            p["intrinsics_ext"] = np.ascontiguousarray(p["intrinsics_ext"], np.float64)
+            s.intrinsics_ext = p["intrinsics_ext"].ctypes.data
+        if p.get("prior_cam") is not None and len(p["prior_cam"]):
+            p["prior_cam"] = np.ascontiguousarray(p["prior_cam"], np.uint32)
+            p["prior_center"] = np.ascontiguousarray(p["prior_center"], np.float64)
+            p["prior_weight"] = np.ascontiguousarray(p["prior_weight"], np.float64)
+            s.n_priors = len(p["prior_cam"])
+            s.prior_cam = p["prior_cam"].ctypes.data
+            s.prior_center = p["prior_center"].ctypes.data
+            s.prior_weight = p["prior_weight"].ctypes.data
         return s
 
     def bundle_adjust(self, p, max_iterations=500, huber_a=16.0, refine_intrinsics=1, **tol):

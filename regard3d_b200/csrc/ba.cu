@@ -48,10 +48,18 @@ struct Dev {
   const uint32_t *pt_ofs, *pt_obs;         // point -> observation CSR
   double *scale, *gu, *du, *g, *diag, *delta;  // nparam each (u = unscaled accumulators)
   double *S, *rhs, *Vinv;
+  const uint8_t* intr_model;               // per group: openMVG EINTRINSIC 1..5 (nullptr: all radial K3)
+  const double* intr_ext;                  // per group 2 doubles: Brown t1 t2 / fisheye k4 (nullptr: zeros); held fixed
+  uint32_t n_priors;                       // pose-centre priors (ViewPriors): camera, centre, weight
+  const uint32_t* prior_cam;
+  const double *prior_center, *prior_weight;
+  double prior_huber_a;
   double* scal;                            // [0] cost [1] model_cost_change*2 [2] |dx|^2 [3] |x|^2 [4] not-PD flag
 };
 
 __device__ __forceinline__ uint32_t intr_col(const Dev& d, uint32_t g) { return 6 * d.n_cams + 6 * g; }
+__device__ __forceinline__ int model_of(const Dev& d, uint32_t g) { return d.intr_model ? (int)d.intr_model[g] : 3; }
+__device__ __forceinline__ const double* ext_of(const Dev& d, uint32_t g) { return d.intr_ext ? d.intr_ext + 2 * (size_t)g : nullptr; }
 
 __device__ __forceinline__ double block_sum(double v, double* smem) {
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -75,7 +83,8 @@ __global__ void __launch_bounds__(256) k_ba_cost(Dev d, const double* poses, con
     const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o];
     const double2 xy = d.obs_xy[o];
     double r[2];
-    residual_only(intr + 6 * (size_t)d.cam_intr[cam], poses + 6 * (size_t)cam, pts + 3 * (size_t)pt, xy.x, xy.y, r);
+    const uint32_t gi = d.cam_intr[cam];
+    residual_only(model_of(d, gi), intr + 6 * (size_t)gi, ext_of(d, gi), poses + 6 * (size_t)cam, pts + 3 * (size_t)pt, xy.x, xy.y, r);
     double rho1;
     c += 0.5 * huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
   }
@@ -89,7 +98,8 @@ __global__ void __launch_bounds__(256) k_ba_abs_residuals(Dev d, double* res) {
     const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o];
     const double2 xy = d.obs_xy[o];
     double r[2];
-    residual_only(d.intr + 6 * (size_t)d.cam_intr[cam], d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r);
+    const uint32_t gi = d.cam_intr[cam];
+    residual_only(model_of(d, gi), d.intr + 6 * (size_t)gi, ext_of(d, gi), d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r);
     res[2 * o] = fabs(r[0]);
     res[2 * o + 1] = fabs(r[1]);
   }
@@ -101,7 +111,8 @@ __global__ void __launch_bounds__(256) k_ba_eval(Dev d) {
     const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o], gi = d.cam_intr[cam];
     const double2 xy = d.obs_xy[o];
     double r[2], Ji[12], Jc[12], Jp[6];
-    residual_jacobian(d.intr + 6 * (size_t)gi, d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r, Ji, Jc, Jp);
+    residual_jacobian(model_of(d, gi), d.intr + 6 * (size_t)gi, ext_of(d, gi), d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt,
+                      xy.x, xy.y, r, Ji, Jc, Jp);
     double rho1;
     huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
     // Corrector (rho'' <= 0): residual and Jacobian scaled by sqrt(rho') -> J^T r and J^T J scale by rho'
@@ -169,7 +180,8 @@ __device__ __forceinline__ void scaled_jacobian(const Dev& d, uint32_t o, double
   const uint32_t cam = d.obs_cam[o], pt = d.obs_pt[o], gi = d.cam_intr[cam];
   const double2 xy = d.obs_xy[o];
   double Ji[12];
-  residual_jacobian(d.intr + 6 * (size_t)gi, d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x, xy.y, r, Ji, Jc, Jp);
+  residual_jacobian(model_of(d, gi), d.intr + 6 * (size_t)gi, ext_of(d, gi), d.poses + 6 * (size_t)cam, d.pts + 3 * (size_t)pt, xy.x,
+                    xy.y, r, Ji, Jc, Jp);
   double rho1;
   huber_rho(r[0] * r[0] + r[1] * r[1], d.huber_a, &rho1);
   const double sq = sqrt(rho1);
@@ -719,6 +731,33 @@ __global__ void __launch_bounds__(128) k_ba_backsub(Dev d) {
   for (int i = 0; i < 3; ++i) d.delta[pcol + i] = Vi[3 * i] * t3[0] + Vi[3 * i + 1] * t3[1] + Vi[3 * i + 2] * t3[2];
 }
 
+// ---- pose-centre priors (ViewPriors / GPS): a camera-only residual block per prior ------------------------
+// mode 0: cost at (poses) -> out[0] ; mode 1: gradient + diag(J^T J), unscaled -> gu, du ; mode 2: U block of S (scaled)
+__global__ void k_ba_priors(Dev d, const double* poses, int mode, double* out_cost) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.n_priors) return;
+  const uint32_t cam = d.prior_cam[k];
+  double r[3], J[18];
+  prior_residual_jacobian(poses + 6 * (size_t)cam, d.prior_center + 3 * (size_t)k, d.prior_weight + 3 * (size_t)k, r, mode ? J : nullptr);
+  double rho1;
+  const double rho = huber_rho(r[0] * r[0] + r[1] * r[1] + r[2] * r[2], d.prior_huber_a, &rho1);
+  if (mode == 0) {
+    atomicAdd(out_cost, 0.5 * rho);
+  } else if (mode == 1) {
+    for (int q = 0; q < 6; ++q) {
+      atomicAdd(&d.gu[6 * (size_t)cam + q], rho1 * (J[q] * r[0] + J[6 + q] * r[1] + J[12 + q] * r[2]));
+      atomicAdd(&d.du[6 * (size_t)cam + q], rho1 * (J[q] * J[q] + J[6 + q] * J[6 + q] + J[12 + q] * J[12 + q]));
+    }
+  } else {
+    const double* sc = d.scale + 6 * (size_t)cam;
+    double blk[36];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j)
+        blk[6 * i + j] = rho1 * sc[i] * sc[j] * (J[i] * J[j] + J[6 + i] * J[6 + j] + J[12 + i] * J[12 + j]);
+    add_block_upper(d.S, d.nB, 6 * cam, 6 * cam, blk, 1.0);
+  }
+}
+
 // ---- candidate parameters, step norms, model cost change ---------------------------------------------
 __global__ void __launch_bounds__(256) k_ba_update(Dev d, double inv_radius) {
   __shared__ double sm[8];
@@ -796,6 +835,7 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   d.refine_intr = refine_intr ? 1u : 0u;
   d.nB = 6 * p->n_cams + (refine_intr ? 6 * p->n_intr : 0);
   d.huber_a = huber_a;
+  d.prior_huber_a = 0.0;
   d.owns_shared = ctx->comm_rank == 0 ? 1u : 0u;
   const size_t nparam = (size_t)d.nB + 3 * (size_t)p->n_pts;
   uint32_t *oc, *op, *ci, *pofs, *pobs;
@@ -816,6 +856,34 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(ci, p->cam_intr, (size_t)p->n_cams * 4, cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(oxy, p->obs_xy, p->n_obs * 16, cudaMemcpyHostToDevice, w.stream));
   d.obs_cam = oc; d.obs_pt = op; d.cam_intr = ci; d.obs_xy = oxy;
+  if (p->intr_model) {
+    for (uint32_t g = 0; g < p->n_intr; ++g)
+      if (p->intr_model[g] < 1 || p->intr_model[g] > 5) return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: unknown camera model");
+    uint8_t* dm;
+    R3D_CUDA_TRY(ctx, mem.alloc(&dm, p->n_intr));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(dm, p->intr_model, p->n_intr, cudaMemcpyHostToDevice, w.stream));
+    d.intr_model = dm;
+  }
+  if (p->intrinsics_ext) {
+    double* de;
+    R3D_CUDA_TRY(ctx, mem.alloc(&de, 2 * (size_t)p->n_intr));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(de, p->intrinsics_ext, 2 * (size_t)p->n_intr * 8, cudaMemcpyHostToDevice, w.stream));
+    d.intr_ext = de;
+  }
+  if (p->n_priors) {
+    if (!p->prior_cam || !p->prior_center || !p->prior_weight) return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: NULL prior array");
+    for (uint32_t k = 0; k < p->n_priors; ++k)
+      if (p->prior_cam[k] >= p->n_cams) return fail(ctx, R3D_ERR_INVALID, "bundle adjustment: prior camera out of range");
+    uint32_t* pc;
+    double *pce, *pw;
+    R3D_CUDA_TRY(ctx, mem.alloc(&pc, p->n_priors));
+    R3D_CUDA_TRY(ctx, mem.alloc(&pce, 3 * (size_t)p->n_priors));
+    R3D_CUDA_TRY(ctx, mem.alloc(&pw, 3 * (size_t)p->n_priors));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pc, p->prior_cam, (size_t)p->n_priors * 4, cudaMemcpyHostToDevice, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pce, p->prior_center, 3 * (size_t)p->n_priors * 8, cudaMemcpyHostToDevice, w.stream));
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(pw, p->prior_weight, 3 * (size_t)p->n_priors * 8, cudaMemcpyHostToDevice, w.stream));
+    d.n_priors = p->n_priors; d.prior_cam = pc; d.prior_center = pce; d.prior_weight = pw;
+  }
   if (!full) return R3D_OK;
   if (p->n_obs > 0xfffffff0ull) return fail(ctx, R3D_ERR_UNSUPPORTED, "bundle adjustment: more than 2^32 observations");
   // point -> observation CSR (host counting sort)
@@ -1035,6 +1103,7 @@ void r3d_ba_default_options(r3d_ba_options* o) {
   o->gradient_tolerance = 1e-10;
   o->parameter_tolerance = 1e-8;
   o->initial_radius = 1e4;
+  o->prior_huber_a = 0.0;       // trivial loss unless the caller passes the registration's robust fitting error
 }
 
 int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res) {
@@ -1069,6 +1138,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   plan.want_batched = !per_point_schur;
   int rc = setup_problem(ctx, w, p, mem, d, opt->refine_intrinsics != 0, opt->huber_a, true, &max_obs, &plan);
   if (rc) return rc;
+  d.prior_huber_a = opt->prior_huber_a;
   if (plan.n_batches)
     R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_ba_schur_batched, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)r3d::ba::kBatchSmemBytes));
@@ -1109,6 +1179,8 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   auto eval_cost = [&](const double* poses, const double* intr, const double* pts, double* out) -> int {
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.scal, 0, sizeof(double), w.stream));
     r3d::ba::k_ba_cost<<<grid_obs, 256, 0, w.stream>>>(d, poses, intr, pts, d.scal);
+    if (d.n_priors && d.owns_shared)  // camera-only blocks: counted once across ranks
+      r3d::ba::k_ba_priors<<<(d.n_priors + 127) / 128, 128, 0, w.stream>>>(d, poses, 0, d.scal);
     R3D_CUDA_TRY(ctx, cudaGetLastError());
     if ((rc = comm_allreduce(ctx, w.stream, d.scal, 1, kCommSum))) return rc;
     if ((rc = read_scal())) return rc;
@@ -1121,6 +1193,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.gu, 0, nparam * 8, w.stream));
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(d.du, 0, nparam * 8, w.stream));
     r3d::ba::k_ba_eval<<<grid_obs, 256, 0, w.stream>>>(d);
+    if (d.n_priors && d.owns_shared) r3d::ba::k_ba_priors<<<(d.n_priors + 127) / 128, 128, 0, w.stream>>>(d, d.poses, 1, nullptr);
     // camera / intrinsic gradient and column norms are sums over every rank's observations
     if ((rc = comm_allreduce(ctx, w.stream, d.gu, nB, kCommSum))) return rc;
     if ((rc = comm_allreduce(ctx, w.stream, d.du, nB, kCommSum))) return rc;
@@ -1161,6 +1234,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     if (plan.n_long)  // long tracks and whatever else the batched kernel cannot take
       r3d::ba::k_ba_schur_cta<<<long_grid, r3d::ba::kCtaThreads, 0, w.stream>>>(d, plan.d_long, plan.n_long, inv_radius, d_long_scr,
                                                                              d_long_cols, plan.long_cap);
+    if (d.n_priors && d.owns_shared) r3d::ba::k_ba_priors<<<(d.n_priors + 127) / 128, 128, 0, w.stream>>>(d, d.poses, 2, nullptr);
     // the exchange step: partial reduced camera systems of the point partitions -> their sum (NVLink)
     if ((rc = comm_allreduce(ctx, w.stream, d.S, (size_t)nB * nB + nB, kCommSum))) return rc;
     {

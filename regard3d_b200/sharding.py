@@ -51,6 +51,10 @@ def partition_ba(prob, rank, world):
         "cam_intr": np.ascontiguousarray(prob["cam_intr"], np.uint32).copy(),
         "obs_xy": np.ascontiguousarray(np.asarray(prob["obs_xy"], np.float64)[sel]),
     }
+    # camera-side options are replicated like the cameras (the library counts prior blocks on rank 0 only)
+    for k in ("intr_model", "intrinsics_ext", "prior_cam", "prior_center", "prior_weight"):
+        if prob.get(k) is not None:
+            local[k] = np.array(prob[k]).copy()
     return local, (p0, p1)
 
 

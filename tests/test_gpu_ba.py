@@ -11,16 +11,20 @@ REL = 1e-5
 
 
 def _prep(oracle, prob):
-    return oracle.ba_prepare(prob["poses"], prob["intrinsics"], prob["points"], prob["obs_cam"], prob["obs_pt"],
-                             prob["cam_intr"], prob["obs_xy"])
+    d = oracle.ba_prepare(prob["poses"], prob["intrinsics"], prob["points"], prob["obs_cam"], prob["obs_pt"],
+                          prob["cam_intr"], prob["obs_xy"])
+    for k in ("intr_model", "intrinsics_ext", "prior_cam", "prior_center", "prior_weight"):
+        if prob.get(k) is not None:
+            d[k] = np.array(prob[k]).copy()
+    return d
 
 
-def _compare(gpu_ctx, oracle, prob, iters, huber_a=16.0, refine=1):
+def _compare(gpu_ctx, oracle, prob, iters, huber_a=16.0, refine=1, prior_huber_a=0.0):
     a = _prep(oracle, prob)
     b = _prep(oracle, prob)
-    opts = oracle.default_ba_options(max_iterations=iters, huber_a=huber_a, refine_intrinsics=refine)
+    opts = oracle.default_ba_options(max_iterations=iters, huber_a=huber_a, refine_intrinsics=refine, prior_huber_a=prior_huber_a)
     so, to = oracle.bundle_adjust(a, opts)
-    sg, tg = gpu_ctx.bundle_adjust(b, max_iterations=iters, huber_a=huber_a, refine_intrinsics=refine)
+    sg, tg = gpu_ctx.bundle_adjust(b, max_iterations=iters, huber_a=huber_a, refine_intrinsics=refine, prior_huber_a=prior_huber_a)
     assert sg["iterations"] == so["iterations"]
     assert sg["successful_steps"] == so["successful_steps"]
     assert sg["termination"] == so["termination"]
@@ -116,3 +120,36 @@ def test_ba_camera_sees_point_twice_and_three_groups(gpu_ctx, oracle):
     prob["obs_pt"] = np.concatenate([prob["obs_pt"], prob["obs_pt"][dup]]).astype(np.uint32)
     prob["obs_xy"] = np.concatenate([prob["obs_xy"], prob["obs_xy"][dup] + 0.3])
     _compare(gpu_ctx, oracle, prob, iters=10)
+
+
+@pytest.mark.parametrize("model", [1, 2, 4, 5])
+def test_ba_other_camera_models_equal_oracle(gpu_ctx, oracle, model):
+    """Pinhole, radial K1, Brown T2 and fisheye groups (src/R3DProject.cpp:1167-1191); two groups of different models in
+    one problem; Brown's t1 t2 / the fisheye's k4 are read and held fixed by both sides."""
+    prob = synth.make_ba_problem(n_cams=10, n_pts=500, obs_per_pt=4, seed=40 + model, outlier_frac=0.01)
+    prob["intrinsics"] = np.repeat(prob["intrinsics"], 2, 0).copy()
+    prob["cam_intr"] = (np.arange(10) % 2).astype(np.uint32)
+    prob["intr_model"] = np.array([model, 3], np.uint8)
+    prob["intrinsics_ext"] = np.array([[1e-4, -2e-4], [0.0, 0.0]])
+    _compare(gpu_ctx, oracle, prob, iters=12)
+    _compare(gpu_ctx, oracle, prob, iters=8, refine=0)
+
+
+def test_ba_pose_center_priors_equal_oracle(gpu_ctx, oracle):
+    """ViewPriors (GPS centres, src/R3DProject.cpp:1194-1220) as camera-only residual blocks, with and without a robust loss."""
+    prob = synth.make_ba_problem(n_cams=12, n_pts=600, obs_per_pt=4, seed=51, outlier_frac=0.0)
+    truth = prob["truth"]
+    rng = np.random.default_rng(5)
+    Cs = np.stack([-synth._rodrigues(truth["poses"][c, :3]).T @ truth["poses"][c, 3:] for c in range(12)])
+    cams = np.array([0, 2, 3, 7, 11], np.uint32)
+    prob["prior_cam"] = cams
+    prob["prior_center"] = Cs[cams] + 0.05 * rng.standard_normal((5, 3))
+    prob["prior_center"][1] += 3.0                                   # one gross GPS error
+    prob["prior_weight"] = np.tile([1.0, 1.0, 2.0], (5, 1))
+    so, _ = _compare(gpu_ctx, oracle, prob, iters=12)
+    _compare(gpu_ctx, oracle, prob, iters=12, prior_huber_a=0.5)
+    plain = dict(prob)
+    for k in ("prior_cam", "prior_center", "prior_weight"):
+        plain.pop(k)
+    s0, _ = _compare(gpu_ctx, oracle, plain, iters=12)
+    assert so["final_cost"] > s0["final_cost"]                       # the priors do take part in the cost

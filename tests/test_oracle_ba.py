@@ -92,3 +92,64 @@ def test_fixed_intrinsics_stay_fixed(oracle):
     i0 = p["intrinsics"].copy()
     oracle.bundle_adjust(p, oracle.default_ba_options(max_iterations=10, refine_intrinsics=0))
     assert np.array_equal(p["intrinsics"], i0)
+
+
+def test_camera_models_analytic_jacobians_equal_autodiff(oracle, r3dlib):
+    """The five OpenMVG camera models the reference can store (src/R3DProject.cpp:1167-1191): the product's analytic
+    residual / Jacobian (host build of ba_model.cuh) against the oracle's forward-mode autodiff of OpenMVG's functors."""
+    rng = np.random.default_rng(0)
+    for model in (1, 2, 3, 4, 5):
+        for _ in range(40):
+            intr = np.array([1800 + 100 * rng.standard_normal(), 960 + 5 * rng.standard_normal(), 540 + 5 * rng.standard_normal(),
+                             0.05 * rng.standard_normal(), 0.02 * rng.standard_normal(), 0.01 * rng.standard_normal()])
+            ext = 0.01 * rng.standard_normal(2)
+            pose = np.concatenate([0.5 * rng.standard_normal(3), rng.standard_normal(3)])
+            X = np.array([rng.standard_normal(), rng.standard_normal(), 6 + rng.random()])
+            obs = np.array([900.0, 500.0])
+            ro, Jo = oracle.ba_jacobian_model(model, intr, ext, pose, X, obs)
+            rg, Jg = r3dlib.debug_ba_jacobian_model(model, intr, ext, pose, X, obs)
+            assert np.allclose(rg, ro, rtol=1e-12, atol=1e-9) and np.allclose(Jg, Jo, rtol=1e-10, atol=1e-9), model
+            npar = {1: 3, 2: 4}.get(model, 6)
+            assert not Jo[:, npar:6].any()                      # slots the model does not own never move
+    # pinhole == K3 with zero distortion; Brown with t = 0 == K3
+    intr = np.array([1500.0, 960.0, 540.0, 0.03, -0.01, 0.002])
+    pose = np.array([0.1, -0.2, 0.05, 0.3, -0.1, 0.2])
+    X = np.array([0.5, -0.3, 7.0])
+    obs = np.array([1000.0, 480.0])
+    r3, _ = oracle.ba_jacobian_model(3, intr, None, pose, X, obs)
+    r4, _ = oracle.ba_jacobian_model(4, intr, [0.0, 0.0], pose, X, obs)
+    assert np.array_equal(r3, r4)
+
+
+def test_pose_center_prior_block(oracle, r3dlib):
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        pose = np.concatenate([rng.standard_normal(3), 3 * rng.standard_normal(3)])
+        c, w = rng.standard_normal(3), rng.random(3) + 0.5
+        ro, Jo = oracle.ba_prior(pose, c, w)
+        rg, Jg = r3dlib.debug_ba_prior(pose, c, w)
+        assert np.allclose(rg, ro, atol=1e-12) and np.allclose(Jg, Jo, atol=1e-11)
+    # residual is weight * (C - prior) with C = -R^T t
+    from regard3d_b200 import synth
+    pose = np.array([0.2, -0.1, 0.3, 1.0, 2.0, 3.0])
+    C = -synth._rodrigues(pose[:3]).T @ pose[3:]
+    r, _ = oracle.ba_prior(pose, C + [0.5, 0.0, -1.0], [2.0, 1.0, 1.0])
+    assert np.allclose(r, [-1.0, 0.0, 1.0])
+
+
+def test_oracle_ba_with_models_and_priors_converges(oracle):
+    from regard3d_b200 import synth
+    prob = synth.make_ba_problem(n_cams=8, n_pts=250, obs_per_pt=4, seed=31, outlier_frac=0.0)
+    truth = prob["truth"]
+    Cs = np.stack([-synth._rodrigues(truth["poses"][c, :3]).T @ truth["poses"][c, 3:] for c in range(8)])
+    for model in (1, 2, 4, 5):
+        a = oracle.ba_prepare(prob["poses"], prob["intrinsics"], prob["points"], prob["obs_cam"], prob["obs_pt"], prob["cam_intr"], prob["obs_xy"])
+        a["intr_model"] = np.full(1, model, np.uint8)
+        a["intrinsics_ext"] = np.zeros((1, 2))
+        a["prior_cam"] = np.arange(8, dtype=np.uint32)
+        a["prior_center"] = Cs + 0.01
+        a["prior_weight"] = np.ones((8, 3))
+        s, t = oracle.bundle_adjust(a, oracle.default_ba_options(max_iterations=15))
+        assert t[-1] < 0.2 * t[0], (model, t[0], t[-1])
+        if model in (1, 2):
+            assert not a["intrinsics"][0, {1: 3, 2: 4}[model]:].any()   # unused distortion slots stay zero
