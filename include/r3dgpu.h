@@ -254,6 +254,18 @@ void r3d_ba_default_options(r3d_ba_options* o);
 int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* io, const r3d_ba_options* opt,
                       r3d_ba_summary* summary, double* cost_trace /* max_iterations+1 or NULL */);
 
+/* openMVG::sfm::Bundle_Adjustment_Ceres::Adjust(SfM_Data&, Optimize_Options) on the SfM_Data container itself: poses
+ * (R, C) <-> angle-axis | t, one parameter block per intrinsic id in its own camera model, landmarks; refined values are
+ * written back into sd.  solver.refine_intrinsics = Intrinsic_Parameter_Type ADJUST_ALL / NONE; use_motion_priors adds
+ * one pose-centre block per ViewPriors view (sfmEngine.Set_Use_Motion_Prior, R3DTriangulationThread.cpp:433).  The C++
+ * adaptor with the reference's class shape is regard3d_b200/csrc/Bundle_Adjustment_b200.h. */
+typedef struct {
+  r3d_ba_options solver;
+  int use_motion_priors;
+} r3d_sfm_ba_options;
+void r3d_sfm_ba_default_options(r3d_sfm_ba_options* o);
+int r3d_sfm_bundle_adjust(r3d_ctx* ctx, r3d_sfm_data* sd, const r3d_sfm_ba_options* opt, r3d_ba_summary* summary);
+
 /* ---- multi-GPU bundle adjustment (the one path with a real exchange step) -------
  * One process per GPU.  The 3-D points (with all their observations) are partitioned over the
  * ranks, cameras and intrinsics are replicated: every rank passes r3d_bundle_adjust ALL cameras /
