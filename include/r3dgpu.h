@@ -79,6 +79,8 @@ int r3d_debug_liop_process(r3d_ctx* ctx, const float* patches, uint32_t n, float
 #define R3D_MATCH_DEFAULT 0u
 #define R3D_MATCH_EXACT_SCAN 1u   /* skip the tensor-core candidate pass: CUDA-core exact scan only */
 #define R3D_MATCH_NO_COORD_DEDUP 2u /* skip IndMatchDecorator (for callers without positions) */
+#define R3D_MATCH_MUTUAL_NN 4u    /* OFF by default and NOT reference behaviour (MatchDistanceRatio has no cross-check):
+                                   * keep (i, j) only if j is also i's nearest neighbour among J's descriptors */
 
 /* Replaces Matcher_Regions(fDistRatio, BRUTE_FORCE_L2)::Match(regions_provider, pairs, out)
  * (src/R3DComputeMatches.cpp:2039, :2048; loop shape :437-488): for every pair (I,J): 2-NN of each
@@ -297,6 +299,8 @@ typedef struct {
   int compute_homography;         /* R3DFParams::computeHomographyMatrix_ -> matches.h.txt */
   int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher */
   uint32_t descriptor_dim;        /* 144 for R3D_AKAZE_LIOP_Regions */
+  int svg_output;                 /* computeMatches(..., bool svgOutput, ...): PutativeAdjacencyMatrix.svg and
+                                   * GeometricAdjacencyMatrix.svg in the matches dir (:2074-2076, :2238-2240) */
 } r3d_cm_params;
 
 typedef struct {

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libr3dgpu.so")
 
 R3D_F32, R3D_U8 = 0, 1
-MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP = 0, 1, 2
+MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP, MATCH_MUTUAL_NN = 0, 1, 2, 4
 MODEL_F, MODEL_E, MODEL_H = 0, 1, 2
 
 indmatch_dtype = np.dtype([("i", np.uint32), ("j", np.uint32)])
@@ -97,7 +97,8 @@ class BASummary(C.Structure):
 
 class CMParams(C.Structure):
     _fields_ = [("dist_ratio", C.c_float), ("compute_fundamental", C.c_int), ("compute_essential", C.c_int),
-                ("compute_homography", C.c_int), ("matching_algorithm", C.c_int), ("descriptor_dim", C.c_uint32)]
+                ("compute_homography", C.c_int), ("matching_algorithm", C.c_int), ("descriptor_dim", C.c_uint32),
+                ("svg_output", C.c_int)]
 
 
 class CMPaths(C.Structure):
@@ -610,12 +611,12 @@ class Context:
 
     def compute_matches(self, matches_dir, basenames, widths, heights, dist_ratio=0.6, dim=144,
                         compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None,
-                        compute_homography=False, compute_essential=False, Ks=None):
+                        compute_homography=False, compute_essential=False, Ks=None, svg_output=False):
         n = len(basenames)
         names = (C.c_char_p * n)(*[b.encode() for b in basenames])
         views = make_views(widths, heights, Ks)
         params = CMParams(dist_ratio, int(compute_fundamental), int(compute_essential), int(compute_homography),
-                          matching_algorithm, dim)
+                          matching_algorithm, dim, int(svg_output))
         paths = CMPaths(matches_dir.encode(), names, views, n, f_filename.encode() if f_filename else None, None, None)
         kp = (C.c_uint32 * n)()
         stats = CMStats()

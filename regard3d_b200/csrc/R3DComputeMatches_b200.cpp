@@ -49,7 +49,7 @@ void R3DComputeMatches::updateProgress(float progress, const std::string& msg) {
   if (progressSink_) progressSink_(progress, msg);
 }
 
-bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, const R3DProjectPaths& paths,
+bool R3DComputeMatches::computeMatches(R3DFParams& params, bool svgOutput, const R3DProjectPaths& paths,
                                        int /*cameraModel*/, int matchingAlgorithm) {
   if (!ctx_) return false;
   const uint32_t n = (uint32_t)imageInfoVector_.size();
@@ -75,6 +75,7 @@ bool R3DComputeMatches::computeMatches(R3DFParams& params, bool /*svgOutput*/, c
   p.compute_homography = params.computeHomographyMatrix_ ? 1 : 0;
   p.matching_algorithm = matchingAlgorithm;
   p.descriptor_dim = 144;
+  p.svg_output = svgOutput ? 1 : 0;
   r3d_cm_paths cp;
   cp.matches_dir = paths.relativeMatchesPath_.c_str();
   cp.image_basenames = base_ptrs.data();

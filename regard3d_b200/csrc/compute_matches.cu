@@ -53,6 +53,43 @@ bool load_desc(const std::string& path, uint32_t dim, std::vector<float>& d, uin
 
 using namespace r3d;
 
+// PairWiseMatchingToAdjacencyMatrixSVG (upstream graph_stats / svgDrawer; called at src/R3DComputeMatches.cpp:2074,
+// :2238): an N x N grid, one blue square per pair that has matches (column J, row I), and the two 0..N axes.
+static bool write_adjacency_svg(uint32_t n_images, const r3d_matches* m, const std::string& path) {
+  if (!m || r3d_matches_num_pairs(m) == 0) return true;  // upstream writes nothing for an empty map
+  const float scale = 5.0f;
+  std::ofstream f(path.c_str());
+  if (!f.is_open()) return false;
+  const float W = (float)(n_images + 3) * 5.0f;
+  f << "<?xml version=\"1.0\" standalone=\"yes\"?>\n<!-- SVG graphic -->\n<svg xmlns='http://www.w3.org/2000/svg'"
+    << " width=\"" << W << "px\" height=\"" << W << "px\" preserveAspectRatio=\"xMinYMin meet\" viewBox=\"0 0 " << W << ' ' << W
+    << "\" version=\"1.1\">\n";
+  const uint64_t P = r3d_matches_num_pairs(m);
+  for (uint64_t k = 0; k < P; ++k) {
+    uint32_t I, J;
+    uint64_t cnt;
+    r3d_matches_get_pair(m, k, &I, &J, nullptr, &cnt);
+    if (!cnt || I >= n_images || J >= n_images) continue;
+    f << "<rect x=\"" << J * scale << "\" y=\"" << I * scale << "\" width=\"" << scale / 2.0f << "\" height=\"" << scale / 2.0f
+      << "\" fill=\"blue\"><title>(" << J << ',' << I << ' ' << cnt << ")</title></rect>\n";
+  }
+  const float a = (float)(n_images + 1) * scale, b = (float)n_images * scale;
+  auto text = [&](float x, float y, const std::string& t) {
+    f << "<text x=\"" << x << "\" y=\"" << y << "\" font-size=\"" << scale << "\" fill=\"black\">" << t << "</text>\n";
+  };
+  auto line = [&](float x0, float y0, float x1, float y1) {
+    f << "<polyline points=\"" << x0 << ',' << y0 << ' ' << x1 << ',' << y1 << "\" stroke=\"black\" stroke-width=\"1\"/>\n";
+  };
+  text(a, scale, "0");
+  text(a, b - scale, std::to_string(n_images));
+  line(a, 2 * scale, a, b - 2 * scale);
+  text(scale, a, "0");
+  text(b - scale, a, std::to_string(n_images));
+  line(2 * scale, a, b - 2 * scale, a);
+  f << "</svg>\n";
+  return f.good();
+}
+
 extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, const r3d_cm_paths* paths,
                                    r3d_progress_cb cb, void* user, r3d_cm_stats* stats) {
   if (!ctx || !params || !paths || !paths->matches_dir || !paths->image_basenames || !paths->views)
@@ -101,6 +138,7 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
   }
   rc = r3d_save_matches_txt(put, (dir + "/matches.putative.txt").c_str());
   if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save matches.putative.txt"); }
+  if (params->svg_output) write_adjacency_svg(N, put, dir + "/PutativeAdjacencyMatrix.svg");  // :2074-2076
   // ---- geometric filtering -------------------------------------------------------------------------
   if (params->compute_fundamental) {
     if (cb) cb(0.8f, "Calculate fundamental matrix", user);
@@ -115,6 +153,7 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
     }
     const std::string fpath = paths->matches_f_filename ? std::string(paths->matches_f_filename) : dir + "/matches.f.txt";
     rc = r3d_save_matches_txt(fm, fpath.c_str());
+    if (params->svg_output) write_adjacency_svg(N, fm, dir + "/GeometricAdjacencyMatrix.svg");  // :2238-2240
     r3d_free_matches(fm);
     if (rc) { r3d_free_matches(put); return fail(ctx, R3D_ERR_IO, "r3d_compute_matches: cannot save " + fpath); }
   }

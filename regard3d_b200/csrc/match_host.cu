@@ -469,9 +469,60 @@ using namespace r3d;
 
 extern "C" {
 
+static int match_pairs_impl(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio, uint32_t flags,
+                            r3d_matches** out);
+
 int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio, uint32_t flags,
                     r3d_matches** out) {
   if (!ctx || !out || (n_pairs && !pairs)) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: bad arguments");
+  *out = nullptr;
+  if (!(flags & R3D_MATCH_MUTUAL_NN)) return match_pairs_impl(ctx, pairs, n_pairs, dist_ratio, flags, out);
+  // Optional mutual-nearest-neighbour select (north_star; NOT part of the reference's MatchDistanceRatio):
+  // a match (i in I, j in J) of the forward pass survives iff j is also the nearest neighbour of i among J's
+  // descriptors.  Second pass = the same matcher on the swapped pairs with the ratio test disabled.
+  r3d_matches* fwd = nullptr;
+  int rc = match_pairs_impl(ctx, pairs, n_pairs, dist_ratio, flags & ~R3D_MATCH_MUTUAL_NN, &fwd);
+  if (rc) return rc;
+  const r3d_match_timing t_fwd = ctx->match_timing;
+  std::vector<uint32_t> rev_pairs(2 * n_pairs);
+  for (uint64_t p = 0; p < n_pairs; ++p) { rev_pairs[2 * p] = pairs[2 * p + 1]; rev_pairs[2 * p + 1] = pairs[2 * p]; }
+  r3d_matches* rev = nullptr;
+  rc = match_pairs_impl(ctx, rev_pairs.data(), n_pairs, 1e18f, (flags & R3D_MATCH_EXACT_SCAN) | R3D_MATCH_NO_COORD_DEDUP, &rev);
+  if (rc) { r3d_free_matches(fwd); return rc; }
+  std::map<std::pair<uint32_t, uint32_t>, uint64_t> rev_of;
+  for (uint64_t k = 0; k < rev->pairs.size() / 2; ++k) rev_of[{rev->pairs[2 * k], rev->pairs[2 * k + 1]}] = k;
+  r3d_matches* m = new r3d_matches();
+  std::vector<uint32_t> nn_in_J;
+  for (uint64_t k = 0; k < fwd->pairs.size() / 2; ++k) {
+    const uint32_t I = fwd->pairs[2 * k], J = fwd->pairs[2 * k + 1];
+    auto it = rev_of.find({J, I});
+    if (it == rev_of.end()) continue;
+    // rev entry (i_ = feature of J, j_ = feature of I): the nearest neighbour in J of I's feature j_
+    const r3d_span& rs = rev->per[it->second];
+    uint32_t maxi = 0;
+    for (const r3d_indmatch& e : rs) maxi = std::max(maxi, e.j);
+    nn_in_J.assign((size_t)maxi + 1, 0xffffffffu);
+    for (const r3d_indmatch& e : rs) nn_in_J[e.j] = e.i;
+    std::vector<r3d_indmatch> keep;
+    for (const r3d_indmatch& e : fwd->per[k])
+      if (e.i <= maxi && nn_in_J[e.i] == e.j) keep.push_back(e);
+    if (!keep.empty()) m->push(I, J, std::move(keep));
+  }
+  r3d_free_matches(fwd);
+  r3d_free_matches(rev);
+  {  // both passes count
+    r3d_match_timing& t = ctx->match_timing;
+    t.ms_candidates += t_fwd.ms_candidates; t.ms_rerank += t_fwd.ms_rerank; t.ms_fallback += t_fwd.ms_fallback;
+    t.ms_device_total += t_fwd.ms_device_total; t.ms_host_post += t_fwd.ms_host_post; t.kernel_launches += t_fwd.kernel_launches;
+    t.queries += t_fwd.queries; t.fallback_queries += t_fwd.fallback_queries; t.rejected_queries += t_fwd.rejected_queries;
+    t.h2d_bytes += t_fwd.h2d_bytes; t.d2h_bytes += t_fwd.d2h_bytes;
+  }
+  *out = m;
+  return R3D_OK;
+}
+
+static int match_pairs_impl(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio, uint32_t flags,
+                            r3d_matches** out) {
   *out = nullptr;
   const double t_call = now_ms();
   const uint64_t h2d_uploads = ctx->pending_h2d;  // uploads since the previous call belong to this one

@@ -98,3 +98,12 @@ def test_missing_region_file_is_an_error(gpu_ctx, r3dlib, tmp_path):
     with pytest.raises(r3dlib.R3DError) as e:
         gpu_ctx.compute_matches(str(tmp_path), ["image000000", "image000001"], [640, 640], [480, 480])
     assert e.value.code == -4
+
+
+def test_compute_matches_svg_output(gpu_ctx, oracle, tmp_path):
+    """computeMatches(..., svgOutput = true, ...): the two adjacency-matrix SVGs (src/R3DComputeMatches.cpp:2074, :2238)."""
+    sc, names = _write_project(oracle, tmp_path, n_img=3, n_feat=800)
+    gpu_ctx.compute_matches(str(tmp_path), names, sc["widths"], sc["heights"], dist_ratio=0.6, dim=144, svg_output=True)
+    for name in ("PutativeAdjacencyMatrix.svg", "GeometricAdjacencyMatrix.svg"):
+        txt = (tmp_path / name).read_text()
+        assert txt.startswith("<?xml") and txt.rstrip().endswith("</svg>") and txt.count("<rect") == 3   # pairs (0,1) (0,2) (1,2)

@@ -154,3 +154,22 @@ def test_descriptors_outside_the_fp16_operand_range_take_the_exact_scan(gpu_ctx,
     got = dict_sets(gpu_ctx.match_pairs(pairs, 0.8).to_dict())
     assert got == match_sets(ofs, m, pairs) and sum(len(s) for s in got.values()) > 100
     gpu_ctx.clear_regions()
+
+
+def test_mutual_nn_flag(gpu_ctx, oracle, r3dlib):
+    """R3D_MATCH_MUTUAL_NN (off by default; not reference behaviour): forward ratio matches whose I-feature also has the
+    J-feature as ITS nearest neighbour -- checked against the oracle's SearchNeighbours in both directions."""
+    sc = synth.make_scene(3, 1200, 64, "msurf", seed=21)
+    pairs = synth.exhaustive_pairs(3)
+    _upload(gpu_ctx, sc)
+    plain = gpu_ctx.match_pairs(pairs, 0.7).to_dict()
+    mutual = gpu_ctx.match_pairs(pairs, 0.7, r3dlib.MATCH_MUTUAL_NN).to_dict()
+    n_plain = n_mut = 0
+    for (I, J), m in plain.items():
+        idx, _ = oracle.search_neighbours(sc["descs"][J], sc["descs"][I])          # for every i of I: its 2-NN in J
+        want = [(int(i), int(j)) for i, j in zip(m["i"], m["j"]) if idx[i, 0] == j]
+        got = mutual.get((I, J))
+        got = [] if got is None else list(zip(got["i"].tolist(), got["j"].tolist()))
+        assert got == want, (I, J)
+        n_plain += len(m); n_mut += len(want)
+    assert 0 < n_mut < n_plain
