@@ -1,6 +1,6 @@
 // k_l2_candidates_2sm.cu -- the candidate kernel on CTA PAIRS (tcgen05 cta_group::2).
 //
-// Why: the single-CTA kernel (k_l2_candidates.cu) is bound by shared-memory operand reads: an
+// Why: a single-CTA kernel (round 1, removed; profiles/r01_k_l2_candidates_1sm_hunt.md) is bound by shared-memory operand reads: an
 // M128 x N128 x K16 SS-MMA fetches 8 KB per 64 tensor cycles = the 128 B/clk port
 // (profiles/r01_k_l2_candidates.md).  With cta_group::2 one instruction computes M = 256: each SM of
 // the pair contributes its own 128 query rows (A) and HALF of the database tile (B, 128 of 256

@@ -234,24 +234,9 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     for (uint32_t k = 0; k < nb; ++k) (*hp)[k] = all[b0 + k].pd;
     auto hitems = std::make_shared<std::vector<WorkItem>>();
     hitems->reserve(2 * n_items + nb);
-    static const int kCluster = []() {
-      const char* e = getenv("R3D_K1_CLUSTER");
-      return (e && atoi(e) == 1) ? 1 : 2;
-    }();
-    static const bool k2sm = []() {
-      const char* e = getenv("R3D_K1_MODE");  // "1sm": single-CTA kernel (k_l2_candidates.cu); default: CTA pairs
-      return !(e && std::string(e) == "1sm");
-    }();
-    for (uint32_t k = 0; k < nb && k2sm; ++k)
+    for (uint32_t k = 0; k < nb; ++k)
       if ((*hp)[k].use_tc)  // CTA-pair kernel: 128-query blocks; n_pad is a multiple of 256 -> always an even count per pair
         for (uint32_t qb = 0; qb < (*hp)[k].nJ_pad / kTileRows; ++qb) hitems->push_back(WorkItem{k, qb});
-    for (uint32_t k = 0; k < nb && !k2sm; ++k)
-      if ((*hp)[k].use_tc) {
-        const uint32_t nsb = (*hp)[k].nJ_pad / kSuperRows;
-        for (uint32_t sb = 0; sb < nsb; ++sb) hitems->push_back(WorkItem{k, sb});
-        // a 2-CTA cluster works on two super-blocks of ONE pair: pad odd counts with a no-store item
-        if (kCluster == 2 && (nsb & 1u)) hitems->push_back(WorkItem{k, 0x80000000u});
-      }
     const bool any_tc = !hitems->empty();
 
     const int sl = (int)(batch_no & 1u);
@@ -299,12 +284,8 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
 
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[0], w.stream));
     if (any_tc) {
-      if (k2sm)
-        rc = launch_l2_candidates_2sm(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items, (uint32_t)hitems->size(),
-                                      (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim));
-      else
-        rc = launch_l2_candidates(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items, (uint32_t)hitems->size(),
-                                  (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim), kCluster);
+      rc = launch_l2_candidates_2sm(ctx, w, (const PairDesc*)w.d_pairs, (const WorkItem*)w.d_items, (uint32_t)hitems->size(),
+                                    (uint32_t*)w.d_keys, kp, operand_ksteps((int)dim));
       if (rc) return rc;
       launches += 1;
     }

@@ -18,7 +18,7 @@
 #include "r3d_matches.h"
 
 // ------------------------------------------------------------------------------------------------
-// Geometry of the tensor-core candidate kernel (k_l2_candidates.cu) and the operand layout.
+// Geometry of the tensor-core candidate kernel (k_l2_candidates_2sm.cu) and the operand layout.
 // ------------------------------------------------------------------------------------------------
 namespace r3d {
 
@@ -196,11 +196,8 @@ inline void parallel_for(int n_threads, size_t n, F&& f) {
 // operand preparation
 int launch_view_stats(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v);
 int launch_view_prepare(r3d_ctx* ctx, DeviceWorker& w, ViewDev& v, int e0);
-// tensor-core candidate kernel
-int launch_l2_candidates(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
-                         uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps, int cluster);
-size_t l2_candidates_smem_bytes(int kp_cols);
-// CTA-pair variant (tcgen05 cta_group::2): work items are 128-query blocks, two consecutive items share a pair
+// tensor-core candidate kernel: persistent CTA pairs (tcgen05 cta_group::2); work items are 128-query blocks, two
+// consecutive items share a pair
 int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs, const WorkItem* d_items,
                              uint32_t n_items, uint32_t* d_keys, int kp_cols, int ksteps);
 // exact re-rank + ratio
