@@ -23,6 +23,7 @@
 #include "acransac_rng.cuh"
 
 #include <random>
+#include <type_traits>
 
 namespace r3d {
 
@@ -30,7 +31,9 @@ namespace {
 
 constexpr int kFThreads = 256;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kBatch = 16;            // iterations drawn, solved and tier-1-scored ahead
+constexpr int kBatch = 32;            // most iterations drawn, solved and tier-1-scored ahead (the batch grows with the
+                                      // number of iterations since the last pool replacement: 4, 5, ... kBatch)
+constexpr double kApproxRel = 1e-9;   // relative accuracy of the tier-1 residuals (see approx_error)
 constexpr int kBins = 1024;           // tier-1 histogram: binades split in 32 (exponent + 5 mantissa bits)
 constexpr int kBinShift = 52 - 5;
 
@@ -43,7 +46,8 @@ struct FusedSmem {                    // fixed part of the shared memory (the so
   double bestF[9];
   double s_nfa[kFWarps];
   uint32_t s_k[kFWarps];
-  uint32_t cnt[kBatch][ac_max_models(MODEL)];
+  uint32_t cnt[kBatch][ac_max_models(MODEL)];      // residuals that may be <= the bound (upper count)
+  uint32_t cnt_lo[kBatch][ac_max_models(MODEL)];   // residuals that certainly are (lower count)
   uint32_t nm[kBatch];
   uint32_t sample[kBatch][8];
   uint32_t used[kBatch];              // generator outputs consumed up to and including iteration b of the batch
@@ -57,21 +61,105 @@ __device__ __forceinline__ double model_error(const double* F, const double2 a, 
                     : MODEL == 1 ? asym_error(F, a.x, a.y, b.x, b.y) : epi_dist_error(F, a.x, a.y, b.x, b.y);
 }
 
+// ---- tier-1 residuals: fused multiply-adds, one reciprocal instead of IEEE divisions ---------------------------
+// Tier 1 only BOUNDS the exact computation, so it need not reproduce the reference's rounding.  approx_bounds()
+// returns an interval [*lo, *hi] that contains the residual the tier-2 / CPU code computes (the same rational
+// function of the same inputs, rounded differently):
+//   * the cancelling term (x2^T F x1 for the epipolar errors, x2 - H x1 for the transfer error) carries an ABSOLUTE
+//     error eta = 64 ulp x (largest model entry) x (2 R + 1)^2, R = the pair's largest |coordinate|: both evaluations
+//     stay within that of the exact value (<= 12 roundings of terms bounded by that magnitude);
+//   * everything else is cancellation-free: relative error <= kApproxRel (2^-53 per operation; the reciprocal is
+//     rcp.approx + one Newton step, ~2^-40).
+// Degenerate inputs (reciprocal argument outside [1e-280, 1e280], NaN) give [0, +inf): "may or may not be an inlier".
+__device__ __forceinline__ double rcp_fast(double x, bool* ok) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+  const double ax = fabs(x);
+  if (!(ax > 1e-280 && ax < 1e280)) *ok = false;
+  return r;
+}
+
+template <int MODEL>
+__device__ __forceinline__ void approx_bounds(const double* F, double eta, const double2 a, const double2 b, double* lo, double* hi) {
+  bool ok = true;
+  double l, h;
+  if (MODEL == 1) {  // asymmetric transfer error of a homography: |x2 - (H x1)_xy / (H x1)_w|^2
+    const double hx = __fma_rn(F[0], a.x, __fma_rn(F[1], a.y, F[2]));
+    const double hy = __fma_rn(F[3], a.x, __fma_rn(F[4], a.y, F[5]));
+    const double hw = __fma_rn(F[6], a.x, __fma_rn(F[7], a.y, F[8]));
+    const double iw = rcp_fast(hw, &ok);
+    const double ex = fabs(__fma_rn(-hx, iw, b.x)), ey = fabs(__fma_rn(-hy, iw, b.y));
+    // eta bounds the absolute error of hx, hy, hw; propagated through the quotient (|hw| >> eta or the point is flagged)
+    const double aiw = fabs(iw);
+    const double q = eta * aiw;                                  // relative error of hw
+    if (!(q < 1e-3)) ok = false;
+    const double dx = eta * aiw + fabs(hx * iw) * q * 1.01 + 4e-16 * (fabs(b.x) + fabs(hx * iw));
+    const double dy = eta * aiw + fabs(hy * iw) * q * 1.01 + 4e-16 * (fabs(b.y) + fabs(hy * iw));
+    const double lx = fmax(ex - dx, 0.0), ly = fmax(ey - dy, 0.0), ux = ex + dx, uy = ey + dy;
+    l = __fma_rn(lx, lx, ly * ly) * (1.0 - kApproxRel);
+    h = __fma_rn(ux, ux, uy * uy) * (1.0 + kApproxRel);
+  } else {
+    const double Fx0 = __fma_rn(F[0], a.x, __fma_rn(F[1], a.y, F[2]));
+    const double Fx1 = __fma_rn(F[3], a.x, __fma_rn(F[4], a.y, F[5]));
+    const double Fx2 = __fma_rn(F[6], a.x, __fma_rn(F[7], a.y, F[8]));
+    const double y = fabs(__fma_rn(b.x, Fx0, __fma_rn(b.y, Fx1, Fx2)));
+    const double A = __fma_rn(Fx0, Fx0, Fx1 * Fx1);
+    double K;  // the cancellation-free factor
+    if (MODEL == 2) {
+      K = rcp_fast(A, &ok);                                      // one-sided epipolar distance: y^2 / A
+    } else {
+      const double Fty0 = __fma_rn(F[0], b.x, __fma_rn(F[3], b.y, F[6]));
+      const double Fty1 = __fma_rn(F[1], b.x, __fma_rn(F[4], b.y, F[7]));
+      const double B = __fma_rn(Fty0, Fty0, Fty1 * Fty1);
+      K = 0.25 * (A + B) * rcp_fast(A * B, &ok);                 // (1/A + 1/B) / 4
+    }
+    const double yl = fmax(y - eta, 0.0), yh = y + eta;
+    l = yl * yl * K * (1.0 - kApproxRel);
+    h = yh * yh * K * (1.0 + kApproxRel);
+  }
+  if (!ok || !(l <= h)) {  // also catches NaN
+    l = 0.0;
+    h = DBL_MAX * 2.0;
+  }
+  *lo = l;
+  *hi = h;
+}
+
 }  // namespace
 
 size_t acransac_fused_smem_bytes(int model, uint32_t cap, bool huge) {
   const size_t fixed = model == 0 ? sizeof(FusedSmem<0>) : (model == 1 ? sizeof(FusedSmem<1>) : sizeof(FusedSmem<2>));
   const size_t hist = (size_t)kFWarps * kBins * sizeof(uint32_t);
-  const size_t sortb = huge ? 0 : (size_t)cap * 12;
-  const size_t pool = huge ? 0 : (size_t)cap * 4;
+  const size_t sortb = huge ? 0 : (size_t)cap * 8;  // residual values; the index array of the inlier sort is global
+  const size_t pool = huge ? 0 : (size_t)cap * 2;   // 16-bit pool entries
   return ((fixed + 15) & ~(size_t)15) + std::max(hist, sortb) + pool;
 }
 
+// exact count of the residuals <= the precision bound (the classic-RANSAC phase needs it exactly; tier 1 brackets it)
+template <int MODEL>
+__device__ uint32_t exact_count(const AcPair& pr, const double2* __restrict__ p1, const double2* __restrict__ p2, const double* Fm,
+                                uint32_t* s_count) {
+  if (threadIdx.x == 0) *s_count = 0;
+  __syncthreads();
+  uint32_t c = 0;
+  for (uint32_t i = threadIdx.x; i < pr.M; i += blockDim.x)
+    if (model_error<MODEL>(Fm, p1[i], p2[i]) <= pr.max_thr) ++c;
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31u) == 0 && c) atomicAdd(s_count, c);
+  __syncthreads();
+  c = *s_count;
+  __syncthreads();
+  return c;
+}
+
 // One persistent CTA per image pair.  order[]: the pairs of this launch (one size class), largest first.
-// HUGE: sort buffers and sampling pool in global scratch (g_se / g_si / g_pool, `cap` entries per CTA) instead of
-// shared memory -- the slow-but-correct path for pairs with more putative matches than shared memory can sort.
+// Shared memory: the fixed block, then one region used by tier 1 (a histogram per warp) and by tier 2 (the residual
+// values being sorted), then the sampling pool (16-bit entries).  g_si: `cap` uint32 per CTA, the index array of the
+// (rare) inlier sorts.  HUGE: values and pool too live in global scratch (g_se / g_pool) -- the slow-but-correct path
+// for pairs with more putative matches than shared memory can sort.
 template <int MODEL, bool HUGE>
-__global__ void __launch_bounds__(kFThreads) k_acransac_fused(
+__global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fused(
     const AcPair* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t n_order, uint32_t* __restrict__ work_counter,
     const double2* __restrict__ x1, const double2* __restrict__ x2, const float* __restrict__ logc_n,
     const float* __restrict__ logc_k, uint32_t cap, uint32_t max_iter, double* __restrict__ g_se, uint32_t* __restrict__ g_si,
@@ -79,15 +167,16 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
     AcFusedOut* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr uint32_t NS = ac_min_samples(MODEL), MAXM = ac_max_models(MODEL);
+  typedef typename std::conditional<HUGE, uint32_t, uint16_t>::type PoolT;
   const double mult_error = MODEL == 1 ? 1.0 : 0.5;
   FusedSmem<MODEL>& S = *reinterpret_cast<FusedSmem<MODEL>*>(smem_raw);
   unsigned char* region = smem_raw + ((sizeof(FusedSmem<MODEL>) + 15) & ~(size_t)15);
   uint32_t* hist_all = reinterpret_cast<uint32_t*>(region);                 // tier 1: kFWarps x kBins
-  const size_t region_bytes = HUGE ? (size_t)kFWarps * kBins * 4
-                                   : ((size_t)cap * 12 > (size_t)kFWarps * kBins * 4 ? (size_t)cap * 12 : (size_t)kFWarps * kBins * 4);
+  const size_t hist_bytes = (size_t)kFWarps * kBins * 4;
+  const size_t region_bytes = HUGE ? hist_bytes : ((size_t)cap * 8 > hist_bytes ? (size_t)cap * 8 : hist_bytes);
   double* se = HUGE ? g_se + (size_t)blockIdx.x * cap : reinterpret_cast<double*>(region);   // tier 2 (aliases hist)
-  uint32_t* si = HUGE ? g_si + (size_t)blockIdx.x * cap : reinterpret_cast<uint32_t*>(se + cap);
-  uint32_t* pool = HUGE ? g_pool + (size_t)blockIdx.x * cap : reinterpret_cast<uint32_t*>(region + region_bytes);
+  uint32_t* si = g_si + (size_t)blockIdx.x * cap;
+  PoolT* pool = HUGE ? reinterpret_cast<PoolT*>(g_pool + (size_t)blockIdx.x * cap) : reinterpret_cast<PoolT*>(region + region_bytes);
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
 
   for (;;) {
@@ -103,8 +192,15 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
     const double2* p1 = x1 + pr.pt_ofs;
     const double2* p2 = x2 + pr.pt_ofs;
 
-    // ---- per-pair set-up: sampling pool, generator, bin edges ---------------------------------------------
-    for (uint32_t i = tid; i < M; i += kFThreads) pool[i] = i;
+    // ---- per-pair set-up: sampling pool, generator, bin edges, coordinate bound --------------------------------
+    double rmax = 0.0;
+    for (uint32_t i = tid; i < M; i += kFThreads) {
+      pool[i] = (PoolT)i;
+      const double2 a = p1[i], b = p2[i];
+      rmax = fmax(rmax, fmax(fmax(fabs(a.x), fabs(a.y)), fmax(fabs(b.x), fabs(b.y))));
+    }
+    for (int o = 16; o >= 1; o >>= 1) rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    if (lane == 0) S.s_nfa[warp] = rmax;
     // bin(e) = clamp((bits(e) >> kBinShift) - bin_base, 0, kBins - 1): the precision bound falls in the top bin
     const long long thr_key = __double_as_longlong(pr.max_thr) >> kBinShift;
     const long long bin_base = thr_key - (kBins - 1);
@@ -114,17 +210,21 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
       S.la[b] = pr.logalpha0 + mult_error * dm::log10_det(lo + (double)FLT_EPSILON);
     }
     if (tid == 0) mt_seed(S.rng);
+    __syncthreads();
+    for (uint32_t wv = 0; wv < (uint32_t)kFWarps; ++wv) rmax = fmax(rmax, S.s_nfa[wv]);
+    const double coord_span = (2.0 * rmax + 1.0) * (2.0 * rmax + 1.0);
     // ACRANSAC state, replicated in the registers of every thread (updated identically from shared data)
     uint32_t iter = 0, nIterReserve = max_iter / 10, nIter = max_iter - nIterReserve;
     bool ac_mode = !(pr.max_thr < DBL_MAX);  // bACRansacMode = (precision == infinity)
     double minNFA = DBL_MAX * 2.0, errorMax = DBL_MAX * 2.0;
-    uint32_t best_k = 0, pool_size = M;
+    uint32_t best_k = 0, pool_size = M, since_event = 0;
     bool have_inliers = false;
     uint32_t n_exact = 0, n_models = 0, n_events = 0;
     __syncthreads();
 
     while (iter < nIter) {
-      const uint32_t B = min((uint32_t)kBatch, nIter - iter);
+      // speculation depth: short right after a pool replacement (improving models come in bursts), longer later
+      const uint32_t B = min(min((uint32_t)kBatch, 4u + since_event), nIter - iter);
       // ---- 1. snapshot the generator, draw B samples (UniformSample: partial Fisher-Yates on the pool) ----
       {
         uint32_t* dst = reinterpret_cast<uint32_t*>(&S.snap);
@@ -138,66 +238,75 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
         for (uint32_t b = 0; b < B; ++b) {
           for (uint32_t i = 0; i < NS; ++i) {
             const uint32_t r = uniform_u32(S.rng, i, last_idx, &used);
-            const uint32_t t = pool[i]; pool[i] = pool[r]; pool[r] = t;
+            const PoolT t = pool[i]; pool[i] = pool[r]; pool[r] = t;
           }
           for (uint32_t i = 0; i < NS; ++i) S.sample[b][i] = pool[i];
           S.used[b] = used;
         }
       }
       __syncthreads();
-      // ---- 2. minimal solver: one thread per iteration of the batch --------------------------------------
-      if (tid < B) {
-        double models[9 * MAXM];
-        int nm;
-        if (MODEL == 2) {
-          double b1[15], b2[15], Es[90];
-          for (int t = 0; t < 5; ++t) {
-            const double2 a = p1[S.sample[tid][t]];
-            const double2 b = p2[S.sample[tid][t]];
-            bearing(pr.K, a.x, a.y, b1 + 3 * t);
-            bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
+      // ---- 2. minimal solver: one thread per iteration of the batch (one per warp first: no lock-step penalty) ----
+      {
+        const uint32_t slot = (lane * kFWarps + warp);  // thread -> iteration: spread over the warps
+        if (slot < B && lane < (kBatch + kFWarps - 1) / kFWarps) {
+          double models[9 * MAXM];
+          int nm;
+          if (MODEL == 2) {
+            double b1[15], b2[15], Es[90];
+            for (int t = 0; t < 5; ++t) {
+              const double2 a = p1[S.sample[slot][t]];
+              const double2 b = p2[S.sample[slot][t]];
+              bearing(pr.K, a.x, a.y, b1 + 3 * t);
+              bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
+            }
+            nm = fp::five_point(b1, b2, Es);
+            for (int mi = 0; mi < nm; ++mi) fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, models + 9 * mi);
+          } else {
+            double s1[14], s2[14];
+            for (uint32_t t = 0; t < NS; ++t) {
+              const double2 a = p1[S.sample[slot][t]];
+              const double2 b = p2[S.sample[slot][t]];
+              s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
+              s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
+            }
+            nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
           }
-          nm = fp::five_point(b1, b2, Es);
-          for (int mi = 0; mi < nm; ++mi) fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, models + 9 * mi);
-        } else {
-          double s1[14], s2[14];
-          for (uint32_t t = 0; t < NS; ++t) {
-            const double2 a = p1[S.sample[tid][t]];
-            const double2 b = p2[S.sample[tid][t]];
-            s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
-            s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
-          }
-          nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
+          S.nm[slot] = (uint32_t)nm;
+          for (int mi = 0; mi < nm; ++mi)
+            for (int t = 0; t < 9; ++t) S.models[slot][mi][t] = models[9 * mi + t];
         }
-        S.nm[tid] = (uint32_t)nm;
-        for (int mi = 0; mi < nm; ++mi)
-          for (int t = 0; t < 9; ++t) S.models[tid][mi][t] = models[9 * mi + t];
       }
       __syncthreads();
-      // ---- 3. tier 1: one warp per model -- count, histogram, lower bound of the best NFA ------------------
+      // ---- 3. tier 1: one warp per model -- bracketed count, histogram, lower bound of the best NFA ------------
       {
         uint32_t* hist = hist_all + (size_t)warp * kBins;
         for (uint32_t slot = warp; slot < B * MAXM; slot += kFWarps) {
           const uint32_t b = slot / MAXM, mi = slot % MAXM;
           if (mi >= S.nm[b]) continue;
-          double Fm[9];
-          for (int t = 0; t < 9; ++t) Fm[t] = S.models[b][mi][t];
+          double Fm[9], fmax_abs = 0.0;
+          for (int t = 0; t < 9; ++t) { Fm[t] = S.models[b][mi][t]; fmax_abs = fmax(fmax_abs, fabs(Fm[t])); }
+          const double eta = 7.2e-15 * fmax_abs * coord_span;  // 64 ulp x the largest term of x2^T F x1 (or H x1)
           for (uint32_t i = lane; i < (uint32_t)kBins; i += 32) hist[i] = 0;
           __syncwarp();
-          uint32_t c = 0;
+          uint32_t c_hi = 0, c_lo = 0;
           for (uint32_t i = lane; i < M; i += 32) {
-            const double e = model_error<MODEL>(Fm, p1[i], p2[i]);
-            if (e <= pr.max_thr) {  // false for NaN
-              long long bin = (__double_as_longlong(e) >> kBinShift) - bin_base;
+            double elo, ehi;
+            approx_bounds<MODEL>(Fm, eta, p1[i], p2[i], &elo, &ehi);
+            if (elo <= pr.max_thr) {  // may be an inlier of the precision bound
+              long long bin = (__double_as_longlong(elo) >> kBinShift) - bin_base;
               bin = bin < 0 ? 0 : (bin > kBins - 1 ? kBins - 1 : bin);
               atomicAdd(&hist[bin], 1u);
-              ++c;
+              ++c_hi;
+              if (ehi <= pr.max_thr) ++c_lo;
             }
           }
-          for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+          for (int o = 16; o >= 1; o >>= 1) {
+            c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o);
+            c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o);
+          }
           __syncwarp();
           double lbv = DBL_MAX * 2.0;
-          if (c > NS) {
+          if (c_hi > NS) {
             // exclusive prefix over the bins, 32 at a time (conflict-free rows + a running carry)
             uint32_t carry = 0;
             for (uint32_t j = 0; j < (uint32_t)kBins; j += 32) {
@@ -211,10 +320,12 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
               carry += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
-            // ranks (lo, hi] live in bin bb: NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]
+            // ranks (lo, hi] live in bin bb.  With e_(k) the true k-th smallest residual: at least k of the lower
+            // bounds are <= e_(k), so the k-th smallest LOWER BOUND is <= e_(k), hence
+            // NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]; extra ranks (c_hi >= c) only lower the minimum
             for (uint32_t bb = lane; bb < (uint32_t)kBins; bb += 32) {
               const uint32_t lo = hist[bb];
-              const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : c;
+              const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : c_hi;
               const double la = S.la[bb];
               for (uint32_t k = max(lo + 1, NS + 1); k <= hi; ++k) {
                 const double g = pr.loge0 + la * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
@@ -228,7 +339,7 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
             // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
             lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
           }
-          if (lane == 0) { S.cnt[b][mi] = c; S.lb[b][mi] = lbv; }
+          if (lane == 0) { S.cnt[b][mi] = c_hi; S.cnt_lo[b][mi] = c_lo; S.lb[b][mi] = lbv; }
           __syncwarp();
         }
       }
@@ -241,10 +352,17 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
         const uint32_t nm = S.nm[it];
         for (uint32_t mi = 0; mi < nm; ++mi) {
           ++n_models;
-          if (!ac_mode && (double)S.cnt[it][mi] > 2.5 * NS) ac_mode = true;
+          double Fm[9];
+          if (!ac_mode) {  // classic-RANSAC phase: the exact number of residuals within the bound decides the switch
+            uint32_t c = S.cnt_lo[it][mi];
+            if (c != S.cnt[it][mi] && (double)c <= 2.5 * NS && (double)S.cnt[it][mi] > 2.5 * NS) {
+              for (int t = 0; t < 9; ++t) Fm[t] = S.models[it][mi][t];
+              c = exact_count<MODEL>(pr, p1, p2, Fm, &S.s_count);
+            }
+            if ((double)c > 2.5 * NS) ac_mode = true;
+          }
           if (ac_mode && S.lb[it][mi] < minNFA) {  // the model may improve on the best one: exact NFA (tier 2)
             ++n_exact;
-            double Fm[9];
             for (int t = 0; t < 9; ++t) Fm[t] = S.models[it][mi][t];
             const uint32_t c = residuals_sorted<MODEL, false>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
             const NfaBest r = nfa_scan_sorted<MODEL>(pr, se, c, lcn, logc_k, S.s_nfa, S.s_k);
@@ -271,6 +389,7 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
         }
       }
       iter += consumed;
+      since_event = event ? 0u : since_event + consumed;
       // ---- 5. pool replacement: draw the next samples among the best model's inliers -------------------------
       if (event) {
         ++n_events;
@@ -279,7 +398,7 @@ __global__ void __launch_bounds__(kFThreads) k_acransac_fused(
         for (int t = 0; t < 9; ++t) Fm[t] = S.bestF[t];
         const uint32_t c = residuals_sorted<MODEL, true>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
         pool_size = best_k < c ? best_k : c;
-        for (uint32_t i = tid; i < pool_size; i += kFThreads) pool[i] = si[i];
+        for (uint32_t i = tid; i < pool_size; i += kFThreads) pool[i] = (PoolT)si[i];
         if (nIterReserve) {
           nIter = iter + nIterReserve;
           nIterReserve = 0;
@@ -339,8 +458,8 @@ int acransac_fused_ctas_per_sm(int model, uint32_t cap, bool huge) {
   const size_t per_sm = 227 * 1024;
   int n = (int)(per_sm / (smem + 1024));
   if (n < 1) n = 1;
-  if (n > 4) n = 4;  // 256 threads x ~128 registers
-  return n;
+  const int by_regs = model == 2 ? 1 : 3;  // __launch_bounds__ of the kernel
+  return n < by_regs ? n : by_regs;
 }
 
 int launch_acransac_fused(r3d_ctx* ctx, DeviceWorker& w, int model, bool huge, const AcPair* pairs, const uint32_t* order,

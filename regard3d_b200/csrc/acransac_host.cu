@@ -147,7 +147,10 @@ int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const
   for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));
   struct EvGuard { cudaEvent_t* e; ~EvGuard() { for (int i = 0; i < 2; ++i) cudaEventDestroy(e[i]); } } evg{ev};
   R3D_CUDA_TRY(ctx, cudaEventRecord(ev[0], w.stream));
-  for (int c = kClasses - 1; c >= 0; --c) {  // the long-running classes first
+  // launch geometry of every class first: the scratch buffers are shared by the launches (same stream) and must not move
+  uint32_t caps[kClasses] = {0}, grids[kClasses] = {0};
+  size_t si_need = 0, huge_need = 0;
+  for (int c = 0; c < kClasses; ++c) {
     const uint32_t cnt = class_ofs[c + 1] - class_ofs[c];
     if (!cnt) continue;
     const bool huge = c == 5;
@@ -157,14 +160,22 @@ int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const
       while (cap < huge_maxM) cap <<= 1;
     }
     uint32_t grid = std::min<uint32_t>(cnt, (uint32_t)w.sm_count * (uint32_t)acransac_fused_ctas_per_sm(model, cap, huge));
-    if (huge) {
-      grid = std::min<uint32_t>(grid, (uint32_t)w.sm_count);
-      R3D_CUDA_TRY(ctx, d_se.ensure((size_t)grid * cap));
-      R3D_CUDA_TRY(ctx, d_si.ensure((size_t)grid * cap));
-      R3D_CUDA_TRY(ctx, d_pool.ensure((size_t)grid * cap));
-    }
-    int rc = launch_acransac_fused(ctx, w, model, huge, d_pairs, d_order.p + class_ofs[c], cnt, d_work.p + c, d_x1, d_x2, d_logc_n,
-                                   d_logc_k, cap, max_iter, d_se.p, d_si.p, d_pool.p, d_match, d_outm.p, d_out.p, grid);
+    if (huge) grid = std::min<uint32_t>(grid, (uint32_t)w.sm_count);
+    caps[c] = cap;
+    grids[c] = grid;
+    si_need = std::max(si_need, (size_t)grid * cap);
+    if (huge) huge_need = (size_t)grid * cap;
+  }
+  R3D_CUDA_TRY(ctx, d_si.ensure(si_need));
+  if (huge_need) {
+    R3D_CUDA_TRY(ctx, d_se.ensure(huge_need));
+    R3D_CUDA_TRY(ctx, d_pool.ensure(huge_need));
+  }
+  for (int c = kClasses - 1; c >= 0; --c) {  // the long-running classes first
+    const uint32_t cnt = class_ofs[c + 1] - class_ofs[c];
+    if (!cnt) continue;
+    int rc = launch_acransac_fused(ctx, w, model, c == 5, d_pairs, d_order.p + class_ofs[c], cnt, d_work.p + c, d_x1, d_x2, d_logc_n,
+                                   d_logc_k, caps[c], max_iter, d_se.p, d_si.p, d_pool.p, d_match, d_outm.p, d_out.p, grids[c]);
     if (rc) return rc;
     T.kernel_launches += 1;
   }
@@ -185,6 +196,7 @@ int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const
             (unsigned long long)T.hypotheses, (unsigned long long)mo, (unsigned long long)ex, 100.0 * (double)ex / (double)std::max<uint64_t>(mo, 1),
             (unsigned long long)evs);
   }
+  const double t_after_kernel = now_ms();
   // ---- inlier lists back: chunks of whole pairs through two pinned staging buffers, copied out by the host pool ----
   // GeometricFilter_*Matrix_AC::Robust_estimation keeps the pair iff #inliers > MINIMUM_SAMPLES * 2.5
   const size_t kStageElems = (size_t)4 << 20;  // 32 MB of (i, j) per buffer
@@ -244,6 +256,8 @@ int run_fused(r3d_ctx* ctx, DeviceWorker& w, int model, uint32_t max_iter, const
     });
   }
   (void)put;
+  if (getenv("R3D_DEBUG_TIMING"))
+    fprintf(stderr, "[r3d] fused filter total %.2f ms (kernel %.2f, results back %.2f)\n", now_ms() - t_begin, T.ms_score, now_ms() - t_after_kernel);
   T.ms_device_total = T.ms_score;
   T.ms_host = now_ms() - t_begin - T.ms_device_total;
   return R3D_OK;
@@ -310,6 +324,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     hlogc_k[n] = r;
   }
   std::atomic<int> bad{0};
+  const double t_pairs0 = now_ms();
   parallel_for(ctx->host_threads, st.size(), [&](size_t a) {
     PairState& s = st[a];
     const uint64_t p = s.src;
@@ -366,6 +381,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
   });
   (void)bad;
+  if (getenv("R3D_DEBUG_TIMING"))
+    fprintf(stderr, "[r3d] filter set-up: pair scan %.2f ms, per-pair tables + match copy %.2f ms\n", t_pairs0 - t_begin, now_ms() - t_pairs0);
   uint32_t cap = 32;
   while (cap < maxM) cap <<= 1;
   // the persistent per-pair kernel draws the sample stream on the device; it needs the restated
@@ -410,6 +427,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_n.p, hlogc_n.data(), hlogc_n.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_k.p, hlogc_k.data(), hlogc_k.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
 
+  if (getenv("R3D_DEBUG_TIMING")) fprintf(stderr, "[r3d] filter host set-up + point upload: %.2f ms\n", now_ms() - t_begin);
   if (use_fused)
     return run_fused(ctx, w, model, max_iter, put, st_src(st), hpairs, d_pairs.p, d_x1.p, d_x2.p, d_match.p, d_logc_n.p, d_logc_k.p,
                      (uint32_t)hmatch.size(), sizeSample, t_begin, T, result);
