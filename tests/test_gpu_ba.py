@@ -156,3 +156,10 @@ def test_ba_pose_center_priors_equal_oracle(gpu_ctx, oracle):
         plain.pop(k)
     s0, _ = _compare(gpu_ctx, oracle, plain, iters=12)
     assert so["final_cost"] > s0["final_cost"]                       # the priors do take part in the cost
+
+
+def test_ba_c5_full_size_equals_oracle(gpu_ctx, oracle):
+    """BASELINE config 5 at FULL size (200 cameras / 200 000 points / 1 000 000 observations): per-observation residuals
+    within 1e-5 relative of the oracle's after the same LM iterations (round 1 only checked 40 cameras / 20 000 points)."""
+    prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
+    _compare(gpu_ctx, oracle, prob, iters=3)
