@@ -68,6 +68,7 @@ int launch_acransac_fused(r3d_ctx* ctx, DeviceWorker& w, int model, bool huge, c
 // x1/x2[pt_ofs + k] = normalised positions of putative match k of every pair (double, like MatchesPairToMat)
 int launch_ac_points(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const AcPointSrc* src, uint32_t n_pairs,
                      const uint2* matches, double2* x1, double2* x2, uint32_t* bad_flag);
+int launch_ac_tables(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, uint32_t n_pairs, const float* vlog10, float* logc_n);
 int launch_f7_solve(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,
                     const AcHyp* hyps, uint32_t n_hyp, double* F, uint32_t* nmodels);
 int launch_f7_score(r3d_ctx* ctx, DeviceWorker& w, int model, const AcPair* pairs, const double2* x1, const double2* x2,

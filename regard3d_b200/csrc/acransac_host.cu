@@ -278,8 +278,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   std::vector<PairState> st;
   std::vector<AcPair> hpairs;
   std::vector<AcPointSrc> hsrc;
-  std::vector<uint2> hmatch;  // (i, j) of every putative match, pair after pair: the device looks the positions up
-  std::vector<float> hlogc_n;
+  uint64_t n_match_total = 0, n_table_total = 0;  // (i, j) of every putative match / logc_n entries, pair after pair
   uint32_t maxM = 0;
   {
     uint64_t pt_total = 0, tbl_total = 0;
@@ -304,11 +303,14 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     }
     if (st.empty()) return R3D_OK;
     if (pt_total > 0xfffffff0ull) return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: too many putative matches in one call");
-    hmatch.resize(pt_total);
+    n_match_total = pt_total;
+    n_table_total = tbl_total;
     hsrc.resize(st.size());
-    hlogc_n.resize(tbl_total);
     hpairs.resize(st.size());
   }
+  // the persistent per-pair kernel draws the sample stream on the device; it needs the restated
+  // std::uniform_int_distribution to agree with this process's <random> (acransac_rng.cuh)
+  const bool use_fused = rng_selftest() && !getenv("R3D_FILTER_HOST_ROUNDS");
   // log-combinatorial tables (float, upstream makelogcombi_n / makelogcombi_k).  logcombi(k,n) is a
   // running float sum over i = 1..min(k,n-k): its partial sums ARE the entries for smaller k, so one
   // O(n) pass reproduces the upstream O(n^2) table bit for bit.
@@ -340,7 +342,6 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     // the matched positions are looked up, promoted to double and normalised on the device (k_ac_points):
     // the host only ships the (i, j) list
     static_assert(sizeof(r3d_indmatch) == sizeof(uint2), "IndMatch layout");
-    std::memcpy(hmatch.data() + s.pt_ofs, put->per[p].data(), (size_t)M * sizeof(uint2));
     AcPointSrc& ps = hsrc[a];
     ps.xyI = vi.d_xy; ps.xyJ = vj.d_xy;
     ps.s1 = s1; ps.c1x = c1x; ps.c1y = c1y; ps.s2 = s2; ps.c2x = c2x; ps.c2y = c2y;
@@ -364,30 +365,19 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     ap.K[0] = views[s.I].focal; ap.K[1] = views[s.I].ppx; ap.K[2] = views[s.I].ppy;
     ap.K[3] = views[s.J].focal; ap.K[4] = views[s.J].ppx; ap.K[5] = views[s.J].ppy;
     hpairs[a] = ap;
-    s.vec_index.resize(M);
-    std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
+    if (!use_fused) {  // state of the host-round path only
+      s.vec_index.resize(M);
+      std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
+    }
     s.nIterReserve = max_iter / 10;
     s.nIter = max_iter - s.nIterReserve;
     s.ac_mode = (precision == std::numeric_limits<double>::infinity());
-    // logc_n table of this pair
-    const uint32_t n = M;
-    float* t = hlogc_n.data() + s.tbl_ofs;
-    t[0] = 0.f;
-    float r = 0.f;
-    for (uint32_t i = 1; i <= n / 2; ++i) {
-      r += vlog10[n - i + 1] - vlog10[i];
-      t[i] = r;
-    }
-    for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
   });
   (void)bad;
   if (getenv("R3D_DEBUG_TIMING"))
     fprintf(stderr, "[r3d] filter set-up: pair scan %.2f ms, per-pair tables + match copy %.2f ms\n", t_pairs0 - t_begin, now_ms() - t_pairs0);
   uint32_t cap = 32;
   while (cap < maxM) cap <<= 1;
-  // the persistent per-pair kernel draws the sample stream on the device; it needs the restated
-  // std::uniform_int_distribution to agree with this process's <random> (acransac_rng.cuh)
-  const bool use_fused = rng_selftest() && !getenv("R3D_FILTER_HOST_ROUNDS");
   if (!use_fused && (size_t)cap * 12 > 200 * 1024)
     return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_filter_pairs: more than 16384 putative matches in one pair (host-round path)");
 
@@ -397,23 +387,65 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
   DevBuf<AcPointSrc> d_src(w);
   DevBuf<uint2> d_match(w);
   DevBuf<uint32_t> d_bad(w);
-  DevBuf<float> d_logc_n(w), d_logc_k(w);
+  DevBuf<float> d_logc_n(w), d_logc_k(w), d_vlog10(w);
   DevBuf<AcHyp> d_hyp(w);
   DevBuf<double> d_F(w);
   DevBuf<uint32_t> d_nm(w), d_inl(w);
   DevBuf<AcScore> d_score(w);
   DevBuf<AcInlierReq> d_req(w);
   R3D_CUDA_TRY(ctx, d_pairs.ensure(hpairs.size()));
-  R3D_CUDA_TRY(ctx, d_x1.ensure(hmatch.size()));
-  R3D_CUDA_TRY(ctx, d_x2.ensure(hmatch.size()));
+  R3D_CUDA_TRY(ctx, d_x1.ensure(n_match_total));
+  R3D_CUDA_TRY(ctx, d_x2.ensure(n_match_total));
   R3D_CUDA_TRY(ctx, d_src.ensure(hsrc.size()));
-  R3D_CUDA_TRY(ctx, d_match.ensure(hmatch.size()));
+  R3D_CUDA_TRY(ctx, d_match.ensure(n_match_total));
   R3D_CUDA_TRY(ctx, d_bad.ensure(1));
-  R3D_CUDA_TRY(ctx, d_logc_n.ensure(hlogc_n.size()));
+  R3D_CUDA_TRY(ctx, d_logc_n.ensure(n_table_total));
+  R3D_CUDA_TRY(ctx, d_vlog10.ensure(vlog10.size()));
   R3D_CUDA_TRY(ctx, d_logc_k.ensure(hlogc_k.size()));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_pairs.p, hpairs.data(), hpairs.size() * sizeof(AcPair), cudaMemcpyHostToDevice, w.stream));
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_src.p, hsrc.data(), hsrc.size() * sizeof(AcPointSrc), cudaMemcpyHostToDevice, w.stream));
-  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_match.p, hmatch.data(), hmatch.size() * sizeof(uint2), cudaMemcpyHostToDevice, w.stream));
+  // the putative (i, j) lists: gathered by the host pool into two pinned staging buffers, chunk by chunk, while the
+  // previous chunk is on its way to the device (a pageable 800 MB source at C3 would move at a fraction of the link)
+  {
+    const size_t kStageElems = (size_t)4 << 20;  // 32 MB of (i, j) per buffer
+    if (w.h_fstage_cap < kStageElems) {
+      for (void*& hp : w.h_fstage) {
+        if (hp) cudaFreeHost(hp);
+        hp = nullptr;
+        R3D_CUDA_TRY(ctx, cudaMallocHost(&hp, kStageElems * sizeof(uint2)));
+      }
+      w.h_fstage_cap = kStageElems;
+    }
+    cudaEvent_t uev[2];
+    for (auto& e : uev) R3D_CUDA_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    struct UevGuard { cudaEvent_t* e; ~UevGuard() { for (int i = 0; i < 2; ++i) cudaEventDestroy(e[i]); } } uevg{uev};
+    size_t a0 = 0, chunk_no = 0;
+    while (a0 < st.size()) {
+      size_t a1 = a0;
+      const size_t lo = hpairs[a0].pt_ofs;
+      size_t hi = lo;
+      while (a1 < st.size() && ((size_t)hpairs[a1].pt_ofs + hpairs[a1].M - lo <= kStageElems || a1 == a0)) {
+        hi = (size_t)hpairs[a1].pt_ofs + hpairs[a1].M;
+        ++a1;
+      }
+      if (hi - lo > kStageElems) {  // one pair larger than the staging buffer: straight from its (pageable) span
+        R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_match.p + lo, put->per[st[a0].src].data(), (hi - lo) * sizeof(uint2), cudaMemcpyHostToDevice, w.stream));
+        R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+      } else {
+        const int buf = (int)(chunk_no & 1);
+        if (chunk_no >= 2) R3D_CUDA_TRY(ctx, cudaEventSynchronize(uev[buf]));  // the copy that last read this buffer is done
+        uint2* stage = (uint2*)w.h_fstage[buf];
+        parallel_for(ctx->host_threads, a1 - a0, [&](size_t k) {
+          const size_t a = a0 + k;
+          std::memcpy(stage + (hpairs[a].pt_ofs - lo), put->per[st[a].src].data(), (size_t)hpairs[a].M * sizeof(uint2));
+        });
+        R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_match.p + lo, stage, (hi - lo) * sizeof(uint2), cudaMemcpyHostToDevice, w.stream));
+        R3D_CUDA_TRY(ctx, cudaEventRecord(uev[buf], w.stream));
+        ++chunk_no;
+      }
+      a0 = a1;
+    }
+  }
   R3D_CUDA_TRY(ctx, cudaMemsetAsync(d_bad.p, 0, sizeof(uint32_t), w.stream));
   {
     int rcp = launch_ac_points(ctx, w, d_pairs.p, d_src.p, (uint32_t)hpairs.size(), d_match.p, d_x1.p, d_x2.p, d_bad.p);
@@ -424,13 +456,19 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     if (hbad) return fail(ctx, R3D_ERR_INVALID, "r3d_filter_pairs: match index out of range");
     T.kernel_launches += 1;
   }
-  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_n.p, hlogc_n.data(), hlogc_n.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
+  // logc_n tables: float prefix sums over the host's log10 table, one thread per pair in the upstream order
+  R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_vlog10.p, vlog10.data(), vlog10.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
+  {
+    int rct = launch_ac_tables(ctx, w, d_pairs.p, (uint32_t)hpairs.size(), d_vlog10.p, d_logc_n.p);
+    if (rct) return rct;
+    T.kernel_launches += 1;
+  }
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_logc_k.p, hlogc_k.data(), hlogc_k.size() * sizeof(float), cudaMemcpyHostToDevice, w.stream));
 
   if (getenv("R3D_DEBUG_TIMING")) fprintf(stderr, "[r3d] filter host set-up + point upload: %.2f ms\n", now_ms() - t_begin);
   if (use_fused)
     return run_fused(ctx, w, model, max_iter, put, st_src(st), hpairs, d_pairs.p, d_x1.p, d_x2.p, d_match.p, d_logc_n.p, d_logc_k.p,
-                     (uint32_t)hmatch.size(), sizeSample, t_begin, T, result);
+                     (uint32_t)n_match_total, sizeSample, t_begin, T, result);
 
   cudaEvent_t ev[3];
   for (auto& e : ev) R3D_CUDA_TRY(ctx, cudaEventCreate(&e));

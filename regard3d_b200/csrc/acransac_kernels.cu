@@ -123,6 +123,31 @@ __global__ void __launch_bounds__(256) k_ac_points(const AcPair* __restrict__ pa
   }
 }
 
+// makelogcombi_n (robust_estimator_ACRansac.hpp): logc_n[k] = log10 C(n, k) as a running FLOAT sum over
+// i = 1 .. min(k, n - k) of log10(n - i + 1) - log10(i); the partial sums are the entries for smaller k, so one pass per
+// pair reproduces the upstream table bit for bit (the log10 table itself comes from the host's libm).
+__global__ void __launch_bounds__(128) k_ac_tables(const AcPair* __restrict__ pairs, uint32_t n_pairs, const float* __restrict__ vlog10,
+                                                   float* __restrict__ logc_n) {
+  const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_pairs) return;
+  const uint32_t n = pairs[a].M;
+  float* t = logc_n + pairs[a].tbl_ofs;
+  t[0] = 0.f;
+  float r = 0.f;
+  for (uint32_t i = 1; i <= n / 2; ++i) {
+    r = __fadd_rn(r, __fsub_rn(vlog10[n - i + 1], vlog10[i]));
+    t[i] = r;
+  }
+  for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
+}
+
+int launch_ac_tables(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, uint32_t n_pairs, const float* vlog10, float* logc_n) {
+  if (!n_pairs) return R3D_OK;
+  k_ac_tables<<<(n_pairs + 127) / 128, 128, 0, w.stream>>>(pairs, n_pairs, vlog10, logc_n);
+  R3D_CUDA_TRY(ctx, cudaGetLastError());
+  return R3D_OK;
+}
+
 int launch_ac_points(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, const AcPointSrc* src, uint32_t n_pairs,
                      const uint2* matches, double2* x1, double2* x2, uint32_t* bad_flag) {
   if (!n_pairs) return R3D_OK;
