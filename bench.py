@@ -437,6 +437,11 @@ def main():
                            "roofline_frac": fl / (np.mean(c_ms) * 1e-3) / 1e12 / peak, "matches": mm.total}
             del sc2
 
+    # ---- side line: the LIOP-144 descriptor stage, N = 1 ----
+    liop = None
+    if world == 1 and not args.no_extras:
+        liop = liop_leg(ctx, torch, args)
+
     if rank == 0:
         peaks, peak_src = load_peaks()
         value = n_pairs * args.steps / t_res
@@ -478,6 +483,8 @@ def main():
             line["ba"] = ba
         if extras:
             line["extras"] = extras
+        if liop:
+            line["liop"] = liop
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as po
             nthreads = effective_cpus()
@@ -499,6 +506,45 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def liop_leg(ctx, torch, args):
+    """LIOP-144 descriptors of one 1080p image with 10 000 keypoints through r3d_liop_describe (host image and keypoints
+    in, host descriptors out).  CPU side: the oracle port with OpenMP over keypoints, and THE REFERENCE's own
+    r3d_vl_liopdesc_process (oracle/_ref, compiled from the reference source) on the same patches, one thread."""
+    rng = np.random.default_rng(20260924)
+    h, w, n = 1080, 1920, 10000
+    img = rng.random((h, w)).astype(np.float32)
+    kps = np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n), rng.uniform(3, 40, n), rng.uniform(0, 360, n)], 1).astype(np.float32)
+    for _ in range(2):
+        d = ctx.liop_describe(img, kps, 8.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        d = ctx.liop_describe(img, kps, 8.0)
+    torch.cuda.synchronize()
+    tg = (time.perf_counter() - t0) / reps
+    out = {"descriptors_per_s": n / tg, "ms_per_image": 1e3 * tg, "keypoints": n, "image": "%dx%d float32" % (w, h),
+           "what": "r3d_liop_describe end to end (image H2D, warp + blur + exact quick-sort replay + order patterns, D2H)"}
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        ns = 2000
+        tc0 = time.perf_counter()
+        dc, patches = po.liop_describe(img, kps[:ns], 8.0, want_patches=True)
+        tc = time.perf_counter() - tc0
+        out["cpu_baseline"] = {"value": ns / tc, "unit": "descriptors/s", "cores": effective_cpus(), "kind": "port",
+                               "sample": "%d keypoints of the same image, omp over keypoints" % ns,
+                               "parity_on_sample": bool(np.array_equal(dc.view(np.uint32), d[:ns].view(np.uint32)))}
+        if po.liop_ref_available():
+            tr0 = time.perf_counter()
+            dr = po.liop_ref_process(patches[:500])
+            tr = time.perf_counter() - tr0
+            out["cpu_reference"] = {"value": 500 / tr, "unit": "descriptors/s", "cores": 1, "kind": "reference",
+                                    "sample": "r3d_vl_liopdesc_process of oracle/_ref (the reference's vl_liop.c) on 500 of those "
+                                              "patches; descriptor step only (warp + blur excluded)",
+                                    "parity_on_sample": bool(np.array_equal(dr.view(np.uint32), d[:500].view(np.uint32)))}
+    return out
 
 
 def ba_leg(args, ctx, torch, dist, rank, world, barrier, max_over_ranks):
