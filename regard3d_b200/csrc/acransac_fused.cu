@@ -31,26 +31,33 @@ namespace {
 
 constexpr int kFThreads = 256;
 constexpr int kFWarps = kFThreads / 32;
-constexpr int kBatch = 32;            // most iterations drawn, solved and tier-1-scored ahead (the batch grows with the
+constexpr int kBatch = 24;            // most iterations drawn, solved and tier-1-scored ahead (the batch grows with the
                                       // number of iterations since the last pool replacement: 4, 5, ... kBatch)
 constexpr double kApproxRel = 1e-9;   // relative accuracy of the tier-1 residuals (see approx_error)
 constexpr int kBins = 1024;           // tier-1 histogram: binades split in 32 (exponent + 5 mantissa bits)
 constexpr int kBinShift = 52 - 5;
 
 template <int MODEL>
-struct FusedSmem {                    // fixed part of the shared memory (the sort / histogram region follows)
-  Mt19937 rng, snap;
-  double la[kBins];                   // logalpha of every bin's lower edge
+struct BatchBuf {                     // one speculative batch of RANSAC iterations
+  Mt19937 snap;                       // generator state before the batch's first draw
   double models[kBatch][ac_max_models(MODEL)][9];
   double lb[kBatch][ac_max_models(MODEL)];
-  double bestF[9];
-  double s_nfa[kFWarps];
-  uint32_t s_k[kFWarps];
   uint32_t cnt[kBatch][ac_max_models(MODEL)];      // residuals that may be <= the bound (upper count)
   uint32_t cnt_lo[kBatch][ac_max_models(MODEL)];   // residuals that certainly are (lower count)
   uint32_t nm[kBatch];
   uint32_t sample[kBatch][8];
   uint32_t used[kBatch];              // generator outputs consumed up to and including iteration b of the batch
+  uint32_t B;                         // iterations in the batch
+};
+
+template <int MODEL>
+struct FusedSmem {                    // fixed part of the shared memory (the sort / histogram region follows)
+  Mt19937 rng;
+  BatchBuf<MODEL> q[2];               // the batch being scored / replayed and the one warp 0 prepares meanwhile
+  double la[kBins];                   // logalpha of every bin's lower edge
+  double bestF[9];
+  double s_nfa[kFWarps];
+  uint32_t s_k[kFWarps];
   uint32_t s_count;
   uint32_t work;
 };
@@ -222,69 +229,84 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fuse
     uint32_t n_exact = 0, n_models = 0, n_events = 0;
     __syncthreads();
 
-    while (iter < nIter) {
-      // speculation depth: short right after a pool replacement (improving models come in bursts), longer later
-      const uint32_t B = min(min((uint32_t)kBatch, 4u + since_event), nIter - iter);
-      // ---- 1. snapshot the generator, draw B samples (UniformSample: partial Fisher-Yates on the pool) ----
+    // ---- producer (warp 0): draw the next `Bq` samples and solve them into batch buffer q -------------------
+    // UniformSample = a partial Fisher-Yates on the pool, sequential by nature (lane 0); the minimal solvers of the
+    // batch then run one per lane.  Called either ahead of time (while warps 1.. score the previous batch) or, after a
+    // pool replacement invalidated that speculation, with the whole CTA waiting.
+    auto produce = [&](BatchBuf<MODEL>& Q, uint32_t Bq, uint32_t psize) {
       {
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&S.snap);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&Q.snap);
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.rng);
-        for (uint32_t i = tid; i < sizeof(Mt19937) / 4; i += kFThreads) dst[i] = src[i];
+        for (uint32_t i = lane; i < sizeof(Mt19937) / 4; i += 32) dst[i] = src[i];
       }
-      __syncthreads();
-      if (tid == 0) {
+      __syncwarp();
+      if (lane == 0) {
         uint32_t used = 0;
-        const uint32_t last_idx = pool_size - 1;
-        for (uint32_t b = 0; b < B; ++b) {
+        const uint32_t last_idx = psize - 1;
+        for (uint32_t b = 0; b < Bq; ++b) {
           for (uint32_t i = 0; i < NS; ++i) {
             const uint32_t r = uniform_u32(S.rng, i, last_idx, &used);
             const PoolT t = pool[i]; pool[i] = pool[r]; pool[r] = t;
           }
-          for (uint32_t i = 0; i < NS; ++i) S.sample[b][i] = pool[i];
-          S.used[b] = used;
+          for (uint32_t i = 0; i < NS; ++i) Q.sample[b][i] = pool[i];
+          Q.used[b] = used;
         }
+        Q.B = Bq;
       }
-      __syncthreads();
-      // ---- 2. minimal solver: one thread per iteration of the batch (one per warp first: no lock-step penalty) ----
-      {
-        const uint32_t slot = (lane * kFWarps + warp);  // thread -> iteration: spread over the warps
-        if (slot < B && lane < (kBatch + kFWarps - 1) / kFWarps) {
-          double models[9 * MAXM];
-          int nm;
-          if (MODEL == 2) {
-            double b1[15], b2[15], Es[90];
-            for (int t = 0; t < 5; ++t) {
-              const double2 a = p1[S.sample[slot][t]];
-              const double2 b = p2[S.sample[slot][t]];
-              bearing(pr.K, a.x, a.y, b1 + 3 * t);
-              bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
-            }
-            nm = fp::five_point(b1, b2, Es);
-            for (int mi = 0; mi < nm; ++mi) fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, models + 9 * mi);
-          } else {
-            double s1[14], s2[14];
-            for (uint32_t t = 0; t < NS; ++t) {
-              const double2 a = p1[S.sample[slot][t]];
-              const double2 b = p2[S.sample[slot][t]];
-              s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
-              s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
-            }
-            nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
+      __syncwarp();
+      if (lane < Bq) {
+        double models[9 * MAXM];
+        int nm;
+        if (MODEL == 2) {
+          double b1[15], b2[15], Es[90];
+          for (int t = 0; t < 5; ++t) {
+            const double2 a = p1[Q.sample[lane][t]];
+            const double2 b = p2[Q.sample[lane][t]];
+            bearing(pr.K, a.x, a.y, b1 + 3 * t);
+            bearing(pr.K + 3, b.x, b.y, b2 + 3 * t);
           }
-          S.nm[slot] = (uint32_t)nm;
-          for (int mi = 0; mi < nm; ++mi)
-            for (int t = 0; t < 9; ++t) S.models[slot][mi][t] = models[9 * mi + t];
+          nm = fp::five_point(b1, b2, Es);
+          for (int mi = 0; mi < nm; ++mi) fundamental_from_essential(Es + 9 * mi, pr.K, pr.K + 3, models + 9 * mi);
+        } else {
+          double s1[14], s2[14];
+          for (uint32_t t = 0; t < NS; ++t) {
+            const double2 a = p1[Q.sample[lane][t]];
+            const double2 b = p2[Q.sample[lane][t]];
+            s1[2 * t] = a.x; s1[2 * t + 1] = a.y;
+            s2[2 * t] = b.x; s2[2 * t + 1] = b.y;
+          }
+          nm = MODEL == 0 ? seven_point(s1, s2, models) : four_point(s1, s2, models);
         }
+        Q.nm[lane] = (uint32_t)nm;
+        for (int mi = 0; mi < nm; ++mi)
+          for (int t = 0; t < 9; ++t) Q.models[lane][mi][t] = models[9 * mi + t];
       }
-      __syncthreads();
-      // ---- 3. tier 1: one warp per model -- bracketed count, histogram, lower bound of the best NFA ------------
-      {
-        uint32_t* hist = hist_all + (size_t)warp * kBins;
-        for (uint32_t slot = warp; slot < B * MAXM; slot += kFWarps) {
+      __syncwarp();
+    };
+    // speculation depth: short right after a pool replacement (improving models come in bursts), longer later
+    auto batch_size = [&](uint32_t since, uint32_t remaining) { return min(min((uint32_t)kBatch, 4u + since), remaining); };
+
+    uint32_t cur = 0;
+    bool have_cur = false;  // q[cur] holds drawn + solved iterations that continue the sequence at `iter`
+    while (iter < nIter) {
+      if (!have_cur) {  // (re)start the pipeline: nothing was prepared ahead, or a pool replacement discarded it
+        if (warp == 0) produce(S.q[cur], batch_size(since_event, nIter - iter), pool_size);
+        __syncthreads();
+      }
+      BatchBuf<MODEL>& Q = S.q[cur];
+      const uint32_t B = Q.B;
+      // ---- phase A: warps 1.. score batch `cur` (tier 1); warp 0 prepares the batch after it, assuming that the
+      //      replay of `cur` will not replace the pool (if it does, the work is thrown away and the generator rewound)
+      const uint32_t ahead = nIter - iter > B ? batch_size(since_event + B, nIter - iter - B) : 0u;
+      if (warp == 0) {
+        if (ahead) produce(S.q[cur ^ 1u], ahead, pool_size);
+      } else {
+        uint32_t* hist = hist_all + (size_t)(warp - 1) * kBins;
+        for (uint32_t slot = warp - 1; slot < B * MAXM; slot += kFWarps - 1) {
           const uint32_t b = slot / MAXM, mi = slot % MAXM;
-          if (mi >= S.nm[b]) continue;
+          if (mi >= Q.nm[b]) continue;
           double Fm[9], fmax_abs = 0.0;
-          for (int t = 0; t < 9; ++t) { Fm[t] = S.models[b][mi][t]; fmax_abs = fmax(fmax_abs, fabs(Fm[t])); }
+          for (int t = 0; t < 9; ++t) { Fm[t] = Q.models[b][mi][t]; fmax_abs = fmax(fmax_abs, fabs(Fm[t])); }
           const double eta = 7.2e-15 * fmax_abs * coord_span;  // 64 ulp x the largest term of x2^T F x1 (or H x1)
           for (uint32_t i = lane; i < (uint32_t)kBins; i += 32) hist[i] = 0;
           __syncwarp();
@@ -339,31 +361,31 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fuse
             // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
             lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
           }
-          if (lane == 0) { S.cnt[b][mi] = c_hi; S.cnt_lo[b][mi] = c_lo; S.lb[b][mi] = lbv; }
+          if (lane == 0) { Q.cnt[b][mi] = c_hi; Q.cnt_lo[b][mi] = c_lo; Q.lb[b][mi] = lbv; }
           __syncwarp();
         }
       }
       __syncthreads();
-      // ---- 4. replay the ACRANSAC state machine over the batch (uniform control flow) ---------------------
+      // ---- phase B: replay the ACRANSAC state machine over the batch (uniform control flow) ---------------------
       uint32_t consumed = B;
       bool event = false;
       for (uint32_t it = 0; it < B; ++it) {
         bool better = false;
-        const uint32_t nm = S.nm[it];
+        const uint32_t nm = Q.nm[it];
         for (uint32_t mi = 0; mi < nm; ++mi) {
           ++n_models;
           double Fm[9];
           if (!ac_mode) {  // classic-RANSAC phase: the exact number of residuals within the bound decides the switch
-            uint32_t c = S.cnt_lo[it][mi];
-            if (c != S.cnt[it][mi] && (double)c <= 2.5 * NS && (double)S.cnt[it][mi] > 2.5 * NS) {
-              for (int t = 0; t < 9; ++t) Fm[t] = S.models[it][mi][t];
+            uint32_t c = Q.cnt_lo[it][mi];
+            if (c != Q.cnt[it][mi] && (double)c <= 2.5 * NS && (double)Q.cnt[it][mi] > 2.5 * NS) {
+              for (int t = 0; t < 9; ++t) Fm[t] = Q.models[it][mi][t];
               c = exact_count<MODEL>(pr, p1, p2, Fm, &S.s_count);
             }
             if ((double)c > 2.5 * NS) ac_mode = true;
           }
-          if (ac_mode && S.lb[it][mi] < minNFA) {  // the model may improve on the best one: exact NFA (tier 2)
+          if (ac_mode && Q.lb[it][mi] < minNFA) {  // the model may improve on the best one: exact NFA (tier 2)
             ++n_exact;
-            for (int t = 0; t < 9; ++t) Fm[t] = S.models[it][mi][t];
+            for (int t = 0; t < 9; ++t) Fm[t] = Q.models[it][mi][t];
             const uint32_t c = residuals_sorted<MODEL, false>(pr, x1, x2, Fm, se, si, cap, &S.s_count);
             const NfaBest r = nfa_scan_sorted<MODEL>(pr, se, c, lcn, logc_k, S.s_nfa, S.s_k);
             if (r.nfa < minNFA) {
@@ -390,7 +412,8 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fuse
       }
       iter += consumed;
       since_event = event ? 0u : since_event + consumed;
-      // ---- 5. pool replacement: draw the next samples among the best model's inliers -------------------------
+      // ---- pool replacement: draw the next samples among the best model's inliers; whatever was drawn after
+      //      iteration `consumed - 1` (the tail of this batch, the batch prepared ahead) never happened ----------------
       if (event) {
         ++n_events;
         __syncthreads();  // bestF
@@ -403,15 +426,20 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fuse
           nIter = iter + nIterReserve;
           nIterReserve = 0;
         }
-        if (consumed < B) {  // rewind the generator to the end of iteration `consumed - 1`
+        {  // rewind the generator to the end of iteration `consumed - 1`
           uint32_t* dst = reinterpret_cast<uint32_t*>(&S.rng);
-          const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.snap);
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.snap);
           for (uint32_t i = tid; i < sizeof(Mt19937) / 4; i += kFThreads) dst[i] = src[i];
           __syncthreads();
           if (tid == 0)
-            for (uint32_t u = 0; u < S.used[consumed - 1]; ++u) (void)mt_next(S.rng);
+            for (uint32_t u = 0; u < Q.used[consumed - 1]; ++u) (void)mt_next(S.rng);
         }
         __syncthreads();
+        have_cur = false;
+      } else {
+        have_cur = ahead != 0;  // the batch prepared ahead continues the sequence
+        cur ^= 1u;
+        __syncthreads();        // warp 0's batch is complete (phase A barrier) and nobody reads the old one any more
       }
     }
 
