@@ -268,6 +268,29 @@ typedef struct {
 void r3d_sfm_ba_default_options(r3d_sfm_ba_options* o);
 int r3d_sfm_bundle_adjust(r3d_ctx* ctx, r3d_sfm_data* sd, const r3d_sfm_ba_options* opt, r3d_ba_summary* summary);
 
+/* ---- the steps either side of bundle adjustment -------------------------------------------------
+ * openMVG::tracks::TracksBuilder Build + Filter(min_length) + ExportToSTL, as Regard3D calls them itself
+ * (src/threads/PreviewGeneratorThread.cpp:345-352) and as every SfM engine it drives starts: union-find over the
+ * pairwise matches; tracks with two features of one image or fewer than min_length images are dropped.  Tracks come
+ * in track-id order (upstream: the union-find root), each as its (view, feature) pairs in view order. */
+typedef struct r3d_tracks r3d_tracks;
+int r3d_tracks_build(const r3d_matches* m, uint32_t min_length /* 2 */, r3d_tracks** out);
+uint64_t r3d_tracks_count(const r3d_tracks* t);
+int r3d_tracks_get(const r3d_tracks* t, uint64_t k, uint32_t* track_id, const uint32_t** views, const uint32_t** feats,
+                   uint32_t* n);
+/* TracksUtilsMap::GetTracksInImages (PreviewGeneratorThread.cpp:354-358): tracks seen in ALL listed views, cut to them */
+int r3d_tracks_in_images(const r3d_tracks* t, const uint32_t* view_ids, uint32_t n, r3d_tracks** out);
+void r3d_tracks_free(r3d_tracks* t);
+/* Tracks -> sd.structure (observation = position of the feature, from r3d_upload_regions of that view id), then
+ * SfM_Data_Structure_Computation_Blind::triangulate: every landmark from all its views with a pose and an intrinsic
+ * (iteratively re-weighted DLT); landmarks with fewer than two such views or a non-positive depth are erased. */
+int r3d_sfm_structure_from_tracks(r3d_ctx* ctx, r3d_sfm_data* sd, const r3d_tracks* tracks, uint32_t* n_rejected);
+/* RemoveOutliers_PixelResidualError(sd, max_pixel_residual, min_track_length) then RemoveOutliers_AngleError(sd,
+ * min_angle_deg) -- the rejection step the engines run after each bundle adjustment (4.0 px / 2.0 degrees upstream).
+ * min_angle_deg <= 0 skips the angle test. */
+int r3d_sfm_remove_outliers(r3d_ctx* ctx, r3d_sfm_data* sd, double max_pixel_residual, uint32_t min_track_length,
+                            double min_angle_deg, uint32_t* removed_observations, uint32_t* removed_landmarks);
+
 /* ---- multi-GPU bundle adjustment (the one path with a real exchange step) -------
  * One process per GPU.  The 3-D points (with all their observations) are partitioned over the
  * ranks, cameras and intrinsics are replicated: every rank passes r3d_bundle_adjust ALL cameras /

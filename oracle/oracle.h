@@ -146,6 +146,17 @@ void orc_ba_prior(const double* pose, const double* center, const double* weight
 /* OpenMVGHelper::calculateResiduals twin: |residual| per coordinate, 2 per obs. */
 void orc_ba_residuals(const orc_ba_problem* p, double* res /* n_obs x 2 */);
 
+/* ---- steps either side of BA: tracks, triangulation from known poses, outlier checks ---- */
+int64_t orc_tracks_build(const uint32_t* pairs, uint64_t P, const uint64_t* pair_ofs, const orc_indmatch* m, uint32_t min_length,
+                         uint32_t* track_ids, uint64_t* track_ofs, uint32_t* views, uint32_t* feats, uint64_t cap_tracks,
+                         uint64_t cap_nodes);
+void orc_triangulate_landmarks(uint32_t n_lm, const uint64_t* obs_ofs, const uint32_t* obs_cam, const double* obs_xy,
+                               const double* poses, const uint32_t* cam_intr, const double* intrinsics, const uint8_t* intr_model,
+                               double* X, uint8_t* ok);
+void orc_landmark_checks(uint32_t n_lm, const uint64_t* obs_ofs, const uint32_t* obs_cam, const double* obs_xy, const double* poses,
+                         const uint32_t* cam_intr, const double* intrinsics, const uint8_t* intr_model, const double* intrinsics_ext,
+                         const double* X, double thr_px, uint8_t* keep_obs, double* max_angle);
+
 int orc_num_threads(void);
 #ifdef __cplusplus
 }

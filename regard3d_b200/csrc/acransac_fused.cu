@@ -58,6 +58,7 @@ struct FusedSmem {                    // fixed part of the shared memory (the so
   double bestF[9];
   double s_nfa[kFWarps];
   uint32_t s_k[kFWarps];
+  uint32_t gcnt[2 * (kFWarps - 1)];   // per model of the tier-1 group: upper / lower count
   uint32_t s_count;
   uint32_t work;
 };
@@ -166,7 +167,7 @@ __device__ uint32_t exact_count(const AcPair& pr, const double2* __restrict__ p1
 // (rare) inlier sorts.  HUGE: values and pool too live in global scratch (g_se / g_pool) -- the slow-but-correct path
 // for pairs with more putative matches than shared memory can sort.
 template <int MODEL, bool HUGE>
-__global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fused(
+__global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fused(
     const AcPair* __restrict__ pairs, const uint32_t* __restrict__ order, uint32_t n_order, uint32_t* __restrict__ work_counter,
     const double2* __restrict__ x1, const double2* __restrict__ x2, const float* __restrict__ logc_n,
     const float* __restrict__ logc_k, uint32_t cap, uint32_t max_iter, double* __restrict__ g_se, uint32_t* __restrict__ g_si,
@@ -301,68 +302,107 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 3) k_acransac_fuse
       if (warp == 0) {
         if (ahead) produce(S.q[cur ^ 1u], ahead, pool_size);
       } else {
-        uint32_t* hist = hist_all + (size_t)(warp - 1) * kBins;
-        for (uint32_t slot = warp - 1; slot < B * MAXM; slot += kFWarps - 1) {
-          const uint32_t b = slot / MAXM, mi = slot % MAXM;
-          if (mi >= Q.nm[b]) continue;
-          double Fm[9], fmax_abs = 0.0;
-          for (int t = 0; t < 9; ++t) { Fm[t] = Q.models[b][mi][t]; fmax_abs = fmax(fmax_abs, fabs(Fm[t])); }
-          const double eta = 7.2e-15 * fmax_abs * coord_span;  // 64 ulp x the largest term of x2^T F x1 (or H x1)
-          for (uint32_t i = lane; i < (uint32_t)kBins; i += 32) hist[i] = 0;
-          __syncwarp();
-          uint32_t c_hi = 0, c_lo = 0;
-          for (uint32_t i = lane; i < M; i += 32) {
-            double elo, ehi;
-            approx_bounds<MODEL>(Fm, eta, p1[i], p2[i], &elo, &ehi);
-            if (elo <= pr.max_thr) {  // may be an inlier of the precision bound
-              long long bin = (__double_as_longlong(elo) >> kBinShift) - bin_base;
-              bin = bin < 0 ? 0 : (bin > kBins - 1 ? kBins - 1 : bin);
-              atomicAdd(&hist[bin], 1u);
-              ++c_hi;
-              if (ehi <= pr.max_thr) ++c_lo;
+        // Tier 1, points outer / models inner: the consumer warps split the pair's points, each point is loaded ONCE
+        // and scored against a group of kGroup models (their matrices are broadcast reads from shared memory), so the
+        // loop is bound by the fp64 pipe instead of by the latency of re-streaming the points for every model.
+        constexpr uint32_t kGroup = kFWarps - 1;                 // models per group = consumer warps (one LB scan each)
+        constexpr uint32_t kConsumers = (kFWarps - 1) * 32;
+        const uint32_t cw = warp - 1, ctid = tid - 32;
+        // the batch's models as a flat list (iteration b, model mi) -- every consumer thread walks it identically
+        uint32_t n_models_batch = 0;
+        for (uint32_t b = 0; b < B; ++b) n_models_batch += Q.nm[b];
+        for (uint32_t g0 = 0; g0 < n_models_batch; g0 += kGroup) {
+          const uint32_t gn = min(kGroup, n_models_batch - g0);
+          // locate the group's models
+          uint32_t gb[kGroup], gm[kGroup];
+          {
+            uint32_t seen = 0, k = 0;
+            for (uint32_t b = 0; b < B && k < gn; ++b) {
+              const uint32_t nmb = Q.nm[b];
+              if (seen + nmb <= g0) { seen += nmb; continue; }
+              for (uint32_t mi = (g0 > seen ? g0 - seen : 0u); mi < nmb && k < gn; ++mi) { gb[k] = b; gm[k] = mi; ++k; }
+              seen += nmb;
             }
           }
-          for (int o = 16; o >= 1; o >>= 1) {
-            c_hi += __shfl_xor_sync(0xffffffffu, c_hi, o);
-            c_lo += __shfl_xor_sync(0xffffffffu, c_lo, o);
+          for (uint32_t i = ctid; i < gn * (uint32_t)kBins; i += kConsumers) hist_all[i] = 0;
+          if (ctid < 2 * kGroup) S.gcnt[ctid] = 0;
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+          double eta[kGroup];
+          for (uint32_t k = 0; k < gn; ++k) {
+            const double* Fm = &Q.models[gb[k]][gm[k]][0];
+            double fmax_abs = 0.0;
+            for (int t = 0; t < 9; ++t) fmax_abs = fmax(fmax_abs, fabs(Fm[t]));
+            eta[k] = 7.2e-15 * fmax_abs * coord_span;            // 64 ulp x the largest term of x2^T F x1 (or H x1)
           }
-          __syncwarp();
-          double lbv = DBL_MAX * 2.0;
-          if (c_hi > NS) {
-            // exclusive prefix over the bins, 32 at a time (conflict-free rows + a running carry)
-            uint32_t carry = 0;
-            for (uint32_t j = 0; j < (uint32_t)kBins; j += 32) {
-              const uint32_t v = hist[j + lane];
-              uint32_t incl = v;
-              for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += u;
-              }
-              hist[j + lane] = carry + incl - v;
-              carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            __syncwarp();
-            // ranks (lo, hi] live in bin bb.  With e_(k) the true k-th smallest residual: at least k of the lower
-            // bounds are <= e_(k), so the k-th smallest LOWER BOUND is <= e_(k), hence
-            // NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]; extra ranks (c_hi >= c) only lower the minimum
-            for (uint32_t bb = lane; bb < (uint32_t)kBins; bb += 32) {
-              const uint32_t lo = hist[bb];
-              const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : c_hi;
-              const double la = S.la[bb];
-              for (uint32_t k = max(lo + 1, NS + 1); k <= hi; ++k) {
-                const double g = pr.loge0 + la * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
-                lbv = g < lbv ? g : lbv;
+          uint32_t c_hi[kGroup], c_lo[kGroup];
+          for (uint32_t k = 0; k < kGroup; ++k) { c_hi[k] = 0; c_lo[k] = 0; }
+          for (uint32_t i = ctid; i < M; i += kConsumers) {
+            const double2 a = p1[i], b2 = p2[i];
+#pragma unroll
+            for (uint32_t k = 0; k < kGroup; ++k) {
+              if (k >= gn) break;
+              double elo, ehi;
+              approx_bounds<MODEL>(&Q.models[gb[k]][gm[k]][0], eta[k], a, b2, &elo, &ehi);
+              if (elo <= pr.max_thr) {  // may be an inlier of the precision bound
+                long long bin = (__double_as_longlong(elo) >> kBinShift) - bin_base;
+                bin = bin < 0 ? 0 : (bin > kBins - 1 ? kBins - 1 : bin);
+                atomicAdd(&hist_all[k * kBins + (uint32_t)bin], 1u);
+                ++c_hi[k];
+                if (ehi <= pr.max_thr) ++c_lo[k];
               }
             }
+          }
+#pragma unroll
+          for (uint32_t k = 0; k < kGroup; ++k) {
+            if (k >= gn) break;
+            uint32_t h = c_hi[k], l = c_lo[k];
             for (int o = 16; o >= 1; o >>= 1) {
-              const double ov = __shfl_xor_sync(0xffffffffu, lbv, o);
-              lbv = ov < lbv ? ov : lbv;
+              h += __shfl_xor_sync(0xffffffffu, h, o);
+              l += __shfl_xor_sync(0xffffffffu, l, o);
             }
-            // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
-            lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
+            if (lane == 0) { atomicAdd(&S.gcnt[2 * k], h); atomicAdd(&S.gcnt[2 * k + 1], l); }
           }
-          if (lane == 0) { Q.cnt[b][mi] = c_hi; Q.cnt_lo[b][mi] = c_lo; Q.lb[b][mi] = lbv; }
-          __syncwarp();
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+          if (cw < gn) {  // one warp per model of the group: lower bound of its best NFA from its histogram
+            uint32_t* hist = hist_all + (size_t)cw * kBins;
+            const uint32_t ch = S.gcnt[2 * cw], cl = S.gcnt[2 * cw + 1];
+            double lbv = DBL_MAX * 2.0;
+            if (ch > NS) {
+              // exclusive prefix over the bins, 32 at a time (conflict-free rows + a running carry)
+              uint32_t carry = 0;
+              for (uint32_t j = 0; j < (uint32_t)kBins; j += 32) {
+                const uint32_t v = hist[j + lane];
+                uint32_t incl = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                  const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                  if ((int)lane >= o) incl += u;
+                }
+                hist[j + lane] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+              }
+              __syncwarp();
+              // ranks (lo, hi] live in bin bb.  With e_(k) the true k-th smallest residual: at least k of the lower
+              // bounds are <= e_(k), so the k-th smallest LOWER BOUND is <= e_(k), hence
+              // NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]; extra ranks (c_hi >= c) only lower the minimum
+              for (uint32_t bb = lane; bb < (uint32_t)kBins; bb += 32) {
+                const uint32_t lo = hist[bb];
+                const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : ch;
+                const double la = S.la[bb];
+                for (uint32_t k = max(lo + 1, NS + 1); k <= hi; ++k) {
+                  const double g = pr.loge0 + la * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
+                  lbv = g < lbv ? g : lbv;
+                }
+              }
+              for (int o = 16; o >= 1; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, lbv, o);
+                lbv = ov < lbv ? ov : lbv;
+              }
+              // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
+              lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
+            }
+            if (lane == 0) { Q.cnt[gb[cw]][gm[cw]] = ch; Q.cnt_lo[gb[cw]][gm[cw]] = cl; Q.lb[gb[cw]][gm[cw]] = lbv; }
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");  // histograms and counters are reused by the next group
         }
       }
       __syncthreads();
@@ -486,7 +526,7 @@ int acransac_fused_ctas_per_sm(int model, uint32_t cap, bool huge) {
   const size_t per_sm = 227 * 1024;
   int n = (int)(per_sm / (smem + 1024));
   if (n < 1) n = 1;
-  const int by_regs = model == 2 ? 1 : 3;  // __launch_bounds__ of the kernel
+  const int by_regs = model == 2 ? 1 : 2;  // __launch_bounds__ of the kernel
   return n < by_regs ? n : by_regs;
 }
 

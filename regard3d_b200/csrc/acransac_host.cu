@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <numeric>
 #include <random>
 
@@ -38,7 +39,7 @@ struct PairState {
   uint32_t pt_ofs, tbl_ofs;
   // ACRANSAC state
   std::vector<uint32_t> vec_index;
-  std::mt19937 rng{std::mt19937::default_seed};
+  std::unique_ptr<std::mt19937[]> rngs;  // [0] generator (default seed), [1] its snapshot: host-round path only (5 KB)
   uint32_t iter = 0, nIter = 0, nIterReserve = 0;
   bool ac_mode = false;
   double minNFA = std::numeric_limits<double>::infinity();
@@ -49,7 +50,6 @@ struct PairState {
   // per-round bookkeeping
   uint32_t hyp_ofs = 0, hyp_n = 0;
   std::vector<uint32_t> swap_log;  // 7 swap targets per drawn iteration (undo log of the partial Fisher-Yates)
-  std::mt19937 snap_rng;
   uint32_t since_event = 0;
   bool best_changed = false, event = false;
   uint32_t best_hyp = 0, best_model = 0;
@@ -366,6 +366,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     ap.K[3] = views[s.J].focal; ap.K[4] = views[s.J].ppx; ap.K[5] = views[s.J].ppy;
     hpairs[a] = ap;
     if (!use_fused) {  // state of the host-round path only
+      s.rngs.reset(new std::mt19937[2]);
       s.vec_index.resize(M);
       std::iota(s.vec_index.begin(), s.vec_index.end(), 0u);
     }
@@ -504,12 +505,12 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
     parallel_for(round_threads, active.size(), [&](size_t ai) {
       const uint32_t a = active[ai];
       PairState& s = st[a];
-      s.snap_rng = s.rng;
+      s.rngs[1] = s.rngs[0];
       s.swap_log.resize((size_t)s.hyp_n * 7);
       for (uint32_t b = 0; b < s.hyp_n; ++b) {
         AcHyp& h = hhyp[s.hyp_ofs + b];
         h.pair = a;
-        uniform_sample7(sizeSample, s.rng, s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
+        uniform_sample7(sizeSample, s.rngs[0], s.vec_index, h.sample, &s.swap_log[(size_t)b * 7]);
       }
     });
     tm_sample += now_ms() - tq; tq = now_ms();
@@ -577,8 +578,8 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       if (consumed < s.hyp_n) {  // discard the speculative tail: undo its swaps, replay the generator
         for (uint32_t b = s.hyp_n; b-- > consumed;)
           for (int i = (int)sizeSample - 1; i >= 0; --i) std::swap(s.vec_index[i], s.vec_index[s.swap_log[(size_t)b * 7 + i]]);
-        s.rng = s.snap_rng;
-        for (uint32_t b = 0; b < consumed; ++b) skip_sample7(sizeSample, s.rng, (uint32_t)s.vec_index.size());
+        s.rngs[0] = s.rngs[1];
+        for (uint32_t b = 0; b < consumed; ++b) skip_sample7(sizeSample, s.rngs[0], (uint32_t)s.vec_index.size());
       }
       s.iter += consumed;
       s.since_event = s.event ? 0 : s.since_event + consumed;
