@@ -499,3 +499,55 @@ def liop_describe(img, kps, factor, want_patches=False):
     lib().orc_liop_describe(_p(img), C.c_int(img.shape[1]), C.c_int(img.shape[0]), _p(kps), C.c_uint64(n), C.c_float(factor),
                             _p(desc), _p(patches) if want_patches else None)
     return (desc, patches) if want_patches else desc
+
+
+# ---- steps either side of BA ----------------------------------------------------------------------
+def tracks_build(pairs, pair_ofs, m, min_length=2):
+    """TracksBuilder Build + Filter + ExportToSTL -> {track id: {view: feature}}."""
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    pair_ofs = np.ascontiguousarray(pair_ofs, np.uint64)
+    m = np.ascontiguousarray(m, indmatch_dtype)
+    cap_n = 2 * len(m) + 1
+    ids = np.zeros(cap_n, np.uint32)
+    ofs = np.zeros(cap_n + 1, np.uint64)
+    views = np.zeros(cap_n, np.uint32)
+    feats = np.zeros(cap_n, np.uint32)
+    lib().orc_tracks_build.restype = C.c_int64
+    T = lib().orc_tracks_build(_p(pairs), C.c_uint64(len(pairs)), _p(pair_ofs), _p(m), C.c_uint32(min_length), _p(ids), _p(ofs),
+                               _p(views), _p(feats), C.c_uint64(cap_n), C.c_uint64(cap_n))
+    assert T >= 0
+    return {int(ids[k]): dict(zip(views[int(ofs[k]):int(ofs[k + 1])].tolist(), feats[int(ofs[k]):int(ofs[k + 1])].tolist()))
+            for k in range(T)}
+
+
+def triangulate_landmarks(obs_ofs, obs_cam, obs_xy, poses, cam_intr, intrinsics, intr_model=None):
+    obs_ofs = np.ascontiguousarray(obs_ofs, np.uint64)
+    obs_cam = np.ascontiguousarray(obs_cam, np.uint32)
+    obs_xy = np.ascontiguousarray(obs_xy, np.float64)
+    poses = np.ascontiguousarray(poses, np.float64)
+    cam_intr = np.ascontiguousarray(cam_intr, np.uint32)
+    intrinsics = np.ascontiguousarray(intrinsics, np.float64)
+    n = len(obs_ofs) - 1
+    X = np.zeros((n, 3))
+    ok = np.zeros(n, np.uint8)
+    im = None if intr_model is None else np.ascontiguousarray(intr_model, np.uint8)
+    lib().orc_triangulate_landmarks(C.c_uint32(n), _p(obs_ofs), _p(obs_cam), _p(obs_xy), _p(poses), _p(cam_intr), _p(intrinsics),
+                                    None if im is None else _p(im), _p(X), _p(ok))
+    return X, ok.astype(bool)
+
+
+def landmark_checks(obs_ofs, obs_cam, obs_xy, poses, cam_intr, intrinsics, X, thr_px, intr_model=None):
+    obs_ofs = np.ascontiguousarray(obs_ofs, np.uint64)
+    obs_cam = np.ascontiguousarray(obs_cam, np.uint32)
+    obs_xy = np.ascontiguousarray(obs_xy, np.float64)
+    poses = np.ascontiguousarray(poses, np.float64)
+    cam_intr = np.ascontiguousarray(cam_intr, np.uint32)
+    intrinsics = np.ascontiguousarray(intrinsics, np.float64)
+    X = np.ascontiguousarray(X, np.float64)
+    n = len(obs_ofs) - 1
+    keep = np.zeros(len(obs_cam), np.uint8)
+    ang = np.zeros(n)
+    im = None if intr_model is None else np.ascontiguousarray(intr_model, np.uint8)
+    lib().orc_landmark_checks(C.c_uint32(n), _p(obs_ofs), _p(obs_cam), _p(obs_xy), _p(poses), _p(cam_intr), _p(intrinsics),
+                              None if im is None else _p(im), None, _p(X), C.c_double(thr_px), _p(keep), _p(ang))
+    return keep.astype(bool), ang

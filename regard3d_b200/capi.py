@@ -31,6 +31,8 @@ EXPORTS = [
     "r3d_sfm_num_views", "r3d_sfm_num_intrinsics", "r3d_sfm_num_poses", "r3d_sfm_num_landmarks", "r3d_sfm_add_view",
     "r3d_sfm_get_view", "r3d_sfm_add_intrinsic", "r3d_sfm_get_intrinsic", "r3d_sfm_add_pose", "r3d_sfm_get_pose",
     "r3d_sfm_add_landmark", "r3d_sfm_get_landmark", "r3d_debug_ba_jacobian_model", "r3d_debug_ba_prior", "r3d_sfm_ba_default_options", "r3d_sfm_bundle_adjust",
+    "r3d_tracks_build", "r3d_tracks_count", "r3d_tracks_get", "r3d_tracks_in_images", "r3d_tracks_free",
+    "r3d_sfm_structure_from_tracks", "r3d_sfm_remove_outliers",
 ]
 
 
@@ -154,6 +156,15 @@ def lib():
         L.r3d_sfm_get_pose.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.r3d_sfm_add_landmark.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.r3d_sfm_get_landmark.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_tracks_count.restype = C.c_uint64
+        L.r3d_tracks_count.argtypes = [C.c_void_p]
+        L.r3d_tracks_free.argtypes = [C.c_void_p]
+        L.r3d_tracks_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_tracks_get.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.r3d_tracks_in_images.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.r3d_sfm_structure_from_tracks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.r3d_sfm_remove_outliers.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_double, C.c_void_p, C.c_void_p]
+        L.r3d_sfm_bundle_adjust.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.r3d_save_matches.argtypes = [C.c_void_p, C.c_char_p]
         L.r3d_save_matches_bin.argtypes = [C.c_void_p, C.c_char_p]
         L.r3d_comm_world.argtypes = [C.c_void_p]
@@ -416,6 +427,58 @@ class SfmData:
         return out
 
 
+class Tracks:
+    """openMVG::tracks::STLMAPTracks handle (TracksBuilder Build + Filter + ExportToSTL)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().r3d_tracks_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def build(matches, min_length=2):
+        h = C.c_void_p()
+        rc = lib().r3d_tracks_build(matches.handle, C.c_uint32(min_length), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_tracks_build")
+        return Tracks(h)
+
+    def __len__(self):
+        return int(lib().r3d_tracks_count(self.h))
+
+    def get(self, k):
+        tid, n = C.c_uint32(), C.c_uint32()
+        pv, pf = C.c_void_p(), C.c_void_p()
+        rc = lib().r3d_tracks_get(self.h, C.c_uint64(k), C.byref(tid), C.byref(pv), C.byref(pf), C.byref(n))
+        if rc:
+            raise R3DError(rc, "r3d_tracks_get")
+        v = np.frombuffer((C.c_uint32 * n.value).from_address(pv.value), np.uint32).copy() if n.value else np.zeros(0, np.uint32)
+        f = np.frombuffer((C.c_uint32 * n.value).from_address(pf.value), np.uint32).copy() if n.value else np.zeros(0, np.uint32)
+        return tid.value, v, f
+
+    def to_dict(self):
+        """{track id: {view: feature}} like STLMAPTracks."""
+        out = {}
+        for k in range(len(self)):
+            tid, v, f = self.get(k)
+            out[tid] = dict(zip(v.tolist(), f.tolist()))
+        return out
+
+    def in_images(self, view_ids):
+        ids = np.ascontiguousarray(view_ids, np.uint32)
+        h = C.c_void_p()
+        rc = lib().r3d_tracks_in_images(self.h, _p(ids), C.c_uint32(len(ids)), C.byref(h))
+        if rc:
+            raise R3DError(rc, "r3d_tracks_in_images")
+        return Tracks(h)
+
+
 def debug_ba_jacobian_model(model, intr, ext, pose, X, obs):
     """Host evaluation of the analytic model of any of the five camera types (no GPU needed)."""
     intr, pose, X, obs = [np.ascontiguousarray(a, np.float64) for a in (intr, pose, X, obs)]
@@ -608,6 +671,32 @@ class Context:
         res = np.zeros((p["obs_xy"].shape[0], 2), np.float64)
         self._check(lib().r3d_ba_residuals(self._h, C.byref(s), _p(res)))
         return res
+
+    # ---- the steps either side of BA on an SfmData container --------------------------------
+    def structure_from_tracks(self, sd, tracks):
+        """Tracks -> landmarks of sd, triangulated from all posed views; returns the number of rejected tracks."""
+        n = C.c_uint32()
+        self._check(lib().r3d_sfm_structure_from_tracks(self._h, sd.h, tracks.h, C.byref(n)))
+        return n.value
+
+    def remove_outliers(self, sd, max_pixel_residual=4.0, min_track_length=2, min_angle_deg=2.0):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._check(lib().r3d_sfm_remove_outliers(self._h, sd.h, C.c_double(max_pixel_residual), C.c_uint32(min_track_length),
+                                                  C.c_double(min_angle_deg), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sfm_bundle_adjust(self, sd, max_iterations=500, refine_intrinsics=1, use_motion_priors=0, huber_a=16.0):
+        class SfmBAOptions(C.Structure):
+            _fields_ = [("solver", BAOptions), ("use_motion_priors", C.c_int)]
+        o = SfmBAOptions()
+        lib().r3d_sfm_ba_default_options(C.byref(o))
+        o.solver.max_iterations = max_iterations
+        o.solver.refine_intrinsics = refine_intrinsics
+        o.solver.huber_a = huber_a
+        o.use_motion_priors = use_motion_priors
+        summ = BASummary()
+        self._check(lib().r3d_sfm_bundle_adjust(self._h, sd.h, C.byref(o), C.byref(summ)))
+        return {k: getattr(summ, k) for k, _ in BASummary._fields_}
 
     def compute_matches(self, matches_dir, basenames, widths, heights, dist_ratio=0.6, dim=144,
                         compute_fundamental=True, matching_algorithm=4, progress=None, f_filename=None,
