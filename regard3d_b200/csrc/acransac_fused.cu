@@ -35,6 +35,9 @@ constexpr int kBatch = 24;            // most iterations drawn, solved and tier-
                                       // number of iterations since the last pool replacement: 4, 5, ... kBatch)
 constexpr double kApproxRel = 1e-9;   // relative accuracy of the tier-1 residuals (see approx_error)
 constexpr int kBins = 1024;           // tier-1 histogram: binades split in 32 (exponent + 5 mantissa bits)
+constexpr int kHistStride = kBins + kBins / 32;  // bin b lives at b + (b >> 5): a lane that owns 32 consecutive bins
+                                                 // walks them without bank conflicts
+__device__ __forceinline__ uint32_t bin_slot(uint32_t b) { return b + (b >> 5); }
 constexpr int kBinShift = 52 - 5;
 
 template <int MODEL>
@@ -54,7 +57,7 @@ template <int MODEL>
 struct FusedSmem {                    // fixed part of the shared memory (the sort / histogram region follows)
   Mt19937 rng;
   BatchBuf<MODEL> q[2];               // the batch being scored / replayed and the one warp 0 prepares meanwhile
-  double la[kBins];                   // logalpha of every bin's lower edge
+  double la[kHistStride];             // logalpha of every bin's lower edge (at bin_slot(b))
   double bestF[9];
   double s_nfa[kFWarps];
   uint32_t s_k[kFWarps];
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
     for (uint32_t b = tid; b < (uint32_t)kBins; b += kFThreads) {
       const long long kb = bin_base + (long long)b;
       const double lo = (b == 0 || kb <= 0) ? 0.0 : __longlong_as_double(kb << kBinShift);
-      S.la[b] = pr.logalpha0 + mult_error * dm::log10_det(lo + (double)FLT_EPSILON);
+      S.la[bin_slot(b)] = pr.logalpha0 + mult_error * dm::log10_det(lo + (double)FLT_EPSILON);
     }
     if (tid == 0) mt_seed(S.rng);
     __syncthreads();
@@ -311,6 +314,10 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
         // the batch's models as a flat list (iteration b, model mi) -- every consumer thread walks it identically
         uint32_t n_models_batch = 0;
         for (uint32_t b = 0; b < B; ++b) n_models_batch += Q.nm[b];
+        // the histograms alias the tier-2 sort buffer: clear them once per batch, every scan clears its own afterwards
+        for (uint32_t i = ctid; i < kGroup * (uint32_t)kHistStride; i += kConsumers) hist_all[i] = 0;
+        if (ctid < 2 * kGroup) S.gcnt[ctid] = 0;
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
         for (uint32_t g0 = 0; g0 < n_models_batch; g0 += kGroup) {
           const uint32_t gn = min(kGroup, n_models_batch - g0);
           // locate the group's models
@@ -324,9 +331,6 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
               seen += nmb;
             }
           }
-          for (uint32_t i = ctid; i < gn * (uint32_t)kBins; i += kConsumers) hist_all[i] = 0;
-          if (ctid < 2 * kGroup) S.gcnt[ctid] = 0;
-          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
           double eta[kGroup];
           for (uint32_t k = 0; k < gn; ++k) {
             const double* Fm = &Q.models[gb[k]][gm[k]][0];
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
               if (elo <= pr.max_thr) {  // may be an inlier of the precision bound
                 long long bin = (__double_as_longlong(elo) >> kBinShift) - bin_base;
                 bin = bin < 0 ? 0 : (bin > kBins - 1 ? kBins - 1 : bin);
-                atomicAdd(&hist_all[k * kBins + (uint32_t)bin], 1u);
+                atomicAdd(&hist_all[k * kHistStride + bin_slot((uint32_t)bin)], 1u);
                 ++c_hi[k];
                 if (ehi <= pr.max_thr) ++c_lo[k];
               }
@@ -364,45 +368,60 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
           }
           asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
           if (cw < gn) {  // one warp per model of the group: lower bound of its best NFA from its histogram
-            uint32_t* hist = hist_all + (size_t)cw * kBins;
+            uint32_t* hist = hist_all + (size_t)cw * kHistStride + lane * 33u;  // this lane's 32 consecutive bins
+            const double* lab = S.la + lane * 33u;
             const uint32_t ch = S.gcnt[2 * cw], cl = S.gcnt[2 * cw + 1];
             double lbv = DBL_MAX * 2.0;
             if (ch > NS) {
-              // exclusive prefix over the bins, 32 at a time (conflict-free rows + a running carry)
-              uint32_t carry = 0;
-              for (uint32_t j = 0; j < (uint32_t)kBins; j += 32) {
-                const uint32_t v = hist[j + lane];
-                uint32_t incl = v;
-                for (int o = 1; o < 32; o <<= 1) {
-                  const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                  if ((int)lane >= o) incl += u;
-                }
-                hist[j + lane] = carry + incl - v;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
+              uint32_t tot = 0;
+#pragma unroll 8
+              for (uint32_t j = 0; j < 32; ++j) tot += hist[j];
+              uint32_t incl = tot;
+              for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += u;
               }
-              __syncwarp();
-              // ranks (lo, hi] live in bin bb.  With e_(k) the true k-th smallest residual: at least k of the lower
-              // bounds are <= e_(k), so the k-th smallest LOWER BOUND is <= e_(k), hence
-              // NFA_k >= loge0 + la[bb] (k - NS) + logc_n[k] + logc_k[k]; extra ranks (c_hi >= c) only lower the minimum
-              for (uint32_t bb = lane; bb < (uint32_t)kBins; bb += 32) {
-                const uint32_t lo = hist[bb];
-                const uint32_t hi = bb + 1 < (uint32_t)kBins ? hist[bb + 1] : ch;
-                const double la = S.la[bb];
-                for (uint32_t k = max(lo + 1, NS + 1); k <= hi; ++k) {
-                  const double g = pr.loge0 + la * (double)(k - NS) + (double)lcn[k] + (double)logc_k[k];
-                  lbv = g < lbv ? g : lbv;
+              uint32_t run = incl - tot;  // lower bounds in the bins before this lane's
+              // Ranks (run, run + v] live in a bin with lower edge e_b.  With e_(k) the true k-th smallest residual: at
+              // least k of the lower bounds are <= e_(k), so the k-th smallest LOWER BOUND is <= e_(k), hence
+              //   NFA_k >= g_b(k) = loge0 + la[b] (k - NS) + logc_n[k] + logc_k[k];
+              // extra ranks (c_hi >= c) only lower the minimum.  log10 C(n, k) and log10 C(k, NS) are concave in k and
+              // the rest of g_b is linear, so over the ranks of one bin g_b is smallest at one of the two end ranks --
+              // for the exact binomials.  The float tables differ from them by at most tbl_err (accumulated by
+              // k_ac_tables while it sums), which the bound gives back twice over.
+              for (uint32_t j = 0; j < 32; ++j) {
+                const uint32_t v = hist[j];
+                if (v) {
+                  const uint32_t ka = max(run + 1, NS + 1), kb = run + v;
+                  if (ka <= kb) {
+                    const double la = lab[j];
+                    const double ga = la * (double)(ka - NS) + ((double)lcn[ka] + (double)logc_k[ka]);
+                    const double gb2 = la * (double)(kb - NS) + ((double)lcn[kb] + (double)logc_k[kb]);
+                    lbv = fmin(lbv, fmin(ga, gb2));
+                  }
+                  run += v;
+                  hist[j] = 0;
                 }
               }
               for (int o = 16; o >= 1; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, lbv, o);
                 lbv = ov < lbv ? ov : lbv;
               }
-              // a few ulp of slack for the (unproven) monotonicity of log10_det at its range-reduction seams
+              lbv += pr.loge0;
+              // table error (see above), then a few ulp for the (unproven) monotonicity of log10_det at its
+              // range-reduction seams
+              lbv -= 2.0 * (double)lcn[M + 1] + 1e-4;
               lbv = lbv - 1e-9 * (1.0 + fabs(lbv));
+            } else {
+#pragma unroll 8
+              for (uint32_t j = 0; j < 32; ++j) hist[j] = 0;
             }
-            if (lane == 0) { Q.cnt[gb[cw]][gm[cw]] = ch; Q.cnt_lo[gb[cw]][gm[cw]] = cl; Q.lb[gb[cw]][gm[cw]] = lbv; }
+            if (lane == 0) {
+              Q.cnt[gb[cw]][gm[cw]] = ch; Q.cnt_lo[gb[cw]][gm[cw]] = cl; Q.lb[gb[cw]][gm[cw]] = lbv;
+              S.gcnt[2 * cw] = 0; S.gcnt[2 * cw + 1] = 0;
+            }
           }
-          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");  // histograms and counters are reused by the next group
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");  // cleared histograms and counters: next group
         }
       }
       __syncthreads();

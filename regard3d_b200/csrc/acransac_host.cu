@@ -297,7 +297,7 @@ int filter_pairs_model(r3d_ctx* ctx, DeviceWorker& w, int model, double precisio
       s.pt_ofs = (uint32_t)pt_total;
       s.tbl_ofs = (uint32_t)tbl_total;
       pt_total += M;
-      tbl_total += M + 1;
+      tbl_total += M + 2;  // logc_n[0..M] and the table's error bound (k_ac_tables)
       maxM = std::max(maxM, M);
       st.push_back(std::move(s));
     }

@@ -134,11 +134,17 @@ __global__ void __launch_bounds__(128) k_ac_tables(const AcPair* __restrict__ pa
   float* t = logc_n + pairs[a].tbl_ofs;
   t[0] = 0.f;
   float r = 0.f;
+  // t[n + 1] = a bound on |t[k] - log10 C(n, k)| for every k: each step rounds the difference and the running sum
+  // (half an ulp of each) and reads two table entries that are within an ulp of the true logarithms
+  double err = 0.0;
   for (uint32_t i = 1; i <= n / 2; ++i) {
-    r = __fadd_rn(r, __fsub_rn(vlog10[n - i + 1], vlog10[i]));
+    const float d = __fsub_rn(vlog10[n - i + 1], vlog10[i]);
+    r = __fadd_rn(r, d);
     t[i] = r;
+    err += 5.97e-8 * ((double)fabsf(r) + (double)fabsf(d)) + 1.2e-7 * ((double)vlog10[n - i + 1] + (double)vlog10[i]);
   }
   for (uint32_t k = n / 2 + 1; k <= n; ++k) t[k] = (k >= n) ? 0.f : t[n - k];
+  t[n + 1] = (float)(err * 1.001 + 1e-6);
 }
 
 int launch_ac_tables(r3d_ctx* ctx, DeviceWorker& w, const AcPair* pairs, uint32_t n_pairs, const float* vlog10, float* logc_n) {

@@ -31,8 +31,10 @@ using namespace tcx;
 namespace {
 
 constexpr int kMaxStages2 = 12;
-constexpr int kEpiWarps2 = 8;
-constexpr int kThreads2 = 32 * (4 + kEpiWarps2);
+// Epilogue warps per CTA: 8 (two per TMEM lane quarter, 128 accumulator columns each) or 16 (four per quarter, 64
+// columns each).  The epilogue's cost per tile does not shrink with the descriptor dimension while the MMA time does
+// (5 K-steps at D = 64 against 10 at D = 144), and it is bound by the latency of its TMEM-load / min-tree chains, not
+// by ALU throughput: short descriptors get twice the warps to hide it.
 constexpr uint32_t kTmemCols2 = 512;
 constexpr uint32_t kTileN = 256;  // database rows per tile (both halves)
 // kind::f16, D = f32, A = B = f16 K-major, N = 256, M = 256 (cta_group::2)
@@ -40,8 +42,8 @@ constexpr uint32_t kInstrDesc2 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | (
 
 }  // namespace
 
-template <bool kVote>
-__global__ void __launch_bounds__(kThreads2, 1)
+template <bool kVote, int kEpiWarps2>
+__global__ void __launch_bounds__(32 * (4 + kEpiWarps2), 1)
 k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
                     const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
                     uint32_t* __restrict__ keys_out, uint32_t nkb, uint32_t ksteps, uint32_t n_stages,
@@ -63,7 +65,7 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
   const uint32_t bar_tfull = bar_qempty + 16;                     // [2]
   const uint32_t bar_tempty = bar_tfull + 16;                     // [2] (leader)
   const uint32_t tmem_slot = bar_tempty + 16;
-  const uint32_t key_xchg = (tmem_slot + 16 + 15u) & ~15u;        // 128 rows x 8 u32: keys of the upper column half
+  const uint32_t key_xchg = (tmem_slot + 16 + 15u) & ~15u;        // (column groups - 1) x 128 rows x 8 u32: partial key sets
   unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = (volatile uint32_t*)(gen_base + (tmem_slot - base));
   uint32_t* xchg = (uint32_t*)(gen_base + (key_xchg - base));
@@ -211,8 +213,11 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
     }
   } else if (warp >= 4) {
     // ======================================= epilogue (both CTAs) =======================================
+    constexpr uint32_t kColGroups = kEpiWarps2 / 4;          // warps that share a TMEM lane quarter
+    constexpr uint32_t kColsPerWarp = kTileN / kColGroups;   // accumulator columns of one warp: 128 or 64
+    constexpr uint32_t kLoads = kColsPerWarp / 32;
     const uint32_t ew = warp - 4u;
-    const uint32_t half = ew >> 2;            // 0: accumulator columns 0-127, 1: columns 128-255
+    const uint32_t half = ew >> 2;            // column group: accumulator columns [half * kColsPerWarp, +kColsPerWarp)
     const uint32_t lane_quarter = warp & 3u;
     const uint32_t r_tempty0 = mapa_shared(bar_tempty, 0);
     uint32_t acc = 0, accphase = 0;
@@ -227,52 +232,49 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
       for (uint32_t t = 0; t < ntiles; ++t) {
         mbar_wait(bar_tfull + 8 * acc, accphase);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((lane_quarter * 32u) << 16) + acc * kTileN + half * 128u;
+        const uint32_t taddr = tmem_base + ((lane_quarter * 32u) << 16) + acc * kTileN + half * kColsPerWarp;
         // accumulator column j of the 256-wide tile is database row t*256 + j (rows 0-127 from the leader's
         // half, 128-255 from the peer's)
-        const uint32_t chunk0 = (t * kTileN + half * 128u) / kChunk;
-        uint32_t va[32], vb[32];
+        const uint32_t chunk0 = (t * kTileN + half * kColsPerWarp) / kChunk;
+        uint32_t v[2][32];
         constexpr uint32_t kCpl = 32 / kChunk;
-        tc_ld32(taddr, va);
-        tc_wait_ld(va);
-        tc_ld32(taddr + 32, vb);
+        tc_ld32(taddr, v[0]);
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(va + c * kChunk, chunk0 + c, keep_mask, key);
-        tc_wait_ld(vb);
-        tc_ld32(taddr + 64, va);
+        for (uint32_t sblk = 0; sblk < kLoads; ++sblk) {
+          tc_wait_ld(v[sblk & 1u]);
+          if (sblk + 1 < kLoads) tc_ld32(taddr + 32 * (sblk + 1), v[(sblk + 1) & 1u]);
+          if (sblk + 1 == kLoads) {  // the stage is drained: release it before the last block's arithmetic
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
+          }
 #pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(vb + c * kChunk, chunk0 + kCpl + c, keep_mask, key);
-        tc_wait_ld(va);
-        tc_ld32(taddr + 96, vb);
-#pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(va + c * kChunk, chunk0 + 2 * kCpl + c, keep_mask, key);
-        tc_wait_ld(vb);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
-#pragma unroll
-        for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(vb + c * kChunk, chunk0 + 3 * kCpl + c, keep_mask, key);
+          for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(v[sblk & 1u] + c * kChunk, chunk0 + sblk * kCpl + c, keep_mask, key);
+        }
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
       }
-      // merge the two column halves of every query row: the upper half hands its keys over in shared memory
+      // merge the column groups of every query row: groups 1.. hand their keys over in shared memory
       const uint32_t r = lane_quarter * 32u + lane;  // row inside the 128-query block
-      if (half == 1) {
+      if (half != 0) {
 #pragma unroll
-        for (int i = 0; i < kNumKeys; ++i) xchg[r * 8 + i] = __float_as_uint(key[i]);
+        for (int i = 0; i < kNumKeys; ++i) xchg[((half - 1u) * 128u + r) * 8 + i] = __float_as_uint(key[i]);
       }
       asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps2 * 32) : "memory");
       if (half == 0) {
 #pragma unroll
-        for (int i = 0; i < kNumKeys; ++i) {
-          float x = __uint_as_float(xchg[r * 8 + i]);
+        for (uint32_t g = 0; g + 1 < kColGroups; ++g) {
 #pragma unroll
-          for (int j = 0; j < kNumKeys - 1; ++j) {
-            const float hi = fmaxf(key[j], x);
-            key[j] = fminf(key[j], x);
-            x = hi;
+          for (int i = 0; i < kNumKeys; ++i) {
+            float x = __uint_as_float(xchg[(g * 128u + r) * 8 + i]);
+#pragma unroll
+            for (int j = 0; j < kNumKeys - 1; ++j) {
+              const float hi = fmaxf(key[j], x);
+              key[j] = fminf(key[j], x);
+              x = hi;
+            }
+            key[kNumKeys - 1] = fminf(key[kNumKeys - 1], x);
           }
-          key[kNumKeys - 1] = fminf(key[kNumKeys - 1], x);
         }
         const uint32_t row = wi.sb * kTileRows + r;
         uint4 o0, o1;
@@ -317,19 +319,27 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
   }();
   int n_qbuf = want_qbuf;
   if (ring_stages2(nkb, n_qbuf) < 4) n_qbuf = 1;  // very wide descriptors: keep the ring deep enough instead
+  // 16 epilogue warps for short descriptors (<= 6 K-steps: D <= 80), 8 otherwise; R3D_K1_EPI = 8 | 16 forces one
+  static const int force_epi = []() {
+    const char* e = getenv("R3D_K1_EPI");
+    return e ? atoi(e) : 0;
+  }();
+  const int epi = force_epi == 8 || force_epi == 16 ? force_epi : (ksteps <= 6 ? 16 : 8);
   const int stages = ring_stages2(nkb, n_qbuf);
-  const size_t smem = 1024 + (size_t)(n_qbuf * nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 6 + 4) + 32 + 16 + 128 * 8 * 4;
+  const size_t smem = 1024 + (size_t)(n_qbuf * nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 6 + 4) + 32 + 16 +
+                      (size_t)(epi / 4 - 1) * 128 * 8 * 4;
   static const bool vote = []() {  // R3D_K1_VOTE=0: always run the insertion network (A/B switch)
     const char* e = getenv("R3D_K1_VOTE");
     return !(e && atoi(e) == 0);
   }();
-  auto kernel = vote ? k_l2_candidates_2sm<true> : k_l2_candidates_2sm<false>;
+  auto kernel = epi == 16 ? (vote ? k_l2_candidates_2sm<true, 16> : k_l2_candidates_2sm<false, 16>)
+                          : (vote ? k_l2_candidates_2sm<true, 8> : k_l2_candidates_2sm<false, 8>);
   R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   uint32_t grid = (uint32_t)w.sm_count / 2 * 2;
   if (n_items < grid) grid = n_items;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads2);
+  cfg.blockDim = dim3(32 * (4 + epi));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = w.stream;
   cudaLaunchAttribute attr[1];
