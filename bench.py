@@ -317,7 +317,7 @@ def main():
         m = step_resident()
     sampler = ClockSampler(local_rank)
     cand_ms, rerank_ms, fb_ms, dev_ms, host_ms, launches = [], [], [], [], [], 0
-    fbq = q = rejq = 0
+    fbq = q = rejq = stbq = stcq = 0
     d2h_lib = 0
     barrier()
     sampler.start()
@@ -329,6 +329,7 @@ def main():
         dev_ms.append(t["ms_device_total"]); host_ms.append(t["ms_host_post"])
         launches += t["kernel_launches"]
         fbq += t["fallback_queries"]; q += t["queries"]; rejq += t["rejected_queries"]
+        stbq += t.get("third_chunk_queries", 0); stcq += t.get("fifth_chunk_queries", 0)
     barrier()
     t_res = time.perf_counter() - t0
     n_matches, n_match_pairs = sum_over_ranks(m.total, m.num_pairs)
@@ -475,7 +476,9 @@ def main():
                              "host_dedup": float(np.mean(host_ms)), "of": "rank 0's shard"},
             "result": {"pairs_with_matches": int(n_match_pairs), "matches": int(n_matches),
                        "fallback_query_frac": fbq / max(q, 1), "early_rejected_query_frac": rejq / max(q, 1),
-                       "gathered_in_pair_order": gather_ok},
+                       "stage_b_query_frac": stbq / max(q, 1), "stage_b_key5_query_frac": stcq / max(q, 1),
+                       "gathered_in_pair_order": gather_ok,
+                       "gather_ms": (gather.ms if gather is not None else None)},
         }
         if filt is not None:
             line["f_filter"] = filt

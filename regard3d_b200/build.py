@@ -40,16 +40,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out_path=None, objdir_name="build"):
+    """defines / out_path / objdir_name: an A/B variant of the library (e.g. -DR3D_CHUNK=16) next to the default one."""
+    if out_path is None and not force and not needs_build():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, objdir_name)
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
-        flags = list(NVCC_FLAGS)
+        flags = list(NVCC_FLAGS) + ["-D" + d for d in defines]
         if os.path.basename(src) in NO_FMAD:
             flags[flags.index("--fmad=true")] = "--fmad=false"
         cmd = [NVCC] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
@@ -65,10 +66,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("libr3dgpu build failed")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++",
+    cmd = [NVCC, "-shared", "-o", out_path or OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++",
                                                "-Xcompiler", "-pthread", "-lpthread", "-ldl"]
     subprocess.check_call(cmd)
-    return OUT
+    return out_path or OUT
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libr3dgpu.so")
+LIB_PATH = os.environ.get("R3D_LIB") or os.path.join(_HERE, "libr3dgpu.so")  # R3D_LIB: an A/B build of the same ABI
 
 R3D_F32, R3D_U8 = 0, 1
 MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP, MATCH_MUTUAL_NN = 0, 1, 2, 4

@@ -708,6 +708,203 @@ __global__ void __launch_bounds__(1024, 1) k_chol_fused(double* A, double* Lm, d
   }
 }
 
+// ---- envelope (skyline) Cholesky: one thread-block CLUSTER, for reduced systems with sparse co-visibility ---------
+// Ceres solves the reduced camera system with a sparse Cholesky (SPARSE_SCHUR); the counterpart here keeps the dense
+// (n+1) x n storage but only touches the ENVELOPE: row i of S (and of L: the factorisation fills nothing outside it) is
+// zero left of first_col(i) = the first camera that shares a point with camera i; intrinsics rows and the right-hand
+// side row reach column 0.  At tile granularity: ft[ti] = first column tile of row tile ti, and panel k only involves
+// the ACTIVE row tiles R_k = { ti > k : ft[ti] <= k } -- for an image sequence a handful (the band, the intrinsics /
+// rhs border, a wrap-around if the sequence closes) instead of all nblk - k.  With so little work per panel the two
+// grid-wide barriers of k_chol_fused are what costs; here a panel is
+//   potrf   warp 0, the 32 x 32 diagonal tile in registers (lane = row, columns exchanged with shuffles); the rhs row
+//           rides along as an extra row when it lies inside the diagonal tile (last panel)
+//   trsm    one warp per active row tile: X L_kk^T = A_panel by substitution (lane = row, L_kk broadcast from shared
+//           memory); X goes to Lm and, transposed, to shared memory
+//   syrk    one warp per pair of active tiles, 4 x 8 outputs per lane: A_ij -= X_i X_j^T
+// Every CTA of the cluster repeats potrf and trsm for itself (cheap, and it removes two of the three exchanges); only
+// the syrk pairs -- the bulk of the flops -- are dealt round-robin over the cluster's warps, so ONE hardware cluster
+// barrier per panel orders "trailing tiles updated" before "next panel loaded".  Data written by another CTA is read
+// with ld.global.cg (L2): the SMs' L1 caches are not coherent.  The backward substitution (CTA 0) skips what lies
+// outside the envelope too.  The host picks this kernel when every |R_k| <= kEnvMaxActive and the tile-pair count says
+// it is cheaper than the dense cooperative kernel.
+constexpr int kEnvThreads = 512;
+constexpr int kEnvWarps = kEnvThreads / 32;
+constexpr int kEnvMaxActive = 16;
+constexpr int kEnvMaxCluster = 8;
+constexpr size_t kEnvSmemBytes = ((size_t)NB * (NB + 1) + NB + (size_t)kEnvMaxActive * NB * NB) * sizeof(double) + 64 * sizeof(int);
+__device__ __forceinline__ void env_cluster_sync(bool clustered) {
+  if (clustered) {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(kEnvThreads, 1) k_chol_envelope(double* A, double* Lm, int n, const int* __restrict__ ft, double* flag,
+                                                                  double* x_out) {
+  extern __shared__ __align__(16) double env_smem[];
+  typedef double Tile[NB][NB + 1];
+  Tile& Ls = *(Tile*)(env_smem);                        // L_kk, row-major (padded)
+  double* invd = env_smem + NB * (NB + 1);              // 1 / L_kk[j][j]
+  double* Xt = invd + NB;                               // [slot][t][row]: the panel's L_ik, transposed
+  int* act = reinterpret_cast<int*>(Xt + (size_t)kEnvMaxActive * NB * NB);  // act[0] = count, act[1..] = tiles
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ncta = gridDim.x, cta = blockIdx.x;         // the grid is one cluster
+  const bool clustered = ncta > 1;
+  const int nblk = (n + NB - 1) / NB;
+  const int ntr = (n + 1 + NB - 1) / NB;                // row tiles including the rhs row n
+  for (int kbi = 0; kbi < nblk; ++kbi) {
+    const int k0 = kbi * NB, kb = min(NB, n - k0);
+    if (warp == 1) {  // the panel's active row tiles, ascending
+      int cnt = 0;
+      for (int base = 0; base < ntr; base += 32) {
+        const int ti = base + lane;
+        const bool a = ti > kbi && ti < ntr && ft[ti] <= kbi;
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (a) act[1 + cnt + __popc(m & ((1u << lane) - 1u))] = ti;
+        cnt += __popc(m);
+      }
+      if (lane == 0) act[0] = cnt;
+    }
+    if (warp == 0) {  // ---- potrf of the diagonal tile; lane kb carries the rhs row when it lies in this tile ----
+      const bool rhs_lane = kb < NB && lane == kb && k0 + kb == n;
+      double a[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+        a[c] = ((lane < kb || rhs_lane) && c < kb) ? __ldcg(&A[(size_t)(k0 + lane) * n + k0 + c]) : (lane == c ? 1.0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (j < kb) {  // (warp-uniform) columns beyond kb are identity padding
+          const double piv = __shfl_sync(0xffffffffu, a[j], j);
+          const bool bad = !(piv > 0.0);
+          const double rs = bad ? 1.0 : rsqrt(piv);
+          if (bad && lane == 0 && cta == 0) *flag = 1.0;
+          double lrj = a[j] * rs;                       // L[r][j] for r > j
+          if (lane == j) { lrj = bad ? 1.0 : piv * rs; invd[j] = rs; }
+          a[j] = lrj;
+#pragma unroll
+          for (int c = j + 1; c < NB; ++c) {
+            const double lcj = __shfl_sync(0xffffffffu, lrj, c);
+            if (lane >= c && c < kb) a[c] -= lrj * lcj;
+          }
+        } else if (lane == j) {
+          invd[j] = 1.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        const double v = c <= lane ? a[c] : 0.0;
+        Ls[lane][c] = (lane < kb || c == lane) ? v : 0.0;   // the rhs lane is not a row of L_kk
+        if (cta == 0 && (lane < kb || rhs_lane) && c < kb && c <= lane) Lm[(size_t)(k0 + lane) * n + k0 + c] = v;
+      }
+    }
+    __syncthreads();
+    const int nact = act[0];
+    // ---- trsm: a warp per active tile (every CTA for itself) ----
+    for (int slot = warp; slot < nact; slot += kEnvWarps) {
+      const int ti = act[1 + slot];
+      const int row = ti * NB + lane;
+      const bool valid = row <= n;
+      double a[NB];
+#pragma unroll
+      for (int c = 0; c < NB; ++c) a[c] = (valid && c < kb) ? __ldcg(&A[(size_t)row * n + k0 + c]) : 0.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const double xj = a[j] * invd[j];
+        a[j] = xj;
+#pragma unroll
+        for (int m = j + 1; m < NB; ++m) a[m] -= xj * Ls[m][j];
+      }
+      double* xt = Xt + (size_t)slot * NB * NB;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) {
+        xt[c * NB + lane] = a[c];
+        if (cta == 0 && valid && c < kb) Lm[(size_t)row * n + k0 + c] = a[c];
+      }
+    }
+    __syncthreads();
+    // ---- syrk over the pairs (ia >= ib) of active tiles, dealt over the cluster's warps;
+    //      lane = (4 rows, 8 columns) of the 32 x 32 target ----
+    {
+      const int npairs = nact * (nact + 1) / 2;
+      const int lr = lane >> 2, lc = lane & 3;
+      for (int pi = warp * ncta + cta; pi < npairs; pi += kEnvWarps * ncta) {
+        int ia = (int)((sqrtf(8.f * (float)pi + 1.f) - 1.f) * 0.5f);
+        while ((ia + 1) * (ia + 2) / 2 <= pi) ++ia;
+        while (ia * (ia + 1) / 2 > pi) --ia;
+        const int ib = pi - ia * (ia + 1) / 2;
+        const double* xa = Xt + (size_t)ia * NB * NB + 4 * lr;
+        const double* xb = Xt + (size_t)ib * NB * NB + 8 * lc;
+        double acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
+        for (int t = 0; t < NB; ++t) {
+          const double2 a01 = *reinterpret_cast<const double2*>(xa + t * NB);
+          const double2 a23 = *reinterpret_cast<const double2*>(xa + t * NB + 2);
+          const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+          double bv[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            const double2 b2 = *reinterpret_cast<const double2*>(xb + t * NB + j);
+            bv[j] = b2.x; bv[j + 1] = b2.y;
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
+        }
+        const int row0 = act[1 + ia] * NB + 4 * lr, col0 = act[1 + ib] * NB + 8 * lc;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = row0 + i;
+          if (row > n) continue;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = col0 + j;
+            if (col < n && col <= row) A[(size_t)row * n + col] = __ldcg(&A[(size_t)row * n + col]) - acc[i][j];
+          }
+        }
+      }
+    }
+    env_cluster_sync(clustered);
+  }
+  if (cta != 0) return;
+  // ---- backward substitution L^T x = y (y = row n of Lm), inside the envelope ----
+  for (int j = tid; j < n; j += kEnvThreads) x_out[j] = __ldcg(&Lm[(size_t)n * n + j]);
+  __syncthreads();
+  for (int kbi = nblk - 1; kbi >= 0; --kbi) {
+    const int k0 = kbi * NB, kb = min(NB, n - k0);
+    if (warp == 0) {  // x_k = L_kk^-T y_k: lane c holds column c of L_kk
+      double col[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j)
+        col[j] = (j < kb && lane < kb && lane <= j) ? __ldcg(&Lm[(size_t)(k0 + j) * n + k0 + lane]) : (j == lane ? 1.0 : 0.0);
+      double y = lane < kb ? __ldcg(&x_out[k0 + lane]) : 0.0;
+      double inv = 1.0;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) if (j == lane) inv = 1.0 / col[j];
+#pragma unroll
+      for (int j = NB - 1; j >= 0; --j) {
+        const double xj = __shfl_sync(0xffffffffu, y * inv, j);
+        if (lane < j) y -= col[j] * xj;
+        if (lane == j) y = xj;
+      }
+      if (lane < kb) x_out[k0 + lane] = y;
+      invd[lane] = lane < kb ? y : 0.0;  // x_k for the update below
+    }
+    __syncthreads();
+    const int lo = min(ft[kbi] * NB, k0);
+    for (int j = lo + tid; j < k0; j += kEnvThreads) {  // y_j -= L_kj^T x_k
+      double sacc = 0.0;
+      for (int tt = 0; tt < kb; ++tt) sacc += __ldcg(&Lm[(size_t)(k0 + tt) * n + j]) * invd[tt];
+      x_out[j] = __ldcg(&x_out[j]) - sacc;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- back substitution ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_ba_backsub(Dev d) {
   const uint32_t ip = blockIdx.x * blockDim.x + threadIdx.x;
@@ -815,6 +1012,7 @@ struct DeviceArrays {  // blocks come from (and return to) the worker's size-buc
 };
 
 struct BatchPlan {  // device tables of the batched Schur kernel + the points that go through the general CTA kernel
+  std::vector<uint32_t> first_cam;  // per camera: the lowest-numbered camera it shares a point with (envelope of S)
   r3d::ba::BatchTables t{};
   uint32_t n_batches = 0;
   const uint32_t* d_long = nullptr;  // point ids for k_ba_schur_cta
@@ -911,6 +1109,16 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
     using namespace r3d::ba;
     const uint32_t n_pts = p->n_pts;
     const int threads = std::max(1, ctx->host_threads);
+    plan->first_cam.resize(p->n_cams);
+    for (uint32_t c = 0; c < p->n_cams; ++c) plan->first_cam[c] = c;
+    for (uint32_t i = 0; i < n_pts; ++i) {
+      uint32_t mn = p->n_cams;
+      for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) mn = std::min(mn, p->obs_cam[hobs[t]]);
+      for (uint32_t t = hofs[i]; t < hofs[i + 1]; ++t) {
+        uint32_t& f = plan->first_cam[p->obs_cam[hobs[t]]];
+        f = std::min(f, mn);
+      }
+    }
     // (0) which points the batched kernel can take: <= 32 observations, <= 2 intrinsic groups, no camera twice.
     //     Everything else (long tracks first of all) goes to the general CTA-per-point kernel.
     std::vector<uint32_t> key(n_pts, 0), nent(n_pts, 0);
@@ -1170,6 +1378,60 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
     R3D_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, r3d::ba::k_chol_fused, 1024, r3d::ba::kCholSmemBytes));
     if (per_sm < 1) return fail(ctx, R3D_ERR_CUDA, "bundle adjustment: k_chol_fused does not fit on an SM");
   }
+  // Envelope of the reduced system at tile granularity (the union over ranks: every rank factors the summed S)
+  bool use_env = false;
+  int env_ctas = r3d::ba::kEnvMaxCluster;  // CTAs of the envelope kernel's cluster
+  int* d_ft = nullptr;
+  {
+    const int ntr = (nB + 1 + r3d::ba::NB - 1) / r3d::ba::NB;
+    std::vector<double> fc(p->n_cams);
+    for (uint32_t c = 0; c < p->n_cams; ++c) fc[c] = -(double)plan.first_cam[c];
+    if (ctx->comm_world > 1 && p->n_cams) {  // min over ranks = -max(-x)
+      double* d_fc = nullptr;
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_fc, p->n_cams));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_fc, fc.data(), (size_t)p->n_cams * 8, cudaMemcpyHostToDevice, w.stream));
+      if ((rc = comm_allreduce(ctx, w.stream, d_fc, p->n_cams, kCommMax))) return rc;
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(fc.data(), d_fc, (size_t)p->n_cams * 8, cudaMemcpyDeviceToHost, w.stream));
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));
+    }
+    std::vector<int> ft(ntr, 0);
+    for (int ti = 0; ti < ntr; ++ti) {
+      int first = ti * r3d::ba::NB;
+      for (int r = ti * r3d::ba::NB; r < std::min((ti + 1) * r3d::ba::NB, nB + 1); ++r) {
+        const int fcol = r < 6 * (int)p->n_cams ? 6 * (int)(-fc[r / 6]) : 0;  // intrinsics rows, rhs row: from column 0
+        first = std::min(first, fcol);
+      }
+      ft[ti] = first / r3d::ba::NB;
+    }
+    // per panel: active row tiles -> tile pairs; compare with the dense kernel's two grid barriers + full trailing update
+    {
+      const char* e = getenv("R3D_BA_ENV_CTAS");
+      if (e && atoi(e) >= 1 && atoi(e) <= r3d::ba::kEnvMaxCluster) env_ctas = atoi(e);
+    }
+    int max_act = 0;
+    double est_env = 0.0, est_dense = 0.0;
+    for (int k = 0; k < chol_blocks; ++k) {
+      int act = 0;
+      for (int ti = k + 1; ti < ntr; ++ti) act += ft[ti] <= k;
+      max_act = std::max(max_act, act);
+      est_env += 4.5 + 0.27 * std::ceil((double)(act * (act + 1) / 2) / (double)env_ctas) + 0.05 * act;
+      const int rem = ntr - k - 1;
+      est_dense += 20.0 + 3.0 * std::ceil((double)(rem * (rem + 1) / 2) / (4.0 * w.sm_count));
+    }
+    const char* force = getenv("R3D_BA_CHOL");
+    use_env = max_act <= r3d::ba::kEnvMaxActive && est_env < est_dense;
+    if (force && std::string(force) == "dense") use_env = false;
+    if (force && std::string(force) == "envelope" && max_act <= r3d::ba::kEnvMaxActive) use_env = true;
+    if (use_env) {
+      R3D_CUDA_TRY(ctx, mem.alloc(&d_ft, (size_t)ntr));
+      R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_ft, ft.data(), (size_t)ntr * sizeof(int), cudaMemcpyHostToDevice, w.stream));
+      R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // ft is a local
+      R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(r3d::ba::k_chol_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r3d::ba::kEnvSmemBytes));
+    }
+    static const bool dbg = getenv("R3D_DEBUG_TIMING") != nullptr;
+    if (dbg) fprintf(stderr, "[r3d] BA linear solve: %s (n = %d, %d tiles, <= %d active row tiles per panel, estimate %.0f vs %.0f us dense)\n",
+                     use_env ? "envelope Cholesky, one cluster" : "dense cooperative Cholesky", nB, ntr, max_act, est_env, est_dense);
+  }
   double h_scal[8];
   auto read_scal = [&]() -> int {
     R3D_CUDA_TRY(ctx, cudaMemcpyAsync(h_scal, d.scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, w.stream));
@@ -1241,7 +1503,21 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
       dim3 b(32, 8), g((nB + 31) / 32, (nB + 7) / 8);
       r3d::ba::k_ba_finish_S<<<g, b, 0, w.stream>>>(d, inv_radius);
     }
-    {
+    if (use_env) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(env_ctas);
+      cfg.blockDim = dim3(r3d::ba::kEnvThreads);
+      cfg.dynamicSmemBytes = r3d::ba::kEnvSmemBytes;
+      cfg.stream = w.stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = env_ctas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      R3D_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, r3d::ba::k_chol_envelope, d.S, d_Lm, nB, (const int*)d_ft, d.scal + 4, d.delta));
+    } else {
       double *pA = d.S, *pL = d_Lm, *pI = d_Linv, *pflag = d.scal + 4, *px = d.delta;
       int pn = nB;
       void* cargs[] = {&pA, &pL, &pI, &pn, &pflag, &px};

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <map>
 #include <new>
 #include <numeric>
@@ -12,6 +13,8 @@
 #include <vector>
 
 #include "r3d_matches.h"
+
+namespace r3d { void pool_parallel_for(int n_threads, size_t n, const std::function<void(size_t)>& f); }
 
 extern "C" {
 
@@ -49,19 +52,26 @@ int r3d_matches_from_csr(const uint32_t* pairs, uint64_t n_pairs, const uint64_t
 
 /* Flat copy of the map (what a host gather across ranks ships): pairs_out 2 x num_pairs view ids in map order,
  * ofs_out num_pairs + 1 prefix offsets, matches_out total entries.  Any output may be NULL. */
-int r3d_matches_export_csr(const r3d_matches* m, uint32_t* pairs_out, uint64_t* ofs_out, r3d_indmatch* matches_out) {
+int r3d_matches_export_csr(const r3d_matches* m, uint32_t* pairs_out, uint64_t* ofs_out, r3d_indmatch* matches_out) try {
   if (!m) return R3D_ERR_INVALID;
   const uint64_t P = m->pairs.size() / 2;
   if (pairs_out && P) std::memcpy(pairs_out, m->pairs.data(), sizeof(uint32_t) * 2 * P);
-  uint64_t acc = 0;
-  for (uint64_t k = 0; k < P; ++k) {
-    if (ofs_out) ofs_out[k] = acc;
-    if (matches_out && m->per[k].n) std::memcpy(matches_out + acc, m->per[k].p, sizeof(r3d_indmatch) * m->per[k].n);
-    acc += m->per[k].n;
+  std::vector<uint64_t> ofs(P + 1, 0);
+  for (uint64_t k = 0; k < P; ++k) ofs[k + 1] = ofs[k] + m->per[k].n;
+  if (ofs_out) std::memcpy(ofs_out, ofs.data(), sizeof(uint64_t) * (P + 1));
+  if (matches_out && P) {
+    // slabs of pairs of ~4 MB each, copied by the persistent host pool (a multi-GPU gather exports hundreds of MB)
+    std::vector<uint64_t> cut{0};
+    for (uint64_t k = 1; k <= P; ++k)
+      if (k == P || (ofs[k] - ofs[cut.back()]) * sizeof(r3d_indmatch) >= ((size_t)4 << 20)) cut.push_back(k);
+    const std::function<void(size_t)> body = [&](size_t c) {
+      for (uint64_t k = cut[c]; k < cut[c + 1]; ++k)
+        if (m->per[k].n) std::memcpy(matches_out + ofs[k], m->per[k].p, sizeof(r3d_indmatch) * m->per[k].n);
+    };
+    r3d::pool_parallel_for(16, cut.size() - 1, body);
   }
-  if (ofs_out) ofs_out[P] = acc;
   return R3D_OK;
-}
+} catch (...) { return R3D_ERR_NOMEM; }
 
 void r3d_free_matches(r3d_matches* m) { delete m; }
 

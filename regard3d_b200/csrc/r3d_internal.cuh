@@ -28,7 +28,10 @@ constexpr int kQB = 2;              // query blocks (of 128 rows) resident per C
 constexpr int kSuperRows = kTileRows * kQB;  // 256 query rows per work item
 constexpr int kRowPad = 256;        // every view is padded to a multiple of this many rows
 constexpr int kBiasCols = 16;       // one UMMA K-step holding the norm terms
-constexpr int kChunk = 8;           // database columns summarised by one candidate key
+#ifndef R3D_CHUNK
+#define R3D_CHUNK 8
+#endif
+constexpr int kChunk = R3D_CHUNK;   // database columns summarised by one candidate key (8, or 16 as a build-time A/B)
 constexpr int kChunkBits = 13;      // max low mantissa bits of a key that hold the chunk id
 constexpr int kNumKeys = 6;         // keys kept per query (5 candidate chunks + 1 bound)
 constexpr int kKeyStride = 8;       // uint32 per query row in the key array (two 16-byte stores)

@@ -2,6 +2,8 @@
 regions, the I-sorted pair list is cut into contiguous cost-balanced ranges (cost of a pair =
 N_I * N_J), results are concatenated in pair order.  No data-path collective.  Same rule as the
 in-process multi-device split of r3d_match_pairs (regard3d_b200/csrc/match_host.cu)."""
+import os
+
 import numpy as np
 
 
@@ -62,11 +64,14 @@ class Gather:
     """Per-rank PairWiseMatches -> rank 0, in pair order (shards are contiguous ranges of the I-sorted pair list, so
     rank order = pair order; the reference inserts into one std::map, src/R3DComputeMatches.cpp:483-486).
     Wire format per rank, 8-byte words: P pair ids (2 x u32) | P + 1 prefix offsets (u64) | T matches (2 x u32).
-    CUDA route: r3d_matches_export_csr into pinned host memory -> H2D -> NCCL send/recv over NVLink -> D2H into
-    rank 0's pinned result buffer; rank 0's own shard is exported straight into that buffer.  With a CPU device
-    (gloo) the same code runs without the staging copies -- that is what the CPU tests exercise."""
+    The matches are HOST data on every rank (the coordinate de-duplication is a host step), so on one node the cheapest
+    route is host to host: mode "shm" -- rank 0 owns a POSIX shared-memory segment (kept across calls, so its pages
+    are faulted in once), every rank's r3d_matches_export_csr writes its slice of it directly (a multi-threaded
+    memcpy), one barrier, done.  Mode "p2p" (R3D_GATHER=p2p, or when /dev/shm is unusable) stages through the GPUs:
+    export into pinned memory -> H2D -> NCCL send/recv over NVLink -> D2H into rank 0's pinned buffer; with a CPU
+    device (gloo) the same code runs without the staging copies.  The CPU tests exercise both modes."""
 
-    def __init__(self, rank, world, device):
+    def __init__(self, rank, world, device, mode=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
@@ -77,6 +82,11 @@ class Gather:
         self.sizes = None
         self.words = None
         self.h2d = self.d2h = 0
+        self.mode = mode or os.environ.get("R3D_GATHER", "shm")
+        self.shm = None          # np.memmap over the shared segment
+        self.shm_cap = 0         # its capacity in words (identical on every rank)
+        self.shm_gen = 0
+        self.ms = {}
 
     def _grow(self, t, n, **kw):
         if t is None or t.numel() < n:
@@ -87,8 +97,42 @@ class Gather:
         for req in (self.dist.batch_isend_irecv(ops) if ops else []):
             req.wait()
 
+    def _shm_ensure(self, total):
+        """(Re)create the shared segment when it is too small; every rank takes the same decision from the same sizes."""
+        if self.shm is not None and self.shm_cap >= total:
+            return True
+        cap = int(total * 1.25) + 4096
+        self.shm_gen += 1
+        path = "/dev/shm/r3d_gather_%s_%d" % (os.environ.get("MASTER_PORT", "0"), self.shm_gen)
+        ok = self.torch.ones(1, dtype=self.torch.int64, device=self.device)
+        self.shm = None
+        if self.rank == 0:
+            try:
+                self.shm = np.memmap(path, dtype=np.int64, mode="w+", shape=(cap,))
+            except (OSError, ValueError):
+                ok[0] = 0
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)  # also orders "created" before "opened"
+        if int(ok.item()) == 1 and self.rank != 0:
+            try:
+                self.shm = np.memmap(path, dtype=np.int64, mode="r+", shape=(cap,))
+            except (OSError, ValueError):
+                ok[0] = 0
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
+        if self.rank == 0:
+            try:
+                os.unlink(path)  # the mappings keep the segment alive; nothing is left behind when the job ends
+            except OSError:
+                pass
+        if int(ok.item()) != 1:
+            self.shm, self.shm_cap, self.mode = None, 0, "p2p"
+            return False
+        self.shm_cap = cap
+        return True
+
     def __call__(self, m):
+        import time
         torch, dist = self.torch, self.dist
+        t0 = time.perf_counter()
         P, T = m.num_pairs, m.total
         mine = torch.tensor([P, T], dtype=torch.int64, device=self.device)
         lst = [torch.zeros(2, dtype=torch.int64, device=self.device) for _ in range(self.world)]
@@ -97,12 +141,21 @@ class Gather:
         words = self.sizes[:, 0] * 2 + 1 + self.sizes[:, 1]
         self.words = words
         self.h2d = self.d2h = 0
+        t1 = time.perf_counter()
 
         def export(buf):
             m.export_csr(buf[0:P].view(np.uint32), buf[P:2 * P + 1].view(np.uint64), buf[2 * P + 1:2 * P + 1 + T])
+        if self.mode == "shm" and self._shm_ensure(int(words.sum())):
+            off = int(words[:self.rank].sum())
+            export(self.shm[off:off + int(words[self.rank])])
+            t2 = time.perf_counter()
+            dist.barrier()
+            self.ms = {"mode": "shm", "sizes": 1e3 * (t1 - t0), "export": 1e3 * (t2 - t1), "barrier": 1e3 * (time.perf_counter() - t2)}
+            return
         if self.rank == 0:
             self.h_result = self._grow(self.h_result, int(words.sum()), pin_memory=self.cuda)
             export(self.h_result.numpy())
+            t2 = time.perf_counter()
             ops, off = [], int(words[0])
             for r in range(1, self.world):
                 w = int(words[r])
@@ -113,6 +166,7 @@ class Gather:
                     ops.append(dist.P2POp(dist.irecv, self.h_result[off:off + w], r))
                 off += w
             self._wait(ops)
+            t3 = time.perf_counter()
             if self.cuda:
                 off = int(words[0])
                 for r in range(1, self.world):
@@ -121,6 +175,8 @@ class Gather:
                     off += w
                     self.d2h += 8 * w
                 torch.cuda.current_stream().synchronize()
+            self.ms = {"mode": "p2p", "sizes": 1e3 * (t1 - t0), "export": 1e3 * (t2 - t1), "recv": 1e3 * (t3 - t2),
+                       "d2h": 1e3 * (time.perf_counter() - t3)}
         else:
             w = int(words[self.rank])
             self.h_send = self._grow(self.h_send, w, pin_memory=self.cuda)
@@ -134,12 +190,13 @@ class Gather:
             self._wait([dist.P2POp(dist.isend, src[:w], 0)])
             if self.cuda:
                 torch.cuda.current_stream().synchronize()
+            self.ms = {"mode": "p2p"}
 
     def result(self):
         """Rank 0: [(pairs[P,2] u32, ofs[P+1] u64, matches[T]) per rank], views into the gathered host buffer."""
         from regard3d_b200 import capi
         out, off = [], 0
-        buf = self.h_result.numpy()
+        buf = self.shm if self.ms.get("mode") == "shm" else self.h_result.numpy()
         for r in range(self.world):
             w, P, T = int(self.words[r]), int(self.sizes[r, 0]), int(self.sizes[r, 1])
             b = buf[off:off + w]

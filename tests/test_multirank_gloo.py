@@ -66,7 +66,7 @@ def test_two_gloo_ranks_equal_single_process(oracle, tmp_path):
     assert np.array_equal(np.concatenate(got_m), m)                    # concatenation == single-process result
 
 
-def _gather_worker(rank, world, port, out_dir):
+def _gather_worker(rank, world, port, out_dir, mode):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -80,9 +80,10 @@ def _gather_worker(rank, world, port, out_dir):
     mine, _ = sharding.my_shard(pairs, counts, rank, world)
     ofs, m = po.match_pairs(sc["descs"], sc["xys"], mine, 0.8, n_threads=2)
     handle = capi.Matches.from_csr(mine, ofs, m)        # the rank's PairWiseMatches (host container of the C ABI)
-    g = sharding.Gather(rank, world, "cpu")
+    g = sharding.Gather(rank, world, "cpu", mode=mode)
     for _ in range(2):                                  # twice: buffers are reused
         g(handle)
+    assert g.ms.get("mode") == mode
     if rank == 0:
         parts = g.result()
         np.savez(os.path.join(out_dir, "g.npz"), pairs=np.concatenate([p[0] for p in parts]),
@@ -92,12 +93,12 @@ def _gather_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_gather_to_rank0_in_pair_order(r3dlib, oracle, tmp_path, world):
-    """The bench's strong-scaling gather (sharding.Gather: export CSR -> send/recv -> rank 0's buffer) returns the
+@pytest.mark.parametrize("world,mode", [(2, "shm"), (3, "shm"), (2, "p2p"), (3, "p2p")])
+def test_gather_to_rank0_in_pair_order(r3dlib, oracle, tmp_path, world, mode):
+    """The bench's strong-scaling gather (sharding.Gather: export CSR -> shared segment, or send/recv -> rank 0's buffer) returns the
     single-process PairWiseMatches: same pairs in std::map order, same match sequences."""
     mp = pytest.importorskip("torch.multiprocessing")
-    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True)
     got = np.load(tmp_path / "g.npz")
     sc = synth.make_scene(6, 300, 32, "msurf", seed=78)
     pairs = synth.exhaustive_pairs(6)
