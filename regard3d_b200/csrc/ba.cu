@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(1024, 1) k_chol_fused(double* A, double* Lm, d
 // it is cheaper than the dense cooperative kernel.
 constexpr int kEnvThreads = 512;
 constexpr int kEnvWarps = kEnvThreads / 32;
-constexpr int kEnvMaxActive = 16;
+constexpr int kEnvMaxActive = 24;
 constexpr int kEnvMaxCluster = 8;
 constexpr size_t kEnvSmemBytes = ((size_t)NB * (NB + 1) + NB + (size_t)kEnvMaxActive * NB * NB) * sizeof(double) + 64 * sizeof(int);
 __device__ __forceinline__ void env_cluster_sync(bool clustered) {
@@ -766,35 +766,49 @@ __global__ void __launch_bounds__(kEnvThreads, 1) k_chol_envelope(double* A, dou
       if (lane == 0) act[0] = cnt;
     }
     if (warp == 0) {  // ---- potrf of the diagonal tile; lane kb carries the rhs row when it lies in this tile ----
+      // lane = row, the row in registers; column j reaches the other lanes through shared memory (one broadcast read
+      // per update).  Every lane updates all 32 entries of its row: what lands above the diagonal or in the padding
+      // is never read, and leaving the predicates out keeps the unrolled code small (it runs once per panel, from
+      // the instruction cache's point of view always cold).
       const bool rhs_lane = kb < NB && lane == kb && k0 + kb == n;
+      const bool real = lane < kb || rhs_lane;
       double a[NB];
+      {
+        const double2* src = reinterpret_cast<const double2*>(A + (size_t)(k0 + (real ? lane : 0)) * n + k0);
 #pragma unroll
-      for (int c = 0; c < NB; ++c)
-        a[c] = ((lane < kb || rhs_lane) && c < kb) ? __ldcg(&A[(size_t)(k0 + lane) * n + k0 + c]) : (lane == c ? 1.0 : 0.0);
+        for (int c = 0; c < NB; c += 2) {
+          const double2 v = __ldcg(src + c / 2);
+          a[c] = (real && c < kb) ? v.x : (lane == c ? 1.0 : 0.0);
+          a[c + 1] = (real && c + 1 < kb) ? v.y : (lane == c + 1 ? 1.0 : 0.0);
+        }
+      }
+      double* colb = Xt;  // 2 x 32 doubles of scratch (Xt is not in use before the trsm)
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         if (j < kb) {  // (warp-uniform) columns beyond kb are identity padding
-          const double piv = __shfl_sync(0xffffffffu, a[j], j);
+          double* cb = colb + (j & 1) * 2 * NB;
+          if (lane == j) cb[NB] = a[j];
+          __syncwarp();
+          const double piv = cb[NB];
           const bool bad = !(piv > 0.0);
           const double rs = bad ? 1.0 : rsqrt(piv);
           if (bad && lane == 0 && cta == 0) *flag = 1.0;
           double lrj = a[j] * rs;                       // L[r][j] for r > j
           if (lane == j) { lrj = bad ? 1.0 : piv * rs; invd[j] = rs; }
           a[j] = lrj;
+          cb[lane] = lrj;
+          __syncwarp();
 #pragma unroll
-          for (int c = j + 1; c < NB; ++c) {
-            const double lcj = __shfl_sync(0xffffffffu, lrj, c);
-            if (lane >= c && c < kb) a[c] -= lrj * lcj;
-          }
+          for (int c = j + 1; c < NB; ++c) a[c] -= lrj * cb[c];
         } else if (lane == j) {
           invd[j] = 1.0;
         }
       }
 #pragma unroll
       for (int c = 0; c < NB; ++c) {
-        const double v = c <= lane ? a[c] : 0.0;
-        Ls[lane][c] = (lane < kb || c == lane) ? v : 0.0;   // the rhs lane is not a row of L_kk
-        if (cta == 0 && (lane < kb || rhs_lane) && c < kb && c <= lane) Lm[(size_t)(k0 + lane) * n + k0 + c] = v;
+        const double v = lane < kb ? (c <= lane ? a[c] : 0.0) : (c == lane ? 1.0 : 0.0);  // the rhs lane is not a row of L_kk
+        Ls[lane][c] = v;
+        if (cta == 0 && real && c < kb && c <= lane) Lm[(size_t)(k0 + lane) * n + k0 + c] = a[c];
       }
     }
     __syncthreads();
@@ -805,8 +819,15 @@ __global__ void __launch_bounds__(kEnvThreads, 1) k_chol_envelope(double* A, dou
       const int row = ti * NB + lane;
       const bool valid = row <= n;
       double a[NB];
+      {
+        const double2* src = reinterpret_cast<const double2*>(A + (size_t)(valid ? row : n) * n + k0);
 #pragma unroll
-      for (int c = 0; c < NB; ++c) a[c] = (valid && c < kb) ? __ldcg(&A[(size_t)row * n + k0 + c]) : 0.0;
+        for (int c = 0; c < NB; c += 2) {
+          const double2 v = __ldcg(src + c / 2);
+          a[c] = (valid && c < kb) ? v.x : 0.0;
+          a[c + 1] = (valid && c + 1 < kb) ? v.y : 0.0;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < NB; ++j) {
         const double xj = a[j] * invd[j];
@@ -856,16 +877,23 @@ __global__ void __launch_bounds__(kEnvThreads, 1) k_chol_envelope(double* A, dou
             for (int j = 0; j < 8; ++j) acc[i][j] += av[i] * bv[j];
         }
         const int row0 = act[1 + ia] * NB + 4 * lr, col0 = act[1 + ib] * NB + 8 * lc;
+        // read-modify-write of the target: all loads first (the compiler will not hoist a load over a store that
+        // may alias it, and 32 serialised L2 round trips would cost more than the tile product)
+        double old[4][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = row0 + i;
-          if (row > n) continue;
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int col = col0 + j;
-            if (col < n && col <= row) A[(size_t)row * n + col] = __ldcg(&A[(size_t)row * n + col]) - acc[i][j];
+            const int row = row0 + i, col = col0 + j;
+            old[i][j] = (row <= n && col < n && col <= row) ? __ldcg(&A[(size_t)row * n + col]) : 0.0;
           }
-        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = row0 + i, col = col0 + j;
+            if (row <= n && col < n && col <= row) A[(size_t)row * n + col] = old[i][j] - acc[i][j];
+          }
       }
     }
     env_cluster_sync(clustered);
@@ -876,29 +904,39 @@ __global__ void __launch_bounds__(kEnvThreads, 1) k_chol_envelope(double* A, dou
   __syncthreads();
   for (int kbi = nblk - 1; kbi >= 0; --kbi) {
     const int k0 = kbi * NB, kb = min(NB, n - k0);
-    if (warp == 0) {  // x_k = L_kk^-T y_k: lane c holds column c of L_kk
+    if (warp == 0) {  // x_k = L_kk^-T y_k: lane c holds column c of L_kk (col[j] = L[j][c], zero above the diagonal)
       double col[NB];
 #pragma unroll
-      for (int j = 0; j < NB; ++j)
-        col[j] = (j < kb && lane < kb && lane <= j) ? __ldcg(&Lm[(size_t)(k0 + j) * n + k0 + lane]) : (j == lane ? 1.0 : 0.0);
+      for (int j = 0; j < NB; ++j) {
+        const double v = __ldcg(&Lm[(size_t)(k0 + min(j, kb - 1)) * n + k0 + min(lane, kb - 1)]);
+        col[j] = (j < kb && lane < kb && lane <= j) ? v : (j == lane ? 1.0 : 0.0);
+      }
       double y = lane < kb ? __ldcg(&x_out[k0 + lane]) : 0.0;
-      double inv = 1.0;
+      double diag = 1.0;
 #pragma unroll
-      for (int j = 0; j < NB; ++j) if (j == lane) inv = 1.0 / col[j];
+      for (int j = 0; j < NB; ++j) diag = (j == lane) ? col[j] : diag;
+      const double inv = 1.0 / diag;
+      double* xb = Xt;  // scratch: x_k as it is solved, last entry first
 #pragma unroll
       for (int j = NB - 1; j >= 0; --j) {
-        const double xj = __shfl_sync(0xffffffffu, y * inv, j);
-        if (lane < j) y -= col[j] * xj;
-        if (lane == j) y = xj;
+        if (lane == j) xb[j] = y * inv;
+        __syncwarp();
+        y -= col[j] * xb[j];   // lanes > j: col[j] = 0; lane j: y becomes 0 and is not used again
       }
-      if (lane < kb) x_out[k0 + lane] = y;
-      invd[lane] = lane < kb ? y : 0.0;  // x_k for the update below
+      __syncwarp();
+      const double x = xb[lane];
+      if (lane < kb) x_out[k0 + lane] = x;
+      invd[lane] = lane < kb ? x : 0.0;  // x_k for the update below
     }
     __syncthreads();
     const int lo = min(ft[kbi] * NB, k0);
-    for (int j = lo + tid; j < k0; j += kEnvThreads) {  // y_j -= L_kj^T x_k
+    for (int j = lo + tid; j < k0; j += kEnvThreads) {  // y_j -= L_kj^T x_k (loads batched: they are L2 round trips)
+      double lv[NB];
+#pragma unroll
+      for (int tt = 0; tt < NB; ++tt) lv[tt] = tt < kb ? __ldcg(&Lm[(size_t)(k0 + tt) * n + j]) : 0.0;
       double sacc = 0.0;
-      for (int tt = 0; tt < kb; ++tt) sacc += __ldcg(&Lm[(size_t)(k0 + tt) * n + j]) * invd[tt];
+#pragma unroll
+      for (int tt = 0; tt < NB; ++tt) sacc += lv[tt] * invd[tt];
       x_out[j] = __ldcg(&x_out[j]) - sacc;
     }
     __syncthreads();
@@ -1290,7 +1328,7 @@ int setup_problem(r3d_ctx* ctx, DeviceWorker& w, const r3d_ba_problem* p, Device
   R3D_CUDA_TRY(ctx, mem.alloc(&d.g, nparam));
   R3D_CUDA_TRY(ctx, mem.alloc(&d.diag, nparam));
   R3D_CUDA_TRY(ctx, mem.alloc(&d.delta, nparam));
-  R3D_CUDA_TRY(ctx, mem.alloc(&d.S, (size_t)d.nB * d.nB + d.nB));  // S | rhs contiguous: one all-reduce
+  R3D_CUDA_TRY(ctx, mem.alloc(&d.S, (size_t)d.nB * d.nB + d.nB + 64));  // S | rhs contiguous: one all-reduce (+ slack: k_chol_envelope reads whole 32-wide rows)
   d.rhs = d.S + (size_t)d.nB * d.nB;
   R3D_CUDA_TRY(ctx, mem.alloc(&d.Vinv, 9 * (size_t)p->n_pts));
   // intrinsics that are not refined never enter the parameter vector: the candidate copy is constant
@@ -1369,7 +1407,7 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
   // Cholesky scratch: L (with the forward-substituted rhs as row nB) and the inverses of its diagonal blocks
   double *d_Lm = nullptr, *d_Linv = nullptr;
   const int chol_blocks = (nB + r3d::ba::NB - 1) / r3d::ba::NB;
-  R3D_CUDA_TRY(ctx, mem.alloc(&d_Lm, ((size_t)nB + 1) * nB));
+  R3D_CUDA_TRY(ctx, mem.alloc(&d_Lm, ((size_t)nB + 1) * nB + 64));
   R3D_CUDA_TRY(ctx, mem.alloc(&d_Linv, (size_t)chol_blocks * r3d::ba::NB * r3d::ba::NB));
   int chol_grid = w.sm_count;  // persistent: one CTA per SM, all co-resident (cooperative launch)
   {
@@ -1414,14 +1452,19 @@ int r3d_bundle_adjust(r3d_ctx* ctx, r3d_ba_problem* p, const r3d_ba_options* opt
       int act = 0;
       for (int ti = k + 1; ti < ntr; ++ti) act += ft[ti] <= k;
       max_act = std::max(max_act, act);
-      est_env += 4.5 + 0.27 * std::ceil((double)(act * (act + 1) / 2) / (double)env_ctas) + 0.05 * act;
+      est_env += 32.0 + 5.0 * std::ceil((double)(act * (act + 1) / 2) / (16.0 * env_ctas)) + 0.6 * act;
       const int rem = ntr - k - 1;
       est_dense += 20.0 + 3.0 * std::ceil((double)(rem * (rem + 1) / 2) / (4.0 * w.sm_count));
     }
+    // Measured at C5 (profiles/r02_ba_cholesky_ab.md): the envelope kernel does 7x fewer tile products but its panels
+    // cost 54 us on 8 SMs (register potrf 8, redundant trsm 10 -- shared-memory instruction issue --, fp64 syrk on 8 SMs
+    // 20, cluster barrier 14) against 29 us for the dense cooperative kernel on 148 SMs, so the dense kernel stays the
+    // default; R3D_BA_CHOL=envelope selects the envelope kernel where it applies (A/B and tests), =auto trusts the
+    // estimate.
     const char* force = getenv("R3D_BA_CHOL");
-    use_env = max_act <= r3d::ba::kEnvMaxActive && est_env < est_dense;
-    if (force && std::string(force) == "dense") use_env = false;
-    if (force && std::string(force) == "envelope" && max_act <= r3d::ba::kEnvMaxActive) use_env = true;
+    use_env = false;
+    if (force && std::string(force) == "auto") use_env = max_act <= r3d::ba::kEnvMaxActive && est_env < est_dense;
+    if (force && std::string(force) == "envelope") use_env = max_act <= r3d::ba::kEnvMaxActive;
     if (use_env) {
       R3D_CUDA_TRY(ctx, mem.alloc(&d_ft, (size_t)ntr));
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_ft, ft.data(), (size_t)ntr * sizeof(int), cudaMemcpyHostToDevice, w.stream));

@@ -42,7 +42,7 @@ constexpr uint32_t kInstrDesc2 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | (
 
 }  // namespace
 
-template <bool kVote, int kEpiWarps2>
+template <bool kVote, int kEpiWarps2, bool kDrain>
 __global__ void __launch_bounds__(32 * (4 + kEpiWarps2), 1)
 k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __restrict__ tmapD,
                     const PairDesc* __restrict__ pairs, const WorkItem* __restrict__ items, uint32_t n_items,
@@ -236,20 +236,37 @@ k_l2_candidates_2sm(const CUtensorMap* __restrict__ tmapQ, const CUtensorMap* __
         // accumulator column j of the 256-wide tile is database row t*256 + j (rows 0-127 from the leader's
         // half, 128-255 from the peer's)
         const uint32_t chunk0 = (t * kTileN + half * kColsPerWarp) / kChunk;
-        uint32_t v[2][32];
         constexpr uint32_t kCpl = 32 / kChunk;
-        tc_ld32(taddr, v[0]);
+        if constexpr (kDrain) {
+          // drain first: all of this warp's columns go to registers, the accumulator stage is handed back to the MMA
+          // issuer after ONE TMEM round trip, and the min / insertion arithmetic overlaps the next tiles' MMAs
+          uint32_t v[kLoads][32];
 #pragma unroll
-        for (uint32_t sblk = 0; sblk < kLoads; ++sblk) {
-          tc_wait_ld(v[sblk & 1u]);
-          if (sblk + 1 < kLoads) tc_ld32(taddr + 32 * (sblk + 1), v[(sblk + 1) & 1u]);
-          if (sblk + 1 == kLoads) {  // the stage is drained: release it before the last block's arithmetic
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
+          for (uint32_t sblk = 0; sblk < kLoads; ++sblk) tc_ld32(taddr + 32 * sblk, v[sblk]);
+#pragma unroll
+          for (uint32_t sblk = 0; sblk < kLoads; ++sblk) tc_wait_ld(v[sblk]);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
+#pragma unroll
+          for (uint32_t sblk = 0; sblk < kLoads; ++sblk)
+#pragma unroll
+            for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(v[sblk] + c * kChunk, chunk0 + sblk * kCpl + c, keep_mask, key);
+        } else {
+          uint32_t v[2][32];
+          tc_ld32(taddr, v[0]);
+#pragma unroll
+          for (uint32_t sblk = 0; sblk < kLoads; ++sblk) {
+            tc_wait_ld(v[sblk & 1u]);
+            if (sblk + 1 < kLoads) tc_ld32(taddr + 32 * (sblk + 1), v[(sblk + 1) & 1u]);
+            if (sblk + 1 == kLoads) {  // the stage is drained: release it before the last block's arithmetic
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(r_tempty0 + 8 * acc);  // the LEADER's tempty collects both CTAs
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(v[sblk & 1u] + c * kChunk, chunk0 + sblk * kCpl + c, keep_mask, key);
           }
-#pragma unroll
-          for (uint32_t c = 0; c < kCpl; ++c) chunk_update<kVote>(v[sblk & 1u] + c * kChunk, chunk0 + sblk * kCpl + c, keep_mask, key);
         }
         acc ^= 1u;
         if (acc == 0) accphase ^= 1u;
@@ -319,12 +336,13 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
   }();
   int n_qbuf = want_qbuf;
   if (ring_stages2(nkb, n_qbuf) < 4) n_qbuf = 1;  // very wide descriptors: keep the ring deep enough instead
-  // 16 epilogue warps for short descriptors (<= 6 K-steps: D <= 80), 8 otherwise; R3D_K1_EPI = 8 | 16 forces one
+  // Epilogue shape (A/B in profiles/r02_chunk_ab.md): 8 warps everywhere -- 16 change nothing at D = 64 and cost 5 % at
+  // D >= 128; R3D_K1_EPI = 8 | 16 forces one
   static const int force_epi = []() {
     const char* e = getenv("R3D_K1_EPI");
     return e ? atoi(e) : 0;
   }();
-  const int epi = force_epi == 8 || force_epi == 16 ? force_epi : (ksteps <= 6 ? 16 : 8);
+  const int epi = force_epi == 16 ? 16 : 8;
   const int stages = ring_stages2(nkb, n_qbuf);
   const size_t smem = 1024 + (size_t)(n_qbuf * nkb + stages) * kBoxBytes + 8 * (3 * kMaxStages2 + 6 + 4) + 32 + 16 +
                       (size_t)(epi / 4 - 1) * 128 * 8 * 4;
@@ -332,8 +350,17 @@ int launch_l2_candidates_2sm(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pa
     const char* e = getenv("R3D_K1_VOTE");
     return !(e && atoi(e) == 0);
   }();
-  auto kernel = epi == 16 ? (vote ? k_l2_candidates_2sm<true, 16> : k_l2_candidates_2sm<false, 16>)
-                          : (vote ? k_l2_candidates_2sm<true, 8> : k_l2_candidates_2sm<false, 8>);
+  // R3D_K1_DRAIN = 0 | 1: pipelined TMEM loads (two 32-column blocks in flight) or drain-first.  Drain-first gains
+  // 1-2 % where the tile is MMA-bound (>= 7 K-steps) and loses 3 % at D = 64
+  static const int force_drain = []() {
+    const char* e = getenv("R3D_K1_DRAIN");
+    return e ? atoi(e) : -1;
+  }();
+  const int drain = force_drain >= 0 ? force_drain : (ksteps > 6 ? 1 : 0);
+  auto kernel = drain ? (epi == 16 ? (vote ? k_l2_candidates_2sm<true, 16, true> : k_l2_candidates_2sm<false, 16, true>)
+                                   : (vote ? k_l2_candidates_2sm<true, 8, true> : k_l2_candidates_2sm<false, 8, true>))
+                      : (epi == 16 ? (vote ? k_l2_candidates_2sm<true, 16, false> : k_l2_candidates_2sm<false, 16, false>)
+                                   : (vote ? k_l2_candidates_2sm<true, 8, false> : k_l2_candidates_2sm<false, 8, false>));
   R3D_CUDA_TRY(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   uint32_t grid = (uint32_t)w.sm_count / 2 * 2;
   if (n_items < grid) grid = n_items;

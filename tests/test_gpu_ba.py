@@ -165,3 +165,24 @@ def test_ba_c5_full_size_equals_oracle(gpu_ctx, oracle):
     within 1e-5 relative of the oracle's after the same LM iterations (round 1 only checked 40 cameras / 20 000 points)."""
     prob = synth.make_ba_problem(n_cams=200, n_pts=200000, obs_per_pt=5, seed=20260924 + 5)
     _compare(gpu_ctx, oracle, prob, iters=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ctas", ["1", "8"])
+def test_envelope_cholesky_equals_the_dense_solve(gpu_ctx, monkeypatch, ctas):
+    """R3D_BA_CHOL=envelope: the skyline factorisation on a thread-block cluster (k_chol_envelope) reaches the same
+    iterates as the dense cooperative kernel on a sequence-like scene whose reduced system is banded + bordered
+    (ring of cameras, shared intrinsics, the rhs row inside the last diagonal tile: 6 * 37 + 6 = 228 = 7 * 32 + 4)."""
+    prob = synth.make_ba_problem(n_cams=37, n_pts=4000, obs_per_pt=4, seed=41)
+    out = {}
+    for mode in ("dense", "envelope"):
+        monkeypatch.setenv("R3D_BA_CHOL", mode)
+        monkeypatch.setenv("R3D_BA_ENV_CTAS", ctas)
+        p = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in prob.items() if k != "truth"}
+        summ, trace = gpu_ctx.bundle_adjust(p, max_iterations=6)
+        out[mode] = (summ, trace, p)
+    (sa, ta, pa), (sb, tb, pb) = out["dense"], out["envelope"]
+    assert sa["iterations"] == sb["iterations"] and sa["successful_steps"] == sb["successful_steps"]
+    assert np.allclose(ta, tb, rtol=1e-10)
+    assert np.allclose(pa["poses"], pb["poses"], rtol=0, atol=1e-9)
+    assert np.allclose(pa["points"], pb["points"], rtol=0, atol=1e-8)
