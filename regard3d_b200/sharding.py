@@ -3,6 +3,8 @@ regions, the I-sorted pair list is cut into contiguous cost-balanced ranges (cos
 N_I * N_J), results are concatenated in pair order.  No data-path collective.  Same rule as the
 in-process multi-device split of r3d_match_pairs (regard3d_b200/csrc/match_host.cu)."""
 import os
+import sys
+import time
 
 import numpy as np
 
@@ -103,19 +105,25 @@ class Gather:
             return True
         cap = int(total * 1.25) + 4096
         self.shm_gen += 1
-        path = "/dev/shm/r3d_gather_%s_%d" % (os.environ.get("MASTER_PORT", "0"), self.shm_gen)
+        name = [None]
+        if self.rank == 0:
+            name[0] = "/dev/shm/r3d_gather_%d_%d_%d" % (os.getpid(), self.shm_gen, int(time.time() * 1e3) & 0xffffff)
+        self.dist.broadcast_object_list(name, src=0)
+        path = name[0]
         ok = self.torch.ones(1, dtype=self.torch.int64, device=self.device)
         self.shm = None
         if self.rank == 0:
             try:
                 self.shm = np.memmap(path, dtype=np.int64, mode="w+", shape=(cap,))
-            except (OSError, ValueError):
+            except (OSError, ValueError) as e:
+                sys.stderr.write("[sharding.Gather] cannot create %s (%d words): %r\n" % (path, cap, e))
                 ok[0] = 0
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)  # also orders "created" before "opened"
         if int(ok.item()) == 1 and self.rank != 0:
             try:
                 self.shm = np.memmap(path, dtype=np.int64, mode="r+", shape=(cap,))
-            except (OSError, ValueError):
+            except (OSError, ValueError) as e:
+                sys.stderr.write("[sharding.Gather] rank %d cannot map %s: %r\n" % (self.rank, path, e))
                 ok[0] = 0
         self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN)
         if self.rank == 0:
@@ -130,7 +138,6 @@ class Gather:
         return True
 
     def __call__(self, m):
-        import time
         torch, dist = self.torch, self.dist
         t0 = time.perf_counter()
         P, T = m.num_pairs, m.total
