@@ -140,8 +140,8 @@ def measured_traffic_per_pair(wl_key):
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, pairs = 0.0, 128.0
-    for ln in open(p):
-        f = ln.strip().split(",")
+    import csv
+    for f in csv.reader(open(p)):
         if len(f) >= 4 and f[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             tot += float(f[2]) * unit.get(f[3], 1.0)
         if len(f) >= 3 and f[1] == "pairs_in_launch":

@@ -79,6 +79,8 @@ int r3d_debug_liop_process(r3d_ctx* ctx, const float* patches, uint32_t n, float
 #define R3D_MATCH_DEFAULT 0u
 #define R3D_MATCH_EXACT_SCAN 1u   /* skip the tensor-core candidate pass: CUDA-core exact scan only */
 #define R3D_MATCH_NO_COORD_DEDUP 2u /* skip IndMatchDecorator (for callers without positions) */
+#define R3D_MATCH_CASCADE_HASHING 8u /* OpenMVG CASCADE_HASHING_L2 (BASELINE config 4) instead of the exhaustive 2-NN:
+                                   * approximate by construction, bit-identical to the CPU restatement of the algorithm */
 #define R3D_MATCH_MUTUAL_NN 4u    /* OFF by default and NOT reference behaviour (MatchDistanceRatio has no cross-check):
                                    * keep (i, j) only if j is also i's nearest neighbour among J's descriptors */
 
@@ -89,6 +91,15 @@ int r3d_debug_liop_process(r3d_ctx* ctx, const float* patches, uint32_t n, float
  * matches are absent from the result, like in the reference's map. */
 int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float dist_ratio,
                     uint32_t flags, r3d_matches** out);
+
+/* R3D_MATCH_CASCADE_HASHING replaces Cascade_Hashing_Matcher_Regions::Match (OpenMVG matching_image_collection, the
+ * matcher BASELINE config 4 names; Regard3D's own GUI never selects it, src/R3DComputeMatches.cpp:2035-2062).  Its hash
+ * codes depend on the zero-mean descriptor of ALL views of the matching job, so a job that is split over several
+ * r3d_match_pairs calls (ranks, shards) declares its views once: r3d_cascade_prepare hashes the given views (already
+ * uploaded) under their common zero-mean descriptor; later R3D_MATCH_CASCADE_HASHING calls whose pairs stay inside
+ * that set reuse the tables.  Without it every call hashes the views of its own pair list (= one call is one job, the
+ * reference's behaviour).  Views of more than 65536 features or dimension > 256: R3D_ERR_UNSUPPORTED. */
+int r3d_cascade_prepare(r3d_ctx* ctx, const uint32_t* view_ids, uint32_t n_views);
 
 /* Replaces openMVG::matching::ArrayMatcher<float,L2>::SearchNeighbours(query, nbQuery, &idx, &dist,
  * NN=2) -- the plug-in API Regard3D implements in src/utils/matcher_hnsw.h:133-191 -- with the
@@ -386,6 +397,8 @@ int64_t r3d_debug_post_process_ranked(r3d_indmatch* m, int64_t n, const float* x
  * std::uniform_int_distribution<uint32_t> (the ACRANSAC sample stream) reproduces this process's <random>; the
  * filters then run entirely on the device, otherwise samples are drawn on the host, round by round. */
 int r3d_debug_rng_selftest(void);
+/* test hook: hash tables of a prepared view (code n x ceil(dim/32), bucket n x 6, bk_ofs 6 x 1025, bk_ids 6 x n) */
+int r3d_debug_cascade_view(r3d_ctx* ctx, uint32_t view_id, uint32_t* code, uint16_t* bucket, uint32_t* bk_ofs, uint32_t* bk_ids);
 
 /* Diagnostics: the packed candidate keys per query row (n_query padded to 256 rows x 8 uint32:
  * 6 keys ascending + 2 unused)

@@ -45,6 +45,14 @@ int64_t orc_match_pairs(const void* const* descs, const float* const* xys, const
                         const uint32_t* pairs, uint64_t P, float ratio,
                         uint64_t* pair_ofs, orc_indmatch* out, uint64_t cap, int n_threads);
 
+/* Cascade_Hashing_Matcher_Regions::Match (OpenMVG CASCADE_HASHING_L2; BASELINE config 4): same
+ * arguments and output as orc_match_pairs.  orc_cascade_projections: the (dim + 60) x dim projection table. */
+int64_t orc_cascade_match_pairs(const void* const* descs, const float* const* xys, const uint32_t* ns,
+                                uint32_t n_views, uint32_t dim, int dtype,
+                                const uint32_t* pairs, uint64_t P, float ratio,
+                                uint64_t* pair_ofs, orc_indmatch* out, uint64_t cap, int n_threads);
+void orc_cascade_projections(uint32_t dim, float* out);
+
 /* IndMatchDecorator<float>::getDeduplicated on an (i,j)-sorted list, in place; returns new count. */
 int64_t orc_coord_dedup(orc_indmatch* m, int64_t n, const float* xyI, const float* xyJ);
 

@@ -165,6 +165,32 @@ def match_pairs(descs, xys, pairs, ratio, n_threads=0):
     return ofs, out[:n].copy()
 
 
+def cascade_match_pairs(descs, xys, pairs, ratio, n_threads=0):
+    """Cascade_Hashing_Matcher_Regions::Match twin (oracle_cascade.cpp); same return shape as match_pairs."""
+    descs = [np.ascontiguousarray(d) for d in descs]
+    xys = [np.ascontiguousarray(x, np.float32) for x in xys]
+    pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+    P = pairs.shape[0]
+    ns = np.array([d.shape[0] for d in descs], np.uint32)
+    dim = max([d.shape[1] for d in descs if d.ndim == 2 and d.shape[0] > 0] + [0])
+    cap = int(sum(int(ns[j]) for _, j in pairs)) + 1
+    out = np.zeros(cap, indmatch_dtype)
+    ofs = np.zeros(P + 1, np.uint64)
+    fn = lib().orc_cascade_match_pairs
+    fn.restype = C.c_int64
+    n = fn(_ptr_array(descs), _ptr_array(xys), _p(ns), C.c_uint32(len(descs)), C.c_uint32(dim), _dt(descs[0]),
+           _p(pairs), C.c_uint64(P), C.c_float(ratio), _p(ofs), _p(out), C.c_uint64(cap), C.c_int(n_threads))
+    if n < 0:
+        raise RuntimeError("orc_cascade_match_pairs overflow")
+    return ofs, out[:n].copy()
+
+
+def cascade_projections(dim):
+    out = np.zeros((dim + 60, dim), np.float32)
+    lib().orc_cascade_projections(C.c_uint32(dim), _p(out))
+    return out
+
+
 def coord_dedup(m, xyI, xyJ):
     m = np.ascontiguousarray(m, indmatch_dtype).copy()
     xyI = np.ascontiguousarray(xyI, np.float32)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("R3D_LIB") or os.path.join(_HERE, "libr3dgpu.so")  # R3D_LIB: an A/B build of the same ABI
 
 R3D_F32, R3D_U8 = 0, 1
-MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP, MATCH_MUTUAL_NN = 0, 1, 2, 4
+MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP, MATCH_MUTUAL_NN, MATCH_CASCADE_HASHING = 0, 1, 2, 4, 8
 MODEL_F, MODEL_E, MODEL_H = 0, 1, 2
 
 indmatch_dtype = np.dtype([("i", np.uint32), ("j", np.uint32)])
@@ -32,7 +32,7 @@ EXPORTS = [
     "r3d_sfm_get_view", "r3d_sfm_add_intrinsic", "r3d_sfm_get_intrinsic", "r3d_sfm_add_pose", "r3d_sfm_get_pose",
     "r3d_sfm_add_landmark", "r3d_sfm_get_landmark", "r3d_debug_ba_jacobian_model", "r3d_debug_ba_prior", "r3d_sfm_ba_default_options", "r3d_sfm_bundle_adjust",
     "r3d_tracks_build", "r3d_tracks_count", "r3d_tracks_get", "r3d_tracks_in_images", "r3d_tracks_free",
-    "r3d_sfm_structure_from_tracks", "r3d_sfm_remove_outliers",
+    "r3d_sfm_structure_from_tracks", "r3d_sfm_remove_outliers", "r3d_cascade_prepare", "r3d_debug_cascade_view",
 ]
 
 
@@ -574,6 +574,21 @@ class Context:
         self._check(lib().r3d_match_pairs(self._h, _p(pairs), C.c_uint64(len(pairs)), C.c_float(dist_ratio),
                                           C.c_uint32(flags), C.byref(h)))
         return Matches(h)
+
+    def cascade_prepare(self, view_ids):
+        """Hash the given (uploaded) views under their common zero-mean descriptor (R3D_MATCH_CASCADE_HASHING jobs that
+        span several match_pairs calls)."""
+        v = np.ascontiguousarray(view_ids, np.uint32).ravel()
+        self._check(lib().r3d_cascade_prepare(self._h, _p(v), C.c_uint32(len(v))))
+
+    def debug_cascade_view(self, view_id, n, dim):
+        words = (dim + 31) // 32
+        code = np.zeros((n, words), np.uint32)
+        bucket = np.zeros((n, 6), np.uint16)
+        ofs = np.zeros((6, 1025), np.uint32)
+        ids = np.zeros((6, max(n, 1)), np.uint32)
+        self._check(lib().r3d_debug_cascade_view(self._h, C.c_uint32(view_id), _p(code), _p(bucket), _p(ofs), _p(ids)))
+        return code, bucket, ofs, ids[:, :n]
 
     def search_neighbours(self, view_db, view_query, n_query):
         idx = np.zeros((n_query, 2), np.int32)

@@ -79,6 +79,7 @@ static void free_view(DeviceWorker& w, ViewDev& v) {
   pool_release(w, v.d_opD);
   pool_release(w, v.d_xy);
   pool_release(w, v.d_stats);
+  if (v.d_cascade) pool_release(w, v.d_cascade);
   v = ViewDev();
 }
 

@@ -6,6 +6,7 @@
 // launch (work item = pair x 256-query super-block), one re-rank launch, one exact-scan launch for
 // the uncertified remainder, one compacted device->host copy, host de-duplication on a thread pool.
 #include "r3d_internal.cuh"
+#include "r3d_cascade.h"
 
 #include <algorithm>
 #include <atomic>
@@ -16,6 +17,7 @@
 #include <cstring>
 #include <future>
 #include <map>
+#include <set>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -122,6 +124,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   std::mutex slab_mutex;
   const float ratio2 = ratio * ratio;  // Square(fDistRatio): b_squared_metric = true for BRUTE_FORCE_L2
   const bool want_matches = (nn_out == nullptr);
+  const bool cascade = want_matches && (flags & R3D_MATCH_CASCADE_HASHING) != 0;  // CASCADE_HASHING_L2 (cascade.cu)
 
   // ---- build pair descriptors --------------------------------------------------------------
   std::vector<BatchPair> all;
@@ -137,7 +140,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     const ViewDev& vj = iJ->second;
     // reference: skip when either side has no regions (R3DComputeMatches.cpp:444-447, :471-475);
     // SearchNeighbours returns false when NN(2) > #database rows.
-    if (vi.n < 2 || vj.n == 0) continue;
+    if (vi.n < 2 || vj.n == 0) continue;  // (cascade hashing: fewer than 3 candidates -> no result either)
     if (vi.dim != vj.dim || vi.dtype != vj.dtype) continue;  // Type_id() mismatch -> skipped
     if (dtype < 0) { dim = vi.dim; dtype = (int)vi.dtype; }
     if (vi.dim != dim || (int)vi.dtype != dtype)
@@ -149,7 +152,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     pd.I = I; pd.J = J; pd.nI = vi.n; pd.nJ = vj.n; pd.nI_pad = vi.n_pad; pd.nJ_pad = vj.n_pad;
     pd.slotI = w.view_slot[I]; pd.slotJ = w.view_slot[J];
     pd.descI = vi.d_desc; pd.descJ = vj.d_desc;
-    pd.use_tc = ((flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.tc_ok && vj.tc_ok && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
+    pd.use_tc = (!cascade && (flags & R3D_MATCH_EXACT_SCAN) == 0 && vi.tc_ok && vj.tc_ok && vi.n_pad <= kMaxDbRowsTC && vi.kp <= kMaxKBlocks * kKBlock) ? 1u : 0u;
     pd.eps_abs = pair_eps(vi, vj);
     {
       uint32_t nchunks = vi.n_pad / kChunk, bits = 4;
@@ -212,7 +215,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
   while (b0 < all.size()) {
     size_t b1 = b0;
     uint64_t rows = 0, qtotal = 0, n_items = 0;
-    uint32_t max_nJ = 0, max_chunks = 0;
+    uint32_t max_nJ = 0, max_chunks = 0, max_nI = 0;
     // batches shrink geometrically towards the end so that the un-overlapped tail (copy + host
     // de-duplication of the LAST batch) is short
     const size_t remaining = all.size() - b0;
@@ -226,6 +229,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
         max_chunks = std::max(max_chunks, all[b1].pd.nI_pad / (uint32_t)kChunk);
       }
       max_nJ = std::max(max_nJ, all[b1].pd.nJ);
+      max_nI = std::max(max_nI, all[b1].pd.nI);
       ++b1;
     }
     const uint32_t nb = (uint32_t)(b1 - b0);
@@ -238,6 +242,9 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       if ((*hp)[k].use_tc)  // CTA-pair kernel: 128-query blocks; n_pad is a multiple of 256 -> always an even count per pair
         for (uint32_t qb = 0; qb < (*hp)[k].nJ_pad / kTileRows; ++qb) hitems->push_back(WorkItem{k, qb});
     const bool any_tc = !hitems->empty();
+    if (cascade)  // the item array carries (table row of I, table row of J) per pair instead of work items
+      for (uint32_t k = 0; k < nb; ++k)
+        hitems->push_back(WorkItem{w.views.find((*hp)[k].I)->second.cascade_index, w.views.find((*hp)[k].J)->second.cascade_index});
 
     const int sl = (int)(batch_no & 1u);
     OutSlot& o = w.out[sl];
@@ -274,7 +281,7 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
       std::memcpy(o.h_stage, hp->data(), pb);
       std::memcpy((char*)o.h_stage + pb, hitems->data(), ib);
       R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_pairs, o.h_stage, pb, cudaMemcpyHostToDevice, w.stream));
-      if (any_tc) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, (char*)o.h_stage + pb, ib, cudaMemcpyHostToDevice, w.stream));
+      if (ib) R3D_CUDA_TRY(ctx, cudaMemcpyAsync(w.d_items, (char*)o.h_stage + pb, ib, cudaMemcpyHostToDevice, w.stream));
     }
     R3D_CUDA_TRY(ctx, cudaMemsetAsync(o.d_counters, 0, (16 + nb) * sizeof(uint32_t), w.stream));
     uint64_t launches = 0;
@@ -307,14 +314,22 @@ static int match_on_worker(r3d_ctx* ctx, DeviceWorker& w, const uint32_t* pairs,
     R3D_CUDA_TRY(ctx, cudaEventRecord(o.ev[2], w.stream));
     bool any_exact = false;
     for (uint32_t k = 0; k < nb; ++k) any_exact |= ((*hp)[k].use_tc == 0);
+    if (cascade) {
+      any_exact = false;
+      if ((rc = launch_cascade_match(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_items, nb, max_nJ, max_nI, dim, dtype, ratio2,
+                                     o.d_counters, d_matches))) return rc;
+      launches += 1;
+    }
     if (any_exact) {
       if ((rc = launch_fill_all_queries(ctx, w, (const PairDesc*)w.d_pairs, nb, (uint2*)w.d_fb, &o.d_counters[1]))) return rc;
       launches += 1;
     }
-    if ((rc = launch_exact_scan(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_fb, &o.d_counters[1],
-                                (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, o.d_counters,
-                                d_matches, d_nn))) return rc;
-    launches += 1;
+    if (!cascade) {
+      if ((rc = launch_exact_scan(ctx, w, (const PairDesc*)w.d_pairs, (const uint2*)w.d_fb, &o.d_counters[1],
+                                  (uint32_t)std::min<uint64_t>(qtotal, 0xffffffffu), dim, dtype, ratio2, o.d_counters,
+                                  d_matches, d_nn))) return rc;
+      launches += 1;
+    }
     if (want_matches) {
       if ((rc = launch_pack_matches(ctx, w, (const PairDesc*)w.d_pairs, nb, o.d_counters + 16, (const uint2*)w.d_mdense,
                                     (uint2*)o.d_matches))) return rc;
@@ -511,6 +526,20 @@ static int match_pairs_impl(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pair
   for (auto& wk : ctx->workers) wk.timing = r3d_match_timing{};
   const size_t nw = ctx->workers.size();
   if (nw == 0) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: context has no device");
+  if (flags & R3D_MATCH_CASCADE_HASHING) {
+    // the hash tables depend on the zero-mean descriptor of ALL views of the matching job: without an explicit
+    // r3d_cascade_prepare() that covers this pair list, the job is this call (the reference's behaviour)
+    bool ready = true;
+    for (auto& wk : ctx->workers) ready = ready && cascade_ready(wk, pairs, n_pairs);
+    if (!ready) {
+      std::set<uint32_t> su(pairs, pairs + 2 * n_pairs);
+      const std::vector<uint32_t> used(su.begin(), su.end());
+      for (auto& wk : ctx->workers) {
+        const int rc = cascade_prepare(ctx, wk, used);
+        if (rc) return rc;
+      }
+    }
+  }
   // Shard the (I-sorted) pair list into contiguous, cost-balanced ranges: one per device, no
   // collective; every device holds all regions.
   std::vector<uint64_t> cut(nw + 1, 0);

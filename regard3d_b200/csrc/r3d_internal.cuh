@@ -65,6 +65,19 @@ struct ViewDev {
   float max_dnorm = 0.f;     // max_i ||a_i - fp16(a_i)||
   float max_abs = 0.f;       // max |a_ik|
   float* d_stats = nullptr;  // 4 floats: max n2, max hn2, max dn2, max abs
+  // cascade hashing (cascade.cu): one block holding hash codes, bucket offsets / ids, bucket ids of this view
+  void* d_cascade = nullptr;
+  size_t cascade_bytes = 0;
+  uint64_t cascade_epoch = 0;   // the zero-mean epoch the tables were hashed under
+  uint32_t cascade_index = 0;   // row of the worker's CascadeView table
+};
+
+struct CascadeView {            // device-visible tables of one hashed view
+  uint32_t* code;               // [n][words] sign bits of the primary projections
+  uint16_t* bucket;             // [n][6] bucket id per group
+  uint32_t* bk_ofs;             // [6][1025] bucket offsets
+  uint32_t* bk_ids;             // [6][n] descriptor ids, ascending inside a bucket
+  uint32_t n, words;
 };
 
 struct PairDesc {            // one entry per pair of a batch (device + host)
@@ -128,6 +141,11 @@ struct DeviceWorker {
   void* d_scan = nullptr; size_t scan_cap = 0;      // split exact scan: partial top-2s + arrival counters  // (i, j) per pair segment, before packing
   void* h_fstage[2] = {nullptr, nullptr}; size_t h_fstage_cap = 0;  // pinned staging of the filter's result download
   r3d_match_timing timing{};  // per-worker accumulation (summed into the context after a call)
+  // cascade hashing: projection table [dim][dim + 60], the hashed views' table, the epoch they belong to
+  float* d_cascade_proj = nullptr;
+  uint32_t cascade_dim = 0;
+  CascadeView* d_cascade_views = nullptr;
+  uint64_t cascade_epoch = 0;
 };
 
 }  // namespace r3d
@@ -143,6 +161,7 @@ struct r3d_ctx {
   // optional NCCL communicator (comm.cu): only the bundle adjustment exchanges data between ranks
   void* nccl_comm = nullptr;
   int comm_world = 1, comm_rank = 0;
+  uint64_t cascade_epoch_counter = 0;
 };
 
 namespace r3d {
