@@ -44,7 +44,9 @@ WORKLOADS = {
     "c2": dict(images=50, feats=10000, dim=144, kind="liop", u8=False, name="C2 (LIOP-144)", seed=2),
     "c2-msurf64": dict(images=50, feats=10000, dim=64, kind="msurf", u8=False, name="C2 (MSURF-64 = AKAZE-float)", seed=2),
     "c3": dict(images=200, feats=20000, dim=128, kind="sift", u8=True, name="C3", seed=3),
-    "c4": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 (exact matcher + F filter)", seed=4),
+    "c4": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 (cascade hashing + F filter)", seed=4,
+               matcher="cascade"),
+    "c4-exact": dict(images=500, feats=10000, dim=128, kind="sift", u8=True, name="C4 images, exact matcher + F filter", seed=4),
 }
 METRIC = "matched_image_pairs_per_sec_exhaustive"
 
@@ -201,9 +203,15 @@ def run_reference(args, wl, rank, emit):
     pair_cost = wl["feats"] * wl["feats"] * wl["dim"] / (20000.0 * 20000.0 * 128.0)     # relative to a C3 pair
     n_sample = int(os.environ.get("R3D_REF_SAMPLE_PAIRS", "0")) or int(np.clip(round(nthreads / 4.0 / pair_cost), 2, 64))
     sample = pairs[:n_sample]
+    cascade = wl.get("matcher") == "cascade"
     times = []
     for it in range(args.warmup + args.steps):
-        dt, _ = cpu_match_sample(po, sc, sample, nthreads)
+        if cascade:   # the sample is its own job: hashing of its views + the bucket search, omp over views / over J
+            tc0 = time.perf_counter()
+            po.cascade_match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
+            dt = time.perf_counter() - tc0
+        else:
+            dt, _ = cpu_match_sample(po, sc, sample, nthreads)
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
@@ -233,6 +241,8 @@ def main():
     ap.add_argument("--no-filter", action="store_true", help="skip the F-filter leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2 D=64 / D=144 side lines (N = 1)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS), help="BASELINE config (default c3 = the north-star set)")
+    ap.add_argument("--matcher", default=None, choices=["exact", "cascade"],
+                    help="exact = tensor-core brute force (default); cascade = OpenMVG CASCADE_HASHING_L2 (default of c4)")
     ap.add_argument("--feats", type=int, default=0, help="experiment only")
     ap.add_argument("--images", type=int, default=0, help="experiment only")
     args = ap.parse_args()
@@ -244,6 +254,8 @@ def main():
     def emit(obj):
         os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     wl = dict(WORKLOADS[args.workload])
+    if args.matcher:
+        wl["matcher"] = args.matcher
     if args.feats:
         wl["feats"] = args.feats
     if args.images:
@@ -294,7 +306,12 @@ def main():
     counts = np.array([len(d) for d in sc["descs"]], np.int64)
     my_pairs, my_ofs = sharding.my_shard(pairs, counts, rank, world)
     my_pairs = np.ascontiguousarray(my_pairs, np.uint32)
-    my_views = sorted(set(np.unique(my_pairs).tolist()))
+    cascade = wl.get("matcher") == "cascade"
+    mflags = capi.MATCH_CASCADE_HASHING if cascade else capi.MATCH_DEFAULT
+    all_views = list(range(n_img))
+    # cascade hashing: the hash tables depend on the zero-mean descriptor of ALL views of the job, so every rank holds
+    # (and, in the end-to-end leg, uploads) all of them and hashes them itself -- replicated work, no exchange
+    my_views = all_views if cascade else sorted(set(np.unique(my_pairs).tolist()))
     n_pairs = len(pairs)
     # pinned host staging (the e2e leg copies from here every step)
     pinned_desc = {v: torch.from_numpy(sc["descs"][v]).pin_memory() for v in my_views}
@@ -306,7 +323,9 @@ def main():
             ctx.upload_regions(v, pinned_desc[v].numpy(), pinned_xy[v].numpy())
 
     def step_resident():
-        m = ctx.match_pairs(my_pairs, RATIO)
+        if cascade:
+            ctx.cascade_prepare(all_views)   # part of the matcher (Cascade_Hashing_Matcher_Regions::Match hashes first)
+        m = ctx.match_pairs(my_pairs, RATIO, mflags)
         if gather is not None:
             gather(m)
         return m
@@ -480,6 +499,25 @@ def main():
                        "gathered_in_pair_order": gather_ok,
                        "gather_ms": (gather.ms if gather is not None else None)},
         }
+        if cascade:
+            # k_cascade_match: L2/HBM-bound integer work.  Algorithmic bytes per query: the candidate ids of its six
+            # buckets (4 B each), the hash code of every distinct candidate, 10 descriptors + its own descriptor, code
+            # and bucket ids; counted from the kernel's own candidate counters (raw / distinct, summed over the steps).
+            words = (dim + 31) // 32
+            rowb = dim * (1 if wl["u8"] else 4)
+            per_step = (4.0 * stbq + 4.0 * words * stcq + q * (11.0 * rowb + 4.0 * words + 12 + 48)) / max(args.steps, 1)
+            ms_k = float(np.mean(fb_ms))
+            hbm = float(peaks.get("hbm_gbs", 6650.0))
+            line["roofline"] = {"bound": "hbm", "kernel": "k_cascade_match (bucket gather + Hamming + 10 exact distances per query; "
+                                                          "timed with the pack kernel that follows it)",
+                                "achieved": per_step / (ms_k * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                "frac": per_step / (ms_k * 1e-3) / 1e9 / hbm,
+                                "peak_source": "%s hbm_gbs (the tables of a pair fit the L2: the fraction can exceed what DRAM alone allows)" % peak_src,
+                                "ms_per_launch": ms_k, "bytes_per_launch": per_step,
+                                "launch": "rank 0's shard of the step = %d pairs" % len(my_pairs), "traffic": None}
+            line["result"]["candidates_per_query"] = stbq / max(q, 1)
+            line["result"]["distinct_candidates_per_query"] = stcq / max(q, 1)
+            line["config"]["matcher"] = "cascade hashing (OpenMVG CASCADE_HASHING_L2 restated: SURVEY.md A.8), hashing of all views inside the step"
         if filt is not None:
             line["f_filter"] = filt
         if ba is not None:
@@ -493,8 +531,18 @@ def main():
             nthreads = effective_cpus()
             n_sample = int(os.environ.get("R3D_CPU_SAMPLE_PAIRS", "0")) or int(np.clip(nthreads, 8, 32))
             sample = pairs[:n_sample]
-            tc, outs = cpu_match_sample(po, sc, sample, nthreads)
-            got = first_pairs(m, 4 * n_sample)
+            if cascade:   # the sample as a job of its own on both sides (its views' zero-mean descriptor)
+                n_sample = max(n_sample, 4 * nthreads)
+                sample = pairs[:n_sample]
+                tc0 = time.perf_counter()
+                o_ofs, o_m = po.cascade_match_pairs(sc["descs"], sc["xys"], sample, RATIO, n_threads=nthreads)
+                tc = time.perf_counter() - tc0
+                outs = [o_m[int(o_ofs[k]):int(o_ofs[k + 1])] for k in range(len(sample))]
+                ctx.cascade_prepare(sorted(set(np.unique(sample).tolist())))
+                got = first_pairs(ctx.match_pairs(sample, RATIO, mflags), 4 * n_sample)
+            else:
+                tc, outs = cpu_match_sample(po, sc, sample, nthreads)
+                got = first_pairs(m, 4 * n_sample)
             same = True
             for (I, J), e in zip(sample, outs):
                 g = got.get((int(I), int(J)))

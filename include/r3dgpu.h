@@ -371,7 +371,8 @@ typedef struct {
   double ms_device_total;/* first launch -> last kernel of the last r3d_match_pairs */
   double ms_host_post;   /* host de-duplication */
   uint64_t kernel_launches;
-  uint64_t queries, fallback_queries, third_chunk_queries, fifth_chunk_queries;
+  uint64_t queries, fallback_queries, third_chunk_queries, fifth_chunk_queries;  /* R3D_MATCH_CASCADE_HASHING: the last two count
+                                                                                 * raw / distinct bucket candidates instead */
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t rejected_queries; /* dropped before any exact distance: the ratio test provably cannot pass */
 } r3d_match_timing;

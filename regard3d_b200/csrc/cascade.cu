@@ -176,18 +176,23 @@ __global__ void __launch_bounds__(256) k_cascade_buckets(const CascadeView* __re
 }
 
 // One warp per query (a descriptor of view J) against the hashed view I.  Dynamic shared memory per warp: the "seen"
-// bitmap over I's descriptors (kept all-zero between queries) and the Hamming histogram.
+// bitmap over I's descriptors (kept all-zero between queries), the Hamming histogram, the list of first occurrences
+// (Hamming << 16 | id, arrival order) that spares pass 2 its gathers, the selected ids and their distances.
+constexpr uint32_t kListCap = 256;
 template <int DTYPE>
-__global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDesc* __restrict__ pairs, const uint2* __restrict__ cidx,
-                                                                    const CascadeView* __restrict__ views, uint32_t dim, float ratio2,
-                                                                    uint32_t bitmap_words, uint32_t* __restrict__ counters,
-                                                                    uint2* __restrict__ matches) {
+__global__ void __launch_bounds__(kMatchWarps * 32, 4) k_cascade_match(const PairDesc* __restrict__ pairs, const uint2* __restrict__ cidx,
+                                                                       const CascadeView* __restrict__ views, uint32_t dim, float ratio2,
+                                                                       uint32_t bitmap_words, uint32_t* __restrict__ counters,
+                                                                       uint2* __restrict__ matches) {
   extern __shared__ uint32_t s_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t lt = (1u << lane) - 1u;
   const uint32_t hist_words = (dim + 1 + 31u) & ~31u;
-  uint32_t* bitmap = s_raw + (size_t)warp * (bitmap_words + hist_words + 32);
+  uint32_t* bitmap = s_raw + (size_t)warp * (bitmap_words + hist_words + kListCap + 64);
   uint32_t* hist = bitmap + bitmap_words;
-  uint32_t* sel = hist + hist_words;  // ids of the (<= 10) selected candidates
+  uint32_t* list = hist + hist_words;
+  uint32_t* sel = list + kListCap;       // ids of the (<= 10) selected candidates
+  float* seld = reinterpret_cast<float*>(sel + 32);
   for (uint32_t t = lane; t < bitmap_words; t += 32) bitmap[t] = 0u;
   __syncwarp();
   const uint32_t pair = blockIdx.y;
@@ -196,6 +201,9 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
   const CascadeView vI = views[ci.x], vJ = views[ci.y];
   const uint32_t words = vI.words;
   const size_t rb = row_bytes(DTYPE, dim);
+  // uint8 rows of 16 * 2^k bytes: `parts` lanes share one exact distance (integer sum, order-free: exact_l2's own rule)
+  const uint32_t parts = (DTYPE == 1 && (dim == 16 || dim == 32 || dim == 64 || dim == 128 || dim == 256)) ? dim / 16 : 0;
+  uint32_t stat_raw = 0, stat_distinct = 0;  // candidates walked / distinct candidates, over this warp's queries
   for (uint32_t q = blockIdx.x * kMatchWarps + warp; q < pd.nJ; q += gridDim.x * kMatchWarps) {
     // the query's six buckets in I
     uint32_t beg[kGroups], len[kGroups], total = 0;
@@ -209,8 +217,14 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
     }
     if (total <= 2u) continue;  // "not at least NN candidates" (raw count)
     uint32_t qc[8];
+    if (words == 4) {
+      const uint4 c = *reinterpret_cast<const uint4*>(vJ.code + (size_t)q * 4);
+      qc[0] = c.x; qc[1] = c.y; qc[2] = c.z; qc[3] = c.w;
+      qc[4] = qc[5] = qc[6] = qc[7] = 0u;
+    } else {
 #pragma unroll
-    for (int wd = 0; wd < 8; ++wd) qc[wd] = (uint32_t)wd < words ? vJ.code[(size_t)q * words + wd] : 0u;
+      for (int wd = 0; wd < 8; ++wd) qc[wd] = (uint32_t)wd < words ? vJ.code[(size_t)q * words + wd] : 0u;
+    }
     for (uint32_t t = lane; t < hist_words; t += 32) hist[t] = 0u;
     __syncwarp();
     // candidate s of the concatenated bucket lists -> id
@@ -224,13 +238,19 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
       return 0u;
     };
     auto hamming = [&](uint32_t id) -> uint32_t {
+      if (words == 4) {
+        const uint4 c = __ldg(reinterpret_cast<const uint4*>(vI.code + (size_t)id * 4));
+        return __popc(qc[0] ^ c.x) + __popc(qc[1] ^ c.y) + __popc(qc[2] ^ c.z) + __popc(qc[3] ^ c.w);
+      }
       uint32_t h = 0;
 #pragma unroll
       for (int wd = 0; wd < 8; ++wd)
         if ((uint32_t)wd < words) h += __popc(qc[wd] ^ vI.code[(size_t)id * words + wd]);
       return h;
     };
-    // ---- pass 1: first occurrences -> Hamming histogram ----
+    // ---- pass 1: first occurrences -> Hamming histogram (+ the list, when it fits) ----
+    const bool use_list = total <= kListCap;
+    uint32_t n_list = 0;
     for (uint32_t base = 0; base < total; base += 32) {
       const uint32_t s = base + lane;
       const bool act = s < total;
@@ -241,7 +261,13 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
         const uint32_t bit = 1u << (id & 31u);
         fresh = (atomicOr(&bitmap[id >> 5], bit) & bit) == 0u;
       }
-      if (fresh) atomicAdd(&hist[hamming(id)], 1u);
+      const uint32_t h = fresh ? hamming(id) : 0u;
+      if (fresh) atomicAdd(&hist[h], 1u);
+      if (use_list) {
+        const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+        if (fresh) list[n_list + __popc(fm & lt)] = (h << 16) | id;
+        n_list += __popc(fm);
+      }
     }
     __syncwarp();
     // ---- cut: the Hamming distance h* of the 10th distinct candidate ----
@@ -273,35 +299,69 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
     }
     const uint32_t target = distinct < (uint32_t)kTop ? distinct : (uint32_t)kTop;
     const uint32_t need_eq = target - below;
-    // ---- pass 2: same walk; a first occurrence finds its bit set and clears it (the bitmap ends all-zero) ----
+    stat_raw += total;
+    stat_distinct += distinct;
+    // ---- pass 2: every first occurrence again, in arrival order: clear its bit (the bitmap ends all-zero), take it
+    //      when it lies below the cut or among the first arrivals on it ----
     uint32_t n_sel = 0, eq_seen = 0;
-    for (uint32_t base = 0; base < total; base += 32) {
+    const uint32_t walk = use_list ? n_list : total;
+    for (uint32_t base = 0; base < walk; base += 32) {
       const uint32_t s = base + lane;
-      const bool act = s < total;
-      const uint32_t id = act ? candidate(s) : 0xffffffffu;
-      const unsigned same = __match_any_sync(0xffffffffu, id);
+      const bool act = s < walk;
+      uint32_t id = 0xffffffffu, h = 0xffffffffu;
       bool fresh = false;
-      if (act && (uint32_t)(__ffs(same) - 1) == lane) {
-        const uint32_t bit = 1u << (id & 31u);
-        fresh = (atomicAnd(&bitmap[id >> 5], ~bit) & bit) != 0u;
+      if (use_list) {
+        if (act) {
+          const uint32_t e = list[s];
+          id = e & 0xffffu;
+          h = e >> 16;
+          fresh = true;
+          atomicAnd(&bitmap[id >> 5], ~(1u << (id & 31u)));
+        }
+      } else {
+        id = act ? candidate(s) : 0xffffffffu;
+        const unsigned same = __match_any_sync(0xffffffffu, id);
+        if (act && (uint32_t)(__ffs(same) - 1) == lane) {
+          const uint32_t bit = 1u << (id & 31u);
+          fresh = (atomicAnd(&bitmap[id >> 5], ~bit) & bit) != 0u;
+        }
+        h = fresh ? hamming(id) : 0xffffffffu;
       }
-      const uint32_t h = fresh ? hamming(id) : 0xffffffffu;
       const bool is_eq = fresh && h == hstar;
       const unsigned eqm = __ballot_sync(0xffffffffu, is_eq);
-      const bool take = fresh && distinct >= 2u && (h < hstar || (is_eq && eq_seen + __popc(eqm & ((1u << lane) - 1u)) < need_eq));
+      const bool take = fresh && distinct >= 2u && (h < hstar || (is_eq && eq_seen + __popc(eqm & lt) < need_eq));
       eq_seen += __popc(eqm);
       const unsigned tm = __ballot_sync(0xffffffffu, take);
-      if (take) sel[n_sel + __popc(tm & ((1u << lane) - 1u))] = id;
+      if (take) sel[n_sel + __popc(tm & lt)] = id;
       n_sel += __popc(tm);
     }
     __syncwarp();
     if (n_sel < 2u) continue;
-    // ---- exact distances of the selected candidates (a lane each, upstream accumulation order), top-2 by (d, id) ----
+    // ---- exact distances of the selected candidates (upstream accumulation order), top-2 by (d, id) ----
     float d = FLT_MAX;
     uint32_t id = 0xffffffffu;
-    if (lane < n_sel) {
+    const unsigned char* qrow = (const unsigned char*)pd.descJ + (size_t)q * rb;
+    if (parts) {
+      const uint32_t piece = lane % parts, per_pass = 32 / parts;
+      const uint4 qv = *reinterpret_cast<const uint4*>(qrow + piece * 16);
+      for (uint32_t c0 = 0; c0 < n_sel; c0 += per_pass) {
+        const uint32_t c = c0 + lane / parts;
+        uint32_t isum = 0u;
+        if (c < n_sel) {
+          const uint4 dv = __ldg(reinterpret_cast<const uint4*>((const unsigned char*)pd.descI + (size_t)sel[c] * rb + piece * 16));
+          uint32_t ad = __vabsdiffu4(qv.x, dv.x); isum = __dp4a(ad, ad, isum);
+          ad = __vabsdiffu4(qv.y, dv.y); isum = __dp4a(ad, ad, isum);
+          ad = __vabsdiffu4(qv.z, dv.z); isum = __dp4a(ad, ad, isum);
+          ad = __vabsdiffu4(qv.w, dv.w); isum = __dp4a(ad, ad, isum);
+        }
+        for (uint32_t o = parts >> 1; o >= 1; o >>= 1) isum += __shfl_xor_sync(0xffffffffu, isum, o);
+        if (c < n_sel && piece == 0) seld[c] = (float)isum;
+      }
+      __syncwarp();
+      if (lane < n_sel) { id = sel[lane]; d = seld[lane]; }
+    } else if (lane < n_sel) {
       id = sel[lane];
-      d = exact_l2<DTYPE>((const unsigned char*)pd.descJ + (size_t)q * rb, (const unsigned char*)pd.descI + (size_t)id * rb, dim);
+      d = exact_l2<DTYPE>(qrow, (const unsigned char*)pd.descI + (size_t)id * rb, dim);
     }
     const bool have = lane < n_sel;
     // lexicographic minimum over the lanes that hold a candidate, twice
@@ -324,6 +384,10 @@ __global__ void __launch_bounds__(kMatchWarps * 32) k_cascade_match(const PairDe
     warp_min(have && (int)lane != l1, d, id, &t.d2, &t.i2);
     if (lane == 0) emit_result(pd, pair, q, t, ratio2, counters, matches, nullptr);
     __syncwarp();
+  }
+  if (lane == 0 && stat_raw) {  // reported through r3d_match_timing (third_chunk_queries / fifth_chunk_queries slots)
+    atomicAdd(&counters[4], stat_raw);
+    atomicAdd(&counters[3], stat_distinct);
   }
 }
 
@@ -455,7 +519,7 @@ int launch_cascade_match(r3d_ctx* ctx, DeviceWorker& w, const PairDesc* d_pairs,
   if (!n_pairs || !max_nJ) return R3D_OK;
   const uint32_t bitmap_words = ((max_nI + 31) / 32 + 31) & ~31u;
   const uint32_t hist_words = (dim + 1 + 31u) & ~31u;
-  const size_t smem = (size_t)kMatchWarps * (bitmap_words + hist_words + 32) * sizeof(uint32_t);
+  const size_t smem = (size_t)kMatchWarps * (bitmap_words + hist_words + kListCap + 64) * sizeof(uint32_t);
   const uint32_t gx = std::min<uint32_t>((max_nJ + kMatchWarps - 1) / kMatchWarps, 64u);
   for (uint32_t p0 = 0; p0 < n_pairs; p0 += 65535u) {
     const uint32_t np = std::min(65535u, n_pairs - p0);
