@@ -1,5 +1,6 @@
 # One GPU-box session (run: gpurun --timeout T -- bash scripts/gpu_session.sh STEP [STEP...]); outputs in gpurun_out/.
-# Steps: smoke tests bench bench_ref sanitize ncu_k1 ncu_launches ncu_ba c2 c4
+# Steps: smoke tests bench bench_ref sanitize ncu_k1 ncu_launches ncu_ba c2 c4 c4exact filter ncu_filter ncu_cascade
+#        ab_epilogue ab_chol scale (multi-GPU: gpurun --gpus N, SCALE_N="1 2 4 8")
 set -x
 mkdir -p gpurun_out
 for step in "$@"; do
@@ -9,7 +10,28 @@ tests) timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.
 bench) timeout 900 python bench.py ${BENCH_ARGS:-} > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -3 gpurun_out/bench.err; head -c 1500 gpurun_out/bench.json ;;
 bench_ref) timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json ;;
 c2) timeout 600 python bench.py --workload c2 --no-ba > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "c2 rc=$?" ;;
-c4) timeout 900 python bench.py --workload c4 --steps 1 --warmup 1 --no-ba > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?" ;;
+c4) timeout 900 python bench.py --workload c4 --steps 2 --warmup 3 --no-ba --no-extras > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "c4 rc=$?" ;;
+c4exact) timeout 900 python bench.py --workload c4-exact --steps 2 --warmup 3 --no-ba --no-extras > gpurun_out/bench_c4_exact.json 2> gpurun_out/bench_c4_exact.err; echo "c4exact rc=$?" ;;
+ncu_cascade) timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_cascade_match -s 3 -c 1 -f -o gpurun_out/prof_cascade_match python bench.py --workload c4 --steps 1 --warmup 3 --no-ba --no-extras --no-filter --no-cpu-baseline > gpurun_out/b_ncu_cascade.log 2>&1; echo "ncu_cascade rc=$?" ;;
+ab_epilogue)  # candidate-kernel epilogue A/B (profiles/r02_chunk_ab.md): TMEM drain order x epilogue warps, three workloads
+  for cfg in "0 8" "1 8" "1 16" "0 16"; do set -- $cfg
+    for wl in c2-msurf64 c2 c3; do
+      R3D_K1_DRAIN=$1 R3D_K1_EPI=$2 timeout 600 python bench.py --workload $wl --steps 3 --warmup 3 --no-ba --no-extras --no-filter --no-cpu-baseline > gpurun_out/bench_dr$1_e$2_$wl.json 2> gpurun_out/bench_dr$1_e$2_$wl.err
+      python -c "import json; d=json.load(open('gpurun_out/bench_dr$1_e$2_$wl.json')); print('drain $1 epi $2 $wl', round(d['value']), round(d['roofline']['frac'],3), round(d['breakdown_ms']['candidates'],2))"
+    done
+  done ;;
+ab_chol)  # BA linear solve A/B (profiles/r02_ba_cholesky_ab.md)
+  for mode in "envelope 8" "envelope 1" "dense 8"; do set -- $mode
+    R3D_BA_CHOL=$1 R3D_BA_ENV_CTAS=$2 R3D_DEBUG_TIMING=1 timeout 600 python bench.py --workload c2 --steps 2 --warmup 3 --no-filter --no-extras --no-cpu-baseline > gpurun_out/bench_ba_$1$2.json 2> gpurun_out/bench_ba_$1$2.err
+    python -c "import json; d=json.load(open('gpurun_out/bench_ba_$1$2.json'))['ba']; print('$1 $2', d['iters_per_s'], d['final_cost'], d['seconds_linear'])"
+  done ;;
+scale)  # strong scaling of the default workload + the reference arm, one torchrun per N (gpurun --gpus max(N))
+  for n in ${SCALE_N:-1 2 4 8}; do
+    if [ "$n" = 1 ]; then run="python"; else run="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517"; fi
+    timeout 900 $run bench.py --gpus $n ${BENCH_ARGS:---steps 3 --warmup 3} > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; echo "scale n=$n rc=$?"
+    timeout 600 $run bench.py --gpus $n --impl reference --steps 1 --warmup 0 > gpurun_out/scale_ref_n$n.json 2> gpurun_out/scale_ref_n$n.err; echo "ref n=$n rc=$?"
+    python -c "import json; d=json.loads(open('gpurun_out/scale_n$n.json').read().strip().splitlines()[-1]); print($n, d['value'], d['e2e']['value'], (d['result'] or {}).get('gather_ms'))"
+  done ;;
 sanitize)
   for tool in memcheck racecheck synccheck; do
     for part in match filter ba liop; do
