@@ -5,7 +5,8 @@ here -- SURVEY.md 8c -- so these pin the ORACLE itself against drift and give th
     python tests/golden/make_golden.py          # rewrites oracle_v1.json
 
 Content: for a few seeded synthetic scenes (regard3d_b200/synth.py) the SHA-1 of every pair's (i, j) sequence after
-putative matching and after the F / E / H a-contrario filters, and the cost trace of a seeded bundle adjustment."""
+putative matching, after the F / E / H a-contrario filters and of the cascade-hashing matcher (ratio 0.8), and the cost
+trace of a seeded bundle adjustment."""
 import hashlib
 import json
 import os
@@ -41,8 +42,9 @@ def scene_record(po, synth, sc_def):
     fo, fm = po.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m)
     eo, em = po.filter_pairs_E(sc["xys"], sc["widths"], sc["heights"], Ks, pairs, ofs, m)
     ho, hm = po.filter_pairs_H(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m)
+    co, cm = po.cascade_match_pairs(sc["descs"], sc["xys"], pairs, 0.8)   # cascade hashing (BASELINE config 4's matcher)
     return {"def": sc_def, "putative": per_pair(pairs, ofs, m), "F": per_pair(pairs, fo, fm), "E": per_pair(pairs, eo, em),
-            "H": per_pair(pairs, ho, hm)}
+            "H": per_pair(pairs, ho, hm), "cascade_r0.8": per_pair(pairs, co, cm)}
 
 
 def ba_record(po, synth):

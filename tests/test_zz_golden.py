@@ -51,6 +51,8 @@ def test_gpu_path_reproduces_the_golden_fixtures(scene, gpu_ctx, r3dlib):
     for name, model in (("F", r3dlib.MODEL_F), ("E", r3dlib.MODEL_E), ("H", r3dlib.MODEL_H)):
         got = gpu_ctx.filter_pairs(put, sc["widths"], sc["heights"], model=model, Ks=Ks)
         assert _rows(got.to_dict(), pairs) == scene[name], name
+    cas = gpu_ctx.match_pairs(pairs, 0.8, r3dlib.MATCH_CASCADE_HASHING)
+    assert _rows(cas.to_dict(), pairs) == scene["cascade_r0.8"]
 
 
 @pytest.mark.gpu
