@@ -473,6 +473,8 @@ int r3d_match_pairs(r3d_ctx* ctx, const uint32_t* pairs, uint64_t n_pairs, float
   if (!ctx || !out || (n_pairs && !pairs)) return fail(ctx, R3D_ERR_INVALID, "r3d_match_pairs: bad arguments");
   *out = nullptr;
   if (!(flags & R3D_MATCH_MUTUAL_NN)) return match_pairs_impl(ctx, pairs, n_pairs, dist_ratio, flags, out);
+  if (flags & R3D_MATCH_CASCADE_HASHING)
+    return fail(ctx, R3D_ERR_UNSUPPORTED, "r3d_match_pairs: the mutual-NN select is defined for the exact matcher only");
   // Optional mutual-nearest-neighbour select (north_star; NOT part of the reference's MatchDistanceRatio):
   // a match (i in I, j in J) of the forward pass survives iff j is also the nearest neighbour of i among J's
   // descriptors.  Second pass = the same matcher on the swapped pairs with the ratio test disabled.
