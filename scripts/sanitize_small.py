@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small-shape pass over every kernel family for `compute-sanitizer` (memcheck / racecheck / synccheck / initcheck):
 
-    compute-sanitizer --tool racecheck python scripts/sanitize_small.py [match|filter|ba|all]
+    compute-sanitizer --tool racecheck python scripts/sanitize_small.py [match|filter|ba|liop|cascade|ba_envelope|all]
 
 Shapes are tiny on purpose (the sanitizer serialises everything); correctness of the results is checked by the
 `-m gpu` tests, this script only has to execute every kernel once."""
@@ -50,6 +50,30 @@ if what in ("ba", "all"):
     s, trace = ctx.bundle_adjust(arrs, max_iterations=3)
     print("ba:", s["iterations"], "iterations, cost", trace[0], "->", trace[-1])
     ctx.ba_residuals(arrs)
+if what in ("cascade", "all"):
+    s8 = synth.make_scene(3, n_feats, 128, "sift", seed=6, as_u8=True)
+    ctx.clear_regions()
+    for v in range(3):
+        ctx.upload_regions(v, s8["descs"][v], s8["xys"][v])
+    mc = ctx.match_pairs(synth.exhaustive_pairs(3), 0.8, capi.MATCH_CASCADE_HASHING)
+    print("cascade u8/128:", mc.total, "matches")
+    sf = synth.make_scene(3, n_feats, 144, "liop", seed=7)
+    ctx.clear_regions()
+    for v in range(3):
+        ctx.upload_regions(v, sf["descs"][v], sf["xys"][v])
+    mc = ctx.match_pairs(synth.exhaustive_pairs(3), 0.8, capi.MATCH_CASCADE_HASHING)
+    print("cascade f32/144:", mc.total, "matches")
+if what in ("ba_envelope", "all"):
+    os.environ["R3D_BA_CHOL"] = "envelope"
+    prob = synth.make_ba_problem(n_cams=37, n_pts=1500, obs_per_pt=4, seed=41)
+    arrs = {}
+    for k in ("poses", "intrinsics", "points", "obs_xy"):
+        arrs[k] = np.ascontiguousarray(prob[k], np.float64)
+    for k in ("obs_cam", "obs_pt", "cam_intr"):
+        arrs[k] = np.ascontiguousarray(prob[k], np.uint32)
+    s, trace = ctx.bundle_adjust(arrs, max_iterations=2)
+    print("ba (envelope Cholesky, cluster of 8):", s["iterations"], "iterations, cost", trace[0], "->", trace[-1])
+    del os.environ["R3D_BA_CHOL"]
 if what in ("liop", "all"):
     rng = np.random.default_rng(1)
     img = rng.random((120, 160)).astype(np.float32)
