@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- matched image-pairs / second on the compute-matches hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c3|c2|c2-msurf64|c4]
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference] [--workload c3|c2|c2-msurf64|c4|c4-exact] [--matcher exact|cascade]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (default): BASELINE.json configs[2] = **C3**, the configuration the north_star target is quoted on:
@@ -11,9 +11,12 @@ operands), so N = 1 runs the whole set.  One step = one pass over ALL 19 900 pai
 
 N > 1 = STRONG scaling of that one set: every rank holds the regions its shard touches, the I-sorted pair list
 is cut into cost-balanced contiguous ranges (regard3d_b200/sharding.py, SURVEY.md 8e), no data-path collective;
-the per-rank PairWiseMatches are gathered to rank 0 IN PAIR ORDER INSIDE THE TIMED REGION (CSR export -> NCCL
-send/recv over NVLink -> rank 0's pinned host buffer), so the clock stops when rank 0 holds every match list in
-host memory -- the reference's `map_PutativesMatches` (src/R3DComputeMatches.cpp:437-488).
+the per-rank PairWiseMatches are gathered to rank 0 IN PAIR ORDER INSIDE THE TIMED REGION (sharding.Gather: CSR export
+straight into a shared-memory segment rank 0 owns, or -- R3D_GATHER=p2p -- pinned -> NCCL send/recv over NVLink ->
+rank 0's pinned host buffer), so the clock stops when rank 0 holds every match list in host memory -- the
+reference's `map_PutativesMatches` (src/R3DComputeMatches.cpp:437-488).
+--workload c4 = BASELINE configs[3] as named: 500 images, OpenMVG's cascade-hashing matcher (hashing of all views inside
+the step) + the F filter; c4-exact = the same images through the exact tensor-core matcher.
 
 value : pairs/s, descriptors already resident in HBM (r3d_match_pairs on the shard + gather).
 e2e   : pairs/s through the C ABI from pinned HOST buffers: r3d_clear_regions + r3d_upload_regions of every view

@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(kFThreads, MODEL == 2 ? 1 : 2) k_acransac_fuse
 #pragma unroll 8
               for (uint32_t j = 0; j < 32; ++j) hist[j] = 0;
             }
+            __syncwarp();  // every lane has read the group counters before lane 0 clears them (racecheck: intra-warp hazard)
             if (lane == 0) {
               Q.cnt[gb[cw]][gm[cw]] = ch; Q.cnt_lo[gb[cw]][gm[cw]] = cl; Q.lb[gb[cw]][gm[cw]] = lbv;
               S.gcnt[2 * cw] = 0; S.gcnt[2 * cw + 1] = 0;
