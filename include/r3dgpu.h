@@ -324,6 +324,7 @@ int r3d_comm_world(const r3d_ctx* ctx);   /* 1 when no communicator is attached 
 int r3d_ba_residuals(r3d_ctx* ctx, const r3d_ba_problem* p, double* res /* n_obs x 2 */);
 
 /* ---- file-level twin of R3DComputeMatches::computeMatches() --------------------------------- */
+#define R3D_MATCHING_CASCADE_HASHING 100 /* not a value of the reference's matchingAlgorithm switch */
 typedef void (*r3d_progress_cb)(float fraction, const char* message, void* user);
 
 typedef struct {
@@ -331,7 +332,8 @@ typedef struct {
   int compute_fundamental;        /* R3DFParams::computeFundalmentalMatrix_ */
   int compute_essential;          /* R3DFParams::computeEssentialMatrix_ -> matches.e.txt (+ the poor-overlap filter) */
   int compute_homography;         /* R3DFParams::computeHomographyMatrix_ -> matches.h.txt */
-  int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher */
+  int matching_algorithm;         /* 0..8 as src/R3DComputeMatches.cpp:2036-2062; all map to the exact GPU matcher.
+                                   * Extension: R3D_MATCHING_CASCADE_HASHING selects R3D_MATCH_CASCADE_HASHING */
   uint32_t descriptor_dim;        /* 144 for R3D_AKAZE_LIOP_Regions */
   int svg_output;                 /* computeMatches(..., bool svgOutput, ...): PutativeAdjacencyMatrix.svg and
                                    * GeometricAdjacencyMatrix.svg in the matches dir (:2074-2076, :2238-2240) */

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("R3D_LIB") or os.path.join(_HERE, "libr3dgpu.so")  # R
 
 R3D_F32, R3D_U8 = 0, 1
 MATCH_DEFAULT, MATCH_EXACT_SCAN, MATCH_NO_COORD_DEDUP, MATCH_MUTUAL_NN, MATCH_CASCADE_HASHING = 0, 1, 2, 4, 8
+MATCHING_CASCADE_HASHING = 100  # r3d_cm_params.matching_algorithm extension
 MODEL_F, MODEL_E, MODEL_H = 0, 1, 2
 
 indmatch_dtype = np.dtype([("i", np.uint32), ("j", np.uint32)])

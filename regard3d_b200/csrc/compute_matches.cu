@@ -129,7 +129,10 @@ extern "C" int r3d_compute_matches(r3d_ctx* ctx, const r3d_cm_params* params, co
   // every matchingAlgorithm value of the reference (0 FLANN, 1-3 KGraph, 4 brute force, 5 MRPT, 6-8 HNSW:
   // src/R3DComputeMatches.cpp:2036-2062) maps to the exact brute-force matcher: the ANN variants are
   // approximations of it
-  rc = r3d_match_pairs(ctx, pairs.data(), pairs.size() / 2, params->dist_ratio, R3D_MATCH_DEFAULT, &put);
+  // matchingAlgorithm 0..8 (FLANN / KGraph / MRPT / HNSW / brute force) all map to the exact matcher; the one extension is
+  // R3D_MATCHING_CASCADE_HASHING = OpenMVG's CASCADE_HASHING_L2, which the reference's switch does not offer
+  const uint32_t mflags = params->matching_algorithm == R3D_MATCHING_CASCADE_HASHING ? R3D_MATCH_CASCADE_HASHING : R3D_MATCH_DEFAULT;
+  rc = r3d_match_pairs(ctx, pairs.data(), pairs.size() / 2, params->dist_ratio, mflags, &put);
   if (rc) return rc;
   if (stats) {
     stats->seconds_match = now_s() - t0;

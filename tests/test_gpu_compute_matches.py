@@ -107,3 +107,20 @@ def test_compute_matches_svg_output(gpu_ctx, oracle, tmp_path):
     for name in ("PutativeAdjacencyMatrix.svg", "GeometricAdjacencyMatrix.svg"):
         txt = (tmp_path / name).read_text()
         assert txt.startswith("<?xml") and txt.rstrip().endswith("</svg>") and txt.count("<rect") == 3   # pairs (0,1) (0,2) (1,2)
+
+
+def test_compute_matches_with_the_cascade_hashing_matcher(gpu_ctx, oracle, r3dlib, tmp_path):
+    """matching_algorithm = R3D_MATCHING_CASCADE_HASHING (an extension: the reference's switch has no such entry): the
+    putative and F files equal the oracle's cascade matcher + F filter."""
+    sc, names = _write_project(oracle, tmp_path)
+    gpu_ctx.compute_matches(str(tmp_path), names, sc["widths"], sc["heights"], dist_ratio=0.8, dim=144,
+                            matching_algorithm=r3dlib.MATCHING_CASCADE_HASHING)
+    pairs = synth.exhaustive_pairs(len(names))
+    ofs, m = oracle.cascade_match_pairs(sc["descs"], sc["xys"], pairs, 0.8)
+    fo, fm = oracle.filter_pairs_F(sc["xys"], sc["widths"], sc["heights"], pairs, ofs, m)
+    po, pf = str(tmp_path / "oracle.putative.txt"), str(tmp_path / "oracle.f.txt")
+    oracle.save_matches_txt(po, pairs, ofs, m)
+    oracle.save_matches_txt(pf, pairs, fo, fm)
+    assert len(m) > 500
+    assert open(tmp_path / "matches.putative.txt").read() == open(po).read()
+    assert open(tmp_path / "matches.f.txt").read() == open(pf).read()
