@@ -22,6 +22,9 @@
 #include "r3d_cascade.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <set>
 #include <string>
@@ -61,17 +64,29 @@ __global__ void k_cascade_zero_mean(const float* __restrict__ means, uint32_t n_
   out[j] = n_views ? __fdiv_rn(acc, (float)n_views) : 0.f;
 }
 
-// Hash codes + bucket ids of kHashRows descriptors per CTA.  projT: [dim][np] (np = dim + 60), thread p owns
-// projection p (and p + blockDim.x).
+// Hash codes + bucket ids of kHashRows descriptors per CTA, all views of the job in ONE launch: CTA b belongs to the view
+// v with first_block[v] <= b < first_block[v + 1].  projT: [dim][np] (np = dim + 60), thread p owns projection p (and
+// p + blockDim.x).
 constexpr int kHashRows = 8;
+struct HashJob { const void* desc; uint32_t* code; uint16_t* bucket; uint32_t n; uint32_t first_block; };
 template <int DTYPE>
-__global__ void __launch_bounds__(256) k_cascade_hash(const void* __restrict__ desc, uint32_t n, uint32_t dim,
+__global__ void __launch_bounds__(256) k_cascade_hash(const HashJob* __restrict__ jobs, uint32_t n_jobs, uint32_t dim,
                                                       const float* __restrict__ projT, const float* __restrict__ zero_mean,
-                                                      uint32_t words, uint32_t* __restrict__ code, uint16_t* __restrict__ bucket) {
+                                                      uint32_t words) {
   extern __shared__ float s_d[];                 // kHashRows x dim centred descriptors
   __shared__ uint32_t s_code[kHashRows][8];
   __shared__ uint32_t s_bucket[kHashRows][kGroups];
-  const uint32_t row0 = blockIdx.x * kHashRows;
+  uint32_t lo = 0, hi = n_jobs;                  // last job whose first_block <= blockIdx.x
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (jobs[mid].first_block <= blockIdx.x) lo = mid; else hi = mid;
+  }
+  const HashJob jb = jobs[lo];
+  const void* desc = jb.desc;
+  const uint32_t n = jb.n;
+  uint32_t* code = jb.code;
+  uint16_t* bucket = jb.bucket;
+  const uint32_t row0 = (blockIdx.x - jb.first_block) * kHashRows;
   const uint32_t np = dim + kGroups * kBitsPerBucket;
   for (uint32_t t = threadIdx.x; t < kHashRows * dim; t += blockDim.x) {
     const uint32_t r = t / dim, k = t % dim;
@@ -405,6 +420,7 @@ void cascade_release_view(DeviceWorker& w, ViewDev& v) {
 }
 
 int cascade_prepare(r3d_ctx* ctx, DeviceWorker& w, const std::vector<uint32_t>& used) {
+  const auto t_begin = std::chrono::steady_clock::now();
   R3D_CUDA_TRY(ctx, cudaSetDevice(w.device));
   if (used.empty()) return R3D_OK;
   uint32_t dim = 0;
@@ -463,6 +479,9 @@ int cascade_prepare(r3d_ctx* ctx, DeviceWorker& w, const std::vector<uint32_t>& 
   // (3) per view: tables, hash codes; (4) buckets of all views in one launch
   const uint64_t epoch = ++ctx->cascade_epoch_counter;
   std::vector<CascadeView> hv(nu);
+  std::vector<HashJob> hjobs;
+  uint32_t total_blocks = 0;
+  void* to_release = nullptr;
   for (uint32_t k = 0; k < nu; ++k) {
     ViewDev& v = w.views.find(used[k])->second;
     const size_t b_code = align16((size_t)v.n * words * 4), b_ofs = align16((size_t)kGroups * (kBuckets + 1) * 4),
@@ -485,11 +504,18 @@ int cascade_prepare(r3d_ctx* ctx, DeviceWorker& w, const std::vector<uint32_t>& 
     v.cascade_epoch = epoch;
     v.cascade_index = k;
     if (v.n) {
-      const uint32_t grid = (v.n + kHashRows - 1) / kHashRows;
-      const size_t smem = (size_t)kHashRows * dim * sizeof(float);
-      if (dtype == 0) k_cascade_hash<0><<<grid, 256, smem, w.stream>>>(v.d_desc, v.n, dim, w.d_cascade_proj, d_zero, words, cv.code, cv.bucket);
-      else k_cascade_hash<1><<<grid, 256, smem, w.stream>>>(v.d_desc, v.n, dim, w.d_cascade_proj, d_zero, words, cv.code, cv.bucket);
+      hjobs.push_back(HashJob{v.d_desc, cv.code, cv.bucket, v.n, total_blocks});
+      total_blocks += (v.n + kHashRows - 1) / kHashRows;
     }
+  }
+  if (!hjobs.empty()) {
+    HashJob* d_hjobs = (HashJob*)pool_alloc(w, hjobs.size() * sizeof(HashJob));
+    if (!d_hjobs) return fail(ctx, R3D_ERR_NOMEM, "cascade hashing: job table");
+    R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_hjobs, hjobs.data(), hjobs.size() * sizeof(HashJob), cudaMemcpyHostToDevice, w.stream));
+    const size_t smem = (size_t)kHashRows * dim * sizeof(float);
+    if (dtype == 0) k_cascade_hash<0><<<total_blocks, 256, smem, w.stream>>>(d_hjobs, (uint32_t)hjobs.size(), dim, w.d_cascade_proj, d_zero, words);
+    else k_cascade_hash<1><<<total_blocks, 256, smem, w.stream>>>(d_hjobs, (uint32_t)hjobs.size(), dim, w.d_cascade_proj, d_zero, words);
+    to_release = d_hjobs;
   }
   R3D_CUDA_TRY(ctx, cudaGetLastError());
   R3D_CUDA_TRY(ctx, cudaMemcpyAsync(d_views, hv.data(), hv.size() * sizeof(CascadeView), cudaMemcpyHostToDevice, w.stream));
@@ -498,9 +524,14 @@ int cascade_prepare(r3d_ctx* ctx, DeviceWorker& w, const std::vector<uint32_t>& 
   R3D_CUDA_TRY(ctx, cudaStreamSynchronize(w.stream));  // hv / jobs are locals
   pool_release(w, d_means);
   pool_release(w, d_jobs);
+  if (to_release) pool_release(w, to_release);
   if (w.d_cascade_views) pool_release(w, w.d_cascade_views);
   w.d_cascade_views = d_views;
   w.cascade_epoch = epoch;
+  static const bool dbg = getenv("R3D_DEBUG_TIMING") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[r3d] cascade hashing of %u views: %.2f ms\n", nu,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
   return R3D_OK;
 }
 
