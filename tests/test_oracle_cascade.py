@@ -72,3 +72,41 @@ def test_empty_and_tiny_views_give_nothing(oracle):
     got = match_sets(ofs, m, pairs)
     for (I, J) in got:
         assert sizes[I] >= 3 and sizes[J] >= 1
+
+
+def test_projection_table_equals_a_numpy_replay_of_libstdcxx(oracle):
+    """CascadeHasher::Init draws std::normal_distribution<>(0, 1) from std::mt19937(default_seed = 5489).  libstdc++'s
+    normal_distribution is Marsaglia's polar method on generate_canonical<double, 53> (two 32-bit draws per uniform, low
+    word first) and hands out y * mult first, keeping x * mult for the next call.  numpy's legacy RandomState(5489) is
+    the same init_genrand(5489) generator, so its raw 32-bit stream replays the table."""
+    rs = np.random.RandomState(5489)
+    raw = rs._bit_generator.random_raw(200000).astype(np.uint64)
+    pos = [0]
+
+    def canonical():
+        lo, hi = raw[pos[0]], raw[pos[0] + 1]
+        pos[0] += 2
+        v = (float(lo) + float(hi) * 4294967296.0) / 18446744073709551616.0
+        return v if v < 1.0 else np.nextafter(1.0, 0.0)
+
+    out, saved = [], None
+    need = 300
+    while len(out) < need:
+        if saved is not None:
+            out.append(saved)
+            saved = None
+            continue
+        while True:
+            x = 2.0 * canonical() - 1.0
+            y = 2.0 * canonical() - 1.0
+            r2 = x * x + y * y
+            if not (r2 > 1.0 or r2 == 0.0):
+                break
+        mult = np.sqrt(-2.0 * np.log(r2) / r2)
+        saved = x * mult
+        out.append(y * mult)
+    ref = np.array(out[:need], np.float64).astype(np.float32)
+    P = oracle.cascade_projections(128)
+    got = P.reshape(-1)[:need]
+    assert np.allclose(got, ref, rtol=2e-7, atol=0)          # libm log/sqrt may differ from numpy's in the last ulp
+    assert np.array_equal(got, ref) or np.count_nonzero(got != ref) <= 2
